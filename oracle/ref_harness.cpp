@@ -1,0 +1,194 @@
+// TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// C-ABI harness around the UNMODIFIED reference library (NVTT 2.1.2, /root/reference), compiled by
+// oracle/build_ref.sh into oracle/_ref/libnvtt_ref.so.  It only *calls* the reference's public API
+// (src/nvtt/nvtt.h) — no reference source is copied here.  The tests use it (1) to pin the plain-C
+// restatement in oracle/*.c and (2) as the checker for the CUDA path; bench.py uses it as the
+// `--impl reference` arm / cpu_baseline ("kind": "reference").
+#include <nvtt/nvtt.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+
+using namespace nvtt;
+
+namespace {
+struct MemHandler : public OutputHandler {
+    std::vector<unsigned char> buf;
+    int images = 0;
+    virtual void beginImage(int, int, int, int, int, int) { images++; }
+    virtual bool writeData(const void *data, int size) {
+        const unsigned char *p = (const unsigned char *)data;
+        buf.insert(buf.end(), p, p + size);
+        return true;
+    }
+    virtual void endImage() {}
+};
+struct ErrCount : public ErrorHandler {
+    int n = 0, last = -1;
+    virtual void error(Error e) { n++; last = (int)e; }
+};
+
+struct SeqDispatcher : public TaskDispatcher {
+    virtual void dispatch(Task *task, void *context, int count) {
+        for (int i = 0; i < count; i++) task(context, i);
+    }
+};
+
+void setup_co(CompressionOptions &co, int format, int quality, const float *cw, int pixelType) {
+    co.setFormat((Format)format);
+    co.setQuality((Quality)quality);
+    if (cw) co.setColorWeights(cw[0], cw[1], cw[2], cw[3]);
+    co.setPixelType((PixelType)pixelType);
+}
+}  // namespace
+
+extern "C" {
+
+// One mip level through Compressor::compress(w,h,d,face,mip,rgba,...) (src/nvtt/Context.cpp:187-190,486-516).
+// planar fp32 RGBA [c][y][x].  threads: 0 = reference default (nvthread pool), 1 = sequential dispatcher.
+// alphaMode != None goes through the Surface API so that the alpha mode reaches the compressor.
+// Returns bytes written (<= out_cap) or -1.
+long ref_compress_level(int format, int quality, int alphaMode, int w, int h, const float *rgba,
+                        const float *colorWeights4, int pixelType, int threads, unsigned char *out, long out_cap) {
+    Compressor ctx;
+    ctx.enableCudaAcceleration(false);
+    SeqDispatcher seq;
+    if (threads == 1) ctx.setTaskDispatcher(&seq);
+    CompressionOptions co;
+    setup_co(co, format, quality, colorWeights4, pixelType);
+    OutputOptions oo;
+    MemHandler mh;
+    ErrCount eh;
+    oo.setOutputHandler(&mh);
+    oo.setErrorHandler(&eh);
+    oo.setOutputHeader(false);
+    bool ok;
+    if (alphaMode == 0) {
+        ok = ctx.compress(w, h, 1, 0, 0, rgba, co, oo);
+    } else {
+        Surface s;
+        s.setAlphaMode((AlphaMode)alphaMode);
+        // RGBA_32F input is interleaved; re-interleave from planar.
+        std::vector<float> il((size_t)w * h * 4);
+        for (size_t i = 0; i < (size_t)w * h; i++)
+            for (int c = 0; c < 4; c++) il[i * 4 + c] = rgba[(size_t)c * w * h + i];
+        s.setImage(InputFormat_RGBA_32F, w, h, 1, il.data());
+        ok = ctx.compress(s, 0, 0, co, oo);
+    }
+    if (!ok || eh.n) return -1;
+    if ((long)mh.buf.size() > out_cap) return -2;
+    memcpy(out, mh.buf.data(), mh.buf.size());
+    return (long)mh.buf.size();
+}
+
+struct RefProcessDesc {
+    int inputFormat;     // nvtt::InputFormat
+    int textureType;     // nvtt::TextureType
+    int width, height, faces;
+    int wrapMode;        // nvtt::WrapMode
+    int mipmapFilter;    // nvtt::MipmapFilter
+    int generateMipmaps; // bool
+    int maxLevel;        // -1 = all
+    float kaiserWidth, kaiserAlpha, kaiserStretch;
+    float inputGamma, outputGamma;
+    int isNormalMap, convertToNormalMap, normalizeMipmaps;
+    int alphaMode;
+    int format, quality, pixelType;
+    float colorWeights[4];
+    int outputHeader;    // bool
+    int container;       // nvtt::Container
+    int threads;         // 0 default pool, 1 sequential
+};
+
+// Whole InputOptions pipeline: Compressor::process (src/nvtt/Context.cpp:117-120,217-346).
+// images[f] = level-0 data of face f in `inputFormat`.  Returns total bytes (header + every level).
+long ref_process(const RefProcessDesc *d, const void *const *images, unsigned char *out, long out_cap) {
+    InputOptions io;
+    io.setTextureLayout((TextureType)d->textureType, d->width, d->height, 1, d->textureType == TextureType_Array ? d->faces : 1);
+    io.setFormat((InputFormat)d->inputFormat);
+    for (int f = 0; f < d->faces; f++) io.setMipmapData(images[f], d->width, d->height, 1, f, 0);
+    io.setWrapMode((WrapMode)d->wrapMode);
+    io.setMipmapFilter((MipmapFilter)d->mipmapFilter);
+    io.setMipmapGeneration(d->generateMipmaps != 0, d->maxLevel);
+    io.setKaiserParameters(d->kaiserWidth, d->kaiserAlpha, d->kaiserStretch);
+    io.setGamma(d->inputGamma, d->outputGamma);
+    io.setNormalMap(d->isNormalMap != 0);
+    io.setConvertToNormalMap(d->convertToNormalMap != 0);
+    io.setNormalizeMipmaps(d->normalizeMipmaps != 0);
+    io.setAlphaMode((AlphaMode)d->alphaMode);
+    CompressionOptions co;
+    setup_co(co, d->format, d->quality, d->colorWeights, d->pixelType);
+    OutputOptions oo;
+    MemHandler mh;
+    ErrCount eh;
+    oo.setOutputHandler(&mh);
+    oo.setErrorHandler(&eh);
+    oo.setOutputHeader(d->outputHeader != 0);
+    oo.setContainer((Container)d->container);
+    Compressor ctx;
+    ctx.enableCudaAcceleration(false);
+    SeqDispatcher seq;
+    if (d->threads == 1) ctx.setTaskDispatcher(&seq);
+    if (!ctx.process(io, co, oo)) return -1;
+    if (eh.n) return -1;
+    if (out == NULL) return (long)mh.buf.size();
+    if ((long)mh.buf.size() > out_cap) return -2;
+    memcpy(out, mh.buf.data(), mh.buf.size());
+    return (long)mh.buf.size();
+}
+
+// ---- Surface ("imperative") API, handle based (src/nvtt/Surface.cpp) ----
+void *ref_surf_create(int wrapMode, int alphaMode, int isNormalMap) {
+    Surface *s = new Surface();
+    s->setWrapMode((WrapMode)wrapMode);
+    s->setAlphaMode((AlphaMode)alphaMode);
+    s->setNormalMap(isNormalMap != 0);
+    return s;
+}
+void ref_surf_destroy(void *h) { delete (Surface *)h; }
+int ref_surf_set_image(void *h, int inputFormat, int w, int ht, const void *data) {
+    return ((Surface *)h)->setImage((InputFormat)inputFormat, w, ht, 1, data) ? 1 : 0;
+}
+int ref_surf_width(void *h) { return ((Surface *)h)->width(); }
+int ref_surf_height(void *h) { return ((Surface *)h)->height(); }
+// copies planar fp32 RGBA (4*w*h floats)
+void ref_surf_get(void *h, float *out) {
+    Surface *s = (Surface *)h;
+    memcpy(out, s->data(), sizeof(float) * 4 * (size_t)s->width() * s->height() * s->depth());
+}
+void ref_surf_to_linear(void *h, float g) { ((Surface *)h)->toLinear(g); }
+void ref_surf_to_gamma(void *h, float g) { ((Surface *)h)->toGamma(g); }
+int ref_surf_build_next_mipmap(void *h, int filter, int useParams, float filterWidth, float p0, float p1) {
+    Surface *s = (Surface *)h;
+    if (useParams) {
+        float params[2] = {p0, p1};
+        return s->buildNextMipmap((MipmapFilter)filter, filterWidth, params) ? 1 : 0;
+    }
+    return s->buildNextMipmap((MipmapFilter)filter) ? 1 : 0;
+}
+void ref_surf_resize(void *h, int w, int ht, int filter, int useParams, float filterWidth, float p0, float p1) {
+    Surface *s = (Surface *)h;
+    if (useParams) {
+        float params[2] = {p0, p1};
+        s->resize(w, ht, 1, (ResizeFilter)filter, filterWidth, params);
+    } else {
+        s->resize(w, ht, 1, (ResizeFilter)filter);
+    }
+}
+void ref_surf_expand_normals(void *h) { ((Surface *)h)->expandNormals(); }
+void ref_surf_pack_normals(void *h) { ((Surface *)h)->packNormals(); }
+void ref_surf_normalize_normal_map(void *h) { ((Surface *)h)->normalizeNormalMap(); }
+void ref_surf_to_grey_scale(void *h, float r, float g, float b, float a) { ((Surface *)h)->toGreyScale(r, g, b, a); }
+void ref_surf_to_normal_map(void *h, float sm, float md, float bg, float lg) { ((Surface *)h)->toNormalMap(sm, md, bg, lg); }
+
+// Decode a BCn level with the reference decoder (Surface::setImage2D, src/nvtt/Surface.cpp:908-1118) -> planar fp32.
+int ref_decode(int format, int w, int h, const void *data, float *out) {
+    Surface s;
+    if (!s.setImage2D((Format)format, Decoder_D3D10, w, h, data)) return 0;
+    memcpy(out, s.data(), sizeof(float) * 4 * (size_t)w * h);
+    return 1;
+}
+
+int ref_version() { return (int)nvtt::version(); }
+}
