@@ -1,0 +1,164 @@
+// Host-side (plain C++) builders for the small lookup tables the kernels consume.  Everything here is computed
+// from the published formulae, not copied from the reference's generated tables.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace nvb {
+
+// ---- gamma 2.2 exponent tables: table[k] = float(2^((k-127)*p/q)), k = sign|exponent bits ------------------
+// src/nvmath/Gamma.cpp:33-300 lists the same numbers; entries with the sign bit set are 0, k=0 (zero/denormal)
+// is 0 and k=255 (inf/NaN) is +inf.
+inline void build_gamma_tables(float to_gamma[512], float to_linear[512]) {
+    for (int k = 0; k < 512; k++) {
+        to_gamma[k] = 0.0f;
+        to_linear[k] = 0.0f;
+    }
+    for (int k = 1; k < 255; k++) {
+        const double e = (double)(k - 127);
+        to_gamma[k] = (float)pow(2.0, e * 5.0 / 11.0);
+        to_linear[k] = (float)pow(2.0, e * 11.0 / 5.0);  // underflows to 0 / overflows to +inf at the ends
+    }
+    to_gamma[255] = INFINITY;
+    to_linear[255] = INFINITY;
+}
+
+// ---- squish cluster splits (src/nvtt/squish/weightedclusterfit.cpp:496-553 loop nest, flattened) -----------
+// For a colour set of n points: all (c0,c1,c2) with c0+c1+c2 <= n in lexicographic order, packed c0|c1<<5|c2<<10.
+inline void build_squish_splits(std::vector<uint16_t> &cand, int off[18]) {
+    cand.clear();
+    off[0] = 0;
+    for (int n = 1; n <= 16; n++) {
+        off[n] = (int)cand.size();
+        for (int c0 = 0; c0 <= n; c0++)
+            for (int c1 = 0; c1 <= n - c0; c1++)
+                for (int c2 = 0; c2 <= n - c0 - c1; c2++) cand.push_back((uint16_t)(c0 | (c1 << 5) | (c2 << 10)));
+    }
+    off[17] = (int)cand.size();
+}
+
+// ---- single-colour endpoint match tables (src/nvtt/SingleColorLookup.cpp:34-89, non-alpha mode) ------------
+// For every 8-bit value find (max,min) 5/6-bit endpoints whose 2/3-1/3 interpolant is closest, with a small
+// penalty on the endpoint distance; first best in (min,max) scan order wins.
+inline void build_omatch(uint8_t *table /*[256][2]*/, int size) {
+    std::vector<int> expand(size);
+    for (int i = 0; i < size; i++) expand[i] = (size == 32) ? ((i << 3) | (i >> 2)) : ((i << 2) | (i >> 4));
+    for (int i = 0; i < 256; i++) {
+        int bestErr = 256 * 100;
+        for (int mn = 0; mn < size; mn++) {
+            for (int mx = 0; mx < size; mx++) {
+                const int mine = expand[mn], maxe = expand[mx];
+                int err = abs((maxe * 2 + mine) / 3 - i) * 100;
+                err += abs(mx - mn) * 3;
+                if (err < bestErr) {
+                    table[i * 2 + 0] = (uint8_t)mx;
+                    table[i * 2 + 1] = (uint8_t)mn;
+                    bestErr = err;
+                }
+            }
+        }
+    }
+}
+
+// ---- polyphase kernels (src/nvimage/Filter.cpp:115-131,157-271,563-608) ------------------------------------
+enum FilterKind { Filter_Box = 0, Filter_Triangle = 1, Filter_Kaiser = 2, Filter_Mitchell = 3 };
+
+struct FilterDesc {
+    int kind;
+    float width;
+    float p0, p1;  // Kaiser: alpha, stretch.  Mitchell: B, C.
+};
+
+inline float filt_sincf(const float x) {
+    if (fabs(x) < 0.0001f) return 1.0f + x * x * (-1.0f / 6.0f + x * x * 1.0f / 120.0f);
+    return sinf(x) / x;
+}
+inline float filt_bessel0(float x) {
+    const float EPSILON_RATIO = 1e-6f;
+    float xh = 0.5f * x, sum = 1.0f, pw = 1.0f, ds = 1.0;
+    int k = 0;
+    while (ds > sum * EPSILON_RATIO) {
+        ++k;
+        pw = pw * (xh / k);
+        ds = pw * pw;
+        sum = sum + ds;
+    }
+    return sum;
+}
+inline float filter_eval(const FilterDesc &f, float x) {
+    switch (f.kind) {
+    case Filter_Box:
+        return (fabsf(x) <= f.width) ? 1.0f : 0.0f;
+    case Filter_Triangle:
+        x = fabsf(x);
+        return (x < f.width) ? f.width - x : 0.0f;
+    case Filter_Kaiser: {
+        const float PI_F = 3.14159265358979323846f;
+        const float sinc_value = filt_sincf(PI_F * x * f.p1);
+        const float t = x / f.width;
+        if ((1 - t * t) >= 0) return sinc_value * filt_bessel0(f.p0 * sqrtf(1 - t * t)) / filt_bessel0(f.p0);
+        return 0;
+    }
+    default: {  // Mitchell
+        const float b = f.p0, c = f.p1;
+        const float p0 = (6.0f - 2.0f * b) / 6.0f;
+        const float p2 = (-18.0f + 12.0f * b + 6.0f * c) / 6.0f;
+        const float p3 = (12.0f - 9.0f * b - 6.0f * c) / 6.0f;
+        const float q0 = (8.0f * b + 24.0f * c) / 6.0f;
+        const float q1 = (-12.0f * b - 48.0f * c) / 6.0f;
+        const float q2 = (6.0f * b + 30.0f * c) / 6.0f;
+        const float q3 = (-b - 6.0f * c) / 6.0f;
+        x = fabsf(x);
+        if (x < 1.0f) return p0 + x * x * (p2 + x * p3);
+        if (x < 2.0f) return q0 + x * (q1 + x * (q2 + x * q3));
+        return 0.0f;
+    }
+    }
+}
+inline float filter_sample_box(const FilterDesc &f, float x, float scale, int samples) {
+    double sum = 0;
+    const float isamples = 1.0f / float(samples);
+    for (int s = 0; s < samples; s++) {
+        const float p = (x + (float(s) + 0.5f) * isamples) * scale;
+        sum += filter_eval(f, p);
+    }
+    return float(sum * isamples);
+}
+
+struct PolyphaseTable {
+    int length = 0, window = 0;
+    float width = 0;
+    std::vector<float> weights;  // [length][window], each row normalised
+    std::vector<int> left;       // [length]
+};
+
+inline void build_polyphase(const FilterDesc &f, unsigned srcLength, unsigned dstLength, PolyphaseTable &t) {
+    int samples = 32;
+    float scale = float(dstLength) / float(srcLength);
+    const float iscale = 1.0f / scale;
+    if (scale > 1) {
+        samples = 1;
+        scale = 1;
+    }
+    t.length = (int)dstLength;
+    t.width = f.width * iscale;
+    t.window = (int)ceilf(t.width * 2) + 1;
+    t.weights.assign((size_t)t.window * t.length, 0.0f);
+    t.left.assign(t.length, 0);
+    for (int i = 0; i < t.length; i++) {
+        const float center = (0.5f + i) * iscale;
+        const int left = (int)floorf(center - t.width);
+        t.left[i] = left;
+        float total = 0.0f;
+        for (int j = 0; j < t.window; j++) {
+            const float sample = filter_sample_box(f, left + j - center, scale, samples);
+            t.weights[(size_t)i * t.window + j] = sample;
+            total += sample;
+        }
+        for (int j = 0; j < t.window; j++) t.weights[(size_t)i * t.window + j] /= total;
+    }
+}
+
+}  // namespace nvb

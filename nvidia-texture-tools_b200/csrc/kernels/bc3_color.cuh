@@ -1,0 +1,283 @@
+// BC2/BC3 colour block encoder: nvsquish weighted cluster fit (4-colour mode), 16 lanes per 4x4 block.
+//
+// Replaces, bit-exactly (intended semantics = the -O0/-O2 behaviour of the reference):
+//   CompressorDXT5::compressBlock (colour part)       src/nvtt/CompressorDX9.cpp:160-175
+//   ColorBlock::init(w,h,float*,x,y) / isSingleColor  src/nvimage/ColorBlock.cpp:80-110,136-149
+//   nvsquish::ColourSet::ColourSet (minimal set)      src/nvtt/squish/colourset.cpp:35-139
+//   ComputeWeightedCovariance / ComputePrincipleComponent (scalar)   src/nvtt/squish/maths.cpp:32-133
+//   WeightedClusterFit::SetColourSet / Compress4 (scalar)            src/nvtt/squish/weightedclusterfit.cpp:39-105,476-589
+//   WriteColourBlock4 / FloatTo565                    src/nvtt/squish/colourblock.cpp:30-53,108-138
+//   OptimalCompress::compressDXT1(Color32)            src/nvtt/OptimalCompressDXT.cpp:254-269
+//
+// Mapping: a half-warp owns one block, one lane per texel.  Texel de-duplication uses shuffles; the sequential
+// fp32 reductions whose order matters (centroid, covariance, power iteration, xsum) are evaluated redundantly
+// by every lane from shared memory (broadcast reads) in the reference's order; the <= 969 cluster splits
+// (c0,c1,c2) are striped over the 16 lanes, each split reading three running sums from a per-block table
+// T[start][len] that is accumulated in exactly the order of the reference's nested loops; the winner is the
+// minimum error with the lowest split number (== first strict minimum of the sequential search).
+#pragma once
+#include "../nvb_common.cuh"
+
+namespace nvb {
+
+struct Bc3ColorParams {
+    LevelView lv;
+    unsigned char *out;     // BCn level
+    int out_stride;         // bytes between blocks (16 for BC2/BC3)
+    int out_offset;         // byte offset of the colour block inside a block (8)
+    float metric[3];        // CompressionOptions colour weights
+    int weight_by_alpha;    // AlphaMode_Transparency => kWeightColourByAlpha
+    const unsigned short *cand;  // packed (c0 | c1<<5 | c2<<10) splits, all counts concatenated
+    const int *cand_off;    // cand_off[n] .. cand_off[n+1] = splits for a set of n points (n = 1..16), 18 ints
+    const unsigned char *omatch5;  // [256][2]
+    const unsigned char *omatch6;  // [256][2]
+};
+
+#define NVB_BC3_GROUPS 8  // 4x4 blocks per CTA (128 threads)
+
+struct Bc3GroupSmem {
+    float4 pts[16];      // de-duplicated points (x=R,y=G,z=B in [0,1], w=weight)
+    float4 sorted[16];   // weighted points in principal-axis order (w*x, w*y, w*z, w)
+    float4 T[154];       // running sums: T[off(start)+len] = sum_{k<len} sorted[start+k]
+    int rank[16];        // point -> position in the sorted order
+};
+
+NVB_DEV int squish_float_to_int(float a, int limit) {
+    int i = x86_ftoi(a + 0.5f);
+    if (i < 0) i = 0;
+    else if (i > limit) i = limit;
+    return i;
+}
+
+struct SquishSplit {
+    float ax, ay, az, bx, by, bz, error;
+};
+
+NVB_DEV SquishSplit squish_eval_split(const float4 *T, int n, int c0, int c1, int c2, float4 xsum, float mx, float my, float mz) {
+    // rows of T start at off(s) = s*(n+1) - s*(s-1)/2
+    const int s1 = c0, s2 = c0 + c1;
+    const float4 x0 = T[c0];
+    const float4 x1 = T[s1 * (n + 1) - ((s1 * (s1 - 1)) >> 1) + c1];
+    const float4 x2 = T[s2 * (n + 1) - ((s2 * (s2 - 1)) >> 1) + c2];
+    const float w0 = x0.w, w1 = x1.w, w2 = x2.w;
+    const float w3 = xsum.w - w0 - w1 - w2;
+    const float alpha2_sum = w0 + w1 * (4.0f / 9.0f) + w2 * (1.0f / 9.0f);
+    const float beta2_sum = w3 + w2 * (4.0f / 9.0f) + w1 * (1.0f / 9.0f);
+    const float alphabeta_sum = (w1 + w2) * (2.0f / 9.0f);
+    const float factor = 1.0f / (alpha2_sum * beta2_sum - alphabeta_sum * alphabeta_sum);
+    SquishSplit r;
+    float e[3];
+    const float X0[3] = {x0.x, x0.y, x0.z}, X1[3] = {x1.x, x1.y, x1.z}, X2[3] = {x2.x, x2.y, x2.z};
+    const float XS[3] = {xsum.x, xsum.y, xsum.z};
+    const float grid[3] = {31.0f, 63.0f, 31.0f};
+    const float gridrcp[3] = {1.0f / 31.0f, 1.0f / 63.0f, 1.0f / 31.0f};
+    float A[3], B[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float alphax_sum = X0[k] + X1[k] * (2.0f / 3.0f) + X2[k] * (1.0f / 3.0f);
+        const float betax_sum = XS[k] - alphax_sum;
+        float a = (alphax_sum * beta2_sum - betax_sum * alphabeta_sum) * factor;
+        float b = (betax_sum * alpha2_sum - alphax_sum * alphabeta_sum) * factor;
+        a = std_min(1.0f, std_max(0.0f, a));
+        b = std_min(1.0f, std_max(0.0f, b));
+        a = floorf(grid[k] * a + 0.5f) * gridrcp[k];
+        b = floorf(grid[k] * b + 0.5f) * gridrcp[k];
+        e[k] = a * a * alpha2_sum + b * b * beta2_sum + 2.0f * (a * b * alphabeta_sum - a * alphax_sum - b * betax_sum);
+        A[k] = a;
+        B[k] = b;
+    }
+    r.error = e[0] * mx + e[1] * my + e[2] * mz;
+    r.ax = A[0]; r.ay = A[1]; r.az = A[2];
+    r.bx = B[0]; r.by = B[1]; r.bz = B[2];
+    return r;
+}
+
+__global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParams P) {
+    __shared__ Bc3GroupSmem smem[NVB_BC3_GROUPS];
+    const int grp = threadIdx.x >> 4;
+    const int l = threadIdx.x & 15;
+    const int nblocks = P.lv.bw * P.lv.bh;
+    const int blk = blockIdx.x * NVB_BC3_GROUPS + grp;
+    if (blk >= nblocks) return;  // whole half-warp leaves together; only half-warp-scoped syncs follow
+    const unsigned gm = 0xFFFFu << (threadIdx.x & 16);
+    Bc3GroupSmem &S = smem[grp];
+
+    // ---- gather + quantise my texel (ColorBlock::init: truncation, partial blocks repeat by modulo) ----
+    const int bx = blk % P.lv.bw, by = blk / P.lv.bw;
+    const int tw = min(P.lv.w - bx * 4, 4), th = min(P.lv.h - by * 4, 4);
+    const int px = bx * 4 + (l & 3) % tw, py = by * 4 + (l >> 2) % th;
+    const unsigned r8 = quantize_u8_trunc(load_texel(P.lv, 0, px, py));
+    const unsigned g8 = quantize_u8_trunc(load_texel(P.lv, 1, px, py));
+    const unsigned b8 = quantize_u8_trunc(load_texel(P.lv, 2, px, py));
+    float walpha = 1.0f;
+    if (P.weight_by_alpha) {
+        const unsigned a8 = quantize_u8_trunc(load_texel(P.lv, 3, px, py));
+        walpha = (float)(a8 + 1) / 256.0f;
+    }
+    const unsigned key = (r8 << 16) | (g8 << 8) | b8;
+
+    // ---- minimal colour set: first occurrence keeps the point, duplicates add their weight in texel order ----
+    unsigned match = 0;
+    float weight = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const unsigned kj = __shfl_sync(gm, key, j, 16);
+        const float wj = __shfl_sync(gm, walpha, j, 16);
+        if (kj == key) {
+            weight = (match == 0) ? wj : weight + wj;
+            match |= 1u << j;
+        }
+    }
+    const int first = __ffs((int)match) - 1;
+    const unsigned uniq = (__ballot_sync(gm, first == l) >> (threadIdx.x & 16)) & 0xFFFFu;
+    const int n = __popc(uniq);
+    const int myPoint = __popc(uniq & ((1u << first) - 1u));  // m_remap[l]
+
+    unsigned char *dst = P.out + (size_t)blk * P.out_stride + P.out_offset;
+
+    if (n == 1) {
+        // single colour: optimal endpoints from the match tables, all indices 2.
+        if (l == 0) {
+            unsigned c0 = ((unsigned)P.omatch5[r8 * 2 + 0] << 11) | ((unsigned)P.omatch6[g8 * 2 + 0] << 5) | P.omatch5[b8 * 2 + 0];
+            unsigned c1 = ((unsigned)P.omatch5[r8 * 2 + 1] << 11) | ((unsigned)P.omatch6[g8 * 2 + 1] << 5) | P.omatch5[b8 * 2 + 1];
+            unsigned indices = 0xaaaaaaaau;
+            if (c0 < c1) {
+                unsigned t = c0; c0 = c1; c1 = t;
+                indices ^= 0x55555555u;
+            }
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(c0 | (c1 << 16), indices);
+        }
+        return;
+    }
+
+    if (first == l) S.pts[myPoint] = make_float4((float)r8 / 255.0f, (float)g8 / 255.0f, (float)b8 / 255.0f, weight);
+    __syncwarp(gm);
+
+    // ---- weighted covariance about the weighted centroid (every lane, reference order) ----
+    const float mx = P.metric[0], my = P.metric[1], mz = P.metric[2];
+    float total = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const float4 p = S.pts[i];
+        total += p.w;
+        cx += p.w * p.x;
+        cy += p.w * p.y;
+        cz += p.w * p.z;
+    }
+    {
+        const float t = 1.0f / total;
+        cx *= t; cy *= t; cz *= t;
+    }
+    float cov0 = 0, cov1 = 0, cov2 = 0, cov3 = 0, cov4 = 0, cov5 = 0;
+    for (int i = 0; i < n; i++) {
+        const float4 p = S.pts[i];
+        const float ax = (p.x - cx) * mx, ay = (p.y - cy) * my, az = (p.z - cz) * mz;
+        const float bxv = p.w * ax, byv = p.w * ay, bzv = p.w * az;
+        cov0 += ax * bxv;
+        cov1 += ax * byv;
+        cov2 += ax * bzv;
+        cov3 += ay * byv;
+        cov4 += ay * bzv;
+        cov5 += az * bzv;
+    }
+    // ---- principal axis: best row estimate + 8 power iterations normalised by the max component ----
+    float vx, vy, vz;
+    {
+        const float r0 = cov0 * cov0 + cov1 * cov1 + cov2 * cov2;
+        const float r1 = cov1 * cov1 + cov3 * cov3 + cov4 * cov4;
+        const float r2 = cov2 * cov2 + cov4 * cov4 + cov5 * cov5;
+        if (r0 > r1 && r0 > r2) { vx = cov0; vy = cov1; vz = cov2; }
+        else if (r1 > r2) { vx = cov1; vy = cov3; vz = cov4; }
+        else { vx = cov2; vy = cov4; vz = cov5; }
+        for (int it = 0; it < 8; it++) {
+            const float x = vx * cov0 + vy * cov1 + vz * cov2;
+            const float y = vx * cov1 + vy * cov3 + vz * cov4;
+            const float z = vx * cov2 + vy * cov4 + vz * cov5;
+            const float norm = std_max(std_max(x, y), z);
+            const float iv = 1.0f / norm;
+            if (norm == 0.0f) { vx = 0.0f; vy = 0.0f; vz = 0.0f; break; }
+            vx = x * iv; vy = y * iv; vz = z * iv;
+        }
+    }
+    // ---- order the points along the axis: stable ascending sort == rank by (dps, index) ----
+    float dps = 0.0f;
+    if (l < n) {
+        const float4 p = S.pts[l];
+        dps = p.x * vx + p.y * vy + p.z * vz;
+    }
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float dj = __shfl_sync(gm, dps, j, 16);
+        if (j < n && (dj < dps || (dj == dps && j < l))) rank++;
+    }
+    if (l < n) {
+        const float4 p = S.pts[l];
+        S.sorted[rank] = make_float4(p.w * p.x, p.w * p.y, p.w * p.z, p.w);
+        S.rank[l] = rank;
+    }
+    __syncwarp(gm);
+    float4 xsum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int i = 0; i < n; i++) {
+        const float4 s = S.sorted[i];
+        xsum.x += s.x; xsum.y += s.y; xsum.z += s.z; xsum.w += s.w;
+    }
+    // ---- running-sum table, row `start` accumulated front to back like the loop-carried x0/x1/x2 ----
+    for (int start = l; start <= n; start += 16) {
+        const int off = start * (n + 1) - ((start * (start - 1)) >> 1);
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        S.T[off] = acc;
+        for (int k = 0; start + k < n; k++) {
+            const float4 s = S.sorted[start + k];
+            acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+            S.T[off + k + 1] = acc;
+        }
+    }
+    __syncwarp(gm);
+
+    // ---- all cluster splits, striped over the 16 lanes ----
+    const float mqx = mx * mx, mqy = my * my, mqz = mz * mz;
+    const int cbeg = P.cand_off[n], ncand = P.cand_off[n + 1] - cbeg;
+    float besterror = FLT_MAX;
+    int bestci = 0x7fffffff;
+    for (int ci = l; ci < ncand; ci += 16) {
+        const unsigned pk = __ldg(P.cand + cbeg + ci);
+        const SquishSplit s = squish_eval_split(S.T, n, pk & 31, (pk >> 5) & 31, (pk >> 10) & 31, xsum, mqx, mqy, mqz);
+        if (s.error < besterror) {
+            besterror = s.error;
+            bestci = ci;
+        }
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {
+        const float oe = __shfl_xor_sync(gm, besterror, d, 16);
+        const int oc = __shfl_xor_sync(gm, bestci, d, 16);
+        if (oe < besterror || (oe == besterror && oc < bestci)) {
+            besterror = oe;
+            bestci = oc;
+        }
+    }
+    unsigned c565a = 0, c565b = 0, idx = 0;
+    if (bestci != 0x7fffffff) {
+        const unsigned pk = __ldg(P.cand + cbeg + bestci);
+        const int b0 = pk & 31, b1 = (pk >> 5) & 31, b2 = (pk >> 10) & 31;
+        const SquishSplit s = squish_eval_split(S.T, n, b0, b1, b2, xsum, mqx, mqy, mqz);
+        const int pos = S.rank[myPoint];
+        idx = (pos < b0) ? 0u : (pos < b0 + b1) ? 2u : (pos < b0 + b1 + b2) ? 3u : 1u;
+        c565a = ((unsigned)squish_float_to_int(31.0f * s.ax, 31) << 11) | ((unsigned)squish_float_to_int(63.0f * s.ay, 63) << 5) |
+                (unsigned)squish_float_to_int(31.0f * s.az, 31);
+        c565b = ((unsigned)squish_float_to_int(31.0f * s.bx, 31) << 11) | ((unsigned)squish_float_to_int(63.0f * s.by, 63) << 5) |
+                (unsigned)squish_float_to_int(31.0f * s.bz, 31);
+        if (c565a < c565b) {
+            const unsigned t = c565a; c565a = c565b; c565b = t;
+            idx = (idx ^ 1u) & 3u;
+        } else if (c565a == c565b) {
+            idx = 0;
+        }
+    }
+    unsigned bits = idx << (2 * l);
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) bits |= __shfl_xor_sync(gm, bits, d, 16);
+    if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(c565a | (c565b << 16), bits);
+}
+
+}  // namespace nvb

@@ -1,0 +1,190 @@
+// BC4 / BC5 / BC3-alpha block encoders (the "DXT5 alpha block": two 8-bit endpoints + 16 x 3-bit indices).
+//
+// Replaces, bit-exactly:
+//   QuickCompress::compressDXT5A            src/nvtt/QuickCompressDXT.cpp:779-821  (Fastest, Normal)
+//     computeAlphaIndices                   src/nvtt/QuickCompressDXT.cpp:505-536
+//     optimizeAlpha8                        src/nvtt/QuickCompressDXT.cpp:538-592
+//     sameIndices                           src/nvtt/QuickCompressDXT.cpp:643-647
+//   AlphaBlockDXT5::evaluatePalette8/6      src/nvimage/BlockDXT.cpp:336-378, layout BlockDXT.h:123-162
+//   FastCompressorBC4/BC5::compressBlock    src/nvtt/CompressorDX10.cpp:42-62
+//
+// One thread per channel-block: the work is ~2k integer/fp32 ops per block, i.e. the kernel is HBM-bound
+// (16 B/px read for BC5 from the planar fp32 level, 1 B/px written).
+#pragma once
+#include "../nvb_common.cuh"
+
+namespace nvb {
+
+// 8-entry palette of an alpha block (D3D10 rounding, bias 0).
+NVB_DEV void alpha_palette(unsigned a0, unsigned a1, unsigned pal[8]) {
+    pal[0] = a0;
+    pal[1] = a1;
+    if (a0 > a1) {
+        pal[2] = (6 * a0 + 1 * a1) / 7;
+        pal[3] = (5 * a0 + 2 * a1) / 7;
+        pal[4] = (4 * a0 + 3 * a1) / 7;
+        pal[5] = (3 * a0 + 4 * a1) / 7;
+        pal[6] = (2 * a0 + 5 * a1) / 7;
+        pal[7] = (1 * a0 + 6 * a1) / 7;
+    } else {
+        pal[2] = (4 * a0 + 1 * a1) / 5;
+        pal[3] = (3 * a0 + 2 * a1) / 5;
+        pal[4] = (2 * a0 + 3 * a1) / 5;
+        pal[5] = (1 * a0 + 4 * a1) / 5;
+        pal[6] = 0x00;
+        pal[7] = 0xFF;
+    }
+}
+
+// Exhaustive nearest-palette-entry search; first minimum wins (strict <).  Returns the summed squared error and
+// writes the 16 3-bit indices into bits [16,64) of *blk (bits [0,16) = endpoints are left untouched).
+NVB_DEV unsigned alpha_compute_indices(const unsigned src[16], unsigned a0, unsigned a1, unsigned long long *blk) {
+    unsigned pal[8];
+    alpha_palette(a0, a1, pal);
+    unsigned total = 0;
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        int alpha = (int)src[i];
+        unsigned besterror = 256 * 256;
+        unsigned best = 8;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            int d = (int)pal[p] - alpha;
+            unsigned error = (unsigned)(d * d);
+            if (error < besterror) {
+                besterror = error;
+                best = p;
+            }
+        }
+        total += besterror;
+        bits |= (unsigned long long)(best & 7) << (3 * i);
+    }
+    *blk = (*blk & 0xFFFFull) | (bits << 16);
+    return total;
+}
+
+// Least-squares endpoint refit for the current indices (always with the 8-step weights, also when the block is
+// in 6-step mode — that is what the reference does).
+NVB_DEV void alpha_optimize8(const unsigned src[16], unsigned long long *blk) {
+    float alpha2_sum = 0, beta2_sum = 0, alphabeta_sum = 0, alphax_sum = 0, betax_sum = 0;
+    unsigned long long bits = *blk >> 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned idx = (unsigned)(bits >> (3 * i)) & 7u;
+        float alpha;
+        if (idx < 2) alpha = 1.0f - (float)idx;
+        else alpha = (8.0f - (float)idx) / 7.0f;
+        float beta = 1 - alpha;
+        float x = (float)src[i];
+        alpha2_sum += alpha * alpha;
+        beta2_sum += beta * beta;
+        alphabeta_sum += alpha * beta;
+        alphax_sum += alpha * x;
+        betax_sum += beta * x;
+    }
+    const float factor = 1.0f / (alpha2_sum * beta2_sum - alphabeta_sum * alphabeta_sum);
+    float a = (alphax_sum * beta2_sum - betax_sum * alphabeta_sum) * factor;
+    float b = (betax_sum * alpha2_sum - alphax_sum * alphabeta_sum) * factor;
+    // uint(min(max(a, 0.0f), 255.0f)) with nv::min/max NaN semantics (NaN -> 0).
+    unsigned alpha0 = (unsigned)(int)nv_min(nv_max(a, 0.0f), 255.0f);
+    unsigned alpha1 = (unsigned)(int)nv_min(nv_max(b, 0.0f), 255.0f);
+    if (alpha0 < alpha1) {
+        unsigned t = alpha0;
+        alpha0 = alpha1;
+        alpha1 = t;
+        unsigned long long nb = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            unsigned idx = (unsigned)(bits >> (3 * i)) & 7u;
+            unsigned n = (idx < 2) ? (1 - idx) : (9 - idx);
+            nb |= (unsigned long long)(n & 7) << (3 * i);
+        }
+        bits = nb;
+    } else if (alpha0 == alpha1) {
+        bits = 0;
+    }
+    *blk = (bits << 16) | ((unsigned long long)alpha1 << 8) | alpha0;
+}
+
+// QuickCompress::compressDXT5A with iterationCount = 8.
+NVB_DEV unsigned long long alpha_quick_compress(const unsigned src[16]) {
+    unsigned amax = 0, amin = 255;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        amax = max(amax, src[i]);
+        amin = min(amin, src[i]);
+    }
+    // uint8 arithmetic promoted to int; results stored back into 8-bit fields.
+    unsigned a0 = (amax - (amax - amin) / 34) & 0xFF;
+    unsigned a1 = (amin + (amax - amin) / 34) & 0xFF;
+    unsigned long long block = ((unsigned long long)a1 << 8) | a0;
+    unsigned besterror = alpha_compute_indices(src, a0, a1, &block);
+    unsigned long long best = block;
+    for (int it = 0; it < 8; it++) {
+        alpha_optimize8(src, &block);
+        unsigned error = alpha_compute_indices(src, (unsigned)(block & 0xFF), (unsigned)((block >> 8) & 0xFF), &block);
+        if (error >= besterror) break;
+        if ((block >> 16) == (best >> 16)) {
+            best = block;
+            break;
+        }
+        besterror = error;
+        best = block;
+    }
+    return best;
+}
+
+// One thread per 4x4 block of one channel.  `channel` is the FloatImage plane (0=R,1=G,2=B,3=A): BC4 -> R,
+// BC5 -> R then G (second launch, out_offset 8), BC3 alpha -> A.  mode 0 = QuickCompress (Fastest/Normal).
+struct AlphaBlocksParams {
+    LevelView lv;
+    int channel;
+    unsigned char *out;
+    int out_stride;  // bytes between consecutive blocks in the output (8 for BC4, 16 for BC5/BC3)
+    int out_offset;  // byte offset of this alpha block inside the output block
+    int mode;        // 0 quick, 1 optimal (Production / Highest)
+};
+
+NVB_DEV void alpha_gather_block(const LevelView &lv, int channel, int bx, int by, unsigned src[16]) {
+    const int x0 = bx * 4, y0 = by * 4;
+    const float *plane = lv.data + (size_t)channel * lv.w * lv.h;
+    const bool gam = (lv.to_gamma_table != nullptr && channel < 3);
+    if (x0 + 4 <= lv.w && y0 + 4 <= lv.h && (lv.w & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 v = *reinterpret_cast<const float4 *>(plane + (size_t)(y0 + i) * lv.w + x0);
+            float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float f = t[e];
+                if (gam) f = nvb_powf_5_11(f, lv.to_gamma_table);
+                src[i * 4 + e] = quantize_u8_trunc(f);
+            }
+        }
+    } else {
+        const int tw = min(lv.w - x0, 4), th = min(lv.h - y0, 4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float f = plane[(size_t)(y0 + i % th) * lv.w + x0 + e % tw];
+                if (gam) f = nvb_powf_5_11(f, lv.to_gamma_table);
+                src[i * 4 + e] = quantize_u8_trunc(f);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_alpha_blocks(AlphaBlocksParams P) {
+    const int nblocks = P.lv.bw * P.lv.bh;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += gridDim.x * blockDim.x) {
+        unsigned src[16];
+        alpha_gather_block(P.lv, P.channel, blk % P.lv.bw, blk / P.lv.bw, src);
+        unsigned long long b = alpha_quick_compress(src);
+        *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+            make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
+    }
+}
+
+}  // namespace nvb

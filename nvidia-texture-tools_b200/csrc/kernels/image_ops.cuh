@@ -1,0 +1,287 @@
+// Image-op kernels of the mip chain: input conversion, gamma, box / polyphase down-sampling, normal-map
+// renormalisation.  All are HBM-bound streaming kernels over planar fp32 [c][y][x]; arithmetic follows the
+// reference operation-for-operation (no FMA contraction, same summation order) so results are bit-identical.
+//
+// Replaces:
+//   Surface::setImage (BGRA8 / RGBA16F / RGBA32F / R32F)   src/nvtt/Surface.cpp:728-815
+//   half_to_float                                          src/nvmath/Half.cpp:443-498
+//   FloatImage::toLinear / toGamma / exponentiate          src/nvimage/FloatImage.cpp:259-298 (Gamma.cpp:311-354)
+//   FloatImage::fastDownSample                             src/nvimage/FloatImage.cpp:559-737
+//   FloatImage::applyKernelX / applyKernelY                src/nvimage/FloatImage.cpp:1115-1176 (wrap: FloatImage.h:298-351)
+//   FloatImage::scaleBias / normalize                      src/nvimage/FloatImage.cpp:201-242
+#pragma once
+#include "../nvb_common.cuh"
+
+namespace nvb {
+
+// ---------------------------------------------------------------------------------------------------------
+// Input conversion (+ optional fused toLinear on R,G,B).
+// ---------------------------------------------------------------------------------------------------------
+NVB_DEV float half_bits_to_float(unsigned h) {
+    const unsigned s = (h & 0x8000u) << 16;
+    const unsigned e = (h >> 10) & 0x1Fu;
+    const unsigned m = h & 0x3FFu;
+    unsigned r;
+    if (e == 0) {
+        if (m == 0) r = 0;
+        else {
+            // denormal half: normalise
+            const int nlz = __clz((int)m) - 21;  // leading zeros within the 11-bit field (1..10)
+            const unsigned mm = (m << nlz) & 0x3FFu;
+            r = ((unsigned)(113 - nlz) << 23) | (mm << 13);
+        }
+    } else if (e == 31) {
+        r = 0x7F800000u | (m << 13);
+    } else {
+        r = ((e + 112u) << 23) | (m << 13);
+    }
+    return __uint_as_float(s | r);
+}
+
+struct SetImageParams {
+    const void *src;  // interleaved input texels
+    float *dst;       // planar fp32 RGBA
+    int count;        // pixels
+    int format;       // nvtt::InputFormat: 0 BGRA_8UB, 1 RGBA_16F, 2 RGBA_32F, 3 R_32F
+    const float *to_linear_table;  // non-null => fused Surface::toLinear(2.2) on R,G,B
+};
+
+__global__ void __launch_bounds__(256) k_set_image(SetImageParams P) {
+    const size_t n = (size_t)P.count;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float r, g, b, a;
+        if (P.format == 0) {
+            const uchar4 c = reinterpret_cast<const uchar4 *>(P.src)[i];  // memory order B,G,R,A (Color32)
+            r = (float)c.z / 255.0f;
+            g = (float)c.y / 255.0f;
+            b = (float)c.x / 255.0f;
+            a = (float)c.w / 255.0f;
+        } else if (P.format == 1) {
+            const ushort4 c = reinterpret_cast<const ushort4 *>(P.src)[i];
+            r = half_bits_to_float(c.x);
+            g = half_bits_to_float(c.y);
+            b = half_bits_to_float(c.z);
+            a = half_bits_to_float(c.w);
+        } else if (P.format == 2) {
+            const float4 c = reinterpret_cast<const float4 *>(P.src)[i];
+            r = c.x; g = c.y; b = c.z; a = c.w;
+        } else {
+            r = reinterpret_cast<const float *>(P.src)[i];
+            g = 0.0f; b = 0.0f; a = 0.0f;
+        }
+        if (P.to_linear_table != nullptr) {
+            r = nvb_powf_11_5(r, P.to_linear_table);
+            g = nvb_powf_11_5(g, P.to_linear_table);
+            b = nvb_powf_11_5(b, P.to_linear_table);
+        }
+        P.dst[i] = r;
+        P.dst[n + i] = g;
+        P.dst[2 * n + i] = b;
+        P.dst[3 * n + i] = a;
+    }
+}
+
+// In-place gamma on the first 3 planes.  mode 0: powf_11_5 (toLinear 2.2), 1: powf_5_11 (toGamma 2.2),
+// 2: powf(max(0,x), power) (any other gamma; libm vs CUDA powf => tolerance, not bit-exact).
+struct GammaParams {
+    float *data;
+    size_t count;  // 3 * pixels
+    int mode;
+    const float *table;
+    float power;
+};
+
+__global__ void __launch_bounds__(256) k_gamma(GammaParams P) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x) {
+        float v = P.data[i];
+        if (P.mode == 0) v = nvb_powf_11_5(v, P.table);
+        else if (P.mode == 1) v = nvb_powf_5_11(v, P.table);
+        else v = powf(nv_max(0.0f, v), P.power);
+        P.data[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fastDownSample: 2x2 box for even sizes, 3-tap polyphase box for odd sizes, 1-D when one side is 1.
+// ---------------------------------------------------------------------------------------------------------
+struct BoxDownParams {
+    const float *src;
+    float *dst;
+    int sw, sh;  // source size
+    int dw, dh;  // max(1, sw/2), max(1, sh/2)
+    int planes;  // 4
+};
+
+__global__ void __launch_bounds__(256) k_box_down(BoxDownParams P) {
+    const int sw = P.sw, sh = P.sh, w = P.dw, h = P.dh;
+    const size_t per_plane = (size_t)w * h;
+    const size_t total = per_plane * P.planes;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per_plane);
+        const size_t r = i - (size_t)c * per_plane;
+        const int y = (int)(r / w), x = (int)(r - (size_t)y * w);
+        const float *src = P.src + (size_t)c * sw * sh;
+        float out;
+        if (sw == 1 || sh == 1) {
+            const unsigned n = (unsigned)(w * h);
+            const unsigned k = (unsigned)r;  // linear index along the long side
+            const float *s = src + 2 * (size_t)k;
+            if ((sw * sh) & 1) {
+                const float scale = 1.0f / (float)(2 * n + 1);
+                const float w0 = (float)(n - k), w1 = (float)(n - 0), w2 = (float)(1 + k);
+                out = scale * (w0 * s[0] + w1 * s[1] + w2 * s[2]);
+            } else {
+                out = 0.5f * (s[0] + s[1]);
+            }
+        } else if ((sw & 1) == 0 && (sh & 1) == 0) {
+            const float *s = src + (size_t)(2 * y) * sw + 2 * x;
+            out = 0.25f * (s[0] + s[1] + s[sw] + s[sw + 1]);
+        } else if ((sw & 1) && (sh & 1)) {
+            const float scale = 1.0f / (float)(sw * sh);
+            const float v0 = (float)(h - y), v1 = (float)(h - 0), v2 = (float)(1 + y);
+            const float w0 = (float)(w - x), w1 = (float)(w - 0), w2 = (float)(1 + x);
+            const float *s = src + (size_t)(2 * y) * sw + 2 * x;
+            float f = 0.0f;
+            f += v0 * (w0 * s[0] + w1 * s[1] + w2 * s[2]);
+            f += v1 * (w0 * s[sw] + w1 * s[sw + 1] + w2 * s[sw + 2]);
+            f += v2 * (w0 * s[2 * sw] + w1 * s[2 * sw + 1] + w2 * s[2 * sw + 2]);
+            out = f * scale;
+        } else if (sw & 1) {
+            const float scale = 1.0f / (float)(2 * sw);
+            const float w0 = (float)(w - x), w1 = (float)(w - 0), w2 = (float)(1 + x);
+            const float *s = src + (size_t)(2 * y) * sw + 2 * x;
+            float f = 0.0f;
+            f += w0 * (s[0] + s[sw]);
+            f += w1 * (s[1] + s[sw + 1]);
+            f += w2 * (s[2] + s[sw + 2]);
+            out = f * scale;
+        } else {
+            const float scale = 1.0f / (float)(2 * sh);
+            const float v0 = (float)(h - y), v1 = (float)(h - 0), v2 = (float)(1 + y);
+            const float *s = src + (size_t)(2 * y) * sw + 2 * x;
+            float f = 0.0f;
+            f += v0 * (s[0] + s[1]);
+            f += v1 * (s[sw] + s[sw + 1]);
+            f += v2 * (s[2 * sw] + s[2 * sw + 1]);
+            out = f * scale;
+        }
+        P.dst[i] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Polyphase separable resize.  Per output coordinate i the host precomputes (Filter.cpp:563-608 restated in
+// host/polyphase.cpp): left[i] and `win` normalised weights.  sum = ((0 + w0*s0) + w1*s1) + ... in tap order.
+// ---------------------------------------------------------------------------------------------------------
+NVB_DEV int wrap_coord(int x, int w, int mode) {
+    if (mode == 0) {  // clamp
+        return nv_min(nv_max(x, 0), w - 1);
+    } else if (mode == 1) {  // repeat
+        if (x >= 0) return x % w;
+        return (x + 1) % w + w - 1;
+    } else {  // mirror
+        if (w == 1) x = 0;
+        x = abs(x);
+        while (x >= w) x = abs(w + w - x - 2);
+        return x;
+    }
+}
+
+struct PolyphaseParams {
+    const float *src;
+    float *dst;
+    int sw, sh;  // source plane size
+    int dw, dh;  // destination plane size (X pass: dh == sh; Y pass: dw == sw)
+    int planes;
+    int win;            // taps per output
+    const float *weights;  // [len][win]
+    const int *left;       // [len]
+    int wrap;              // nvtt::WrapMode: 0 clamp, 1 repeat, 2 mirror
+};
+
+__global__ void __launch_bounds__(256) k_polyphase_x(PolyphaseParams P) {
+    const size_t per_plane = (size_t)P.dw * P.dh;
+    const size_t total = per_plane * P.planes;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per_plane);
+        const size_t r = i - (size_t)c * per_plane;
+        const int y = (int)(r / P.dw), x = (int)(r - (size_t)y * P.dw);
+        const float *row = P.src + (size_t)c * P.sw * P.sh + (size_t)y * P.sw;
+        const float *wt = P.weights + (size_t)x * P.win;
+        const int left = P.left[x];
+        float sum = 0;
+        for (int j = 0; j < P.win; j++) {
+            const int idx = wrap_coord(left + j, P.sw, P.wrap);
+            sum += wt[j] * row[idx];
+        }
+        P.dst[i] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_polyphase_y(PolyphaseParams P) {
+    const size_t per_plane = (size_t)P.dw * P.dh;
+    const size_t total = per_plane * P.planes;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per_plane);
+        const size_t r = i - (size_t)c * per_plane;
+        const int y = (int)(r / P.dw), x = (int)(r - (size_t)y * P.dw);
+        const float *col = P.src + (size_t)c * P.sw * P.sh + x;
+        const float *wt = P.weights + (size_t)y * P.win;
+        const int left = P.left[y];
+        float sum = 0;
+        for (int j = 0; j < P.win; j++) {
+            const int idx = wrap_coord(left + j, P.sh, P.wrap);
+            sum += wt[j] * col[(size_t)idx * P.sw];
+        }
+        P.dst[i] = sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Normal-map helpers.  k_scale_bias: ptr = scale*ptr + bias on planes 0..2.  k_normalize: normalizeSafe with
+// epsilon 0 (zero vector stays zero).  k_renormalize = expandNormals -> normalizeNormalMap -> packNormals
+// fused (element-wise, so fusing does not change a single bit), src/nvtt/Context.cpp:329-334.
+// ---------------------------------------------------------------------------------------------------------
+struct ScaleBiasParams {
+    float *data;
+    size_t count;  // 3 * pixels
+    float scale, bias;
+};
+__global__ void __launch_bounds__(256) k_scale_bias(ScaleBiasParams P) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x)
+        P.data[i] = P.scale * P.data[i] + P.bias;
+}
+
+struct NormalizeParams {
+    float *data;
+    size_t pixels;
+    int expand_pack;  // 1 => x = 2x-1 before, x = 0.5x+0.5 after
+};
+__global__ void __launch_bounds__(256) k_normalize(NormalizeParams P) {
+    const size_t n = P.pixels;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float x = P.data[i], y = P.data[n + i], z = P.data[2 * n + i];
+        if (P.expand_pack) {
+            x = 2.0f * x + -1.0f;
+            y = 2.0f * y + -1.0f;
+            z = 2.0f * z + -1.0f;
+        }
+        const float l = sqrtf(x * x + y * y + z * z);
+        if (fabsf(l) <= 0.0f) {
+            x = 0.0f; y = 0.0f; z = 0.0f;
+        } else {
+            const float s = 1.0f / l;
+            x = x * s; y = y * s; z = z * s;
+        }
+        if (P.expand_pack) {
+            x = 0.5f * x + 0.5f;
+            y = 0.5f * y + 0.5f;
+            z = 0.5f * z + 0.5f;
+        }
+        P.data[i] = x;
+        P.data[n + i] = y;
+        P.data[2 * n + i] = z;
+    }
+}
+
+}  // namespace nvb

@@ -1,0 +1,79 @@
+// Shared device helpers for the sm_100a BCn + mip kernels.
+//
+// Parity rules: the whole library is compiled with -fmad=false so that nvcc never contracts
+// a*b+c into an FMA — every +,-,*,/ and sqrtf below is a single IEEE-754 round-to-nearest operation, exactly
+// like the pinned reference build (-O2 -ffp-contract=off, scalar code paths).  min/max/clamp and float->int
+// conversions reproduce the *reference's* semantics (nvcore/Utils.h:158-204, x86 cvttss2si), not CUDA's.
+#pragma once
+#ifndef NVB_EMU
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#endif
+
+#define NVB_DEV __device__ __forceinline__
+
+// nv::max(a,b) = (b < a) ? a : b  /  nv::min(a,b) = (a < b) ? a : b   (src/nvcore/Utils.h:161-188)
+// NaN behaviour: max(NaN, x) = x, max(x, NaN) = NaN; min(NaN, x) = x; min(x, NaN) = NaN.
+template <class T> NVB_DEV T nv_max(T a, T b) { return (b < a) ? a : b; }
+template <class T> NVB_DEV T nv_min(T a, T b) { return (a < b) ? a : b; }
+template <class T> NVB_DEV T nv_clamp(T x, T a, T b) { return nv_min(nv_max(x, a), b); }
+// std::max(a,b) = (a < b) ? b : a ; std::min(a,b) = (b < a) ? b : a   (used by squish maths.h:163-178)
+template <class T> NVB_DEV T std_max(T a, T b) { return (a < b) ? b : a; }
+template <class T> NVB_DEV T std_min(T a, T b) { return (b < a) ? b : a; }
+
+// (int)f as compiled for x86-64 (cvttss2si): NaN and out-of-range give INT_MIN ("integer indefinite").
+// CUDA's cvt.rzi.s32.f32 saturates and maps NaN to 0, so the difference must be made explicit.
+NVB_DEV int x86_ftoi(float f) {
+    return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000;
+}
+// (uint32)f on x86-64 is compiled as a 64-bit cvttss2si followed by truncation to 32 bits.
+NVB_DEV unsigned x86_ftou(float f) {
+    if (f >= -9223372036854775808.0f && f < 9223372036854775808.0f) return (unsigned)(long long)f;
+    return 0u;  // 0x8000000000000000 truncated
+}
+
+// ---- gamma 2.2 approximations (src/nvmath/Gamma.cpp:311-354) -------------------------------------------
+// table[k] = float(2^((k-127)*p/q)) for the 9 "sign|exponent" bits; the tables are generated on the host by
+// nvb::build_gamma_tables() (capi.cu) and uploaded once per context.
+struct GammaTables {
+    const float *to_gamma;   // pow_5_11 table, 512 floats (linear -> gamma 2.2)
+    const float *to_linear;  // pow_11_5 table, 512 floats (gamma 2.2 -> linear)
+};
+
+NVB_DEV float nvb_powf_5_11(float x, const float *__restrict__ table) {
+    unsigned u = __float_as_uint(x);
+    int k = (int)(u >> 23);
+    float m = __uint_as_float((u & 0x7FFFFFu) | (127u << 23));
+    float pe = table[k];
+    float pm = (((-0.0110083047f * m + 0.0905038750f) * m - 0.324697506f) * m + 0.876040946f) * m + 0.369160989f;
+    return pe * pm;
+}
+NVB_DEV float nvb_powf_11_5(float x, const float *__restrict__ table) {
+    unsigned u = __float_as_uint(x);
+    int k = (int)(u >> 23);
+    float m = __uint_as_float((u & 0x7FFFFFu) | (127u << 23));
+    float pe = table[k];
+    float pm = (((-0.00916587552f * m + 0.119315466f) * m + 1.01847068f) * m - 0.158338739f) * m + 0.0297184721f;
+    return pe * pm;
+}
+
+// uint8(255 * clamp(v, 0, 1))  — truncating quantiser of ColorBlock::init (src/nvimage/ColorBlock.cpp:104-107)
+NVB_DEV unsigned quantize_u8_trunc(float v) {
+    float c = nv_clamp(v, 0.0f, 1.0f);
+    return (unsigned)(int)(255.0f * c);
+}
+
+// How an encoder kernel reads one mip level: planar fp32 [c][y][x] (FloatImage layout, FloatImage.h:193-229).
+struct LevelView {
+    const float *__restrict__ data;  // 4 planes of w*h floats
+    int w, h;
+    int bw, bh;                   // blocks per row / column = (w+3)/4, (h+3)/4
+    const float *to_gamma_table;  // non-null => apply powf_5_11 to R,G,B while loading (fused Surface::toGamma)
+};
+
+NVB_DEV float load_texel(const LevelView &lv, int c, int x, int y) {
+    float v = lv.data[(size_t)c * lv.w * lv.h + (size_t)y * lv.w + x];
+    if (lv.to_gamma_table != nullptr && c < 3) v = nvb_powf_5_11(v, lv.to_gamma_table);
+    return v;
+}

@@ -1,0 +1,96 @@
+// TEST / DEBUG INFRASTRUCTURE ONLY — runs the product's device code (csrc/kernels/*.cuh) under the lock-step
+// CPU emulator so kernel logic can be checked against the oracle in a container without a GPU.
+#include "cuda_emu.h"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc_alpha.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
+
+using namespace nvb;
+
+static float g_to_gamma[512], g_to_linear[512];
+static std::vector<uint16_t> g_cand;
+static int g_cand_off[18];
+static uint8_t g_om5[512], g_om6[512];
+static bool g_init = false;
+static void init_tables() {
+    if (g_init) return;
+    build_gamma_tables(g_to_gamma, g_to_linear);
+    build_squish_splits(g_cand, g_cand_off);
+    build_omatch(g_om5, 32);
+    build_omatch(g_om6, 64);
+    g_init = true;
+}
+static LevelView make_lv(const float *data, int w, int h, int gamma) {
+    LevelView lv;
+    lv.data = data; lv.w = w; lv.h = h; lv.bw = (w + 3) / 4; lv.bh = (h + 3) / 4;
+    lv.to_gamma_table = gamma ? g_to_gamma : nullptr;
+    return lv;
+}
+
+extern "C" {
+
+void emu_alpha_blocks(const float *planar, int w, int h, int channel, unsigned char *out, int stride, int offset, int gamma, int mode) {
+    init_tables();
+    AlphaBlocksParams P;
+    P.lv = make_lv(planar, w, h, gamma);
+    P.channel = channel; P.out = out; P.out_stride = stride; P.out_offset = offset; P.mode = mode;
+    int nb = P.lv.bw * P.lv.bh;
+    emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_alpha_blocks(P); });
+}
+
+void emu_bc3_color(const float *planar, int w, int h, const float *metric, int weight_by_alpha, unsigned char *out, int stride, int offset, int gamma) {
+    init_tables();
+    Bc3ColorParams P;
+    P.lv = make_lv(planar, w, h, gamma);
+    P.out = out; P.out_stride = stride; P.out_offset = offset;
+    P.metric[0] = metric[0]; P.metric[1] = metric[1]; P.metric[2] = metric[2];
+    P.weight_by_alpha = weight_by_alpha;
+    P.cand = g_cand.data(); P.cand_off = g_cand_off; P.omatch5 = g_om5; P.omatch6 = g_om6;
+    int nb = P.lv.bw * P.lv.bh;
+    emu::launch(dim3((nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS), dim3(NVB_BC3_GROUPS * 16), 0, [&] { k_bc3_color(P); });
+}
+
+void emu_set_image(const void *src, float *dst, int count, int format, int to_linear) {
+    init_tables();
+    SetImageParams P{src, dst, count, format, to_linear ? g_to_linear : nullptr};
+    emu::launch(dim3((count + 255) / 256), dim3(256), 0, [&] { k_set_image(P); });
+}
+
+void emu_gamma(float *data, size_t pixels, int mode, float power) {
+    init_tables();
+    GammaParams P{data, 3 * pixels, mode, mode == 0 ? g_to_linear : g_to_gamma, power};
+    emu::launch(dim3((unsigned)((P.count + 255) / 256)), dim3(256), 0, [&] { k_gamma(P); });
+}
+
+void emu_box_down(const float *src, int sw, int sh, float *dst) {
+    BoxDownParams P{src, dst, sw, sh, sw / 2 > 1 ? sw / 2 : 1, sh / 2 > 1 ? sh / 2 : 1, 4};
+    size_t total = (size_t)P.dw * P.dh * 4;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [&] { k_box_down(P); });
+}
+
+// full 2-D resize: X pass into tmp (dw x sh) then Y pass (FloatImage::resize, FloatImage.cpp:761-808)
+void emu_resize(const float *src, int sw, int sh, float *dst, int dw, int dh, int kind, float width, float p0, float p1, int wrap) {
+    FilterDesc f{kind, width, p0, p1};
+    PolyphaseTable tx, ty;
+    build_polyphase(f, sw, dw, tx);
+    build_polyphase(f, sh, dh, ty);
+    std::vector<float> tmp((size_t)dw * sh * 4);
+    PolyphaseParams X{src, tmp.data(), sw, sh, dw, sh, 4, tx.window, tx.weights.data(), tx.left.data(), wrap};
+    size_t total = (size_t)dw * sh * 4;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [&] { k_polyphase_x(X); });
+    PolyphaseParams Y{tmp.data(), dst, dw, sh, dw, dh, 4, ty.window, ty.weights.data(), ty.left.data(), wrap};
+    total = (size_t)dw * dh * 4;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [&] { k_polyphase_y(Y); });
+}
+
+void emu_normalize(float *data, size_t pixels, int expand_pack) {
+    NormalizeParams P{data, pixels, expand_pack};
+    emu::launch(dim3((unsigned)((pixels + 255) / 256)), dim3(256), 0, [&] { k_normalize(P); });
+}
+
+void emu_scale_bias(float *data, size_t pixels, float scale, float bias) {
+    ScaleBiasParams P{data, 3 * pixels, scale, bias};
+    emu::launch(dim3((unsigned)((P.count + 255) / 256)), dim3(256), 0, [&] { k_scale_bias(P); });
+}
+}
