@@ -1,0 +1,161 @@
+/*
+ * nvtt_b200 — C ABI of the B200-native (sm_100a) block-compression + mip-generation path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes.  Each entry point names the interface of the
+ * reference (castano/nvidia-texture-tools 2.1.2) that it replaces; enum values are the reference's own
+ * (nvtt::Format, nvtt::Quality, ... src/nvtt/nvtt.h:80-277) so a caller can pass them through unchanged.
+ * The C++ mirror of nvtt::Compressor / CompressionOptions / InputOptions / OutputOptions lives in
+ * nvidia-texture-tools_b200/host/ and is implemented on top of these functions only.
+ *
+ * There is NO CPU fallback: every function that computes needs a CUDA device and fails with
+ * NVTTB_ERR_CUDA (nvtt::Error_CudaError) otherwise.
+ */
+#ifndef NVTT_B200_H
+#define NVTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NVTTB_API __declspec(dllexport)
+#else
+#define NVTTB_API __attribute__((visibility("default")))
+#endif
+
+/* Return codes: 0 = success, otherwise 1 + nvtt::Error (src/nvtt/nvtt.h:345-356). */
+enum {
+    NVTTB_OK = 0,
+    NVTTB_ERR_UNKNOWN = 1,
+    NVTTB_ERR_INVALID_INPUT = 2,
+    NVTTB_ERR_UNSUPPORTED_FEATURE = 3,
+    NVTTB_ERR_CUDA = 4,
+    NVTTB_ERR_FILE_OPEN = 5,
+    NVTTB_ERR_FILE_WRITE = 6,
+    NVTTB_ERR_UNSUPPORTED_OUTPUT_FORMAT = 7
+};
+
+/* Where a buffer lives. */
+enum { NVTTB_HOST = 0, NVTTB_DEVICE = 1 };
+
+typedef struct NvttbContext NvttbContext; /* one per GPU: stream, lookup tables, scratch (replaces nvtt::Compressor::Private state, src/nvtt/Context.h) */
+typedef struct NvttbSurface NvttbSurface; /* device-resident planar fp32 RGBA image (replaces nvtt::Surface, src/nvtt/Surface.h:37-75) */
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+/* Number of CUDA devices visible (0 if none / no driver).  Replaces nv::cuda::isHardwarePresent (src/nvtt/cuda/CudaUtils.cpp). */
+NVTTB_API int nvttb_device_count(void);
+/* Create a context on `device`.  Replaces Compressor::Compressor + enableCudaAcceleration (src/nvtt/Context.cpp:61-98). */
+NVTTB_API int nvttb_context_create(int device, NvttbContext **out);
+NVTTB_API void nvttb_context_destroy(NvttbContext *ctx);
+/* Human-readable description of the last failure on this context (never NULL). */
+NVTTB_API const char *nvttb_last_error(const NvttbContext *ctx);
+/* Kernel launches issued by this context so far (for bench.py's gpu_launches). */
+NVTTB_API uint64_t nvttb_launch_count(const NvttbContext *ctx);
+/* Block until all work queued on the context's stream is done. */
+NVTTB_API int nvttb_synchronize(NvttbContext *ctx);
+/* The context's cudaStream_t (as void*), so a caller can record CUDA events on the launching stream. */
+NVTTB_API void *nvttb_stream(NvttbContext *ctx);
+
+/* ---- one mip level: the nv::CompressorInterface::compress seam ------------------------------------------ */
+/* Replaces Compressor::Private::compress(AlphaMode,w,h,d,face,mip,const float*,...) + chooseCpuCompressor
+ * (src/nvtt/Context.cpp:486-516,1038-1163; src/nvtt/Compressor.h:34-38). */
+typedef struct NvttbEncodeDesc {
+    int format;            /* nvtt::Format */
+    int quality;           /* nvtt::Quality */
+    int alphaMode;         /* nvtt::AlphaMode */
+    int pixelType;         /* nvtt::PixelType (BC6: UnsignedFloat / Float) */
+    float colorWeights[4]; /* CompressionOptions::setColorWeights */
+    int width, height;     /* texels; depth is 1 */
+    int applyToGamma;      /* 1: fuse Surface::toGamma(2.2) on R,G,B into the block gather (pipeline use) */
+} NvttbEncodeDesc;
+
+/* Bytes of one encoded level = blocks * block size (nv::computeImageSize, src/nvtt/Surface.cpp:210-218); 0 if unsupported. */
+NVTTB_API size_t nvttb_level_size(int format, int width, int height);
+/* 1 if (format, quality) is implemented by this library. */
+NVTTB_API int nvttb_format_supported(int format, int quality);
+/* rgba: planar fp32 [4][h][w] (FloatImage layout) on host or device; out: BCn bytes, host or device.
+ * Asynchronous when both buffers are on the device; synchronous otherwise. */
+NVTTB_API int nvttb_encode_level(NvttbContext *ctx, const NvttbEncodeDesc *desc, const float *rgba, int rgba_location,
+                                 void *out, int out_location, size_t out_capacity);
+
+/* ---- Surface ops on the device (the image-op seam called from src/nvtt/Context.cpp:267-343) ------------- */
+NVTTB_API int nvttb_surface_create(NvttbContext *ctx, NvttbSurface **out);
+NVTTB_API void nvttb_surface_destroy(NvttbSurface *s);
+NVTTB_API int nvttb_surface_clone(const NvttbSurface *s, NvttbSurface **out);       /* Surface copy (COW in the reference) */
+NVTTB_API void nvttb_surface_set_wrap_mode(NvttbSurface *s, int wrapMode);          /* Surface::setWrapMode */
+NVTTB_API void nvttb_surface_set_alpha_mode(NvttbSurface *s, int alphaMode);        /* Surface::setAlphaMode */
+NVTTB_API void nvttb_surface_set_normal_map(NvttbSurface *s, int isNormalMap);      /* Surface::setNormalMap */
+NVTTB_API int nvttb_surface_width(const NvttbSurface *s);
+NVTTB_API int nvttb_surface_height(const NvttbSurface *s);
+/* Surface::setImage(InputFormat,w,h,1,data)  src/nvtt/Surface.cpp:728-815 */
+NVTTB_API int nvttb_surface_set_image(NvttbSurface *s, int inputFormat, int w, int h, const void *data, int location);
+/* Surface::toLinear / toGamma  src/nvtt/Surface.cpp:1470-1488 */
+NVTTB_API int nvttb_surface_to_linear(NvttbSurface *s, float gamma);
+NVTTB_API int nvttb_surface_to_gamma(NvttbSurface *s, float gamma);
+/* Surface::buildNextMipmap(filter[,filterWidth,params])  src/nvtt/Surface.cpp:1344-1406.
+ * params may be NULL (defaults: Box 0.5, Triangle 1.0, Kaiser 3.0/alpha 4/stretch 1).  *built = 0 when the surface is already 1x1. */
+NVTTB_API int nvttb_surface_build_next_mipmap(NvttbSurface *s, int mipmapFilter, int useParams, float filterWidth,
+                                              const float *params, int *built);
+/* Surface::resize(w,h,1,filter[,filterWidth,params])  src/nvtt/Surface.cpp:1152-1219 */
+NVTTB_API int nvttb_surface_resize(NvttbSurface *s, int w, int h, int resizeFilter, int useParams, float filterWidth,
+                                   const float *params);
+/* Surface::expandNormals / normalizeNormalMap / packNormals  src/nvtt/Surface.cpp:2810-2817,2952-2963 */
+NVTTB_API int nvttb_surface_expand_normals(NvttbSurface *s);
+NVTTB_API int nvttb_surface_normalize_normal_map(NvttbSurface *s);
+NVTTB_API int nvttb_surface_pack_normals(NvttbSurface *s);
+/* Surface::toGreyScale / toNormalMap  src/nvtt/Surface.cpp:1732-1756,2794-2808 */
+NVTTB_API int nvttb_surface_to_grey_scale(NvttbSurface *s, float r, float g, float b, float a);
+NVTTB_API int nvttb_surface_to_normal_map(NvttbSurface *s, float sm, float medium, float big, float large);
+/* Surface::data(): copy planar fp32 RGBA (4*w*h floats) to the host. */
+NVTTB_API int nvttb_surface_download(const NvttbSurface *s, float *out);
+/* Device pointer of the planar fp32 data (valid until the next op on the surface). */
+NVTTB_API const float *nvttb_surface_device_data(const NvttbSurface *s);
+/* Compressor::compress(Surface, face, mip, ...)  src/nvtt/Context.cpp:146-149,477-484.  desc->width/height are ignored. */
+NVTTB_API int nvttb_surface_encode(NvttbSurface *s, const NvttbEncodeDesc *desc, void *out, int out_location, size_t out_capacity);
+
+/* ---- the whole InputOptions pipeline on the device ------------------------------------------------------ */
+/* Replaces Compressor::process -> Compressor::Private::compress(InputOptions...) (src/nvtt/Context.cpp:117-120,217-346):
+ * per face: setImage -> [toGreyScale+toNormalMap] -> toLinear -> level 0 -> { buildNextMipmap -> [renormalise] ->
+ * toGamma -> compress } per level.  The DDS/KTX header is written by the C++ host layer, not here. */
+typedef struct NvttbProcessDesc {
+    int inputFormat;   /* nvtt::InputFormat */
+    int width, height; /* level-0 extent of every face */
+    int faceCount;     /* 1 (2D), 6 (cube) or array size */
+    int wrapMode;      /* nvtt::WrapMode */
+    int mipmapFilter;  /* nvtt::MipmapFilter */
+    int generateMipmaps;
+    int maxLevel;      /* <= 0: full chain */
+    float kaiserWidth, kaiserAlpha, kaiserStretch;
+    float inputGamma, outputGamma;
+    int isNormalMap, convertToNormalMap, normalizeMipmaps;
+    float heightFactors[4];      /* InputOptions::setHeightEvaluation */
+    float bumpFrequencyScale[4]; /* InputOptions::setNormalFilter */
+    int alphaMode;     /* nvtt::AlphaMode */
+    NvttbEncodeDesc encode; /* format, quality, colour weights, pixel type (width/height/applyToGamma ignored) */
+    int firstFace, lastFace;   /* process faces [firstFace, lastFace); 0,0 = all (multi-GPU sharding by face) */
+} NvttbProcessDesc;
+
+/* Called once per (face, mip) in the reference's order (face-major, mip-minor); data is host memory owned by the
+ * library and valid only during the call — exactly like OutputHandler::writeData (src/nvtt/nvtt.h:330-342).
+ * Return 0 to stop (maps to Error_FileWrite). */
+typedef int (*NvttbEmitFn)(void *user, int face, int mip, int width, int height, int depth, const void *data, size_t size);
+
+/* images[f] = level-0 texels of face f in inputFormat, on host or device. */
+NVTTB_API int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *desc, const void *const *images, int images_location,
+                            NvttbEmitFn emit, void *user);
+/* Same pipeline, but the encoded chain of every processed face stays in one caller-provided DEVICE buffer
+ * (face-major, mip-minor, tightly packed); nothing is copied to the host.  *written = bytes produced. */
+NVTTB_API int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *desc, const void *const *images,
+                                      int images_location, void *out_device, size_t out_capacity, size_t *written);
+/* Total bytes nvttb_process emits for this description (Compressor::estimateSize, src/nvtt/Context.cpp:122-137). */
+NVTTB_API size_t nvttb_process_output_size(const NvttbProcessDesc *desc);
+/* Number of mip levels the pipeline produces (nv::countMipmaps, src/nvtt/Surface.cpp:181-193, capped by maxLevel). */
+NVTTB_API int nvttb_process_mip_count(const NvttbProcessDesc *desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVTT_B200_H */

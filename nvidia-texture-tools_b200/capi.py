@@ -1,0 +1,294 @@
+"""ctypes binding of include/nvtt_b200.h.  Fails loudly when the CUDA library or a GPU is missing — there is no
+CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200.so")
+
+# nvtt enums (src/nvtt/nvtt.h:80-277 of the reference)
+Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
+Format_BC6, Format_BC7 = 10, 11
+Format_BC1, Format_BC2, Format_BC3 = Format_DXT1, Format_DXT3, Format_DXT5
+Quality_Fastest, Quality_Normal, Quality_Production, Quality_Highest = range(4)
+WrapMode_Clamp, WrapMode_Repeat, WrapMode_Mirror = range(3)
+InputFormat_BGRA_8UB, InputFormat_RGBA_16F, InputFormat_RGBA_32F, InputFormat_R_32F = range(4)
+MipmapFilter_Box, MipmapFilter_Triangle, MipmapFilter_Kaiser = range(3)
+ResizeFilter_Box, ResizeFilter_Triangle, ResizeFilter_Kaiser, ResizeFilter_Mitchell = range(4)
+AlphaMode_None, AlphaMode_Transparency, AlphaMode_Premultiplied = range(3)
+PixelType_UnsignedNorm, PixelType_Float, PixelType_UnsignedFloat = 0, 4, 5
+HOST, DEVICE = 0, 1
+
+ERRORS = {0: "OK", 1: "Error_Unknown", 2: "Error_InvalidInput", 3: "Error_UnsupportedFeature", 4: "Error_CudaError",
+          5: "Error_FileOpen", 6: "Error_FileWrite", 7: "Error_UnsupportedOutputFormat"}
+
+
+class NvttbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERRORS.get(code, code), msg))
+        self.code = code
+
+
+class EncodeDesc(C.Structure):
+    _fields_ = [("format", C.c_int), ("quality", C.c_int), ("alphaMode", C.c_int), ("pixelType", C.c_int),
+                ("colorWeights", C.c_float * 4), ("width", C.c_int), ("height", C.c_int), ("applyToGamma", C.c_int)]
+
+
+class ProcessDesc(C.Structure):
+    _fields_ = [("inputFormat", C.c_int), ("width", C.c_int), ("height", C.c_int), ("faceCount", C.c_int),
+                ("wrapMode", C.c_int), ("mipmapFilter", C.c_int), ("generateMipmaps", C.c_int), ("maxLevel", C.c_int),
+                ("kaiserWidth", C.c_float), ("kaiserAlpha", C.c_float), ("kaiserStretch", C.c_float),
+                ("inputGamma", C.c_float), ("outputGamma", C.c_float),
+                ("isNormalMap", C.c_int), ("convertToNormalMap", C.c_int), ("normalizeMipmaps", C.c_int),
+                ("heightFactors", C.c_float * 4), ("bumpFrequencyScale", C.c_float * 4),
+                ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int)]
+
+
+EMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t)
+
+EXPORTS = [
+    "nvttb_device_count", "nvttb_context_create", "nvttb_context_destroy", "nvttb_last_error", "nvttb_launch_count",
+    "nvttb_synchronize", "nvttb_stream", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level",
+    "nvttb_surface_create", "nvttb_surface_destroy", "nvttb_surface_clone", "nvttb_surface_set_wrap_mode",
+    "nvttb_surface_set_alpha_mode", "nvttb_surface_set_normal_map", "nvttb_surface_width", "nvttb_surface_height",
+    "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
+    "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
+    "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
+    "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
+    "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count",
+]
+
+_lib = None
+
+
+def lib():
+    """dlopen the CUDA library (no GPU needed just to load it and look at its symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    L.nvttb_context_create.argtypes = [ci, C.POINTER(vp)]
+    L.nvttb_context_destroy.argtypes = [vp]
+    L.nvttb_last_error.argtypes = [vp]
+    L.nvttb_last_error.restype = C.c_char_p
+    L.nvttb_launch_count.argtypes = [vp]
+    L.nvttb_launch_count.restype = C.c_uint64
+    L.nvttb_synchronize.argtypes = [vp]
+    L.nvttb_stream.argtypes = [vp]
+    L.nvttb_stream.restype = vp
+    L.nvttb_level_size.argtypes = [ci, ci, ci]
+    L.nvttb_level_size.restype = sz
+    L.nvttb_format_supported.argtypes = [ci, ci]
+    L.nvttb_encode_level.argtypes = [vp, C.POINTER(EncodeDesc), vp, ci, vp, ci, sz]
+    L.nvttb_surface_create.argtypes = [vp, C.POINTER(vp)]
+    L.nvttb_surface_destroy.argtypes = [vp]
+    L.nvttb_surface_clone.argtypes = [vp, C.POINTER(vp)]
+    for n in ("set_wrap_mode", "set_alpha_mode", "set_normal_map"):
+        getattr(L, "nvttb_surface_" + n).argtypes = [vp, ci]
+        getattr(L, "nvttb_surface_" + n).restype = None
+    L.nvttb_surface_width.argtypes = [vp]
+    L.nvttb_surface_height.argtypes = [vp]
+    L.nvttb_surface_set_image.argtypes = [vp, ci, ci, ci, vp, ci]
+    L.nvttb_surface_to_linear.argtypes = [vp, cf]
+    L.nvttb_surface_to_gamma.argtypes = [vp, cf]
+    L.nvttb_surface_build_next_mipmap.argtypes = [vp, ci, ci, cf, C.POINTER(cf), C.POINTER(ci)]
+    L.nvttb_surface_resize.argtypes = [vp, ci, ci, ci, ci, cf, C.POINTER(cf)]
+    for n in ("expand_normals", "normalize_normal_map", "pack_normals"):
+        getattr(L, "nvttb_surface_" + n).argtypes = [vp]
+    L.nvttb_surface_to_grey_scale.argtypes = [vp, cf, cf, cf, cf]
+    L.nvttb_surface_to_normal_map.argtypes = [vp, cf, cf, cf, cf]
+    L.nvttb_surface_download.argtypes = [vp, vp]
+    L.nvttb_surface_device_data.argtypes = [vp]
+    L.nvttb_surface_device_data.restype = vp
+    L.nvttb_surface_encode.argtypes = [vp, C.POINTER(EncodeDesc), vp, ci, sz]
+    L.nvttb_process.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, EMIT_FN, vp]
+    L.nvttb_process_to_device.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, sz, C.POINTER(sz)]
+    L.nvttb_process_output_size.argtypes = [C.POINTER(ProcessDesc)]
+    L.nvttb_process_output_size.restype = sz
+    L.nvttb_process_mip_count.argtypes = [C.POINTER(ProcessDesc)]
+    _lib = L
+    return L
+
+
+def make_encode_desc(fmt, quality, w=0, h=0, alpha_mode=AlphaMode_None, color_weights=(1, 1, 1, 1),
+                     pixel_type=PixelType_UnsignedNorm, apply_to_gamma=False):
+    d = EncodeDesc()
+    d.format, d.quality, d.alphaMode, d.pixelType = fmt, quality, alpha_mode, pixel_type
+    d.colorWeights = (C.c_float * 4)(*color_weights)
+    d.width, d.height, d.applyToGamma = w, h, int(apply_to_gamma)
+    return d
+
+
+def make_process_desc(input_format, w, h, fmt, quality, *, faces=1, wrap=WrapMode_Mirror, mip_filter=MipmapFilter_Box,
+                      mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
+                      to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
+                      pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), first_face=0, last_face=0):
+    d = ProcessDesc()
+    d.inputFormat, d.width, d.height, d.faceCount = input_format, w, h, faces
+    d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
+    d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = kaiser
+    d.inputGamma, d.outputGamma = gamma
+    d.isNormalMap, d.convertToNormalMap, d.normalizeMipmaps = int(normal_map), int(to_normal_map), int(normalize_mipmaps)
+    d.heightFactors = (C.c_float * 4)(0, 0, 0, 1)
+    d.bumpFrequencyScale = (C.c_float * 4)(1.0 / 1.875, 0.5 / 1.875, 0.25 / 1.875, 0.125 / 1.875)
+    d.alphaMode = alpha_mode
+    d.encode = make_encode_desc(fmt, quality, alpha_mode=alpha_mode, color_weights=color_weights, pixel_type=pixel_type)
+    d.firstFace, d.lastFace = first_face, last_face
+    return d
+
+
+class Context:
+    """One GPU context (stream + tables + scratch).  Raises NvttbError(Error_CudaError) when there is no GPU."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.nvttb_context_create(device, C.byref(h))
+        if rc != 0:
+            raise NvttbError(rc, "nvttb_context_create(device=%d) failed (no CUDA device?) — no CPU fallback exists" % device)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nvttb_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NvttbError(rc, self.L.nvttb_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return int(self.L.nvttb_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.L.nvttb_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.nvttb_synchronize(self.h))
+
+    def encode_level(self, fmt, quality, planar_rgba, **kw):
+        """planar_rgba float32 [4,h,w] on the host -> np.uint8 BCn bytes."""
+        a = np.ascontiguousarray(planar_rgba, dtype=np.float32)
+        _, h, w = a.shape
+        d = make_encode_desc(fmt, quality, w, h, **kw)
+        n = self.L.nvttb_level_size(fmt, w, h)
+        out = np.empty(n, np.uint8)
+        self._ck(self.L.nvttb_encode_level(self.h, C.byref(d), a.ctypes.data, HOST, out.ctypes.data, HOST, n))
+        return out
+
+    def encode_level_device(self, desc, d_rgba_ptr, d_out_ptr, cap):
+        self._ck(self.L.nvttb_encode_level(self.h, C.byref(desc), d_rgba_ptr, DEVICE, d_out_ptr, DEVICE, cap))
+
+    def process(self, images, desc, location=HOST):
+        """Runs the whole pipeline; images = list of numpy arrays (host) or raw device pointers.
+        Returns list of (face, mip, w, h, bytes)."""
+        out = []
+
+        def _emit(user, face, mip, w, h, d, data, size):
+            out.append((face, mip, w, h, np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (size,)).copy()))
+            return 1
+
+        cb = EMIT_FN(_emit)
+        ptrs, keep = self._image_ptrs(images, location)
+        self._ck(self.L.nvttb_process(self.h, C.byref(desc), ptrs, location, cb, None))
+        return out
+
+    def process_bytes(self, images, desc, location=HOST):
+        return np.concatenate([b for (_, _, _, _, b) in self.process(images, desc, location)])
+
+    def process_to_device(self, images, desc, d_out_ptr, cap, location=DEVICE):
+        ptrs, keep = self._image_ptrs(images, location)
+        written = C.c_size_t(0)
+        self._ck(self.L.nvttb_process_to_device(self.h, C.byref(desc), ptrs, location, d_out_ptr, cap, C.byref(written)))
+        return written.value
+
+    @staticmethod
+    def _image_ptrs(images, location):
+        keep = []
+        vals = []
+        for im in images:
+            if isinstance(im, np.ndarray):
+                im = np.ascontiguousarray(im)
+                keep.append(im)
+                vals.append(im.ctypes.data)
+            else:
+                vals.append(int(im))
+        return (C.c_void_p * len(vals))(*vals), keep
+
+
+class Surface:
+    """Device-resident nvtt::Surface mirror (subset on the hot path)."""
+
+    def __init__(self, ctx, wrap=WrapMode_Mirror, alpha_mode=AlphaMode_None, normal_map=False):
+        self.ctx, self.L = ctx, ctx.L
+        h = C.c_void_p()
+        ctx._ck(self.L.nvttb_surface_create(ctx.h, C.byref(h)))
+        self.h = h
+        self.L.nvttb_surface_set_wrap_mode(h, wrap)
+        self.L.nvttb_surface_set_alpha_mode(h, alpha_mode)
+        self.L.nvttb_surface_set_normal_map(h, int(normal_map))
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.L.nvttb_surface_destroy(self.h)
+        self.h = None
+
+    width = property(lambda s: s.L.nvttb_surface_width(s.h))
+    height = property(lambda s: s.L.nvttb_surface_height(s.h))
+
+    def set_image(self, input_format, w, h, data):
+        data = np.ascontiguousarray(data)
+        self._keep = data
+        self.ctx._ck(self.L.nvttb_surface_set_image(self.h, input_format, w, h, data.ctypes.data, HOST))
+
+    def get(self):
+        out = np.empty((4, self.height, self.width), np.float32)
+        self.ctx._ck(self.L.nvttb_surface_download(self.h, out.ctypes.data))
+        return out
+
+    def to_linear(self, g):
+        self.ctx._ck(self.L.nvttb_surface_to_linear(self.h, g))
+
+    def to_gamma(self, g):
+        self.ctx._ck(self.L.nvttb_surface_to_gamma(self.h, g))
+
+    def build_next_mipmap(self, filt, params=None):
+        built = C.c_int(0)
+        if params is None:
+            self.ctx._ck(self.L.nvttb_surface_build_next_mipmap(self.h, filt, 0, 0.0, None, C.byref(built)))
+        else:
+            p = (C.c_float * 2)(params[1], params[2])
+            self.ctx._ck(self.L.nvttb_surface_build_next_mipmap(self.h, filt, 1, params[0], p, C.byref(built)))
+        return bool(built.value)
+
+    def resize(self, w, h, filt, params=None):
+        if params is None:
+            self.ctx._ck(self.L.nvttb_surface_resize(self.h, w, h, filt, 0, 0.0, None))
+        else:
+            p = (C.c_float * 2)(params[1], params[2])
+            self.ctx._ck(self.L.nvttb_surface_resize(self.h, w, h, filt, 1, params[0], p))
+
+    def expand_normals(self):
+        self.ctx._ck(self.L.nvttb_surface_expand_normals(self.h))
+
+    def pack_normals(self):
+        self.ctx._ck(self.L.nvttb_surface_pack_normals(self.h))
+
+    def normalize_normal_map(self):
+        self.ctx._ck(self.L.nvttb_surface_normalize_normal_map(self.h))
+
+    def encode(self, fmt, quality, **kw):
+        d = make_encode_desc(fmt, quality, **kw)
+        n = self.L.nvttb_level_size(fmt, self.width, self.height)
+        out = np.empty(n, np.uint8)
+        self.ctx._ck(self.L.nvttb_surface_encode(self.h, C.byref(d), out.ctypes.data, HOST, n))
+        return out

@@ -1,0 +1,768 @@
+// C-ABI implementation (include/nvtt_b200.h): context, device surfaces, per-level encode dispatch and the whole
+// InputOptions pipeline, all on one CUDA stream per context.  Host logic mirrors
+// Compressor::Private::compress (src/nvtt/Context.cpp:217-346, 486-516) and chooseCpuCompressor (:1038-1163).
+// There is no CPU code path: without a CUDA device nvttb_context_create fails and nothing else can be called.
+#include "../../include/nvtt_b200.h"
+#include "host_tables.h"
+#include "kernels/bc_alpha.cuh"
+#include "kernels/bc3_color.cuh"
+#include "kernels/image_ops.cuh"
+
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+#include <string.h>
+#include <stdio.h>
+
+using namespace nvb;
+
+// nvtt enums used here (src/nvtt/nvtt.h:80-277)
+enum { F_RGB = 0, F_DXT1 = 1, F_DXT1a = 2, F_DXT3 = 3, F_DXT5 = 4, F_DXT5n = 5, F_BC4 = 6, F_BC5 = 7, F_BC6 = 10, F_BC7 = 11 };
+enum { Q_Fastest = 0, Q_Normal = 1, Q_Production = 2, Q_Highest = 3 };
+enum { AM_None = 0, AM_Transparency = 1, AM_Premultiplied = 2 };
+enum { MF_Box = 0, MF_Triangle = 1, MF_Kaiser = 2 };
+enum { RF_Box = 0, RF_Triangle = 1, RF_Kaiser = 2, RF_Mitchell = 3 };
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct PolyDev {
+    int window = 0, length = 0;
+    float *weights = nullptr;
+    int *left = nullptr;
+};
+
+struct NvttbContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    float *d_to_gamma = nullptr, *d_to_linear = nullptr;
+    unsigned short *d_cand = nullptr;
+    int *d_cand_off = nullptr;
+    unsigned char *d_om5 = nullptr, *d_om6 = nullptr;
+    DevBuf in_stage, tmp_filter, tmp_level, out_dev, lvlA, lvlB;
+    void *h_out = nullptr;  // pinned
+    size_t h_out_cap = 0;
+    std::map<std::tuple<int, unsigned, unsigned, unsigned, int, int>, PolyDev> poly_cache;
+};
+
+struct NvttbSurface {
+    NvttbContext *ctx = nullptr;
+    DevBuf buf;
+    int w = 0, h = 0;
+    int wrapMode = 2;  // nvtt default WrapMode_Mirror (Surface.cpp / InputOptions.cpp:98)
+    int alphaMode = 0;
+    int isNormalMap = 0;
+};
+
+static int fail(NvttbContext *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return fail(ctx, NVTTB_ERR_CUDA, #call, _e); \
+    } while (0)
+
+static int ensure(NvttbContext *ctx, DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes && b.p) return NVTTB_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CK(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return NVTTB_OK;
+}
+static int ensure_pinned(NvttbContext *ctx, size_t bytes) {
+    if (ctx->h_out_cap >= bytes && ctx->h_out) return NVTTB_OK;
+    if (ctx->h_out) CK(cudaFreeHost(ctx->h_out));
+    ctx->h_out = nullptr;
+    ctx->h_out_cap = 0;
+    CK(cudaMallocHost(&ctx->h_out, bytes));
+    ctx->h_out_cap = bytes;
+    return NVTTB_OK;
+}
+
+static inline unsigned grid_for(size_t items, int per_cta) {
+    size_t g = (items + per_cta - 1) / per_cta;
+    const size_t cap = 148u * 32u;  // grid-stride kernels: a few waves of the 148 SMs
+    if (g > cap) g = cap;
+    if (g == 0) g = 1;
+    return (unsigned)g;
+}
+
+static int block_bytes(int format) {
+    switch (format) {
+    case F_DXT1: case F_DXT1a: case F_BC4: return 8;
+    case F_DXT3: case F_DXT5: case F_DXT5n: case F_BC5: case F_BC6: case F_BC7: return 16;
+    default: return 0;
+    }
+}
+
+extern "C" {
+
+int nvttb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int nvttb_context_create(int device, NvttbContext **out) {
+    if (!out) return NVTTB_ERR_INVALID_INPUT;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+        fprintf(stderr, "nvtt_b200: no usable CUDA device (%s); this library has no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return NVTTB_ERR_CUDA;
+    }
+    NvttbContext *ctx = new NvttbContext();
+    ctx->device = device;
+    auto bail = [&](const char *what, cudaError_t err) {
+        fprintf(stderr, "nvtt_b200: %s: %s\n", what, cudaGetErrorString(err));
+        delete ctx;
+        return NVTTB_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    float tg[512], tl[512];
+    build_gamma_tables(tg, tl);
+    std::vector<uint16_t> cand;
+    int off[18];
+    build_squish_splits(cand, off);
+    uint8_t om5[512], om6[512];
+    build_omatch(om5, 32);
+    build_omatch(om6, 64);
+    if ((e = cudaMalloc(&ctx->d_to_gamma, sizeof(tg))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_to_linear, sizeof(tl))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_cand, cand.size() * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_cand_off, sizeof(off))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_om5, 512)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_om6, 512)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_to_gamma, tg, sizeof(tg), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_to_linear, tl, sizeof(tl), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_cand, cand.data(), cand.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_cand_off, off, sizeof(off), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_om5, om5, 512, cudaMemcpyHostToDevice);
+    if ((e = cudaMemcpy(ctx->d_om6, om6, 512, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    *out = ctx;
+    return NVTTB_OK;
+}
+
+void nvttb_context_destroy(NvttbContext *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_to_gamma);
+    cudaFree(ctx->d_to_linear);
+    cudaFree(ctx->d_cand);
+    cudaFree(ctx->d_cand_off);
+    cudaFree(ctx->d_om5);
+    cudaFree(ctx->d_om6);
+    cudaFree(ctx->in_stage.p);
+    cudaFree(ctx->tmp_filter.p);
+    cudaFree(ctx->tmp_level.p);
+    cudaFree(ctx->out_dev.p);
+    cudaFree(ctx->lvlA.p);
+    cudaFree(ctx->lvlB.p);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (auto &kv : ctx->poly_cache) {
+        cudaFree(kv.second.weights);
+        cudaFree(kv.second.left);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *nvttb_last_error(const NvttbContext *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t nvttb_launch_count(const NvttbContext *ctx) { return ctx ? ctx->launches : 0; }
+void *nvttb_stream(NvttbContext *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int nvttb_synchronize(NvttbContext *ctx) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NVTTB_OK;
+}
+
+size_t nvttb_level_size(int format, int w, int h) {
+    if (w <= 0 || h <= 0) return 0;
+    return (size_t)((w + 3) / 4) * ((h + 3) / 4) * block_bytes(format);
+}
+
+int nvttb_format_supported(int format, int quality) {
+    switch (format) {
+    case F_BC4:
+    case F_BC5:
+        return quality == Q_Fastest || quality == Q_Normal;
+    case F_DXT5:
+        return quality == Q_Normal || quality == Q_Production;
+    default:
+        return 0;
+    }
+}
+
+}  // extern "C"
+
+// ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
+static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out) {
+    if (!nvttb_format_supported(d->format, d->quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
+    LevelView lv;
+    lv.data = d_rgba;
+    lv.w = w;
+    lv.h = h;
+    lv.bw = (w + 3) / 4;
+    lv.bh = (h + 3) / 4;
+    lv.to_gamma_table = d->applyToGamma ? ctx->d_to_gamma : nullptr;
+    const int nb = lv.bw * lv.bh;
+    auto alpha = [&](int channel, int stride, int offset) {
+        AlphaBlocksParams P;
+        P.lv = lv;
+        P.channel = channel;
+        P.out = d_out;
+        P.out_stride = stride;
+        P.out_offset = offset;
+        P.mode = 0;
+        k_alpha_blocks<<<grid_for(nb, 128), 128, 0, ctx->stream>>>(P);
+        ctx->launches++;
+    };
+    if (d->format == F_BC4) {
+        alpha(0, 8, 0);
+    } else if (d->format == F_BC5) {
+        alpha(0, 16, 0);
+        alpha(1, 16, 8);
+    } else if (d->format == F_DXT5) {
+        alpha(3, 16, 0);
+        Bc3ColorParams P;
+        P.lv = lv;
+        P.out = d_out;
+        P.out_stride = 16;
+        P.out_offset = 8;
+        P.metric[0] = d->colorWeights[0];
+        P.metric[1] = d->colorWeights[1];
+        P.metric[2] = d->colorWeights[2];
+        P.weight_by_alpha = (d->alphaMode == AM_Transparency);
+        P.cand = ctx->d_cand;
+        P.cand_off = ctx->d_cand_off;
+        P.omatch5 = ctx->d_om5;
+        P.omatch6 = ctx->d_om6;
+        k_bc3_color<<<(nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, 0, ctx->stream>>>(P);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+// ---- polyphase tables, cached per (filter, params, src, dst) ------------------------------------------------
+static int get_poly(NvttbContext *ctx, const FilterDesc &f, int src, int dst, PolyDev *out) {
+    unsigned uw, u0, u1;
+    memcpy(&uw, &f.width, 4);
+    memcpy(&u0, &f.p0, 4);
+    memcpy(&u1, &f.p1, 4);
+    auto key = std::make_tuple(f.kind, uw, u0, u1, src, dst);
+    auto it = ctx->poly_cache.find(key);
+    if (it != ctx->poly_cache.end()) {
+        *out = it->second;
+        return NVTTB_OK;
+    }
+    PolyphaseTable t;
+    build_polyphase(f, (unsigned)src, (unsigned)dst, t);
+    PolyDev pd;
+    pd.window = t.window;
+    pd.length = t.length;
+    CK(cudaMalloc(&pd.weights, t.weights.size() * sizeof(float)));
+    CK(cudaMalloc(&pd.left, t.left.size() * sizeof(int)));
+    CK(cudaMemcpy(pd.weights, t.weights.data(), t.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.left, t.left.data(), t.left.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->poly_cache[key] = pd;
+    *out = pd;
+    return NVTTB_OK;
+}
+
+// src (sw x sh) -> dst (dw x dh), X pass into ctx->tmp_filter then Y pass (FloatImage::resize, FloatImage.cpp:761-808)
+static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const float *src, int sw, int sh, float *dst, int dw, int dh) {
+    PolyDev px, py;
+    int rc;
+    if ((rc = get_poly(ctx, f, sw, dw, &px)) != NVTTB_OK) return rc;
+    if ((rc = get_poly(ctx, f, sh, dh, &py)) != NVTTB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_filter, (size_t)dw * sh * 4 * sizeof(float))) != NVTTB_OK) return rc;
+    float *tmp = (float *)ctx->tmp_filter.p;
+    PolyphaseParams X{src, tmp, sw, sh, dw, sh, 4, px.window, px.weights, px.left, wrap};
+    k_polyphase_x<<<grid_for((size_t)dw * sh * 4, 256), 256, 0, ctx->stream>>>(X);
+    PolyphaseParams Y{tmp, dst, dw, sh, dw, dh, 4, py.window, py.weights, py.left, wrap};
+    k_polyphase_y<<<grid_for((size_t)dw * dh * 4, 256), 256, 0, ctx->stream>>>(Y);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+// Surface::buildNextMipmap semantics on raw device buffers.  Returns via *dw,*dh the new size.
+static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidth, float p0, float p1, int alphaMode, int wrap,
+                           const float *src, int sw, int sh, float *dst, int dw, int dh) {
+    if (mipmapFilter == MF_Box && filterWidth == 0.5f && alphaMode != AM_Transparency) {
+        BoxDownParams P{src, dst, sw, sh, dw, dh, 4};
+        k_box_down<<<grid_for((size_t)dw * dh * 4, 256), 256, 0, ctx->stream>>>(P);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return NVTTB_OK;
+    }
+    FilterDesc f;
+    f.kind = (mipmapFilter == MF_Box) ? Filter_Box : (mipmapFilter == MF_Triangle) ? Filter_Triangle : Filter_Kaiser;
+    f.width = filterWidth;
+    f.p0 = (f.kind == Filter_Kaiser) ? p0 : 0.0f;
+    f.p1 = (f.kind == Filter_Kaiser) ? p1 : 0.0f;
+    return resize_device(ctx, f, wrap, src, sw, sh, dst, dw, dh);
+}
+
+static void default_filter(int filter, float *width, float params[2]) {
+    params[0] = params[1] = 0.0f;
+    if (filter == RF_Box) *width = 0.5f;
+    else if (filter == RF_Triangle) *width = 1.0f;
+    else if (filter == RF_Kaiser) {
+        *width = 3.0f;
+        params[0] = 4.0f;
+        params[1] = 1.0f;
+    } else {
+        *width = 2.0f;
+        params[0] = 1.0f / 3.0f;
+        params[1] = 1.0f / 3.0f;
+    }
+}
+
+static bool nv_equal(float f0, float f1) {  // nv::equal, src/nvmath/nvmath.h:139-143
+    const float eps = 0.0001f;
+    float m = 1.0f;
+    if (fabsf(f0) > m) m = fabsf(f0);
+    if (fabsf(f1) > m) m = fabsf(f1);
+    return fabs(f0 - f1) <= eps * m;
+}
+
+static int gamma_device(NvttbContext *ctx, float *data, size_t pixels, bool toLinear, float gamma) {
+    if (nv_equal(gamma, 1.0f)) return NVTTB_OK;
+    GammaParams P;
+    P.data = data;
+    P.count = 3 * pixels;
+    if (gamma == 2.2f) {
+        P.mode = toLinear ? 0 : 1;
+        P.table = toLinear ? ctx->d_to_linear : ctx->d_to_gamma;
+        P.power = 0.0f;
+    } else {
+        P.mode = 2;
+        P.table = nullptr;
+        P.power = toLinear ? gamma : 1.0f / gamma;
+    }
+    k_gamma<<<grid_for(P.count, 256), 256, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+static size_t input_bpp(int inputFormat) {
+    switch (inputFormat) {
+    case 0: return 4;
+    case 1: return 8;
+    case 2: return 16;
+    case 3: return 4;
+    default: return 0;
+    }
+}
+
+// upload (if needed) + convert to planar fp32, optionally fusing toLinear(2.2)
+static int set_image_device(NvttbContext *ctx, int inputFormat, int w, int h, const void *data, int location, float *dst, bool fuseToLinear) {
+    const size_t bpp = input_bpp(inputFormat);
+    if (bpp == 0 || w <= 0 || h <= 0 || !data) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad input image");
+    const size_t bytes = (size_t)w * h * bpp;
+    const void *d_src = data;
+    if (location == NVTTB_HOST) {
+        int rc = ensure(ctx, ctx->in_stage, bytes);
+        if (rc != NVTTB_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->in_stage.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_src = ctx->in_stage.p;
+    }
+    SetImageParams P{d_src, dst, w * h, inputFormat, fuseToLinear ? ctx->d_to_linear : nullptr};
+    k_set_image<<<grid_for((size_t)w * h, 256), 256, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+extern "C" {
+
+int nvttb_encode_level(NvttbContext *ctx, const NvttbEncodeDesc *desc, const float *rgba, int rgba_location, void *out,
+                       int out_location, size_t out_capacity) {
+    if (!ctx || !desc || !rgba || !out) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int w = desc->width, h = desc->height;
+    const size_t size = nvttb_level_size(desc->format, w, h);
+    if (size == 0) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "unsupported format");
+    if (out_capacity < size) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
+    int rc;
+    const float *d_rgba = rgba;
+    if (rgba_location == NVTTB_HOST) {
+        const size_t bytes = (size_t)w * h * 4 * sizeof(float);
+        if ((rc = ensure(ctx, ctx->tmp_level, bytes)) != NVTTB_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->tmp_level.p, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_rgba = (const float *)ctx->tmp_level.p;
+    }
+    unsigned char *d_out = (unsigned char *)out;
+    if (out_location == NVTTB_HOST) {
+        if ((rc = ensure(ctx, ctx->out_dev, size)) != NVTTB_OK) return rc;
+        d_out = (unsigned char *)ctx->out_dev.p;
+    }
+    if ((rc = encode_device(ctx, desc, d_rgba, w, h, d_out)) != NVTTB_OK) return rc;
+    if (out_location == NVTTB_HOST) {
+        CK(cudaMemcpyAsync(out, d_out, size, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (rgba_location == NVTTB_HOST) {
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return NVTTB_OK;
+}
+
+// ---- surfaces ---------------------------------------------------------------------------------------------
+int nvttb_surface_create(NvttbContext *ctx, NvttbSurface **out) {
+    if (!ctx || !out) return NVTTB_ERR_INVALID_INPUT;
+    NvttbSurface *s = new NvttbSurface();
+    s->ctx = ctx;
+    *out = s;
+    return NVTTB_OK;
+}
+void nvttb_surface_destroy(NvttbSurface *s) {
+    if (!s) return;
+    if (s->buf.p) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+        cudaFree(s->buf.p);
+    }
+    delete s;
+}
+int nvttb_surface_clone(const NvttbSurface *s, NvttbSurface **out) {
+    if (!s || !out) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    NvttbSurface *c = new NvttbSurface();
+    c->ctx = ctx;
+    c->w = s->w;
+    c->h = s->h;
+    c->wrapMode = s->wrapMode;
+    c->alphaMode = s->alphaMode;
+    c->isNormalMap = s->isNormalMap;
+    if (s->buf.p && s->w > 0) {
+        const size_t bytes = (size_t)s->w * s->h * 16;
+        int rc = ensure(ctx, c->buf, bytes);
+        if (rc != NVTTB_OK) { delete c; return rc; }
+        cudaError_t e = cudaMemcpyAsync(c->buf.p, s->buf.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(c->buf.p); delete c; return fail(ctx, NVTTB_ERR_CUDA, "clone", e); }
+    }
+    *out = c;
+    return NVTTB_OK;
+}
+void nvttb_surface_set_wrap_mode(NvttbSurface *s, int m) { if (s) s->wrapMode = m; }
+void nvttb_surface_set_alpha_mode(NvttbSurface *s, int m) { if (s) s->alphaMode = m; }
+void nvttb_surface_set_normal_map(NvttbSurface *s, int b) { if (s) s->isNormalMap = b; }
+int nvttb_surface_width(const NvttbSurface *s) { return s ? s->w : 0; }
+int nvttb_surface_height(const NvttbSurface *s) { return s ? s->h : 0; }
+const float *nvttb_surface_device_data(const NvttbSurface *s) { return s ? (const float *)s->buf.p : nullptr; }
+
+int nvttb_surface_set_image(NvttbSurface *s, int inputFormat, int w, int h, const void *data, int location) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, s->buf, (size_t)w * h * 16);
+    if (rc != NVTTB_OK) return rc;
+    if ((rc = set_image_device(ctx, inputFormat, w, h, data, location, (float *)s->buf.p, false)) != NVTTB_OK) return rc;
+    s->w = w;
+    s->h = h;
+    if (location == NVTTB_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return NVTTB_OK;
+}
+
+int nvttb_surface_to_linear(NvttbSurface *s, float gamma) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    if (!s->buf.p || s->w == 0) return NVTTB_OK;
+    cudaSetDevice(s->ctx->device);
+    return gamma_device(s->ctx, (float *)s->buf.p, (size_t)s->w * s->h, true, gamma);
+}
+int nvttb_surface_to_gamma(NvttbSurface *s, float gamma) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    if (!s->buf.p || s->w == 0) return NVTTB_OK;
+    cudaSetDevice(s->ctx->device);
+    return gamma_device(s->ctx, (float *)s->buf.p, (size_t)s->w * s->h, false, gamma);
+}
+
+int nvttb_surface_build_next_mipmap(NvttbSurface *s, int mipmapFilter, int useParams, float filterWidth, const float *params, int *built) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (built) *built = 0;
+    if (!s->buf.p || (s->w == 1 && s->h == 1)) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    float fw, pr[2];
+    default_filter(mipmapFilter, &fw, pr);
+    if (useParams) {
+        fw = filterWidth;
+        if (params) { pr[0] = params[0]; pr[1] = params[1]; }
+    }
+    const int dw = s->w / 2 > 1 ? s->w / 2 : 1, dh = s->h / 2 > 1 ? s->h / 2 : 1;
+    DevBuf nb;
+    int rc = ensure(ctx, nb, (size_t)dw * dh * 16);
+    if (rc != NVTTB_OK) return rc;
+    rc = next_mip_device(ctx, mipmapFilter, fw, pr[0], pr[1], s->alphaMode, s->wrapMode, (const float *)s->buf.p, s->w, s->h, (float *)nb.p, dw, dh);
+    if (rc != NVTTB_OK) { cudaFree(nb.p); return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->buf.p);
+    s->buf = nb;
+    s->w = dw;
+    s->h = dh;
+    if (built) *built = 1;
+    return NVTTB_OK;
+}
+
+int nvttb_surface_resize(NvttbSurface *s, int w, int h, int resizeFilter, int useParams, float filterWidth, const float *params) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p || (w == s->w && h == s->h)) return NVTTB_OK;
+    if (w <= 0 || h <= 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad resize extent");
+    CK(cudaSetDevice(ctx->device));
+    float fw, pr[2];
+    default_filter(resizeFilter, &fw, pr);
+    if (useParams) {
+        fw = filterWidth;
+        if (params) { pr[0] = params[0]; pr[1] = params[1]; }
+    }
+    FilterDesc f;
+    f.kind = resizeFilter;
+    f.width = (resizeFilter == RF_Mitchell) ? 2.0f : fw;  // MitchellFilter() ignores filterWidth (Surface.cpp:1212-1216)
+    f.p0 = (resizeFilter == RF_Kaiser || resizeFilter == RF_Mitchell) ? pr[0] : 0.0f;
+    f.p1 = (resizeFilter == RF_Kaiser || resizeFilter == RF_Mitchell) ? pr[1] : 0.0f;
+    DevBuf nb;
+    int rc = ensure(ctx, nb, (size_t)w * h * 16);
+    if (rc != NVTTB_OK) return rc;
+    rc = resize_device(ctx, f, s->wrapMode, (const float *)s->buf.p, s->w, s->h, (float *)nb.p, w, h);
+    if (rc != NVTTB_OK) { cudaFree(nb.p); return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->buf.p);
+    s->buf = nb;
+    s->w = w;
+    s->h = h;
+    return NVTTB_OK;
+}
+
+static int scale_bias(NvttbSurface *s, float scale, float bias) {
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    ScaleBiasParams P{(float *)s->buf.p, (size_t)3 * s->w * s->h, scale, bias};
+    k_scale_bias<<<grid_for(P.count, 256), 256, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+int nvttb_surface_expand_normals(NvttbSurface *s) { return s ? scale_bias(s, 2.0f, -1.0f) : NVTTB_ERR_INVALID_INPUT; }
+int nvttb_surface_pack_normals(NvttbSurface *s) { return s ? scale_bias(s, 0.5f, 0.5f) : NVTTB_ERR_INVALID_INPUT; }
+int nvttb_surface_normalize_normal_map(NvttbSurface *s) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p || !s->isNormalMap) return NVTTB_OK;  // Surface::normalizeNormalMap is a no-op unless flagged (Surface.cpp:2810-2817)
+    CK(cudaSetDevice(ctx->device));
+    NormalizeParams P{(float *)s->buf.p, (size_t)s->w * s->h, 0};
+    k_normalize<<<grid_for(P.pixels, 256), 256, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+int nvttb_surface_to_grey_scale(NvttbSurface *s, float, float, float, float) {
+    return s ? fail(s->ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "toGreyScale not implemented yet") : NVTTB_ERR_INVALID_INPUT;
+}
+int nvttb_surface_to_normal_map(NvttbSurface *s, float, float, float, float) {
+    return s ? fail(s->ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "toNormalMap not implemented yet") : NVTTB_ERR_INVALID_INPUT;
+}
+
+int nvttb_surface_download(const NvttbSurface *s, float *out) {
+    if (!s || !out) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null surface");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, s->buf.p, (size_t)s->w * s->h * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NVTTB_OK;
+}
+
+int nvttb_surface_encode(NvttbSurface *s, const NvttbEncodeDesc *desc, void *out, int out_location, size_t out_capacity) {
+    if (!s || !desc || !out) return NVTTB_ERR_INVALID_INPUT;
+    if (!s->buf.p) return fail(s->ctx, NVTTB_ERR_INVALID_INPUT, "null surface");
+    NvttbEncodeDesc d = *desc;
+    d.width = s->w;
+    d.height = s->h;
+    d.alphaMode = s->alphaMode;
+    return nvttb_encode_level(s->ctx, &d, (const float *)s->buf.p, NVTTB_DEVICE, out, out_location, out_capacity);
+}
+
+// ---- whole pipeline -----------------------------------------------------------------------------------------
+int nvttb_process_mip_count(const NvttbProcessDesc *d) {
+    if (!d || d->width <= 0 || d->height <= 0) return 0;
+    int count = 1;
+    if (d->generateMipmaps) {
+        unsigned w = d->width, h = d->height;
+        while (w != 1 || h != 1) {
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+            count++;
+        }
+        if (d->maxLevel > 0 && d->maxLevel < count) count = d->maxLevel;
+    }
+    return count;
+}
+
+static size_t face_bytes(const NvttbProcessDesc *d) {
+    const int mips = nvttb_process_mip_count(d);
+    size_t total = 0;
+    int w = d->width, h = d->height;
+    for (int m = 0; m < mips; m++) {
+        total += nvttb_level_size(d->encode.format, w, h);
+        w = w / 2 > 1 ? w / 2 : 1;
+        h = h / 2 > 1 ? h / 2 : 1;
+    }
+    return total;
+}
+
+size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
+    if (!d) return 0;
+    return face_bytes(d) * (size_t)(d->faceCount > 0 ? d->faceCount : 1);
+}
+
+// Runs faces [f0,f1) and leaves their encoded chains in d_out (face-major, mip-minor).
+static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, int f0, int f1,
+                         unsigned char *d_out) {
+    const int mips = nvttb_process_mip_count(d);
+    const size_t fbytes = face_bytes(d);
+    const int W = d->width, H = d->height;
+    int rc;
+    if (d->convertToNormalMap) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "convertToNormalMap not implemented yet");
+    // ping-pong level buffers: A holds level m, B receives level m+1
+    DevBuf &A = ctx->lvlA, &B = ctx->lvlB;  // persistent scratch: no cudaMalloc/cudaFree per call
+    if ((rc = ensure(ctx, A, (size_t)W * H * 16)) != NVTTB_OK) return rc;
+    if (mips > 1) {
+        const int w1 = W / 2 > 1 ? W / 2 : 1, h1 = H / 2 > 1 ? H / 2 : 1;
+        if ((rc = ensure(ctx, B, (size_t)w1 * h1 * 16)) != NVTTB_OK) return rc;
+    }
+    auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); };
+    const bool colour = !d->isNormalMap;
+    const bool linFast = colour && d->inputGamma == 2.2f;
+    const bool gamFast = colour && d->outputGamma == 2.2f;
+    const bool gamSlow = colour && !gamFast && !nv_equal(d->outputGamma, 1.0f);
+    for (int f = f0; f < f1; f++) {
+        unsigned char *out = d_out + (size_t)(f - f0) * fbytes;
+        // setImage (+ toLinear)
+        if ((rc = set_image_device(ctx, d->inputFormat, W, H, images[f], loc, (float *)A.p, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+        if (colour && !linFast) {
+            if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
+        }
+        float *cur = (float *)A.p, *nxt = (float *)B.p;
+        int w = W, h = H;
+        for (int m = 0; m < mips; m++) {
+            if (m > 0) {
+                const int dw = w / 2 > 1 ? w / 2 : 1, dh = h / 2 > 1 ? h / 2 : 1;
+                float fw, pr[2];
+                default_filter(d->mipmapFilter, &fw, pr);
+                if (d->mipmapFilter == MF_Kaiser) {
+                    fw = d->kaiserWidth;
+                    pr[0] = d->kaiserAlpha;
+                    pr[1] = d->kaiserStretch;
+                }
+                if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh)) != NVTTB_OK) { cleanup(); return rc; }
+                float *t = cur; cur = nxt; nxt = t;
+                w = dw;
+                h = dh;
+                if (d->isNormalMap && d->normalizeMipmaps) {
+                    NormalizeParams P{cur, (size_t)w * h, 1};
+                    k_normalize<<<grid_for(P.pixels, 256), 256, 0, ctx->stream>>>(P);
+                    ctx->launches++;
+                }
+            }
+            // tmp = img; tmp.toGamma(outputGamma); compress(tmp)
+            NvttbEncodeDesc e = d->encode;
+            e.width = w;
+            e.height = h;
+            e.alphaMode = d->alphaMode;
+            e.applyToGamma = gamFast ? 1 : 0;
+            const float *src = cur;
+            if (gamSlow) {
+                if ((rc = ensure(ctx, ctx->tmp_level, (size_t)w * h * 16)) != NVTTB_OK) { cleanup(); return rc; }
+                cudaMemcpyAsync(ctx->tmp_level.p, cur, (size_t)w * h * 16, cudaMemcpyDeviceToDevice, ctx->stream);
+                if ((rc = gamma_device(ctx, (float *)ctx->tmp_level.p, (size_t)w * h, false, d->outputGamma)) != NVTTB_OK) { cleanup(); return rc; }
+                src = (const float *)ctx->tmp_level.p;
+            }
+            if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
+            out += nvttb_level_size(e.format, w, h);
+        }
+        // the level buffers are reused by the next face: same stream, so ordering is implicit
+    }
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+static int check_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int *f0, int *f1) {
+    if (!ctx || !d || !images) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null argument");
+    if (d->width <= 0 || d->height <= 0 || d->faceCount <= 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad extent");
+    if (!nvttb_format_supported(d->encode.format, d->encode.quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
+    *f0 = 0;
+    *f1 = d->faceCount;
+    if (d->lastFace > d->firstFace) {
+        *f0 = d->firstFace;
+        *f1 = d->lastFace < d->faceCount ? d->lastFace : d->faceCount;
+    }
+    for (int f = *f0; f < *f1; f++)
+        if (!images[f]) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "missing face image");
+    return NVTTB_OK;
+}
+
+int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, void *out_device,
+                            size_t out_capacity, size_t *written) {
+    int f0, f1, rc;
+    if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t total = face_bytes(d) * (size_t)(f1 - f0);
+    if (!out_device || out_capacity < total) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
+    if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)out_device)) != NVTTB_OK) return rc;
+    if (written) *written = total;
+    return NVTTB_OK;
+}
+
+int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, NvttbEmitFn emit, void *user) {
+    int f0, f1, rc;
+    if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
+    if (!emit) return fail(ctx, NVTTB_ERR_FILE_OPEN, "no output handler");
+    CK(cudaSetDevice(ctx->device));
+    const size_t fbytes = face_bytes(d);
+    const size_t total = fbytes * (size_t)(f1 - f0);
+    if ((rc = ensure(ctx, ctx->out_dev, total)) != NVTTB_OK) return rc;
+    if ((rc = ensure_pinned(ctx, total)) != NVTTB_OK) return rc;
+    if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)ctx->out_dev.p)) != NVTTB_OK) return rc;
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->out_dev.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int mips = nvttb_process_mip_count(d);
+    const unsigned char *p = (const unsigned char *)ctx->h_out;
+    for (int f = f0; f < f1; f++) {
+        int w = d->width, h = d->height;
+        for (int m = 0; m < mips; m++) {
+            const size_t sz = nvttb_level_size(d->encode.format, w, h);
+            if (!emit(user, f, m, w, h, 1, p, sz)) return fail(ctx, NVTTB_ERR_FILE_WRITE, "emit callback asked to stop");
+            p += sz;
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+        }
+    }
+    return NVTTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the unmodified reference built with the pinned
+parity flags (oracle/_ref) on the same seeded inputs.  Bar: bit-exact for every integer / block output and for the
+fp32 image ops (they are implemented operation-for-operation without FMA contraction)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 64), (128, 32), (37, 22), (4, 4), (3, 2), (1, 1), (5, 9), (260, 4)]
+
+
+def _images(nvtt, w, h):
+    s = nvtt.synth
+    yield "photo", s.planar_from_bgra8(s.photo_bgra8(w, h, seed=1234, alpha=True))
+    yield "normal", s.planar_from_bgra8(s.normal_bgra8(w, h, seed=7))
+    yield "adversarial", s.planar_from_bgra8(s.adversarial_bgra8(w, h, seed=5))
+    rng = np.random.default_rng(w * 1000 + h)
+    yield "float_oob", (rng.random((4, h, w), dtype=np.float32) * 1.5 - 0.25)  # exercises the clamp in the quantiser
+
+
+def _assert_blocks_equal(got, want, bs, what):
+    assert got.shape == want.shape, what
+    bad = (got.reshape(-1, bs) != want.reshape(-1, bs)).any(1)
+    if bad.any():
+        i = int(np.nonzero(bad)[0][0])
+        raise AssertionError("%s: %d/%d blocks differ; first block %d got %s want %s"
+                             % (what, int(bad.sum()), bad.size, i, got.reshape(-1, bs)[i], want.reshape(-1, bs)[i]))
+
+
+@pytest.mark.parametrize("fmt_name,quality", [("BC4", 0), ("BC4", 1), ("BC5", 0), ("BC5", 1), ("BC3", 1), ("BC3", 2)])
+def test_level_encode_bit_exact(nvtt, ref, ctx, fmt_name, quality):
+    fmt = getattr(nvtt, "Format_" + fmt_name)
+    bs = 8 if fmt_name == "BC4" else 16
+    for (w, h) in SIZES:
+        for name, img in _images(nvtt, w, h):
+            got = ctx.encode_level(fmt, quality, img)
+            want = ref.compress_level(fmt, quality, img)
+            _assert_blocks_equal(got, want, bs, "%s q%d %s %dx%d" % (fmt_name, quality, name, w, h))
+
+
+def test_bc3_weights_and_transparency(nvtt, ref, ctx):
+    img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(256, 256, seed=3, alpha=True))
+    for cw in [(1, 1, 1, 1), (0.3, 0.59, 0.11, 1.0), (1, 0, 0, 1)]:
+        for am in (nvtt.AlphaMode_None, nvtt.AlphaMode_Transparency):
+            got = ctx.encode_level(nvtt.Format_BC3, 1, img, alpha_mode=am, color_weights=cw)
+            want = ref.compress_level(ref.Format_BC3, 1, img, alpha_mode=am, color_weights=cw)
+            _assert_blocks_equal(got, want, 16, "BC3 weights %s alphaMode %d" % (cw, am))
+
+
+def test_surface_ops_bit_exact(nvtt, ref, ctx):
+    rng = np.random.default_rng(0)
+    for (w, h) in [(64, 64), (37, 22), (33, 16), (16, 33), (7, 1), (1, 8), (2, 2), (5, 5), (256, 128)]:
+        im8 = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        for wrap in (0, 1, 2):
+            for filt, params in [(0, None), (1, None), (2, None), (2, (3.0, 4.0, 1.0)), (2, (2.0, 3.0, 1.5))]:
+                a = ref.Surface(wrap=wrap)
+                b = nvtt.Surface(ctx, wrap=wrap)
+                a.set_image(0, w, h, im8)
+                b.set_image(0, w, h, im8)
+                assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "setImage"
+                a.to_linear(2.2)
+                b.to_linear(2.2)
+                assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "toLinear"
+                level = 0
+                while True:
+                    ra = a.build_next_mipmap(filt, params)
+                    rb = b.build_next_mipmap(filt, params)
+                    assert ra == rb
+                    if not ra:
+                        break
+                    level += 1
+                    ga, gb = a.get(), b.get()
+                    assert ga.shape == gb.shape
+                    assert np.array_equal(ga.view(np.uint32), gb.view(np.uint32)), \
+                        "mip %d filter %d wrap %d %dx%d maxdiff %g" % (level, filt, wrap, w, h, np.abs(ga - gb).max())
+                a.to_gamma(2.2)
+                b.to_gamma(2.2)
+                assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "toGamma"
+
+
+def test_surface_misc_bit_exact(nvtt, ref, ctx):
+    rng = np.random.default_rng(1)
+    w, h = 96, 40
+    # fp16 / fp32 / R32F inputs
+    for fmt, data in [(1, rng.integers(0, 65536, (h, w, 4)).astype(np.uint16)),
+                      (2, rng.normal(0, 1, (h, w, 4)).astype(np.float32)),
+                      (3, rng.normal(0, 1, (h, w)).astype(np.float32))]:
+        a = ref.Surface()
+        b = nvtt.Surface(ctx)
+        a.set_image(fmt, w, h, data)
+        b.set_image(fmt, w, h, data)
+        assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "setImage fmt %d" % fmt
+    # normal-map renormalisation
+    im8 = nvtt.synth.normal_bgra8(w, h)
+    a = ref.Surface(normal_map=True)
+    b = nvtt.Surface(ctx, normal_map=True)
+    a.set_image(0, w, h, im8)
+    b.set_image(0, w, h, im8)
+    for op in ("expand_normals", "normalize_normal_map", "pack_normals"):
+        getattr(a, op)()
+        getattr(b, op)()
+        assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), op
+    # resize with every filter
+    for filt in (0, 1, 2, 3):
+        a = ref.Surface(wrap=1)
+        b = nvtt.Surface(ctx, wrap=1)
+        a.set_image(0, w, h, im8)
+        b.set_image(0, w, h, im8)
+        a.resize(50, 30, filt)
+        b.resize(50, 30, filt)
+        assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "resize filter %d" % filt
+    # non-2.2 gamma goes through powf: tolerance 1e-5 relative (libm vs CUDA powf), stated by north_star
+    a = ref.Surface()
+    b = nvtt.Surface(ctx)
+    a.set_image(0, w, h, im8)
+    b.set_image(0, w, h, im8)
+    a.to_linear(1.8)
+    b.to_linear(1.8)
+    np.testing.assert_allclose(b.get(), a.get(), rtol=1e-5, atol=1e-7)
+
+
+PIPE_CASES = [
+    # (name, synth, fmt, quality, kwargs)
+    ("bc3_kaiser_alpha", "alpha", "BC3", 1, dict(mip_filter=2, wrap=2)),
+    ("bc3_kaiser_clamp", "alpha", "BC3", 1, dict(mip_filter=2, wrap=0)),
+    ("bc5_normal_kaiser", "normal", "BC5", 1, dict(mip_filter=2, wrap=2, normal_map=True)),
+    ("bc5_normal_box", "normal", "BC5", 1, dict(mip_filter=0, wrap=1, normal_map=True)),
+    ("bc4_box", "photo", "BC4", 1, dict(mip_filter=0)),
+    ("bc3_triangle_transparency", "alpha", "BC3", 1, dict(mip_filter=1, alpha_mode=1)),
+    ("bc3_box_transparency", "alpha", "BC3", 2, dict(mip_filter=0, alpha_mode=1)),
+    ("bc3_no_mips_gamma1", "alpha", "BC3", 1, dict(mipmaps=False, gamma=(1.0, 1.0))),
+    ("bc3_maxlevel3", "photo", "BC3", 1, dict(max_level=3)),
+]
+
+
+def _synth(nvtt, kind, w, h):
+    s = nvtt.synth
+    if kind == "alpha":
+        return s.photo_bgra8(w, h, seed=1234, alpha=True)
+    if kind == "photo":
+        return s.photo_bgra8(w, h, seed=99)
+    return s.normal_bgra8(w, h)
+
+
+@pytest.mark.parametrize("case", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_pipeline_bit_exact(nvtt, ref, ctx, case):
+    name, kind, fmt_name, quality, kw = case
+    fmt = getattr(nvtt, "Format_" + fmt_name)
+    bs = 8 if fmt_name == "BC4" else 16
+    for (w, h) in [(256, 256), (100, 60), (31, 17)]:
+        img = _synth(nvtt, kind, w, h)
+        d = nvtt.make_process_desc(nvtt.InputFormat_BGRA_8UB, w, h, fmt, quality, **kw)
+        got = ctx.process_bytes([img], d)
+        want = ref.process([img], 0, w, h, fmt, quality, **kw)
+        _assert_blocks_equal(got, want, bs, "%s %dx%d" % (name, w, h))
+
+
+def test_pipeline_faces_and_emit_order(nvtt, ref, ctx):
+    w = h = 64
+    faces = [nvtt.synth.photo_bgra8(w, h, seed=10 + f, alpha=True) for f in range(6)]
+    d = nvtt.make_process_desc(0, w, h, nvtt.Format_BC3, 1, faces=6, mip_filter=0)
+    out = ctx.process(faces, d)
+    assert [(f, m) for (f, m, _, _, _) in out] == [(f, m) for f in range(6) for m in range(7)]  # face-major, mip-minor
+    got = np.concatenate([b for *_, b in out])
+    want = ref.process(faces, 0, w, h, ref.Format_BC3, 1, mip_filter=0, texture_type=ref.TextureType_Cube)
+    assert np.array_equal(got, want)
+    # face sharding used by the multi-GPU path: faces [2,4) alone give the same bytes as that slice of the whole
+    d2 = nvtt.make_process_desc(0, w, h, nvtt.Format_BC3, 1, faces=6, mip_filter=0, first_face=2, last_face=4)
+    part = ctx.process_bytes(faces, d2)
+    per_face = got.size // 6
+    assert np.array_equal(part, got[2 * per_face:4 * per_face])
+
+
+def test_config2_full_size_properties(nvtt, ref, ctx):
+    """BASELINE config 2 at full size (4096^2, Kaiser mips): checked through size-independent properties —
+    (a) determinism, (b) every level's size, (c) block encoding is local, so random 64x64 crops of level 0 and the
+    whole tail of the chain (levels <= 256^2, produced from the GPU's own fp32 mips) must match the reference."""
+    w = h = 4096
+    img = nvtt.synth.photo_bgra8(w, h, seed=1234, alpha=True)
+    kw = dict(mip_filter=2, wrap=2)
+    d = nvtt.make_process_desc(0, w, h, nvtt.Format_BC3, 1, **kw)
+    out1 = ctx.process([img], d)
+    out2 = ctx.process([img], d)
+    assert len(out1) == 13
+    for (f, m, lw, lh, b), (_, _, _, _, b2) in zip(out1, out2):
+        assert (lw, lh) == (max(1, w >> m), max(1, h >> m))
+        assert b.size == ((lw + 3) // 4) * ((lh + 3) // 4) * 16
+        assert np.array_equal(b, b2), "non-deterministic level %d" % m
+    # (c1) level-0 crops: toLinear->toGamma is per-texel, so a crop through the reference pipeline (no mips) must
+    # equal the corresponding blocks of our level 0.
+    lvl0 = out1[0][4].reshape(h // 4, w // 4, 16)
+    rng = np.random.default_rng(0)
+    for _ in range(8):
+        x0 = int(rng.integers(0, w // 64)) * 64
+        y0 = int(rng.integers(0, h // 64)) * 64
+        crop = np.ascontiguousarray(img[y0:y0 + 64, x0:x0 + 64])
+        want = ref.process([crop], 0, 64, 64, ref.Format_BC3, 1, mipmaps=False).reshape(16, 16, 16)
+        assert np.array_equal(lvl0[y0 // 4:y0 // 4 + 16, x0 // 4:x0 // 4 + 16], want), "crop %d,%d" % (x0, y0)
+    # (c2) the chain below 512^2: rebuild the linear fp32 level on the GPU with Surface ops, hand that exact level
+    # to the reference (RGBA32F input, gamma in=1.0) and let it produce the remaining levels.
+    s = nvtt.Surface(ctx, wrap=2)
+    s.set_image(0, w, h, img)
+    s.to_linear(2.2)
+    for _ in range(3):
+        assert s.build_next_mipmap(2, (3.0, 4.0, 1.0))
+    lin = s.get()  # 512 x 512 linear
+    il = np.ascontiguousarray(lin.transpose(1, 2, 0))
+    want_tail = ref.process([il], ref.InputFormat_RGBA_32F, 512, 512, ref.Format_BC3, 1, gamma=(1.0, 2.2), **kw)
+    got_tail = np.concatenate([b for (_, m, _, _, b) in out1 if m >= 3])
+    assert np.array_equal(got_tail, want_tail)
