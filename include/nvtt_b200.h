@@ -59,6 +59,20 @@ NVTTB_API int nvttb_synchronize(NvttbContext *ctx);
 /* The context's cudaStream_t (as void*), so a caller can record CUDA events on the launching stream. */
 NVTTB_API void *nvttb_stream(NvttbContext *ctx);
 
+/* Device-side timing on the context's stream (CUDA events), for bench.py: start / stop+elapsed in ms. */
+NVTTB_API int nvttb_timer_start(NvttbContext *ctx);
+NVTTB_API int nvttb_timer_stop(NvttbContext *ctx, float *elapsed_ms);
+/* Per-kernel CUDA-event timing of everything launched between begin and end (bench.py's roofline leg).
+ * units = texels the launches covered.  Replaces nothing in the reference (it only has nv::Timer, src/nvcore/Timer.cpp). */
+typedef struct NvttbKernelStat {
+    const char *name;
+    int launches;
+    double total_ms, max_ms; /* summed / longest single launch */
+    double total_units, max_units; /* texels covered by all launches / by the longest one */
+} NvttbKernelStat;
+NVTTB_API int nvttb_profile_begin(NvttbContext *ctx);
+NVTTB_API int nvttb_profile_end(NvttbContext *ctx, NvttbKernelStat *stats, int max_stats, int *count);
+
 /* ---- one mip level: the nv::CompressorInterface::compress seam ------------------------------------------ */
 /* Replaces Compressor::Private::compress(AlphaMode,w,h,d,face,mip,const float*,...) + chooseCpuCompressor
  * (src/nvtt/Context.cpp:486-516,1038-1163; src/nvtt/Compressor.h:34-38). */

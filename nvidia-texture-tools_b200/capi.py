@@ -45,11 +45,16 @@ class ProcessDesc(C.Structure):
                 ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int)]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_int), ("total_ms", C.c_double), ("max_ms", C.c_double),
+                ("total_units", C.c_double), ("max_units", C.c_double)]
+
+
 EMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t)
 
 EXPORTS = [
     "nvttb_device_count", "nvttb_context_create", "nvttb_context_destroy", "nvttb_last_error", "nvttb_launch_count",
-    "nvttb_synchronize", "nvttb_stream", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level",
+    "nvttb_synchronize", "nvttb_stream", "nvttb_timer_start", "nvttb_timer_stop", "nvttb_profile_begin", "nvttb_profile_end", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level",
     "nvttb_surface_create", "nvttb_surface_destroy", "nvttb_surface_clone", "nvttb_surface_set_wrap_mode",
     "nvttb_surface_set_alpha_mode", "nvttb_surface_set_normal_map", "nvttb_surface_width", "nvttb_surface_height",
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
@@ -80,6 +85,10 @@ def lib():
     L.nvttb_synchronize.argtypes = [vp]
     L.nvttb_stream.argtypes = [vp]
     L.nvttb_stream.restype = vp
+    L.nvttb_timer_start.argtypes = [vp]
+    L.nvttb_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.nvttb_profile_begin.argtypes = [vp]
+    L.nvttb_profile_end.argtypes = [vp, C.POINTER(KernelStat), ci, C.POINTER(ci)]
     L.nvttb_level_size.argtypes = [ci, ci, ci]
     L.nvttb_level_size.restype = sz
     L.nvttb_format_supported.argtypes = [ci, ci]
@@ -171,6 +180,24 @@ class Context:
     @property
     def stream(self):
         return self.L.nvttb_stream(self.h)
+
+    def timer_start(self):
+        self._ck(self.L.nvttb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.L.nvttb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_begin(self):
+        self._ck(self.L.nvttb_profile_begin(self.h))
+
+    def profile_end(self):
+        st = (KernelStat * 16)()
+        n = C.c_int(0)
+        self._ck(self.L.nvttb_profile_end(self.h, st, 16, C.byref(n)))
+        return {st[i].name.decode(): dict(launches=st[i].launches, total_ms=st[i].total_ms, max_ms=st[i].max_ms,
+                                          total_units=st[i].total_units, max_units=st[i].max_units) for i in range(n.value)}
 
     def synchronize(self):
         self._ck(self.L.nvttb_synchronize(self.h))

@@ -36,8 +36,20 @@ struct PolyDev {
     int *left = nullptr;
 };
 
+enum { K_ALPHA = 0, K_BC3_COLOR, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_bc3_color", "k_set_image", "k_gamma", "k_box_down",
+                                                  "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
+struct ProfRec {
+    int kid;
+    cudaEvent_t a, b;
+    double units;  // pixels (or texels) the launch processed
+};
+
 struct NvttbContext {
     int device = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
@@ -74,6 +86,25 @@ static int fail(NvttbContext *c, int code, const char *what, cudaError_t e = cud
     do {                                                                \
         cudaError_t _e = (call);                                        \
         if (_e != cudaSuccess) return fail(ctx, NVTTB_ERR_CUDA, #call, _e); \
+    } while (0)
+
+// Every kernel launch goes through this: counts it and, while profiling, brackets it with CUDA events on the stream.
+#define NVB_LAUNCH(ctx, kid_, units_, KFN, grid, block, ...)                           \
+    do {                                                                               \
+        ProfRec _r;                                                                    \
+        if ((ctx)->profiling) {                                                        \
+            _r.kid = (kid_);                                                           \
+            _r.units = (double)(units_);                                               \
+            cudaEventCreate(&_r.a);                                                    \
+            cudaEventCreate(&_r.b);                                                    \
+            cudaEventRecord(_r.a, (ctx)->stream);                                      \
+        }                                                                              \
+        KFN<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                       \
+        if ((ctx)->profiling) {                                                        \
+            cudaEventRecord(_r.b, (ctx)->stream);                                      \
+            (ctx)->prof.push_back(_r);                                                 \
+        }                                                                              \
+        (ctx)->launches++;                                                             \
     } while (0)
 
 static int ensure(NvttbContext *ctx, DevBuf &b, size_t bytes) {
@@ -196,6 +227,68 @@ int nvttb_synchronize(NvttbContext *ctx) {
     return NVTTB_OK;
 }
 
+int nvttb_timer_start(NvttbContext *ctx) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    if (!ctx->t0) {
+        CK(cudaEventCreate(&ctx->t0));
+        CK(cudaEventCreate(&ctx->t1));
+    }
+    CK(cudaEventRecord(ctx->t0, ctx->stream));
+    return NVTTB_OK;
+}
+int nvttb_timer_stop(NvttbContext *ctx, float *ms) {
+    if (!ctx || !ms || !ctx->t0) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaEventRecord(ctx->t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return NVTTB_OK;
+}
+int nvttb_profile_begin(NvttbContext *ctx) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return NVTTB_OK;
+}
+int nvttb_profile_end(NvttbContext *ctx, NvttbKernelStat *stats, int max_stats, int *count) {
+    if (!ctx || !stats || !count) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = false;
+    NvttbKernelStat acc[K_COUNT];
+    for (int k = 0; k < K_COUNT; k++) {
+        acc[k].name = kKernelNames[k];
+        acc[k].launches = 0;
+        acc[k].total_ms = 0.0;
+        acc[k].max_ms = 0.0;
+        acc[k].max_units = 0.0;
+        acc[k].total_units = 0.0;
+    }
+    for (auto &r : ctx->prof) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        NvttbKernelStat &a = acc[r.kid];
+        a.launches++;
+        a.total_ms += ms;
+        a.total_units += r.units;
+        if (ms > a.max_ms) {
+            a.max_ms = ms;
+            a.max_units = r.units;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    int n = 0;
+    for (int k = 0; k < K_COUNT && n < max_stats; k++)
+        if (acc[k].launches) stats[n++] = acc[k];
+    *count = n;
+    return NVTTB_OK;
+}
+
 size_t nvttb_level_size(int format, int w, int h) {
     if (w <= 0 || h <= 0) return 0;
     return (size_t)((w + 3) / 4) * ((h + 3) / 4) * block_bytes(format);
@@ -234,8 +327,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.out_stride = stride;
         P.out_offset = offset;
         P.mode = 0;
-        k_alpha_blocks<<<grid_for(nb, 128), 128, 0, ctx->stream>>>(P);
-        ctx->launches++;
+        NVB_LAUNCH(ctx, K_ALPHA, (double)w * h, k_alpha_blocks, grid_for(nb, 128), 128, P);
     };
     if (d->format == F_BC4) {
         alpha(0, 8, 0);
@@ -257,8 +349,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.cand_off = ctx->d_cand_off;
         P.omatch5 = ctx->d_om5;
         P.omatch6 = ctx->d_om6;
-        k_bc3_color<<<(nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, 0, ctx->stream>>>(P);
-        ctx->launches++;
+        NVB_LAUNCH(ctx, K_BC3_COLOR, (double)w * h, k_bc3_color, (nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, P);
     }
     CK(cudaGetLastError());
     return NVTTB_OK;
@@ -299,10 +390,9 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
     if ((rc = ensure(ctx, ctx->tmp_filter, (size_t)dw * sh * 4 * sizeof(float))) != NVTTB_OK) return rc;
     float *tmp = (float *)ctx->tmp_filter.p;
     PolyphaseParams X{src, tmp, sw, sh, dw, sh, 4, px.window, px.weights, px.left, wrap};
-    k_polyphase_x<<<grid_for((size_t)dw * sh * 4, 256), 256, 0, ctx->stream>>>(X);
+    NVB_LAUNCH(ctx, K_POLY_X, (double)dw * sh, k_polyphase_x, grid_for((size_t)dw * sh * 4, 256), 256, X);
     PolyphaseParams Y{tmp, dst, dw, sh, dw, dh, 4, py.window, py.weights, py.left, wrap};
-    k_polyphase_y<<<grid_for((size_t)dw * dh * 4, 256), 256, 0, ctx->stream>>>(Y);
-    ctx->launches += 2;
+    NVB_LAUNCH(ctx, K_POLY_Y, (double)dw * dh, k_polyphase_y, grid_for((size_t)dw * dh * 4, 256), 256, Y);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
@@ -312,8 +402,7 @@ static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidt
                            const float *src, int sw, int sh, float *dst, int dw, int dh) {
     if (mipmapFilter == MF_Box && filterWidth == 0.5f && alphaMode != AM_Transparency) {
         BoxDownParams P{src, dst, sw, sh, dw, dh, 4};
-        k_box_down<<<grid_for((size_t)dw * dh * 4, 256), 256, 0, ctx->stream>>>(P);
-        ctx->launches++;
+        NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down, grid_for((size_t)dw * dh * 4, 256), 256, P);
         CK(cudaGetLastError());
         return NVTTB_OK;
     }
@@ -362,8 +451,7 @@ static int gamma_device(NvttbContext *ctx, float *data, size_t pixels, bool toLi
         P.table = nullptr;
         P.power = toLinear ? gamma : 1.0f / gamma;
     }
-    k_gamma<<<grid_for(P.count, 256), 256, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    NVB_LAUNCH(ctx, K_GAMMA, (double)pixels, k_gamma, grid_for(P.count, 256), 256, P);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
@@ -391,8 +479,7 @@ static int set_image_device(NvttbContext *ctx, int inputFormat, int w, int h, co
         d_src = ctx->in_stage.p;
     }
     SetImageParams P{d_src, dst, w * h, inputFormat, fuseToLinear ? ctx->d_to_linear : nullptr};
-    k_set_image<<<grid_for((size_t)w * h, 256), 256, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    NVB_LAUNCH(ctx, K_SET_IMAGE, (double)w * h, k_set_image, grid_for((size_t)w * h, 256), 256, P);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
@@ -562,8 +649,7 @@ static int scale_bias(NvttbSurface *s, float scale, float bias) {
     if (!s->buf.p) return NVTTB_OK;
     CK(cudaSetDevice(ctx->device));
     ScaleBiasParams P{(float *)s->buf.p, (size_t)3 * s->w * s->h, scale, bias};
-    k_scale_bias<<<grid_for(P.count, 256), 256, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    NVB_LAUNCH(ctx, K_SCALE_BIAS, (double)s->w * s->h, k_scale_bias, grid_for(P.count, 256), 256, P);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
@@ -575,8 +661,7 @@ int nvttb_surface_normalize_normal_map(NvttbSurface *s) {
     if (!s->buf.p || !s->isNormalMap) return NVTTB_OK;  // Surface::normalizeNormalMap is a no-op unless flagged (Surface.cpp:2810-2817)
     CK(cudaSetDevice(ctx->device));
     NormalizeParams P{(float *)s->buf.p, (size_t)s->w * s->h, 0};
-    k_normalize<<<grid_for(P.pixels, 256), 256, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
@@ -685,8 +770,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 h = dh;
                 if (d->isNormalMap && d->normalizeMipmaps) {
                     NormalizeParams P{cur, (size_t)w * h, 1};
-                    k_normalize<<<grid_for(P.pixels, 256), 256, 0, ctx->stream>>>(P);
-                    ctx->launches++;
+                    NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
                 }
             }
             // tmp = img; tmp.toGamma(outputGamma); compress(tmp)
