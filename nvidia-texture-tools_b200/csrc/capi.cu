@@ -6,6 +6,7 @@
 #include "host_tables.h"
 #include "kernels/bc_alpha.cuh"
 #include "kernels/bc3_color.cuh"
+#include "kernels/bc1_icbc.cuh"
 #include "kernels/image_ops.cuh"
 
 #include <cuda_runtime.h>
@@ -36,8 +37,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_BC3_COLOR, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_bc3_color", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_BC3_COLOR, K_BC1, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_bc3_color", "k_bc1_icbc", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
 struct ProfRec {
     int kid;
@@ -57,6 +58,12 @@ struct NvttbContext {
     unsigned short *d_cand = nullptr;
     int *d_cand_off = nullptr;
     unsigned char *d_om5 = nullptr, *d_om6 = nullptr;
+    // ICBC tables: [four splits | three splits] u16, [four_total | three_total] int, [mid5 | mid6] float, [match5 | match6] u8
+    unsigned short *d_icbc_splits = nullptr;
+    int *d_icbc_totals = nullptr;
+    float *d_icbc_mid = nullptr;
+    unsigned char *d_icbc_match = nullptr;
+    int icbc_four_count = 0;
     DevBuf in_stage, tmp_filter, tmp_level, out_dev, lvlA, lvlB;
     void *h_out = nullptr;  // pinned
     size_t h_out_cap = 0;
@@ -183,6 +190,27 @@ int nvttb_context_create(int device, NvttbContext **out) {
     if ((e = cudaMalloc(&ctx->d_cand_off, sizeof(off))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_om5, 512)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_om6, 512)) != cudaSuccess) return bail("cudaMalloc", e);
+    {
+        std::vector<uint16_t> four, three;
+        int totals[32];
+        float mid[96];
+        uint8_t match[1024];
+        build_icbc_splits(four, totals, three, totals + 16);
+        build_icbc_midpoints(mid, mid + 32);
+        build_icbc_match(match, 32);
+        build_icbc_match(match + 512, 64);
+        ctx->icbc_four_count = (int)four.size();
+        std::vector<uint16_t> all(four);
+        all.insert(all.end(), three.begin(), three.end());
+        if ((e = cudaMalloc(&ctx->d_icbc_splits, all.size() * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_icbc_totals, sizeof(totals))) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_icbc_mid, sizeof(mid))) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_icbc_match, sizeof(match))) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemcpy(ctx->d_icbc_splits, all.data(), all.size() * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_icbc_totals, totals, sizeof(totals), cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_icbc_mid, mid, sizeof(mid), cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_icbc_match, match, sizeof(match), cudaMemcpyHostToDevice);
+    }
     cudaMemcpy(ctx->d_to_gamma, tg, sizeof(tg), cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_to_linear, tl, sizeof(tl), cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_cand, cand.data(), cand.size() * 2, cudaMemcpyHostToDevice);
@@ -203,6 +231,10 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     cudaFree(ctx->d_cand_off);
     cudaFree(ctx->d_om5);
     cudaFree(ctx->d_om6);
+    cudaFree(ctx->d_icbc_splits);
+    cudaFree(ctx->d_icbc_totals);
+    cudaFree(ctx->d_icbc_mid);
+    cudaFree(ctx->d_icbc_match);
     cudaFree(ctx->in_stage.p);
     cudaFree(ctx->tmp_filter.p);
     cudaFree(ctx->tmp_level.p);
@@ -299,6 +331,8 @@ int nvttb_format_supported(int format, int quality) {
     case F_BC4:
     case F_BC5:
         return quality == Q_Fastest || quality == Q_Normal;
+    case F_DXT1:
+        return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5:
         return quality == Q_Normal || quality == Q_Production;
     default:
@@ -329,7 +363,28 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.mode = 0;
         NVB_LAUNCH(ctx, K_ALPHA, (double)w * h, k_alpha_blocks, grid_for(nb, 128), 128, P);
     };
-    if (d->format == F_BC4) {
+    if (d->format == F_DXT1) {
+        // CompressorDXT1 -> ICBC: Fastest -> Level 1, Production -> Level 9, Normal and Highest -> Level 8 (BlockCompressor.cpp:211-217)
+        Bc1Params P;
+        P.lv = lv;
+        P.out = d_out;
+        P.out_stride = 8;
+        P.out_offset = 0;
+        P.level = (d->quality == Q_Fastest) ? 1 : (d->quality == Q_Production) ? 9 : 8;
+        P.transparency = (d->alphaMode == AM_Transparency);
+        P.cw[0] = d->colorWeights[0];
+        P.cw[1] = d->colorWeights[1];
+        P.cw[2] = d->colorWeights[2];
+        P.four = ctx->d_icbc_splits;
+        P.three = ctx->d_icbc_splits + ctx->icbc_four_count;
+        P.four_total = ctx->d_icbc_totals;
+        P.three_total = ctx->d_icbc_totals + 16;
+        P.midpoints5 = ctx->d_icbc_mid;
+        P.midpoints6 = ctx->d_icbc_mid + 32;
+        P.match5 = ctx->d_icbc_match;
+        P.match6 = ctx->d_icbc_match + 512;
+        NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
+    } else if (d->format == F_BC4) {
         alpha(0, 8, 0);
     } else if (d->format == F_BC5) {
         alpha(0, 16, 0);

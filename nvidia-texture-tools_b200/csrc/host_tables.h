@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <vector>
 
 namespace nvb {
@@ -56,6 +57,64 @@ inline void build_omatch(uint8_t *table /*[256][2]*/, int size) {
                     table[i * 2 + 0] = (uint8_t)mx;
                     table[i * 2 + 1] = (uint8_t)mn;
                     bestErr = err;
+                }
+            }
+        }
+    }
+}
+
+// ---- ICBC tables (src/nvtt/icbc.h) ------------------------------------------------------------------------
+// Cluster splits (icbc.h:1906-1975): cumulative cluster sizes (c0, c0+c1, c0+c1+c2) packed c0|c1<<5|c2<<10, grouped by
+// the total t = last cumulative count (1..16) and, inside a group, in (c0, c1) order; total[t-1] = entries usable by a
+// colour set of t points.  968 four-cluster and 152 three-cluster splits.
+inline void build_icbc_splits(std::vector<uint16_t> &four, int four_total[16], std::vector<uint16_t> &three, int three_total[16]) {
+    four.clear();
+    three.clear();
+    for (int t = 1; t <= 16; t++) {
+        for (int c0 = 0; c0 <= t; c0++)
+            for (int c1 = 0; c1 <= t - c0; c1++) four.push_back((uint16_t)(c0 | ((c0 + c1) << 5) | (t << 10)));
+        four_total[t - 1] = (int)four.size();
+        for (int c0 = 0; c0 <= t; c0++) three.push_back((uint16_t)(c0 | (t << 5)));
+        three_total[t - 1] = (int)three.size();
+    }
+}
+// 565 rounding midpoints (icbc.h:1516-1526): the arithmetic mean of two neighbouring bit-expanded codes / 255,
+// written with six decimals; the last entry is FLT_MAX.
+inline void build_icbc_midpoints(float mid5[32], float mid6[64]) {
+    char buf[32];
+    for (int i = 0; i < 31; i++) {
+        const int e0 = (i << 3) | (i >> 2), e1 = ((i + 1) << 3) | ((i + 1) >> 2);
+        snprintf(buf, sizeof buf, "%.6f", (e0 + e1) / 510.0);
+        mid5[i] = strtof(buf, nullptr);
+    }
+    mid5[31] = 3.402823466e+38F;
+    for (int i = 0; i < 63; i++) {
+        const int e0 = (i << 2) | (i >> 4), e1 = ((i + 1) << 2) | ((i + 1) >> 4);
+        snprintf(buf, sizeof buf, "%.6f", (e0 + e1) / 510.0);
+        mid6[i] = strtof(buf, nullptr);
+    }
+    mid6[63] = 3.402823466e+38F;
+}
+// ICBC single-colour tables for Decoder_D3D10 (icbc.h:3166-3270): the error actually minimised is
+// max(|amd - i|, |nv - i|) of the AMD and NVIDIA hardware interpolants; first best in (mn, mx) scan order.
+inline void build_icbc_match(uint8_t *table /*[256][2]*/, int size) {
+    std::vector<int> expand(size);
+    for (int i = 0; i < size; i++) expand[i] = (size == 32) ? ((i << 3) | (i >> 2)) : ((i << 2) | (i >> 4));
+    for (int i = 0; i < 256; i++) {
+        int bestErr = 256 * 100;
+        for (int mn = 0; mn < size; mn++) {
+            for (int mx = 0; mx < size; mx++) {
+                const int mine = expand[mn], maxe = expand[mx];
+                const int amd = (43 * maxe + 21 * mine + 32) >> 6;
+                int nv;
+                if (size == 32) nv = ((2 * mx + mn) * 22) / 8;
+                else nv = (256 * mine + (maxe - mine) / 4 + 128 + (maxe - mine) * 80) / 256;
+                const int amd_err = abs(amd - i), nv_err = abs(nv - i);
+                const int err = amd_err > nv_err ? amd_err : nv_err;
+                if (err < bestErr) {
+                    bestErr = err;
+                    table[i * 2 + 0] = (uint8_t)mx;
+                    table[i * 2 + 1] = (uint8_t)mn;
                 }
             }
         }

@@ -1,0 +1,576 @@
+// BC1 block encoder: ICBC v1.05 semantics (scalar code path), 16 lanes per 4x4 block.
+//
+// Replaces, bit-exactly at Quality_Fastest (Level 1) / Normal + Highest (Level 8) / Production (Level 9):
+//   FloatColorCompressor task (gather, zero padding, weights)   src/nvtt/BlockCompressor.cpp:116-166
+//   CompressorDXT1::compressBlock -> icbc::compress_dxt1         src/nvtt/BlockCompressor.cpp:211-222, icbc.h:3485-3559
+//   reduce_colors / skip_blacks / is_black                      src/nvtt/icbc.h:1622-1702
+//   computeCentroid / computeCovariance / power method          src/nvtt/icbc.h:1709-1799
+//   compute_sat                                                 src/nvtt/icbc.h:1812-1882
+//   cluster tables (968 four-cluster / 152 three-cluster)       src/nvtt/icbc.h:1894-1975 (regenerated in host_tables.h)
+//   cluster_fit_three / cluster_fit_four (scalar lanes)         src/nvtt/icbc.h:2016-2247 / 2250-2549
+//   vector3_to_color16, midpoint rounding                       src/nvtt/icbc.h:1516-1526,1580-1595
+//   evaluate_palette (D3D10), evaluate_mse                      src/nvtt/icbc.h:2558-2585,2687-2760
+//   compute_indices4 / compute_indices3 / compute_indices       src/nvtt/icbc.h:2803-2941
+//   output_block3 / output_block4                               src/nvtt/icbc.h:2944-2980
+//   optimize_end_points4, fit_colors_bbox, select_diagonal, inset_bbox   src/nvtt/icbc.h:2984-3016,3096-3151
+//   compress_dxt1_single_color_optimal                          src/nvtt/icbc.h:3274-3289
+//   compress_dxt1_cluster_fit, refine_endpoints                 src/nvtt/icbc.h:3290-3406
+//
+// Mapping: a half-warp owns a block, lane l owns texel l.  Per-texel work (distances, indices) is lane-parallel;
+// every fp32 reduction whose order matters is evaluated in the reference's order (either redundantly in all
+// lanes from shared memory, or as an ordered 16-step shuffle sum); cluster splits are striped over the lanes
+// and reduced with (error, split number) so the first strict minimum of the sequential search wins.
+#pragma once
+#include "../nvb_common.cuh"
+
+namespace nvb {
+
+struct Bc1Params {
+    LevelView lv;
+    unsigned char *out;   // 8 bytes per block
+    int out_stride, out_offset;
+    int level;            // ICBC quality level: 1 (Fastest), 8 (Normal/Highest), 9 (Production)
+    int transparency;     // AlphaMode_Transparency: weight = saturate(alpha)
+    float cw[3];          // colour weights
+    const unsigned short *four;   // 968 packed cumulative splits c0 | c1<<5 | c2<<10
+    const unsigned short *three;  // 152 packed cumulative splits c0 | c1<<5
+    const int *four_total;        // [16]
+    const int *three_total;       // [16]
+    const float *midpoints5;      // [32]
+    const float *midpoints6;      // [64]
+    const unsigned char *match5;  // [256][2] ICBC single-colour tables
+    const unsigned char *match6;  // [256][2]
+};
+
+#define NVB_BC1_GROUPS 8
+
+struct Bc1GroupSmem {
+    float4 pts[16];   // reduced colour set (x,y,z,weight)
+    float4 sat[16];   // summed-area table along the principal axis
+};
+
+struct Bc1Block {
+    unsigned c0, c1;  // Color16.u
+    unsigned indices;
+};
+
+NVB_DEV float icbc_saturate(float x) { return nv_min(nv_max(x, 0.0f), 1.0f); }
+
+// ordered sum over the 16 lanes of the group: ((0 + t0) + t1) + ... + t15
+NVB_DEV float group_ordered_sum(unsigned gm, float t) {
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += __shfl_sync(gm, t, j, 16);
+    return s;
+}
+
+NVB_DEV unsigned icbc_vector3_to_color16(const Bc1Params &P, float x, float y, float z) {
+    unsigned r = (unsigned)x86_ftoi(nv_clamp(x * 31.0f, 0.0f, 31.0f));
+    unsigned g = (unsigned)x86_ftoi(nv_clamp(y * 63.0f, 0.0f, 63.0f));
+    unsigned b = (unsigned)x86_ftoi(nv_clamp(z * 31.0f, 0.0f, 31.0f));
+    r += (x > P.midpoints5[r]) ? 1u : 0u;
+    g += (y > P.midpoints6[g]) ? 1u : 0u;
+    b += (z > P.midpoints5[b]) ? 1u : 0u;
+    return ((r << 11) | (g << 5) | b) & 0xFFFFu;
+}
+
+// D3D10 palette as 8-bit channels: pal[i] = r | g<<8 | b<<16 (| 0xFF<<24 unless transparent black)
+NVB_DEV void icbc_palette32(unsigned c0, unsigned c1, unsigned pr[4], unsigned pg[4], unsigned pb[4]) {
+    const unsigned r0 = (c0 >> 11) & 31, g0 = (c0 >> 5) & 63, b0 = c0 & 31;
+    const unsigned r1 = (c1 >> 11) & 31, g1 = (c1 >> 5) & 63, b1 = c1 & 31;
+    pr[0] = (r0 << 3) | (r0 >> 2); pg[0] = (g0 << 2) | (g0 >> 4); pb[0] = (b0 << 3) | (b0 >> 2);
+    pr[1] = (r1 << 3) | (r1 >> 2); pg[1] = (g1 << 2) | (g1 >> 4); pb[1] = (b1 << 3) | (b1 >> 2);
+    if (c0 > c1) {
+        pr[2] = (2 * pr[0] + pr[1]) / 3; pg[2] = (2 * pg[0] + pg[1]) / 3; pb[2] = (2 * pb[0] + pb[1]) / 3;
+        pr[3] = (2 * pr[1] + pr[0]) / 3; pg[3] = (2 * pg[1] + pg[0]) / 3; pb[3] = (2 * pb[1] + pb[0]) / 3;
+    } else {
+        pr[2] = (pr[0] + pr[1]) / 2; pg[2] = (pg[0] + pg[1]) / 2; pb[2] = (pb[0] + pb[1]) / 2;
+        pr[3] = 0; pg[3] = 0; pb[3] = 0;
+    }
+}
+
+struct Pal3 {
+    float x[4], y[4], z[4];
+};
+NVB_DEV Pal3 icbc_palette_f(unsigned c0, unsigned c1) {
+    unsigned pr[4], pg[4], pb[4];
+    icbc_palette32(c0, c1, pr, pg, pb);
+    Pal3 p;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        p.x[i] = (float)pr[i] / 255.0f;
+        p.y[i] = (float)pg[i] / 255.0f;
+        p.z[i] = (float)pb[i] / 255.0f;
+    }
+    return p;
+}
+
+NVB_DEV float dist2w(float cx, float cy, float cz, float px, float py, float pz) {
+    // vlen2(vc - vp): both already multiplied by the colour weights
+    const float dx = cx - px, dy = cy - py, dz = cz - pz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// per-texel squared error term of evaluate_mse: |(p - c) * w * 255|^2
+NVB_DEV float mse_term(float px, float py, float pz, float cx, float cy, float cz, const float cw[3]) {
+    const float dx = (px - cx) * cw[0] * 255.0f;
+    const float dy = (py - cy) * cw[1] * 255.0f;
+    const float dz = (pz - cz) * cw[2] * 255.0f;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+NVB_DEV unsigned group_gather_bits2(unsigned gm, unsigned idx, int l) {
+    unsigned bits = (idx & 3u) << (2 * l);
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) bits |= __shfl_xor_sync(gm, bits, d, 16);
+    return bits;
+}
+
+NVB_DEV float select4(const float v[4], unsigned i) { return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : v[3]; }
+
+// output_block4 / output_block3: endpoints -> 565, palette, per-texel index, weighted MSE (ordered sum).
+NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool four, bool allow_black, float sx, float sy, float sz,
+                                float ex, float ey, float ez, float cx, float cy, float cz, float wt, Bc1Block *blk) {
+    unsigned color0 = icbc_vector3_to_color16(P, sx, sy, sz);
+    unsigned color1 = icbc_vector3_to_color16(P, ex, ey, ez);
+    if (four ? (color0 < color1) : (color0 > color1)) {
+        const unsigned t = color0; color0 = color1; color1 = t;
+    }
+    const Pal3 pal = icbc_palette_f(color0, color1);
+    const float vcx = cx * P.cw[0], vcy = cy * P.cw[1], vcz = cz * P.cw[2];
+    float d[4];
+    unsigned idx;
+    if (four) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = dist2w(vcx, vcy, vcz, pal.x[i] * P.cw[0], pal.y[i] * P.cw[1], pal.z[i] * P.cw[2]);
+        const bool b1 = d[1] > d[2], b2 = d[0] > d[2];
+        bool x0 = b1 && b2;
+        const bool b0 = d[0] > d[3], b3 = d[1] > d[3];
+        x0 = x0 || (b0 && b3);
+        const bool b4 = d[2] > d[3];
+        const bool x1 = b0 && b4;
+        idx = (x1 ? 1u : 0u) | (x0 ? 2u : 0u);  // interleave(indices1, indices0): x1 -> bit 0, x0 -> bit 1
+    } else {
+        // note the operand order vp - vc here (compute_indices3)
+#pragma unroll
+        for (int i = 0; i < 3; i++) d[i] = dist2w(pal.x[i] * P.cw[0], pal.y[i] * P.cw[1], pal.z[i] * P.cw[2], vcx, vcy, vcz);
+        const bool i1 = d[1] < d[2];
+        const bool i2 = (d[2] <= d[0]) && (d[2] <= d[1]);
+        bool i3 = false;
+        if (allow_black) {
+            const float d3 = vcx * vcx + vcy * vcy + vcz * vcz;
+            i3 = (d3 <= d[0]) && (d3 <= d[1]) && (d3 <= d[2]);
+        }
+        // interleave(indices1, indices0): indices1 = i1|i3 goes to bit 0, indices0 = i2|i3 to bit 1
+        idx = ((i1 || i3) ? 1u : 0u) | ((i2 || i3) ? 2u : 0u);
+    }
+    blk->c0 = color0;
+    blk->c1 = color1;
+    blk->indices = group_gather_bits2(gm, idx, l);
+    const float t = wt * mse_term(select4(pal.x, idx), select4(pal.y, idx), select4(pal.z, idx), cx, cy, cz, P.cw);
+    return group_ordered_sum(gm, t);
+}
+
+// evaluate_mse(input_colors, input_weights, color_weights, const BlockDXT1*)
+NVB_DEV float icbc_evaluate_block_mse(const Bc1Params &P, unsigned gm, int l, const Bc1Block &b, float cx, float cy, float cz, float wt) {
+    const Pal3 pal = icbc_palette_f(b.c0, b.c1);
+    const unsigned idx = (b.indices >> (2 * l)) & 3u;
+    const float t = wt * mse_term(select4(pal.x, idx), select4(pal.y, idx), select4(pal.z, idx), cx, cy, cz, P.cw);
+    return group_ordered_sum(gm, t);
+}
+
+// compute_sat on S.pts[0..n): PCA ordering + summed area table in S.sat.  All lanes of the group call it.
+NVB_DEV void icbc_compute_sat(Bc1GroupSmem &S, unsigned gm, int l, int n) {
+    // centroid
+    float total = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const float4 p = S.pts[i];
+        total += p.w;
+        cx += p.x * p.w;
+        cy += p.y * p.w;
+        cz += p.z * p.w;
+    }
+    {
+        const float t = 1.0f / total;
+        cx *= t; cy *= t; cz *= t;
+    }
+    float m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+    for (int i = 0; i < n; i++) {
+        const float4 p = S.pts[i];
+        const float ax = p.x - cx, ay = p.y - cy, az = p.z - cz;
+        const float bx = ax * p.w, by = ay * p.w, bz = az * p.w;
+        m0 += ax * bx;
+        m1 += ax * by;
+        m2 += ax * bz;
+        m3 += ay * by;
+        m4 += ay * bz;
+        m5 += az * bz;
+    }
+    float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+    if (!(m0 == 0 && m3 == 0 && m5 == 0)) {
+        const float r0 = m0 * m0 + m1 * m1 + m2 * m2;
+        const float r1 = m1 * m1 + m3 * m3 + m4 * m4;
+        const float r2 = m2 * m2 + m4 * m4 + m5 * m5;
+        if (r0 > r1 && r0 > r2) { vx = m0; vy = m1; vz = m2; }
+        else if (r1 > r2) { vx = m1; vy = m3; vz = m4; }
+        else { vx = m2; vy = m4; vz = m5; }
+        for (int it = 0; it < 8; it++) {
+            const float x = vx * m0 + vy * m1 + vz * m2;
+            const float y = vx * m1 + vy * m3 + vz * m4;
+            const float z = vx * m2 + vy * m4 + vz * m5;
+            const float norm = nv_max(nv_max(x, y), z);
+            const float inv = 1.0f / norm;
+            vx = x * inv; vy = y * inv; vz = z * inv;
+        }
+    }
+    // order by projection: stable insertion sort == rank by (dps, index)
+    float dps = 0.0f;
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < n) {
+        mine = S.pts[l];
+        dps = mine.x * vx + mine.y * vy + mine.z * vz;
+    }
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float dj = __shfl_sync(gm, dps, j, 16);
+        if (j < n && (dj < dps || (dj == dps && j < l))) rank++;
+    }
+    __syncwarp(gm);  // everyone is done reading S.sat from a previous call
+    if (l < n) S.sat[rank] = make_float4(mine.x * mine.w, mine.y * mine.w, mine.z * mine.w, mine.w);
+    __syncwarp(gm);
+    // inclusive prefix sums, sequentially (lane 0), in the reference's order
+    if (l == 0) {
+        float4 acc = S.sat[0];
+        for (int i = 1; i < n; i++) {
+            const float4 s = S.sat[i];
+            acc.x = acc.x + s.x; acc.y = acc.y + s.y; acc.z = acc.z + s.z; acc.w = acc.w + s.w;
+            S.sat[i] = acc;
+        }
+    }
+    __syncwarp(gm);
+}
+
+struct FitResult {
+    float sx, sy, sz, ex, ey, ez;
+};
+
+NVB_DEV float icbc_round5(float x) { return (float)x86_ftoi(icbc_saturate(x) * 31.0f + 0.5f) * (1.0f / 31.0f); }
+NVB_DEV float icbc_round6(float x) { return (float)x86_ftoi(icbc_saturate(x) * 63.0f + 0.5f) * (1.0f / 63.0f); }
+
+// One split of cluster_fit_four (FOUR) or cluster_fit_three.  Returns the error; a/b = snapped endpoints.
+template <bool FOUR>
+NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const float msq[3], float a[3], float b[3]) {
+    const int c0 = (int)(pk & 31) - 1, c1 = (int)((pk >> 5) & 31) - 1, c2 = (int)((pk >> 10) & 31) - 1;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 s0 = (c0 >= 0) ? sat[c0] : zero;
+    const float4 s1 = (c1 >= 0) ? sat[c1] : zero;
+    float alpha2_sum, beta2_sum, alphabeta_sum;
+    float ax[3];
+    if (FOUR) {
+        const float4 s2 = (c2 >= 0) ? sat[c2] : zero;
+        const float w3 = sum.w - s2.w;
+        const float x2[3] = {s2.x - s1.x, s2.y - s1.y, s2.z - s1.z};
+        const float x1[3] = {s1.x - s0.x, s1.y - s0.y, s1.z - s0.z};
+        const float x0[3] = {s0.x, s0.y, s0.z};
+        const float w2 = s2.w - s1.w;
+        const float w1 = s1.w - s0.w;
+        const float w0 = s0.w;
+        alpha2_sum = w2 * (1.0f / 9.0f) + (w1 * (4.0f / 9.0f) + w0);
+        beta2_sum = w1 * (1.0f / 9.0f) + (w2 * (4.0f / 9.0f) + w3);
+        alphabeta_sum = (w1 + w2) * (2.0f / 9.0f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) ax[k] = x2[k] * (1.0f / 3.0f) + (x1[k] * (2.0f / 3.0f) + x0[k]);
+    } else {
+        const float w2 = sum.w - s1.w;
+        const float x1[3] = {s1.x - s0.x, s1.y - s0.y, s1.z - s0.z};
+        const float x0[3] = {s0.x, s0.y, s0.z};
+        const float w1 = s1.w - s0.w;
+        const float w0 = s0.w;
+        alphabeta_sum = w1 * 0.25f;
+        alpha2_sum = w0 + alphabeta_sum;
+        beta2_sum = w2 + alphabeta_sum;
+#pragma unroll
+        for (int k = 0; k < 3; k++) ax[k] = x0[k] + x1[k] * 0.5f;
+    }
+    const float factor = 1.0f / (alpha2_sum * beta2_sum - alphabeta_sum * alphabeta_sum);
+    const float S[3] = {sum.x, sum.y, sum.z};
+    float e1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float alphax = ax[k];
+        const float betax = S[k] - alphax;
+        float av = (alphax * beta2_sum - betax * alphabeta_sum) * factor;
+        float bv = (betax * alpha2_sum - alphax * alphabeta_sum) * factor;
+        av = (k == 1) ? icbc_round6(av) : icbc_round5(av);
+        bv = (k == 1) ? icbc_round6(bv) : icbc_round5(bv);
+        const float e2 = (av * (bv * alphabeta_sum - alphax) - bv * betax) * 2.0f;
+        e1[k] = (av * av) * alpha2_sum + ((bv * bv) * beta2_sum + e2);
+        a[k] = av;
+        b[k] = bv;
+    }
+    return e1[0] * msq[0] + e1[1] * msq[1] + e1[2] * msq[2];
+}
+
+template <bool FOUR>
+NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, unsigned gm, int l, int count) {
+    const float4 sum = S.sat[count - 1];
+    const float msq[3] = {P.cw[0] * P.cw[0], P.cw[1] * P.cw[1], P.cw[2] * P.cw[2]};
+    const unsigned short *tab = FOUR ? P.four : P.three;
+    const int total = FOUR ? P.four_total[count - 1] : P.three_total[count - 1];
+    float besterror = FLT_MAX;
+    int besti = 0x7fffffff;
+    float a[3], b[3];
+    for (int i = l; i < total; i += 16) {
+        const float e = icbc_eval_split<FOUR>(S.sat, __ldg(tab + i), sum, msq, a, b);
+        if (e < besterror) {
+            besterror = e;
+            besti = i;
+        }
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {
+        const float oe = __shfl_xor_sync(gm, besterror, d, 16);
+        const int oi = __shfl_xor_sync(gm, besti, d, 16);
+        if (oe < besterror || (oe == besterror && oi < besti)) {
+            besterror = oe;
+            besti = oi;
+        }
+    }
+    FitResult r;
+    r.sx = r.sy = r.sz = r.ex = r.ey = r.ez = 0.0f;  // vbeststart / vbestend start at zero
+    if (besti != 0x7fffffff) {
+        icbc_eval_split<FOUR>(S.sat, __ldg(tab + besti), sum, msq, a, b);
+        r.sx = a[0]; r.sy = a[1]; r.sz = a[2];
+        r.ex = b[0]; r.ey = b[1]; r.ez = b[2];
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
+    __shared__ Bc1GroupSmem smem[NVB_BC1_GROUPS];
+    const int grp = threadIdx.x >> 4;
+    const int l = threadIdx.x & 15;
+    const int nblocks = P.lv.bw * P.lv.bh;
+    const int blkid = blockIdx.x * NVB_BC1_GROUPS + grp;
+    if (blkid >= nblocks) return;
+    const unsigned gsh = threadIdx.x & 16;
+    const unsigned gm = 0xFFFFu << gsh;
+    Bc1GroupSmem &S = smem[grp];
+
+    // ---- gather: fp32 texels, zero padding + zero weight outside the image ----
+    const int bx = blkid % P.lv.bw, by = blkid / P.lv.bw;
+    const int px = bx * 4 + (l & 3), py = by * 4 + (l >> 2);
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f, wt = 0.0f;
+    if (px < P.lv.w && py < P.lv.h) {
+        cx = load_texel(P.lv, 0, px, py);
+        cy = load_texel(P.lv, 1, px, py);
+        cz = load_texel(P.lv, 2, px, py);
+        wt = 1.0f;
+        if (P.transparency) wt = icbc_saturate(load_texel(P.lv, 3, px, py));
+    }
+    unsigned char *dst = P.out + (size_t)blkid * P.out_stride + P.out_offset;
+    Bc1Block out;
+    out.c0 = out.c1 = out.indices = 0;
+    float error = FLT_MAX;
+    int count = 16;
+    bool any_black = false;
+
+    if (P.level >= 2) {
+        // ---- reduce_colors: merge texel i into the first earlier cluster within 1/256 per channel ----
+        const float threshold = 1.0f / 256;
+        float qx = 0.0f, qy = 0.0f, qz = 0.0f, qw = 0.0f;  // cluster l (valid for l < n)
+        int n = 0;
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) {
+            const float tx = __shfl_sync(gm, cx, i, 16), ty = __shfl_sync(gm, cy, i, 16), tz = __shfl_sync(gm, cz, i, 16);
+            const float tw = __shfl_sync(gm, wt, i, 16);
+            if (tw > 0) {  // group-uniform
+                const bool match = (l < n) && (fabsf(qx - tx) < threshold) && (fabsf(qy - ty) < threshold) && (fabsf(qz - tz) < threshold);
+                const unsigned mm = (__ballot_sync(gm, match) >> gsh) & 0xFFFFu;
+                if (mm) {
+                    if (l == __ffs((int)mm) - 1) {
+                        const float den = qw + tw;
+                        qx = (qx * qw + tx * tw) / den;
+                        qy = (qy * qw + ty * tw) / den;
+                        qz = (qz * qw + tz * tw) / den;
+                        qw += tw;
+                    }
+                } else {
+                    if (l == n) { qx = tx; qy = ty; qz = tz; qw = tw; }
+                    n++;
+                }
+            }
+        }
+        count = n;
+        const bool black = (wt > 0) && (cx < 1.0f / 8) && (cy < 1.0f / 8) && (cz < 1.0f / 8);
+        any_black = __ballot_sync(gm, black) & gm;
+        if (count == 0) {
+            if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(0u, 0u);
+            return;
+        }
+        if (count == 1) {
+            // compress_dxt1_single_color_optimal(vector3_to_color32(colors[0]))
+            if (l == 0) {
+                const unsigned r = (unsigned)x86_ftoi(icbc_saturate(qx) * 255 + 0.5f) & 0xFF;
+                const unsigned g = (unsigned)x86_ftoi(icbc_saturate(qy) * 255 + 0.5f) & 0xFF;
+                const unsigned b = (unsigned)x86_ftoi(icbc_saturate(qz) * 255 + 0.5f) & 0xFF;
+                unsigned c0 = ((unsigned)P.match5[r * 2 + 0] << 11) | ((unsigned)P.match6[g * 2 + 0] << 5) | P.match5[b * 2 + 0];
+                unsigned c1 = ((unsigned)P.match5[r * 2 + 1] << 11) | ((unsigned)P.match6[g * 2 + 1] << 5) | P.match5[b * 2 + 1];
+                unsigned indices = 0xaaaaaaaau;
+                if (c0 < c1) {
+                    const unsigned t = c0; c0 = c1; c1 = t;
+                    indices ^= 0x55555555u;
+                }
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(c0 | (c1 << 16), indices);
+            }
+            return;
+        }
+        if (l < count) S.pts[l] = make_float4(qx, qy, qz, qw);
+        __syncwarp(gm);
+    }
+
+    if (P.level == 1) {
+        // ---- box fit on all 16 (un-reduced, padding included) colours + least squares refit ----
+        // fit_colors_bbox: fold over the texels in order with icbc::max/min semantics
+        float c0x = 0.0f, c0y = 0.0f, c0z = 0.0f, c1x = 1.0f, c1y = 1.0f, c1z = 1.0f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float tx = __shfl_sync(gm, cx, j, 16), ty = __shfl_sync(gm, cy, j, 16), tz = __shfl_sync(gm, cz, j, 16);
+            c0x = nv_max(c0x, tx); c0y = nv_max(c0y, ty); c0z = nv_max(c0z, tz);
+            c1x = nv_min(c1x, tx); c1y = nv_min(c1y, ty); c1z = nv_min(c1z, tz);
+        }
+        // inset_bbox
+        {
+            const float bias = (8.0f / 255.0f) / 16.0f;
+            const float ix = (c0x - c1x) / 16.0f - bias, iy = (c0y - c1y) / 16.0f - bias, iz = (c0z - c1z) / 16.0f - bias;
+            c0x = icbc_saturate(c0x - ix); c0y = icbc_saturate(c0y - iy); c0z = icbc_saturate(c0z - iz);
+            c1x = icbc_saturate(c1x + ix); c1y = icbc_saturate(c1y + iy); c1z = icbc_saturate(c1z + iz);
+        }
+        // select_diagonal
+        {
+            const float mx = (c0x + c1x) * 0.5f, my = (c0y + c1y) * 0.5f, mz = (c0z + c1z) * 0.5f;
+            const float tx = cx - mx, ty = cy - my, tz = cz - mz;
+            const float cov_xz = group_ordered_sum(gm, tx * tz);
+            const float cov_yz = group_ordered_sum(gm, ty * tz);
+            if (cov_xz < 0) { const float t = c0x; c0x = c1x; c1x = t; }
+            if (cov_yz < 0) { const float t = c0y; c0y = c1y; c1y = t; }
+        }
+        error = icbc_output_block(P, gm, l, true, false, c0x, c0y, c0z, c1x, c1y, c1z, cx, cy, cz, wt, &out);
+        // optimize_end_points4 on the chosen indices (unweighted, all 16 texels)
+        {
+            const unsigned bits = out.indices >> (2 * l);
+            float beta = (float)(bits & 1);
+            if (bits & 2) beta = (1 + beta) / 3.0f;
+            const float alpha = 1.0f - beta;
+            const float alpha2_sum = group_ordered_sum(gm, alpha * alpha);
+            const float beta2_sum = group_ordered_sum(gm, beta * beta);
+            const float alphabeta_sum = group_ordered_sum(gm, alpha * beta);
+            const float axx = group_ordered_sum(gm, alpha * cx), axy = group_ordered_sum(gm, alpha * cy), axz = group_ordered_sum(gm, alpha * cz);
+            const float bxx = group_ordered_sum(gm, beta * cx), bxy = group_ordered_sum(gm, beta * cy), bxz = group_ordered_sum(gm, beta * cz);
+            const float denom = alpha2_sum * beta2_sum - alphabeta_sum * alphabeta_sum;
+            if (!(fabsf(denom - 0.0f) < 0.0001f)) {
+                const float factor = 1.0f / denom;
+                const float ax = icbc_saturate((axx * beta2_sum - bxx * alphabeta_sum) * factor);
+                const float ay = icbc_saturate((axy * beta2_sum - bxy * alphabeta_sum) * factor);
+                const float az = icbc_saturate((axz * beta2_sum - bxz * alphabeta_sum) * factor);
+                const float bx2 = icbc_saturate((bxx * alpha2_sum - axx * alphabeta_sum) * factor);
+                const float by2 = icbc_saturate((bxy * alpha2_sum - axy * alphabeta_sum) * factor);
+                const float bz2 = icbc_saturate((bxz * alpha2_sum - axz * alphabeta_sum) * factor);
+                Bc1Block opt;
+                const float oe = icbc_output_block(P, gm, l, true, false, ax, ay, az, bx2, by2, bz2, cx, cy, cz, wt, &opt);
+                if (oe < error) {
+                    error = oe;
+                    out = opt;
+                }
+            }
+        }
+    } else {
+        // ---- compress_dxt1_cluster_fit ----
+        icbc_compute_sat(S, gm, l, count);
+        FitResult f4 = icbc_cluster_fit<true>(P, S, gm, l, count);
+        Bc1Block cf;
+        float best = icbc_output_block(P, gm, l, true, false, f4.sx, f4.sy, f4.sz, f4.ex, f4.ey, f4.ez, cx, cy, cz, wt, &cf);
+        // three colour mode (Levels 8/9: always tried; transparent black allowed)
+        int sat_count = count;
+        bool do_three = true;
+        if (any_black) {
+            // skip_blacks on the reduced set, then a new SAT
+            const float4 q = (l < count) ? S.pts[l] : make_float4(1.f, 1.f, 1.f, 0.f);
+            const bool keep = (l < count) && !((q.x < 1.0f / 8) && (q.y < 1.0f / 8) && (q.z < 1.0f / 8));
+            const unsigned km = (__ballot_sync(gm, keep) >> gsh) & 0xFFFFu;
+            const int tmp_count = __popc(km);
+            if (tmp_count == 0) {
+                do_three = false;
+            } else {
+                __syncwarp(gm);
+                if (keep) S.pts[__popc(km & ((1u << l) - 1u))] = q;
+                __syncwarp(gm);
+                icbc_compute_sat(S, gm, l, tmp_count);
+                sat_count = tmp_count;
+            }
+        }
+        if (do_three) {
+            FitResult f3 = icbc_cluster_fit<false>(P, S, gm, l, sat_count);
+            Bc1Block tb;
+            const float te = icbc_output_block(P, gm, l, false, true, f3.sx, f3.sy, f3.sz, f3.ex, f3.ey, f3.ez, cx, cy, cz, wt, &tb);
+            if (te < best) {
+                best = te;
+                cf = tb;
+            }
+        }
+        if (best < error) {
+            out = cf;
+            error = best;
+        }
+        if (P.level == 9) {
+            // ---- refine_endpoints (three_color_mode == true: no endpoint re-ordering) ----
+            float best_error = error;
+            int lastImprovement = 0;
+            const float vcx = cx * P.cw[0], vcy = cy * P.cw[1], vcz = cz * P.cw[2];
+#pragma unroll 1
+            for (int i = 0; i < 256; i++) {
+                // deltas[i % 16]
+                const int k = i & 15;
+                int dr, dg, db;
+                {
+                    // rows: (1,0,0)(0,1,0)(0,0,1)(-1,0,0)(0,-1,0)(0,0,-1)(1,1,0)(1,0,1)(0,1,1)(-1,-1,0)(-1,0,-1)(0,-1,-1)(-1,1,0)(1,-1,0)(0,-1,1)(0,1,-1)
+                    const signed char tr[16] = {1, 0, 0, -1, 0, 0, 1, 1, 0, -1, -1, 0, -1, 1, 0, 0};
+                    const signed char tg[16] = {0, 1, 0, 0, -1, 0, 1, 0, 1, -1, 0, -1, 1, -1, -1, 1};
+                    const signed char tb2[16] = {0, 0, 1, 0, 0, -1, 0, 1, 1, 0, -1, -1, 0, 0, 1, -1};
+                    dr = tr[k]; dg = tg[k]; db = tb2[k];
+                }
+                Bc1Block refined = out;
+                unsigned c = ((i / 16) & 1) ? refined.c0 : refined.c1;
+                {
+                    const unsigned r = (((c >> 11) & 31) + (unsigned)dr) & 31;
+                    const unsigned g = (((c >> 5) & 63) + (unsigned)dg) & 63;
+                    const unsigned b = ((c & 31) + (unsigned)db) & 31;
+                    c = (r << 11) | (g << 5) | b;
+                }
+                if ((i / 16) & 1) refined.c0 = c; else refined.c1 = c;
+                // indices from the palette of *output* (sic), general 4-way rule
+                const Pal3 pal = icbc_palette_f(out.c0, out.c1);
+                float d[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) d[q] = dist2w(vcx, vcy, vcz, pal.x[q] * P.cw[0], pal.y[q] * P.cw[1], pal.z[q] * P.cw[2]);
+                const bool i1 = (d[1] <= d[0]) && (d[1] < d[2]) && (d[1] < d[3]);
+                const bool i2 = (d[2] <= d[0]) && (d[2] <= d[1]) && (d[2] < d[3]);
+                const bool i3 = (d[3] <= d[0]) && (d[3] <= d[1]) && (d[3] <= d[2]);
+                const unsigned idx = ((i1 || i3) ? 1u : 0u) | ((i2 || i3) ? 2u : 0u);
+                refined.indices = group_gather_bits2(gm, idx, l);
+                const float refined_error = icbc_evaluate_block_mse(P, gm, l, refined, cx, cy, cz, wt);
+                if (refined_error < best_error) {
+                    best_error = refined_error;
+                    out = refined;
+                    lastImprovement = i;
+                }
+                if (i - lastImprovement > 32) break;
+            }
+            error = best_error;
+        }
+    }
+    if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(out.c0 | (out.c1 << 16), out.indices);
+}
+
+}  // namespace nvb

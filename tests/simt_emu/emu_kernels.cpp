@@ -3,6 +3,7 @@
 #include "cuda_emu.h"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc_alpha.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_icbc.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -12,6 +13,10 @@ static float g_to_gamma[512], g_to_linear[512];
 static std::vector<uint16_t> g_cand;
 static int g_cand_off[18];
 static uint8_t g_om5[512], g_om6[512];
+static std::vector<uint16_t> g_four, g_three;
+static int g_four_total[16], g_three_total[16];
+static float g_mid5[32], g_mid6[64];
+static uint8_t g_match5[512], g_match6[512];
 static bool g_init = false;
 static void init_tables() {
     if (g_init) return;
@@ -19,6 +24,10 @@ static void init_tables() {
     build_squish_splits(g_cand, g_cand_off);
     build_omatch(g_om5, 32);
     build_omatch(g_om6, 64);
+    build_icbc_splits(g_four, g_four_total, g_three, g_three_total);
+    build_icbc_midpoints(g_mid5, g_mid6);
+    build_icbc_match(g_match5, 32);
+    build_icbc_match(g_match6, 64);
     g_init = true;
 }
 static LevelView make_lv(const float *data, int w, int h, int gamma) {
@@ -49,6 +58,19 @@ void emu_bc3_color(const float *planar, int w, int h, const float *metric, int w
     P.cand = g_cand.data(); P.cand_off = g_cand_off; P.omatch5 = g_om5; P.omatch6 = g_om6;
     int nb = P.lv.bw * P.lv.bh;
     emu::launch(dim3((nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS), dim3(NVB_BC3_GROUPS * 16), 0, [&] { k_bc3_color(P); });
+}
+
+void emu_bc1(const float *planar, int w, int h, const float *cw, int level, int transparency, unsigned char *out, int gamma) {
+    init_tables();
+    Bc1Params P;
+    P.lv = make_lv(planar, w, h, gamma);
+    P.out = out; P.out_stride = 8; P.out_offset = 0;
+    P.level = level; P.transparency = transparency;
+    P.cw[0] = cw[0]; P.cw[1] = cw[1]; P.cw[2] = cw[2];
+    P.four = g_four.data(); P.three = g_three.data(); P.four_total = g_four_total; P.three_total = g_three_total;
+    P.midpoints5 = g_mid5; P.midpoints6 = g_mid6; P.match5 = g_match5; P.match6 = g_match6;
+    int nb = P.lv.bw * P.lv.bh;
+    emu::launch(dim3((nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS), dim3(NVB_BC1_GROUPS * 16), 0, [&] { k_bc1_icbc(P); });
 }
 
 void emu_set_image(const void *src, float *dst, int count, int format, int to_linear) {

@@ -27,10 +27,11 @@ def _assert_blocks_equal(got, want, bs, what):
                              % (what, int(bad.sum()), bad.size, i, got.reshape(-1, bs)[i], want.reshape(-1, bs)[i]))
 
 
-@pytest.mark.parametrize("fmt_name,quality", [("BC4", 0), ("BC4", 1), ("BC5", 0), ("BC5", 1), ("BC3", 1), ("BC3", 2)])
+@pytest.mark.parametrize("fmt_name,quality", [("BC1", 0), ("BC1", 1), ("BC1", 2), ("BC1", 3), ("BC4", 0), ("BC4", 1), ("BC5", 0),
+                                              ("BC5", 1), ("BC3", 1), ("BC3", 2)])
 def test_level_encode_bit_exact(nvtt, ref, ctx, fmt_name, quality):
     fmt = getattr(nvtt, "Format_" + fmt_name)
-    bs = 8 if fmt_name == "BC4" else 16
+    bs = 8 if fmt_name in ("BC4", "BC1") else 16
     for (w, h) in SIZES:
         for name, img in _images(nvtt, w, h):
             got = ctx.encode_level(fmt, quality, img)
@@ -45,6 +46,22 @@ def test_bc3_weights_and_transparency(nvtt, ref, ctx):
             got = ctx.encode_level(nvtt.Format_BC3, 1, img, alpha_mode=am, color_weights=cw)
             want = ref.compress_level(ref.Format_BC3, 1, img, alpha_mode=am, color_weights=cw)
             _assert_blocks_equal(got, want, 16, "BC3 weights %s alphaMode %d" % (cw, am))
+
+
+def test_bc1_weights_transparency_and_blacks(nvtt, ref, ctx):
+    """ICBC paths that depend on the input: colour weights, alpha-weighted texels, dark blocks (3-colour + transparent
+    black), out-of-range floats."""
+    s = nvtt.synth
+    photo = s.planar_from_bgra8(s.photo_bgra8(128, 128, seed=3, alpha=True))
+    dark = np.ascontiguousarray((s.planar_from_bgra8(s.photo_bgra8(128, 128, seed=4)) * 0.2).astype(np.float32))
+    rng = np.random.default_rng(9)
+    oob = rng.random((4, 64, 64), dtype=np.float32) * 1.5 - 0.25
+    for name, img in (("photo", photo), ("dark", dark), ("oob", oob)):
+        for q in (0, 1, 2):
+            for cw, am in (((1, 1, 1, 1), 0), ((0.3, 0.59, 0.11, 1.0), 1), ((1, 1, 1, 1), 1)):
+                got = ctx.encode_level(nvtt.Format_BC1, q, img, alpha_mode=am, color_weights=cw)
+                want = ref.compress_level(ref.Format_BC1, q, img, alpha_mode=am, color_weights=cw)
+                _assert_blocks_equal(got, want, 8, "BC1 %s q%d weights %s alphaMode %d" % (name, q, cw, am))
 
 
 def test_surface_ops_bit_exact(nvtt, ref, ctx):
@@ -126,6 +143,10 @@ PIPE_CASES = [
     ("bc5_normal_kaiser", "normal", "BC5", 1, dict(mip_filter=2, wrap=2, normal_map=True)),
     ("bc5_normal_box", "normal", "BC5", 1, dict(mip_filter=0, wrap=1, normal_map=True)),
     ("bc4_box", "photo", "BC4", 1, dict(mip_filter=0)),
+    ("bc1_normal_box_config0", "photo", "BC1", 1, dict(mip_filter=0, wrap=0)),
+    ("bc1_fastest_box", "photo", "BC1", 0, dict(mip_filter=0)),
+    ("bc1_production_box_config2", "photo", "BC1", 2, dict(mip_filter=0)),
+    ("bc1_production_kaiser_transparency", "alpha", "BC1", 2, dict(mip_filter=2, alpha_mode=1)),
     ("bc3_triangle_transparency", "alpha", "BC3", 1, dict(mip_filter=1, alpha_mode=1)),
     ("bc3_box_transparency", "alpha", "BC3", 2, dict(mip_filter=0, alpha_mode=1)),
     ("bc3_no_mips_gamma1", "alpha", "BC3", 1, dict(mipmaps=False, gamma=(1.0, 1.0))),
@@ -146,7 +167,7 @@ def _synth(nvtt, kind, w, h):
 def test_pipeline_bit_exact(nvtt, ref, ctx, case):
     name, kind, fmt_name, quality, kw = case
     fmt = getattr(nvtt, "Format_" + fmt_name)
-    bs = 8 if fmt_name == "BC4" else 16
+    bs = 8 if fmt_name in ("BC4", "BC1") else 16
     for (w, h) in [(256, 256), (100, 60), (31, 17)]:
         img = _synth(nvtt, kind, w, h)
         d = nvtt.make_process_desc(nvtt.InputFormat_BGRA_8UB, w, h, fmt, quality, **kw)
@@ -208,3 +229,34 @@ def test_config2_full_size_properties(nvtt, ref, ctx):
     want_tail = ref.process([il], ref.InputFormat_RGBA_32F, 512, 512, ref.Format_BC3, 1, gamma=(1.0, 2.2), **kw)
     got_tail = np.concatenate([b for (_, m, _, _, b) in out1 if m >= 3])
     assert np.array_equal(got_tail, want_tail)
+
+
+def test_config0_and_config2_full_size_properties(nvtt, ref, ctx):
+    """BASELINE configs[0] (BC1 Normal, 2048^2, Box mips) and configs[2] (BC1 Production, 8192^2, Box mips) at full
+    size.  The 2x2 box filter is local, so any 4-aligned crop whose size is a power of two reproduces — through the
+    reference's own pipeline — exactly the corresponding blocks of every level the crop still covers."""
+    for (size, quality, crop) in ((2048, 1, 256), (8192, 2, 256)):
+        img = nvtt.synth.photo_bgra8(size, size, seed=1234)
+        if quality == 2:  # configs[2]: S1 + S5 mix
+            adv = nvtt.synth.adversarial_bgra8(size // 4, size // 4, seed=5)
+            img[: size // 4, : size // 4] = adv
+        d = nvtt.make_process_desc(0, size, size, nvtt.Format_BC1, quality, mip_filter=0)
+        out = ctx.process([img], d)
+        assert len(out) == size.bit_length()
+        for (f, m, lw, lh, b) in out:
+            assert (lw, lh) == (max(1, size >> m), max(1, size >> m))
+            assert b.size == ((lw + 3) // 4) * ((lh + 3) // 4) * 8
+        rng = np.random.default_rng(1)
+        spots = [(0, 0)] + [(int(rng.integers(0, size // crop)) * crop, int(rng.integers(0, size // crop)) * crop) for _ in range(5)]
+        for (x0, y0) in spots:
+            c = np.ascontiguousarray(img[y0:y0 + crop, x0:x0 + crop])
+            want = ref.process([c], 0, crop, crop, ref.Format_BC1, quality, mip_filter=0)
+            off = 0
+            for m in range(crop.bit_length() - 2):  # levels where the crop is still >= 4 texels wide
+                cw = crop >> m
+                nb = cw // 4
+                lvl = out[m][4].reshape((size >> m) // 4, (size >> m) // 4, 8)
+                got = lvl[(y0 >> m) // 4:(y0 >> m) // 4 + nb, (x0 >> m) // 4:(x0 >> m) // 4 + nb]
+                exp = want[off:off + nb * nb * 8].reshape(nb, nb, 8)
+                assert np.array_equal(got, exp), "size %d crop (%d,%d) level %d" % (size, x0, y0, m)
+                off += nb * nb * 8
