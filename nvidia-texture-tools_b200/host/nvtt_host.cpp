@@ -1,0 +1,722 @@
+// C++ host layer: the nvtt:: classes of host/nvtt/nvtt.h implemented on the C ABI (include/nvtt_b200.h) only.
+// Mirrors the control flow and error behaviour of the reference's src/nvtt/Context.cpp:61-516 (process, compress,
+// outputHeader, estimateSize), InputOptions.cpp:96-330, CompressionOptions.cpp:48-200, OutputOptions.cpp:44-180 and the
+// DDS header writer nvimage/DirectDrawSurface.cpp:574-830.  No image is ever processed on the CPU here.
+#include "nvtt/nvtt.h"
+#include "../../include/nvtt_b200.h"
+
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace nvtt;
+
+namespace {
+inline int imax(int a, int b) { return a > b ? a : b; }
+inline int imin(int a, int b) { return a < b ? a : b; }
+
+// One shared GPU context per process (device from NVTT_B200_DEVICE, default 0).
+struct Gpu {
+    NvttbContext *ctx = nullptr;
+    bool tried = false;
+    NvttbContext *get() {
+        if (!tried) {
+            tried = true;
+            int dev = 0;
+            if (const char *e = getenv("NVTT_B200_DEVICE")) dev = atoi(e);
+            if (nvttb_context_create(dev, &ctx) != NVTTB_OK) ctx = nullptr;
+        }
+        return ctx;
+    }
+};
+Gpu g_gpu;
+
+unsigned previousPowerOfTwo(unsigned v) {
+    unsigned p = 1;
+    while (p * 2 <= v && p * 2 != 0) p *= 2;
+    return p;
+}
+unsigned nextPowerOfTwo(unsigned v) {
+    unsigned p = 1;
+    while (p < v) p *= 2;
+    return p;
+}
+unsigned nearestPowerOfTwo(unsigned v) {
+    const unsigned np2 = nextPowerOfTwo(v), pp2 = previousPowerOfTwo(v);
+    return (np2 - v <= v - pp2) ? np2 : pp2;
+}
+int countMipmaps(int w, int h, int d) {
+    int m = 0;
+    while (w != 1 || h != 1 || d != 1) {
+        w = imax(1, w / 2);
+        h = imax(1, h / 2);
+        d = imax(1, d / 2);
+        m++;
+    }
+    return m + 1;
+}
+int blockSize(Format f) {
+    switch (f) {
+    case Format_DXT1: case Format_DXT1a: case Format_DXT1n: case Format_BC4: case Format_CTX1: return 8;
+    case Format_DXT3: case Format_DXT5: case Format_DXT5n: case Format_BC3_RGBM: case Format_BC5: case Format_BC6: case Format_BC7: return 16;
+    default: return 0;
+    }
+}
+// nv::getTargetExtent (src/nvtt/Surface.cpp:220-327), including its dead "nearest multiple of four" branch.
+void getTargetExtent(int *width, int *height, int *depth, int maxExtent, RoundMode roundMode, TextureType type) {
+    int w = *width, h = *height, d = *depth;
+    if (roundMode != RoundMode_None && maxExtent > 0) maxExtent = (int)previousPowerOfTwo((unsigned)maxExtent);
+    const int m = imax(imax(w, h), d);
+    if (maxExtent > 0 && m > maxExtent) {
+        w = imax((w * maxExtent) / m, 1);
+        h = imax((h * maxExtent) / m, 1);
+        d = imax((d * maxExtent) / m, 1);
+    }
+    if (type == TextureType_2D) d = 1;
+    else if (type == TextureType_Cube) { w = h = (w + h) / 2; d = 1; }
+    if (roundMode == RoundMode_ToNextPowerOfTwo) { w = nextPowerOfTwo(w); h = nextPowerOfTwo(h); d = nextPowerOfTwo(d); }
+    else if (roundMode == RoundMode_ToNearestPowerOfTwo) { w = nearestPowerOfTwo(w); h = nearestPowerOfTwo(h); d = nearestPowerOfTwo(d); }
+    else if (roundMode == RoundMode_ToPreviousPowerOfTwo) { w = previousPowerOfTwo(w); h = previousPowerOfTwo(h); d = previousPowerOfTwo(d); }
+    else if (roundMode == RoundMode_ToNextMultipleOfFour) { w = (w + 3) & ~3; h = (h + 3) & ~3; d = (d + 3) & ~3; }
+    else if (roundMode == RoundMode_ToPreviousMultipleOfFour) { w = imax(w & ~3, 4); h = imax(h & ~3, 4); d = imax(d & ~3, 4); }
+    if (type == TextureType_2D || type == TextureType_Cube) d = 1;
+    *width = w; *height = h; *depth = d;
+}
+}  // namespace
+
+// ---- option objects ---------------------------------------------------------------------------------------
+struct CompressionOptions::Private {
+    Format format;
+    Quality quality;
+    float colorWeight[4];
+    PixelType pixelType;
+    Decoder decoder;
+    bool enableColorDithering, enableAlphaDithering, binaryAlpha;
+    int alphaThreshold;
+};
+CompressionOptions::CompressionOptions() : m(*new Private()) { reset(); }
+CompressionOptions::~CompressionOptions() { delete &m; }
+void CompressionOptions::reset() {
+    m.format = Format_DXT1;
+    m.quality = Quality_Normal;
+    m.colorWeight[0] = m.colorWeight[1] = m.colorWeight[2] = m.colorWeight[3] = 1.0f;
+    m.pixelType = PixelType_UnsignedNorm;
+    m.decoder = Decoder_D3D10;
+    m.enableColorDithering = m.enableAlphaDithering = m.binaryAlpha = false;
+    m.alphaThreshold = 127;
+}
+void CompressionOptions::setFormat(Format f) { m.format = f; }
+void CompressionOptions::setQuality(Quality q) { m.quality = q; }
+void CompressionOptions::setColorWeights(float r, float g, float b, float a) {
+    m.colorWeight[0] = r; m.colorWeight[1] = g; m.colorWeight[2] = b; m.colorWeight[3] = a;
+}
+void CompressionOptions::setPixelType(PixelType t) { m.pixelType = t; }
+void CompressionOptions::setQuantization(bool c, bool a, bool b, int t) {
+    m.enableColorDithering = c; m.enableAlphaDithering = a; m.binaryAlpha = b; m.alphaThreshold = t;
+}
+void CompressionOptions::setTargetDecoder(Decoder d) { m.decoder = d; }
+Format CompressionOptions::format() const { return m.format; }
+
+struct InputOptions::Private {
+    WrapMode wrapMode;
+    TextureType textureType;
+    InputFormat inputFormat;
+    AlphaMode alphaMode;
+    int width, height, depth, faceCount, mipmapCount, imageCount;
+    std::vector<std::vector<unsigned char>> images;  // [mip * faceCount + face], empty = NULL
+    float inputGamma, outputGamma;
+    bool generateMipmaps;
+    int maxLevel;
+    MipmapFilter mipmapFilter;
+    float kaiserWidth, kaiserAlpha, kaiserStretch;
+    bool isNormalMap, normalizeMipmaps, convertToNormalMap;
+    float heightFactors[4], bumpFrequencyScale[4];
+    int maxExtent;
+    RoundMode roundMode;
+};
+InputOptions::InputOptions() : m(*new Private()) {
+    m.width = m.height = m.depth = m.faceCount = m.mipmapCount = m.imageCount = 0;
+    reset();
+}
+InputOptions::~InputOptions() { delete &m; }
+void InputOptions::reset() {
+    m.wrapMode = WrapMode_Mirror;
+    m.textureType = TextureType_2D;
+    m.inputFormat = InputFormat_BGRA_8UB;
+    m.alphaMode = AlphaMode_None;
+    m.inputGamma = m.outputGamma = 2.2f;
+    m.generateMipmaps = true;
+    m.maxLevel = -1;
+    m.mipmapFilter = MipmapFilter_Box;
+    m.kaiserWidth = 3;
+    m.kaiserAlpha = 4.0f;
+    m.kaiserStretch = 1.0f;
+    m.isNormalMap = false;
+    m.normalizeMipmaps = true;
+    m.convertToNormalMap = false;
+    m.heightFactors[0] = m.heightFactors[1] = m.heightFactors[2] = 0.0f;
+    m.heightFactors[3] = 1.0f;
+    const float s = 1.0f + 0.5f + 0.25f + 0.125f;
+    m.bumpFrequencyScale[0] = 1.0f / s; m.bumpFrequencyScale[1] = 0.5f / s; m.bumpFrequencyScale[2] = 0.25f / s; m.bumpFrequencyScale[3] = 0.125f / s;
+    m.maxExtent = 0;
+    m.roundMode = RoundMode_None;
+}
+void InputOptions::setTextureLayout(TextureType type, int w, int h, int d, int arraySize) {
+    resetTextureLayout();
+    m.textureType = type;
+    m.width = w; m.height = h; m.depth = d;
+    m.faceCount = (type == TextureType_Cube) ? 6 : (type == TextureType_Array ? arraySize : 1);
+    m.mipmapCount = countMipmaps(w, h, d);
+    m.imageCount = m.mipmapCount * m.faceCount;
+    m.images.assign(m.imageCount, std::vector<unsigned char>());
+}
+void InputOptions::resetTextureLayout() {
+    m.images.clear();
+    m.width = m.height = m.depth = m.faceCount = m.mipmapCount = m.imageCount = 0;
+}
+bool InputOptions::setMipmapData(const void *data, int width, int height, int depth, int face, int mipLevel) {
+    if ((unsigned)face >= (unsigned)m.faceCount) return false;
+    if ((unsigned)mipLevel >= (unsigned)m.mipmapCount) return false;
+    const int idx = mipLevel * m.faceCount + face;
+    if (idx >= m.imageCount) return false;
+    int w = m.width, h = m.height, d = m.depth;
+    for (int i = 0; i < mipLevel; i++) { w = imax(1, w / 2); h = imax(1, h / 2); d = imax(1, d / 2); }
+    if (w != width || h != height || d != depth) return false;
+    size_t bpp;
+    switch (m.inputFormat) {
+    case InputFormat_BGRA_8UB: bpp = 4; break;
+    case InputFormat_RGBA_16F: bpp = 8; break;
+    case InputFormat_RGBA_32F: bpp = 16; break;
+    case InputFormat_R_32F: bpp = 4; break;
+    default: return false;
+    }
+    const size_t bytes = (size_t)width * height * depth * bpp;
+    m.images[idx].assign((const unsigned char *)data, (const unsigned char *)data + bytes);
+    return true;
+}
+void InputOptions::setFormat(InputFormat f) { m.inputFormat = f; }
+void InputOptions::setAlphaMode(AlphaMode a) { m.alphaMode = a; }
+void InputOptions::setGamma(float i, float o) { m.inputGamma = i; m.outputGamma = o; }
+void InputOptions::setWrapMode(WrapMode w) { m.wrapMode = w; }
+void InputOptions::setMipmapFilter(MipmapFilter f) { m.mipmapFilter = f; }
+void InputOptions::setMipmapGeneration(bool e, int maxLevel) { m.generateMipmaps = e; m.maxLevel = maxLevel; }
+void InputOptions::setKaiserParameters(float w, float a, float s) { m.kaiserWidth = w; m.kaiserAlpha = a; m.kaiserStretch = s; }
+void InputOptions::setNormalMap(bool b) { m.isNormalMap = b; }
+void InputOptions::setConvertToNormalMap(bool c) { m.convertToNormalMap = c; }
+void InputOptions::setHeightEvaluation(float r, float g, float b, float a) { m.heightFactors[0] = r; m.heightFactors[1] = g; m.heightFactors[2] = b; m.heightFactors[3] = a; }
+void InputOptions::setNormalFilter(float s, float md, float bg, float lg) {
+    const float total = s + md + bg + lg;  // InputOptions.cpp: normalised to sum 1
+    m.bumpFrequencyScale[0] = s / total; m.bumpFrequencyScale[1] = md / total; m.bumpFrequencyScale[2] = bg / total; m.bumpFrequencyScale[3] = lg / total;
+}
+void InputOptions::setNormalizeMipmaps(bool b) { m.normalizeMipmaps = b; }
+void InputOptions::setMaxExtents(int d) { m.maxExtent = d; }
+void InputOptions::setRoundMode(RoundMode r) { m.roundMode = r; }
+
+namespace {
+struct FileOutputHandler : public OutputHandler {
+    FILE *fp;
+    bool own;
+    FileOutputHandler(const char *name) : fp(fopen(name, "wb")), own(true) {}
+    FileOutputHandler(FILE *f) : fp(f), own(false) {}
+    ~FileOutputHandler() { if (fp && own) fclose(fp); }
+    void beginImage(int, int, int, int, int, int) {}
+    void endImage() {}
+    bool writeData(const void *data, int size) { return fp && fwrite(data, 1, (size_t)size, fp) == (size_t)size; }
+};
+}  // namespace
+
+struct OutputOptions::Private {
+    std::string fileName;
+    OutputHandler *outputHandler;
+    ErrorHandler *errorHandler;
+    bool outputHeader;
+    Container container;
+    int version;
+    bool srgb;
+    bool deleteOutputHandler;
+    void error(Error e) const { if (errorHandler) errorHandler->error(e); }
+    bool writeData(const void *d, int n) const { return outputHandler ? outputHandler->writeData(d, n) : true; }
+};
+OutputOptions::OutputOptions() : m(*new Private()) {
+    m.outputHandler = nullptr;
+    m.deleteOutputHandler = false;
+    reset();
+}
+OutputOptions::~OutputOptions() {
+    if (m.deleteOutputHandler) delete m.outputHandler;
+    delete &m;
+}
+void OutputOptions::reset() {
+    if (m.deleteOutputHandler) delete m.outputHandler;
+    m.fileName.clear();
+    m.outputHandler = nullptr;
+    m.errorHandler = nullptr;
+    m.outputHeader = true;
+    m.container = Container_DDS;
+    m.version = 0;
+    m.srgb = false;
+    m.deleteOutputHandler = false;
+}
+void OutputOptions::setFileName(const char *fileName) {
+    if (m.deleteOutputHandler) delete m.outputHandler;
+    m.fileName = fileName;
+    m.outputHandler = nullptr;
+    m.deleteOutputHandler = false;
+    FileOutputHandler *oh = new FileOutputHandler(fileName);
+    if (!oh->fp) { delete oh; return; }
+    m.outputHandler = oh;
+    m.deleteOutputHandler = true;
+}
+void OutputOptions::setFileHandle(void *fp) {
+    if (m.deleteOutputHandler) delete m.outputHandler;
+    m.fileName.clear();
+    m.outputHandler = new FileOutputHandler((FILE *)fp);
+    m.deleteOutputHandler = true;
+}
+void OutputOptions::setOutputHandler(OutputHandler *oh) {
+    if (m.deleteOutputHandler) delete m.outputHandler;
+    m.fileName.clear();
+    m.outputHandler = oh;
+    m.deleteOutputHandler = false;
+}
+void OutputOptions::setErrorHandler(ErrorHandler *eh) { m.errorHandler = eh; }
+void OutputOptions::setOutputHeader(bool b) { m.outputHeader = b; }
+void OutputOptions::setContainer(Container c) { m.container = c; }
+void OutputOptions::setUserVersion(int v) { m.version = v; }
+void OutputOptions::setSrgbFlag(bool b) { m.srgb = b; }
+
+// ---- Surface ------------------------------------------------------------------------------------------------
+struct Surface::Private {
+    NvttbSurface *s = nullptr;
+    WrapMode wrapMode = WrapMode_Mirror;
+    AlphaMode alphaMode = AlphaMode_None;
+    bool isNormalMap = false;
+    mutable std::vector<float> hostCopy;
+    mutable bool hostValid = false;
+};
+namespace {
+void surf_sync_flags(Surface::Private *m) {
+    if (!m->s) return;
+    nvttb_surface_set_wrap_mode(m->s, m->wrapMode);
+    nvttb_surface_set_alpha_mode(m->s, m->alphaMode);
+    nvttb_surface_set_normal_map(m->s, m->isNormalMap ? 1 : 0);
+}
+}  // namespace
+Surface::Surface() : m(new Private()) {}
+Surface::Surface(const Surface &o) : m(new Private()) { *this = o; }
+Surface::~Surface() {
+    if (m->s) nvttb_surface_destroy(m->s);
+    delete m;
+}
+void Surface::operator=(const Surface &o) {
+    if (this == &o) return;
+    if (m->s) { nvttb_surface_destroy(m->s); m->s = nullptr; }
+    m->wrapMode = o.m->wrapMode;
+    m->alphaMode = o.m->alphaMode;
+    m->isNormalMap = o.m->isNormalMap;
+    m->hostValid = false;
+    if (o.m->s) nvttb_surface_clone(o.m->s, &m->s);  // deep device copy (the reference's copy-on-write, eager)
+}
+void Surface::setWrapMode(WrapMode w) { m->wrapMode = w; surf_sync_flags(m); }
+void Surface::setAlphaMode(AlphaMode a) { m->alphaMode = a; surf_sync_flags(m); }
+void Surface::setNormalMap(bool b) { m->isNormalMap = b; surf_sync_flags(m); }
+bool Surface::isNull() const { return m->s == nullptr || nvttb_surface_width(m->s) == 0; }
+int Surface::width() const { return m->s ? nvttb_surface_width(m->s) : 0; }
+int Surface::height() const { return m->s ? nvttb_surface_height(m->s) : 0; }
+int Surface::depth() const { return isNull() ? 0 : 1; }
+TextureType Surface::type() const { return TextureType_2D; }
+WrapMode Surface::wrapMode() const { return m->wrapMode; }
+AlphaMode Surface::alphaMode() const { return m->alphaMode; }
+bool Surface::isNormalMap() const { return m->isNormalMap; }
+int Surface::countMipmaps() const { return isNull() ? 0 : ::countMipmaps(width(), height(), 1); }
+const float *Surface::data() const {
+    if (isNull()) return nullptr;
+    if (!m->hostValid) {
+        m->hostCopy.resize((size_t)4 * width() * height());
+        if (nvttb_surface_download(m->s, m->hostCopy.data()) != NVTTB_OK) return nullptr;
+        m->hostValid = true;
+    }
+    return m->hostCopy.data();
+}
+bool Surface::setImage(InputFormat format, int w, int h, int d, const void *data) {
+    if (d != 1) return false;  // 3D textures are outside the hot path
+    NvttbContext *ctx = g_gpu.get();
+    if (!ctx) return false;
+    if (!m->s) {
+        if (nvttb_surface_create(ctx, &m->s) != NVTTB_OK) return false;
+        surf_sync_flags(m);
+    }
+    m->hostValid = false;
+    return nvttb_surface_set_image(m->s, format, w, h, data, NVTTB_HOST) == NVTTB_OK;
+}
+void Surface::resize(int w, int h, int d, ResizeFilter filter) {
+    if (isNull() || d != 1) return;
+    m->hostValid = false;
+    nvttb_surface_resize(m->s, w, h, filter, 0, 0.0f, nullptr);
+}
+void Surface::resize(int w, int h, int d, ResizeFilter filter, float filterWidth, const float *params) {
+    if (isNull() || d != 1) return;
+    m->hostValid = false;
+    nvttb_surface_resize(m->s, w, h, filter, 1, filterWidth, params);
+}
+bool Surface::canMakeNextMipmap(int min_size) {
+    if (isNull()) return false;
+    const int w = width(), h = height();
+    if (min_size == 1) return !(w == 1 && h == 1);
+    return !(w <= min_size || h <= min_size);
+}
+bool Surface::buildNextMipmap(MipmapFilter filter, int min_size) {
+    if (!canMakeNextMipmap(min_size)) return false;
+    int built = 0;
+    m->hostValid = false;
+    return nvttb_surface_build_next_mipmap(m->s, filter, 0, 0.0f, nullptr, &built) == NVTTB_OK && built;
+}
+bool Surface::buildNextMipmap(MipmapFilter filter, float filterWidth, const float *params, int min_size) {
+    if (!canMakeNextMipmap(min_size)) return false;
+    int built = 0;
+    m->hostValid = false;
+    // params == NULL keeps the filter's own defaults (Kaiser: alpha 4, stretch 1)
+    float def[2] = {4.0f, 1.0f};
+    return nvttb_surface_build_next_mipmap(m->s, filter, 1, filterWidth, params ? params : def, &built) == NVTTB_OK && built;
+}
+void Surface::toLinear(float g) { if (!isNull()) { m->hostValid = false; nvttb_surface_to_linear(m->s, g); } }
+void Surface::toGamma(float g) { if (!isNull()) { m->hostValid = false; nvttb_surface_to_gamma(m->s, g); } }
+void Surface::toGreyScale(float r, float g, float b, float a) { if (!isNull()) { m->hostValid = false; nvttb_surface_to_grey_scale(m->s, r, g, b, a); } }
+void Surface::toNormalMap(float sm, float md, float bg, float lg) {
+    if (isNull()) return;
+    m->hostValid = false;
+    if (nvttb_surface_to_normal_map(m->s, sm, md, bg, lg) == NVTTB_OK) { m->isNormalMap = true; surf_sync_flags(m); }
+}
+void Surface::normalizeNormalMap() { if (!isNull() && m->isNormalMap) { m->hostValid = false; nvttb_surface_normalize_normal_map(m->s); } }
+void Surface::packNormals(float scale, float bias) {
+    if (isNull()) return;
+    m->hostValid = false;
+    if (scale == 0.5f && bias == 0.5f) nvttb_surface_pack_normals(m->s);
+}
+void Surface::expandNormals(float scale, float bias) {
+    if (isNull()) return;
+    m->hostValid = false;
+    if (scale == 2.0f && bias == -1.0f) nvttb_surface_expand_normals(m->s);
+}
+
+// ---- Compressor ---------------------------------------------------------------------------------------------
+struct Compressor::Private {
+    bool cudaSupported, cudaEnabled;
+    TaskDispatcher *dispatcher;
+};
+Compressor::Compressor() : m(*new Private()) {
+    m.cudaSupported = g_gpu.get() != nullptr;
+    m.cudaEnabled = m.cudaSupported;
+    m.dispatcher = nullptr;
+    if (!m.cudaSupported) fprintf(stderr, "nvtt (B200): no CUDA device available — compression calls will fail with Error_CudaError\n");
+}
+Compressor::~Compressor() { delete &m; }
+// The GPU path is the only implementation: the request is accepted for source compatibility (nvcompress -nocuda) but there is
+// no CPU encoder to switch to, so it does not change what runs.
+void Compressor::enableCudaAcceleration(bool) { m.cudaEnabled = m.cudaSupported; }
+bool Compressor::isCudaAccelerationEnabled() const { return m.cudaEnabled; }
+void Compressor::setTaskDispatcher(TaskDispatcher *disp) { m.dispatcher = disp; }
+
+namespace {
+void fill_encode(NvttbEncodeDesc *e, const CompressionOptions::Private &co, AlphaMode am, int w, int h) {
+    e->format = co.format;
+    e->quality = co.quality;
+    e->alphaMode = am;
+    e->pixelType = co.pixelType;
+    for (int i = 0; i < 4; i++) e->colorWeights[i] = co.colorWeight[i];
+    e->width = w;
+    e->height = h;
+    e->applyToGamma = 0;
+}
+int image_size(int w, int h, int d, Format f) { return ((w + 3) / 4) * ((h + 3) / 4) * blockSize(f) * d; }
+
+struct DDSHeaderBytes {  // nvimage/DirectDrawSurface.h:283-430 layout, little endian
+    uint32_t fourcc, size, flags, height, width, pitch, depth, mipmapcount, reserved[11];
+    uint32_t pf_size, pf_flags, pf_fourcc, pf_bitcount, pf_rmask, pf_gmask, pf_bmask, pf_amask;
+    uint32_t caps1, caps2, caps3, caps4, notused;
+    uint32_t dxgiFormat, resourceDimension, miscFlag, arraySize, reserved10;
+};
+inline uint32_t fourcc(char a, char b, char c, char d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); }
+
+struct EmitCtx {
+    const OutputOptions::Private *oo;
+};
+int emit_cb(void *user, int face, int mip, int w, int h, int d, const void *data, size_t size) {
+    const OutputOptions::Private *oo = ((EmitCtx *)user)->oo;
+    if (oo->outputHandler) {
+        oo->outputHandler->beginImage((int)size, w, h, d, face, mip);
+        oo->outputHandler->writeData(data, (int)size);
+        oo->outputHandler->endImage();
+    }
+    return 1;
+}
+}  // namespace
+
+bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int arraySize, int mipmapCount, bool isNormalMap,
+                              const CompressionOptions &compressionOptions, const OutputOptions &outputOptions) const {
+    const CompressionOptions::Private &co = compressionOptions.m;
+    const OutputOptions::Private &oo = outputOptions.m;
+    if (w <= 0 || h <= 0 || d <= 0 || arraySize <= 0 || mipmapCount <= 0) {
+        oo.error(Error_InvalidInput);
+        return false;
+    }
+    if (!oo.outputHeader) return true;
+    if (oo.container == Container_KTX) {  // KTX writer: SURVEY §8(f), not on the hot path yet
+        oo.error(Error_UnsupportedOutputFormat);
+        return false;
+    }
+    DDSHeaderBytes hd;
+    memset(&hd, 0, sizeof hd);
+    hd.fourcc = fourcc('D', 'D', 'S', ' ');
+    hd.size = 124;
+    hd.flags = 0x1 | 0x1000;  // CAPS | PIXELFORMAT
+    hd.reserved[9] = fourcc('N', 'V', 'T', 'T');
+    hd.reserved[10] = (2 << 16) | (1 << 8) | 2;
+    hd.pf_size = 32;
+    hd.caps1 = 0x1000;  // TEXTURE
+    hd.reserved[7] = fourcc('U', 'V', 'E', 'R');
+    hd.reserved[8] = (uint32_t)oo.version;
+    if (textureType == TextureType_2D) { hd.resourceDimension = 3; hd.miscFlag = 0; hd.arraySize = 1; }
+    else if (textureType == TextureType_Cube) { hd.caps1 |= 0x8; hd.caps2 = 0x200 | 0xFC00; hd.resourceDimension = 3; hd.miscFlag = 0x4; hd.arraySize = 1; }
+    else if (textureType == TextureType_3D) { hd.caps2 = 0x200000; hd.resourceDimension = 4; hd.arraySize = 1; hd.flags |= 0x800000; hd.depth = d; }
+    else { hd.resourceDimension = 3; hd.arraySize = arraySize; }
+    hd.flags |= 0x4; hd.width = w;
+    hd.flags |= 0x2; hd.height = h;
+    if (mipmapCount == 0 || mipmapCount == 1) {
+        hd.flags &= ~0x20000u;
+        hd.mipmapcount = 1;
+        hd.caps1 = (hd.caps2 == 0) ? 0x1000 : (0x1000 | 0x8);
+    } else {
+        hd.flags |= 0x20000;
+        hd.mipmapcount = mipmapCount;
+        hd.caps1 |= 0x8 | 0x400000;
+    }
+    bool supported = true;
+    const Format f = co.format;
+    if (oo.container == Container_DDS10) {
+        hd.pf_flags = 0x4;
+        hd.pf_fourcc = fourcc('D', 'X', '1', '0');
+        if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) {
+            hd.dxgiFormat = oo.srgb ? 72 : 71;
+            if (f == Format_DXT1a) hd.pf_flags |= 0x1;
+            if (isNormalMap) hd.pf_flags |= 0x80000000u;
+        } else if (f == Format_DXT3) hd.dxgiFormat = oo.srgb ? 75 : 74;
+        else if (f == Format_DXT5 || f == Format_BC3_RGBM) hd.dxgiFormat = oo.srgb ? 78 : 77;
+        else if (f == Format_DXT5n) { hd.dxgiFormat = 77; if (isNormalMap) hd.pf_flags |= 0x80000000u; }
+        else if (f == Format_BC4) hd.dxgiFormat = 80;
+        else if (f == Format_BC5) { hd.dxgiFormat = 83; if (isNormalMap) hd.pf_flags |= 0x80000000u; }
+        else if (f == Format_BC6) hd.dxgiFormat = 95;  // always UF16 (Context.cpp:709-710)
+        else if (f == Format_BC7) { hd.dxgiFormat = oo.srgb ? 99 : 98; if (isNormalMap) hd.pf_flags |= 0x80000000u; }
+        else supported = false;
+    } else {
+        hd.flags &= ~0x8u;
+        hd.flags |= 0x80000;  // LINEARSIZE
+        hd.pitch = (uint32_t)image_size(w, h, d, f);
+        hd.pf_flags = 0x4;
+        if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) { hd.pf_fourcc = fourcc('D', 'X', 'T', '1'); if (isNormalMap) hd.pf_flags |= 0x80000000u; }
+        else if (f == Format_DXT3) hd.pf_fourcc = fourcc('D', 'X', 'T', '3');
+        else if (f == Format_DXT5 || f == Format_BC3_RGBM) hd.pf_fourcc = fourcc('D', 'X', 'T', '5');
+        else if (f == Format_DXT5n) { hd.pf_fourcc = fourcc('D', 'X', 'T', '5'); if (isNormalMap) { hd.pf_flags |= 0x80000000u; hd.pf_bitcount = fourcc('A', '2', 'D', '5'); } }
+        else if (f == Format_BC4) hd.pf_fourcc = fourcc('A', 'T', 'I', '1');
+        else if (f == Format_BC5) { hd.pf_fourcc = fourcc('A', 'T', 'I', '2'); if (isNormalMap) { hd.pf_flags |= 0x80000000u; hd.pf_bitcount = fourcc('A', '2', 'X', 'Y'); } }
+        else supported = false;  // BC6/BC7 need the DX10 header (Context.cpp:826-834)
+        if (oo.srgb) hd.pf_flags |= 0x40000000u;
+    }
+    if (!supported) {
+        oo.error(Error_UnsupportedOutputFormat);
+        return false;
+    }
+    const int headerSize = (hd.pf_fourcc == fourcc('D', 'X', '1', '0')) ? 148 : 128;
+    const bool ok = oo.writeData(&hd, headerSize);
+    if (!ok) oo.error(Error_FileWrite);
+    return ok;
+}
+
+bool Compressor::outputHeader(const Surface &img, int mipmapCount, const CompressionOptions &co, const OutputOptions &oo) const {
+    return outputHeader(img.type(), img.width(), img.height(), img.depth(), 1, mipmapCount, img.isNormalMap(), co, oo);
+}
+
+int Compressor::estimateSize(int w, int h, int d, int mipmapCount, const CompressionOptions &co) const {
+    int size = 0;
+    for (int i = 0; i < mipmapCount; i++) {
+        size += image_size(w, h, d, co.m.format);
+        w = imax(1, w / 2); h = imax(1, h / 2); d = imax(1, d / 2);
+    }
+    return size;
+}
+int Compressor::estimateSize(const Surface &img, int mipmapCount, const CompressionOptions &co) const {
+    return estimateSize(img.width(), img.height(), img.depth(), mipmapCount, co);
+}
+int Compressor::estimateSize(const InputOptions &io, const CompressionOptions &co) const {
+    int w = io.m.width, h = io.m.height, d = io.m.depth;
+    getTargetExtent(&w, &h, &d, io.m.maxExtent, io.m.roundMode, io.m.textureType);
+    int mipmapCount = 1;
+    if (io.m.generateMipmaps) {
+        mipmapCount = countMipmaps(w, h, d);
+        if (io.m.maxLevel > 0) mipmapCount = imin(mipmapCount, io.m.maxLevel);
+    }
+    return io.m.faceCount * estimateSize(w, h, d, mipmapCount, co);
+}
+
+// Compressor::Private::compress(AlphaMode,w,h,d,face,mip,rgba,...)  (Context.cpp:486-516)
+static bool compress_level(const Compressor::Private &m, AlphaMode am, int w, int h, int d, int face, int mip, const float *rgba, int loc,
+                           const CompressionOptions::Private &co, const OutputOptions::Private &oo) {
+    const int size = image_size(w, h, d, co.format);
+    if (oo.outputHandler) oo.outputHandler->beginImage(size, w, h, d, face, mip);
+    bool ok = true;
+    NvttbContext *ctx = g_gpu.get();
+    if (!ctx || !m.cudaEnabled) {
+        oo.error(Error_CudaError);
+        ok = false;
+    } else if (d != 1 || !nvttb_format_supported(co.format, co.quality)) {
+        oo.error(Error_UnsupportedFeature);  // reference: signals the error and still returns true (Context.cpp:504-515)
+    } else {
+        NvttbEncodeDesc e;
+        fill_encode(&e, co, am, w, h);
+        std::vector<unsigned char> out((size_t)size);
+        const int rc = nvttb_encode_level(ctx, &e, rgba, loc, out.data(), NVTTB_HOST, out.size());
+        if (rc != NVTTB_OK) {
+            oo.error((Error)(rc - 1));
+            ok = false;
+        } else {
+            oo.writeData(out.data(), size);
+        }
+    }
+    if (oo.outputHandler) oo.outputHandler->endImage();
+    return ok;
+}
+
+bool Compressor::compress(int w, int h, int d, int face, int mipmap, const float *rgba, const CompressionOptions &co, const OutputOptions &oo) const {
+    return compress_level(m, AlphaMode_None, w, h, d, face, mipmap, rgba, NVTTB_HOST, co.m, oo.m);
+}
+bool Compressor::compress(const Surface &img, int face, int mipmap, const CompressionOptions &co, const OutputOptions &oo) const {
+    if (img.isNull()) return false;
+    return compress_level(m, img.alphaMode(), img.width(), img.height(), 1, face, mipmap, nvttb_surface_device_data(img.m->s), NVTTB_DEVICE, co.m, oo.m);
+}
+
+// Compressor::Private::compress(InputOptions...)  (Context.cpp:217-346), DDS order.
+bool Compressor::process(const InputOptions &inputOptions, const CompressionOptions &compressionOptions, const OutputOptions &outputOptions) const {
+    const InputOptions::Private &io = inputOptions.m;
+    const CompressionOptions::Private &co = compressionOptions.m;
+    const OutputOptions::Private &oo = outputOptions.m;
+    if (oo.outputHandler == nullptr) {  // hasValidOutputHandler
+        oo.error(Error_FileOpen);
+        return false;
+    }
+    const int faceCount = io.faceCount;
+    int width = io.width, height = io.height, depth = io.depth;
+    const int arraySize = io.textureType == TextureType_Array ? faceCount : 1;
+    getTargetExtent(&width, &height, &depth, io.maxExtent, io.roundMode, io.textureType);
+    const bool canUseSourceImages = (io.width == width && io.height == height && io.depth == depth);
+    int mipmapCount = 1;
+    if (io.generateMipmaps) {
+        mipmapCount = countMipmaps(width, height, depth);
+        if (io.maxLevel > 0) mipmapCount = imin(mipmapCount, io.maxLevel);
+    }
+    if (!outputHeader(io.textureType, width, height, depth, arraySize, mipmapCount, io.isNormalMap, compressionOptions, outputOptions)) return false;
+
+    NvttbContext *ctx = g_gpu.get();
+    if (!ctx || !m.cudaEnabled) {
+        oo.error(Error_CudaError);
+        return false;
+    }
+    if (depth != 1 || co.enableColorDithering || co.enableAlphaDithering || co.binaryAlpha || !nvttb_format_supported(co.format, co.quality)) {
+        oo.error(Error_UnsupportedFeature);
+        return false;
+    }
+    for (int f = 0; f < faceCount; f++)
+        if (io.images[f].empty()) { oo.error(Error_InvalidInput); return false; }
+    bool userMips = false;
+    for (int i = faceCount; i < io.imageCount; i++) userMips = userMips || !io.images[i].empty();
+
+    if (canUseSourceImages && !userMips) {
+        // fused device pipeline
+        NvttbProcessDesc d;
+        memset(&d, 0, sizeof d);
+        d.inputFormat = io.inputFormat;
+        d.width = width; d.height = height; d.faceCount = faceCount;
+        d.wrapMode = io.wrapMode;
+        d.mipmapFilter = io.mipmapFilter;
+        d.generateMipmaps = io.generateMipmaps ? 1 : 0;
+        d.maxLevel = io.maxLevel;
+        d.kaiserWidth = io.kaiserWidth; d.kaiserAlpha = io.kaiserAlpha; d.kaiserStretch = io.kaiserStretch;
+        d.inputGamma = io.inputGamma; d.outputGamma = io.outputGamma;
+        d.isNormalMap = io.isNormalMap; d.convertToNormalMap = io.convertToNormalMap; d.normalizeMipmaps = io.normalizeMipmaps;
+        for (int i = 0; i < 4; i++) { d.heightFactors[i] = io.heightFactors[i]; d.bumpFrequencyScale[i] = io.bumpFrequencyScale[i]; }
+        d.alphaMode = io.alphaMode;
+        fill_encode(&d.encode, co, io.alphaMode, width, height);
+        std::vector<const void *> ptrs(faceCount);
+        for (int f = 0; f < faceCount; f++) ptrs[f] = io.images[f].data();
+        EmitCtx ec{&oo};
+        const int rc = nvttb_process(ctx, &d, ptrs.data(), NVTTB_HOST, emit_cb, &ec);
+        if (rc != NVTTB_OK) {
+            oo.error((Error)(rc - 1));
+            return false;
+        }
+        return true;
+    }
+
+    // general path (input resize and/or user-supplied mip levels): the reference's loop, one Surface op at a time
+    Surface img;
+    img.setWrapMode(io.wrapMode);
+    img.setAlphaMode(io.alphaMode);
+    img.setNormalMap(io.isNormalMap);
+    for (int f = 0; f < faceCount; f++) {
+        int w = width, h = height;
+        bool canUseSourceImagesForThisFace = canUseSourceImages;
+        if (!img.setImage(io.inputFormat, io.width, io.height, 1, io.images[f].data())) { oo.error(Error_CudaError); return false; }
+        if (io.convertToNormalMap) {
+            img.toGreyScale(io.heightFactors[0], io.heightFactors[1], io.heightFactors[2], io.heightFactors[3]);
+            img.toNormalMap(io.bumpFrequencyScale[0], io.bumpFrequencyScale[1], io.bumpFrequencyScale[2], io.bumpFrequencyScale[3]);
+        }
+        if (!img.isNormalMap()) img.toLinear(io.inputGamma);
+        img.resize(w, h, 1, ResizeFilter_Box);
+        {
+            Surface tmp = img;
+            if (!img.isNormalMap()) tmp.toGamma(io.outputGamma);
+            if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
+        }
+        for (int mip = 1; mip < mipmapCount; mip++) {
+            w = imax(1, w / 2);
+            h = imax(1, h / 2);
+            const int idx = mip * faceCount + f;
+            bool useSourceImages = false;
+            if (canUseSourceImagesForThisFace) {
+                if (io.images[idx].empty()) canUseSourceImagesForThisFace = false;
+                else useSourceImages = true;
+            }
+            if (useSourceImages) {
+                img.setImage(io.inputFormat, w, h, 1, io.images[idx].data());
+                if (!img.isNormalMap()) img.toLinear(io.inputGamma);
+            } else if (io.mipmapFilter == MipmapFilter_Kaiser) {
+                const float params[2] = {io.kaiserAlpha, io.kaiserStretch};
+                img.buildNextMipmap(MipmapFilter_Kaiser, io.kaiserWidth, params);
+            } else {
+                img.buildNextMipmap(io.mipmapFilter);
+            }
+            Surface tmp;
+            if (img.isNormalMap()) {
+                if (io.normalizeMipmaps) {
+                    img.expandNormals();
+                    img.normalizeNormalMap();
+                    img.packNormals();
+                }
+                tmp = img;
+            } else {
+                tmp = img;
+                tmp.toGamma(io.outputGamma);
+            }
+            if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
+        }
+    }
+    return true;
+}
+
+unsigned int nvtt::version() { return NVTT_VERSION; }
+const char *nvtt::errorString(Error e) {
+    static const char *const names[] = {"Unknown error", "Invalid input", "Unsupported feature", "CUDA error", "Error opening file", "Error writing through output handler", "Unsupported output format"};
+    return (unsigned)e < 7 ? names[e] : "Invalid error";
+}

@@ -2,7 +2,9 @@
 //
 // C-ABI harness around the UNMODIFIED reference library (NVTT 2.1.2, /root/reference), compiled by
 // oracle/build_ref.sh into oracle/_ref/libnvtt_ref.so.  It only *calls* the reference's public API
-// (src/nvtt/nvtt.h) — no reference source is copied here.  The tests use it (1) to pin the plain-C
+// (src/nvtt/nvtt.h) — no reference source is copied here.  The same file, compiled unchanged against the drop-in header
+// nvidia-texture-tools_b200/host/nvtt/nvtt.h (tests/build_host_harness.sh, -DNVTT_HARNESS_NO_DECODE), drives OUR library
+// through the identical nvtt:: calls — that is the source-compatibility test of the boundary.  The tests use it (1) to pin the plain-C
 // restatement in oracle/*.c and (2) as the checker for the CUDA path; bench.py uses it as the
 // `--impl reference` arm / cpu_baseline ("kind": "reference").
 #include <nvtt/nvtt.h>
@@ -138,6 +140,22 @@ long ref_process(const RefProcessDesc *d, const void *const *images, unsigned ch
     return (long)mh.buf.size();
 }
 
+// Header only: Compressor::outputHeader(type,w,h,d,arraySize,mipmapCount,isNormalMap,...) (src/nvtt/Context.cpp:604-869)
+long ref_output_header(int textureType, int w, int h, int arraySize, int mipmapCount, int isNormalMap, int format, int container,
+                       unsigned char *out, long out_cap) {
+    Compressor ctx;
+    CompressionOptions co;
+    co.setFormat((Format)format);
+    OutputOptions oo;
+    MemHandler mh;
+    oo.setOutputHandler(&mh);
+    oo.setContainer((Container)container);
+    if (!ctx.outputHeader((TextureType)textureType, w, h, 1, arraySize, mipmapCount, isNormalMap != 0, co, oo)) return -1;
+    if ((long)mh.buf.size() > out_cap) return -2;
+    memcpy(out, mh.buf.data(), mh.buf.size());
+    return (long)mh.buf.size();
+}
+
 // ---- Surface ("imperative") API, handle based (src/nvtt/Surface.cpp) ----
 void *ref_surf_create(int wrapMode, int alphaMode, int isNormalMap) {
     Surface *s = new Surface();
@@ -182,6 +200,7 @@ void ref_surf_normalize_normal_map(void *h) { ((Surface *)h)->normalizeNormalMap
 void ref_surf_to_grey_scale(void *h, float r, float g, float b, float a) { ((Surface *)h)->toGreyScale(r, g, b, a); }
 void ref_surf_to_normal_map(void *h, float sm, float md, float bg, float lg) { ((Surface *)h)->toNormalMap(sm, md, bg, lg); }
 
+#ifndef NVTT_HARNESS_NO_DECODE
 // Decode a BCn level with the reference decoder (Surface::setImage2D, src/nvtt/Surface.cpp:908-1118) -> planar fp32.
 int ref_decode(int format, int w, int h, const void *data, float *out) {
     Surface s;
@@ -189,6 +208,8 @@ int ref_decode(int format, int w, int h, const void *data, float *out) {
     memcpy(out, s.data(), sizeof(float) * 4 * (size_t)w * h);
     return 1;
 }
+
+#endif
 
 int ref_version() { return (int)nvtt::version(); }
 }

@@ -42,3 +42,59 @@ def test_no_cpu_fallback(nvtt):
     with pytest.raises(nvtt.NvttbError) as e:
         nvtt.Context(0)
     assert e.value.code == 4  # Error_CudaError
+
+
+def test_host_library_exports_nvtt_api():
+    """The C++ drop-in (lib/libnvtt.so) exports the nvtt:: classes the reference's callers link against."""
+    import subprocess
+    lib = os.path.join(ROOT, "nvidia-texture-tools_b200", "lib", "libnvtt.so")
+    if not os.path.exists(lib):
+        pytest.skip("host library not built")
+    syms = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True).stdout
+    for want in ("nvtt::Compressor::process(", "nvtt::Compressor::compress(int, int, int, int, int, float const*",
+                 "nvtt::Compressor::outputHeader(", "nvtt::Compressor::estimateSize(", "nvtt::InputOptions::setMipmapData(",
+                 "nvtt::CompressionOptions::setFormat(", "nvtt::OutputOptions::setOutputHandler(", "nvtt::Surface::buildNextMipmap(",
+                 "nvtt::Surface::toGamma(", "nvtt::version()"):
+        assert want in syms, want
+
+
+def test_dds_header_matches_reference(ref):
+    """The DDS / DDS10 header written by our outputHeader (host code, no GPU needed) is byte-identical to the reference's."""
+    import ctypes as C
+    import numpy as np
+    so = os.path.join(ROOT, "tests", "_build", "libnvtt_b200_harness.so")
+    if not os.path.exists(so):
+        pytest.skip("harness against the drop-in header not built")
+    ours = C.CDLL(so)
+    ours.ref_process.restype = C.c_long
+    ours.ref_process.argtypes = [C.POINTER(ref.RefProcessDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_long]
+    img = np.zeros((8, 8, 4), np.uint8)
+    for fmt in (ref.Format_BC1, ref.Format_DXT1a, ref.Format_BC2, ref.Format_BC3, ref.Format_BC3n, ref.Format_BC4, ref.Format_BC5,
+                ref.Format_BC6, ref.Format_BC7):
+        for container in (ref.Container_DDS, ref.Container_DDS10):
+            for normal in (False, True):
+                for (ttype, faces) in ((ref.TextureType_2D, 1), (ref.TextureType_Cube, 6)):
+                    for mips in (True, False):
+                        if container == ref.Container_DDS and fmt in (ref.Format_BC6, ref.Format_BC7):
+                            continue  # reference reports Error_UnsupportedOutputFormat
+                        try:
+                            want = ref.process([img] * faces, 0, 8, 8, fmt, 1, header=True, container=container, normal_map=normal,
+                                               texture_type=ttype, mipmaps=mips, pixel_type=5 if fmt == ref.Format_BC6 else 0)
+                        except RuntimeError:
+                            continue
+                        hs = 148 if container == ref.Container_DDS10 else 128
+                        # ours: without a GPU process() fails after the header was written; capture the header through
+                        # a direct outputHeader call instead
+                        got = _our_header(ours, fmt, container, normal, ttype, faces, 4 if mips else 1)
+                        assert got is not None
+                        assert bytes(want[:hs]) == got, (fmt, container, normal, ttype, mips)
+
+
+def _our_header(ours, fmt, container, normal, ttype, faces, mipcount):
+    import ctypes as C
+    if not hasattr(ours, "ref_output_header"):
+        return None
+    buf = (C.c_ubyte * 256)()
+    ours.ref_output_header.restype = C.c_long
+    n = ours.ref_output_header(ttype, 8, 8, faces if ttype == 3 else 1, mipcount, int(normal), fmt, container, buf, 256)
+    return bytes(buf[:n]) if n > 0 else None
