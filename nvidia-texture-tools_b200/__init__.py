@@ -6,3 +6,4 @@ The directory name is not a valid Python identifier: load it with `nvtt_b200_loa
 """
 from .capi import *  # noqa: F401,F403
 from . import synth  # noqa: E402,F401
+from . import sharding  # noqa: E402,F401

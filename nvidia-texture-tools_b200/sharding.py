@@ -1,0 +1,34 @@
+"""Host-side sharding helpers for the multi-GPU path (one process per GPU, torch.distributed for the plumbing).
+The encode itself never communicates: textures / cube faces are independent (src/nvtt/Context.cpp:260 loops over them
+serially).  Only the owner of the OutputHandler gathers the BCn bytes of the other ranks."""
+import numpy as np
+
+
+def face_range(face_count, rank, world):
+    """Contiguous, balanced split of faces/textures [0, face_count) over ranks; the first `rem` ranks get one extra."""
+    base, rem = divmod(face_count, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_bytes(mine, dst=0):
+    """Gathers variable-length uint8 arrays to rank `dst` in rank order (face-major order is preserved because
+    face_range is contiguous).  Works with the gloo (CPU tensors) and nccl (CUDA tensors) backends."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n = torch.tensor([mine.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(sizes) if sizes else 0
+    buf = torch.zeros(max(cap, 1), dtype=torch.uint8, device=dev)
+    if mine.size:
+        buf[:mine.size] = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+    out = [torch.zeros(max(cap, 1), dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(out, buf)
+    if rank != dst:
+        return None
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)]) if sizes else np.zeros(0, np.uint8)

@@ -1,0 +1,53 @@
+"""Case tables shared by tests/golden/make_golden.py (writer) and the tests that read tests/golden/golden_v1.npz."""
+import numpy as np
+
+
+def make_input(kind, w, h, planar):
+    import nvtt_b200_loader
+    s = nvtt_b200_loader.load().synth
+    if kind == "photo":
+        img = s.photo_bgra8(w, h, seed=1234, alpha=True)
+    elif kind == "normal":
+        img = s.normal_bgra8(w, h, seed=7)
+    elif kind == "adv":
+        img = s.adversarial_bgra8(w, h, seed=5)
+    elif kind == "dark":
+        img = (s.photo_bgra8(w, h, seed=3, alpha=True) // 5).astype(np.uint8)
+    else:
+        raise ValueError(kind)
+    return s.planar_from_bgra8(img) if planar else img
+
+
+def level_cases():
+    """key -> (input kind, w, h, nvtt format, quality, alphaMode, colour weights)"""
+    c = {}
+    for kind in ("photo", "adv", "dark"):
+        for (w, h) in ((48, 40), (13, 7)):
+            for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (1, 2)), (6, "bc4", (0, 1)), (7, "bc5", (0, 1))):
+                for q in qs:
+                    c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1))
+    c["level_bc1_photo_48x40_q2_transp_w"] = ("photo", 48, 40, 1, 2, 1, (0.3, 0.59, 0.11, 1.0))
+    c["level_bc3_photo_48x40_q1_transp_w"] = ("photo", 48, 40, 4, 1, 1, (0.3, 0.59, 0.11, 1.0))
+    return c
+
+
+def pipeline_cases():
+    """key -> (input kind, w, h, format, quality, kwargs of refapi.process / make_process_desc)"""
+    return {
+        "pipe_bc1_normal_box_64": ("photo", 64, 64, 1, 1, dict(mip_filter=0, wrap=0)),
+        "pipe_bc1_production_box_37x22": ("photo", 37, 22, 1, 2, dict(mip_filter=0)),
+        "pipe_bc3_kaiser_mirror_64": ("photo", 64, 64, 4, 1, dict(mip_filter=2, wrap=2)),
+        "pipe_bc3_triangle_transp_37x22": ("photo", 37, 22, 4, 1, dict(mip_filter=1, alpha_mode=1)),
+        "pipe_bc5_normal_kaiser_64": ("normal", 64, 64, 7, 1, dict(mip_filter=2, normal_map=True)),
+        "pipe_bc4_box_repeat_33x16": ("photo", 33, 16, 6, 1, dict(mip_filter=0, wrap=1)),
+    }
+
+
+def imageop_cases():
+    """key -> (input kind, w, h, wrap, mipmap filter, params or None): sha256 of every level after toLinear ... toGamma"""
+    c = {}
+    for (w, h) in ((64, 64), (37, 22), (33, 16), (7, 1)):
+        for wrap in (0, 1, 2):
+            for filt, params, name in ((0, None, "box"), (1, None, "tri"), (2, (3.0, 4.0, 1.0), "kaiser")):
+                c["ops_%s_wrap%d_%dx%d" % (name, wrap, w, h)] = ("photo", w, h, wrap, filt, params)
+    return c

@@ -1,0 +1,84 @@
+"""CPU tests of the oracle (oracle/oracle.c, plain-C restatement): pinned against the golden vectors generated from the
+unmodified reference (tests/golden/golden_v1.npz) and, where the reference build is present, against it directly."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracleapi
+    if not oracleapi.available():
+        pytest.skip("oracle/_build/liboracle.so not built (run __graft_entry__.build())")
+    return oracleapi
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def test_oracle_levels_match_golden(orc, golden):
+    for key, (kind, w, h, fmt, q, am, cw) in G.level_cases().items():
+        img = G.make_input(kind, w, h, planar=True)
+        got = orc.compress_level(fmt, q, img, am, cw)
+        assert np.array_equal(got, golden[key]), key
+
+
+def test_oracle_pipeline_matches_golden(orc, golden):
+    for key, (kind, w, h, fmt, q, kw) in G.pipeline_cases().items():
+        img = G.make_input(kind, w, h, planar=False)
+        got = orc.process([img], 0, w, h, fmt, q, **kw)
+        assert np.array_equal(got, golden[key]), key
+
+
+def test_oracle_image_ops_match_golden(orc, golden):
+    for key, (kind, w, h, wrap, filt, params) in G.imageop_cases().items():
+        img = G.make_input(kind, w, h, planar=False)
+        cur = orc.to_linear(orc.set_image(0, w, h, img), 2.2)
+        hashes = [_sha(cur)]
+        fw, p0, p1 = (0.5, 0, 0) if filt == 0 else (1.0, 0, 0) if filt == 1 else params
+        while cur.shape[1] > 1 or cur.shape[2] > 1:
+            cur = orc.next_mipmap(cur, filt, fw, p0, p1, wrap)
+            hashes.append(_sha(cur))
+        hashes.append(_sha(orc.to_gamma(cur, 2.2)))
+        assert np.array_equal(np.stack(hashes), golden[key]), key
+
+
+def test_oracle_vs_reference_direct(orc, ref, nvtt):
+    """Wider sweep against the reference itself (only where oracle/_ref exists)."""
+    s = nvtt.synth
+    rng = np.random.default_rng(3)
+    for (w, h) in ((32, 32), (21, 9), (4, 4), (2, 3), (1, 1)):
+        imgs = [s.planar_from_bgra8(s.photo_bgra8(w, h, seed=8, alpha=True)), s.planar_from_bgra8(s.adversarial_bgra8(w, h, seed=2)),
+                rng.random((4, h, w), dtype=np.float32) * 1.5 - 0.25]
+        for img in imgs:
+            for fmt, qs in ((1, (0, 1, 2, 3)), (4, (1, 2)), (6, (0, 1)), (7, (0, 1))):
+                for q in qs:
+                    for am in (0, 1):
+                        a = orc.compress_level(fmt, q, img, am, (0.8, 1.0, 0.6, 1.0))
+                        b = ref.compress_level(fmt, q, img, alpha_mode=am, color_weights=(0.8, 1.0, 0.6, 1.0))
+                        assert np.array_equal(a, b), (w, h, fmt, q, am)
+    # fp16 input + Mitchell resize + renormalise
+    hh = rng.integers(0, 65536, (16, 24, 4)).astype(np.uint16)
+    r = ref.Surface()
+    r.set_image(1, 24, 16, hh)
+    assert np.array_equal(orc.set_image(1, 24, 16, hh).view(np.uint32), r.get().view(np.uint32))
+    im8 = s.normal_bgra8(40, 24)
+    r = ref.Surface(wrap=1, normal_map=True)
+    r.set_image(0, 40, 24, im8)
+    r.resize(17, 11, 3)
+    o = orc.resize(orc.set_image(0, 40, 24, im8), 17, 11, 3, 2.0, 1.0 / 3.0, 1.0 / 3.0, 1)
+    assert np.array_equal(o.view(np.uint32), r.get().view(np.uint32))
+    r.expand_normals(); r.normalize_normal_map(); r.pack_normals()
+    assert np.array_equal(orc.renormalize(o).view(np.uint32), r.get().view(np.uint32))
