@@ -37,8 +37,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_BC3_COLOR, K_BC1, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_bc3_color", "k_bc1_icbc", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
 struct ProfRec {
     int kid;
@@ -330,11 +330,11 @@ int nvttb_format_supported(int format, int quality) {
     switch (format) {
     case F_BC4:
     case F_BC5:
-        return quality == Q_Fastest || quality == Q_Normal;
+        return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT1:
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5:
-        return quality == Q_Normal || quality == Q_Production;
+        return quality >= Q_Normal && quality <= Q_Highest;
     default:
         return 0;
     }
@@ -353,15 +353,20 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     lv.bh = (h + 3) / 4;
     lv.to_gamma_table = d->applyToGamma ? ctx->d_to_gamma : nullptr;
     const int nb = lv.bw * lv.bh;
-    auto alpha = [&](int channel, int stride, int offset) {
+    auto alpha = [&](int channel, int stride, int offset, bool optimal) {
         AlphaBlocksParams P;
         P.lv = lv;
         P.channel = channel;
         P.out = d_out;
         P.out_stride = stride;
         P.out_offset = offset;
-        P.mode = 0;
-        NVB_LAUNCH(ctx, K_ALPHA, (double)w * h, k_alpha_blocks, grid_for(nb, 128), 128, P);
+        P.mode = optimal ? 1 : 0;
+        if (optimal) {
+            // OptimalCompress::compressDXT5A: one warp per channel-block, 4 warps per CTA
+            NVB_LAUNCH(ctx, K_ALPHA_OPT, (double)w * h, k_alpha_optimal, grid_for(nb, 4), 128, P);
+        } else {
+            NVB_LAUNCH(ctx, K_ALPHA, (double)w * h, k_alpha_blocks, grid_for(nb, 128), 128, P);
+        }
     };
     if (d->format == F_DXT1) {
         // CompressorDXT1 -> ICBC: Fastest -> Level 1, Production -> Level 9, Normal and Highest -> Level 8 (BlockCompressor.cpp:211-217)
@@ -385,12 +390,13 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.match6 = ctx->d_icbc_match + 512;
         NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
     } else if (d->format == F_BC4) {
-        alpha(0, 8, 0);
+        // Fastest/Normal -> QuickCompress, Production/Highest -> OptimalCompress (Context.cpp:1098-1115)
+        alpha(0, 8, 0, d->quality >= Q_Production);
     } else if (d->format == F_BC5) {
-        alpha(0, 16, 0);
-        alpha(1, 16, 8);
+        alpha(0, 16, 0, d->quality >= Q_Production);
+        alpha(1, 16, 8, d->quality >= Q_Production);
     } else if (d->format == F_DXT5) {
-        alpha(3, 16, 0);
+        alpha(3, 16, 0, d->quality == Q_Highest);  // CompressorDX9.cpp:149-157
         Bc3ColorParams P;
         P.lv = lv;
         P.out = d_out;

@@ -187,4 +187,109 @@ __global__ void __launch_bounds__(128) k_alpha_blocks(AlphaBlocksParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// OptimalCompress::compressDXT5A (src/nvtt/OptimalCompressDXT.cpp:512-607; computeAlphaError :189-217,
+// computeAlphaIndices :219-244) — BC4/BC5 at Production/Highest, BC3 alpha at Highest.
+// Brute force over every (alpha0, alpha1) pair of the 8-step and then the 6-step encoding; the error of a pair is
+// an exact integer (weights are 1), so the early-outs of the reference only save time and the result is the first
+// strict minimum in loop order.  One warp per channel-block: the pairs are flattened in loop order and striped
+// over the 32 lanes, then reduced with (error, order number).
+// Canonical behaviour for the reference's read of uninitialised output bytes (:546, besterror is first computed
+// from whatever the output buffer held): the output is treated as zero-filled (alpha0 = alpha1 = 0).
+// ---------------------------------------------------------------------------------------------------------
+NVB_DEV unsigned alpha_pair_error(const unsigned src[16], unsigned a0, unsigned a1) {
+    unsigned pal[8];
+    alpha_palette(a0, a1, pal);
+    unsigned total = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned best = 0x7fffffffu;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            const int d = (int)src[i] - (int)pal[p];
+            best = min(best, (unsigned)(d * d));
+        }
+        total += best;
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(128) k_alpha_optimal(AlphaBlocksParams P) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int nblocks = P.lv.bw * P.lv.bh;
+    for (int blk = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); blk < nblocks; blk += gridDim.x * warps_per_cta) {
+        unsigned src[16];
+        alpha_gather_block(P.lv, P.channel, blk % P.lv.bw, blk / P.lv.bw, src);  // every lane holds the whole block
+        int mina = 255, maxa = 0, mina_no01 = 255, maxa_no01 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int a = (int)src[i];
+            mina = min(mina, a);
+            maxa = max(maxa, a);
+            if (a != 0 && a != 255) {
+                mina_no01 = min(mina_no01, a);
+                maxa_no01 = max(maxa_no01, a);
+            }
+        }
+        unsigned a0, a1;
+        if (maxa - mina < 8) {
+            a0 = (unsigned)maxa;
+            a1 = (unsigned)mina;
+        } else if (maxa_no01 - mina_no01 < 6) {
+            a0 = (unsigned)mina_no01;
+            a1 = (unsigned)maxa_no01;
+        } else {
+            unsigned besterror = alpha_pair_error(src, 0, 0);  // zero-filled output block
+            unsigned bestk = 0xffffffffu;                      // "no candidate improved": keep (maxa, mina)
+            unsigned bestpair = ((unsigned)maxa << 8) | (unsigned)mina;  // alpha0 << 8 | alpha1
+            // 8-step pairs: for a0 in [lo+9, hi) for a1 in [lo, a0-8)
+            const int lo8 = (mina <= 8) ? 0 : mina - 8, hi8 = (maxa >= 255 - 8) ? 255 : maxa + 8;
+            const int R8 = hi8 - lo8;
+            const int n8 = (R8 > 9) ? ((R8 - 9) * (R8 - 8)) / 2 : 0;
+            const int lo6 = (mina_no01 <= 6) ? 0 : mina_no01 - 6, hi6 = (maxa_no01 >= 255 - 6) ? 255 : maxa_no01 + 6;
+            const int R6 = hi6 - lo6;
+            const int n6 = (R6 > 9) ? ((R6 - 9) * (R6 - 8)) / 2 : 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const int lo = pass ? lo6 : lo8, hi = pass ? hi6 : hi8, n = pass ? n6 : n8;
+                const unsigned kbase = pass ? (unsigned)n8 : 0u;
+                // walk the flattened (row = x0, column = x1) triangle; row r (x0 = lo+9+r) has r+1 entries
+                int row = 0, col = lane;
+                while (row < hi - lo - 9 && col > row) { col -= row + 1; row++; }
+                for (int k = lane; k < n; k += 32) {
+                    const unsigned x0 = (unsigned)(lo + 9 + row), x1 = (unsigned)(lo + col);
+                    const unsigned e = pass ? alpha_pair_error(src, x1, x0) : alpha_pair_error(src, x0, x1);
+                    if (e < besterror) {
+                        besterror = e;
+                        bestk = kbase + (unsigned)k;
+                        bestpair = pass ? ((x1 << 8) | x0) : ((x0 << 8) | x1);
+                    }
+                    col += 32;
+                    while (col > row) { col -= row + 1; row++; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const unsigned oe = __shfl_xor_sync(0xffffffffu, besterror, d);
+                const unsigned ok = __shfl_xor_sync(0xffffffffu, bestk, d);
+                const unsigned op = __shfl_xor_sync(0xffffffffu, bestpair, d);
+                if (oe < besterror || (oe == besterror && ok < bestk)) {
+                    besterror = oe;
+                    bestk = ok;
+                    bestpair = op;
+                }
+            }
+            a0 = bestpair >> 8;
+            a1 = bestpair & 0xFF;
+        }
+        if (lane == 0) {
+            unsigned long long b = ((unsigned long long)a1 << 8) | a0;
+            alpha_compute_indices(src, a0, a1, &b);
+            *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+                make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
+        }
+    }
+}
+
 }  // namespace nvb

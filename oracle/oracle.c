@@ -419,6 +419,62 @@ static uint64_t alpha_quick(const uint8_t src[16]) {
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * OptimalCompress::compressDXT5A (OptimalCompressDXT.cpp:189-244,512-607): brute force over (alpha0, alpha1).
+ * The reference computes the first `besterror` from the not-yet-written output block (:546); the canonical behaviour
+ * restated here is a zero-filled output buffer (alpha0 = alpha1 = 0), see DESIGN.md.
+ * ------------------------------------------------------------------------------------------------------------- */
+static float alpha_error_opt(const uint8_t src[16], unsigned a0, unsigned a1, float bestError) {
+    uint8_t pal[8];
+    alpha_palette(a0, a1, pal);
+    float total = 0;
+    for (int i = 0; i < 16; i++) {
+        int minDist = 0x7fffffff;
+        for (int p = 0; p < 8; p++) {
+            int d = (int)src[i] - (int)pal[p];
+            d *= d;
+            if (d < minDist) minDist = d;
+        }
+        total += minDist * 1.0f;
+        if (total > bestError) return total;
+    }
+    return total;
+}
+static uint64_t alpha_optimal(const uint8_t src[16]) {
+    uint8_t mina = 255, maxa = 0, mina_no01 = 255, maxa_no01 = 0;
+    for (int i = 0; i < 16; i++) {
+        uint8_t a = src[i];
+        if (a < mina) mina = a;
+        if (a > maxa) maxa = a;
+        if (a != 0 && a != 255) { if (a < mina_no01) mina_no01 = a; if (a > maxa_no01) maxa_no01 = a; }
+    }
+    unsigned alpha0, alpha1;
+    if (maxa - mina < 8) { alpha0 = maxa; alpha1 = mina; }
+    else if (maxa_no01 - mina_no01 < 6) { alpha0 = mina_no01; alpha1 = maxa_no01; }
+    else {
+        float besterror = alpha_error_opt(src, 0, 0, FLT_MAX);
+        int besta0 = maxa, besta1 = mina;
+        mina = (uint8_t)((mina <= 8) ? 0 : mina - 8);
+        maxa = (uint8_t)((maxa >= 255 - 8) ? 255 : maxa + 8);
+        for (int a0 = mina + 9; a0 < maxa; a0++)
+            for (int a1 = mina; a1 < a0 - 8; a1++) {
+                float e = alpha_error_opt(src, (unsigned)a0, (unsigned)a1, besterror);
+                if (e < besterror) { besterror = e; besta0 = a0; besta1 = a1; }
+            }
+        mina_no01 = (uint8_t)((mina_no01 <= 6) ? 0 : mina_no01 - 6);
+        maxa_no01 = (uint8_t)((maxa_no01 >= 255 - 6) ? 255 : maxa_no01 + 6);
+        for (int a0 = mina_no01 + 9; a0 < maxa_no01; a0++)
+            for (int a1 = mina_no01; a1 < a0 - 8; a1++) {
+                float e = alpha_error_opt(src, (unsigned)a1, (unsigned)a0, besterror);
+                if (e < besterror) { besterror = e; besta0 = a1; besta1 = a0; }
+            }
+        alpha0 = (unsigned)besta0; alpha1 = (unsigned)besta1;
+    }
+    uint64_t block = (uint64_t)alpha0 | ((uint64_t)alpha1 << 8);
+    alpha_indices(src, &block);
+    return block;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * BC3 colour: nvsquish WeightedClusterFit, scalar path, intended (-O2) semantics
  * (colourset.cpp:35-139, maths.cpp:32-133, weightedclusterfit.cpp:39-105,476-589, colourblock.cpp:30-138,
  *  OptimalCompressDXT.cpp:254-269 + SingleColorLookup.cpp:34-89)
@@ -964,8 +1020,9 @@ long orc_compress_level(int format, int quality, int alphaMode, int w, int h, co
         return (long)bw * bh * 8;
     }
     if (format == 4 || format == 6 || format == 7) {
-        if (format == 4 && !(quality == 1 || quality == 2)) return 0;
-        if (format != 4 && quality > 1) return 0;
+        if (format == 4 && quality == 0) return 0; /* QuickCompress::compressDXT5 (fast DXT1) is not restated */
+        /* BC4/BC5: Production/Highest -> OptimalCompress (Context.cpp:1098-1115); BC3: Highest only (CompressorDX9.cpp:149) */
+        const int optimal = (format == 4) ? (quality == 3) : (quality >= 2);
         const int bs = format == 6 ? 8 : 16;
         for (int by = 0; by < bh; by++)
             for (int bx = 0; bx < bw; bx++) {
@@ -974,16 +1031,16 @@ long orc_compress_level(int format, int quality, int alphaMode, int w, int h, co
                 uint64_t a;
                 if (format == 6 || format == 7) {
                     for (int i = 0; i < 16; i++) ch[i] = bgra[4 * i + 2]; /* red */
-                    a = alpha_quick(ch);
+                    a = optimal ? alpha_optimal(ch) : alpha_quick(ch);
                     memcpy(dst, &a, 8);
                     if (format == 7) {
                         for (int i = 0; i < 16; i++) ch[i] = bgra[4 * i + 1]; /* green */
-                        a = alpha_quick(ch);
+                        a = optimal ? alpha_optimal(ch) : alpha_quick(ch);
                         memcpy(dst + 8, &a, 8);
                     }
                 } else {
                     for (int i = 0; i < 16; i++) ch[i] = bgra[4 * i + 3];
-                    a = alpha_quick(ch);
+                    a = optimal ? alpha_optimal(ch) : alpha_quick(ch);
                     memcpy(dst, &a, 8);
                     int single = 1;
                     for (int i = 1; i < 16; i++) if (memcmp(bgra, bgra + 4 * i, 3)) single = 0;

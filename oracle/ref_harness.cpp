@@ -14,6 +14,20 @@
 
 using namespace nvtt;
 
+#ifdef REF_ZERO_NEW
+// Pinned parity build only: OptimalCompress::compressDXT5A reads the not-yet-written output block
+// (OptimalCompressDXT.cpp:546; the buffer is a bare `new uint8[]`, BlockCompressor.cpp:106), so the reference's BC4/BC5
+// Production output depends on heap garbage.  Replacing the global allocation functions *of this .so* (linked
+// -Bsymbolic) with zero-filling ones pins that read to "zero-filled output buffer" without touching reference sources.
+#include <new>
+void *operator new(size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) throw std::bad_alloc(); return p; }
+void *operator new[](size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) throw std::bad_alloc(); return p; }
+void operator delete(void *p) noexcept { free(p); }
+void operator delete[](void *p) noexcept { free(p); }
+void operator delete(void *p, size_t) noexcept { free(p); }
+void operator delete[](void *p, size_t) noexcept { free(p); }
+#endif
+
 namespace {
 struct MemHandler : public OutputHandler {
     std::vector<unsigned char> buf;

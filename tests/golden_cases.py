@@ -23,7 +23,7 @@ def level_cases():
     c = {}
     for kind in ("photo", "adv", "dark"):
         for (w, h) in ((48, 40), (13, 7)):
-            for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (1, 2)), (6, "bc4", (0, 1)), (7, "bc5", (0, 1))):
+            for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (1, 2, 3)), (6, "bc4", (0, 1, 2)), (7, "bc5", (0, 1, 2))):
                 for q in qs:
                     c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1))
     c["level_bc1_photo_48x40_q2_transp_w"] = ("photo", 48, 40, 1, 2, 1, (0.3, 0.59, 0.11, 1.0))

@@ -45,7 +45,8 @@ void emu_alpha_blocks(const float *planar, int w, int h, int channel, unsigned c
     P.lv = make_lv(planar, w, h, gamma);
     P.channel = channel; P.out = out; P.out_stride = stride; P.out_offset = offset; P.mode = mode;
     int nb = P.lv.bw * P.lv.bh;
-    emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_alpha_blocks(P); });
+    if (mode == 1) emu::launch(dim3((nb + 3) / 4), dim3(128), 0, [&] { k_alpha_optimal(P); });
+    else emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_alpha_blocks(P); });
 }
 
 void emu_bc3_color(const float *planar, int w, int h, const float *metric, int weight_by_alpha, unsigned char *out, int stride, int offset, int gamma) {

@@ -35,14 +35,14 @@ def _encode(E, fmt, q, img, am, cw):
         E.emu_bc1(p, w, h, c, {0: 1, 1: 8, 2: 9, 3: 8}[q], int(am == 1), C.c_void_p(out.ctypes.data), 0)
     elif fmt == 6:
         out = np.zeros(nb * 8, np.uint8)
-        E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 8, 0, 0, 0)
+        E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 8, 0, 0, int(q >= 2))
     elif fmt == 7:
         out = np.zeros(nb * 16, np.uint8)
-        E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 16, 0, 0, 0)
-        E.emu_alpha_blocks(p, w, h, 1, C.c_void_p(out.ctypes.data), 16, 8, 0, 0)
+        E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 16, 0, 0, int(q >= 2))
+        E.emu_alpha_blocks(p, w, h, 1, C.c_void_p(out.ctypes.data), 16, 8, 0, int(q >= 2))
     else:
         out = np.zeros(nb * 16, np.uint8)
-        E.emu_alpha_blocks(p, w, h, 3, C.c_void_p(out.ctypes.data), 16, 0, 0, 0)
+        E.emu_alpha_blocks(p, w, h, 3, C.c_void_p(out.ctypes.data), 16, 0, 0, int(q == 3))
         m = (C.c_float * 3)(*cw[:3])
         E.emu_bc3_color(p, w, h, m, int(am == 1), C.c_void_p(out.ctypes.data), 16, 8, 0)
     return out
