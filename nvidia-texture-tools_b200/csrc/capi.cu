@@ -7,6 +7,7 @@
 #include "kernels/bc_alpha.cuh"
 #include "kernels/bc3_color.cuh"
 #include "kernels/bc1_icbc.cuh"
+#include "kernels/bc6h.cuh"
 #include "kernels/image_ops.cuh"
 
 #include <cuda_runtime.h>
@@ -37,8 +38,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
 struct ProfRec {
     int kid;
@@ -64,7 +65,7 @@ struct NvttbContext {
     float *d_icbc_mid = nullptr;
     unsigned char *d_icbc_match = nullptr;
     int icbc_four_count = 0;
-    DevBuf in_stage, tmp_filter, tmp_level, out_dev, lvlA, lvlB;
+    DevBuf in_stage, tmp_filter, tmp_level, out_dev, lvlA, lvlB, enc_scratch;
     void *h_out = nullptr;  // pinned
     size_t h_out_cap = 0;
     std::map<std::tuple<int, unsigned, unsigned, unsigned, int, int>, PolyDev> poly_cache;
@@ -241,6 +242,7 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     cudaFree(ctx->out_dev.p);
     cudaFree(ctx->lvlA.p);
     cudaFree(ctx->lvlB.p);
+    cudaFree(ctx->enc_scratch.p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     for (auto &kv : ctx->poly_cache) {
         cudaFree(kv.second.weights);
@@ -335,6 +337,8 @@ int nvttb_format_supported(int format, int quality) {
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5:
         return quality >= Q_Normal && quality <= Q_Highest;
+    case F_BC6:
+        return 1;  // quality is ignored for BC6 (CompressorDX11.cpp:42-78)
     default:
         return 0;
     }
@@ -411,6 +415,24 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.omatch5 = ctx->d_om5;
         P.omatch6 = ctx->d_om6;
         NVB_LAUNCH(ctx, K_BC3_COLOR, (double)w * h, k_bc3_color, (nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, P);
+    }
+    else if (d->format == F_BC6) {
+        // scratch per block: 20 floats of rough endpoints, 2 candidate blocks, 2 errors
+        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 32 + 8));
+        if (rc != NVTTB_OK) return rc;
+        Bc6Params P;
+        P.lv = lv;
+        P.out = d_out;
+        // ZOH::Utils::FORMAT: unsigned for PixelType_UnsignedFloat / UnsignedNorm / UnsignedInt (CompressorDX11.cpp:47-56)
+        P.is_signed = !(d->pixelType == 5 || d->pixelType == 0 || d->pixelType == 2);
+        P.transparency = (d->alphaMode == AM_Transparency);
+        P.rough = (float *)ctx->enc_scratch.p;
+        P.cand = (unsigned char *)ctx->enc_scratch.p + (size_t)nb * 80;
+        P.cand_err = (float *)((unsigned char *)ctx->enc_scratch.p + (size_t)nb * 112);
+        NVB_LAUNCH(ctx, K_BC6_ROUGH, (double)w * h, k_bc6_rough, grid_for(nb, NVB_BC6_ROUGH_WARPS), NVB_BC6_ROUGH_WARPS * 32, P);
+        const int padded = (nb + 127) / 128 * 128;
+        NVB_LAUNCH(ctx, K_BC6_REFINE, (double)w * h, k_bc6_refine, 2 * padded / 128, 128, P, padded);
+        NVB_LAUNCH(ctx, K_BC6_SELECT, (double)w * h, k_bc6_select, grid_for(nb, 256), 256, P);
     }
     CK(cudaGetLastError());
     return NVTTB_OK;

@@ -12,6 +12,12 @@
 #endif
 
 #define NVB_DEV __device__ __forceinline__
+// read-only lookup tables defined in headers (global memory, L1/L2-cached; plain static data under the emulator)
+#ifdef NVB_EMU
+#define NVB_TABLE static const
+#else
+#define NVB_TABLE static __device__ const
+#endif
 
 // nv::max(a,b) = (b < a) ? a : b  /  nv::min(a,b) = (a < b) ? a : b   (src/nvcore/Utils.h:161-188)
 // NaN behaviour: max(NaN, x) = x, max(x, NaN) = NaN; min(NaN, x) = x; min(x, NaN) = NaN.

@@ -13,12 +13,22 @@ cases = {
     "bc1_fastest_8192_box": (8192, m.Format_BC1, 0, dict(mip_filter=0)),
     "c1_bc3_normal_4096_kaiser": (4096, m.Format_BC3, 1, dict(mip_filter=2)),
     "c1_bc5_normal_4096_kaiser": (4096, m.Format_BC5, 1, dict(mip_filter=2, normal_map=True)),
+    "bc5_production_2048_box": (2048, m.Format_BC5, 2, dict(mip_filter=0, normal_map=True)),
+    "c4_bc6h_face_2048_fp16_box": (2048, m.Format_BC6, 1, dict(mip_filter=0, pixel_type=5)),
+    "c3_bc7_1024_box": (1024, m.Format_BC7, 1, dict(mip_filter=0)),
 }
 sel = sys.argv[1:] or list(cases)
 for name in sel:
     size, fmt, q, kw = cases[name]
-    img = torch.from_numpy(m.synth.photo_bgra8(size, size, seed=1234, alpha=True)).cuda()
-    d = m.make_process_desc(0, size, size, fmt, q, **kw)
+    if fmt == m.Format_BC6:
+        img = torch.from_numpy(m.synth.hdr_rgba16f(size, size, seed=11).view("uint16").astype("int16")).cuda()
+        d = m.make_process_desc(m.InputFormat_RGBA_16F, size, size, fmt, q, **kw)
+    else:
+        img = torch.from_numpy(m.synth.photo_bgra8(size, size, seed=1234, alpha=True)).cuda()
+        d = m.make_process_desc(0, size, size, fmt, q, **kw)
+    if not m.lib().nvttb_format_supported(fmt, q):
+        print(name, "not supported yet")
+        continue
     n = int(m.lib().nvttb_process_output_size(d))
     out = torch.empty(n, dtype=torch.uint8, device="cuda")
     for _ in range(2):

@@ -25,9 +25,9 @@ def sha(a):
 
 def main():
     out = {}
-    for key, (kind, w, h, fmt, q, am, cw) in level_cases().items():
+    for key, (kind, w, h, fmt, q, am, cw, pt) in level_cases().items():
         img = make_input(kind, w, h, planar=True)
-        out[key] = R.compress_level(fmt, q, img, alpha_mode=am, color_weights=cw)
+        out[key] = R.compress_level(fmt, q, img, alpha_mode=am, color_weights=cw, pixel_type=pt)
     for key, (kind, w, h, fmt, q, kw) in pipeline_cases().items():
         img = make_input(kind, w, h, planar=False)
         out[key] = R.process([img], 0, w, h, fmt, q, **kw)

@@ -11,6 +11,9 @@ def make_input(kind, w, h, planar):
         img = s.normal_bgra8(w, h, seed=7)
     elif kind == "adv":
         img = s.adversarial_bgra8(w, h, seed=5)
+    elif kind == "hdr":
+        f = s.hdr_rgba16f(w, h, seed=11).astype(np.float32)
+        return np.ascontiguousarray(f.transpose(2, 0, 1)) if planar else s.hdr_rgba16f(w, h, seed=11)
     elif kind == "dark":
         img = (s.photo_bgra8(w, h, seed=3, alpha=True) // 5).astype(np.uint8)
     else:
@@ -19,15 +22,20 @@ def make_input(kind, w, h, planar):
 
 
 def level_cases():
-    """key -> (input kind, w, h, nvtt format, quality, alphaMode, colour weights)"""
+    """key -> (input kind, w, h, nvtt format, quality, alphaMode, colour weights, pixel type)"""
     c = {}
     for kind in ("photo", "adv", "dark"):
         for (w, h) in ((48, 40), (13, 7)):
             for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (1, 2, 3)), (6, "bc4", (0, 1, 2)), (7, "bc5", (0, 1, 2))):
                 for q in qs:
-                    c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1))
-    c["level_bc1_photo_48x40_q2_transp_w"] = ("photo", 48, 40, 1, 2, 1, (0.3, 0.59, 0.11, 1.0))
-    c["level_bc3_photo_48x40_q1_transp_w"] = ("photo", 48, 40, 4, 1, 1, (0.3, 0.59, 0.11, 1.0))
+                    c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1), 0)
+    # BC6H: quality is ignored; pixel type 5 = UnsignedFloat, 4 = Float (signed).
+    for kind in ("hdr", "photo"):
+        for (w, h) in ((32, 24), (13, 7)):
+            for pt in (5, 4):
+                c["level_bc6_%s_%dx%d_pt%d" % (kind, w, h, pt)] = (kind, w, h, 10, 1, 0, (1, 1, 1, 1), pt)
+    c["level_bc1_photo_48x40_q2_transp_w"] = ("photo", 48, 40, 1, 2, 1, (0.3, 0.59, 0.11, 1.0), 0)
+    c["level_bc3_photo_48x40_q1_transp_w"] = ("photo", 48, 40, 4, 1, 1, (0.3, 0.59, 0.11, 1.0), 0)
     return c
 
 

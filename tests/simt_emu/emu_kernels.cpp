@@ -4,6 +4,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc_alpha.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_icbc.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -73,6 +74,23 @@ void emu_bc1(const float *planar, int w, int h, const float *cw, int level, int 
     int nb = P.lv.bw * P.lv.bh;
     emu::launch(dim3((nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS), dim3(NVB_BC1_GROUPS * 16), 0, [&] { k_bc1_icbc(P); });
 }
+
+void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency, unsigned char *out, int gamma) {
+    init_tables();
+    Bc6Params P;
+    P.lv = make_lv(planar, w, h, gamma);
+    P.out = out; P.is_signed = is_signed; P.transparency = transparency;
+    int nb = P.lv.bw * P.lv.bh;
+    std::vector<float> rough((size_t)nb * 20), err((size_t)nb * 2);
+    std::vector<unsigned char> cand((size_t)nb * 32);
+    P.rough = rough.data(); P.cand = cand.data(); P.cand_err = err.data();
+    emu::launch(dim3((nb + NVB_BC6_ROUGH_WARPS - 1) / NVB_BC6_ROUGH_WARPS), dim3(NVB_BC6_ROUGH_WARPS * 32), 0, [&] { k_bc6_rough(P); });
+    int padded = (nb + 127) / 128 * 128;
+    emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_refine(P, padded); });
+    emu::launch(dim3((nb + 255) / 256), dim3(256), 0, [&] { k_bc6_select(P); });
+}
+
+unsigned emu_half_from_float(unsigned f) { return half_from_float_bits(f); }
 
 void emu_set_image(const void *src, float *dst, int count, int format, int to_linear) {
     init_tables();

@@ -21,9 +21,9 @@ def _sha(a):
 
 
 def test_gpu_levels_match_golden(nvtt, ctx, golden):
-    for key, (kind, w, h, fmt, q, am, cw) in G.level_cases().items():
+    for key, (kind, w, h, fmt, q, am, cw, pt) in G.level_cases().items():
         img = G.make_input(kind, w, h, planar=True)
-        got = ctx.encode_level(fmt, q, img, alpha_mode=am, color_weights=cw)
+        got = ctx.encode_level(fmt, q, img, alpha_mode=am, color_weights=cw, pixel_type=pt)
         assert np.array_equal(got, golden[key]), key
 
 

@@ -39,6 +39,39 @@ def test_level_encode_bit_exact(nvtt, ref, ctx, fmt_name, quality):
             _assert_blocks_equal(got, want, bs, "%s q%d %s %dx%d" % (fmt_name, quality, name, w, h))
 
 
+def _hdr_planar(nvtt, w, h, seed):
+    f = nvtt.synth.hdr_rgba16f(w, h, seed=seed).astype(np.float32)
+    return np.ascontiguousarray(f.transpose(2, 0, 1))
+
+
+def test_bc6h_level_bit_exact(nvtt, ref, ctx):
+    """BC6H (ZOH): unsigned and signed half, HDR / LDR / out-of-range / flat inputs, ragged sizes, alpha-weighted texels."""
+    rng = np.random.default_rng(17)
+    for (w, h) in SIZES:
+        wild = (rng.standard_normal((4, h, w)) * np.exp(rng.normal(0, 4, (4, h, w)))).astype(np.float32)
+        imgs = [("hdr", _hdr_planar(nvtt, w, h, 11)), ("ldr", nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(w, h, seed=2, alpha=True))),
+                ("wild", wild), ("flat", np.full((4, h, w), 0.5, np.float32))]
+        for name, img in imgs:
+            for pt in (nvtt.PixelType_UnsignedFloat, nvtt.PixelType_Float):
+                for am in (0, 1):
+                    got = ctx.encode_level(nvtt.Format_BC6, 1, img, pixel_type=pt, alpha_mode=am)
+                    want = ref.compress_level(ref.Format_BC6, 1, img, pixel_type=pt, alpha_mode=am)
+                    _assert_blocks_equal(got, want, 16, "BC6H %s %dx%d pixelType %d alphaMode %d" % (name, w, h, pt, am))
+
+
+def test_bc6h_cubemap_pipeline_bit_exact(nvtt, ref, ctx):
+    """BASELINE configs[4] in small: 6 fp16 faces, gamma-correct (2.2 in / 2.2 out) and linear (1.0/1.0) box mip chains."""
+    w = h = 64
+    faces = [nvtt.synth.hdr_rgba16f(w, h, seed=30 + f) for f in range(6)]
+    for gamma in ((2.2, 2.2), (1.0, 1.0)):
+        d = nvtt.make_process_desc(nvtt.InputFormat_RGBA_16F, w, h, nvtt.Format_BC6, 1, faces=6, mip_filter=0, gamma=gamma,
+                                   pixel_type=nvtt.PixelType_UnsignedFloat)
+        got = ctx.process_bytes(faces, d)
+        want = ref.process(faces, ref.InputFormat_RGBA_16F, w, h, ref.Format_BC6, 1, mip_filter=0, gamma=gamma,
+                           pixel_type=ref.PixelType_UnsignedFloat, texture_type=ref.TextureType_Cube)
+        _assert_blocks_equal(got, want, 16, "BC6H cube gamma %s" % (gamma,))
+
+
 def test_bc3_weights_and_transparency(nvtt, ref, ctx):
     img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(256, 256, seed=3, alpha=True))
     for cw in [(1, 1, 1, 1), (0.3, 0.59, 0.11, 1.0), (1, 0, 0, 1)]:
