@@ -8,6 +8,7 @@
 #include "kernels/bc3_color.cuh"
 #include "kernels/bc1_icbc.cuh"
 #include "kernels/bc6h.cuh"
+#include "kernels/bc7.cuh"
 #include "kernels/image_ops.cuh"
 
 #include <cuda_runtime.h>
@@ -38,8 +39,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
 struct ProfRec {
     int kid;
@@ -338,13 +339,22 @@ int nvttb_format_supported(int format, int quality) {
     case F_DXT5:
         return quality >= Q_Normal && quality <= Q_Highest;
     case F_BC6:
-        return 1;  // quality is ignored for BC6 (CompressorDX11.cpp:42-78)
+    case F_BC7:
+        return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102)
     default:
         return 0;
     }
 }
 
 }  // extern "C"
+
+// BC7: rough shape ranking (modes 0,1,2,3,7) + one refine launch per mode + select
+template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, const Bc7Params &P, int nb, double units) {
+    if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
+        NVB_LAUNCH(ctx, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(nb, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, P);
+    const unsigned grid = (unsigned)(((size_t)nb * NCAND + 127) / 128);
+    NVB_LAUNCH(ctx, K_BC7_REFINE, units, (k_bc7_refine<M, NCAND>), grid, 128, P);
+}
 
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
 static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out) {
@@ -433,6 +443,27 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         const int padded = (nb + 127) / 128 * 128;
         NVB_LAUNCH(ctx, K_BC6_REFINE, (double)w * h, k_bc6_refine, 2 * padded / 128, 128, P, padded);
         NVB_LAUNCH(ctx, K_BC6_SELECT, (double)w * h, k_bc6_select, grid_for(nb, 256), 256, P);
+    }
+    else if (d->format == F_BC7) {
+        // scratch per block: 5 x 16 shape bytes, 8 x 16 candidate bytes, 8 errors
+        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32));
+        if (rc != NVTTB_OK) return rc;
+        Bc7Params P;
+        P.lv = lv;
+        P.out = d_out;
+        P.shapes = (unsigned char *)ctx->enc_scratch.p;
+        P.cand = P.shapes + (size_t)nb * 80;
+        P.cand_err = (float *)(P.shapes + (size_t)nb * 208);
+        const double units = (double)w * h;
+        launch_bc7_mode<0, 4>(ctx, P, nb, units);
+        launch_bc7_mode<1, 16>(ctx, P, nb, units);
+        launch_bc7_mode<2, 16>(ctx, P, nb, units);
+        launch_bc7_mode<3, 16>(ctx, P, nb, units);
+        launch_bc7_mode<4, 8>(ctx, P, nb, units);
+        launch_bc7_mode<5, 4>(ctx, P, nb, units);
+        launch_bc7_mode<6, 1>(ctx, P, nb, units);
+        launch_bc7_mode<7, 16>(ctx, P, nb, units);
+        NVB_LAUNCH(ctx, K_BC7_SELECT, units, k_bc7_select, grid_for(nb, 256), 256, P);
     }
     CK(cudaGetLastError());
     return NVTTB_OK;

@@ -143,8 +143,7 @@ NVB_DEV void principal_axis4(int n, const float (*pts)[4], float dir[4]) {
     float c[4] = {0, 0, 0, 0};
     for (int i = 0; i < n; i++)
         for (int k = 0; k < 4; k++) c[k] += pts[i][k];
-    const float is = 1.0f / (float)n;
-    for (int k = 0; k < 4; k++) c[k] *= is;
+    for (int k = 0; k < 4; k++) c[k] /= (float)n;  // Vector4::operator/=(float) is a true division (Vector.inl:242-248)
     float cov[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; i++) {
         const float vx = pts[i][0] - c[0], vy = pts[i][1] - c[1], vz = pts[i][2] - c[2], vw = pts[i][3] - c[3];

@@ -34,6 +34,9 @@ def level_cases():
         for (w, h) in ((32, 24), (13, 7)):
             for pt in (5, 4):
                 c["level_bc6_%s_%dx%d_pt%d" % (kind, w, h, pt)] = (kind, w, h, 10, 1, 0, (1, 1, 1, 1), pt)
+    for kind in ("photo", "adv"):
+        for (w, h) in ((24, 16), (13, 7)):
+            c["level_bc7_%s_%dx%d" % (kind, w, h)] = (kind, w, h, 11, 1, 0, (1, 1, 1, 1), 0)
     c["level_bc1_photo_48x40_q2_transp_w"] = ("photo", 48, 40, 1, 2, 1, (0.3, 0.59, 0.11, 1.0), 0)
     c["level_bc3_photo_48x40_q1_transp_w"] = ("photo", 48, 40, 4, 1, 1, (0.3, 0.59, 0.11, 1.0), 0)
     return c

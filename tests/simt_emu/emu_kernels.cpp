@@ -5,6 +5,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_icbc.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -36,6 +37,12 @@ static LevelView make_lv(const float *data, int w, int h, int gamma) {
     lv.data = data; lv.w = w; lv.h = h; lv.bw = (w + 3) / 4; lv.bh = (h + 3) / 4;
     lv.to_gamma_table = gamma ? g_to_gamma : nullptr;
     return lv;
+}
+
+template <int M, int NCAND> static void emu_bc7_mode(Bc7Params &P, int nb) {
+    if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
+        emu::launch(dim3((nb + NVB_BC7_ROUGH_WARPS - 1) / NVB_BC7_ROUGH_WARPS), dim3(NVB_BC7_ROUGH_WARPS * 32), 0, [&] { k_bc7_rough<M>(P); });
+    emu::launch(dim3((nb * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_refine<M, NCAND>(P); });
 }
 
 extern "C" {
@@ -88,6 +95,29 @@ void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency,
     int padded = (nb + 127) / 128 * 128;
     emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_refine(P, padded); });
     emu::launch(dim3((nb + 255) / 256), dim3(256), 0, [&] { k_bc6_select(P); });
+}
+
+// mode_mask: bit m set = run mode m (the others keep error FLT_MAX).  errs (optional): [8][nb] per-mode errors.
+void emu_bc7(const float *planar, int w, int h, unsigned char *out, int gamma, int mode_mask, float *errs, unsigned char *cands) {
+    init_tables();
+    Bc7Params P;
+    P.lv = make_lv(planar, w, h, gamma);
+    P.out = out;
+    int nb = P.lv.bw * P.lv.bh;
+    std::vector<unsigned char> shapes((size_t)nb * 5 * 16), cand((size_t)nb * 8 * 16);
+    std::vector<float> err((size_t)nb * 8, FLT_MAX);
+    P.shapes = shapes.data(); P.cand = cand.data(); P.cand_err = err.data();
+    if (mode_mask & 1) emu_bc7_mode<0, 4>(P, nb);
+    if (mode_mask & 2) emu_bc7_mode<1, 16>(P, nb);
+    if (mode_mask & 4) emu_bc7_mode<2, 16>(P, nb);
+    if (mode_mask & 8) emu_bc7_mode<3, 16>(P, nb);
+    if (mode_mask & 16) emu_bc7_mode<4, 8>(P, nb);
+    if (mode_mask & 32) emu_bc7_mode<5, 4>(P, nb);
+    if (mode_mask & 64) emu_bc7_mode<6, 1>(P, nb);
+    if (mode_mask & 128) emu_bc7_mode<7, 16>(P, nb);
+    emu::launch(dim3((nb + 255) / 256), dim3(256), 0, [&] { k_bc7_select(P); });
+    if (errs) memcpy(errs, err.data(), err.size() * sizeof(float));
+    if (cands) memcpy(cands, cand.data(), cand.size());
 }
 
 unsigned emu_half_from_float(unsigned f) { return half_from_float_bits(f); }

@@ -36,6 +36,9 @@ def _encode(E, fmt, q, img, am, cw, pt=0):
     elif fmt == 10:
         out = np.zeros(nb * 16, np.uint8)
         E.emu_bc6(p, w, h, int(pt not in (0, 2, 5)), int(am == 1), C.c_void_p(out.ctypes.data), 0)
+    elif fmt == 11:
+        out = np.zeros(nb * 16, np.uint8)
+        E.emu_bc7(p, w, h, C.c_void_p(out.ctypes.data), 0, 255, None, None)
     elif fmt == 6:
         out = np.zeros(nb * 8, np.uint8)
         E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 8, 0, 0, int(q >= 2))
@@ -53,7 +56,7 @@ def _encode(E, fmt, q, img, am, cw, pt=0):
 
 def test_emulated_encoders_match_golden(emu, golden):
     for key, (kind, w, h, fmt, q, am, cw, pt) in G.level_cases().items():
-        if (w, h) != (13, 7) and kind != "photo" and fmt != 10:
+        if (w, h) != (13, 7) and kind != "photo" and fmt not in (10, 11):
             continue  # keep the CPU suite short: ragged size for every input kind, full size for one
         img = G.make_input(kind, w, h, planar=True)
         got = _encode(emu, fmt, q, img, am, cw, pt)

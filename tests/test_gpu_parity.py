@@ -72,6 +72,33 @@ def test_bc6h_cubemap_pipeline_bit_exact(nvtt, ref, ctx):
         _assert_blocks_equal(got, want, 16, "BC6H cube gamma %s" % (gamma,))
 
 
+def test_bc7_level_bit_exact(nvtt, ref, ctx):
+    """BC7 (AVPCL, all 8 modes): photo with alpha, opaque photo, adversarial noise / flat tiles, normal map, fp32 mip-like
+    values (not multiples of 1/255), ragged sizes.  The reference asserts on values outside [0,1], so inputs stay in range."""
+    rng = np.random.default_rng(23)
+    s = nvtt.synth
+    for (w, h) in SIZES:
+        imgs = [("alpha", s.planar_from_bgra8(s.photo_bgra8(w, h, seed=1234, alpha=True))),
+                ("opaque", s.planar_from_bgra8(s.photo_bgra8(w, h, seed=7))),
+                ("adversarial", s.planar_from_bgra8(s.adversarial_bgra8(w, h, seed=5))),
+                ("normal", s.planar_from_bgra8(s.normal_bgra8(w, h, seed=7))),
+                ("float", np.clip(s.planar_from_bgra8(s.photo_bgra8(w, h, seed=5, alpha=True)) + rng.normal(0, 0.01, (4, h, w)), 0, 1).astype(np.float32))]
+        for name, img in imgs:
+            got = ctx.encode_level(nvtt.Format_BC7, 1, img)
+            want = ref.compress_level(ref.Format_BC7, 1, img)
+            _assert_blocks_equal(got, want, 16, "BC7 %s %dx%d" % (name, w, h))
+
+
+def test_bc7_pipeline_bit_exact(nvtt, ref, ctx):
+    """BASELINE configs[3] in small: BGRA8 texture -> BC7 with a box mip chain (and a Kaiser one), through the whole pipeline."""
+    for (w, h, kw) in ((64, 64, dict(mip_filter=0)), (40, 24, dict(mip_filter=2, wrap=0))):
+        img = nvtt.synth.photo_bgra8(w, h, seed=77, alpha=True)
+        d = nvtt.make_process_desc(0, w, h, nvtt.Format_BC7, 1, **kw)
+        got = ctx.process_bytes([img], d)
+        want = ref.process([img], 0, w, h, ref.Format_BC7, 1, **kw)
+        _assert_blocks_equal(got, want, 16, "BC7 pipeline %dx%d %s" % (w, h, kw))
+
+
 def test_bc3_weights_and_transparency(nvtt, ref, ctx):
     img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(256, 256, seed=3, alpha=True))
     for cw in [(1, 1, 1, 1), (0.3, 0.59, 0.11, 1.0), (1, 0, 0, 1)]:
