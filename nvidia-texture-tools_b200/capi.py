@@ -313,6 +313,12 @@ class Surface:
     def normalize_normal_map(self):
         self.ctx._ck(self.L.nvttb_surface_normalize_normal_map(self.h))
 
+    def to_grey_scale(self, r, g, b, a):
+        self.ctx._ck(self.L.nvttb_surface_to_grey_scale(self.h, r, g, b, a))
+
+    def to_normal_map(self, sm, md, bg, lg):
+        self.ctx._ck(self.L.nvttb_surface_to_normal_map(self.h, sm, md, bg, lg))
+
     def encode(self, fmt, quality, **kw):
         d = make_encode_desc(fmt, quality, **kw)
         n = self.L.nvttb_level_size(fmt, self.width, self.height)

@@ -39,9 +39,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -570,6 +570,35 @@ static int gamma_device(NvttbContext *ctx, float *data, size_t pixels, bool toLi
     return NVTTB_OK;
 }
 
+// Surface::toGreyScale: the four scales are divided by their sum first (Surface.cpp:1738-1742)
+static int grey_scale_device(NvttbContext *ctx, float *data, size_t pixels, float r, float g, float b, float a) {
+    const float sum = r + g + b + a;
+    GreyScaleParams P;
+    P.data = data;
+    P.pixels = pixels;
+    P.scale[0] = r / sum;
+    P.scale[1] = g / sum;
+    P.scale[2] = b / sum;
+    P.scale[3] = a / sum;
+    NVB_LAUNCH(ctx, K_GREY_SCALE, (double)pixels, k_grey_scale, grid_for(pixels, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
+// Surface::toNormalMap: src -> dst (different buffers), 9x9 blended Sobel on the alpha plane
+static int normal_map_device(NvttbContext *ctx, const float *src, float *dst, int w, int h, int wrap, const float filterWeights[4]) {
+    NormalMapParams P;
+    P.src = src;
+    P.dst = dst;
+    P.w = w;
+    P.h = h;
+    P.wrap = wrap;
+    build_blended_sobel(filterWeights, P.kdu);
+    NVB_LAUNCH(ctx, K_NORMAL_MAP, (double)w * h, k_to_normal_map, grid_for((size_t)w * h, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
 static size_t input_bpp(int inputFormat) {
     switch (inputFormat) {
     case 0: return 4;
@@ -779,11 +808,29 @@ int nvttb_surface_normalize_normal_map(NvttbSurface *s) {
     CK(cudaGetLastError());
     return NVTTB_OK;
 }
-int nvttb_surface_to_grey_scale(NvttbSurface *s, float, float, float, float) {
-    return s ? fail(s->ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "toGreyScale not implemented yet") : NVTTB_ERR_INVALID_INPUT;
+int nvttb_surface_to_grey_scale(NvttbSurface *s, float r, float g, float b, float a) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    return grey_scale_device(ctx, (float *)s->buf.p, (size_t)s->w * s->h, r, g, b, a);
 }
-int nvttb_surface_to_normal_map(NvttbSurface *s, float, float, float, float) {
-    return s ? fail(s->ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "toNormalMap not implemented yet") : NVTTB_ERR_INVALID_INPUT;
+int nvttb_surface_to_normal_map(NvttbSurface *s, float sm, float medium, float big, float large) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf nb;
+    int rc = ensure(ctx, nb, (size_t)s->w * s->h * 16);
+    if (rc != NVTTB_OK) return rc;
+    const float fw[4] = {sm, medium, big, large};
+    rc = normal_map_device(ctx, (const float *)s->buf.p, (float *)nb.p, s->w, s->h, s->wrapMode, fw);
+    if (rc != NVTTB_OK) { cudaFree(nb.p); return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->buf.p);
+    s->buf = nb;
+    s->isNormalMap = 1;  // Surface::toNormalMap sets the flag (Surface.cpp:2807)
+    return NVTTB_OK;
 }
 
 int nvttb_surface_download(const NvttbSurface *s, float *out) {
@@ -846,7 +893,6 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     const size_t fbytes = face_bytes(d);
     const int W = d->width, H = d->height;
     int rc;
-    if (d->convertToNormalMap) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "convertToNormalMap not implemented yet");
     // ping-pong level buffers: A holds level m, B receives level m+1
     DevBuf &A = ctx->lvlA, &B = ctx->lvlB;  // persistent scratch: no cudaMalloc/cudaFree per call
     if ((rc = ensure(ctx, A, (size_t)W * H * 16)) != NVTTB_OK) return rc;
@@ -855,7 +901,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
         if ((rc = ensure(ctx, B, (size_t)w1 * h1 * 16)) != NVTTB_OK) return rc;
     }
     auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); };
-    const bool colour = !d->isNormalMap;
+    const bool toNormal = d->convertToNormalMap != 0;
+    const bool isNormal = d->isNormalMap || toNormal;  // toNormalMap flags the surface as a normal map (Surface.cpp:2807)
+    const bool colour = !isNormal;
     const bool linFast = colour && d->inputGamma == 2.2f;
     const bool gamFast = colour && d->outputGamma == 2.2f;
     const bool gamSlow = colour && !gamFast && !nv_equal(d->outputGamma, 1.0f);
@@ -867,6 +915,13 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
         }
         float *cur = (float *)A.p, *nxt = (float *)B.p;
+        if (toNormal) {
+            // img.toGreyScale(heightFactors); img.toNormalMap(bumpFrequencyScale)  (Context.cpp:269-272)
+            if ((rc = ensure(ctx, ctx->tmp_level, (size_t)W * H * 16)) != NVTTB_OK) { cleanup(); return rc; }
+            if ((rc = grey_scale_device(ctx, cur, (size_t)W * H, d->heightFactors[0], d->heightFactors[1], d->heightFactors[2], d->heightFactors[3])) != NVTTB_OK) { cleanup(); return rc; }
+            if ((rc = normal_map_device(ctx, cur, (float *)ctx->tmp_level.p, W, H, d->wrapMode, d->bumpFrequencyScale)) != NVTTB_OK) { cleanup(); return rc; }
+            CK(cudaMemcpyAsync(cur, ctx->tmp_level.p, (size_t)W * H * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         int w = W, h = H;
         for (int m = 0; m < mips; m++) {
             if (m > 0) {
@@ -882,7 +937,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 float *t = cur; cur = nxt; nxt = t;
                 w = dw;
                 h = dh;
-                if (d->isNormalMap && d->normalizeMipmaps) {
+                if (isNormal && d->normalizeMipmaps) {
                     NormalizeParams P{cur, (size_t)w * h, 1};
                     NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
                 }

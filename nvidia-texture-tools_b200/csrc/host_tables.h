@@ -220,4 +220,26 @@ inline void build_polyphase(const FilterDesc &f, unsigned srcLength, unsigned ds
     }
 }
 
+// Kernel2(9)::initBlendedSobel(scale) + Kernel2::normalize (src/nvimage/Filter.cpp:494-560,358-369).
+// A (2k+1)^2 Sobel-like derivative kernel has element sign(e-k) * ((k+1-|e-k|) + (k-|i-k|)) at row i, column e; the four
+// sizes 9,7,5,3 are blended with weights scale.w, .z, .y, .x (accumulated in that order) and L1-normalised.
+static inline void build_blended_sobel(const float scale[4], float out[81]) {
+    const float wts[4] = {scale[3], scale[2], scale[1], scale[0]};
+    for (int s = 0; s < 4; s++) {
+        const int k = 4 - s, n = 2 * k + 1, off = s;
+        for (int i = 0; i < n; i++)
+            for (int e = 0; e < n; e++) {
+                const int de = e - k, ae = de < 0 ? -de : de, ai = (i - k) < 0 ? (k - i) : (i - k);
+                const float elem = (de == 0) ? 0.0f : (float)((de < 0 ? -1 : 1) * ((k + 1 - ae) + (k - ai)));
+                float &dst = out[(i + off) * 9 + e + off];
+                if (s == 0) dst = elem * wts[s];
+                else dst += elem * wts[s];
+            }
+    }
+    float total = 0.0f;
+    for (int i = 0; i < 81; i++) total += fabsf(out[i]);
+    const float inv = 1.0f / total;
+    for (int i = 0; i < 81; i++) out[i] *= inv;
+}
+
 }  // namespace nvb

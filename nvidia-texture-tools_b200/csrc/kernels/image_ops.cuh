@@ -284,4 +284,68 @@ __global__ void __launch_bounds__(256) k_normalize(NormalizeParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Surface::toGreyScale (src/nvtt/Surface.cpp:1732-1756): grey = r*rs + g*gs + b*bs + a*as written to all four planes.
+// The scales are normalised by their sum on the host exactly like the reference does.
+// ---------------------------------------------------------------------------------------------------------
+struct GreyScaleParams {
+    float *data;    // planar fp32 RGBA, in place
+    size_t pixels;
+    float scale[4];
+};
+
+__global__ void __launch_bounds__(256) k_grey_scale(GreyScaleParams P) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.pixels; i += (size_t)gridDim.x * blockDim.x) {
+        const float grey = P.data[i] * P.scale[0] + P.data[P.pixels + i] * P.scale[1] + P.data[2 * P.pixels + i] * P.scale[2] +
+                           P.data[3 * P.pixels + i] * P.scale[3];
+        P.data[i] = grey;
+        P.data[P.pixels + i] = grey;
+        P.data[2 * P.pixels + i] = grey;
+        P.data[3 * P.pixels + i] = grey;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Surface::toNormalMap -> nv::createNormalMap(FloatImage*, wm, filterWeights) (src/nvimage/NormalMap.cpp:82-124,183-198):
+// du/dv = 9x9 blended-Sobel response of the alpha plane (FloatImage::applyKernelXY, FloatImage.cpp:1019-1044: rows
+// outer, columns inner, one running fp32 sum), n = normalize(du, dv, 1/16); alpha is copied.  The 9x9 kernel
+// (Kernel2::initBlendedSobel + L1 normalize, Filter.cpp:494-560,358-369) is built on the host; kdv is its transpose.
+// 162 taps per texel from a plane that lives in L2 after the first touch: HBM-bound at 4 B in + 16 B out per texel.
+// ---------------------------------------------------------------------------------------------------------
+struct NormalMapParams {
+    const float *src;  // planar fp32 RGBA
+    float *dst;        // planar fp32 RGBA (different buffer)
+    int w, h;
+    int wrap;
+    float kdu[81];     // kdu[i*9 + e] = valueAt(e, i)
+};
+
+__global__ void __launch_bounds__(256) k_to_normal_map(NormalMapParams P) {
+    const size_t pixels = (size_t)P.w * P.h;
+    const float *alpha = P.src + 3 * pixels;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(p % P.w), y = (int)(p / P.w);
+        float du = 0.0f, dv = 0.0f;
+        int xs[9];
+#pragma unroll
+        for (int e = 0; e < 9; e++) xs[e] = wrap_coord(x + e - 4, P.w, P.wrap);
+        for (int i = 0; i < 9; i++) {
+            const float *row = alpha + (size_t)wrap_coord(y + i - 4, P.h, P.wrap) * P.w;
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                const float v = row[xs[e]];
+                du += P.kdu[i * 9 + e] * v;
+                dv += P.kdu[e * 9 + i] * v;  // kdv = transpose(kdu)
+            }
+        }
+        const float hs = 1.0f / 16.0f;
+        const float l = sqrtf(du * du + dv * dv + hs * hs);
+        const float il = 1.0f / l;
+        P.dst[p] = du * il;
+        P.dst[pixels + p] = dv * il;
+        P.dst[2 * pixels + p] = hs * il;
+        P.dst[3 * pixels + p] = alpha[p];
+    }
+}
+
 }  // namespace nvb

@@ -160,6 +160,20 @@ void emu_normalize(float *data, size_t pixels, int expand_pack) {
     emu::launch(dim3((unsigned)((pixels + 255) / 256)), dim3(256), 0, [&] { k_normalize(P); });
 }
 
+void emu_grey_scale(float *data, size_t pixels, float r, float g, float b, float a) {
+    const float sum = r + g + b + a;
+    GreyScaleParams P{data, pixels, {r / sum, g / sum, b / sum, a / sum}};
+    emu::launch(dim3((unsigned)((pixels + 255) / 256)), dim3(256), 0, [&] { k_grey_scale(P); });
+}
+
+void emu_to_normal_map(const float *src, float *dst, int w, int h, int wrap, const float *fw) {
+    NormalMapParams P;
+    P.src = src; P.dst = dst; P.w = w; P.h = h; P.wrap = wrap;
+    build_blended_sobel(fw, P.kdu);
+    size_t pixels = (size_t)w * h;
+    emu::launch(dim3((unsigned)((pixels + 255) / 256)), dim3(256), 0, [&] { k_to_normal_map(P); });
+}
+
 void emu_scale_bias(float *data, size_t pixels, float scale, float bias) {
     ScaleBiasParams P{data, 3 * pixels, scale, bias};
     emu::launch(dim3((unsigned)((P.count + 255) / 256)), dim3(256), 0, [&] { k_scale_bias(P); });

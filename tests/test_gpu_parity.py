@@ -177,6 +177,20 @@ def test_surface_misc_bit_exact(nvtt, ref, ctx):
         getattr(a, op)()
         getattr(b, op)()
         assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), op
+    # height map -> normal map (toGreyScale + 9x9 blended Sobel toNormalMap), every wrap mode
+    for wrap in (0, 1, 2):
+        for (ww, hh) in ((96, 40), (7, 5), (1, 1)):
+            hm = rng.integers(0, 256, (hh, ww, 4), dtype=np.uint8)
+            a = ref.Surface(wrap=wrap)
+            b = nvtt.Surface(ctx, wrap=wrap)
+            a.set_image(0, ww, hh, hm)
+            b.set_image(0, ww, hh, hm)
+            a.to_grey_scale(0.3, 0.5, 0.1, 0.4)
+            b.to_grey_scale(0.3, 0.5, 0.1, 0.4)
+            assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "toGreyScale"
+            a.to_normal_map(1.0 / 1.875, 0.5 / 1.875, 0.25 / 1.875, 0.125 / 1.875)
+            b.to_normal_map(1.0 / 1.875, 0.5 / 1.875, 0.25 / 1.875, 0.125 / 1.875)
+            assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "toNormalMap wrap %d %dx%d" % (wrap, ww, hh)
     # resize with every filter
     for filt in (0, 1, 2, 3):
         a = ref.Surface(wrap=1)
@@ -211,6 +225,9 @@ PIPE_CASES = [
     ("bc3_box_transparency", "alpha", "BC3", 2, dict(mip_filter=0, alpha_mode=1)),
     ("bc3_no_mips_gamma1", "alpha", "BC3", 1, dict(mipmaps=False, gamma=(1.0, 1.0))),
     ("bc3_maxlevel3", "photo", "BC3", 1, dict(max_level=3)),
+    ("bc5_height_to_normal_kaiser", "alpha", "BC5", 1, dict(mip_filter=2, to_normal_map=True)),
+    ("bc5_production_normal_box", "normal", "BC5", 2, dict(mip_filter=0, normal_map=True)),
+    ("bc3_highest_box", "alpha", "BC3", 3, dict(mip_filter=0)),
 ]
 
 
