@@ -39,8 +39,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
@@ -337,7 +337,10 @@ int nvttb_format_supported(int format, int quality) {
     case F_DXT1:
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5:
+    case F_DXT3:
         return quality >= Q_Normal && quality <= Q_Highest;
+    case F_DXT5n:
+        return quality == Q_Normal || quality == Q_Production;
     case F_BC6:
     case F_BC7:
         return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102)
@@ -409,16 +412,30 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     } else if (d->format == F_BC5) {
         alpha(0, 16, 0, d->quality >= Q_Production);
         alpha(1, 16, 8, d->quality >= Q_Production);
-    } else if (d->format == F_DXT5) {
-        alpha(3, 16, 0, d->quality == Q_Highest);  // CompressorDX9.cpp:149-157
+    } else if (d->format == F_DXT5 || d->format == F_DXT3 || d->format == F_DXT5n) {
+        if (d->format == F_DXT5) {
+            alpha(3, 16, 0, d->quality == Q_Highest);  // CompressorDX9.cpp:149-157
+        } else if (d->format == F_DXT5n) {
+            alpha(0, 16, 0, false);  // "rgba.swizzle(4,1,5,0)": alpha block = red channel, QuickCompress (CompressorDX9.cpp:212-221)
+        } else {
+            AlphaBlocksParams A;  // CompressorDXT3: OptimalCompress::compressDXT3A on the alpha channel (CompressorDX9.cpp:119-124)
+            A.lv = lv;
+            A.channel = 3;
+            A.out = d_out;
+            A.out_stride = 16;
+            A.out_offset = 0;
+            A.mode = 0;
+            NVB_LAUNCH(ctx, K_ALPHA_DXT3, (double)w * h, k_alpha_dxt3, grid_for(nb, 128), 128, A);
+        }
         Bc3ColorParams P;
         P.lv = lv;
         P.out = d_out;
         P.out_stride = 16;
         P.out_offset = 8;
-        P.metric[0] = d->colorWeights[0];
-        P.metric[1] = d->colorWeights[1];
-        P.metric[2] = d->colorWeights[2];
+        P.dxt5n = (d->format == F_DXT5n);
+        P.metric[0] = P.dxt5n ? 0.0f : d->colorWeights[0];
+        P.metric[1] = P.dxt5n ? 1.0f : d->colorWeights[1];
+        P.metric[2] = P.dxt5n ? 0.0f : d->colorWeights[2];
         P.weight_by_alpha = (d->alphaMode == AM_Transparency);
         P.cand = ctx->d_cand;
         P.cand_off = ctx->d_cand_off;

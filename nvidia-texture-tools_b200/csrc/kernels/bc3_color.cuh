@@ -31,6 +31,7 @@ struct Bc3ColorParams {
     const int *cand_off;    // cand_off[n] .. cand_off[n+1] = splits for a set of n points (n = 1..16), 18 ints
     const unsigned char *omatch5;  // [256][2]
     const unsigned char *omatch6;  // [256][2]
+    int dxt5n;              // 1: CompressorDXT5n colour block — tile swizzled to (0xFF, G, 0) and metric (0,1,0) (CompressorDX9.cpp:179-210)
 };
 
 #define NVB_BC3_GROUPS 8  // 4x4 blocks per CTA (128 threads)
@@ -106,9 +107,12 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
     const int bx = blk % P.lv.bw, by = blk / P.lv.bw;
     const int tw = min(P.lv.w - bx * 4, 4), th = min(P.lv.h - by * 4, 4);
     const int px = bx * 4 + (l & 3) % tw, py = by * 4 + (l >> 2) % th;
-    const unsigned r8 = quantize_u8_trunc(load_texel(P.lv, 0, px, py));
+    unsigned r8 = 0xFF, b8 = 0;
     const unsigned g8 = quantize_u8_trunc(load_texel(P.lv, 1, px, py));
-    const unsigned b8 = quantize_u8_trunc(load_texel(P.lv, 2, px, py));
+    if (!P.dxt5n) {
+        r8 = quantize_u8_trunc(load_texel(P.lv, 0, px, py));
+        b8 = quantize_u8_trunc(load_texel(P.lv, 2, px, py));
+    }
     float walpha = 1.0f;
     if (P.weight_by_alpha) {
         const unsigned a8 = quantize_u8_trunc(load_texel(P.lv, 3, px, py));
@@ -137,7 +141,17 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
 
     if (n == 1) {
         // single colour: optimal endpoints from the match tables, all indices 2.
-        if (l == 0) {
+        if (l == 0 && P.dxt5n) {
+            // OptimalCompress::compressDXT1G(uint8 g): red 31, blue 0, green from the 6-bit match table
+            unsigned c0 = (31u << 11) | ((unsigned)P.omatch6[g8 * 2 + 0] << 5);
+            unsigned c1 = (31u << 11) | ((unsigned)P.omatch6[g8 * 2 + 1] << 5);
+            unsigned indices = 0xaaaaaaaau;
+            if (c0 < c1) {
+                unsigned t = c0; c0 = c1; c1 = t;
+                indices ^= 0x55555555u;
+            }
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(c0 | (c1 << 16), indices);
+        } else if (l == 0) {
             unsigned c0 = ((unsigned)P.omatch5[r8 * 2 + 0] << 11) | ((unsigned)P.omatch6[g8 * 2 + 0] << 5) | P.omatch5[b8 * 2 + 0];
             unsigned c1 = ((unsigned)P.omatch5[r8 * 2 + 1] << 11) | ((unsigned)P.omatch6[g8 * 2 + 1] << 5) | P.omatch5[b8 * 2 + 1];
             unsigned indices = 0xaaaaaaaau;

@@ -292,4 +292,33 @@ __global__ void __launch_bounds__(128) k_alpha_optimal(AlphaBlocksParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// BC2 explicit alpha: OptimalCompress::compressDXT3A (src/nvtt/OptimalCompressDXT.cpp:140-157,485-503) — each texel
+// takes the nearest of the three 4-bit levels around a>>4 (bit-replicated to 8 bits), first on ties as written.
+// One thread per block; texel i lands in bits [4i, 4i+4) (AlphaBlockDXT3, src/nvimage/BlockDXT.h:77-99).
+// ---------------------------------------------------------------------------------------------------------
+NVB_DEV unsigned alpha_quantize4(unsigned a) {
+    int q0 = max((int)(a >> 4) - 1, 0), q1 = (int)(a >> 4), q2 = min((int)(a >> 4) + 1, 0xF);
+    q0 = (q0 << 4) | q0;
+    q1 = (q1 << 4) | q1;
+    q2 = (q2 << 4) | q2;
+    const int d0 = (q0 - (int)a) * (q0 - (int)a), d1 = (q1 - (int)a) * (q1 - (int)a), d2 = (q2 - (int)a) * (q2 - (int)a);
+    if (d0 < d1 && d0 < d2) return (unsigned)(q0 >> 4);
+    if (d1 < d2) return (unsigned)(q1 >> 4);
+    return (unsigned)(q2 >> 4);
+}
+
+__global__ void __launch_bounds__(128) k_alpha_dxt3(AlphaBlocksParams P) {
+    const int nblocks = P.lv.bw * P.lv.bh;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += gridDim.x * blockDim.x) {
+        unsigned src[16];
+        alpha_gather_block(P.lv, P.channel, blk % P.lv.bw, blk / P.lv.bw, src);
+        unsigned long long b = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) b |= (unsigned long long)alpha_quantize4(src[i]) << (4 * i);
+        *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+            make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
+    }
+}
+
 }  // namespace nvb

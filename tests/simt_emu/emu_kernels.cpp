@@ -53,17 +53,23 @@ void emu_alpha_blocks(const float *planar, int w, int h, int channel, unsigned c
     P.lv = make_lv(planar, w, h, gamma);
     P.channel = channel; P.out = out; P.out_stride = stride; P.out_offset = offset; P.mode = mode;
     int nb = P.lv.bw * P.lv.bh;
-    if (mode == 1) emu::launch(dim3((nb + 3) / 4), dim3(128), 0, [&] { k_alpha_optimal(P); });
+    if (mode == 2) emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_alpha_dxt3(P); });
+    else if (mode == 1) emu::launch(dim3((nb + 3) / 4), dim3(128), 0, [&] { k_alpha_optimal(P); });
     else emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_alpha_blocks(P); });
 }
 
+void emu_bc3_color_ex(const float *planar, int w, int h, const float *metric, int weight_by_alpha, unsigned char *out, int stride, int offset, int gamma, int dxt5n);
 void emu_bc3_color(const float *planar, int w, int h, const float *metric, int weight_by_alpha, unsigned char *out, int stride, int offset, int gamma) {
+    emu_bc3_color_ex(planar, w, h, metric, weight_by_alpha, out, stride, offset, gamma, 0);
+}
+void emu_bc3_color_ex(const float *planar, int w, int h, const float *metric, int weight_by_alpha, unsigned char *out, int stride, int offset, int gamma, int dxt5n) {
     init_tables();
     Bc3ColorParams P;
     P.lv = make_lv(planar, w, h, gamma);
     P.out = out; P.out_stride = stride; P.out_offset = offset;
     P.metric[0] = metric[0]; P.metric[1] = metric[1]; P.metric[2] = metric[2];
     P.weight_by_alpha = weight_by_alpha;
+    P.dxt5n = dxt5n;
     P.cand = g_cand.data(); P.cand_off = g_cand_off; P.omatch5 = g_om5; P.omatch6 = g_om6;
     int nb = P.lv.bw * P.lv.bh;
     emu::launch(dim3((nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS), dim3(NVB_BC3_GROUPS * 16), 0, [&] { k_bc3_color(P); });
