@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200.so")
 # nvtt enums (src/nvtt/nvtt.h:80-277 of the reference)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
 Format_BC6, Format_BC7 = 10, 11
-Format_BC1, Format_BC2, Format_BC3 = Format_DXT1, Format_DXT3, Format_DXT5
+Format_BC1, Format_BC2, Format_BC3, Format_BC3n = Format_DXT1, Format_DXT3, Format_DXT5, Format_DXT5n
 Quality_Fastest, Quality_Normal, Quality_Production, Quality_Highest = range(4)
 WrapMode_Clamp, WrapMode_Repeat, WrapMode_Mirror = range(3)
 InputFormat_BGRA_8UB, InputFormat_RGBA_16F, InputFormat_RGBA_32F, InputFormat_R_32F = range(4)
