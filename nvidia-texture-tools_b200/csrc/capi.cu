@@ -54,6 +54,11 @@ struct NvttbContext {
     std::vector<ProfRec> prof;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaStream_t stream = nullptr;
+    // copy engines run beside the kernels: host->device bands are uploaded on h2d_stream while earlier bands are
+    // converted and encoded on `stream`; finished level-0 bands go back on d2h_stream while the mip chain is computed
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    enum { MAX_BANDS = 8 };
+    cudaEvent_t ev_up[MAX_BANDS] = {}, ev_enc[MAX_BANDS] = {}, ev_stage_free = nullptr, ev_tail = nullptr;
     std::string err;
     uint64_t launches = 0;
     float *d_to_gamma = nullptr, *d_to_linear = nullptr;
@@ -178,6 +183,14 @@ int nvttb_context_create(int device, NvttbContext **out) {
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < NvttbContext::MAX_BANDS; i++) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     float tg[512], tl[512];
     build_gamma_tables(tg, tl);
     std::vector<uint16_t> cand;
@@ -227,6 +240,8 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
     cudaFree(ctx->d_to_gamma);
     cudaFree(ctx->d_to_linear);
     cudaFree(ctx->d_cand);
@@ -249,6 +264,14 @@ void nvttb_context_destroy(NvttbContext *ctx) {
         cudaFree(kv.second.weights);
         cudaFree(kv.second.left);
     }
+    for (int i = 0; i < NvttbContext::MAX_BANDS; i++) {
+        if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+        if (ctx->ev_enc[i]) cudaEventDestroy(ctx->ev_enc[i]);
+    }
+    if (ctx->ev_stage_free) cudaEventDestroy(ctx->ev_stage_free);
+    if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -360,10 +383,12 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, const
 }
 
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
-static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out) {
+// d_rgba points at row 0 of the rows to encode (h of them); plane = floats between the planes of the level they belong to
+static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out, size_t plane = 0) {
     if (!nvttb_format_supported(d->format, d->quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
     LevelView lv;
     lv.data = d_rgba;
+    lv.plane = plane ? plane : (size_t)w * h;
     lv.w = w;
     lv.h = h;
     lv.bw = (w + 3) / 4;
@@ -626,6 +651,14 @@ static size_t input_bpp(int inputFormat) {
     }
 }
 
+// convert `pixels` interleaved texels at d_src to planar fp32 at dst (plane stride `plane`), optionally fusing toLinear(2.2)
+static int convert_device(NvttbContext *ctx, int inputFormat, const void *d_src, size_t pixels, float *dst, size_t plane, bool fuseToLinear) {
+    SetImageParams P{d_src, dst, (int)pixels, inputFormat, fuseToLinear ? ctx->d_to_linear : nullptr, plane};
+    NVB_LAUNCH(ctx, K_SET_IMAGE, (double)pixels, k_set_image, grid_for(pixels, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
 // upload (if needed) + convert to planar fp32, optionally fusing toLinear(2.2)
 static int set_image_device(NvttbContext *ctx, int inputFormat, int w, int h, const void *data, int location, float *dst, bool fuseToLinear) {
     const size_t bpp = input_bpp(inputFormat);
@@ -638,10 +671,7 @@ static int set_image_device(NvttbContext *ctx, int inputFormat, int w, int h, co
         CK(cudaMemcpyAsync(ctx->in_stage.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_src = ctx->in_stage.p;
     }
-    SetImageParams P{d_src, dst, w * h, inputFormat, fuseToLinear ? ctx->d_to_linear : nullptr};
-    NVB_LAUNCH(ctx, K_SET_IMAGE, (double)w * h, k_set_image, grid_for((size_t)w * h, 256), 256, P);
-    CK(cudaGetLastError());
-    return NVTTB_OK;
+    return convert_device(ctx, inputFormat, d_src, (size_t)w * h, dst, (size_t)w * h, fuseToLinear);
 }
 
 extern "C" {
@@ -904,8 +934,10 @@ size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
 }
 
 // Runs faces [f0,f1) and leaves their encoded chains in d_out (face-major, mip-minor).
+// h_out (optional, pinned host memory of the same layout as d_out): finished pieces are copied back on d2h_stream while
+// the rest of the chain is still being computed; the caller synchronises d2h_stream.
 static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, int f0, int f1,
-                         unsigned char *d_out) {
+                         unsigned char *d_out, unsigned char *h_out = nullptr) {
     const int mips = nvttb_process_mip_count(d);
     const size_t fbytes = face_bytes(d);
     const int W = d->width, H = d->height;
@@ -917,19 +949,69 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
         const int w1 = W / 2 > 1 ? W / 2 : 1, h1 = H / 2 > 1 ? H / 2 : 1;
         if ((rc = ensure(ctx, B, (size_t)w1 * h1 * 16)) != NVTTB_OK) return rc;
     }
-    auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); };
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+    };
     const bool toNormal = d->convertToNormalMap != 0;
     const bool isNormal = d->isNormalMap || toNormal;  // toNormalMap flags the surface as a normal map (Surface.cpp:2807)
     const bool colour = !isNormal;
     const bool linFast = colour && d->inputGamma == 2.2f;
     const bool gamFast = colour && d->outputGamma == 2.2f;
     const bool gamSlow = colour && !gamFast && !nv_equal(d->outputGamma, 1.0f);
+    // Row-band pipeline for host input: level 0 is uploaded, converted and encoded band by band, so the H2D copy of band
+    // b+1 (h2d_stream) runs under the encode of band b (stream) and the D2H copy of band b's blocks (d2h_stream) under
+    // everything that follows.  Needs the per-texel-only prologue (fused toLinear or none).
+    const size_t bpp = input_bpp(d->inputFormat);
+    const bool banded = loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
+    const int bhTotal = (H + 3) / 4;
+    const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
+    const int bandBlockRows = (bhTotal + nbands - 1) / nbands;
+    const size_t bs = (size_t)block_bytes(d->encode.format), bw0 = (size_t)((W + 3) / 4);
     for (int f = f0; f < f1; f++) {
         unsigned char *out = d_out + (size_t)(f - f0) * fbytes;
-        // setImage (+ toLinear)
-        if ((rc = set_image_device(ctx, d->inputFormat, W, H, images[f], loc, (float *)A.p, linFast)) != NVTTB_OK) { cleanup(); return rc; }
-        if (colour && !linFast) {
-            if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
+        unsigned char *hout = h_out ? h_out + (size_t)(f - f0) * fbytes : nullptr;
+        bool level0_done = false;
+        if (banded) {
+            if (!images[f]) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad input image");
+            if ((rc = ensure(ctx, ctx->in_stage, (size_t)W * H * bpp)) != NVTTB_OK) { cleanup(); return rc; }
+            // the staging buffer is still being read by the previous face's conversion kernels
+            if (f > f0) CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
+            for (int b = 0; b < nbands; b++) {
+                const int y0 = b * bandBlockRows * 4, y1 = (b + 1) * bandBlockRows * 4 < H ? (b + 1) * bandBlockRows * 4 : H;
+                if (y0 >= y1) continue;
+                const size_t off = (size_t)y0 * W * bpp;
+                CK(cudaMemcpyAsync((char *)ctx->in_stage.p + off, (const char *)images[f] + off, (size_t)(y1 - y0) * W * bpp, cudaMemcpyHostToDevice, ctx->h2d_stream));
+                CK(cudaEventRecord(ctx->ev_up[b], ctx->h2d_stream));
+            }
+            NvttbEncodeDesc e = d->encode;
+            e.width = W;
+            e.alphaMode = d->alphaMode;
+            e.applyToGamma = gamFast ? 1 : 0;
+            for (int b = 0; b < nbands; b++) {
+                const int y0 = b * bandBlockRows * 4, y1 = (b + 1) * bandBlockRows * 4 < H ? (b + 1) * bandBlockRows * 4 : H;
+                if (y0 >= y1) continue;
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[b], 0));
+                float *rows = (float *)A.p + (size_t)y0 * W;
+                if ((rc = convert_device(ctx, d->inputFormat, (const char *)ctx->in_stage.p + (size_t)y0 * W * bpp, (size_t)(y1 - y0) * W, rows, (size_t)W * H, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+                e.height = y1 - y0;
+                const size_t ooff = (size_t)(y0 / 4) * bw0 * bs, obytes = (size_t)((y1 - y0 + 3) / 4) * bw0 * bs;
+                if ((rc = encode_device(ctx, &e, rows, W, y1 - y0, out + ooff, (size_t)W * H)) != NVTTB_OK) { cleanup(); return rc; }
+                if (hout) {
+                    CK(cudaEventRecord(ctx->ev_enc[b], ctx->stream));
+                    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_enc[b], 0));
+                    CK(cudaMemcpyAsync(hout + ooff, out + ooff, obytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                }
+            }
+            CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+            level0_done = true;
+        } else {
+            // setImage (+ toLinear)
+            if ((rc = set_image_device(ctx, d->inputFormat, W, H, images[f], loc, (float *)A.p, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+            if (colour && !linFast) {
+                if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
+            }
         }
         float *cur = (float *)A.p, *nxt = (float *)B.p;
         if (toNormal) {
@@ -972,8 +1054,19 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 if ((rc = gamma_device(ctx, (float *)ctx->tmp_level.p, (size_t)w * h, false, d->outputGamma)) != NVTTB_OK) { cleanup(); return rc; }
                 src = (const float *)ctx->tmp_level.p;
             }
-            if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
+            if (!(m == 0 && level0_done)) {
+                if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
+            }
             out += nvttb_level_size(e.format, w, h);
+        }
+        if (hout) {
+            // whatever of this face has not been sent yet: the mip tail (banded) or the whole chain
+            const size_t done = level0_done ? nvttb_level_size(d->encode.format, W, H) : 0;
+            if (fbytes > done) {
+                CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_tail, 0));
+                CK(cudaMemcpyAsync(hout + done, d_out + (size_t)(f - f0) * fbytes + done, fbytes - done, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
         }
         // the level buffers are reused by the next face: same stream, so ordering is implicit
     }
@@ -1017,9 +1110,9 @@ int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *cons
     const size_t total = fbytes * (size_t)(f1 - f0);
     if ((rc = ensure(ctx, ctx->out_dev, total)) != NVTTB_OK) return rc;
     if ((rc = ensure_pinned(ctx, total)) != NVTTB_OK) return rc;
-    if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)ctx->out_dev.p)) != NVTTB_OK) return rc;
-    CK(cudaMemcpyAsync(ctx->h_out, ctx->out_dev.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)ctx->out_dev.p, (unsigned char *)ctx->h_out)) != NVTTB_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
     const int mips = nvttb_process_mip_count(d);
     const unsigned char *p = (const unsigned char *)ctx->h_out;
     for (int f = f0; f < f1; f++) {

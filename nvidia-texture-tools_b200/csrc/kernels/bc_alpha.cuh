@@ -148,7 +148,7 @@ struct AlphaBlocksParams {
 
 NVB_DEV void alpha_gather_block(const LevelView &lv, int channel, int bx, int by, unsigned src[16]) {
     const int x0 = bx * 4, y0 = by * 4;
-    const float *plane = lv.data + (size_t)channel * lv.w * lv.h;
+    const float *plane = lv.data + (size_t)channel * lv.plane;
     const bool gam = (lv.to_gamma_table != nullptr && channel < 3);
     if (x0 + 4 <= lv.w && y0 + 4 <= lv.h && (lv.w & 3) == 0) {
 #pragma unroll

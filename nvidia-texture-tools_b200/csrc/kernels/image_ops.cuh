@@ -41,9 +41,10 @@ NVB_DEV float half_bits_to_float(unsigned h) {
 struct SetImageParams {
     const void *src;  // interleaved input texels
     float *dst;       // planar fp32 RGBA
-    int count;        // pixels
+    int count;        // pixels converted by this launch
     int format;       // nvtt::InputFormat: 0 BGRA_8UB, 1 RGBA_16F, 2 RGBA_32F, 3 R_32F
     const float *to_linear_table;  // non-null => fused Surface::toLinear(2.2) on R,G,B
+    size_t plane;     // floats between output planes (= pixels of the whole image; a row band converts `count` < plane pixels)
 };
 
 __global__ void __launch_bounds__(256) k_set_image(SetImageParams P) {
@@ -75,9 +76,9 @@ __global__ void __launch_bounds__(256) k_set_image(SetImageParams P) {
             b = nvb_powf_11_5(b, P.to_linear_table);
         }
         P.dst[i] = r;
-        P.dst[n + i] = g;
-        P.dst[2 * n + i] = b;
-        P.dst[3 * n + i] = a;
+        P.dst[P.plane + i] = g;
+        P.dst[2 * P.plane + i] = b;
+        P.dst[3 * P.plane + i] = a;
     }
 }
 

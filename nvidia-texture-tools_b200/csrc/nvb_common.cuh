@@ -72,14 +72,15 @@ NVB_DEV unsigned quantize_u8_trunc(float v) {
 
 // How an encoder kernel reads one mip level: planar fp32 [c][y][x] (FloatImage layout, FloatImage.h:193-229).
 struct LevelView {
-    const float *__restrict__ data;  // 4 planes of w*h floats
+    const float *__restrict__ data;  // 4 planes; row y of plane c starts at data + c*plane + y*w
+    size_t plane;                 // floats between planes (w*h of the whole level; a row band of a level keeps the level's stride)
     int w, h;
     int bw, bh;                   // blocks per row / column = (w+3)/4, (h+3)/4
     const float *to_gamma_table;  // non-null => apply powf_5_11 to R,G,B while loading (fused Surface::toGamma)
 };
 
 NVB_DEV float load_texel(const LevelView &lv, int c, int x, int y) {
-    float v = lv.data[(size_t)c * lv.w * lv.h + (size_t)y * lv.w + x];
+    float v = lv.data[(size_t)c * lv.plane + (size_t)y * lv.w + x];
     if (lv.to_gamma_table != nullptr && c < 3) v = nvb_powf_5_11(v, lv.to_gamma_table);
     return v;
 }

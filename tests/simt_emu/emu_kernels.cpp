@@ -34,7 +34,7 @@ static void init_tables() {
 }
 static LevelView make_lv(const float *data, int w, int h, int gamma) {
     LevelView lv;
-    lv.data = data; lv.w = w; lv.h = h; lv.bw = (w + 3) / 4; lv.bh = (h + 3) / 4;
+    lv.data = data; lv.plane = (size_t)w * h; lv.w = w; lv.h = h; lv.bw = (w + 3) / 4; lv.bh = (h + 3) / 4;
     lv.to_gamma_table = gamma ? g_to_gamma : nullptr;
     return lv;
 }
@@ -130,7 +130,7 @@ unsigned emu_half_from_float(unsigned f) { return half_from_float_bits(f); }
 
 void emu_set_image(const void *src, float *dst, int count, int format, int to_linear) {
     init_tables();
-    SetImageParams P{src, dst, count, format, to_linear ? g_to_linear : nullptr};
+    SetImageParams P{src, dst, count, format, to_linear ? g_to_linear : nullptr, (size_t)count};
     emu::launch(dim3((count + 255) / 256), dim3(256), 0, [&] { k_set_image(P); });
 }
 
