@@ -35,13 +35,14 @@ struct DevBuf {
 
 struct PolyDev {
     int window = 0, length = 0;
+    int max_extent = 0;  // most source samples any NVB_PF_TILE-wide run of outputs touches (for the fused 2-D kernel)
     float *weights = nullptr;
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -528,6 +529,11 @@ static int get_poly(NvttbContext *ctx, const FilterDesc &f, int src, int dst, Po
     PolyDev pd;
     pd.window = t.window;
     pd.length = t.length;
+    for (int i0 = 0; i0 < t.length; i0 += NVB_PF_TILE) {
+        const int i1 = (i0 + NVB_PF_TILE - 1 < t.length) ? i0 + NVB_PF_TILE - 1 : t.length - 1;
+        const int ext = t.left[i1] + t.window - t.left[i0];
+        if (ext > pd.max_extent) pd.max_extent = ext;
+    }
     CK(cudaMalloc(&pd.weights, t.weights.size() * sizeof(float)));
     CK(cudaMalloc(&pd.left, t.left.size() * sizeof(int)));
     CK(cudaMemcpy(pd.weights, t.weights.data(), t.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -543,6 +549,14 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
     int rc;
     if ((rc = get_poly(ctx, f, sw, dw, &px)) != NVTTB_OK) return rc;
     if ((rc = get_poly(ctx, f, sh, dh, &py)) != NVTTB_OK) return rc;
+    if (px.max_extent <= NVB_PF_EXT && py.max_extent <= NVB_PF_EXT && px.window <= NVB_PF_MAXWIN && py.window <= NVB_PF_MAXWIN) {
+        // fused X+Y in shared memory: the dw x sh intermediate never reaches HBM
+        Polyphase2DParams Q{src, dst, sw, sh, dw, dh, px.window, py.window, px.weights, px.left, py.weights, py.left, wrap};
+        dim3 grid((dw + NVB_PF_TILE - 1) / NVB_PF_TILE, (dh + NVB_PF_TILE - 1) / NVB_PF_TILE, 4);
+        NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, k_polyphase_2d, grid, 256, Q);
+        CK(cudaGetLastError());
+        return NVTTB_OK;
+    }
     if ((rc = ensure(ctx, ctx->tmp_filter, (size_t)dw * sh * 4 * sizeof(float))) != NVTTB_OK) return rc;
     float *tmp = (float *)ctx->tmp_filter.p;
     PolyphaseParams X{src, tmp, sw, sh, dw, sh, 4, px.window, px.weights, px.left, wrap};

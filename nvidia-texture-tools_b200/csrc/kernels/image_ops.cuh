@@ -239,6 +239,92 @@ __global__ void __launch_bounds__(256) k_polyphase_y(PolyphaseParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Fused separable resize: one CTA produces a 32x32 tile of one destination plane.  The source footprint of the tile is
+// staged in shared memory once (wrap mode applied while loading), the X pass is evaluated for the footprint's rows
+// into a second shared buffer and the Y pass reads that — the `dw x sh` intermediate image of FloatImage::resize
+// (FloatImage.cpp:761-808) never goes to HBM.  Every output is the same tap-ordered sum as in k_polyphase_x / _y, so the
+// result is bit-identical; HBM traffic drops from 16+8+8+4 to 16+4 bytes per source texel and channel group.
+// ---------------------------------------------------------------------------------------------------------
+#define NVB_PF_TILE 32
+#define NVB_PF_EXT 88   // max source rows / columns a tile may need (2:1 Kaiser width 3 needs 75)
+#define NVB_PF_MAXWIN 32
+
+struct Polyphase2DParams {
+    const float *src;
+    float *dst;
+    int sw, sh, dw, dh;
+    int winx, winy;
+    const float *wx;   // [dw][winx]
+    const int *leftx;  // [dw]
+    const float *wy;   // [dh][winy]
+    const int *lefty;  // [dh]
+    int wrap;
+};
+
+// source column cc of a staged row lives at NVB_PF_COL(cc): even and odd columns are kept apart so that the stride-2
+// reads of a 2:1 X pass (lane ox reads column 2*ox + const) hit 32 different banks
+#define NVB_PF_HALF ((NVB_PF_EXT + 1) / 2 + 1)
+#define NVB_PF_COL(cc) ((((cc) & 1) ? NVB_PF_HALF : 0) + ((cc) >> 1))
+
+__global__ void __launch_bounds__(256) k_polyphase_2d(Polyphase2DParams P) {
+    __shared__ float s_in[NVB_PF_EXT][2 * NVB_PF_HALF];
+    __shared__ float s_tmp[NVB_PF_EXT][NVB_PF_TILE + 1];
+    const int c = blockIdx.z;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * NVB_PF_TILE, ty0 = blockIdx.y * NVB_PF_TILE;
+    const int tw = min(NVB_PF_TILE, P.dw - tx0), th = min(NVB_PF_TILE, P.dh - ty0);
+    const int x_lo = P.leftx[tx0], x_hi = P.leftx[tx0 + tw - 1] + P.winx;
+    const int y_lo = P.lefty[ty0], y_hi = P.lefty[ty0 + th - 1] + P.winy;
+    const int ncols = x_hi - x_lo, nrows = y_hi - y_lo;
+    const float *plane = P.src + (size_t)c * P.sw * P.sh;
+    // 1. stage the footprint: one warp per row, lanes along x (coalesced); wrap only for tiles that touch the border
+    const bool interior = x_lo >= 0 && x_hi <= P.sw && y_lo >= 0 && y_hi <= P.sh;
+    for (int r = wid; r < nrows; r += 8) {
+        const int sy = interior ? y_lo + r : wrap_coord(y_lo + r, P.sh, P.wrap);
+        const float *row = plane + (size_t)sy * P.sw;
+        for (int cc = lane; cc < ncols; cc += 32) {
+            const int sx = interior ? x_lo + cc : wrap_coord(x_lo + cc, P.sw, P.wrap);
+            s_in[r][NVB_PF_COL(cc)] = row[sx];
+        }
+    }
+    __syncthreads();
+    // 2. X pass for every staged row: lane = output column, warp w owns rows w, w+8, ...; the taps are walked once and
+    //    every row keeps its own running sum, so each sum still adds its taps in ascending order
+    if (lane < tw) {
+        const float *wt = P.wx + (size_t)(tx0 + lane) * P.winx;
+        const int off = P.leftx[tx0 + lane] - x_lo;
+        float acc[(NVB_PF_EXT + 7) / 8];
+#pragma unroll
+        for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) acc[k] = 0.0f;
+        for (int j = 0; j < P.winx; j++) {
+            const float w = wt[j];
+            const int col = NVB_PF_COL(off + j);
+#pragma unroll
+            for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) {
+                const int r = wid + 8 * k;
+                if (r < nrows) acc[k] += w * s_in[r][col];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) {
+            const int r = wid + 8 * k;
+            if (r < nrows) s_tmp[r][lane] = acc[k];
+        }
+    }
+    __syncthreads();
+    // 3. Y pass: warp w owns output rows w, w+8, w+16, w+24
+    if (lane < tw) {
+        for (int oy = wid; oy < th; oy += 8) {
+            const float *wt = P.wy + (size_t)(ty0 + oy) * P.winy;
+            const int off = P.lefty[ty0 + oy] - y_lo;
+            float sum = 0;
+            for (int j = 0; j < P.winy; j++) sum += wt[j] * s_tmp[off + j][lane];
+            P.dst[(size_t)c * P.dw * P.dh + (size_t)(ty0 + oy) * P.dw + tx0 + lane] = sum;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Normal-map helpers.  k_scale_bias: ptr = scale*ptr + bias on planes 0..2.  k_normalize: normalizeSafe with
 // epsilon 0 (zero vector stays zero).  k_renormalize = expandNormals -> normalizeNormalMap -> packNormals
 // fused (element-wise, so fusing does not change a single bit), src/nvtt/Context.cpp:329-334.

@@ -1,6 +1,7 @@
 // TEST / DEBUG INFRASTRUCTURE ONLY — runs the product's device code (csrc/kernels/*.cuh) under the lock-step
 // CPU emulator so kernel logic can be checked against the oracle in a container without a GPU.
 #include "cuda_emu.h"
+#include <algorithm>
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc_alpha.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_icbc.cuh"
@@ -152,6 +153,19 @@ void emu_resize(const float *src, int sw, int sh, float *dst, int dw, int dh, in
     PolyphaseTable tx, ty;
     build_polyphase(f, sw, dw, tx);
     build_polyphase(f, sh, dh, ty);
+    auto ext = [](const PolyphaseTable &t) {
+        int m = 0;
+        for (int i0 = 0; i0 < t.length; i0 += NVB_PF_TILE) {
+            int i1 = std::min(i0 + NVB_PF_TILE - 1, t.length - 1);
+            m = std::max(m, t.left[i1] + t.window - t.left[i0]);
+        }
+        return m;
+    };
+    if (!getenv("NVB_EMU_UNFUSED") && ext(tx) <= NVB_PF_EXT && ext(ty) <= NVB_PF_EXT && tx.window <= NVB_PF_MAXWIN && ty.window <= NVB_PF_MAXWIN) {
+        Polyphase2DParams Q{src, dst, sw, sh, dw, dh, tx.window, ty.window, tx.weights.data(), tx.left.data(), ty.weights.data(), ty.left.data(), wrap};
+        emu::launch(dim3((dw + NVB_PF_TILE - 1) / NVB_PF_TILE, (dh + NVB_PF_TILE - 1) / NVB_PF_TILE, 4), dim3(256), 0, [&] { k_polyphase_2d(Q); });
+        return;
+    }
     std::vector<float> tmp((size_t)dw * sh * 4);
     PolyphaseParams X{src, tmp.data(), sw, sh, dw, sh, 4, tx.window, tx.weights.data(), tx.left.data(), wrap};
     size_t total = (size_t)dw * sh * 4;
