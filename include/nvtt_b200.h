@@ -150,6 +150,11 @@ typedef struct NvttbProcessDesc {
     int alphaMode;     /* nvtt::AlphaMode */
     NvttbEncodeDesc encode; /* format, quality, colour weights, pixel type (width/height/applyToGamma ignored) */
     int firstFace, lastFace;   /* process faces [firstFace, lastFace); 0,0 = all (multi-GPU sharding by face) */
+    /* Block-row sharding of ONE image over bandCount GPUs (bandCount <= 1: off).  Every band builds the whole fp32 mip
+     * chain (cheap, keeps every level bit-identical) but encodes only its own block rows of each level whose block-row
+     * count divides by bandCount; the remaining small levels are encoded by band 0 alone.  The call then produces, per
+     * face, the concatenation of this band's slices (see nvttb_process_band_slice); emit is called with the slice. */
+    int bandIndex, bandCount;
 } NvttbProcessDesc;
 
 /* Called once per (face, mip) in the reference's order (face-major, mip-minor); data is host memory owned by the
@@ -166,6 +171,10 @@ NVTTB_API int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc 
                                       int images_location, void *out_device, size_t out_capacity, size_t *written);
 /* Total bytes nvttb_process emits for this description (Compressor::estimateSize, src/nvtt/Context.cpp:122-137). */
 NVTTB_API size_t nvttb_process_output_size(const NvttbProcessDesc *desc);
+/* Where band `desc->bandIndex` of `desc->bandCount` sits inside mip level `level`: *offset = byte offset of the slice in
+ * the level, *bytes = its size (0: this band emits nothing for the level).  With bandCount <= 1 the slice is the level.
+ * Replaces nothing in the reference (it has no multi-device path); it is the contract between ranks for the gather. */
+NVTTB_API int nvttb_process_band_slice(const NvttbProcessDesc *desc, int level, size_t *offset, size_t *bytes);
 /* Number of mip levels the pipeline produces (nv::countMipmaps, src/nvtt/Surface.cpp:181-193, capped by maxLevel). */
 NVTTB_API int nvttb_process_mip_count(const NvttbProcessDesc *desc);
 

@@ -42,7 +42,8 @@ class ProcessDesc(C.Structure):
                 ("inputGamma", C.c_float), ("outputGamma", C.c_float),
                 ("isNormalMap", C.c_int), ("convertToNormalMap", C.c_int), ("normalizeMipmaps", C.c_int),
                 ("heightFactors", C.c_float * 4), ("bumpFrequencyScale", C.c_float * 4),
-                ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int)]
+                ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int),
+                ("bandIndex", C.c_int), ("bandCount", C.c_int)]
 
 
 class KernelStat(C.Structure):
@@ -61,7 +62,7 @@ EXPORTS = [
     "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
-    "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count",
+    "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
 ]
 
 _lib = None
@@ -119,6 +120,7 @@ def lib():
     L.nvttb_process_output_size.argtypes = [C.POINTER(ProcessDesc)]
     L.nvttb_process_output_size.restype = sz
     L.nvttb_process_mip_count.argtypes = [C.POINTER(ProcessDesc)]
+    L.nvttb_process_band_slice.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -135,7 +137,8 @@ def make_encode_desc(fmt, quality, w=0, h=0, alpha_mode=AlphaMode_None, color_we
 def make_process_desc(input_format, w, h, fmt, quality, *, faces=1, wrap=WrapMode_Mirror, mip_filter=MipmapFilter_Box,
                       mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
                       to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
-                      pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), first_face=0, last_face=0):
+                      pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), first_face=0, last_face=0, band_index=0,
+                      band_count=0):
     d = ProcessDesc()
     d.inputFormat, d.width, d.height, d.faceCount = input_format, w, h, faces
     d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
@@ -147,6 +150,7 @@ def make_process_desc(input_format, w, h, fmt, quality, *, faces=1, wrap=WrapMod
     d.alphaMode = alpha_mode
     d.encode = make_encode_desc(fmt, quality, alpha_mode=alpha_mode, color_weights=color_weights, pixel_type=pixel_type)
     d.firstFace, d.lastFace = first_face, last_face
+    d.bandIndex, d.bandCount = band_index, band_count
     return d
 
 

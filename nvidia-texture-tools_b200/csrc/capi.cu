@@ -930,16 +930,49 @@ int nvttb_process_mip_count(const NvttbProcessDesc *d) {
     return count;
 }
 
+// rows [*y0,*y1) of a w x h level that band (b of n) encodes; returns false when the band has nothing in this level
+static bool band_rows(int h, int b, int n, int *y0, int *y1) {
+    const int bh = (h + 3) / 4;
+    if (n <= 1) { *y0 = 0; *y1 = h; return true; }
+    if (bh % n == 0 && (h & 3) == 0) {
+        *y0 = (bh / n) * b * 4;
+        *y1 = (bh / n) * (b + 1) * 4;
+        return true;
+    }
+    *y0 = 0;
+    *y1 = h;
+    return b == 0;  // small / ragged levels: band 0 encodes the whole level
+}
+
 static size_t face_bytes(const NvttbProcessDesc *d) {
     const int mips = nvttb_process_mip_count(d);
     size_t total = 0;
     int w = d->width, h = d->height;
     for (int m = 0; m < mips; m++) {
-        total += nvttb_level_size(d->encode.format, w, h);
+        int y0, y1;
+        if (band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) total += nvttb_level_size(d->encode.format, w, y1 - y0);
         w = w / 2 > 1 ? w / 2 : 1;
         h = h / 2 > 1 ? h / 2 : 1;
     }
     return total;
+}
+
+extern "C" int nvttb_process_band_slice(const NvttbProcessDesc *d, int level, size_t *offset, size_t *bytes) {
+    if (!d || !offset || !bytes || level < 0 || level >= nvttb_process_mip_count(d)) return NVTTB_ERR_INVALID_INPUT;
+    int w = d->width, h = d->height;
+    for (int m = 0; m < level; m++) {
+        w = w / 2 > 1 ? w / 2 : 1;
+        h = h / 2 > 1 ? h / 2 : 1;
+    }
+    int y0, y1;
+    if (!band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) {
+        *offset = 0;
+        *bytes = 0;
+        return NVTTB_OK;
+    }
+    *offset = (size_t)(y0 / 4) * ((w + 3) / 4) * block_bytes(d->encode.format);
+    *bytes = nvttb_level_size(d->encode.format, w, y1 - y0);
+    return NVTTB_OK;
 }
 
 size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
@@ -978,7 +1011,8 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     // b+1 (h2d_stream) runs under the encode of band b (stream) and the D2H copy of band b's blocks (d2h_stream) under
     // everything that follows.  Needs the per-texel-only prologue (fused toLinear or none).
     const size_t bpp = input_bpp(d->inputFormat);
-    const bool banded = loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
+    const bool sharded = d->bandCount > 1;
+    const bool banded = !sharded && loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
     const int bhTotal = (H + 3) / 4;
     const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
     const int bandBlockRows = (bhTotal + nbands - 1) / nbands;
@@ -1068,6 +1102,16 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 if ((rc = gamma_device(ctx, (float *)ctx->tmp_level.p, (size_t)w * h, false, d->outputGamma)) != NVTTB_OK) { cleanup(); return rc; }
                 src = (const float *)ctx->tmp_level.p;
             }
+            if (sharded) {
+                // block-row sharding of one image: every band has the whole fp32 level, each encodes its own rows
+                int y0, y1;
+                if (band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) {
+                    e.height = y1 - y0;
+                    if ((rc = encode_device(ctx, &e, src + (size_t)y0 * w, w, y1 - y0, out, (size_t)w * h)) != NVTTB_OK) { cleanup(); return rc; }
+                    out += nvttb_level_size(e.format, w, y1 - y0);
+                }
+                continue;
+            }
             if (!(m == 0 && level0_done)) {
                 if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
             }
@@ -1091,6 +1135,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
 static int check_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int *f0, int *f1) {
     if (!ctx || !d || !images) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null argument");
     if (d->width <= 0 || d->height <= 0 || d->faceCount <= 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad extent");
+    if (d->bandCount > 1 && (d->bandIndex < 0 || d->bandIndex >= d->bandCount)) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad band index");
     if (!nvttb_format_supported(d->encode.format, d->encode.quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
     *f0 = 0;
     *f1 = d->faceCount;
@@ -1132,8 +1177,9 @@ int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *cons
     for (int f = f0; f < f1; f++) {
         int w = d->width, h = d->height;
         for (int m = 0; m < mips; m++) {
-            const size_t sz = nvttb_level_size(d->encode.format, w, h);
-            if (!emit(user, f, m, w, h, 1, p, sz)) return fail(ctx, NVTTB_ERR_FILE_WRITE, "emit callback asked to stop");
+            size_t sz = nvttb_level_size(d->encode.format, w, h), off = 0;
+            if (d->bandCount > 1) nvttb_process_band_slice(d, m, &off, &sz);
+            if (sz != 0 && !emit(user, f, m, w, h, 1, p, sz)) return fail(ctx, NVTTB_ERR_FILE_WRITE, "emit callback asked to stop");
             p += sz;
             w = w / 2 > 1 ? w / 2 : 1;
             h = h / 2 > 1 ? h / 2 : 1;

@@ -32,3 +32,38 @@ def gather_bytes(mine, dst=0):
     if rank != dst:
         return None
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)]) if sizes else np.zeros(0, np.uint8)
+
+
+def band_layout(lib, desc, world):
+    """Per mip level and band: (offset, bytes) of the band's slice inside the level (nvttb_process_band_slice), for
+    block-row sharding of ONE image over `world` GPUs.  desc.bandCount must equal world."""
+    import ctypes as C
+    import copy
+    mips = lib.nvttb_process_mip_count(C.byref(desc))
+    out = []
+    for m in range(mips):
+        row = []
+        for b in range(world):
+            d = copy.copy(desc)
+            d.bandIndex, d.bandCount = b, world
+            off, n = C.c_size_t(0), C.c_size_t(0)
+            lib.nvttb_process_band_slice(C.byref(d), m, C.byref(off), C.byref(n))
+            row.append((off.value, n.value))
+        out.append(row)
+    return out
+
+
+def assemble_bands(layout, per_band_bytes):
+    """per_band_bytes[b] = the bytes band b produced (its slices of every level, concatenated).  Returns the whole
+    mip chain (levels in order, each level = its band slices in band order) exactly as a single GPU would emit it."""
+    cur = [0] * len(per_band_bytes)
+    levels = []
+    for row in layout:
+        size = max(off + n for off, n in row)
+        lvl = np.zeros(size, np.uint8)
+        for b, (off, n) in enumerate(row):
+            if n:
+                lvl[off:off + n] = per_band_bytes[b][cur[b]:cur[b] + n]
+                cur[b] += n
+        levels.append(lvl)
+    return np.concatenate(levels)

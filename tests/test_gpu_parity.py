@@ -337,3 +337,26 @@ def test_config0_and_config2_full_size_properties(nvtt, ref, ctx):
                 exp = want[off:off + nb * nb * 8].reshape(nb, nb, 8)
                 assert np.array_equal(got, exp), "size %d crop (%d,%d) level %d" % (size, x0, y0, m)
                 off += nb * nb * 8
+
+
+def test_block_row_sharding_of_one_image(nvtt, ref, ctx):
+    """BASELINE configs[2]-style tiling of ONE image over N GPUs, exercised band by band on one GPU: the bands' slices,
+    put back together with the layout contract, must be byte-identical to the single-GPU chain (and to the reference)."""
+    for (w, h, fmt_name, q, kw, world) in ((256, 256, "BC1", 2, dict(mip_filter=0), 8), (128, 64, "BC3", 1, dict(mip_filter=2), 2),
+                                            (100, 60, "BC1", 1, dict(mip_filter=0), 4), (64, 64, "BC7", 1, dict(mip_filter=0), 4)):
+        fmt = getattr(nvtt, "Format_" + fmt_name)
+        img = nvtt.synth.photo_bgra8(w, h, seed=5, alpha=True)
+        whole = ctx.process_bytes([img], nvtt.make_process_desc(0, w, h, fmt, q, **kw))
+        parts = []
+        for b in range(world):
+            d = nvtt.make_process_desc(0, w, h, fmt, q, band_index=b, band_count=world, **kw)
+            parts.append(ctx.process_bytes([img], d))
+        d0 = nvtt.make_process_desc(0, w, h, fmt, q, band_index=0, band_count=world, **kw)
+        layout = nvtt.sharding.band_layout(nvtt.lib(), d0, world)
+        got = nvtt.sharding.assemble_bands(layout, parts)
+        assert np.array_equal(got, whole), (w, h, fmt_name, world)
+        if fmt_name != "BC7":
+            assert np.array_equal(got, ref.process([img], 0, w, h, fmt, q, **kw))
+        # the big levels really are split: no band carries the whole level 0 when it divides
+        if (h // 4) % world == 0 and h % 4 == 0:
+            assert all(n == layout[0][0][1] for _, n in layout[0]) and layout[0][0][1] * world == ((w + 3) // 4) * (h // 4) * (8 if fmt_name == "BC1" else 16)

@@ -41,6 +41,60 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _band_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import nvtt_b200_loader
+    import oracleapi
+    m = nvtt_b200_loader.load()
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    w, h = 64, 32
+    img = m.synth.photo_bgra8(w, h, seed=9, alpha=True)
+    d = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=rank, band_count=world)
+    layout = m.sharding.band_layout(m.lib(), d, world)
+    # stand-in for this rank's GPU encode of its block rows (no GPU here): the oracle's whole chain, cut by the contract
+    whole = oracleapi.process([img], 0, w, h, 1, 1, mip_filter=0)
+    mine, base = [], 0
+    for row in layout:
+        off, n = row[rank]
+        mine.append(whole[base + off:base + off + n])
+        base += max(o + k for o, k in row)
+    mine = np.concatenate(mine) if mine else np.zeros(0, np.uint8)
+    sizes_ok = mine.size == int(m.lib().nvttb_process_output_size(d))
+    allb = m.sharding.gather_bytes(mine, dst=0)
+    if rank == 0:
+        per_band, p = [], 0
+        for b in range(world):
+            db = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=b, band_count=world)
+            n = int(m.lib().nvttb_process_output_size(db))
+            per_band.append(allb[p:p + n])
+            p += n
+        got = m.sharding.assemble_bands(layout, per_band)
+        q.put(bool(sizes_ok and np.array_equal(got, whole)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_block_row_bands():
+    """Block-row sharding of one image (configs[2]): layout contract + gather + re-assembly, world_size 2 on gloo."""
+    import oracleapi
+    if not oracleapi.available():
+        pytest.skip("oracle not built")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok
+    assert all(p.exitcode == 0 for p in procs)
+
+
 def test_face_ranges_cover_everything(nvtt):
     for faces in (1, 6, 7, 64):
         for world in (1, 2, 3, 4, 8):
