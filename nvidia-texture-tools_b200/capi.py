@@ -234,7 +234,8 @@ class Context:
         return out
 
     def process_bytes(self, images, desc, location=HOST):
-        return np.concatenate([b for (_, _, _, _, b) in self.process(images, desc, location)])
+        parts = [b for (_, _, _, _, b) in self.process(images, desc, location)]
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)  # a band may own nothing of a small image
 
     def process_to_device(self, images, desc, d_out_ptr, cap, location=DEVICE):
         ptrs, keep = self._image_ptrs(images, location)

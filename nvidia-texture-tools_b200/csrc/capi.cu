@@ -1154,6 +1154,10 @@ int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *d, const 
     if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t total = face_bytes(d) * (size_t)(f1 - f0);
+    if (total == 0) {
+        if (written) *written = 0;
+        return NVTTB_OK;
+    }
     if (!out_device || out_capacity < total) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
     if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)out_device)) != NVTTB_OK) return rc;
     if (written) *written = total;
@@ -1167,6 +1171,7 @@ int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *cons
     CK(cudaSetDevice(ctx->device));
     const size_t fbytes = face_bytes(d);
     const size_t total = fbytes * (size_t)(f1 - f0);
+    if (total == 0) return NVTTB_OK;  // a band that owns no block row of this (small) image emits nothing
     if ((rc = ensure(ctx, ctx->out_dev, total)) != NVTTB_OK) return rc;
     if ((rc = ensure_pinned(ctx, total)) != NVTTB_OK) return rc;
     if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)ctx->out_dev.p, (unsigned char *)ctx->h_out)) != NVTTB_OK) return rc;
