@@ -7,6 +7,7 @@
 #include "kernels/bc_alpha.cuh"
 #include "kernels/bc3_color.cuh"
 #include "kernels/bc1_icbc.cuh"
+#include "kernels/bc1_quick.cuh"
 #include "kernels/bc6h.cuh"
 #include "kernels/bc7.cuh"
 #include "kernels/image_ops.cuh"
@@ -40,8 +41,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1_icbc", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
@@ -60,6 +61,10 @@ struct NvttbContext {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     enum { MAX_BANDS = 8 };
     cudaEvent_t ev_up[MAX_BANDS] = {}, ev_enc[MAX_BANDS] = {}, ev_stage_free = nullptr, ev_tail = nullptr;
+    // BC7: the eight mode searches of a level are independent until the final select, so each runs on its own stream
+    // (small levels cannot fill 148 SMs with one mode's candidates; together they do)
+    cudaStream_t mode_stream[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
     std::string err;
     uint64_t launches = 0;
     float *d_to_gamma = nullptr, *d_to_linear = nullptr;
@@ -104,7 +109,7 @@ static int fail(NvttbContext *c, int code, const char *what, cudaError_t e = cud
     } while (0)
 
 // Every kernel launch goes through this: counts it and, while profiling, brackets it with CUDA events on the stream.
-#define NVB_LAUNCH(ctx, kid_, units_, KFN, grid, block, ...)                           \
+#define NVB_LAUNCH_ON(ctx, strm_, kid_, units_, KFN, grid, block, ...)                 \
     do {                                                                               \
         ProfRec _r;                                                                    \
         if ((ctx)->profiling) {                                                        \
@@ -112,15 +117,16 @@ static int fail(NvttbContext *c, int code, const char *what, cudaError_t e = cud
             _r.units = (double)(units_);                                               \
             cudaEventCreate(&_r.a);                                                    \
             cudaEventCreate(&_r.b);                                                    \
-            cudaEventRecord(_r.a, (ctx)->stream);                                      \
+            cudaEventRecord(_r.a, (strm_));                                            \
         }                                                                              \
-        KFN<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                       \
+        KFN<<<(grid), (block), 0, (strm_)>>>(__VA_ARGS__);                             \
         if ((ctx)->profiling) {                                                        \
-            cudaEventRecord(_r.b, (ctx)->stream);                                      \
+            cudaEventRecord(_r.b, (strm_));                                            \
             (ctx)->prof.push_back(_r);                                                 \
         }                                                                              \
         (ctx)->launches++;                                                             \
     } while (0)
+#define NVB_LAUNCH(ctx, kid_, units_, KFN, grid, block, ...) NVB_LAUNCH_ON(ctx, (ctx)->stream, kid_, units_, KFN, grid, block, __VA_ARGS__)
 
 static int ensure(NvttbContext *ctx, DevBuf &b, size_t bytes) {
     if (b.cap >= bytes && b.p) return NVTTB_OK;
@@ -190,6 +196,11 @@ int nvttb_context_create(int device, NvttbContext **out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
+    for (int i = 0; i < 8; i++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->mode_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     float tg[512], tl[512];
@@ -269,6 +280,11 @@ void nvttb_context_destroy(NvttbContext *ctx) {
         if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
         if (ctx->ev_enc[i]) cudaEventDestroy(ctx->ev_enc[i]);
     }
+    for (int i = 0; i < 8; i++) {
+        if (ctx->mode_stream[i]) { cudaStreamSynchronize(ctx->mode_stream[i]); cudaStreamDestroy(ctx->mode_stream[i]); }
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_stage_free) cudaEventDestroy(ctx->ev_stage_free);
     if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
     cudaStreamDestroy(ctx->h2d_stream);
@@ -362,9 +378,11 @@ int nvttb_format_supported(int format, int quality) {
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5:
     case F_DXT3:
-        return quality >= Q_Normal && quality <= Q_Highest;
+        return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5n:
-        return quality == Q_Normal || quality == Q_Production;
+        return quality >= Q_Fastest && quality <= Q_Production;
+    case F_DXT1a:
+        return quality == Q_Fastest;
     case F_BC6:
     case F_BC7:
         return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102)
@@ -377,10 +395,14 @@ int nvttb_format_supported(int format, int quality) {
 
 // BC7: rough shape ranking (modes 0,1,2,3,7) + one refine launch per mode + select
 template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, const Bc7Params &P, int nb, double units) {
+    cudaStream_t st = ctx->mode_stream[M];
+    cudaStreamWaitEvent(st, ctx->ev_fork, 0);
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
-        NVB_LAUNCH(ctx, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(nb, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, P);
+        NVB_LAUNCH_ON(ctx, st, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(nb, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, P);
     const unsigned grid = (unsigned)(((size_t)nb * NCAND + 127) / 128);
-    NVB_LAUNCH(ctx, K_BC7_REFINE, units, (k_bc7_refine<M, NCAND>), grid, 128, P);
+    NVB_LAUNCH_ON(ctx, st, K_BC7_REFINE, units, (k_bc7_refine<M, NCAND>), grid, 128, P);
+    cudaEventRecord(ctx->ev_join[M], st);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join[M], 0);
 }
 
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
@@ -438,6 +460,26 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     } else if (d->format == F_BC5) {
         alpha(0, 16, 0, d->quality >= Q_Production);
         alpha(1, 16, 8, d->quality >= Q_Production);
+    } else if (d->format == F_DXT1a || (d->quality == Q_Fastest && (d->format == F_DXT5 || d->format == F_DXT3 || d->format == F_DXT5n))) {
+        // FastCompressorDXT1a / DXT3 / DXT5 / DXT5n (CompressorDX9.cpp:55-81): QuickCompress colour block (+ alpha block)
+        const bool wide = d->format != F_DXT1a;
+        if (d->format == F_DXT5) alpha(3, 16, 0, false);
+        if (d->format == F_DXT5n) alpha(0, 16, 0, false);  // swizzle(4,1,5,0): alpha block = red channel
+        if (d->format == F_DXT3) {
+            AlphaBlocksParams A;
+            A.lv = lv; A.channel = 3; A.out = d_out; A.out_stride = 16; A.out_offset = 0; A.mode = 0;
+            NVB_LAUNCH(ctx, K_ALPHA_DXT3, (double)w * h, k_alpha_dxt3, grid_for(nb, 128), 128, A);
+        }
+        Dxt1QuickParams Q;
+        Q.lv = lv;
+        Q.out = d_out;
+        Q.out_stride = wide ? 16 : 8;
+        Q.out_offset = wide ? 8 : 0;
+        Q.dxt1a = (d->format == F_DXT1a);
+        Q.dxt5n = (d->format == F_DXT5n);
+        Q.omatch5 = ctx->d_om5;
+        Q.omatch6 = ctx->d_om6;
+        NVB_LAUNCH(ctx, K_DXT1_QUICK, (double)w * h, k_dxt1_quick, grid_for(nb, 128), 128, Q);
     } else if (d->format == F_DXT5 || d->format == F_DXT3 || d->format == F_DXT5n) {
         if (d->format == F_DXT5) {
             alpha(3, 16, 0, d->quality == Q_Highest);  // CompressorDX9.cpp:149-157
@@ -498,14 +540,15 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.cand = P.shapes + (size_t)nb * 80;
         P.cand_err = (float *)(P.shapes + (size_t)nb * 208);
         const double units = (double)w * h;
-        launch_bc7_mode<0, 4>(ctx, P, nb, units);
-        launch_bc7_mode<1, 16>(ctx, P, nb, units);
-        launch_bc7_mode<2, 16>(ctx, P, nb, units);
-        launch_bc7_mode<3, 16>(ctx, P, nb, units);
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));  // the level (and the scratch) is ready at this point of ctx->stream
+        launch_bc7_mode<6, 1>(ctx, P, nb, units);        // longest dependent chain per thread first
         launch_bc7_mode<4, 8>(ctx, P, nb, units);
-        launch_bc7_mode<5, 4>(ctx, P, nb, units);
-        launch_bc7_mode<6, 1>(ctx, P, nb, units);
+        launch_bc7_mode<3, 16>(ctx, P, nb, units);
         launch_bc7_mode<7, 16>(ctx, P, nb, units);
+        launch_bc7_mode<1, 16>(ctx, P, nb, units);
+        launch_bc7_mode<0, 4>(ctx, P, nb, units);
+        launch_bc7_mode<2, 16>(ctx, P, nb, units);
+        launch_bc7_mode<5, 4>(ctx, P, nb, units);
         NVB_LAUNCH(ctx, K_BC7_SELECT, units, k_bc7_select, grid_for(nb, 256), 256, P);
     }
     CK(cudaGetLastError());

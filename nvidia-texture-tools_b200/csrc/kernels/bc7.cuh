@@ -276,12 +276,30 @@ template <int M> NVB_DEV float bc7_map_colors(const float (*colors)[4], int np, 
     for (int i = 0; i < np; ++i) {
         float besterr = FLT_MAX;
         int bestj = 0;
-        for (int j = 0; j < C::NIDX && besterr > 0; ++j) {
-            const float err = bc7_metric4(colors[i], pal[j]);
-            if (err > besterr) break;
-            if (err < besterr) {
-                besterr = err;
-                bestj = j;
+        if (C::NIDX <= 8) {
+            // same scan as the reference ("stop at the first increase, or once the error is 0"), written without branches so
+            // that the lanes of a warp — which work on different candidates — stay converged
+            const float c0 = colors[i][0], c1 = colors[i][1], c2 = colors[i][2], c3 = colors[i][3];
+            bool live = true;
+#pragma unroll
+            for (int j = 0; j < C::NIDX; ++j) {
+                const float x = c0 - pal[j][0], y = c1 - pal[j][1], z = c2 - pal[j][2], w = c3 - pal[j][3];
+                const float err = x * x + y * y + z * z + w * w;
+                live = live && (besterr > 0);
+                const bool stop = live && (err > besterr);
+                const bool upd = live && !stop && (err < besterr);
+                besterr = upd ? err : besterr;
+                bestj = upd ? j : bestj;
+                live = live && !stop;
+            }
+        } else {
+            for (int j = 0; j < C::NIDX && besterr > 0; ++j) {
+                const float err = bc7_metric4(colors[i], pal[j]);
+                if (err > besterr) break;
+                if (err < besterr) {
+                    besterr = err;
+                    bestj = j;
+                }
             }
         }
         idx |= (unsigned long long)bestj << (4 * i);

@@ -5,6 +5,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc_alpha.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc3_color.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_icbc.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_quick.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
@@ -128,6 +129,16 @@ void emu_bc7(const float *planar, int w, int h, unsigned char *out, int gamma, i
 }
 
 unsigned emu_half_from_float(unsigned f) { return half_from_float_bits(f); }
+
+void emu_dxt1_quick(const float *planar, int w, int h, int dxt1a, int dxt5n, unsigned char *out, int stride, int offset, int gamma) {
+    init_tables();
+    Dxt1QuickParams Q;
+    Q.lv = make_lv(planar, w, h, gamma);
+    Q.out = out; Q.out_stride = stride; Q.out_offset = offset; Q.dxt1a = dxt1a; Q.dxt5n = dxt5n;
+    Q.omatch5 = g_om5; Q.omatch6 = g_om6;
+    int nb = Q.lv.bw * Q.lv.bh;
+    emu::launch(dim3((nb + 127) / 128), dim3(128), 0, [&] { k_dxt1_quick(Q); });
+}
 
 void emu_set_image(const void *src, float *dst, int count, int format, int to_linear) {
     init_tables();

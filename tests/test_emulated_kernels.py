@@ -46,6 +46,14 @@ def _encode(E, fmt, q, img, am, cw, pt=0):
         out = np.zeros(nb * 16, np.uint8)
         E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 16, 0, 0, int(q >= 2))
         E.emu_alpha_blocks(p, w, h, 1, C.c_void_p(out.ctypes.data), 16, 8, 0, int(q >= 2))
+    elif fmt in (3, 4, 5) and q == 0:
+        out = np.zeros(nb * 16, np.uint8)
+        o = C.c_void_p(out.ctypes.data)
+        if fmt == 3:
+            E.emu_alpha_blocks(p, w, h, 3, o, 16, 0, 0, 2)
+        else:
+            E.emu_alpha_blocks(p, w, h, 3 if fmt == 4 else 0, o, 16, 0, 0, 0)
+        E.emu_dxt1_quick(p, w, h, 0, int(fmt == 5), o, 16, 8, 0)
     elif fmt == 3:
         out = np.zeros(nb * 16, np.uint8)
         E.emu_alpha_blocks(p, w, h, 3, C.c_void_p(out.ctypes.data), 16, 0, 0, 2)
