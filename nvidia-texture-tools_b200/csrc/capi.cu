@@ -41,8 +41,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_REFINE, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_refine", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
@@ -71,6 +71,9 @@ struct NvttbContext {
     unsigned short *d_cand = nullptr;
     int *d_cand_off = nullptr;
     unsigned char *d_om5 = nullptr, *d_om6 = nullptr;
+    unsigned char *d_om5a = nullptr, *d_om6a = nullptr;  // OMatchAlpha5/6
+    unsigned short *d_cand3 = nullptr;
+    int *d_cand3_off = nullptr;
     // ICBC tables: [four splits | three splits] u16, [four_total | three_total] int, [mid5 | mid6] float, [match5 | match6] u8
     unsigned short *d_icbc_splits = nullptr;
     int *d_icbc_totals = nullptr;
@@ -211,6 +214,22 @@ int nvttb_context_create(int device, NvttbContext **out) {
     uint8_t om5[512], om6[512];
     build_omatch(om5, 32);
     build_omatch(om6, 64);
+    {
+        std::vector<uint16_t> cand3;
+        int off3[18];
+        build_squish_splits3(cand3, off3);
+        uint8_t om5a[512], om6a[512];
+        build_omatch(om5a, 32, true);
+        build_omatch(om6a, 64, true);
+        if ((e = cudaMalloc(&ctx->d_cand3, cand3.size() * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_cand3_off, sizeof(off3))) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_om5a, 512)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&ctx->d_om6a, 512)) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemcpy(ctx->d_cand3, cand3.data(), cand3.size() * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_cand3_off, off3, sizeof(off3), cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_om5a, om5a, 512, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_om6a, om6a, 512, cudaMemcpyHostToDevice);
+    }
     if ((e = cudaMalloc(&ctx->d_to_gamma, sizeof(tg))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_to_linear, sizeof(tl))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_cand, cand.size() * 2)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -260,6 +279,10 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     cudaFree(ctx->d_cand_off);
     cudaFree(ctx->d_om5);
     cudaFree(ctx->d_om6);
+    cudaFree(ctx->d_om5a);
+    cudaFree(ctx->d_om6a);
+    cudaFree(ctx->d_cand3);
+    cudaFree(ctx->d_cand3_off);
     cudaFree(ctx->d_icbc_splits);
     cudaFree(ctx->d_icbc_totals);
     cudaFree(ctx->d_icbc_mid);
@@ -382,7 +405,7 @@ int nvttb_format_supported(int format, int quality) {
     case F_DXT5n:
         return quality >= Q_Fastest && quality <= Q_Production;
     case F_DXT1a:
-        return quality == Q_Fastest;
+        return quality >= Q_Fastest && quality <= Q_Highest;
     case F_BC6:
     case F_BC7:
         return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102)
@@ -460,6 +483,27 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     } else if (d->format == F_BC5) {
         alpha(0, 16, 0, d->quality >= Q_Production);
         alpha(1, 16, 8, d->quality >= Q_Production);
+    } else if (d->format == F_DXT1a && d->quality != Q_Fastest) {
+        // CompressorDXT1a (CompressorDX9.cpp:83-111): squish weighted cluster fit in DXT1 mode (3-colour, then 4-colour when opaque)
+        Bc3ColorParams P;
+        P.lv = lv;
+        P.out = d_out;
+        P.out_stride = 8;
+        P.out_offset = 0;
+        P.dxt5n = 0;
+        P.metric[0] = d->colorWeights[0];
+        P.metric[1] = d->colorWeights[1];
+        P.metric[2] = d->colorWeights[2];
+        P.weight_by_alpha = (d->alphaMode == AM_Transparency);
+        P.cand = ctx->d_cand;
+        P.cand_off = ctx->d_cand_off;
+        P.omatch5 = ctx->d_om5;
+        P.omatch6 = ctx->d_om6;
+        P.cand3 = ctx->d_cand3;
+        P.cand3_off = ctx->d_cand3_off;
+        P.omatch5a = ctx->d_om5a;
+        P.omatch6a = ctx->d_om6a;
+        NVB_LAUNCH(ctx, K_BC1A_COLOR, (double)w * h, k_bc1a_color, (nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, P);
     } else if (d->format == F_DXT1a || (d->quality == Q_Fastest && (d->format == F_DXT5 || d->format == F_DXT3 || d->format == F_DXT5n))) {
         // FastCompressorDXT1a / DXT3 / DXT5 / DXT5n (CompressorDX9.cpp:55-81): QuickCompress colour block (+ alpha block)
         const bool wide = d->format != F_DXT1a;
@@ -509,6 +553,10 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.cand_off = ctx->d_cand_off;
         P.omatch5 = ctx->d_om5;
         P.omatch6 = ctx->d_om6;
+        P.cand3 = nullptr;
+        P.cand3_off = nullptr;
+        P.omatch5a = nullptr;
+        P.omatch6a = nullptr;
         NVB_LAUNCH(ctx, K_BC3_COLOR, (double)w * h, k_bc3_color, (nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, P);
     }
     else if (d->format == F_BC6) {

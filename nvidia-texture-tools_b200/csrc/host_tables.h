@@ -40,10 +40,23 @@ inline void build_squish_splits(std::vector<uint16_t> &cand, int off[18]) {
     off[17] = (int)cand.size();
 }
 
+// Two-cluster splits of WeightedClusterFit::Compress3 (weightedclusterfit.cpp:391-446): (c0,c1), c0+c1 <= n, packed c0|c1<<5.
+inline void build_squish_splits3(std::vector<uint16_t> &cand, int off[18]) {
+    cand.clear();
+    off[0] = 0;
+    for (int n = 1; n <= 16; n++) {
+        off[n] = (int)cand.size();
+        for (int c0 = 0; c0 <= n; c0++)
+            for (int c1 = 0; c1 <= n - c0; c1++) cand.push_back((uint16_t)(c0 | (c1 << 5)));
+    }
+    off[17] = (int)cand.size();
+}
+
 // ---- single-colour endpoint match tables (src/nvtt/SingleColorLookup.cpp:34-89, non-alpha mode) ------------
 // For every 8-bit value find (max,min) 5/6-bit endpoints whose 2/3-1/3 interpolant is closest, with a small
 // penalty on the endpoint distance; first best in (min,max) scan order wins.
-inline void build_omatch(uint8_t *table /*[256][2]*/, int size) {
+// alpha_mode (OMatchAlpha5/6, used by the 3-colour single-colour block of BC1a): the interpolant is the midpoint.
+inline void build_omatch(uint8_t *table /*[256][2]*/, int size, bool alpha_mode = false) {
     std::vector<int> expand(size);
     for (int i = 0; i < size; i++) expand[i] = (size == 32) ? ((i << 3) | (i >> 2)) : ((i << 2) | (i >> 4));
     for (int i = 0; i < 256; i++) {
@@ -51,7 +64,7 @@ inline void build_omatch(uint8_t *table /*[256][2]*/, int size) {
         for (int mn = 0; mn < size; mn++) {
             for (int mx = 0; mx < size; mx++) {
                 const int mine = expand[mn], maxe = expand[mx];
-                int err = abs((maxe * 2 + mine) / 3 - i) * 100;
+                int err = (alpha_mode ? abs((maxe + mine) / 2 - i) : abs((maxe * 2 + mine) / 3 - i)) * 100;
                 err += abs(mx - mn) * 3;
                 if (err < bestErr) {
                     table[i * 2 + 0] = (uint8_t)mx;

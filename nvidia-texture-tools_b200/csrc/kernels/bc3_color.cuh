@@ -32,6 +32,11 @@ struct Bc3ColorParams {
     const unsigned char *omatch5;  // [256][2]
     const unsigned char *omatch6;  // [256][2]
     int dxt5n;              // 1: CompressorDXT5n colour block — tile swizzled to (0xFF, G, 0) and metric (0,1,0) (CompressorDX9.cpp:179-210)
+    // BC1a (CompressorDXT1a, CompressorDX9.cpp:83-111) only: two-cluster splits c0|c1<<5 and the alpha-mode match tables
+    const unsigned short *cand3;
+    const int *cand3_off;
+    const unsigned char *omatch5a;  // OMatchAlpha5 [256][2]
+    const unsigned char *omatch6a;  // OMatchAlpha6 [256][2]
 };
 
 #define NVB_BC3_GROUPS 8  // 4x4 blocks per CTA (128 threads)
@@ -93,7 +98,49 @@ NVB_DEV SquishSplit squish_eval_split(const float4 *T, int n, int c0, int c1, in
     return r;
 }
 
-__global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParams P) {
+// WeightedClusterFit::Compress3 (weightedclusterfit.cpp:370-472): clusters at 0, 1/2, 1
+NVB_DEV SquishSplit squish_eval_split3(const float4 *T, int n, int c0, int c1, float4 xsum, float mx, float my, float mz) {
+    const float4 x0 = T[c0];
+    const float4 x1 = T[c0 * (n + 1) - ((c0 * (c0 - 1)) >> 1) + c1];
+    const float w0 = x0.w, w1 = x1.w;
+    const float w2 = xsum.w - w0 - w1;
+    const float alpha2_sum = w0 + w1 * 0.25f;
+    const float beta2_sum = w2 + w1 * 0.25f;
+    const float alphabeta_sum = w1 * 0.25f;
+    const float factor = 1.0f / (alpha2_sum * beta2_sum - alphabeta_sum * alphabeta_sum);
+    SquishSplit r;
+    float e[3];
+    const float X0[3] = {x0.x, x0.y, x0.z}, X1[3] = {x1.x, x1.y, x1.z};
+    const float XS[3] = {xsum.x, xsum.y, xsum.z};
+    const float grid[3] = {31.0f, 63.0f, 31.0f};
+    const float gridrcp[3] = {1.0f / 31.0f, 1.0f / 63.0f, 1.0f / 31.0f};
+    float A[3], B[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float alphax_sum = X0[k] + X1[k] * 0.5f;
+        const float betax_sum = XS[k] - alphax_sum;
+        float a = (alphax_sum * beta2_sum - betax_sum * alphabeta_sum) * factor;
+        float b = (betax_sum * alpha2_sum - alphax_sum * alphabeta_sum) * factor;
+        a = std_min(1.0f, std_max(0.0f, a));
+        b = std_min(1.0f, std_max(0.0f, b));
+        a = floorf(grid[k] * a + 0.5f) * gridrcp[k];
+        b = floorf(grid[k] * b + 0.5f) * gridrcp[k];
+        e[k] = a * a * alpha2_sum + b * b * beta2_sum + 2.0f * (a * b * alphabeta_sum - a * alphax_sum - b * betax_sum);
+        A[k] = a;
+        B[k] = b;
+    }
+    r.error = e[0] * mx + e[1] * my + e[2] * mz;
+    r.ax = A[0]; r.ay = A[1]; r.az = A[2];
+    r.bx = B[0]; r.by = B[1]; r.bz = B[2];
+    return r;
+}
+
+NVB_DEV unsigned squish_to_565(float x, float y, float z) {
+    return ((unsigned)squish_float_to_int(31.0f * x, 31) << 11) | ((unsigned)squish_float_to_int(63.0f * y, 63) << 5) |
+           (unsigned)squish_float_to_int(31.0f * z, 31);
+}
+
+template <bool DXT1A> NVB_DEV void bc3_color_body(const Bc3ColorParams &P) {
     __shared__ Bc3GroupSmem smem[NVB_BC3_GROUPS];
     const int grp = threadIdx.x >> 4;
     const int l = threadIdx.x & 15;
@@ -114,11 +161,15 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
         b8 = quantize_u8_trunc(load_texel(P.lv, 2, px, py));
     }
     float walpha = 1.0f;
-    if (P.weight_by_alpha) {
-        const unsigned a8 = quantize_u8_trunc(load_texel(P.lv, 3, px, py));
-        walpha = (float)(a8 + 1) / 256.0f;
+    unsigned a8 = 255;
+    if (P.weight_by_alpha || DXT1A) {
+        a8 = quantize_u8_trunc(load_texel(P.lv, 3, px, py));
+        if (P.weight_by_alpha) walpha = (float)(a8 + 1) / 256.0f;
     }
     const unsigned key = (r8 << 16) | (g8 << 8) | b8;
+    // kDxt1: texels with alpha 0 are left out of the colour set (m_remap = -1) and get index 3 (colourset.cpp:49-55,141-152)
+    const bool opaque = !(DXT1A && a8 == 0);
+    const unsigned transparent_mask = DXT1A ? ((__ballot_sync(gm, !opaque) >> (threadIdx.x & 16)) & 0xFFFFu) : 0u;
 
     // ---- minimal colour set: first occurrence keeps the point, duplicates add their weight in texel order ----
     unsigned match = 0;
@@ -127,19 +178,54 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
     for (int j = 0; j < 16; j++) {
         const unsigned kj = __shfl_sync(gm, key, j, 16);
         const float wj = __shfl_sync(gm, walpha, j, 16);
-        if (kj == key) {
+        if (kj == key && opaque && !((transparent_mask >> j) & 1)) {
             weight = (match == 0) ? wj : weight + wj;
             match |= 1u << j;
         }
     }
-    const int first = __ffs((int)match) - 1;
+    const int first = __ffs((int)match) - 1;  // -1 for a transparent texel
     const unsigned uniq = (__ballot_sync(gm, first == l) >> (threadIdx.x & 16)) & 0xFFFFu;
     const int n = __popc(uniq);
-    const int myPoint = __popc(uniq & ((1u << first) - 1u));  // m_remap[l]
+    const int myPoint = (first >= 0) ? __popc(uniq & ((1u << first) - 1u)) : 0;  // m_remap[l]
 
     unsigned char *dst = P.out + (size_t)blk * P.out_stride + P.out_offset;
 
-    if (n == 1) {
+    if (DXT1A) {
+        // CompressorDXT1a: rgba.isSingleColor() looks at the RGB of all 16 texels, transparent ones included
+        const unsigned key0 = __shfl_sync(gm, key, 0, 16);
+        const bool single = ((__ballot_sync(gm, key != key0) >> (threadIdx.x & 16)) & 0xFFFFu) == 0u;
+        if (single) {
+            if (l == 0) {
+                unsigned c0, c1, indices = 0xaaaaaaaau;
+                if (transparent_mask == 0) {  // OptimalCompress::compressDXT1
+                    c0 = ((unsigned)P.omatch5[r8 * 2 + 0] << 11) | ((unsigned)P.omatch6[g8 * 2 + 0] << 5) | P.omatch5[b8 * 2 + 0];
+                    c1 = ((unsigned)P.omatch5[r8 * 2 + 1] << 11) | ((unsigned)P.omatch6[g8 * 2 + 1] << 5) | P.omatch5[b8 * 2 + 1];
+                    if (c0 < c1) {
+                        unsigned t = c0; c0 = c1; c1 = t;
+                        indices ^= 0x55555555u;
+                    }
+                } else {  // OptimalCompress::compressDXT1a: 3-colour mode, midpoint tables, index 3 where alpha is 0
+                    c0 = ((unsigned)P.omatch5a[r8 * 2 + 0] << 11) | ((unsigned)P.omatch6a[g8 * 2 + 0] << 5) | P.omatch5a[b8 * 2 + 0];
+                    c1 = ((unsigned)P.omatch5a[r8 * 2 + 1] << 11) | ((unsigned)P.omatch6a[g8 * 2 + 1] << 5) | P.omatch5a[b8 * 2 + 1];
+                    if (c0 > c1) {
+                        unsigned t = c0; c0 = c1; c1 = t;
+                    }
+                    unsigned am = 0;
+                    for (int i = 0; i < 16; i++)
+                        if ((transparent_mask >> i) & 1) am |= 3u << (2 * i);
+                    indices |= am;
+                }
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(c0 | (c1 << 16), indices);
+            }
+            return;
+        }
+        if (n == 0) {
+            // every texel transparent (but not all the same RGB): the one split of an empty set has error 0 with both endpoints 0
+            if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(0u, 0xFFFFFFFFu);
+            return;
+        }
+    }
+    if (!DXT1A && n == 1) {
         // single colour: optimal endpoints from the match tables, all indices 2.
         if (l == 0 && P.dxt5n) {
             // OptimalCompress::compressDXT1G(uint8 g): red 31, blue 0, green from the 6-bit match table
@@ -164,7 +250,7 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
         return;
     }
 
-    if (first == l) S.pts[myPoint] = make_float4((float)r8 / 255.0f, (float)g8 / 255.0f, (float)b8 / 255.0f, weight);
+    if (first == l && first >= 0) S.pts[myPoint] = make_float4((float)r8 / 255.0f, (float)g8 / 255.0f, (float)b8 / 255.0f, weight);
     __syncwarp(gm);
 
     // ---- weighted covariance about the weighted centroid (every lane, reference order) ----
@@ -251,9 +337,32 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
     // ---- all cluster splits, striped over the 16 lanes ----
     const float mqx = mx * mx, mqy = my * my, mqz = mz * mz;
     const int cbeg = P.cand_off[n], ncand = P.cand_off[n + 1] - cbeg;
+    float besterror3 = FLT_MAX;
+    int bestci3 = 0x7fffffff;
+    if (DXT1A) {
+        const int c3beg = P.cand3_off[n], n3 = P.cand3_off[n + 1] - c3beg;
+        for (int ci = l; ci < n3; ci += 16) {
+            const unsigned pk = __ldg(P.cand3 + c3beg + ci);
+            const SquishSplit s = squish_eval_split3(S.T, n, pk & 31, (pk >> 5) & 31, xsum, mqx, mqy, mqz);
+            if (s.error < besterror3) {
+                besterror3 = s.error;
+                bestci3 = ci;
+            }
+        }
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) {
+            const float oe = __shfl_xor_sync(gm, besterror3, d, 16);
+            const int oc = __shfl_xor_sync(gm, bestci3, d, 16);
+            if (oe < besterror3 || (oe == besterror3 && oc < bestci3)) {
+                besterror3 = oe;
+                bestci3 = oc;
+            }
+        }
+    }
     float besterror = FLT_MAX;
     int bestci = 0x7fffffff;
-    for (int ci = l; ci < ncand; ci += 16) {
+    const bool try4 = !DXT1A || transparent_mask == 0;  // ColourFit::Compress: Compress4 only when nothing is transparent
+    for (int ci = l; try4 && ci < ncand; ci += 16) {
         const unsigned pk = __ldg(P.cand + cbeg + ci);
         const SquishSplit s = squish_eval_split(S.T, n, pk & 31, (pk >> 5) & 31, (pk >> 10) & 31, xsum, mqx, mqy, mqz);
         if (s.error < besterror) {
@@ -271,7 +380,23 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
         }
     }
     unsigned c565a = 0, c565b = 0, idx = 0;
-    if (bestci != 0x7fffffff) {
+    // Compress4 replaces the 3-colour result only when strictly better (m_besterror carries over, weightedclusterfit.cpp:555)
+    if (DXT1A && bestci3 != 0x7fffffff && !(bestci != 0x7fffffff && besterror < besterror3)) {
+        const unsigned pk = __ldg(P.cand3 + P.cand3_off[n] + bestci3);
+        const int b0 = pk & 31, b1 = (pk >> 5) & 31;
+        const SquishSplit s = squish_eval_split3(S.T, n, b0, b1, xsum, mqx, mqy, mqz);
+        if (first >= 0) {
+            const int pos = S.rank[myPoint];
+            idx = (pos < b0) ? 0u : (pos < b0 + b1) ? 2u : 1u;
+        }
+        c565a = squish_to_565(s.ax, s.ay, s.az);
+        c565b = squish_to_565(s.bx, s.by, s.bz);
+        if (c565a > c565b) {  // WriteColourBlock3: a <= b keeps the indices, otherwise swap and exchange 0 <-> 1
+            const unsigned t = c565a; c565a = c565b; c565b = t;
+            idx = (idx == 0) ? 1u : (idx == 1) ? 0u : idx;
+        }
+        if (first < 0) idx = 3;
+    } else if (bestci != 0x7fffffff) {
         const unsigned pk = __ldg(P.cand + cbeg + bestci);
         const int b0 = pk & 31, b1 = (pk >> 5) & 31, b2 = (pk >> 10) & 31;
         const SquishSplit s = squish_eval_split(S.T, n, b0, b1, b2, xsum, mqx, mqy, mqz);
@@ -293,5 +418,9 @@ __global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParam
     for (int d = 8; d >= 1; d >>= 1) bits |= __shfl_xor_sync(gm, bits, d, 16);
     if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(c565a | (c565b << 16), bits);
 }
+
+__global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc3_color(Bc3ColorParams P) { bc3_color_body<false>(P); }
+// BC1a (Normal and above): 3-colour + 4-colour weighted cluster fit with punch-through alpha
+__global__ void __launch_bounds__(NVB_BC3_GROUPS * 16) k_bc1a_color(Bc3ColorParams P) { bc3_color_body<true>(P); }
 
 }  // namespace nvb

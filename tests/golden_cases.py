@@ -26,7 +26,7 @@ def level_cases():
     c = {}
     for kind in ("photo", "adv", "dark"):
         for (w, h) in ((48, 40), (13, 7)):
-            for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (0, 1, 2, 3)), (6, "bc4", (0, 1, 2)), (7, "bc5", (0, 1, 2)), (3, "bc2", (0, 1)), (5, "bc3n", (0, 1))):
+            for fmt, name, qs in ((1, "bc1", (0, 1, 2, 3)), (4, "bc3", (0, 1, 2, 3)), (6, "bc4", (0, 1, 2)), (7, "bc5", (0, 1, 2)), (3, "bc2", (0, 1)), (5, "bc3n", (0, 1)), (2, "bc1a", (1,))):
                 for q in qs:
                     c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1), 0)
     # BC6H: quality is ignored; pixel type 5 = UnsignedFloat, 4 = Float (signed).

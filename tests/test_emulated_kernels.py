@@ -46,6 +46,9 @@ def _encode(E, fmt, q, img, am, cw, pt=0):
         out = np.zeros(nb * 16, np.uint8)
         E.emu_alpha_blocks(p, w, h, 0, C.c_void_p(out.ctypes.data), 16, 0, 0, int(q >= 2))
         E.emu_alpha_blocks(p, w, h, 1, C.c_void_p(out.ctypes.data), 16, 8, 0, int(q >= 2))
+    elif fmt == 2:
+        out = np.zeros(nb * 8, np.uint8)
+        E.emu_bc3_color_ex(p, w, h, (C.c_float * 3)(*cw[:3]), int(am == 1), C.c_void_p(out.ctypes.data), 8, 0, 0, 2)
     elif fmt in (3, 4, 5) and q == 0:
         out = np.zeros(nb * 16, np.uint8)
         o = C.c_void_p(out.ctypes.data)

@@ -113,6 +113,22 @@ def test_bc1a_fastest_bit_exact_where_the_reference_is_defined(nvtt, ref, ctx):
             assert np.array_equal(got[defined], want[defined]), "BC1a fastest %s %dx%d" % (name, w, h)
 
 
+def test_bc1a_cluster_fit_bit_exact(nvtt, ref, ctx):
+    """BC1a Normal/Production (squish cluster fit in DXT1 mode): punch-through texels, all-transparent blocks, single colours
+    with holes, colour weights and alpha weighting."""
+    rng = np.random.default_rng(4)
+    extra = []
+    img = np.zeros((4, 16, 16), np.float32); img[:3] = rng.random((3, 16, 16)); extra.append(("alltransp", img))
+    img = np.full((4, 16, 16), 0.5, np.float32); img[3] = (rng.random((16, 16)) > 0.5); extra.append(("singleholes", img))
+    img = np.full((4, 16, 16), 0.25, np.float32); img[0, :, ::2] = 0.75; img[3] = (rng.random((16, 16)) > 0.3); extra.append(("twoholes", img))
+    for (w, h) in SIZES:
+        for name, img in list(_images(nvtt, w, h)) + (extra if (w, h) == SIZES[0] else []):
+            for q, am, cw in ((1, 0, (1, 1, 1, 1)), (2, 1, (0.3, 0.59, 0.11, 1.0))):
+                got = ctx.encode_level(nvtt.Format_DXT1a, q, img, alpha_mode=am, color_weights=cw)
+                want = ref.compress_level(ref.Format_DXT1a, q, img, alpha_mode=am, color_weights=cw)
+                _assert_blocks_equal(got, want, 8, "BC1a q%d %s %dx%d" % (q, name, w, h))
+
+
 def test_bc3_weights_and_transparency(nvtt, ref, ctx):
     img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(256, 256, seed=3, alpha=True))
     for cw in [(1, 1, 1, 1), (0.3, 0.59, 0.11, 1.0), (1, 0, 0, 1)]:

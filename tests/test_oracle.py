@@ -30,7 +30,7 @@ def _sha(a):
 
 def test_oracle_levels_match_golden(orc, golden):
     for key, (kind, w, h, fmt, q, am, cw, pt) in G.level_cases().items():
-        if fmt in (3, 5, 10, 11) or (fmt == 4 and q == 0):
+        if fmt in (2, 3, 5, 10, 11) or (fmt == 4 and q == 0):
             continue  # BC2 / BC3n / BC6H / BC7 are checked against the compiled reference itself (oracle/_ref), not restated in oracle.c
         img = G.make_input(kind, w, h, planar=True)
         got = orc.compress_level(fmt, q, img, am, cw)
