@@ -72,6 +72,7 @@ struct NvttbContext {
     int *d_cand_off = nullptr;
     unsigned char *d_om5 = nullptr, *d_om6 = nullptr;
     unsigned char *d_om5a = nullptr, *d_om6a = nullptr;  // OMatchAlpha5/6
+    unsigned *d_cand_idx = nullptr;
     unsigned short *d_cand3 = nullptr;
     int *d_cand3_off = nullptr;
     // ICBC tables: [four splits | three splits] u16, [four_total | three_total] int, [mid5 | mid6] float, [match5 | match6] u8
@@ -215,6 +216,10 @@ int nvttb_context_create(int device, NvttbContext **out) {
     build_omatch(om5, 32);
     build_omatch(om6, 64);
     {
+        std::vector<uint32_t> cidx;
+        build_squish_split_indices(cidx);
+        if ((e = cudaMalloc(&ctx->d_cand_idx, cidx.size() * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemcpy(ctx->d_cand_idx, cidx.data(), cidx.size() * 4, cudaMemcpyHostToDevice);
         std::vector<uint16_t> cand3;
         int off3[18];
         build_squish_splits3(cand3, off3);
@@ -282,6 +287,7 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     cudaFree(ctx->d_om5a);
     cudaFree(ctx->d_om6a);
     cudaFree(ctx->d_cand3);
+    cudaFree(ctx->d_cand_idx);
     cudaFree(ctx->d_cand3_off);
     cudaFree(ctx->d_icbc_splits);
     cudaFree(ctx->d_icbc_totals);
@@ -496,6 +502,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.metric[2] = d->colorWeights[2];
         P.weight_by_alpha = (d->alphaMode == AM_Transparency);
         P.cand = ctx->d_cand;
+        P.cand_idx = ctx->d_cand_idx;
         P.cand_off = ctx->d_cand_off;
         P.omatch5 = ctx->d_om5;
         P.omatch6 = ctx->d_om6;
@@ -550,6 +557,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.metric[2] = P.dxt5n ? 0.0f : d->colorWeights[2];
         P.weight_by_alpha = (d->alphaMode == AM_Transparency);
         P.cand = ctx->d_cand;
+        P.cand_idx = ctx->d_cand_idx;
         P.cand_off = ctx->d_cand_off;
         P.omatch5 = ctx->d_om5;
         P.omatch6 = ctx->d_om6;

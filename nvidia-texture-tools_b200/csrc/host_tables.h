@@ -40,6 +40,19 @@ inline void build_squish_splits(std::vector<uint16_t> &cand, int off[18]) {
     off[17] = (int)cand.size();
 }
 
+// Same splits, as positions in the kernel's running-sum table T (row s of T starts at off(s) = s*(n+1) - s*(s-1)/2 and
+// holds the sums of 0..n-s consecutive sorted points starting at point s): i0 | i1<<8 | i2<<16.
+inline void build_squish_split_indices(std::vector<uint32_t> &idx) {
+    idx.clear();
+    for (int n = 1; n <= 16; n++) {
+        auto off = [n](int s) { return s * (n + 1) - (s * (s - 1)) / 2; };
+        for (int c0 = 0; c0 <= n; c0++)
+            for (int c1 = 0; c1 <= n - c0; c1++)
+                for (int c2 = 0; c2 <= n - c0 - c1; c2++)
+                    idx.push_back((uint32_t)(c0 | ((off(c0) + c1) << 8) | ((off(c0 + c1) + c2) << 16)));
+    }
+}
+
 // Two-cluster splits of WeightedClusterFit::Compress3 (weightedclusterfit.cpp:391-446): (c0,c1), c0+c1 <= n, packed c0|c1<<5.
 inline void build_squish_splits3(std::vector<uint16_t> &cand, int off[18]) {
     cand.clear();

@@ -28,6 +28,7 @@ struct Bc3ColorParams {
     float metric[3];        // CompressionOptions colour weights
     int weight_by_alpha;    // AlphaMode_Transparency => kWeightColourByAlpha
     const unsigned short *cand;  // packed (c0 | c1<<5 | c2<<10) splits, all counts concatenated
+    const unsigned *cand_idx;    // same order: positions of the split's three running sums in T, i0 | i1<<8 | i2<<16
     const int *cand_off;    // cand_off[n] .. cand_off[n+1] = splits for a set of n points (n = 1..16), 18 ints
     const unsigned char *omatch5;  // [256][2]
     const unsigned char *omatch6;  // [256][2]
@@ -59,12 +60,12 @@ struct SquishSplit {
     float ax, ay, az, bx, by, bz, error;
 };
 
-NVB_DEV SquishSplit squish_eval_split(const float4 *T, int n, int c0, int c1, int c2, float4 xsum, float mx, float my, float mz) {
-    // rows of T start at off(s) = s*(n+1) - s*(s-1)/2
-    const int s1 = c0, s2 = c0 + c1;
-    const float4 x0 = T[c0];
-    const float4 x1 = T[s1 * (n + 1) - ((s1 * (s1 - 1)) >> 1) + c1];
-    const float4 x2 = T[s2 * (n + 1) - ((s2 * (s2 - 1)) >> 1) + c2];
+// i0, i1, i2 = positions in T of the three running sums of the split (c0, c1, c2):
+//   i0 = c0, i1 = off(c0) + c1, i2 = off(c0 + c1) + c2 with off(s) = s*(n+1) - s*(s-1)/2 (start of row s of T)
+NVB_DEV SquishSplit squish_eval_split(const float4 *T, int i0, int i1, int i2, float4 xsum, float mx, float my, float mz) {
+    const float4 x0 = T[i0];
+    const float4 x1 = T[i1];
+    const float4 x2 = T[i2];
     const float w0 = x0.w, w1 = x1.w, w2 = x2.w;
     const float w3 = xsum.w - w0 - w1 - w2;
     const float alpha2_sum = w0 + w1 * (4.0f / 9.0f) + w2 * (1.0f / 9.0f);
@@ -96,6 +97,45 @@ NVB_DEV SquishSplit squish_eval_split(const float4 *T, int n, int c0, int c1, in
     r.ax = A[0]; r.ay = A[1]; r.az = A[2];
     r.bx = B[0]; r.by = B[1]; r.bz = B[2];
     return r;
+}
+
+// Two splits at once: every quantity of squish_eval_split is carried as a (split A, split B) pair so that the
+// multiplications issue as FMUL2 and the product-free additions as FADD2.  Operation for operation the same arithmetic
+// as squish_eval_split (each lane of a pair is an independent IEEE round-to-nearest op), only the errors are returned.
+NVB_DEV float2 squish_eval_pair(const float4 *T, unsigned pa, unsigned pb, float4 xsum, float mx, float my, float mz) {
+    const float4 a0 = T[pa & 0xFF], a1 = T[(pa >> 8) & 0xFF], a2 = T[pa >> 16];
+    const float4 b0 = T[pb & 0xFF], b1 = T[(pb >> 8) & 0xFF], b2 = T[pb >> 16];
+    const float2 w0 = make_float2(a0.w, b0.w), w1 = make_float2(a1.w, b1.w), w2 = make_float2(a2.w, b2.w);
+    const float2 w3 = f2sub(f2sub(f2sub(f2splat(xsum.w), w0), w1), w2);
+    const float2 c49 = f2splat(4.0f / 9.0f), c19 = f2splat(1.0f / 9.0f), c29 = f2splat(2.0f / 9.0f);
+    const float2 alpha2 = f2add_s(f2add_s(w0, f2mul(w1, c49)), f2mul(w2, c19));
+    const float2 beta2 = f2add_s(f2add_s(w3, f2mul(w2, c49)), f2mul(w1, c19));
+    const float2 ab = f2mul(f2add(w1, w2), c29);
+    const float2 det = f2sub_s(f2mul(alpha2, beta2), f2mul(ab, ab));
+    const float2 factor = make_float2(1.0f / det.x, 1.0f / det.y);
+    const float2 c23 = f2splat(2.0f / 3.0f), c13 = f2splat(1.0f / 3.0f);
+    float2 e[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float2 X0 = (k == 0) ? make_float2(a0.x, b0.x) : (k == 1) ? make_float2(a0.y, b0.y) : make_float2(a0.z, b0.z);
+        const float2 X1 = (k == 0) ? make_float2(a1.x, b1.x) : (k == 1) ? make_float2(a1.y, b1.y) : make_float2(a1.z, b1.z);
+        const float2 X2 = (k == 0) ? make_float2(a2.x, b2.x) : (k == 1) ? make_float2(a2.y, b2.y) : make_float2(a2.z, b2.z);
+        const float xs = (k == 0) ? xsum.x : (k == 1) ? xsum.y : xsum.z;
+        const float g = (k == 1) ? 63.0f : 31.0f, gr = (k == 1) ? (1.0f / 63.0f) : (1.0f / 31.0f);
+        const float2 alphax = f2add_s(f2add_s(X0, f2mul(X1, c23)), f2mul(X2, c13));
+        const float2 betax = f2sub(f2splat(xs), alphax);
+        const float2 an = f2mul(f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab)), factor);
+        const float2 bn = f2mul(f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab)), factor);
+        float2 a = make_float2(std_min(1.0f, std_max(0.0f, an.x)), std_min(1.0f, std_max(0.0f, an.y)));
+        float2 b = make_float2(std_min(1.0f, std_max(0.0f, bn.x)), std_min(1.0f, std_max(0.0f, bn.y)));
+        const float2 ga = f2mul(f2splat(g), a), gb = f2mul(f2splat(g), b);
+        a = f2mul(make_float2(floorf(__fadd_rn(ga.x, 0.5f)), floorf(__fadd_rn(ga.y, 0.5f))), f2splat(gr));
+        b = f2mul(make_float2(floorf(__fadd_rn(gb.x, 0.5f)), floorf(__fadd_rn(gb.y, 0.5f))), f2splat(gr));
+        const float2 s1 = f2add_s(f2mul(f2mul(a, a), alpha2), f2mul(f2mul(b, b), beta2));
+        const float2 d = f2sub_s(f2sub_s(f2mul(f2mul(a, b), ab), f2mul(a, alphax)), f2mul(b, betax));
+        e[k] = f2add(s1, f2add(d, d));
+    }
+    return f2add_s(f2add_s(f2mul(e[0], f2splat(mx)), f2mul(e[1], f2splat(my))), f2mul(e[2], f2splat(mz)));
 }
 
 // WeightedClusterFit::Compress3 (weightedclusterfit.cpp:370-472): clusters at 0, 1/2, 1
@@ -362,12 +402,19 @@ template <bool DXT1A> NVB_DEV void bc3_color_body(const Bc3ColorParams &P) {
     float besterror = FLT_MAX;
     int bestci = 0x7fffffff;
     const bool try4 = !DXT1A || transparent_mask == 0;  // ColourFit::Compress: Compress4 only when nothing is transparent
-    for (int ci = l; try4 && ci < ncand; ci += 16) {
-        const unsigned pk = __ldg(P.cand + cbeg + ci);
-        const SquishSplit s = squish_eval_split(S.T, n, pk & 31, (pk >> 5) & 31, (pk >> 10) & 31, xsum, mqx, mqy, mqz);
-        if (s.error < besterror) {
-            besterror = s.error;
+    // two splits per trip (ci and ci + 16); the last, unpaired one re-uses split ci for the idle half
+    for (int ci = l; try4 && ci < ncand; ci += 32) {
+        const bool two = ci + 16 < ncand;
+        const unsigned pa = __ldg(P.cand_idx + cbeg + ci);
+        const unsigned pb = two ? __ldg(P.cand_idx + cbeg + ci + 16) : pa;
+        const float2 err = squish_eval_pair(S.T, pa, pb, xsum, mqx, mqy, mqz);
+        if (err.x < besterror) {
+            besterror = err.x;
             bestci = ci;
+        }
+        if (two && err.y < besterror) {
+            besterror = err.y;
+            bestci = ci + 16;
         }
     }
 #pragma unroll
@@ -399,7 +446,8 @@ template <bool DXT1A> NVB_DEV void bc3_color_body(const Bc3ColorParams &P) {
     } else if (bestci != 0x7fffffff) {
         const unsigned pk = __ldg(P.cand + cbeg + bestci);
         const int b0 = pk & 31, b1 = (pk >> 5) & 31, b2 = (pk >> 10) & 31;
-        const SquishSplit s = squish_eval_split(S.T, n, b0, b1, b2, xsum, mqx, mqy, mqz);
+        const unsigned pi = __ldg(P.cand_idx + cbeg + bestci);
+        const SquishSplit s = squish_eval_split(S.T, pi & 0xFF, (pi >> 8) & 0xFF, pi >> 16, xsum, mqx, mqy, mqz);
         const int pos = S.rank[myPoint];
         idx = (pos < b0) ? 0u : (pos < b0 + b1) ? 2u : (pos < b0 + b1 + b2) ? 3u : 1u;
         c565a = ((unsigned)squish_float_to_int(31.0f * s.ax, 31) << 11) | ((unsigned)squish_float_to_int(63.0f * s.ay, 63) << 5) |

@@ -39,6 +39,23 @@ NVB_DEV unsigned x86_ftou(float f) {
     return 0u;  // 0x8000000000000000 truncated
 }
 
+// ---- packed fp32 pairs (sm_100 FMUL2 / FADD2: two IEEE round-to-nearest results per issue slot) -----------------------
+// ptxas 12.9 contracts mul.rn.f32x2 -> add.rn.f32x2 into FFMA2 even with --fmad=false (measured; scalar ops are left
+// alone), which would change results.  So a sum that consumes a packed product is always done with two scalar FADDs
+// (f2add_s / f2sub_s); f2add / f2sub (one FADD2) are only used where neither operand is a product.
+#ifdef NVB_EMU
+NVB_DEV float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+NVB_DEV float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+NVB_DEV float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#else
+NVB_DEV float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+NVB_DEV float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+NVB_DEV float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+#endif
+NVB_DEV float2 f2add_s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+NVB_DEV float2 f2sub_s(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+NVB_DEV float2 f2splat(float v) { return make_float2(v, v); }
+
 // ---- gamma 2.2 approximations (src/nvmath/Gamma.cpp:311-354) -------------------------------------------
 // table[k] = float(2^((k-127)*p/q)) for the 9 "sign|exponent" bits; the tables are generated on the host by
 // nvb::build_gamma_tables() (capi.cu) and uploaded once per context.

@@ -18,6 +18,7 @@ static std::vector<uint16_t> g_cand;
 static int g_cand_off[18];
 static uint8_t g_om5[512], g_om6[512], g_om5a[512], g_om6a[512];
 static std::vector<uint16_t> g_cand3;
+static std::vector<uint32_t> g_cand_idx;
 static int g_cand3_off[18];
 static std::vector<uint16_t> g_four, g_three;
 static int g_four_total[16], g_three_total[16];
@@ -33,6 +34,7 @@ static void init_tables() {
     build_omatch(g_om5a, 32, true);
     build_omatch(g_om6a, 64, true);
     build_squish_splits3(g_cand3, g_cand3_off);
+    build_squish_split_indices(g_cand_idx);
     build_icbc_splits(g_four, g_four_total, g_three, g_three_total);
     build_icbc_midpoints(g_mid5, g_mid6);
     build_icbc_match(g_match5, 32);
@@ -78,6 +80,7 @@ void emu_bc3_color_ex(const float *planar, int w, int h, const float *metric, in
     P.weight_by_alpha = weight_by_alpha;
     P.dxt5n = dxt5n & 1;
     P.cand3 = g_cand3.data(); P.cand3_off = g_cand3_off; P.omatch5a = g_om5a; P.omatch6a = g_om6a;
+    P.cand_idx = g_cand_idx.data();
     P.cand = g_cand.data(); P.cand_off = g_cand_off; P.omatch5 = g_om5; P.omatch6 = g_om6;
     int nb = P.lv.bw * P.lv.bh;
     if (dxt5n & 2) emu::launch(dim3((nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS), dim3(NVB_BC3_GROUPS * 16), 0, [&] { k_bc1a_color(P); });
