@@ -10,6 +10,7 @@
 #include "kernels/bc1_quick.cuh"
 #include "kernels/bc6h.cuh"
 #include "kernels/bc7.cuh"
+#include "kernels/bc7_coop.cuh"
 #include "kernels/image_ops.cuh"
 
 #include <cuda_runtime.h>
@@ -428,8 +429,14 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, const
     cudaStreamWaitEvent(st, ctx->ev_fork, 0);
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
         NVB_LAUNCH_ON(ctx, st, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(nb, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, P);
-    const unsigned grid = (unsigned)(((size_t)nb * NCAND + 127) / 128);
-    NVB_LAUNCH_ON(ctx, st, K_BC7_REFINE, units, (k_bc7_refine<M, NCAND>), grid, 128, P);
+    if constexpr (M != 4 && M != 5) {
+        // warp-cooperative search: one warp per candidate, the candidates of a block share a CTA
+        constexpr int WPC = NCAND >= 4 ? NCAND : 4, BPC = WPC / NCAND;
+        NVB_LAUNCH_ON(ctx, st, K_BC7_REFINE, units, (k_bc7_refine_coop<M, NCAND>), (unsigned)((nb + BPC - 1) / BPC), WPC * 32, P);
+    } else {
+        const unsigned grid = (unsigned)(((size_t)nb * NCAND + 127) / 128);
+        NVB_LAUNCH_ON(ctx, st, K_BC7_REFINE, units, (k_bc7_refine<M, NCAND>), grid, 128, P);
+    }
     cudaEventRecord(ctx->ev_join[M], st);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join[M], 0);
 }

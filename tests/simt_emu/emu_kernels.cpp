@@ -8,6 +8,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_quick.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_coop.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -51,6 +52,13 @@ static LevelView make_lv(const float *data, int w, int h, int gamma) {
 template <int M, int NCAND> static void emu_bc7_mode(Bc7Params &P, int nb) {
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
         emu::launch(dim3((nb + NVB_BC7_ROUGH_WARPS - 1) / NVB_BC7_ROUGH_WARPS), dim3(NVB_BC7_ROUGH_WARPS * 32), 0, [&] { k_bc7_rough<M>(P); });
+    if constexpr (M != 4 && M != 5) {
+        if (!getenv("NVB_EMU_BC7_SCALAR")) {
+            constexpr int WPC = NCAND >= 4 ? NCAND : 4, BPC = WPC / NCAND;
+            emu::launch(dim3((nb + BPC - 1) / BPC), dim3(WPC * 32), 0, [&] { k_bc7_refine_coop<M, NCAND>(P); });
+            return;
+        }
+    }
     emu::launch(dim3((nb * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_refine<M, NCAND>(P); });
 }
 
