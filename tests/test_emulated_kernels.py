@@ -77,6 +77,8 @@ def test_emulated_encoders_match_golden(emu, golden):
     for key, (kind, w, h, fmt, q, am, cw, pt) in G.level_cases().items():
         if (w, h) != (13, 7) and kind != "photo" and fmt not in (10, 11):
             continue  # keep the CPU suite short: ragged size for every input kind, full size for one
+        if fmt == 11 and (w, h) != (13, 7) and not os.environ.get("NVB_EMU_FULL"):
+            continue  # warp-cooperative BC7 under the fibre emulator: 2+ minutes per 24x16 image (set NVB_EMU_FULL=1)
         img = G.make_input(kind, w, h, planar=True)
         got = _encode(emu, fmt, q, img, am, cw, pt)
         assert np.array_equal(got, golden[key]), key
