@@ -986,13 +986,13 @@ template <> struct Bc7Slot<7> { static constexpr int v = 4; };
 
 #define NVB_BC7_ROUGH_WARPS 4
 
-template <int M> __global__ void __launch_bounds__(NVB_BC7_ROUGH_WARPS * 32) k_bc7_rough(Bc7Params P) {
+template <int M> __global__ void __launch_bounds__(NVB_BC7_ROUGH_WARPS * 32) k_bc7_rough(Bc7Params P, int blk_begin, int blk_end) {
     using C = Bc7Cfg<M>;
     __shared__ Bc7Tile s_tile[NVB_BC7_ROUGH_WARPS];
     __shared__ float s_mse[NVB_BC7_ROUGH_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nblocks = P.lv.bw * P.lv.bh;
-    for (int blk = blockIdx.x * NVB_BC7_ROUGH_WARPS + wib; blk < nblocks; blk += gridDim.x * NVB_BC7_ROUGH_WARPS) {
+    for (int blk = blk_begin + blockIdx.x * NVB_BC7_ROUGH_WARPS + wib; blk < blk_end; blk += gridDim.x * NVB_BC7_ROUGH_WARPS) {
         __syncwarp();
         if (lane < 16) {
             const int x = (blk % P.lv.bw) * 4 + (lane & 3), y = (blk / P.lv.bw) * 4 + (lane >> 2);

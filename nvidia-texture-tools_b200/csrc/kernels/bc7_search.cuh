@@ -1,0 +1,705 @@
+// BC7 endpoint search as a per-thread state machine: one thread per *searcher*.
+//
+// The reference's refine() (src/bc7/avpcl_mode*.cpp: optimize_endpts -> optimize_one -> perturb_one / exhaustive) runs one
+// independent sequential search per (candidate shape | rotation x index mode, region, lsb combination): a few hundred
+// map_colors() trials each, every trial depending on the outcome of the previous ones.  A block has up to 432 such
+// searchers over its eight modes.  Here each searcher is one thread, and the search is written as an explicit state
+// machine whose only expensive step — map_colors of one trial endpoint pair over the region's texels — sits at a single
+// point of the loop.  The 32 lanes of a warp are therefore always converged in the trial evaluation, whatever phase
+// (first / alternating perturbation, +-3 exhaustive window, restart) each of them is in; only the few instructions
+// that pick the next trial diverge.  The thread-per-candidate kernels (bc7.cuh) and the warp-per-candidate kernels
+// (bc7_coop.cuh) execute the same search; all three give bit-identical blocks.
+//
+//   k_bc7_tiles        texels of the chunk's blocks (x255, zero outside the image) as [block][16] float4
+//   k_bc7_setup<M>     thread per candidate: rough fit, quantise, assign, anchor swap  -> start endpoints + error per region
+//   k_bc7_search<M,IM> thread per searcher (grid-stride): the state machine           -> best endpoints + error
+//   k_bc7_finish<M>    thread per candidate: first strict minimum over the lsb searches of each region, re-assign, emit,
+//                      (error, rank) reduction over the candidates of a block
+//
+// Trial errors do not depend on the running threshold: map_colors only uses it to leave early with FLT_MAX once the partial
+// sum exceeds it, errors are non-negative and fp32 addition of non-negative terms is monotone, so the comparison
+// "err < threshold" that follows gives the same answer for the full sum.
+#pragma once
+#include "bc7.cuh"
+
+namespace nvb {
+
+struct Bc7SearchParams {
+    Bc7Params P;
+    int blk0, nblk;        // this chunk = linear blocks [blk0, blk0 + nblk) of the level
+    const float4 *tiles;   // [nblk][16]
+    uint4 *setup;          // [nblk][NCAND][NR]          {A, B, lsbs, error bits}
+    uint4 *setup_idx;      // [nblk][NCAND]              indices of the start endpoints after the anchor swap, 4 bits per texel
+    uint4 *res;            // [nblk][NCAND][NR][NLSB]    {A, B, lsbs, error bits}
+};
+
+// ---- compile-time view shared by the six single-index modes and the two split modes -------------------------------------
+template <int M, bool SPLIT = (M == 4 || M == 5)> struct Bc7X;
+template <int M> struct Bc7X<M, false> {
+    static constexpr bool SPLIT = false, EXHREF = Bc7Cfg<M>::EXHREF;
+    static constexpr int NCH = Bc7Cfg<M>::NCH, NR = Bc7Cfg<M>::NR, LSB = Bc7Cfg<M>::LSB;
+    static constexpr int NLSB = LSB == 0 ? 1 : (LSB == 1 ? 2 : 4);
+    NVB_DEV static int prec(int) { return Bc7Cfg<M>::PREC; }
+};
+template <int M> struct Bc7X<M, true> {
+    static constexpr bool SPLIT = true, EXHREF = false;
+    static constexpr int NCH = 4, NR = 1, LSB = 0, NLSB = 1;
+    NVB_DEV static int prec(int ch) { return bc7s_prec<M>(ch); }
+};
+
+// index arrays are only ever compared for equality inside optimize_one: 4 bits per texel (two arrays for the split modes)
+template <bool WIDE> struct Bc7Idx;
+template <> struct Bc7Idx<false> {
+    unsigned long long lo;
+    NVB_DEV void clear() { lo = 0; }
+    NVB_DEV bool differs(const Bc7Idx &o) const { return lo != o.lo; }
+};
+template <> struct Bc7Idx<true> {
+    unsigned long long lo, hi;
+    NVB_DEV void clear() { lo = hi = 0; }
+    NVB_DEV bool differs(const Bc7Idx &o) const { return lo != o.lo || hi != o.hi; }
+};
+
+NVB_DEV int bx_get(unsigned v, int ch) { return (int)((v >> (8 * ch)) & 0xFFu); }
+NVB_DEV unsigned bx_set(unsigned v, int ch, int x) { return (v & ~(0xFFu << (8 * ch))) | ((unsigned)(x & 0xFF) << (8 * ch)); }
+
+// interpolation weights as compile-time constants (same values as kAvpclW3/7/15)
+NVB_DEV constexpr int avpcl_wc(int nidx, int i) {
+    constexpr int w3[4] = {0, 21, 43, 64};
+    constexpr int w7[8] = {0, 9, 18, 27, 37, 46, 55, 64};
+    constexpr int w15[16] = {0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64};
+    return nidx == 16 ? w15[i] : nidx == 8 ? w7[i] : w3[i];
+}
+template <int NIDX> NVB_DEV void bx_lerp_row(int a, int b, float *out, int stride) {
+#pragma unroll
+    for (int j = 0; j < NIDX; ++j) out[j * stride] = (float)((a * avpcl_wc(NIDX, NIDX - 1 - j) + b * avpcl_wc(NIDX, j) + 32) >> 6);
+}
+
+// "stop at the first increase" scan of the reference, one more palette entry: err_j against the running best
+#define NVB_BX_SCAN_STEP(e, j)                     \
+    {                                              \
+        const bool gt_ = (e) > best, lt_ = (e) < best; \
+        live = live && !gt_;                       \
+        const bool upd_ = live && lt_;             \
+        best = upd_ ? (e) : best;                  \
+        bj = upd_ ? (j) : bj;                      \
+    }
+
+// map_colors of modes 0,1,2,3,6,7 for one trial: texels `members` (4-bit texel numbers, np of them) of tile
+template <int M> NVB_DEV float bx_eval(const float4 *__restrict__ tile, unsigned long long members, int np, unsigned A, unsigned B, int la, int lb,
+                                       Bc7Idx<false> &idx) {
+    using C = Bc7Cfg<M>;
+    constexpr int N = C::NIDX;
+    float pal[C::NCH][N];
+#pragma unroll
+    for (int ch = 0; ch < C::NCH; ch++) {
+        int a, b;
+        if (C::LSB == 0) {
+            a = avpcl_unquantize(bx_get(A, ch), C::PREC);
+            b = avpcl_unquantize(bx_get(B, ch), C::PREC);
+        } else {
+            const int lbb = (C::LSB == 1) ? la : lb;
+            a = avpcl_unquantize((bx_get(A, ch) << 1) | la, C::PREC + 1);
+            b = avpcl_unquantize((bx_get(B, ch) << 1) | lbb, C::PREC + 1);
+        }
+        bx_lerp_row<N>(a, b, pal[ch], 1);
+    }
+    float tot = 0;
+    unsigned long long id = 0;
+    for (int i = 0; i < np; ++i) {
+        const int t = (int)(members >> (4 * i)) & 15;
+        const float4 c = __ldg(tile + t);
+        float ww = 0;
+        if (C::NCH == 3) {
+            const float w = c.w - 255.0f;
+            ww = w * w;
+        }
+        float best = 0;
+        int bj = 0;
+        bool live = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float x = c.x - pal[0][j], y = c.y - pal[1][j], z = c.z - pal[2][j];
+            float e;
+            if (C::NCH == 3) {
+                e = x * x + y * y + z * z + ww;
+            } else {
+                const float w = c.w - pal[C::NCH - 1][j];
+                e = x * x + y * y + z * z + w * w;
+            }
+            if (j == 0) best = e;
+            else NVB_BX_SCAN_STEP(e, j)
+        }
+        tot += best;
+        id |= (unsigned long long)bj << (4 * i);
+    }
+    idx.lo = id;
+    return tot;
+}
+
+// map_colors of modes 4,5 for one trial (all 16 texels; rotation applied to the texel as it is read)
+template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *__restrict__ tile, int rot, unsigned A, unsigned B, Bc7Idx<true> &idx) {
+    constexpr int NRGB = (M == 5) ? 4 : (IM == 1 ? 8 : 4), NA = (M == 5) ? 4 : (IM == 1 ? 4 : 8);
+    float prgb[3][NRGB], pa[NA];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++)
+        bx_lerp_row<NRGB>(avpcl_unquantize(bx_get(A, ch), Bc7SplitCfg<M>::PREC_RGB), avpcl_unquantize(bx_get(B, ch), Bc7SplitCfg<M>::PREC_RGB), prgb[ch], 1);
+    bx_lerp_row<NA>(avpcl_unquantize(bx_get(A, 3), Bc7SplitCfg<M>::PREC_A), avpcl_unquantize(bx_get(B, 3), Bc7SplitCfg<M>::PREC_A), pa, 1);
+    float tot = 0;
+    unsigned long long irgb = 0, ia = 0;
+    for (int i = 0; i < 16; ++i) {
+        float4 c = __ldg(tile + i);
+        {
+            // AGBR / RABG / RGAB: swap channel rot-1 with alpha
+            const float w0 = c.w;
+            c.w = rot == 1 ? c.x : rot == 2 ? c.y : rot == 3 ? c.z : c.w;
+            c.x = rot == 1 ? w0 : c.x;
+            c.y = rot == 2 ? w0 : c.y;
+            c.z = rot == 3 ? w0 : c.z;
+        }
+        float ea, er;
+        int ja, jr;
+        {
+            float best = 0;
+            int bj = 0;
+            bool live = true;
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                const float d = c.w - pa[j];
+                const float e = d * d;
+                if (j == 0) best = e;
+                else NVB_BX_SCAN_STEP(e, j)
+            }
+            ea = best;
+            ja = bj;
+        }
+        {
+            float best = 0;
+            int bj = 0;
+            bool live = true;
+#pragma unroll
+            for (int j = 0; j < NRGB; ++j) {
+                const float x = c.x - prgb[0][j], y = c.y - prgb[1][j], z = c.z - prgb[2][j];
+                const float e = x * x + y * y + z * z;
+                if (j == 0) best = e;
+                else NVB_BX_SCAN_STEP(e, j)
+            }
+            er = best;
+            jr = bj;
+        }
+        const float e1 = rot == 0 ? ea : er, e2 = rot == 0 ? er : ea;
+        tot += e1;
+        tot += e2;
+        irgb |= (unsigned long long)jr << (4 * i);
+        ia |= (unsigned long long)ja << (4 * i);
+    }
+    idx.lo = irgb;
+    idx.hi = ia;
+    return tot;
+}
+
+// ---- the searcher ---------------------------------------------------------------------------------------------------------
+enum {
+    BXP_LOAD = 0, BXP_INIT_WAIT, BXP_CH_START, BXP_PERT_EMIT, BXP_PERT_WAIT, BXP_PERT_FIN,
+    BXP_EXH_CH_START, BXP_EXH_EMIT, BXP_EXH_WAIT, BXP_EXH_CH_END, BXP_STORE, BXP_EXIT
+};
+
+// IM: index mode of mode 4 (0 or 1); 0 for every other mode
+template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7SearchParams S) {
+    using X = Bc7X<M>;
+    using Idx = Bc7Idx<X::SPLIT>;
+    constexpr int NCAND_SPLIT = 4 * (M == 4 ? 2 : 1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total;
+    int ncand = 1;
+    if constexpr (X::SPLIT) total = (long long)S.nblk * 4;
+    else {
+        ncand = Bc7Cfg<M>::NITEMS;
+        total = (long long)S.nblk * ncand * X::NR * X::NLSB;
+    }
+    const int nblocks = S.P.lv.bw * S.P.lv.bh;
+
+    // searcher state
+    int phase = BXP_LOAD;
+    const float4 *tile = S.tiles;
+    unsigned long long members = 0;
+    int np = 0, rot = 0;
+    long long slot = 0;          // where the result goes
+    unsigned A = 0, B = 0;       // current best endpoints ("opt"), 8 bits per channel
+    int la = 0, lb = 0;
+    float opt_err = 0;
+    int ch = 0;
+    // perturb_one
+    int pk = 0, do_b = 0, pv = 0, step = 0, sgn = -1, beststep = 0;
+    bool improved = false;
+    float pmin = 0;              // min_err of perturb_one / best_err of exhaustive
+    Idx pidx;                    // indices of the best trial of the running perturb_one / exhaustive
+    float err0 = 0;
+    int va = 0;
+    Idx t0, orig_idx, new_idx;
+    // exhaustive
+    bool first = true, exh_done = false;
+    float exh_orig = 0;
+    int eo = 0, ei = 0, ta = 0, tb = 0, amin = 0, bmin = 0;
+    pidx.clear(); t0.clear(); orig_idx.clear(); new_idx.clear();
+
+    for (;;) {
+        unsigned tA = 0, tB = 0;
+        bool have = false;
+        while (!have && phase != BXP_EXIT) {
+            switch (phase) {
+            case BXP_LOAD: {
+                if (s >= total) {
+                    phase = BXP_EXIT;
+                    break;
+                }
+                uint4 su;
+                if constexpr (X::SPLIT) {
+                    const int blk = (int)(s >> 2);
+                    rot = (int)(s & 3);
+                    slot = (long long)blk * NCAND_SPLIT + rot * (M == 4 ? 2 : 1) + IM;
+                    su = S.setup[slot];
+                    tile = S.tiles + (size_t)blk * 16;
+                    np = 16;
+                    la = lb = 0;
+                } else {
+                    using C = Bc7Cfg<M>;
+                    long long q = s;
+                    const int lsbmode = (int)(q % X::NLSB);
+                    q /= X::NLSB;
+                    const int region = (int)(q % X::NR);
+                    q /= X::NR;
+                    const int cand = (int)(q % ncand);
+                    const int blk = (int)(q / ncand);
+                    slot = s;
+                    su = S.setup[((size_t)blk * ncand + cand) * X::NR + region];
+                    tile = S.tiles + (size_t)blk * 16;
+                    int shape = 0;
+                    if constexpr (C::NSH > 1) shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + cand];
+                    members = 0;
+                    np = 0;
+                    for (int i = 0; i < 16; i++)
+                        if (bc7_region<C::NR>(shape, i) == region) {
+                            members |= (unsigned long long)i << (4 * np);
+                            ++np;
+                        }
+                    la = lsbmode & 1;
+                    lb = (X::LSB == 2) ? (lsbmode >> 1) & 1 : 0;
+                }
+                A = su.x;
+                B = su.y;
+                if (X::LSB != 0) {
+                    // in_err = map_colors(temp_in with this lsb combination)
+                    tA = A;
+                    tB = B;
+                    phase = BXP_INIT_WAIT;
+                    have = true;
+                } else {
+                    opt_err = __uint_as_float(su.w);
+                    ch = 0;
+                    phase = BXP_CH_START;
+                }
+                break;
+            }
+            case BXP_CH_START:
+                if (ch >= X::NCH) {
+                    ch = 0;
+                    first = true;
+                    phase = BXP_EXH_CH_START;
+                } else {
+                    pk = 0;
+                    do_b = 0;
+                    pv = bx_get(A, ch);
+                    pmin = opt_err;
+                    step = 1 << (X::prec(ch) - 1);
+                    sgn = -1;
+                    improved = false;
+                    phase = BXP_PERT_EMIT;
+                }
+                break;
+            case BXP_PERT_EMIT: {
+                if (step == 0) {
+                    phase = BXP_PERT_FIN;
+                    break;
+                }
+                const int v = pv + sgn * step;
+                if (v >= 0 && v < (1 << X::prec(ch))) {
+                    tA = do_b ? A : bx_set(A, ch, v);
+                    tB = do_b ? bx_set(B, ch, v) : B;
+                    phase = BXP_PERT_WAIT;
+                    have = true;
+                } else if (sgn < 0) {
+                    sgn = 1;
+                } else {
+                    if (improved) pv += beststep;
+                    improved = false;
+                    step >>= 1;
+                    sgn = -1;
+                }
+                break;
+            }
+            case BXP_PERT_FIN: {
+                bool again = false;  // start another perturb_one on endpoint do_b
+                if (pk == 0) {
+                    err0 = pmin;
+                    va = pv;
+                    t0 = pidx;
+                    pk = 1;
+                    do_b = 1;
+                    again = true;
+                } else if (pk == 1) {
+                    const float err1 = pmin;
+                    if (err0 < err1) {
+                        if (!(err0 >= opt_err)) {
+                            new_idx = orig_idx = t0;
+                            A = bx_set(A, ch, va);
+                            opt_err = err0;
+                            do_b = 1;
+                            again = true;
+                        }
+                    } else {
+                        if (!(err1 >= opt_err)) {
+                            new_idx = orig_idx = pidx;
+                            B = bx_set(B, ch, pv);
+                            opt_err = err1;
+                            do_b = 0;
+                            again = true;
+                        }
+                    }
+                    pk = 2;
+                    if (!again) {  // `continue`: next channel without the restart test
+                        ++ch;
+                        phase = BXP_CH_START;
+                    }
+                } else {
+                    if (pmin >= opt_err) {
+                        if (orig_idx.differs(new_idx)) ch = -1;  // indices changed: start over
+                        ++ch;
+                        phase = BXP_CH_START;
+                    } else {
+                        new_idx = pidx;
+                        if (do_b == 0) A = bx_set(A, ch, pv);
+                        else B = bx_set(B, ch, pv);
+                        opt_err = pmin;
+                        do_b = 1 - do_b;
+                        again = true;
+                    }
+                }
+                if (again) {
+                    pv = bx_get(do_b ? B : A, ch);
+                    pmin = opt_err;
+                    step = 1 << (X::prec(ch) - 1);
+                    sgn = -1;
+                    improved = false;
+                    phase = BXP_PERT_EMIT;
+                }
+                break;
+            }
+            case BXP_EXH_CH_START: {
+                if (ch >= X::NCH) {
+                    phase = BXP_STORE;
+                    break;
+                }
+                exh_orig = opt_err;
+                pmin = exh_orig;
+                if (exh_orig == 0) {  // exhaustive() returns at once; nothing can improve
+                    ++ch;
+                    break;
+                }
+                const int prec = X::prec(ch), A0 = bx_get(A, ch), B0 = bx_get(B, ch);
+                const int alow = max(0, A0 - 3), ahigh = min((1 << prec) - 1, A0 + 3);
+                const int blow = max(0, B0 - 3), bhigh = min((1 << prec) - 1, B0 + 3);
+                const bool a_le_b = A0 <= B0;
+                const int o_end = a_le_b ? ahigh : bhigh - 1, i_end = a_le_b ? bhigh - 1 : ahigh, lowi = a_le_b ? blow : alow;
+                eo = a_le_b ? alow : blow;
+                exh_done = eo > o_end;
+                if (!exh_done) ei = max(eo, lowi);
+                while (!exh_done && ei > i_end) {
+                    ++eo;
+                    if (eo > o_end) exh_done = true;
+                    else ei = max(eo, lowi);
+                }
+                phase = BXP_EXH_EMIT;
+                break;
+            }
+            case BXP_EXH_EMIT: {
+                if (exh_done) {
+                    phase = BXP_EXH_CH_END;
+                    break;
+                }
+                const int prec = X::prec(ch), A0 = bx_get(A, ch), B0 = bx_get(B, ch);
+                const int alow = max(0, A0 - 3), ahigh = min((1 << prec) - 1, A0 + 3);
+                const int blow = max(0, B0 - 3), bhigh = min((1 << prec) - 1, B0 + 3);
+                const bool a_le_b = A0 <= B0;
+                const int o_end = a_le_b ? ahigh : bhigh - 1, i_end = a_le_b ? bhigh - 1 : ahigh, lowi = a_le_b ? blow : alow;
+                ta = a_le_b ? eo : ei;
+                tb = a_le_b ? ei : eo;
+                tA = bx_set(A, ch, ta);
+                tB = bx_set(B, ch, tb);
+                ++ei;
+                while (!exh_done && ei > i_end) {
+                    ++eo;
+                    if (eo > o_end) exh_done = true;
+                    else ei = max(eo, lowi);
+                }
+                phase = BXP_EXH_WAIT;
+                have = true;
+                break;
+            }
+            case BXP_EXH_CH_END: {
+                const float new_err = pmin;
+                if (pmin < exh_orig) {
+                    A = bx_set(A, ch, amin);
+                    B = bx_set(B, ch, bmin);
+                    t0 = pidx;
+                    if (X::EXHREF) opt_err = pmin;  // modes 0 and 3 pass the error by reference
+                }
+                if (new_err < opt_err) {
+                    opt_err = new_err;
+                    if (first) {
+                        orig_idx = t0;
+                        first = false;
+                    } else if (orig_idx.differs(t0)) {
+                        ch = -1;
+                        first = true;
+                    }
+                }
+                ++ch;
+                phase = BXP_EXH_CH_START;
+                break;
+            }
+            case BXP_STORE:
+                S.res[slot] = make_uint4(A, B, (unsigned)(la | (lb << 1)), __float_as_uint(opt_err));
+                s += stride;
+                phase = BXP_LOAD;
+                break;
+            default:
+                break;
+            }
+        }
+        if (phase == BXP_EXIT) break;
+
+        // ---- the one expensive step: every live lane of the warp is here together ----
+        Idx ti;
+        float err;
+        if constexpr (X::SPLIT) err = bx_eval_split<M, IM>(tile, rot, tA, tB, ti);
+        else err = bx_eval<M>(tile, members, np, tA, tB, la, lb, ti);
+
+        if (phase == BXP_INIT_WAIT) {
+            opt_err = err;
+            ch = 0;
+            phase = BXP_CH_START;
+        } else if (phase == BXP_PERT_WAIT) {
+            if (err < pmin) {
+                improved = true;
+                pmin = err;
+                beststep = sgn * step;
+                pidx = ti;
+            }
+            if (sgn < 0) {
+                sgn = 1;
+            } else {
+                if (improved) pv += beststep;
+                improved = false;
+                step >>= 1;
+                sgn = -1;
+            }
+            phase = BXP_PERT_EMIT;
+        } else {  // BXP_EXH_WAIT
+            if (err < pmin) {
+                amin = ta;
+                bmin = tb;
+                pmin = err;
+                pidx = ti;
+            }
+            phase = BXP_EXH_EMIT;
+        }
+    }
+}
+
+// ---- tiles -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bc7_tiles(Bc7SearchParams S, float4 *tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.nblk * 16) return;
+    const int blk = S.blk0 + (t >> 4), i = t & 15;
+    const LevelView &lv = S.P.lv;
+    const int x = (blk % lv.bw) * 4 + (i & 3), y = (blk / lv.bw) * 4 + (i >> 2);
+    float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // texels outside the image are Vector4(0) (BlockCompressor.cpp:152-163)
+    if (x < lv.w && y < lv.h) {
+        c.x = load_texel(lv, 0, x, y) * 255.0f;
+        c.y = load_texel(lv, 1, x, y) * 255.0f;
+        c.z = load_texel(lv, 2, x, y) * 255.0f;
+        c.w = load_texel(lv, 3, x, y) * 255.0f;
+    }
+    tiles[t] = c;
+}
+
+NVB_DEV void bx_read_tile(const float4 *tiles, int blk, Bc7Tile &t) {
+    for (int i = 0; i < 16; i++) {
+        const float4 c = tiles[(size_t)blk * 16 + i];
+        t.c[i][0] = c.x;
+        t.c[i][1] = c.y;
+        t.c[i][2] = c.z;
+        t.c[i][3] = c.w;
+    }
+}
+NVB_DEV uint4 bx_pack(const Bc7Ep &e, float err) {
+    unsigned A = 0, B = 0;
+    for (int k = 0; k < 4; k++) {
+        A = bx_set(A, k, e.A[k]);
+        B = bx_set(B, k, e.B[k]);
+    }
+    return make_uint4(A, B, (unsigned)(e.a_lsb | (e.b_lsb << 1)), __float_as_uint(err));
+}
+NVB_DEV uint4 bx_pack_idx(const int *i0, const int *i1) {
+    unsigned w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) {
+        w[i >> 3] |= (unsigned)(i0[i] & 15) << (4 * (i & 7));
+        if (i1) w[2 + (i >> 3)] |= (unsigned)(i1[i] & 15) << (4 * (i & 7));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+NVB_DEV void bx_unpack_idx(const uint4 &u, int *i0, int *i1) {
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+    for (int i = 0; i < 16; i++) {
+        i0[i] = (int)((w[i >> 3] >> (4 * (i & 7))) & 15);
+        if (i1) i1[i] = (int)((w[2 + (i >> 3)] >> (4 * (i & 7))) & 15);
+    }
+}
+NVB_DEV void bx_unpack(const uint4 &u, Bc7Ep &e) {
+    for (int k = 0; k < 4; k++) {
+        e.A[k] = bx_get(u.x, k);
+        e.B[k] = bx_get(u.y, k);
+    }
+    e.a_lsb = (int)(u.z & 1);
+    e.b_lsb = (int)((u.z >> 1) & 1);
+}
+
+// ---- setup: the part of refine() before optimize_endpts -------------------------------------------------------------------
+template <int M, int NCAND> __global__ void __launch_bounds__(128) k_bc7_setup(Bc7SearchParams S) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int blk = t / NCAND, rank = t % NCAND;
+    if (blk >= S.nblk) return;
+    Bc7Tile tile;
+    bx_read_tile(S.tiles, blk, tile);
+    if constexpr (M == 4 || M == 5) {
+        const int nim = Bc7SplitCfg<M>::NIDXMODES, rotatemode = rank / nim, indexmode = rank % nim;
+        Bc7Tile t1;
+        bc7_rotate_tile(tile, rotatemode, t1);
+        float ep[8];
+        bc7s_rough(t1, ep);
+        Bc7Ep orig;
+        orig.a_lsb = orig.b_lsb = 0;
+        for (int k = 0; k < 4; k++) {
+            orig.A[k] = avpcl_quantize(ep[k], bc7s_prec<M>(k));
+            orig.B[k] = avpcl_quantize(ep[4 + k], bc7s_prec<M>(k));
+        }
+        int orig_rgb[16], orig_a[16];
+        const float orig_err = bc7s_assign_indices<M>(t1, rotatemode, indexmode, orig, orig_rgb, orig_a);
+        bc7s_swap_indices<M>(indexmode, orig, orig_rgb, orig_a);
+        S.setup[(size_t)blk * NCAND + rank] = bx_pack(orig, orig_err);
+        S.setup_idx[(size_t)blk * NCAND + rank] = bx_pack_idx(orig_rgb, orig_a);
+    } else {
+        using C = Bc7Cfg<M>;
+        const int nblocks = S.P.lv.bw * S.P.lv.bh;
+        int shape = 0;
+        if constexpr (C::NSH > 1) shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + rank];
+        float ep[C::NR][8];
+        bc7_rough_endpoints<M>(tile, shape, ep);
+        float orig_err[C::NR];
+        Bc7Ep orig[C::NR];
+        int orig_idx[16];
+        bc7_quantize_endpts<M>(ep, orig);
+        bc7_assign_indices<M>(tile, shape, orig, orig_idx, orig_err);
+        bc7_swap_indices<M>(orig, orig_idx, shape);
+        for (int r = 0; r < C::NR; r++) S.setup[((size_t)blk * NCAND + rank) * C::NR + r] = bx_pack(orig[r], orig_err[r]);
+        S.setup_idx[(size_t)blk * NCAND + rank] = bx_pack_idx(orig_idx, nullptr);
+    }
+}
+
+// ---- finish: the part of refine() after optimize_endpts, then the reduction over a block's candidates ---------------------
+template <int M, int NCAND> __global__ void __launch_bounds__(128) k_bc7_finish(Bc7SearchParams S) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int blk = t / NCAND, rank = t % NCAND;
+    const int nblocks = S.P.lv.bw * S.P.lv.bh;
+    float err = FLT_MAX;
+    __align__(16) unsigned char out[16];
+    *reinterpret_cast<uint4 *>(out) = make_uint4(0, 0, 0, 0);
+    if (blk < S.nblk) {
+        Bc7Tile tile;
+        bx_read_tile(S.tiles, blk, tile);
+        if constexpr (M == 4 || M == 5) {
+            const int nim = Bc7SplitCfg<M>::NIDXMODES, rotatemode = rank / nim, indexmode = rank % nim;
+            Bc7Tile t1;
+            bc7_rotate_tile(tile, rotatemode, t1);
+            const uint4 su = S.setup[(size_t)blk * NCAND + rank], ru = S.res[(size_t)blk * NCAND + rank];
+            Bc7Ep orig, opt;
+            bx_unpack(su, orig);
+            int orig_rgb[16], orig_a[16], opt_rgb[16], opt_a[16];
+            const float orig_err = __uint_as_float(su.w);
+            opt = orig;
+            const float out_err = __uint_as_float(ru.w);
+            if (out_err < orig_err) bx_unpack(ru, opt);
+            const float opt_err = bc7s_assign_indices<M>(t1, rotatemode, indexmode, opt, opt_rgb, opt_a);
+            bc7s_swap_indices<M>(indexmode, opt, opt_rgb, opt_a);
+            const float orig_tot = 0.0f + orig_err, opt_tot = 0.0f + opt_err;
+            if (opt_tot < orig_tot) {
+                bc7s_emit<M>(opt, opt_rgb, opt_a, rotatemode, indexmode, out);
+                err = opt_tot;
+            } else {
+                bx_unpack_idx(S.setup_idx[(size_t)blk * NCAND + rank], orig_rgb, orig_a);
+                bc7s_emit<M>(orig, orig_rgb, orig_a, rotatemode, indexmode, out);
+                err = orig_tot;
+            }
+        } else {
+            using C = Bc7Cfg<M>;
+            using X = Bc7X<M>;
+            int shape = 0;
+            if constexpr (C::NSH > 1) shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + rank];
+            float orig_err[C::NR], opt_err[C::NR];
+            Bc7Ep orig[C::NR], opt[C::NR];
+            int idx[16];
+            for (int r = 0; r < C::NR; ++r) {
+                const uint4 su = S.setup[((size_t)blk * NCAND + rank) * C::NR + r];
+                bx_unpack(su, orig[r]);
+                orig_err[r] = __uint_as_float(su.w);
+                opt[r] = orig[r];
+                float best_err = orig_err[r];
+                for (int l = 0; l < X::NLSB; ++l) {
+                    const uint4 ru = S.res[(((size_t)blk * NCAND + rank) * C::NR + r) * X::NLSB + l];
+                    const float out_err = __uint_as_float(ru.w);
+                    if (out_err < best_err) {
+                        best_err = out_err;
+                        bx_unpack(ru, opt[r]);
+                    }
+                }
+            }
+            bc7_assign_indices<M>(tile, shape, opt, idx, opt_err);
+            bc7_swap_indices<M>(opt, idx, shape);
+            float orig_tot = 0, opt_tot = 0;
+            for (int i = 0; i < C::NR; ++i) {
+                orig_tot += orig_err[i];
+                opt_tot += opt_err[i];
+            }
+            if (opt_tot < orig_tot) {
+                bc7_emit<M>(opt, shape, idx, out);
+                err = opt_tot;
+            } else {
+                bx_unpack_idx(S.setup_idx[(size_t)blk * NCAND + rank], idx, nullptr);
+                bc7_emit<M>(orig, shape, idx, out);
+                err = orig_tot;
+            }
+        }
+        if (!(err < FLT_MAX)) err = FLT_MAX;
+    }
+    uint4 b = *reinterpret_cast<uint4 *>(out);
+    int r = rank;
+    bc7_group_min<NCAND>(err, r, b);
+    if (blk < S.nblk && rank == 0) {
+        *reinterpret_cast<uint4 *>(S.P.cand + ((size_t)M * nblocks + S.blk0 + blk) * 16) = b;
+        S.P.cand_err[(size_t)M * nblocks + S.blk0 + blk] = err;
+    }
+}
+
+}  // namespace nvb

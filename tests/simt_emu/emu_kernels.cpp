@@ -9,6 +9,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_coop.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -49,17 +50,38 @@ static LevelView make_lv(const float *data, int w, int h, int gamma) {
     return lv;
 }
 
+// NVB_EMU_BC7 = "scalar" (thread per candidate), "coop" (warp per candidate) or unset: the product's searcher state machine
 template <int M, int NCAND> static void emu_bc7_mode(Bc7Params &P, int nb) {
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
-        emu::launch(dim3((nb + NVB_BC7_ROUGH_WARPS - 1) / NVB_BC7_ROUGH_WARPS), dim3(NVB_BC7_ROUGH_WARPS * 32), 0, [&] { k_bc7_rough<M>(P); });
+        emu::launch(dim3((nb + NVB_BC7_ROUGH_WARPS - 1) / NVB_BC7_ROUGH_WARPS), dim3(NVB_BC7_ROUGH_WARPS * 32), 0, [&] { k_bc7_rough<M>(P, 0, nb); });
+    const char *how = getenv("NVB_EMU_BC7");
+    if (how && !strcmp(how, "scalar")) {
+        emu::launch(dim3((nb * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_refine<M, NCAND>(P); });
+        return;
+    }
     if constexpr (M != 4 && M != 5) {
-        if (!getenv("NVB_EMU_BC7_SCALAR")) {
+        if (how && !strcmp(how, "coop")) {
             constexpr int WPC = NCAND >= 4 ? NCAND : 4, BPC = WPC / NCAND;
             emu::launch(dim3((nb + BPC - 1) / BPC), dim3(WPC * 32), 0, [&] { k_bc7_refine_coop<M, NCAND>(P); });
             return;
         }
     }
-    emu::launch(dim3((nb * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_refine<M, NCAND>(P); });
+    // two chunks, to exercise the chunk offsets
+    for (int blk0 = 0; blk0 < nb;) {
+        const int n = blk0 == 0 ? (nb + 1) / 2 : nb - blk0;
+        using X = Bc7X<M>;
+        std::vector<float4> tiles((size_t)n * 16);
+        std::vector<uint4> setup((size_t)n * NCAND * X::NR), sidx((size_t)n * NCAND), res((size_t)n * NCAND * X::NR * X::NLSB);
+        Bc7SearchParams S;
+        S.P = P; S.blk0 = blk0; S.nblk = n; S.tiles = tiles.data(); S.setup = setup.data(); S.setup_idx = sidx.data(); S.res = res.data();
+        emu::launch(dim3((n * 16 + 255) / 256), dim3(256), 0, [&] { k_bc7_tiles(S, tiles.data()); });
+        emu::launch(dim3((n * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_setup<M, NCAND>(S); });
+        const int grid = 3;  // few threads: every thread walks several searchers
+        emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 0>(S); });
+        if constexpr (M == 4) emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 1>(S); });
+        emu::launch(dim3((n * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_finish<M, NCAND>(S); });
+        blk0 += n;
+    }
 }
 
 extern "C" {
