@@ -42,8 +42,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
@@ -429,32 +429,46 @@ int nvttb_format_supported(int format, int quality) {
 template <int M, int NCAND> struct Bc7ModeBytes {
     using X = Bc7X<M>;
     static constexpr size_t setup = (size_t)NCAND * X::NR * 16, idx = (size_t)NCAND * 16, res = (size_t)NCAND * X::NR * X::NLSB * 16;
-    static constexpr size_t per_block = setup + idx + res;
+    static constexpr size_t perm = X::NR > 1 ? (size_t)NCAND * X::NR * 4 : 0;
+    static constexpr size_t per_block = setup + idx + res + perm;
 };
+static constexpr size_t kBc7CounterBytes = 8 * 256;  // one 256-byte counter record per mode
 static constexpr size_t kBc7ChunkBytesPerBlock = 256 + Bc7ModeBytes<0, 4>::per_block + Bc7ModeBytes<1, 16>::per_block + Bc7ModeBytes<2, 16>::per_block +
                                                  Bc7ModeBytes<3, 16>::per_block + Bc7ModeBytes<4, 8>::per_block + Bc7ModeBytes<5, 4>::per_block +
                                                  Bc7ModeBytes<6, 1>::per_block + Bc7ModeBytes<7, 16>::per_block;
 
-template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, double units) {
+template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, unsigned *counters, double units) {
     using X = Bc7X<M>;
     using B = Bc7ModeBytes<M, NCAND>;
     const int n = S.nblk;
     S.setup = (uint4 *)arena;
     S.setup_idx = (uint4 *)(arena + B::setup * NVB_BC7_CHUNK);
     S.res = (uint4 *)(arena + (B::setup + B::idx) * NVB_BC7_CHUNK);
+    S.perm = B::perm ? (unsigned *)(arena + (B::setup + B::idx + B::res) * NVB_BC7_CHUNK) : nullptr;
+    S.counters = counters + M * 64;
     arena += B::per_block * NVB_BC7_CHUNK;
     cudaStream_t st = ctx->mode_stream[M];
     cudaStreamWaitEvent(st, ctx->ev_fork, 0);
+    cudaMemsetAsync(S.counters, 0, NVB_BX_COUNTERS * sizeof(unsigned), st);
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
         NVB_LAUNCH_ON(ctx, st, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(n, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, S.P, S.blk0, S.blk0 + n);
     const unsigned cgrid = (unsigned)(((size_t)n * NCAND + 127) / 128);
     NVB_LAUNCH_ON(ctx, st, K_BC7_SETUP, units, (k_bc7_setup<M, NCAND>), cgrid, 128, S);
-    // searchers: grid-stride, at most 16 CTAs per SM's worth of threads so that every thread walks several searchers
+    if constexpr (X::NR > 1) {
+        const unsigned ogrid = (unsigned)(((size_t)n * NCAND * X::NR + 255) / 256);
+        NVB_LAUNCH_ON(ctx, st, K_BC7_ORDER, units, (k_bc7_order<M, NCAND, 0>), ogrid, 256, S);
+        NVB_LAUNCH_ON(ctx, st, K_BC7_ORDER, units, (k_bc7_order<M, NCAND, 1>), ogrid, 256, S);
+    }
+    // searchers are handed out dynamically; at least ~4 per thread, at most what the GPU can hold
     const size_t searchers = (size_t)n * (X::SPLIT ? 4 : NCAND * X::NR * X::NLSB);
-    size_t sgrid = (searchers + 127) / 128;
-    if (sgrid > 148u * 16u) sgrid = 148u * 16u;
+    size_t sgrid = (searchers / 4 + 127) / 128;
+    if (sgrid > 148u * 6u) sgrid = 148u * 6u;
+    if (sgrid < 1) sgrid = 1;
     NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 0>), (unsigned)sgrid, 128, S);
-    if constexpr (M == 4) NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 1>), (unsigned)sgrid, 128, S);
+    if constexpr (M == 4) {
+        cudaMemsetAsync(S.counters, 0, sizeof(unsigned), st);
+        NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 1>), (unsigned)sgrid, 128, S);
+    }
     NVB_LAUNCH_ON(ctx, st, K_BC7_FINISH, units, (k_bc7_finish<M, NCAND>), cgrid, 128, S);
     cudaEventRecord(ctx->ev_join[M], st);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join[M], 0);
@@ -615,7 +629,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         // scratch per block of the level: 5 x 16 shape bytes, 8 x 16 candidate bytes, 8 errors; per block of a chunk: the
         // texel tile and the setup / result records of every searcher (Bc7ModeBytes)
         const size_t chunk_cap = nb < NVB_BC7_CHUNK ? (size_t)nb : (size_t)NVB_BC7_CHUNK;
-        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32) + (size_t)NVB_BC7_CHUNK * kBc7ChunkBytesPerBlock);
+        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32) + 16 + kBc7CounterBytes + (size_t)NVB_BC7_CHUNK * kBc7ChunkBytesPerBlock);
         (void)chunk_cap;
         if (rc != NVTTB_OK) return rc;
         Bc7Params P;
@@ -626,6 +640,8 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.cand_err = (float *)(P.shapes + (size_t)nb * 208);
         unsigned char *chunk_base = P.shapes + (size_t)nb * 240;
         chunk_base += (16 - ((size_t)chunk_base & 15)) & 15;
+        unsigned *counters = (unsigned *)chunk_base;
+        chunk_base += kBc7CounterBytes;
         const double units = (double)w * h;
         for (int blk0 = 0; blk0 < nb; blk0 += NVB_BC7_CHUNK) {
             Bc7SearchParams S;
@@ -635,19 +651,20 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
             float4 *tiles = (float4 *)chunk_base;
             S.tiles = tiles;
             S.setup = S.setup_idx = S.res = nullptr;
+            S.perm = S.counters = nullptr;
             unsigned char *arena = chunk_base + (size_t)NVB_BC7_CHUNK * 256;
             const double cu = units * S.nblk / nb;
             // the previous chunk's mode streams have all been joined into ctx->stream, so the arena can be reused
             NVB_LAUNCH(ctx, K_BC7_TILES, cu, k_bc7_tiles, (unsigned)((S.nblk * 16 + 255) / 256), 256, S, tiles);
             CK(cudaEventRecord(ctx->ev_fork, ctx->stream));  // level, scratch and tiles are ready at this point of ctx->stream
-            launch_bc7_mode<3, 16>(ctx, S, arena, cu);       // the longest searches first
-            launch_bc7_mode<7, 16>(ctx, S, arena, cu);
-            launch_bc7_mode<1, 16>(ctx, S, arena, cu);
-            launch_bc7_mode<6, 1>(ctx, S, arena, cu);
-            launch_bc7_mode<0, 4>(ctx, S, arena, cu);
-            launch_bc7_mode<2, 16>(ctx, S, arena, cu);
-            launch_bc7_mode<4, 8>(ctx, S, arena, cu);
-            launch_bc7_mode<5, 4>(ctx, S, arena, cu);
+            launch_bc7_mode<6, 1>(ctx, S, arena, counters, cu);  // few, very long searches: start them first
+            launch_bc7_mode<3, 16>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<7, 16>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<1, 16>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<0, 4>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<2, 16>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<4, 8>(ctx, S, arena, counters, cu);
+            launch_bc7_mode<5, 4>(ctx, S, arena, counters, cu);
         }
         NVB_LAUNCH(ctx, K_BC7_SELECT, units, k_bc7_select, grid_for(nb, 256), 256, P);
     }

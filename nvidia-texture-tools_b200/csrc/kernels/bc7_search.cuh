@@ -22,6 +22,10 @@
 #pragma once
 #include "bc7.cuh"
 
+#ifdef NVB_EMU_STATS
+void emu_bx_stat(int mode, int np, int trials, int iters);
+#endif
+
 namespace nvb {
 
 struct Bc7SearchParams {
@@ -31,7 +35,10 @@ struct Bc7SearchParams {
     uint4 *setup;          // [nblk][NCAND][NR]          {A, B, lsbs, error bits}
     uint4 *setup_idx;      // [nblk][NCAND]              indices of the start endpoints after the anchor swap, 4 bits per texel
     uint4 *res;            // [nblk][NCAND][NR][NLSB]    {A, B, lsbs, error bits}
+    unsigned *perm;        // [nblk][NCAND][NR] (candidate, region) entries ordered by texel count; null = identity
+    unsigned *counters;    // [0] next searcher to hand out, [1..17] texel-count histogram, [18..34] scatter cursors
 };
+#define NVB_BX_COUNTERS 40
 
 // ---- compile-time view shared by the six single-index modes and the two split modes -------------------------------------
 template <int M, bool SPLIT = (M == 4 || M == 5)> struct Bc7X;
@@ -85,9 +92,9 @@ template <int NIDX> NVB_DEV void bx_lerp_row(int a, int b, float *out, int strid
         bj = upd_ ? (j) : bj;                      \
     }
 
-// map_colors of modes 0,1,2,3,6,7 for one trial: texels `members` (4-bit texel numbers, np of them) of tile
-template <int M> NVB_DEV float bx_eval(const float4 *__restrict__ tile, unsigned long long members, int np, unsigned A, unsigned B, int la, int lb,
-                                       Bc7Idx<false> &idx) {
+// map_colors of modes 0,1,2,3,6,7 for one trial over the np texels of the region (px: this thread's shared-memory slot;
+// for the RGB modes px[i].w already holds (alpha - 255)^2)
+template <int M> NVB_DEV float bx_eval(const float4 *px, int np, unsigned A, unsigned B, int la, int lb, Bc7Idx<false> &idx) {
     using C = Bc7Cfg<M>;
     constexpr int N = C::NIDX;
     float pal[C::NCH][N];
@@ -107,13 +114,8 @@ template <int M> NVB_DEV float bx_eval(const float4 *__restrict__ tile, unsigned
     float tot = 0;
     unsigned long long id = 0;
     for (int i = 0; i < np; ++i) {
-        const int t = (int)(members >> (4 * i)) & 15;
-        const float4 c = __ldg(tile + t);
-        float ww = 0;
-        if (C::NCH == 3) {
-            const float w = c.w - 255.0f;
-            ww = w * w;
-        }
+        const float4 c = px[i];
+        const float ww = c.w;
         float best = 0;
         int bj = 0;
         bool live = true;
@@ -131,14 +133,14 @@ template <int M> NVB_DEV float bx_eval(const float4 *__restrict__ tile, unsigned
             else NVB_BX_SCAN_STEP(e, j)
         }
         tot += best;
-        id |= (unsigned long long)bj << (4 * i);
+        id = (id << 4) | (unsigned long long)bj;  // only ever compared for equality
     }
     idx.lo = id;
     return tot;
 }
 
 // map_colors of modes 4,5 for one trial (all 16 texels; rotation applied to the texel as it is read)
-template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *__restrict__ tile, int rot, unsigned A, unsigned B, Bc7Idx<true> &idx) {
+template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *px, int rot, unsigned A, unsigned B, Bc7Idx<true> &idx) {
     constexpr int NRGB = (M == 5) ? 4 : (IM == 1 ? 8 : 4), NA = (M == 5) ? 4 : (IM == 1 ? 4 : 8);
     float prgb[3][NRGB], pa[NA];
 #pragma unroll
@@ -148,15 +150,7 @@ template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *__restrict__ 
     float tot = 0;
     unsigned long long irgb = 0, ia = 0;
     for (int i = 0; i < 16; ++i) {
-        float4 c = __ldg(tile + i);
-        {
-            // AGBR / RABG / RGAB: swap channel rot-1 with alpha
-            const float w0 = c.w;
-            c.w = rot == 1 ? c.x : rot == 2 ? c.y : rot == 3 ? c.z : c.w;
-            c.x = rot == 1 ? w0 : c.x;
-            c.y = rot == 2 ? w0 : c.y;
-            c.z = rot == 3 ? w0 : c.z;
-        }
+        const float4 c = px[i];  // already rotated
         float ea, er;
         int ja, jr;
         {
@@ -190,8 +184,8 @@ template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *__restrict__ 
         const float e1 = rot == 0 ? ea : er, e2 = rot == 0 ? er : ea;
         tot += e1;
         tot += e2;
-        irgb |= (unsigned long long)jr << (4 * i);
-        ia |= (unsigned long long)ja << (4 * i);
+        irgb = (irgb << 4) | (unsigned long long)jr;
+        ia = (ia << 4) | (unsigned long long)ja;
     }
     idx.lo = irgb;
     idx.hi = ia;
@@ -209,8 +203,10 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
     using X = Bc7X<M>;
     using Idx = Bc7Idx<X::SPLIT>;
     constexpr int NCAND_SPLIT = 4 * (M == 4 ? 2 : 1);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // this thread's texels: 16 float4 + 1 of padding, so that the 128-bit reads of 8 adjacent lanes hit 32 different banks
+    __shared__ float4 s_px[128 * 17];
+    float4 *px = s_px + threadIdx.x * 17;
+    long long s = 0;
     long long total;
     int ncand = 1;
     if constexpr (X::SPLIT) total = (long long)S.nblk * 4;
@@ -222,8 +218,6 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
 
     // searcher state
     int phase = BXP_LOAD;
-    const float4 *tile = S.tiles;
-    unsigned long long members = 0;
     int np = 0, rot = 0;
     long long slot = 0;          // where the result goes
     unsigned A = 0, B = 0;       // current best endpoints ("opt"), 8 bits per channel
@@ -244,12 +238,21 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
     int eo = 0, ei = 0, ta = 0, tb = 0, amin = 0, bmin = 0;
     pidx.clear(); t0.clear(); orig_idx.clear(); new_idx.clear();
 
+#ifdef NVB_EMU_STATS
+    int st_trials = 0, st_iters = 0;
+#endif
     for (;;) {
         unsigned tA = 0, tB = 0;
         bool have = false;
         while (!have && phase != BXP_EXIT) {
+#ifdef NVB_EMU_STATS
+            ++st_iters;
+#endif
             switch (phase) {
             case BXP_LOAD: {
+                // searchers are handed out one at a time: the searches differ a lot in length (every improvement restarts
+                // the channel loop), a static assignment would leave most lanes of a warp waiting for the longest one
+                s = (long long)atomicAdd(S.counters, 1u);
                 if (s >= total) {
                     phase = BXP_EXIT;
                     break;
@@ -260,29 +263,41 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                     rot = (int)(s & 3);
                     slot = (long long)blk * NCAND_SPLIT + rot * (M == 4 ? 2 : 1) + IM;
                     su = S.setup[slot];
-                    tile = S.tiles + (size_t)blk * 16;
+                    const float4 *tile = S.tiles + (size_t)blk * 16;
                     np = 16;
                     la = lb = 0;
+                    for (int i = 0; i < 16; i++) {
+                        float4 c = __ldg(tile + i);
+                        // AGBR / RABG / RGAB: swap channel rot-1 with alpha
+                        const float w0 = c.w;
+                        c.w = rot == 1 ? c.x : rot == 2 ? c.y : rot == 3 ? c.z : c.w;
+                        c.x = rot == 1 ? w0 : c.x;
+                        c.y = rot == 2 ? w0 : c.y;
+                        c.z = rot == 3 ? w0 : c.z;
+                        px[i] = c;
+                    }
                 } else {
                     using C = Bc7Cfg<M>;
-                    long long q = s;
-                    const int lsbmode = (int)(q % X::NLSB);
-                    q /= X::NLSB;
-                    const int region = (int)(q % X::NR);
-                    q /= X::NR;
-                    const int cand = (int)(q % ncand);
-                    const int blk = (int)(q / ncand);
-                    slot = s;
-                    su = S.setup[((size_t)blk * ncand + cand) * X::NR + region];
-                    tile = S.tiles + (size_t)blk * 16;
+                    const int lsbmode = (int)(s % X::NLSB);
+                    const long long q = s / X::NLSB;
+                    const unsigned e = S.perm ? S.perm[q] : (unsigned)q;
+                    const int region = (int)(e % X::NR);
+                    const int cand = (int)((e / X::NR) % ncand);
+                    const int blk = (int)(e / (X::NR * ncand));
+                    slot = (long long)e * X::NLSB + lsbmode;
+                    su = S.setup[e];
+                    const float4 *tile = S.tiles + (size_t)blk * 16;
                     int shape = 0;
                     if constexpr (C::NSH > 1) shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + cand];
-                    members = 0;
                     np = 0;
                     for (int i = 0; i < 16; i++)
                         if (bc7_region<C::NR>(shape, i) == region) {
-                            members |= (unsigned long long)i << (4 * np);
-                            ++np;
+                            float4 c = __ldg(tile + i);
+                            if (C::NCH == 3) {
+                                const float w = c.w - 255.0f;  // the palette's alpha is 255 in the RGB modes
+                                c.w = w * w;
+                            }
+                            px[np++] = c;
                         }
                     la = lsbmode & 1;
                     lb = (X::LSB == 2) ? (lsbmode >> 1) & 1 : 0;
@@ -471,22 +486,34 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
             }
             case BXP_STORE:
                 S.res[slot] = make_uint4(A, B, (unsigned)(la | (lb << 1)), __float_as_uint(opt_err));
-                s += stride;
+#ifdef NVB_EMU_STATS
+                emu_bx_stat(M, np, st_trials, st_iters);
+                st_trials = st_iters = 0;
+#endif
                 phase = BXP_LOAD;
                 break;
             default:
                 break;
             }
         }
-        if (phase == BXP_EXIT) break;
+        // Every lane of the warp stays in the loop until the last one has run out of work (idle lanes carry np = 0), so the
+        // vote below is executed by all 32 lanes: it is the explicit reconvergence point in front of the trial evaluation.
+        // (Without it ptxas treats the hand-out loop as a possible spin loop and lets the warp run on in pieces.)
+        if (__all_sync(0xffffffffu, phase == BXP_EXIT)) break;
+        if (phase == BXP_EXIT) np = 0;
 
+#ifdef NVB_EMU_STATS
+        ++st_trials;
+#endif
         // ---- the one expensive step: every live lane of the warp is here together ----
         Idx ti;
         float err;
-        if constexpr (X::SPLIT) err = bx_eval_split<M, IM>(tile, rot, tA, tB, ti);
-        else err = bx_eval<M>(tile, members, np, tA, tB, la, lb, ti);
+        if constexpr (X::SPLIT) err = bx_eval_split<M, IM>(px, rot, tA, tB, ti);
+        else err = bx_eval<M>(px, np, tA, tB, la, lb, ti);
 
-        if (phase == BXP_INIT_WAIT) {
+        if (phase == BXP_EXIT) {
+            // idle lane
+        } else if (phase == BXP_INIT_WAIT) {
             opt_err = err;
             ch = 0;
             phase = BXP_CH_START;
@@ -515,6 +542,40 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
             }
             phase = BXP_EXH_EMIT;
         }
+    }
+}
+
+// ---- order the (candidate, region) entries of a chunk by texel count -----------------------------------------------------------
+// Lanes of a warp walk the texels of their regions in lock step; a warp whose regions have 3 and 13 texels runs 13 steps
+// with most lanes idle.  Searchers are therefore handed out in order of texel count (counting sort, two passes).
+template <int M, int NCAND, int PASS> __global__ void __launch_bounds__(256) k_bc7_order(Bc7SearchParams S) {
+    using C = Bc7Cfg<M>;
+    __shared__ unsigned s_hist[17], s_base[17];
+    const int nblocks = S.P.lv.bw * S.P.lv.bh;
+    const unsigned total = (unsigned)S.nblk * NCAND * C::NR;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < 17) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    int np = 0;
+    unsigned rank = 0;
+    if (e < total) {
+        const int region = (int)(e % C::NR), cand = (int)((e / C::NR) % NCAND), blk = (int)(e / (C::NR * NCAND));
+        const int shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + cand];
+        np = __popc(bc7_member_mask<C::NR>(shape, region));
+        rank = atomicAdd(&s_hist[np], 1u);
+    }
+    __syncthreads();
+    unsigned *hist = S.counters + 1, *cursor = S.counters + 18;
+    if (PASS == 0) {
+        if (threadIdx.x < 17 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+    } else {
+        if (threadIdx.x < 17) {
+            unsigned off = 0;
+            for (int k = 0; k < (int)threadIdx.x; k++) off += hist[k];
+            s_base[threadIdx.x] = off + (s_hist[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_hist[threadIdx.x]) : 0u);
+        }
+        __syncthreads();
+        if (e < total) S.perm[s_base[np] + rank] = e;
     }
 }
 

@@ -73,12 +73,22 @@ template <int M, int NCAND> static void emu_bc7_mode(Bc7Params &P, int nb) {
         std::vector<float4> tiles((size_t)n * 16);
         std::vector<uint4> setup((size_t)n * NCAND * X::NR), sidx((size_t)n * NCAND), res((size_t)n * NCAND * X::NR * X::NLSB);
         Bc7SearchParams S;
+        std::vector<unsigned> perm((size_t)n * NCAND * X::NR), counters(NVB_BX_COUNTERS, 0);
         S.P = P; S.blk0 = blk0; S.nblk = n; S.tiles = tiles.data(); S.setup = setup.data(); S.setup_idx = sidx.data(); S.res = res.data();
+        S.perm = X::NR > 1 ? perm.data() : nullptr; S.counters = counters.data();
         emu::launch(dim3((n * 16 + 255) / 256), dim3(256), 0, [&] { k_bc7_tiles(S, tiles.data()); });
         emu::launch(dim3((n * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_setup<M, NCAND>(S); });
+        if constexpr (X::NR > 1) {
+            const int og = (n * NCAND * X::NR + 255) / 256;
+            emu::launch(dim3(og), dim3(256), 0, [&] { k_bc7_order<M, NCAND, 0>(S); });
+            emu::launch(dim3(og), dim3(256), 0, [&] { k_bc7_order<M, NCAND, 1>(S); });
+        }
         const int grid = 3;  // few threads: every thread walks several searchers
         emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 0>(S); });
-        if constexpr (M == 4) emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 1>(S); });
+        if constexpr (M == 4) {
+            counters[0] = 0;
+            emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 1>(S); });
+        }
         emu::launch(dim3((n * NCAND + 127) / 128), dim3(128), 0, [&] { k_bc7_finish<M, NCAND>(S); });
         blk0 += n;
     }
