@@ -241,9 +241,56 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
 #ifdef NVB_EMU_STATS
     int st_trials = 0, st_iters = 0;
 #endif
+    // next step of perturb_one's (step, sign) walk
+#define NVB_BX_ADV_SIGN()                  \
+    {                                      \
+        if (sgn < 0) {                     \
+            sgn = 1;                       \
+        } else {                           \
+            if (improved) pv += beststep;  \
+            improved = false;              \
+            step >>= 1;                    \
+            sgn = -1;                      \
+        }                                  \
+    }
+    // the trial of the current (step, sign), or — out of range — on to the next one
+#define NVB_BX_TRY_PERT()                                  \
+    {                                                      \
+        const int v_ = pv + sgn * step;                    \
+        if (v_ >= 0 && v_ < (1 << X::prec(ch))) {          \
+            tA = do_b ? A : bx_set(A, ch, v_);             \
+            tB = do_b ? bx_set(B, ch, v_) : B;             \
+            phase = BXP_PERT_WAIT;                         \
+            have = true;                                   \
+        } else                                             \
+            NVB_BX_ADV_SIGN()                              \
+    }
+    // the trial under exhaustive()'s cursor, and the cursor moved on
+#define NVB_BX_EXH_EMIT()                                                                                             \
+    {                                                                                                                 \
+        const int prec_ = X::prec(ch), A0_ = bx_get(A, ch), B0_ = bx_get(B, ch);                                      \
+        const int alow_ = max(0, A0_ - 3), ahigh_ = min((1 << prec_) - 1, A0_ + 3);                                   \
+        const int blow_ = max(0, B0_ - 3), bhigh_ = min((1 << prec_) - 1, B0_ + 3);                                   \
+        const bool a_le_b_ = A0_ <= B0_;                                                                              \
+        const int o_end_ = a_le_b_ ? ahigh_ : bhigh_ - 1, i_end_ = a_le_b_ ? bhigh_ - 1 : ahigh_, lowi_ = a_le_b_ ? blow_ : alow_; \
+        ta = a_le_b_ ? eo : ei;                                                                                       \
+        tb = a_le_b_ ? ei : eo;                                                                                       \
+        tA = bx_set(A, ch, ta);                                                                                       \
+        tB = bx_set(B, ch, tb);                                                                                       \
+        ++ei;                                                                                                         \
+        while (!exh_done && ei > i_end_) {                                                                            \
+            ++eo;                                                                                                     \
+            if (eo > o_end_) exh_done = true;                                                                         \
+            else ei = max(eo, lowi_);                                                                                 \
+        }                                                                                                             \
+        phase = BXP_EXH_WAIT;                                                                                         \
+        have = true;                                                                                                  \
+    }
+
+    unsigned tA = 0, tB = 0;
+    bool have = false;
     for (;;) {
-        unsigned tA = 0, tB = 0;
-        bool have = false;
+        // slow path: lanes whose next trial is not simply the next step of the running perturb_one / exhaustive walk
         while (!have && phase != BXP_EXIT) {
 #ifdef NVB_EMU_STATS
             ++st_iters;
@@ -331,29 +378,14 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                     sgn = -1;
                     improved = false;
                     phase = BXP_PERT_EMIT;
+                    NVB_BX_TRY_PERT()  // the first step is half the range: exactly one of -step / +step is in range
+                    if (!have) NVB_BX_TRY_PERT()
                 }
                 break;
-            case BXP_PERT_EMIT: {
-                if (step == 0) {
-                    phase = BXP_PERT_FIN;
-                    break;
-                }
-                const int v = pv + sgn * step;
-                if (v >= 0 && v < (1 << X::prec(ch))) {
-                    tA = do_b ? A : bx_set(A, ch, v);
-                    tB = do_b ? bx_set(B, ch, v) : B;
-                    phase = BXP_PERT_WAIT;
-                    have = true;
-                } else if (sgn < 0) {
-                    sgn = 1;
-                } else {
-                    if (improved) pv += beststep;
-                    improved = false;
-                    step >>= 1;
-                    sgn = -1;
-                }
+            case BXP_PERT_EMIT:
+                if (step == 0) phase = BXP_PERT_FIN;
+                else NVB_BX_TRY_PERT()
                 break;
-            }
             case BXP_PERT_FIN: {
                 bool again = false;  // start another perturb_one on endpoint do_b
                 if (pk == 0) {
@@ -408,6 +440,8 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                     sgn = -1;
                     improved = false;
                     phase = BXP_PERT_EMIT;
+                    NVB_BX_TRY_PERT()
+                    if (!have) NVB_BX_TRY_PERT()
                 }
                 break;
             }
@@ -435,33 +469,14 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                     if (eo > o_end) exh_done = true;
                     else ei = max(eo, lowi);
                 }
-                phase = BXP_EXH_EMIT;
+                phase = BXP_EXH_CH_END;
+                if (!exh_done) NVB_BX_EXH_EMIT()
                 break;
             }
-            case BXP_EXH_EMIT: {
-                if (exh_done) {
-                    phase = BXP_EXH_CH_END;
-                    break;
-                }
-                const int prec = X::prec(ch), A0 = bx_get(A, ch), B0 = bx_get(B, ch);
-                const int alow = max(0, A0 - 3), ahigh = min((1 << prec) - 1, A0 + 3);
-                const int blow = max(0, B0 - 3), bhigh = min((1 << prec) - 1, B0 + 3);
-                const bool a_le_b = A0 <= B0;
-                const int o_end = a_le_b ? ahigh : bhigh - 1, i_end = a_le_b ? bhigh - 1 : ahigh, lowi = a_le_b ? blow : alow;
-                ta = a_le_b ? eo : ei;
-                tb = a_le_b ? ei : eo;
-                tA = bx_set(A, ch, ta);
-                tB = bx_set(B, ch, tb);
-                ++ei;
-                while (!exh_done && ei > i_end) {
-                    ++eo;
-                    if (eo > o_end) exh_done = true;
-                    else ei = max(eo, lowi);
-                }
-                phase = BXP_EXH_WAIT;
-                have = true;
+            case BXP_EXH_EMIT:
+                if (exh_done) phase = BXP_EXH_CH_END;
+                else NVB_BX_EXH_EMIT()
                 break;
-            }
             case BXP_EXH_CH_END: {
                 const float new_err = pmin;
                 if (pmin < exh_orig) {
@@ -511,6 +526,8 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
         if constexpr (X::SPLIT) err = bx_eval_split<M, IM>(px, rot, tA, tB, ti);
         else err = bx_eval<M>(px, np, tA, tB, la, lb, ti);
 
+        // consume the result and, on the common path, produce the next trial right here (all lanes together)
+        have = false;
         if (phase == BXP_EXIT) {
             // idle lane
         } else if (phase == BXP_INIT_WAIT) {
@@ -524,15 +541,11 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                 beststep = sgn * step;
                 pidx = ti;
             }
-            if (sgn < 0) {
-                sgn = 1;
-            } else {
-                if (improved) pv += beststep;
-                improved = false;
-                step >>= 1;
-                sgn = -1;
-            }
+            NVB_BX_ADV_SIGN()
             phase = BXP_PERT_EMIT;
+            if (step != 0) NVB_BX_TRY_PERT()
+            if (!have && step != 0) NVB_BX_TRY_PERT()
+            if (!have && step == 0) phase = BXP_PERT_FIN;
         } else {  // BXP_EXH_WAIT
             if (err < pmin) {
                 amin = ta;
@@ -540,9 +553,13 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
                 pmin = err;
                 pidx = ti;
             }
-            phase = BXP_EXH_EMIT;
+            phase = BXP_EXH_CH_END;
+            if (!exh_done) NVB_BX_EXH_EMIT()
         }
     }
+#undef NVB_BX_ADV_SIGN
+#undef NVB_BX_TRY_PERT
+#undef NVB_BX_EXH_EMIT
 }
 
 // ---- order the (candidate, region) entries of a chunk by texel count -----------------------------------------------------------
