@@ -65,7 +65,7 @@ struct NvttbContext {
     // BC7: the eight mode searches of a level are independent until the final select, so each runs on its own stream
     // (small levels cannot fill 148 SMs with one mode's candidates; together they do)
     cudaStream_t mode_stream[8] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+    cudaEvent_t ev_fork[2] = {}, ev_join[2][8] = {};  // [parity of the chunk]
     std::string err;
     uint64_t launches = 0;
     float *d_to_gamma = nullptr, *d_to_linear = nullptr;
@@ -203,9 +203,11 @@ int nvttb_context_create(int device, NvttbContext **out) {
     }
     for (int i = 0; i < 8; i++) {
         if ((e = cudaStreamCreateWithFlags(&ctx->mode_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-        if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        for (int p = 0; p < 2; p++)
+            if ((e = cudaEventCreateWithFlags(&ctx->ev_join[p][i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int p = 0; p < 2; p++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_fork[p], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     float tg[512], tl[512];
@@ -312,9 +314,11 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     }
     for (int i = 0; i < 8; i++) {
         if (ctx->mode_stream[i]) { cudaStreamSynchronize(ctx->mode_stream[i]); cudaStreamDestroy(ctx->mode_stream[i]); }
-        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+        for (int p = 0; p < 2; p++)
+            if (ctx->ev_join[p][i]) cudaEventDestroy(ctx->ev_join[p][i]);
     }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int p = 0; p < 2; p++)
+        if (ctx->ev_fork[p]) cudaEventDestroy(ctx->ev_fork[p]);
     if (ctx->ev_stage_free) cudaEventDestroy(ctx->ev_stage_free);
     if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
     cudaStreamDestroy(ctx->h2d_stream);
@@ -437,7 +441,7 @@ static constexpr size_t kBc7ChunkBytesPerBlock = 256 + Bc7ModeBytes<0, 4>::per_b
                                                  Bc7ModeBytes<3, 16>::per_block + Bc7ModeBytes<4, 8>::per_block + Bc7ModeBytes<5, 4>::per_block +
                                                  Bc7ModeBytes<6, 1>::per_block + Bc7ModeBytes<7, 16>::per_block;
 
-template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, unsigned *counters, double units) {
+template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, unsigned *counters, int parity, double units) {
     using X = Bc7X<M>;
     using B = Bc7ModeBytes<M, NCAND>;
     const int n = S.nblk;
@@ -448,7 +452,7 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
     S.counters = counters + M * 64;
     arena += B::per_block * NVB_BC7_CHUNK;
     cudaStream_t st = ctx->mode_stream[M];
-    cudaStreamWaitEvent(st, ctx->ev_fork, 0);
+    cudaStreamWaitEvent(st, ctx->ev_fork[parity], 0);
     cudaMemsetAsync(S.counters, 0, NVB_BX_COUNTERS * sizeof(unsigned), st);
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
         NVB_LAUNCH_ON(ctx, st, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(n, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, S.P, S.blk0, S.blk0 + n);
@@ -470,8 +474,7 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
         NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 1>), (unsigned)sgrid, 128, S);
     }
     NVB_LAUNCH_ON(ctx, st, K_BC7_FINISH, units, (k_bc7_finish<M, NCAND>), cgrid, 128, S);
-    cudaEventRecord(ctx->ev_join[M], st);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join[M], 0);
+    cudaEventRecord(ctx->ev_join[parity][M], st);
 }
 
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
@@ -628,9 +631,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     else if (d->format == F_BC7) {
         // scratch per block of the level: 5 x 16 shape bytes, 8 x 16 candidate bytes, 8 errors; per block of a chunk: the
         // texel tile and the setup / result records of every searcher (Bc7ModeBytes)
-        const size_t chunk_cap = nb < NVB_BC7_CHUNK ? (size_t)nb : (size_t)NVB_BC7_CHUNK;
-        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32) + 16 + kBc7CounterBytes + (size_t)NVB_BC7_CHUNK * kBc7ChunkBytesPerBlock);
-        (void)chunk_cap;
+        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32) + 16 + kBc7CounterBytes + (size_t)NVB_BC7_CHUNK * (kBc7ChunkBytesPerBlock + 256));
         if (rc != NVTTB_OK) return rc;
         Bc7Params P;
         P.lv = lv;
@@ -643,29 +644,36 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         unsigned *counters = (unsigned *)chunk_base;
         chunk_base += kBc7CounterBytes;
         const double units = (double)w * h;
-        for (int blk0 = 0; blk0 < nb; blk0 += NVB_BC7_CHUNK) {
+        // Chunks of the level flow through the eight mode streams back to back.  A mode's records are only touched by its own
+        // stream; the texel tiles are shared by all modes, so there are two tile buffers and chunk c+2 waits for chunk c.
+        int nchunks = 0;
+        for (int blk0 = 0; blk0 < nb; blk0 += NVB_BC7_CHUNK, ++nchunks) {
+            const int parity = nchunks & 1;
             Bc7SearchParams S;
             S.P = P;
             S.blk0 = blk0;
             S.nblk = nb - blk0 < NVB_BC7_CHUNK ? nb - blk0 : NVB_BC7_CHUNK;
-            float4 *tiles = (float4 *)chunk_base;
+            float4 *tiles = (float4 *)(chunk_base + (size_t)parity * NVB_BC7_CHUNK * 256);
             S.tiles = tiles;
             S.setup = S.setup_idx = S.res = nullptr;
             S.perm = S.counters = nullptr;
-            unsigned char *arena = chunk_base + (size_t)NVB_BC7_CHUNK * 256;
+            unsigned char *arena = chunk_base + (size_t)2 * NVB_BC7_CHUNK * 256;
             const double cu = units * S.nblk / nb;
-            // the previous chunk's mode streams have all been joined into ctx->stream, so the arena can be reused
+            if (nchunks >= 2)
+                for (int m = 0; m < 8; m++) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[parity][m], 0));
             NVB_LAUNCH(ctx, K_BC7_TILES, cu, k_bc7_tiles, (unsigned)((S.nblk * 16 + 255) / 256), 256, S, tiles);
-            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));  // level, scratch and tiles are ready at this point of ctx->stream
-            launch_bc7_mode<6, 1>(ctx, S, arena, counters, cu);  // few, very long searches: start them first
-            launch_bc7_mode<3, 16>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<7, 16>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<1, 16>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<0, 4>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<2, 16>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<4, 8>(ctx, S, arena, counters, cu);
-            launch_bc7_mode<5, 4>(ctx, S, arena, counters, cu);
+            CK(cudaEventRecord(ctx->ev_fork[parity], ctx->stream));  // level, scratch and tiles are ready at this point of ctx->stream
+            launch_bc7_mode<6, 1>(ctx, S, arena, counters, parity, cu);  // few, very long searches: start them first
+            launch_bc7_mode<3, 16>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<7, 16>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<1, 16>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<0, 4>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<2, 16>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<4, 8>(ctx, S, arena, counters, parity, cu);
+            launch_bc7_mode<5, 4>(ctx, S, arena, counters, parity, cu);
         }
+        // join: the last chunk of every mode stream (stream order covers the earlier ones)
+        for (int m = 0; m < 8; m++) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[(nchunks - 1) & 1][m], 0));
         NVB_LAUNCH(ctx, K_BC7_SELECT, units, k_bc7_select, grid_for(nb, 256), 256, P);
     }
     CK(cudaGetLastError());
