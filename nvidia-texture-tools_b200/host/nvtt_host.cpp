@@ -464,9 +464,46 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
         return false;
     }
     if (!oo.outputHeader) return true;
-    if (oo.container == Container_KTX) {  // KTX writer: SURVEY §8(f), not on the hot path yet
-        oo.error(Error_UnsupportedOutputFormat);
-        return false;
+    if (oo.container == Container_KTX) {
+        // KtxHeader (src/nvimage/KtxFile.h:113-131, KtxFile.cpp:17-34) as filled in by Context.cpp:870-1035
+        struct KtxHeaderBytes {
+            uint8_t identifier[12];
+            uint32_t endianness, glType, glTypeSize, glFormat, glInternalFormat, glBaseInternalFormat;
+            uint32_t pixelWidth, pixelHeight, pixelDepth, numberOfArrayElements, numberOfFaces, numberOfMipmapLevels, bytesOfKeyValueData;
+        } kh;
+        static_assert(sizeof(KtxHeaderBytes) == 64, "KTX header is 64 bytes");
+        static const uint8_t ident[12] = {0xAB, 0x4B, 0x54, 0x58, 0x20, 0x31, 0x31, 0xBB, 0x0D, 0x0A, 0x1A, 0x0A};
+        memset(&kh, 0, sizeof kh);
+        memcpy(kh.identifier, ident, 12);
+        kh.endianness = 0x04030201;
+        kh.glType = 0;
+        kh.glTypeSize = 1;
+        kh.glFormat = 0;
+        kh.numberOfFaces = 1;
+        if (textureType == TextureType_Cube) kh.numberOfFaces = 6;
+        else if (textureType == TextureType_3D) kh.pixelDepth = d;
+        else if (textureType == TextureType_Array) kh.numberOfArrayElements = arraySize;
+        kh.pixelWidth = w;
+        kh.pixelHeight = h;
+        kh.numberOfMipmapLevels = mipmapCount;
+        const Format f = co.format;
+        bool supported = true;
+        if (f == Format_DXT1 || f == Format_DXT1n) { kh.glInternalFormat = oo.srgb ? 0x8C4C : 0x83F0; kh.glBaseInternalFormat = 0x1907; }
+        else if (f == Format_DXT1a) { kh.glInternalFormat = oo.srgb ? 0x8C4D : 0x83F1; kh.glBaseInternalFormat = 0x1908; }
+        else if (f == Format_DXT3) { kh.glInternalFormat = oo.srgb ? 0x8C4E : 0x83F2; kh.glBaseInternalFormat = 0x1908; }
+        else if (f == Format_DXT5 || f == Format_DXT5n || f == Format_BC3_RGBM) { kh.glInternalFormat = oo.srgb ? 0x8C4F : 0x83F3; kh.glBaseInternalFormat = 0x1908; }
+        else if (f == Format_BC4) { kh.glInternalFormat = 0x8DBB; kh.glBaseInternalFormat = 0x1903; }
+        else if (f == Format_BC5) { kh.glInternalFormat = 0x8DBD; kh.glBaseInternalFormat = 0x8227; }
+        else if (f == Format_BC6) { kh.glInternalFormat = (co.pixelType == PixelType_Float) ? 0x8E8E : 0x8E8F; kh.glBaseInternalFormat = 0x1907; }
+        else if (f == Format_BC7) { kh.glInternalFormat = oo.srgb ? 0x8E8D : 0x8E8C; kh.glBaseInternalFormat = 0x1908; }
+        else supported = false;  // RGBA / ETC / PVR: out of scope of this library
+        if (!supported) {
+            oo.error(Error_UnsupportedOutputFormat);
+            return false;
+        }
+        const bool ok = oo.writeData(&kh, 64);
+        if (!ok) oo.error(Error_FileWrite);
+        return ok;
     }
     DDSHeaderBytes hd;
     memset(&hd, 0, sizeof hd);
@@ -631,6 +668,66 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         if (io.images[f].empty()) { oo.error(Error_InvalidInput); return false; }
     bool userMips = false;
     for (int i = faceCount; i < io.imageCount; i++) userMips = userMips || !io.images[i].empty();
+
+    if (oo.container == Container_KTX) {
+        // KTX stores the faces of one mip level together: mip-major order, every level prefixed with its byte size
+        // (Context.cpp:347-472).  Kept quirks: the Kaiser parameters are passed as {stretch, alpha}, and normal-map mips
+        // are renormalised without the expand / pack pair of the DDS loop.
+        std::vector<Surface> images;
+        int w = width, h = height;
+        uint32_t imageSize = (uint32_t)estimateSize(w, h, 1, 1, compressionOptions) * faceCount;
+        oo.writeData(&imageSize, 4);
+        for (int f = 0; f < faceCount; f++) {
+            Surface s;
+            s.setWrapMode(io.wrapMode);
+            s.setAlphaMode(io.alphaMode);
+            s.setNormalMap(io.isNormalMap);
+            if (!s.setImage(io.inputFormat, io.width, io.height, 1, io.images[f].data())) { oo.error(Error_CudaError); return false; }
+            if (io.convertToNormalMap) {
+                s.toGreyScale(io.heightFactors[0], io.heightFactors[1], io.heightFactors[2], io.heightFactors[3]);
+                s.toNormalMap(io.bumpFrequencyScale[0], io.bumpFrequencyScale[1], io.bumpFrequencyScale[2], io.bumpFrequencyScale[3]);
+            }
+            if (!s.isNormalMap()) s.toLinear(io.inputGamma);
+            s.resize(w, h, 1, ResizeFilter_Box);
+            Surface tmp = s;
+            if (!s.isNormalMap()) tmp.toGamma(io.outputGamma);
+            if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
+            images.push_back(s);
+        }
+        static const unsigned char padding[3] = {0, 0, 0};
+        for (int mip = 1; mip < mipmapCount; mip++) {
+            w = imax(1, w / 2);
+            h = imax(1, h / 2);
+            imageSize = (uint32_t)estimateSize(w, h, 1, 1, compressionOptions) * faceCount;
+            oo.writeData(&imageSize, 4);
+            for (int f = 0; f < faceCount; f++) {
+                Surface &img = images[f];
+                const int idx = mip * faceCount + f;
+                // mipChainBroken[] is never set in the reference: a user-supplied level is used whenever it exists
+                if (idx < io.imageCount && !io.images[idx].empty()) {
+                    img.setImage(io.inputFormat, w, h, 1, io.images[idx].data());
+                    if (!img.isNormalMap()) img.toLinear(io.inputGamma);
+                } else if (io.mipmapFilter == MipmapFilter_Kaiser) {
+                    const float params[2] = {io.kaiserStretch, io.kaiserAlpha};
+                    img.buildNextMipmap(MipmapFilter_Kaiser, io.kaiserWidth, params);
+                } else {
+                    img.buildNextMipmap(io.mipmapFilter);
+                }
+                Surface tmp;
+                if (img.isNormalMap()) {
+                    if (io.normalizeMipmaps) img.normalizeNormalMap();
+                    tmp = img;
+                } else {
+                    tmp = img;
+                    tmp.toGamma(io.outputGamma);
+                }
+                if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
+            }
+            const int mipPadding = 3 - ((imageSize + 3) % 4);
+            if (mipPadding != 0) oo.writeData(padding, mipPadding);
+        }
+        return true;
+    }
 
     if (canUseSourceImages && !userMips) {
         // fused device pipeline

@@ -66,6 +66,11 @@ def test_process_with_header_identical(nvtt, ref, ours):
         (ref.Format_BC3, 1, s.photo_bgra8(128, 128, seed=2, alpha=True), dict(mip_filter=2)),
         (ref.Format_BC5, 1, s.normal_bgra8(64, 64), dict(mip_filter=2, normal_map=True)),
         (ref.Format_BC4, 1, s.photo_bgra8(37, 22, seed=3), dict(mip_filter=1, container=1)),
+        (ref.Format_BC7, 1, s.photo_bgra8(16, 12, seed=4, alpha=True), dict(mip_filter=0, container=1)),
+        # KTX: mip-major order with size words; Kaiser parameters swapped and pack-less renormalisation (reference quirks)
+        (ref.Format_BC1, 1, s.photo_bgra8(64, 32, seed=7), dict(mip_filter=0, container=2)),
+        (ref.Format_BC3, 1, s.photo_bgra8(40, 40, seed=8, alpha=True), dict(mip_filter=2, container=2)),
+        (ref.Format_BC5, 1, s.normal_bgra8(32, 32), dict(mip_filter=1, normal_map=True, container=2)),
     ]
     for fmt, q, img, kw in cases:
         h, w = img.shape[:2]
@@ -73,6 +78,14 @@ def test_process_with_header_identical(nvtt, ref, ours):
         want = _process(ref.lib(), ref, [img], fmt, q, w, h, **kw)
         assert got.size == want.size
         assert np.array_equal(got, want), (fmt, kw)
+
+
+def test_ktx_cube_identical(nvtt, ref, ours):
+    """Six faces through the KTX container: the faces of a level are stored together (Context.cpp:347-472)."""
+    faces = [nvtt.synth.photo_bgra8(32, 32, seed=20 + f) for f in range(6)]
+    got = _process(ours, ref, faces, ref.Format_BC1, 1, 32, 32, mip_filter=0, container=2, texture_type=1)
+    want = _process(ref.lib(), ref, faces, ref.Format_BC1, 1, 32, 32, mip_filter=0, container=2, texture_type=1)
+    assert got.size == want.size and np.array_equal(got, want)
 
 
 def test_raw_compress_and_surface_api_identical(nvtt, ref, ours):
