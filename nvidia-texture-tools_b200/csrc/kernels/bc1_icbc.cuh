@@ -525,31 +525,20 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
         }
         if (P.level == 9) {
             // ---- refine_endpoints (three_color_mode == true: no endpoint re-ordering) ----
+            // The reference walks up to 256 single-step endpoint moves one after the other and stops 33 candidates after the
+            // last accepted one.  Between two acceptances every candidate is measured against the same block and the same
+            // threshold, so 16 consecutive candidates are evaluated at once, one per lane (each lane sums its candidate's
+            // 16 texel errors in texel order), and the first improving one in candidate order is accepted.
             float best_error = error;
             int lastImprovement = 0;
             const float vcx = cx * P.cw[0], vcy = cy * P.cw[1], vcz = cz * P.cw[2];
+            __syncwarp(gm);
+            S.pts[l] = make_float4(cx, cy, cz, wt);
+            __syncwarp(gm);
+            int i = 0;
 #pragma unroll 1
-            for (int i = 0; i < 256; i++) {
-                // deltas[i % 16]
-                const int k = i & 15;
-                int dr, dg, db;
-                {
-                    // rows: (1,0,0)(0,1,0)(0,0,1)(-1,0,0)(0,-1,0)(0,0,-1)(1,1,0)(1,0,1)(0,1,1)(-1,-1,0)(-1,0,-1)(0,-1,-1)(-1,1,0)(1,-1,0)(0,-1,1)(0,1,-1)
-                    const signed char tr[16] = {1, 0, 0, -1, 0, 0, 1, 1, 0, -1, -1, 0, -1, 1, 0, 0};
-                    const signed char tg[16] = {0, 1, 0, 0, -1, 0, 1, 0, 1, -1, 0, -1, 1, -1, -1, 1};
-                    const signed char tb2[16] = {0, 0, 1, 0, 0, -1, 0, 1, 1, 0, -1, -1, 0, 0, 1, -1};
-                    dr = tr[k]; dg = tg[k]; db = tb2[k];
-                }
-                Bc1Block refined = out;
-                unsigned c = ((i / 16) & 1) ? refined.c0 : refined.c1;
-                {
-                    const unsigned r = (((c >> 11) & 31) + (unsigned)dr) & 31;
-                    const unsigned g = (((c >> 5) & 63) + (unsigned)dg) & 63;
-                    const unsigned b = ((c & 31) + (unsigned)db) & 31;
-                    c = (r << 11) | (g << 5) | b;
-                }
-                if ((i / 16) & 1) refined.c0 = c; else refined.c1 = c;
-                // indices from the palette of *output* (sic), general 4-way rule
+            for (;;) {
+                // indices from the palette of *output* (sic), general 4-way rule: they only change when `out` changes
                 const Pal3 pal = icbc_palette_f(out.c0, out.c1);
                 float d[4];
 #pragma unroll
@@ -558,14 +547,50 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
                 const bool i2 = (d[2] <= d[0]) && (d[2] <= d[1]) && (d[2] < d[3]);
                 const bool i3 = (d[3] <= d[0]) && (d[3] <= d[1]) && (d[3] <= d[2]);
                 const unsigned idx = ((i1 || i3) ? 1u : 0u) | ((i2 || i3) ? 2u : 0u);
-                refined.indices = group_gather_bits2(gm, idx, l);
-                const float refined_error = icbc_evaluate_block_mse(P, gm, l, refined, cx, cy, cz, wt);
-                if (refined_error < best_error) {
-                    best_error = refined_error;
-                    out = refined;
-                    lastImprovement = i;
+                const unsigned indices = group_gather_bits2(gm, idx, l);
+                for (;;) {
+                    const int limit = min(255, lastImprovement + 33);  // last candidate the sequential loop reaches
+                    const int ci = i + l;
+                    // deltas[ci % 16]
+                    // rows: (1,0,0)(0,1,0)(0,0,1)(-1,0,0)(0,-1,0)(0,0,-1)(1,1,0)(1,0,1)(0,1,1)(-1,-1,0)(-1,0,-1)(0,-1,-1)(-1,1,0)(1,-1,0)(0,-1,1)(0,1,-1)
+                    const int k = ci & 15;
+                    const int dr = (k == 0 || k == 6 || k == 7 || k == 13) ? 1 : (k == 3 || k == 9 || k == 10 || k == 12) ? -1 : 0;
+                    const int dg = (k == 1 || k == 6 || k == 8 || k == 12 || k == 15) ? 1 : (k == 4 || k == 9 || k == 11 || k == 13 || k == 14) ? -1 : 0;
+                    const int db = (k == 2 || k == 7 || k == 8 || k == 14) ? 1 : (k == 5 || k == 10 || k == 11 || k == 15) ? -1 : 0;
+                    unsigned c0 = out.c0, c1 = out.c1;
+                    {
+                        unsigned c = ((ci / 16) & 1) ? c0 : c1;
+                        const unsigned r = (((c >> 11) & 31) + (unsigned)dr) & 31;
+                        const unsigned g = (((c >> 5) & 63) + (unsigned)dg) & 63;
+                        const unsigned b = ((c & 31) + (unsigned)db) & 31;
+                        c = (r << 11) | (g << 5) | b;
+                        if ((ci / 16) & 1) c0 = c; else c1 = c;
+                    }
+                    // evaluate_mse of the candidate block, texel by texel in order
+                    const Pal3 rp = icbc_palette_f(c0, c1);
+                    float e = 0.0f;
+#pragma unroll 4
+                    for (int t = 0; t < 16; t++) {
+                        const float4 q = S.pts[t];
+                        const unsigned it = (indices >> (2 * t)) & 3u;
+                        e += q.w * mse_term(select4(rp.x, it), select4(rp.y, it), select4(rp.z, it), q.x, q.y, q.z, P.cw);
+                    }
+                    const bool better = (ci <= limit) && (e < best_error);
+                    const unsigned bm = (__ballot_sync(gm, better) >> gsh) & 0xFFFFu;
+                    if (bm) {
+                        const int wl = __ffs((int)bm) - 1;  // first improving candidate in order
+                        best_error = __shfl_sync(gm, e, wl, 16);
+                        out.c0 = __shfl_sync(gm, c0, wl, 16);
+                        out.c1 = __shfl_sync(gm, c1, wl, 16);
+                        out.indices = indices;
+                        lastImprovement = i + wl;
+                        i += wl + 1;
+                        break;  // `out` changed: new indices
+                    }
+                    i += 16;
+                    if (i > limit) break;
                 }
-                if (i - lastImprovement > 32) break;
+                if (i > min(255, lastImprovement + 33)) break;
             }
             error = best_error;
         }
