@@ -11,6 +11,7 @@
 #include "kernels/bc6h.cuh"
 #include "kernels/bc7.cuh"
 #include "kernels/bc7_search.cuh"
+#include "kernels/bc6h_search.cuh"
 #include "kernels/image_ops.cuh"
 
 #include <cuda_runtime.h>
@@ -42,8 +43,8 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_REFINE, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_refine", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
                                                   "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
 struct ProfRec {
     int kid;
@@ -463,9 +464,10 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
         NVB_LAUNCH_ON(ctx, st, K_BC7_ORDER, units, (k_bc7_order<M, NCAND, 0>), ogrid, 256, S);
         NVB_LAUNCH_ON(ctx, st, K_BC7_ORDER, units, (k_bc7_order<M, NCAND, 1>), ogrid, 256, S);
     }
-    // searchers are handed out dynamically; at least ~4 per thread, at most what the GPU can hold
+    // searchers are handed out dynamically; ~2 per thread on small levels (tuned on B200), at most what the GPU can hold
     const size_t searchers = (size_t)n * (X::SPLIT ? 4 : NCAND * X::NR * X::NLSB);
-    size_t sgrid = (searchers / 4 + 127) / 128;
+    static const int spt = getenv("NVB_BC7_SPT") ? atoi(getenv("NVB_BC7_SPT")) : 2;
+    size_t sgrid = (searchers / spt + 127) / 128;
     if (sgrid > 148u * 6u) sgrid = 148u * 6u;
     if (sgrid < 1) sgrid = 1;
     NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 0>), (unsigned)sgrid, 128, S);
@@ -611,8 +613,10 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         NVB_LAUNCH(ctx, K_BC3_COLOR, (double)w * h, k_bc3_color, (nb + NVB_BC3_GROUPS - 1) / NVB_BC3_GROUPS, NVB_BC3_GROUPS * 16, P);
     }
     else if (d->format == F_BC6) {
-        // scratch per block: 20 floats of rough endpoints, 2 candidate blocks, 2 errors
-        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 32 + 8));
+        // scratch per block: 20 floats of rough endpoints, 2 candidate blocks, 2 errors; then the searcher records:
+        // texel tile (256), meta (2 x 16), start endpoints (3 x 32), start indices (2 x 8), results (3 x 32), order (2 x 4)
+        const size_t per_block = 80 + 32 + 8 + 256 + 32 + 96 + 16 + 96 + 8;
+        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * per_block + 256 + 64);
         if (rc != NVTTB_OK) return rc;
         Bc6Params P;
         P.lv = lv;
@@ -620,13 +624,46 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         // ZOH::Utils::FORMAT: unsigned for PixelType_UnsignedFloat / UnsignedNorm / UnsignedInt (CompressorDX11.cpp:47-56)
         P.is_signed = !(d->pixelType == 5 || d->pixelType == 0 || d->pixelType == 2);
         P.transparency = (d->alphaMode == AM_Transparency);
-        P.rough = (float *)ctx->enc_scratch.p;
-        P.cand = (unsigned char *)ctx->enc_scratch.p + (size_t)nb * 80;
-        P.cand_err = (float *)((unsigned char *)ctx->enc_scratch.p + (size_t)nb * 112);
-        NVB_LAUNCH(ctx, K_BC6_ROUGH, (double)w * h, k_bc6_rough, grid_for(nb, NVB_BC6_ROUGH_WARPS), NVB_BC6_ROUGH_WARPS * 32, P);
+        unsigned char *base = (unsigned char *)ctx->enc_scratch.p;
+        Bc6SearchParams S;
+        float4 *tiles = (float4 *)base;               base += (size_t)nb * 256;
+        S.tiles = tiles;
+        S.meta = (int4 *)base;                        base += (size_t)nb * 32;
+        S.setup = (int4 *)base;                       base += (size_t)nb * 96;
+        S.res = (int4 *)base;                         base += (size_t)nb * 96;
+        S.setup_idx = (uint2 *)base;                  base += (size_t)nb * 16;
+        P.cand = base;                                base += (size_t)nb * 32;
+        P.rough = (float *)base;                      base += (size_t)nb * 80;
+        P.cand_err = (float *)base;                   base += (size_t)nb * 8;
+        S.perm = (unsigned *)base;                    base += (size_t)nb * 8;
+        base += (16 - ((size_t)base & 15)) & 15;
+        S.counters = (unsigned *)base;
+        S.P = P;
+        const double units = (double)w * h;
+        CK(cudaMemsetAsync(S.counters, 0, NVB_BC6_COUNTERS * sizeof(unsigned), ctx->stream));
+        NVB_LAUNCH(ctx, K_BC6_TILES, units, k_bc6_tiles, (unsigned)(((size_t)nb * 16 + 255) / 256), 256, S, tiles);
+        NVB_LAUNCH(ctx, K_BC6_ROUGH, units, k_bc6_rough, grid_for(nb, NVB_BC6_ROUGH_WARPS), NVB_BC6_ROUGH_WARPS * 32, P);
         const int padded = (nb + 127) / 128 * 128;
-        NVB_LAUNCH(ctx, K_BC6_REFINE, (double)w * h, k_bc6_refine, 2 * padded / 128, 128, P, padded);
-        NVB_LAUNCH(ctx, K_BC6_SELECT, (double)w * h, k_bc6_select, grid_for(nb, 256), 256, P);
+        NVB_LAUNCH(ctx, K_BC6_SETUP, units, k_bc6_setup, 2 * padded / 128, 128, S, padded);
+        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<0>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
+        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<1>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
+        // searchers are handed out dynamically, at most what the GPU holds (searchers per thread tuned on B200:
+        // profiles/r1e_summary.md; NVB_BC6_SPT1/2 override for experiments).  The one-region searches (16
+        // texels x 16 palette entries) are the long ones and start first, on a second stream beside the two-region ones.
+        static const int spt1 = getenv("NVB_BC6_SPT1") ? atoi(getenv("NVB_BC6_SPT1")) : 1, spt2 = getenv("NVB_BC6_SPT2") ? atoi(getenv("NVB_BC6_SPT2")) : 2;
+        size_t g1 = ((size_t)nb / spt1 + 127) / 128, g2 = ((size_t)nb * 2 / spt2 + 127) / 128;
+        if (g1 > 148u * 5u) g1 = 148u * 5u;
+        if (g2 > 148u * 6u) g2 = 148u * 6u;
+        if (g1 < 1) g1 = 1;
+        if (g2 < 1) g2 = 1;
+        CK(cudaEventRecord(ctx->ev_fork[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->mode_stream[0], ctx->ev_fork[0], 0));
+        NVB_LAUNCH_ON(ctx, ctx->mode_stream[0], K_BC6_SEARCH, units, k_bc6_search<1>, (unsigned)g1, 128, S);
+        CK(cudaEventRecord(ctx->ev_join[0][0], ctx->mode_stream[0]));
+        NVB_LAUNCH(ctx, K_BC6_SEARCH, units, k_bc6_search<2>, (unsigned)g2, 128, S);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0][0], 0));
+        NVB_LAUNCH(ctx, K_BC6_FINISH, units, k_bc6_finish, 2 * padded / 128, 128, S, padded);
+        NVB_LAUNCH(ctx, K_BC6_SELECT, units, k_bc6_select, grid_for(nb, 256), 256, P);
     }
     else if (d->format == F_BC7) {
         // scratch per block of the level: 5 x 16 shape bytes, 8 x 16 candidate bytes, 8 errors; per block of a chunk: the

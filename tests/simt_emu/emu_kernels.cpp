@@ -10,6 +10,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_coop.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_search.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
@@ -151,7 +152,25 @@ void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency,
     P.rough = rough.data(); P.cand = cand.data(); P.cand_err = err.data();
     emu::launch(dim3((nb + NVB_BC6_ROUGH_WARPS - 1) / NVB_BC6_ROUGH_WARPS), dim3(NVB_BC6_ROUGH_WARPS * 32), 0, [&] { k_bc6_rough(P); });
     int padded = (nb + 127) / 128 * 128;
-    emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_refine(P, padded); });
+    const char *how = getenv("NVB_EMU_BC6");
+    if (how && !strcmp(how, "scalar")) {  // thread per (block, kind)
+        emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_refine(P, padded); });
+    } else {  // the product's searcher state machine
+        std::vector<float4> tiles((size_t)nb * 16);
+        std::vector<int4> meta((size_t)nb * 2), setup((size_t)nb * 6), res((size_t)nb * 6);
+        std::vector<uint2> sidx((size_t)nb * 2);
+        std::vector<unsigned> perm((size_t)nb * 2), counters(NVB_BC6_COUNTERS, 0);
+        Bc6SearchParams S;
+        S.P = P; S.tiles = tiles.data(); S.meta = meta.data(); S.setup = setup.data(); S.setup_idx = sidx.data(); S.res = res.data();
+        S.perm = perm.data(); S.counters = counters.data();
+        emu::launch(dim3((nb * 16 + 255) / 256), dim3(256), 0, [&] { k_bc6_tiles(S, tiles.data()); });
+        emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_setup(S, padded); });
+        emu::launch(dim3((nb * 2 + 255) / 256), dim3(256), 0, [&] { k_bc6_order<0>(S); });
+        emu::launch(dim3((nb * 2 + 255) / 256), dim3(256), 0, [&] { k_bc6_order<1>(S); });
+        emu::launch(dim3(2), dim3(128), 0, [&] { k_bc6_search<1>(S); });
+        emu::launch(dim3(2), dim3(128), 0, [&] { k_bc6_search<2>(S); });
+        emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_finish(S, padded); });
+    }
     emu::launch(dim3((nb + 255) / 256), dim3(256), 0, [&] { k_bc6_select(P); });
 }
 
