@@ -123,6 +123,16 @@ NVTTB_API int nvttb_surface_pack_normals(NvttbSurface *s);
 /* Surface::toGreyScale / toNormalMap  src/nvtt/Surface.cpp:1732-1756,2794-2808 */
 NVTTB_API int nvttb_surface_to_grey_scale(NvttbSurface *s, float r, float g, float b, float a);
 NVTTB_API int nvttb_surface_to_normal_map(NvttbSurface *s, float sm, float medium, float big, float large);
+/* Surface::setImage2D(format, decoder, w, h, data): decode a BCn level into the surface  src/nvtt/Surface.cpp:908-1118.
+ * format: BC1, BC2, BC3, BC3n, BC3_RGBM, BC4, BC5, BC6, BC7 (nvtt::Format values); decoder: nvtt::Decoder (D3D10 / D3D9 / NV5x).
+ * bc6Signed: state of the reference's global ZOH::Utils::FORMAT at decode time (0 = unsigned, its value unless a signed
+ * BC6 encode ran before). */
+NVTTB_API int nvttb_surface_set_image_2d(NvttbSurface *s, int format, int decoder, int w, int h, const void *data, int location, int bc6Signed);
+/* nvtt::rmsError(reference, img) / nvtt::rmsAlphaError  src/nvtt/Surface.cpp:3270-3279 -> nv::rmsColorError / rmsAlphaError
+ * src/nvimage/ErrorMetric.cpp:13-73.  The colour error is alpha-weighted when the reference surface's alpha mode is
+ * AlphaMode_Transparency.  *out = FLT_MAX when the layouts differ (as in the reference). */
+NVTTB_API int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
+NVTTB_API int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
 /* Surface::data(): copy planar fp32 RGBA (4*w*h floats) to the host. */
 NVTTB_API int nvttb_surface_download(const NvttbSurface *s, float *out);
 /* Device pointer of the planar fp32 data (valid until the next op on the surface). */

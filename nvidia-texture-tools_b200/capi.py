@@ -61,6 +61,7 @@ EXPORTS = [
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
     "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
+    "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
 ]
@@ -103,6 +104,9 @@ def lib():
     L.nvttb_surface_width.argtypes = [vp]
     L.nvttb_surface_height.argtypes = [vp]
     L.nvttb_surface_set_image.argtypes = [vp, ci, ci, ci, vp, ci]
+    L.nvttb_surface_set_image_2d.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci]
+    L.nvttb_rms_error.argtypes = [vp, vp, C.POINTER(cf)]
+    L.nvttb_rms_alpha_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_surface_to_linear.argtypes = [vp, cf]
     L.nvttb_surface_to_gamma.argtypes = [vp, cf]
     L.nvttb_surface_build_next_mipmap.argtypes = [vp, ci, ci, cf, C.POINTER(cf), C.POINTER(ci)]
@@ -281,6 +285,23 @@ class Surface:
         data = np.ascontiguousarray(data)
         self._keep = data
         self.ctx._ck(self.L.nvttb_surface_set_image(self.h, input_format, w, h, data.ctypes.data, HOST))
+
+    def set_image_2d(self, fmt, w, h, blocks, decoder=0, bc6_signed=False):
+        """Surface::setImage2D: decode a BCn level (host bytes) into this surface."""
+        blocks = np.ascontiguousarray(blocks)
+        self._keep = blocks
+        self.ctx._ck(self.L.nvttb_surface_set_image_2d(self.h, fmt, decoder, w, h, C.c_void_p(blocks.ctypes.data), HOST, int(bc6_signed)))
+
+    def rms_error(self, img):
+        """nvtt::rmsError(self as reference, img)."""
+        v = C.c_float()
+        self.ctx._ck(self.L.nvttb_rms_error(self.h, img.h, C.byref(v)))
+        return v.value
+
+    def rms_alpha_error(self, img):
+        v = C.c_float()
+        self.ctx._ck(self.L.nvttb_rms_alpha_error(self.h, img.h, C.byref(v)))
+        return v.value
 
     def get(self):
         out = np.empty((4, self.height, self.width), np.float32)

@@ -13,6 +13,7 @@
 #include "kernels/bc7_search.cuh"
 #include "kernels/bc6h_search.cuh"
 #include "kernels/image_ops.cuh"
+#include "kernels/bc_decode.cuh"
 
 #include <cuda_runtime.h>
 #include <map>
@@ -43,9 +44,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -982,6 +983,69 @@ int nvttb_surface_set_image(NvttbSurface *s, int inputFormat, int w, int h, cons
     if (location == NVTTB_HOST) CK(cudaStreamSynchronize(ctx->stream));
     return NVTTB_OK;
 }
+
+int nvttb_surface_set_image_2d(NvttbSurface *s, int format, int decoder, int w, int h, const void *data, int location, int bc6Signed) {
+    if (!s || !data || w <= 0 || h <= 0) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    const bool ok = format == F_DXT1 || format == F_DXT3 || format == F_DXT5 || format == F_DXT5n || format == 12 /*BC3_RGBM*/ ||
+                    format == F_BC4 || format == F_BC5 || format == F_BC6 || format == F_BC7;
+    if (!ok || decoder < 0 || decoder > 2) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "setImage2D: format / decoder not decodable");
+    CK(cudaSetDevice(ctx->device));
+    const int bw = (w + 3) / 4, bh = (h + 3) / 4;
+    const size_t bytes = (size_t)bw * bh * ((format == F_DXT1 || format == F_BC4) ? 8 : 16);
+    int rc = ensure(ctx, s->buf, (size_t)w * h * 16);
+    if (rc != NVTTB_OK) return rc;
+    const unsigned char *d_blocks = (const unsigned char *)data;
+    if (location == NVTTB_HOST) {
+        if ((rc = ensure(ctx, ctx->in_stage, bytes)) != NVTTB_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->in_stage.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_blocks = (const unsigned char *)ctx->in_stage.p;
+    }
+    DecodeParams P;
+    P.blocks = d_blocks;
+    P.out = (float *)s->buf.p;
+    P.w = w; P.h = h; P.bw = bw; P.bh = bh;
+    P.format = format; P.decoder = decoder; P.bc6_signed = bc6Signed;
+    NVB_LAUNCH(ctx, K_DECODE, (double)w * h, k_decode_blocks, grid_for((size_t)bw * bh, 128), 128, P);
+    CK(cudaGetLastError());
+    s->w = w;
+    s->h = h;
+    if (location == NVTTB_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return NVTTB_OK;
+}
+
+static int error_metric(const NvttbSurface *ref, const NvttbSurface *img, int mode, float *out) {
+    if (!ref || !img || !out) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = ref->ctx;
+    if (!ref->buf.p || !img->buf.p || ref->w != img->w || ref->h != img->h) {  // !sameLayout
+        *out = FLT_MAX;
+        return NVTTB_OK;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t count = (size_t)ref->w * ref->h;
+    const unsigned grid = grid_for(count, 256);
+    int rc = ensure(ctx, ctx->tmp_filter, (size_t)grid * sizeof(double));
+    if (rc != NVTTB_OK) return rc;
+    ErrorParams P;
+    P.ref = (const float *)ref->buf.p;
+    P.img = (const float *)img->buf.p;
+    P.count = count;
+    P.mode = mode;
+    P.partial = (double *)ctx->tmp_filter.p;
+    NVB_LAUNCH(ctx, K_ERROR_METRIC, (double)count, k_error_metric, grid, 256, P);
+    CK(cudaGetLastError());
+    std::vector<double> part(grid);
+    CK(cudaMemcpyAsync(part.data(), P.partial, grid * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double mse = 0;
+    for (unsigned i = 0; i < grid; i++) mse += part[i];
+    *out = (float)sqrt(mse / (double)(unsigned)count);
+    return NVTTB_OK;
+}
+int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) {
+    return error_metric(reference, img, (reference && reference->alphaMode == AM_Transparency) ? 1 : 0, out);
+}
+int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 2, out); }
 
 int nvttb_surface_to_linear(NvttbSurface *s, float gamma) {
     if (!s) return NVTTB_ERR_INVALID_INPUT;

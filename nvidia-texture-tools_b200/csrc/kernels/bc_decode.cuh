@@ -1,0 +1,390 @@
+// BCn block decoders and image error metrics — replace, value for value:
+//   Surface::setImage2D(Format, Decoder, w, h, data)      src/nvtt/Surface.cpp:908-1118
+//   BlockDXT1::evaluatePalette / evaluatePaletteNV5x      src/nvimage/BlockDXT.cpp:43-145   (3-colour blocks decode as such
+//                                                         inside BC2/BC3 too, as the reference does)
+//   AlphaBlockDXT3::decodeBlock, AlphaBlockDXT5::evaluatePalette8/6, BlockATI1/ATI2::decodeBlock   BlockDXT.cpp:277-600
+//   BlockBC6::decodeBlock -> ZOH::decompress(one|two)     BlockDXT.cpp:632-652, src/bc6h/zohone.cpp:357, zohtwo.cpp:438
+//   BlockBC7::decodeBlock -> AVPCL::decompress_mode0..7   BlockDXT.cpp:654-671, src/bc7/avpcl_mode*.cpp
+//   nv::rmsColorError / rmsAlphaError                     src/nvimage/ErrorMetric.cpp:13-73 (nvtt::rmsError, rmsAlphaError)
+// One thread decodes one 4x4 block and writes its texels to the four fp32 planes (16-byte row segments: the segments of
+// neighbouring blocks are contiguous, so a warp writes whole 512-byte rows).  HBM-bound: 0.5-1 B/texel in, 16 B/texel out.
+#pragma once
+#include "bc6h.cuh"
+#include "bc7.cuh"
+#include "image_ops.cuh"
+
+namespace nvb {
+
+struct DecodeParams {
+    const unsigned char *blocks;
+    float *out;        // planar fp32 [4][h][w]
+    int w, h, bw, bh;
+    int format;        // nvtt::Format
+    int decoder;       // nvtt::Decoder: 0 D3D10, 1 D3D9, 2 NV5x
+    int bc6_signed;    // ZOH::Utils::FORMAT == SIGNED_F16 at decode time (a global in the reference; unsigned unless a signed encode ran)
+};
+
+struct Rgba8 {
+    unsigned char r, g, b, a;
+};
+
+// BlockDXT1::decodeBlock(colors, d3d9) / decodeBlockNV5x
+NVB_DEV void dec_dxt1(const unsigned char *blk, bool nv5x, int d3d9, Rgba8 out[16]) {
+    const unsigned c0 = blk[0] | (blk[1] << 8), c1 = blk[2] | (blk[3] << 8);
+    const unsigned bits = blk[4] | (blk[5] << 8) | (blk[6] << 16) | ((unsigned)blk[7] << 24);
+    const int r0 = (c0 >> 11) & 31, g0 = (c0 >> 5) & 63, b0 = c0 & 31;
+    const int r1 = (c1 >> 11) & 31, g1 = (c1 >> 5) & 63, b1 = c1 & 31;
+    Rgba8 p[4];
+    if (!nv5x) {
+        p[0].r = (unsigned char)((r0 << 3) | (r0 >> 2)); p[0].g = (unsigned char)((g0 << 2) | (g0 >> 4)); p[0].b = (unsigned char)((b0 << 3) | (b0 >> 2)); p[0].a = 0xFF;
+        p[1].r = (unsigned char)((r1 << 3) | (r1 >> 2)); p[1].g = (unsigned char)((g1 << 2) | (g1 >> 4)); p[1].b = (unsigned char)((b1 << 3) | (b1 >> 2)); p[1].a = 0xFF;
+        if (c0 > c1) {
+            p[2].r = (unsigned char)((2 * p[0].r + p[1].r + d3d9) / 3); p[2].g = (unsigned char)((2 * p[0].g + p[1].g + d3d9) / 3); p[2].b = (unsigned char)((2 * p[0].b + p[1].b + d3d9) / 3); p[2].a = 0xFF;
+            p[3].r = (unsigned char)((2 * p[1].r + p[0].r + d3d9) / 3); p[3].g = (unsigned char)((2 * p[1].g + p[0].g + d3d9) / 3); p[3].b = (unsigned char)((2 * p[1].b + p[0].b + d3d9) / 3); p[3].a = 0xFF;
+        } else {
+            p[2].r = (unsigned char)((p[0].r + p[1].r) / 2); p[2].g = (unsigned char)((p[0].g + p[1].g) / 2); p[2].b = (unsigned char)((p[0].b + p[1].b) / 2); p[2].a = 0xFF;
+            p[3].r = p[3].g = p[3].b = p[3].a = 0;
+        }
+    } else {
+        p[0].r = (unsigned char)((3 * r0 * 22) / 8); p[0].g = (unsigned char)((g0 << 2) | (g0 >> 4)); p[0].b = (unsigned char)((3 * b0 * 22) / 8); p[0].a = 0xFF;
+        p[1].r = (unsigned char)((3 * r1 * 22) / 8); p[1].g = (unsigned char)((g1 << 2) | (g1 >> 4)); p[1].b = (unsigned char)((3 * b1 * 22) / 8); p[1].a = 0xFF;
+        const int gdiff = (int)p[1].g - (int)p[0].g;
+        if (c0 > c1) {
+            p[2].r = (unsigned char)(((2 * r0 + r1) * 22) / 8);
+            p[2].g = (unsigned char)((256 * p[0].g + gdiff / 4 + 128 + gdiff * 80) / 256);
+            p[2].b = (unsigned char)(((2 * b0 + b1) * 22) / 8);
+            p[2].a = 0xFF;
+            p[3].r = (unsigned char)(((2 * r1 + r0) * 22) / 8);
+            p[3].g = (unsigned char)((256 * p[1].g - gdiff / 4 + 128 - gdiff * 80) / 256);
+            p[3].b = (unsigned char)(((2 * b1 + b0) * 22) / 8);
+            p[3].a = 0xFF;
+        } else {
+            p[2].r = (unsigned char)(((r0 + r1) * 33) / 8);
+            p[2].g = (unsigned char)((256 * p[0].g + gdiff / 4 + 128 + gdiff * 128) / 256);
+            p[2].b = (unsigned char)(((b0 + b1) * 33) / 8);
+            p[2].a = 0xFF;
+            p[3].r = p[3].g = p[3].b = p[3].a = 0;
+        }
+    }
+    for (int i = 0; i < 16; i++) out[i] = p[(bits >> (2 * i)) & 3];
+}
+
+// AlphaBlockDXT5::decodeBlock: 8 palette entries, 3-bit indices
+NVB_DEV void dec_alpha5(const unsigned char *blk, bool d3d9, unsigned char out[16]) {
+    const int a0 = blk[0], a1 = blk[1];
+    unsigned char pal[8];
+    pal[0] = (unsigned char)a0;
+    pal[1] = (unsigned char)a1;
+    if (a0 > a1) {
+        const int bias = d3d9 ? 3 : 0;
+        for (int k = 1; k <= 6; k++) pal[1 + k] = (unsigned char)(((7 - k) * a0 + k * a1 + bias) / 7);
+    } else {
+        const int bias = d3d9 ? 2 : 0;
+        for (int k = 1; k <= 4; k++) pal[1 + k] = (unsigned char)(((5 - k) * a0 + k * a1 + bias) / 5);
+        pal[6] = 0x00;
+        pal[7] = 0xFF;
+    }
+    unsigned long long bits = 0;
+    for (int k = 0; k < 6; k++) bits |= (unsigned long long)blk[2 + k] << (8 * k);
+    for (int i = 0; i < 16; i++) out[i] = pal[(bits >> (3 * i)) & 7];
+}
+
+// ---- bit reader (inverse of Bc7Bits / Bits128: LSB first) ------------------------------------------------------------------
+struct BitReader {
+    unsigned w[4];
+    int ptr;
+    NVB_DEV void init(const unsigned char *blk) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(blk);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        ptr = 0;
+    }
+    NVB_DEV int read(int nbits) {
+        int out = 0;
+        for (int i = 0; i < nbits; ++i) {
+            if (ptr < 128) out |= (int)((w[ptr >> 5] >> (ptr & 31)) & 1u) << i;
+            ++ptr;
+        }
+        return out;
+    }
+};
+
+// decompress_modeM for the single-index modes
+template <int M> NVB_DEV void dec_bc7_mode(BitReader &in, Rgba8 out[16]) {
+    using C = Bc7Cfg<M>;
+    const int shape = in.read(C::SHAPEBITS);
+    Bc7Ep e[C::NR];
+    for (int r = 0; r < C::NR; r++) {
+        e[r].a_lsb = e[r].b_lsb = 0;
+        for (int k = 0; k < 4; k++) e[r].A[k] = e[r].B[k] = 0;
+    }
+    for (int j = 0; j < C::NCH; ++j)
+        for (int i = 0; i < C::NR; ++i) {
+            e[i].A[j] = in.read(C::PREC);
+            e[i].B[j] = in.read(C::PREC);
+        }
+    if (C::LSB == 1)
+        for (int i = 0; i < C::NR; ++i) e[i].a_lsb = in.read(1);
+    if (C::LSB == 2)
+        for (int i = 0; i < C::NR; ++i) {
+            e[i].a_lsb = in.read(1);
+            e[i].b_lsb = in.read(1);
+        }
+    float pal[C::NR][C::NIDX][4];
+    for (int r = 0; r < C::NR; r++) bc7_palette<M>(e[r], pal[r]);
+    int anchors[3] = {0, -1, -1};
+    for (int r = 1; r < C::NR; r++) anchors[r] = bc7_anchor<C::NR>(shape, r);
+    for (int pos = 0; pos < 16; ++pos) {
+        const bool match = (pos == anchors[0]) || (pos == anchors[1]) || (pos == anchors[2]);
+        const int idx = in.read(C::IBITS - (match ? 1 : 0));
+        const float *c = pal[bc7_region<C::NR>(shape, pos)][idx];
+        out[pos].r = (unsigned char)c[0];
+        out[pos].g = (unsigned char)c[1];
+        out[pos].b = (unsigned char)c[2];
+        out[pos].a = (unsigned char)c[3];
+    }
+}
+
+// decompress_mode4 / decompress_mode5
+template <int M> NVB_DEV void dec_bc7_split(BitReader &in, Rgba8 out[16]) {
+    const int rotatemode = in.read(2);
+    const int indexmode = (M == 4) ? in.read(1) : 0;
+    Bc7Ep e;
+    e.a_lsb = e.b_lsb = 0;
+    for (int j = 0; j < 4; ++j) {
+        e.A[j] = in.read(bc7s_prec<M>(j));
+        e.B[j] = in.read(bc7s_prec<M>(j));
+    }
+    Bc7SplitPal p;
+    bc7s_palette<M>(e, indexmode, p);
+    int first[16], second[16];
+    const int bits1 = 2, bits2 = (M == 4) ? 3 : 2;
+    for (int i = 0; i < 16; ++i) first[i] = in.read(bits1 - (i == 0 ? 1 : 0));
+    for (int i = 0; i < 16; ++i) second[i] = in.read(bits2 - (i == 0 ? 1 : 0));
+    const bool alpha_is_2bits = (M == 4 && indexmode == 1);
+    for (int i = 0; i < 16; i++) {
+        const int ia = alpha_is_2bits ? first[i] : second[i], irgb = alpha_is_2bits ? second[i] : first[i];
+        float c[4] = {p.rgb[irgb][0], p.rgb[irgb][1], p.rgb[irgb][2], p.a[ia]};
+        if (rotatemode != 0) {  // rotate_tile: swap channel rotatemode-1 with alpha
+            const float t = c[rotatemode - 1];
+            c[rotatemode - 1] = c[3];
+            c[3] = t;
+        }
+        out[i].r = (unsigned char)c[0];
+        out[i].g = (unsigned char)c[1];
+        out[i].b = (unsigned char)c[2];
+        out[i].a = (unsigned char)c[3];
+    }
+}
+
+// AVPCL::decompress: mode = number of leading zero bits of the first byte; byte 0 -> reserved -> black, alpha 0
+NVB_DEV void dec_bc7(const unsigned char *blk, Rgba8 out[16]) {
+    BitReader in;
+    in.init(blk);
+    const unsigned first = blk[0];
+    if (first == 0) {
+        for (int i = 0; i < 16; i++) out[i].r = out[i].g = out[i].b = out[i].a = 0;
+        return;
+    }
+    const int mode = __ffs((int)first) - 1;
+    in.read(mode + 1);
+    switch (mode) {
+    case 0: dec_bc7_mode<0>(in, out); break;
+    case 1: dec_bc7_mode<1>(in, out); break;
+    case 2: dec_bc7_mode<2>(in, out); break;
+    case 3: dec_bc7_mode<3>(in, out); break;
+    case 4: dec_bc7_split<4>(in, out); break;
+    case 5: dec_bc7_split<5>(in, out); break;
+    case 6: dec_bc7_mode<6>(in, out); break;
+    default: dec_bc7_mode<7>(in, out); break;
+    }
+}
+
+// ZOH::decompress -> half bit patterns (as ints in the format's range) per texel; false = reserved mode (all zero)
+template <int NR> NVB_DEV void dec_bc6_kind(const unsigned char *blk, int pat_row, bool sgn, int out[16][3]) {
+    constexpr int NIDX = NR == 1 ? 16 : 8;
+    constexpr int IBITS = NR == 1 ? 4 : 3;
+    const ZohPattern p = kZohPattern[pat_row];
+    BitReader in;
+    in.init(blk);
+    int fv[14];
+    for (int k = 0; k < 14; k++) fv[k] = 0;
+    const int hbits = NR == 1 ? 65 : 82;
+    for (int b = 0; b < hbits; b++) {
+        const unsigned code = kZohHeader[pat_row][b];
+        fv[code >> 4] |= in.read(1) << (code & 15);
+    }
+    const int shape = fv[1];
+    // decompress_endpts
+    const int dp[3] = {p.dr, p.dg, p.db};
+    ZohEndpts e[NR];
+    for (int i = 0; i < 3; ++i) {
+        const int r0 = fv[2 + i * 4];
+        for (int k = 0; k < NR * 2; k++) {
+            const int c = fv[2 + i * 4 + k];
+            int v;
+            if (k == 0) {
+                v = sgn ? zoh_sign_extend(r0, p.prec) : r0;
+            } else if (p.transformed) {
+                int t = zoh_sign_extend(c, dp[i]);
+                t = (t + r0) & zoh_mask(p.prec);
+                v = sgn ? zoh_sign_extend(t, p.prec) : t;
+            } else {
+                v = sgn ? zoh_sign_extend(c, dp[i]) : c;
+            }
+            if (k & 1) e[k >> 1].B[i] = v;
+            else e[k >> 1].A[i] = v;
+        }
+    }
+    float pal[NR][NIDX][3];
+    for (int r = 0; r < NR; r++) zoh_palette<NIDX>(e[r], p.prec, sgn, pal[r]);
+    const int anchor1 = NR == 1 ? -1 : kAnchor2[shape];
+    for (int pos = 0; pos < 16; ++pos) {
+        const int idx = in.read(IBITS - ((pos == 0 || pos == anchor1) ? 1 : 0));
+        const int region = zoh_region<NR>(shape, pos);
+        for (int k = 0; k < 3; k++) out[pos][k] = (int)pal[region][idx][k];
+    }
+}
+
+NVB_DEV bool dec_bc6(const unsigned char *blk, bool sgn, int out[16][3]) {
+    const int code = blk[0] & 0x1F;
+    if (code == 0x03 || code == 0x07 || code == 0x0b || code == 0x0f) {
+        const int row = code == 0x0f ? 0 : code == 0x0b ? 1 : code == 0x07 ? 2 : 3;
+        dec_bc6_kind<1>(blk, row, sgn, out);
+        return true;
+    }
+    int mode = code & 3;
+    if (mode != 0 && mode != 1) mode = code;  // five mode bits
+    int row = -1;
+    for (int r = 4; r < 14; r++)
+        if (kZohPattern[r].mode == mode) row = r;
+    if (row < 0) return false;  // reserved mode: all zeroes
+    dec_bc6_kind<2>(blk, row, sgn, out);
+    return true;
+}
+
+// ---- Surface::setImage2D ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_decode_blocks(DecodeParams P) {
+    const int nblocks = P.bw * P.bh;
+    const size_t plane = (size_t)P.w * P.h;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += gridDim.x * blockDim.x) {
+        const int bx = blk % P.bw, by = blk / P.bw;
+        float v[16][4];
+        const int f = P.format;
+        if (f == 10) {  // Format_BC6: decoded straight to float
+            int hb[16][3];
+            const bool sgn = P.bc6_signed != 0;
+            const bool ok = dec_bc6(P.blocks + (size_t)blk * 16, sgn, hb);
+            for (int i = 0; i < 16; i++) {
+                for (int k = 0; k < 3; k++) {
+                    unsigned h = 0;
+                    if (ok) {
+                        // ZOH::Tile::float2half = Utils::format_to_ushort: sign-magnitude for the signed format
+                        const int x = hb[i][k];
+                        h = (sgn && x < 0) ? (0x8000u | (unsigned)(-x)) : (unsigned)x;
+                    }
+                    v[i][k] = half_bits_to_float(h & 0xFFFFu);
+                }
+                v[i][3] = 1.0f;
+            }
+        } else {
+            Rgba8 c[16];
+            if (f == 1) {  // DXT1
+                dec_dxt1(P.blocks + (size_t)blk * 8, P.decoder == 2, 0, c);
+            } else if (f == 3) {  // DXT3: explicit alpha, then colour block
+                const unsigned char *b = P.blocks + (size_t)blk * 16;
+                dec_dxt1(b + 8, P.decoder == 2, 0, c);
+                for (int i = 0; i < 16; i++) {
+                    const unsigned a4 = (b[i >> 1] >> (4 * (i & 1))) & 15u;
+                    c[i].a = (unsigned char)((a4 << 4) | a4);
+                }
+            } else if (f == 4 || f == 5 || f == 12) {  // DXT5, DXT5n, BC3_RGBM
+                const unsigned char *b = P.blocks + (size_t)blk * 16;
+                dec_dxt1(b + 8, P.decoder == 2, 0, c);
+                unsigned char a[16];
+                dec_alpha5(b, false, a);  // decodeBlock(block, false) for D3D10 and D3D9; NV5x passes no flag either
+                for (int i = 0; i < 16; i++) c[i].a = a[i];
+            } else if (f == 6) {  // BC4
+                unsigned char a[16];
+                dec_alpha5(P.blocks + (size_t)blk * 8, P.decoder == 1, a);
+                for (int i = 0; i < 16; i++) {
+                    c[i].r = c[i].g = c[i].b = a[i];
+                    c[i].a = 255;
+                }
+            } else if (f == 7) {  // BC5
+                unsigned char x[16], y[16];
+                dec_alpha5(P.blocks + (size_t)blk * 16, P.decoder == 1, x);
+                dec_alpha5(P.blocks + (size_t)blk * 16 + 8, P.decoder == 1, y);
+                for (int i = 0; i < 16; i++) {
+                    c[i].r = x[i];
+                    c[i].g = y[i];
+                    c[i].b = 0;
+                    c[i].a = 255;
+                }
+            } else {  // BC7
+                dec_bc7(P.blocks + (size_t)blk * 16, c);
+            }
+            for (int i = 0; i < 16; i++) {
+                v[i][0] = (float)c[i].r * 1.0f / 255.0f;
+                v[i][1] = (float)c[i].g * 1.0f / 255.0f;
+                v[i][2] = (float)c[i].b * 1.0f / 255.0f;
+                v[i][3] = (float)c[i].a * 1.0f / 255.0f;
+            }
+        }
+        const bool full = (bx * 4 + 4 <= P.w) && ((P.w & 3) == 0);
+        for (int yy = 0; yy < 4; yy++) {
+            const int y = by * 4 + yy;
+            if (y >= P.h) break;
+            for (int ch = 0; ch < 4; ch++) {
+                float *row = P.out + ch * plane + (size_t)y * P.w + bx * 4;
+                if (full) {
+                    *reinterpret_cast<float4 *>(row) = make_float4(v[yy * 4][ch], v[yy * 4 + 1][ch], v[yy * 4 + 2][ch], v[yy * 4 + 3][ch]);
+                } else {
+                    for (int xx = 0; xx < 4; xx++)
+                        if (bx * 4 + xx < P.w) row[xx] = v[yy * 4 + xx][ch];
+                }
+            }
+        }
+    }
+}
+
+// ---- nv::rmsColorError / rmsAlphaError -------------------------------------------------------------------------------------
+// The reference adds fp32 terms into one double in texel order.  Here every thread accumulates a strided subset in
+// double, a CTA reduces in shared memory and the per-CTA partial sums are added on the host in double.  The terms are
+// fp32 values, so the partial sums are exact until they exceed 2^29 times the smallest term; the final fp32 result agrees
+// with the sequential sum except when that sum sits within ~1e-16 (relative) of an fp32 rounding boundary.
+struct ErrorParams {
+    const float *ref, *img;  // planar fp32 [4][count]
+    size_t count;
+    int mode;                // 0: rmsColorError, 1: rmsColorError alpha-weighted (a0*a0), 2: rmsAlphaError
+    double *partial;         // one per CTA
+};
+
+__global__ void __launch_bounds__(256) k_error_metric(ErrorParams P) {
+    __shared__ double s_sum[256];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x) {
+        if (P.mode == 2) {
+            const float a = P.img[i + P.count * 3] - P.ref[i + P.count * 3];
+            acc += (double)(a * a);
+        } else {
+            const float r = P.ref[i] - P.img[i], g = P.ref[i + P.count] - P.img[i + P.count], b = P.ref[i + P.count * 2] - P.img[i + P.count * 2];
+            float a = 1.0f;
+            if (P.mode == 1) {
+                const float a0 = P.ref[i + P.count * 3];
+                a = a0 * a0;
+            }
+            acc += (double)((r * r) * a);
+            acc += (double)((g * g) * a);
+            acc += (double)((b * b) * a);
+        }
+    }
+    s_sum[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) s_sum[threadIdx.x] += s_sum[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.partial[blockIdx.x] = s_sum[0];
+}
+
+}  // namespace nvb

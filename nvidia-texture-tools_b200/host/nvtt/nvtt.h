@@ -163,6 +163,7 @@ struct Surface {
     NVTT_API int countMipmaps() const;
     NVTT_API const float *data() const;  // host copy of the planar fp32 RGBA data, refreshed on demand
     NVTT_API bool setImage(InputFormat format, int w, int h, int d, const void *data);
+    NVTT_API bool setImage2D(Format format, Decoder decoder, int w, int h, const void *data);
     NVTT_API void resize(int w, int h, int d, ResizeFilter filter);
     NVTT_API void resize(int w, int h, int d, ResizeFilter filter, float filterWidth, const float *params = 0);
     NVTT_API bool buildNextMipmap(MipmapFilter filter, int min_size = 1);
@@ -178,6 +179,10 @@ struct Surface {
     struct Private;
     Private *m;
 };
+
+// src/nvtt/nvtt.h:699-700
+NVTT_API float rmsError(const Surface &reference, const Surface &img);
+NVTT_API float rmsAlphaError(const Surface &reference, const Surface &img);
 
 NVTT_API unsigned int version();
 NVTT_API const char *errorString(Error e);

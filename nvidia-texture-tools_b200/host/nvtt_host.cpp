@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <float.h>
 #include <string>
 #include <vector>
 
@@ -351,6 +352,17 @@ bool Surface::setImage(InputFormat format, int w, int h, int d, const void *data
     }
     m->hostValid = false;
     return nvttb_surface_set_image(m->s, format, w, h, data, NVTTB_HOST) == NVTTB_OK;
+}
+// Surface::setImage2D (Surface.cpp:908-1118): BCn blocks -> planar fp32, on the device
+bool Surface::setImage2D(Format format, Decoder decoder, int w, int h, const void *data) {
+    NvttbContext *ctx = g_gpu.get();
+    if (!ctx) return false;
+    if (!m->s) {
+        if (nvttb_surface_create(ctx, &m->s) != NVTTB_OK) return false;
+        surf_sync_flags(m);
+    }
+    m->hostValid = false;
+    return nvttb_surface_set_image_2d(m->s, format, decoder, w, h, data, NVTTB_HOST, 0) == NVTTB_OK;
 }
 void Surface::resize(int w, int h, int d, ResizeFilter filter) {
     if (isNull() || d != 1) return;
@@ -810,6 +822,17 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         }
     }
     return true;
+}
+
+float nvtt::rmsError(const Surface &reference, const Surface &img) {
+    float v = FLT_MAX;
+    if (reference.m->s && img.m->s) nvttb_rms_error(reference.m->s, img.m->s, &v);
+    return v;
+}
+float nvtt::rmsAlphaError(const Surface &reference, const Surface &img) {
+    float v = FLT_MAX;
+    if (reference.m->s && img.m->s) nvttb_rms_alpha_error(reference.m->s, img.m->s, &v);
+    return v;
 }
 
 unsigned int nvtt::version() { return NVTT_VERSION; }

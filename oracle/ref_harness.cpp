@@ -3,7 +3,7 @@
 // C-ABI harness around the UNMODIFIED reference library (NVTT 2.1.2, /root/reference), compiled by
 // oracle/build_ref.sh into oracle/_ref/libnvtt_ref.so.  It only *calls* the reference's public API
 // (src/nvtt/nvtt.h) — no reference source is copied here.  The same file, compiled unchanged against the drop-in header
-// nvidia-texture-tools_b200/host/nvtt/nvtt.h (tests/build_host_harness.sh, -DNVTT_HARNESS_NO_DECODE), drives OUR library
+// nvidia-texture-tools_b200/host/nvtt/nvtt.h (tests/build_host_harness.sh), drives OUR library
 // through the identical nvtt:: calls — that is the source-compatibility test of the boundary.  The tests use it (1) to pin the plain-C
 // restatement in oracle/*.c and (2) as the checker for the CUDA path; bench.py uses it as the
 // `--impl reference` arm / cpu_baseline ("kind": "reference").
@@ -214,16 +214,25 @@ void ref_surf_normalize_normal_map(void *h) { ((Surface *)h)->normalizeNormalMap
 void ref_surf_to_grey_scale(void *h, float r, float g, float b, float a) { ((Surface *)h)->toGreyScale(r, g, b, a); }
 void ref_surf_to_normal_map(void *h, float sm, float md, float bg, float lg) { ((Surface *)h)->toNormalMap(sm, md, bg, lg); }
 
-#ifndef NVTT_HARNESS_NO_DECODE
-// Decode a BCn level with the reference decoder (Surface::setImage2D, src/nvtt/Surface.cpp:908-1118) -> planar fp32.
-int ref_decode(int format, int w, int h, const void *data, float *out) {
+// Decode a BCn level with the library's decoder (Surface::setImage2D, src/nvtt/Surface.cpp:908-1118) -> planar fp32.
+int ref_decode_ex(int format, int decoder, int w, int h, const void *data, float *out) {
     Surface s;
-    if (!s.setImage2D((Format)format, Decoder_D3D10, w, h, data)) return 0;
+    if (!s.setImage2D((Format)format, (Decoder)decoder, w, h, data)) return 0;
     memcpy(out, s.data(), sizeof(float) * 4 * (size_t)w * h);
     return 1;
 }
+int ref_decode(int format, int w, int h, const void *data, float *out) { return ref_decode_ex(format, 0, w, h, data, out); }
 
-#endif
+// nvtt::rmsError / rmsAlphaError between an RGBA32F image (reference, with the given alpha mode) and a decoded BCn level
+int ref_rms_error(int format, int w, int h, const void *blocks, const float *rgba32f, int alphaMode, float *rms, float *rmsAlpha) {
+    Surface ref, img;
+    ref.setAlphaMode((AlphaMode)alphaMode);
+    if (!ref.setImage(InputFormat_RGBA_32F, w, h, 1, rgba32f)) return 0;
+    if (!img.setImage2D((Format)format, Decoder_D3D10, w, h, blocks)) return 0;
+    *rms = nvtt::rmsError(ref, img);
+    *rmsAlpha = nvtt::rmsAlphaError(ref, img);
+    return 1;
+}
 
 int ref_version() { return (int)nvtt::version(); }
 }

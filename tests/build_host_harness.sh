@@ -6,6 +6,6 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(dirname "$HERE")"
 PKG="$ROOT/nvidia-texture-tools_b200"
 mkdir -p "$HERE/_build"
-g++ -std=c++11 -O2 -fPIC -shared -DNVTT_HARNESS_NO_DECODE -I"$PKG/host" -o "$HERE/_build/libnvtt_b200_harness.so" \
+g++ -std=c++11 -O2 -fPIC -shared -I"$PKG/host" -o "$HERE/_build/libnvtt_b200_harness.so" \
     "$ROOT/oracle/ref_harness.cpp" -L"$PKG/lib" -lnvtt -lnvtt_b200 -Wl,-rpath,"$PKG/lib"
 echo "built $HERE/_build/libnvtt_b200_harness.so"
