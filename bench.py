@@ -303,7 +303,7 @@ def main():
                                                "time = this run's CUDA events; clock = median SM clock sampled during the timed region"}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline = cpu_baseline_leg(m)
+            cpu_baseline = cpu_baseline_leg(m, ctx)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,8 +319,12 @@ def main():
         print(json.dumps(line))
 
 
-def cpu_baseline_leg(m):
-    """The reference's CPU path on the host cores of this box, on a bounded sample of the same workload."""
+def cpu_baseline_leg(m, ctx=None):
+    """The reference's CPU path on the host cores of this box, on a bounded sample of the same workload.  Its output is
+    also the checker of the metric's second half ("PSNR delta vs ref CPU"): our encode of the same sample is compared
+    block by block, and both level-0 images are decoded and measured on the GPU (nvttb_surface_set_image_2d + rmsError)."""
+    import math
+    import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     try:
         import refapi
@@ -333,12 +337,44 @@ def cpu_baseline_leg(m):
     a = m.synth.photo_bgra8(n, n, seed=1234, alpha=True)
     nm = m.synth.normal_bgra8(n, n, seed=7)
     t0 = time.perf_counter()
-    refapi.process([a], 0, n, n, refapi.Format_BC3, 1, mip_filter=2, fast=fast)
-    refapi.process([nm], 0, n, n, refapi.Format_BC5, 1, mip_filter=2, normal_map=True, fast=fast)
+    ref3 = refapi.process([a], 0, n, n, refapi.Format_BC3, 1, mip_filter=2, fast=fast)
+    ref5 = refapi.process([nm], 0, n, n, refapi.Format_BC5, 1, mip_filter=2, normal_map=True, fast=fast)
     dt = time.perf_counter() - t0
-    return {"value": 2 * n * n / 1e6 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
-            "sample": "one %dx%d BC3(S2)+BC5(S3) Kaiser mip-chain pair (1/4 of the step's texels), %s build, %.1f s"
-                      % (n, n, "fast SSE2 -O3" if fast else "pinned -O2 scalar", dt)}
+    out = {"value": 2 * n * n / 1e6 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+           "sample": "one %dx%d BC3(S2)+BC5(S3) Kaiser mip-chain pair (1/4 of the step's texels), %s build, %.1f s"
+                     % (n, n, "fast SSE2 -O3" if fast else "pinned -O2 scalar", dt)}
+    if ctx is not None:
+        try:
+            d3 = m.make_process_desc(m.InputFormat_BGRA_8UB, n, n, m.Format_BC3, m.Quality_Normal, mip_filter=m.MipmapFilter_Kaiser)
+            d5 = m.make_process_desc(m.InputFormat_BGRA_8UB, n, n, m.Format_BC5, m.Quality_Normal, mip_filter=m.MipmapFilter_Kaiser, normal_map=True)
+            our3, our5 = ctx.process_bytes([a], d3), ctx.process_bytes([nm], d5)
+            pinned = refapi.available()
+            if pinned and fast:  # the checker is the pinned scalar build (untimed); the fast build above is only the timing arm
+                ref3 = refapi.process([a], 0, n, n, refapi.Format_BC3, 1, mip_filter=2)
+                ref5 = refapi.process([nm], 0, n, n, refapi.Format_BC5, 1, mip_filter=2, normal_map=True)
+            par = {}
+            for name, fmt, src, ours, theirs in (("bc3", m.Format_BC3, a, our3, ref3), ("bc5", m.Format_BC5, nm, our5, ref5)):
+                same = ours.size == theirs.size
+                bad = int((ours.reshape(-1, 16) != theirs.reshape(-1, 16)).any(1).sum()) if same else -1
+                org = m.Surface(ctx)
+                if name == "bc5":  # BC5 stores x, y only (decoded blue is 0): measure those two channels
+                    src = src.copy()
+                    src[..., 0] = 0
+                org.set_image(m.InputFormat_BGRA_8UB, n, n, src)
+                lvl0 = (n // 4) * (n // 4) * 16
+                psnr = []
+                for data in (ours, theirs):
+                    dec = m.Surface(ctx)
+                    dec.set_image_2d(fmt, n, n, data[:lvl0])
+                    rms = org.rms_error(dec)
+                    psnr.append(20.0 * math.log10(1.0 / rms) if rms > 0 else float("inf"))
+                par[name] = {"blocks": int(theirs.size // 16), "mismatching_blocks": bad, "psnr_level0_db": psnr[0],  # 20 log10(1 / nvtt::rmsError), rmsError = sqrt(sum over r,g,b / texels)
+                             "psnr_level0_reference_db": psnr[1], "psnr_delta_db": psnr[0] - psnr[1]}
+            out["parity_vs_reference_output"] = par
+            out["parity_note"] = "checker: %s reference build on the same %dx%d sample" % ("pinned scalar" if pinned else "fast SSE", n, n)
+        except Exception as e:  # pragma: no cover
+            out["parity_vs_reference_output"] = "failed: %s" % e
+    return out
 
 
 if __name__ == "__main__":
