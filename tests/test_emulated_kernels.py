@@ -77,8 +77,47 @@ def test_emulated_encoders_match_golden(emu, golden):
     for key, (kind, w, h, fmt, q, am, cw, pt) in G.level_cases().items():
         if (w, h) != (13, 7) and kind != "photo" and fmt not in (10, 11):
             continue  # keep the CPU suite short: ragged size for every input kind, full size for one
-        if fmt == 11 and (w, h) != (13, 7) and not os.environ.get("NVB_EMU_FULL"):
-            continue  # warp-cooperative BC7 under the fibre emulator: 2+ minutes per 24x16 image (set NVB_EMU_FULL=1)
         img = G.make_input(kind, w, h, planar=True)
         got = _encode(emu, fmt, q, img, am, cw, pt)
         assert np.array_equal(got, golden[key]), key
+
+
+def _run_child(env, code):
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    e["PYTHONPATH"] = ROOT + os.pathsep + os.path.join(ROOT, "tests") + os.pathsep + e.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+_CHILD = """
+import ctypes as C, hashlib, numpy as np
+import golden_cases as G
+E = C.CDLL(%r)
+img = G.make_input(%r, %d, %d, planar=True)
+nb = ((%d + 3) // 4) * ((%d + 3) // 4)
+out = np.zeros(nb * 16, np.uint8)
+if %d == 11:
+    errs = np.zeros(8 * nb, np.float32); cands = np.zeros(8 * nb * 16, np.uint8)
+    E.emu_bc7(C.c_void_p(img.ctypes.data), %d, %d, C.c_void_p(out.ctypes.data), 0, 255, C.c_void_p(errs.ctypes.data), C.c_void_p(cands.ctypes.data))
+    print(hashlib.sha1(out.tobytes() + errs.tobytes() + cands.tobytes()).hexdigest())
+else:
+    E.emu_bc6(C.c_void_p(img.ctypes.data), %d, %d, 0, 0, C.c_void_p(out.ctypes.data), 0)
+    print(hashlib.sha1(out.tobytes()).hexdigest())
+"""
+
+
+def test_search_designs_agree(emu):
+    """The product's searcher state machines against the two older mappings of the same search (thread per candidate, warp
+    per candidate for BC7; thread per (block, kind) for BC6H): blocks, per-mode errors and per-mode candidates identical."""
+    def child(kind, w, h, fmt):
+        return _CHILD % (SO, kind, w, h, w, h, fmt, w, h, w, h)
+    for kind, w, h in (("photo", 20, 12), ("adv", 13, 7)):
+        ref = _run_child({"NVB_EMU_BC7": "scalar"}, child(kind, w, h, 11))
+        assert _run_child({"NVB_EMU_BC7": ""}, child(kind, w, h, 11)) == ref, (kind, "search")
+    assert _run_child({"NVB_EMU_BC7": "coop"}, child("photo", 8, 8, 11)) == _run_child({"NVB_EMU_BC7": "scalar"}, child("photo", 8, 8, 11))
+    for kind, w, h in (("hdr", 32, 24), ("photo", 13, 7)):
+        assert _run_child({"NVB_EMU_BC6": "scalar"}, child(kind, w, h, 10)) == _run_child({"NVB_EMU_BC6": ""}, child(kind, w, h, 10)), kind
