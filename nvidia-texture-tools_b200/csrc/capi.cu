@@ -44,9 +44,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -416,7 +416,7 @@ int nvttb_format_supported(int format, int quality) {
     case F_DXT3:
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT5n:
-        return quality >= Q_Fastest && quality <= Q_Production;
+        return quality >= Q_Fastest && quality <= Q_Highest;
     case F_DXT1a:
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_BC6:
@@ -581,7 +581,8 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         if (d->format == F_DXT5) {
             alpha(3, 16, 0, d->quality == Q_Highest);  // CompressorDX9.cpp:149-157
         } else if (d->format == F_DXT5n) {
-            alpha(0, 16, 0, false);  // "rgba.swizzle(4,1,5,0)": alpha block = red channel, QuickCompress (CompressorDX9.cpp:212-221)
+            // "rgba.swizzle(4,1,5,0)": alpha block = red channel; QuickCompress, or OptimalCompress at Highest (CompressorDX9.cpp:212-221)
+            alpha(0, 16, 0, d->quality == Q_Highest);
         } else {
             AlphaBlocksParams A;  // CompressorDXT3: OptimalCompress::compressDXT3A on the alpha channel (CompressorDX9.cpp:119-124)
             A.lv = lv;
@@ -591,6 +592,14 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
             A.out_offset = 0;
             A.mode = 0;
             NVB_LAUNCH(ctx, K_ALPHA_DXT3, (double)w * h, k_alpha_dxt3, grid_for(nb, 128), 128, A);
+        }
+        if (d->format == F_DXT5n && d->quality == Q_Highest) {
+            // CompressorDXT5n at Quality_Highest: brute-force green block (CompressorDX9.cpp:184-187)
+            AlphaBlocksParams G;
+            G.lv = lv; G.channel = 1; G.out = d_out; G.out_stride = 16; G.out_offset = 8; G.mode = 1; G.omatch6 = ctx->d_om6;
+            NVB_LAUNCH(ctx, K_ALPHA_OPT, (double)w * h, k_dxt1g_optimal, grid_for(nb, 4), 128, G);
+            CK(cudaGetLastError());
+            return NVTTB_OK;
         }
         Bc3ColorParams P;
         P.lv = lv;
@@ -1128,6 +1137,18 @@ static int scale_bias(NvttbSurface *s, float scale, float bias) {
 }
 int nvttb_surface_expand_normals(NvttbSurface *s) { return s ? scale_bias(s, 2.0f, -1.0f) : NVTTB_ERR_INVALID_INPUT; }
 int nvttb_surface_pack_normals(NvttbSurface *s) { return s ? scale_bias(s, 0.5f, 0.5f) : NVTTB_ERR_INVALID_INPUT; }
+int nvttb_surface_binarize(NvttbSurface *s, int channel, float threshold, int dither) {
+    if (!s || channel < 0 || channel > 3) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    if (dither) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "binarize with Floyd-Steinberg dithering is not implemented");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)s->w * s->h;
+    BinarizeParams P{(float *)s->buf.p + (size_t)channel * n, n, threshold};
+    NVB_LAUNCH(ctx, K_BINARIZE, (double)n, k_binarize, grid_for(n, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
 int nvttb_surface_normalize_normal_map(NvttbSurface *s) {
     if (!s) return NVTTB_ERR_INVALID_INPUT;
     NvttbContext *ctx = s->ctx;

@@ -144,6 +144,7 @@ struct AlphaBlocksParams {
     int out_stride;  // bytes between consecutive blocks in the output (8 for BC4, 16 for BC5/BC3)
     int out_offset;  // byte offset of this alpha block inside the output block
     int mode;        // 0 quick, 1 optimal (Production / Highest)
+    const unsigned char *omatch6 = nullptr;  // k_dxt1g_optimal only: OMatch6[g][0..1] (single-colour green)
 };
 
 NVB_DEV void alpha_gather_block(const LevelView &lv, int channel, int bx, int by, unsigned src[16]) {
@@ -318,6 +319,117 @@ __global__ void __launch_bounds__(128) k_alpha_dxt3(AlphaBlocksParams P) {
         for (int i = 0; i < 16; i++) b |= (unsigned long long)alpha_quantize4(src[i]) << (4 * i);
         *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
             make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
+    }
+}
+
+// ---- BC3n Quality_Highest colour block: OptimalCompress::compressDXT1G (OptimalCompressDXT.cpp:294-381) -------------------
+// Brute force over the (g0 > g1) green endpoint pairs of [min-4, max+4] in 6-bit space; integer errors.  One warp per block:
+// the pairs are flattened in loop order and striped over the lanes, (error, order) reduction = first strict minimum.
+NVB_DEV int green_pair_error(const unsigned src[16], int g0, int g1) {
+    int pal[4];
+    pal[0] = (g0 << 2) | (g0 >> 4);
+    pal[1] = (g1 << 2) | (g1 >> 4);
+    pal[2] = (2 * pal[0] + pal[1]) / 3;
+    pal[3] = (2 * pal[1] + pal[0]) / 3;
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int g = (int)src[i];
+        int e = (g - pal[0]) * (g - pal[0]);
+        e = min(e, (g - pal[1]) * (g - pal[1]));
+        e = min(e, (g - pal[2]) * (g - pal[2]));
+        e = min(e, (g - pal[3]) * (g - pal[3]));
+        total += e;  // the reference leaves early once total > best; such a total never passes "error < bestError" either
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(128) k_dxt1g_optimal(AlphaBlocksParams P) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int nblocks = P.lv.bw * P.lv.bh;
+    for (int blk = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); blk < nblocks; blk += gridDim.x * warps_per_cta) {
+        unsigned src[16];
+        alpha_gather_block(P.lv, 1, blk % P.lv.bw, blk / P.lv.bw, src);  // green channel, ColorBlock quantisation
+        int ming = 63, maxg = 0;
+        bool single = true;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int green = ((int)src[i] + 1) >> 2;  // may be 64 for g = 255: the 6-bit field assignments below wrap it to 0
+            ming = min(ming, green);
+            maxg = max(maxg, green);
+            if (src[i] != src[0]) single = false;
+        }
+        unsigned c0, c1, indices;
+        if (single) {
+            // compressDXT1G(uint8 g)
+            c0 = (31u << 11) | ((unsigned)P.omatch6[src[0] * 2 + 0] << 5);
+            c1 = (31u << 11) | ((unsigned)P.omatch6[src[0] * 2 + 1] << 5);
+            indices = 0xaaaaaaaau;
+            if (c0 < c1) {
+                const unsigned t = c0; c0 = c1; c1 = t;
+                indices ^= 0x55555555u;
+            }
+        } else {
+            int besterror = green_pair_error(src, maxg & 63, ming & 63);
+            unsigned bestk = 0xffffffffu;
+            int bestg0 = maxg, bestg1 = ming;
+            const int lo = (ming <= 4) ? 0 : ming - 4, hi = (maxg >= 63 - 4) ? 63 : maxg + 4;
+            // for g0 in [lo+1, hi] for g1 in [lo, g0): row r (g0 = lo+1+r) has r+1 entries
+            const int rows = hi - lo;
+            const int n = rows > 0 ? rows * (rows + 1) / 2 : 0;
+            int row = 0, col = lane;
+            while (row < rows && col > row) { col -= row + 1; row++; }
+            for (int k = lane; k < n; k += 32) {
+                const int g0 = lo + 1 + row, g1 = lo + col;
+                const int e = green_pair_error(src, g0, g1);
+                if (e < besterror) {
+                    besterror = e;
+                    bestk = (unsigned)k;
+                    bestg0 = g0;
+                    bestg1 = g1;
+                }
+                col += 32;
+                while (col > row) { col -= row + 1; row++; }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const int oe = __shfl_xor_sync(0xffffffffu, besterror, d);
+                const unsigned ok = __shfl_xor_sync(0xffffffffu, bestk, d);
+                const int o0 = __shfl_xor_sync(0xffffffffu, bestg0, d), o1 = __shfl_xor_sync(0xffffffffu, bestg1, d);
+                if (oe < besterror || (oe == besterror && ok < bestk)) {
+                    besterror = oe;
+                    bestk = ok;
+                    bestg0 = o0;
+                    bestg1 = o1;
+                }
+            }
+            c0 = (31u << 11) | ((unsigned)(bestg0 & 63) << 5);
+            c1 = (31u << 11) | ((unsigned)(bestg1 & 63) << 5);
+            // block->evaluatePalette(palette, false): four colours when col0.u > col1.u, else three + transparent black (g = 0)
+            const int p0 = (int)(((c0 >> 5) & 63) << 2 | ((c0 >> 5) & 63) >> 4), p1 = (int)(((c1 >> 5) & 63) << 2 | ((c1 >> 5) & 63) >> 4);
+            int p2, p3;
+            if (c0 > c1) {
+                p2 = (2 * p0 + p1) / 3;
+                p3 = (2 * p1 + p0) / 3;
+            } else {
+                p2 = (p0 + p1) / 2;
+                p3 = 0;
+            }
+            // computeGreenIndices
+            indices = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int c = (int)src[i];
+                const unsigned d0 = (unsigned)((p0 - c) * (p0 - c)), d1 = (unsigned)((p1 - c) * (p1 - c));
+                const unsigned d2 = (unsigned)((p2 - c) * (p2 - c)), d3 = (unsigned)((p3 - c) * (p3 - c));
+                const unsigned b0 = d0 > d3, b1 = d1 > d2, b2 = d0 > d2, b3 = d1 > d3, b4 = d2 > d3;
+                const unsigned x0 = b1 & b2, x1 = b0 & b3, x2 = b0 & b4;
+                indices |= (x2 | ((x0 | x1) << 1)) << (2 * i);
+            }
+        }
+        if (lane == 0)
+            *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) = make_uint2(c0 | (c1 << 16), indices);
     }
 }
 

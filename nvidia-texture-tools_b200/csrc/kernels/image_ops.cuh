@@ -339,6 +339,17 @@ __global__ void __launch_bounds__(256) k_scale_bias(ScaleBiasParams P) {
         P.data[i] = P.scale * P.data[i] + P.bias;
 }
 
+// Surface::binarize(channel, threshold, dither = false): c = float(c > threshold)   (src/nvtt/Surface.cpp:2656-2670)
+struct BinarizeParams {
+    float *data;   // the channel's plane
+    size_t count;
+    float threshold;
+};
+__global__ void __launch_bounds__(256) k_binarize(BinarizeParams P) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x)
+        P.data[i] = (P.data[i] > P.threshold) ? 1.0f : 0.0f;
+}
+
 struct NormalizeParams {
     float *data;
     size_t pixels;

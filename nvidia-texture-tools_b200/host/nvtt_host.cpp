@@ -403,6 +403,11 @@ void Surface::toNormalMap(float sm, float md, float bg, float lg) {
     if (nvttb_surface_to_normal_map(m->s, sm, md, bg, lg) == NVTTB_OK) { m->isNormalMap = true; surf_sync_flags(m); }
 }
 void Surface::normalizeNormalMap() { if (!isNull() && m->isNormalMap) { m->hostValid = false; nvttb_surface_normalize_normal_map(m->s); } }
+void Surface::binarize(int channel, float threshold, bool dither) {
+    if (isNull()) return;
+    m->hostValid = false;
+    nvttb_surface_binarize(m->s, channel, threshold, dither ? 1 : 0);
+}
 void Surface::packNormals(float scale, float bias) {
     if (isNull()) return;
     m->hostValid = false;
@@ -672,7 +677,12 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         oo.error(Error_CudaError);
         return false;
     }
-    if (depth != 1 || co.enableColorDithering || co.enableAlphaDithering || co.binaryAlpha || !nvttb_format_supported(co.format, co.quality)) {
+    // Compressor::Private::quantize (Context.cpp:519-541): colour dithering acts on BC1..BC3 (Floyd-Steinberg: not implemented);
+    // alpha dithering only on Format_RGB, i.e. never here; binary alpha = non-dithered binarize, and only when alpha dithering
+    // is off (so nvcompress's settings for -bc1a / -bc2 are both no-ops, as in the reference).
+    const bool colorDither = co.enableColorDithering && co.format >= Format_BC1 && co.format <= Format_BC3;
+    const bool binarizeAlpha = !co.enableAlphaDithering && co.binaryAlpha;
+    if (depth != 1 || colorDither || !nvttb_format_supported(co.format, co.quality)) {
         oo.error(Error_UnsupportedFeature);
         return false;
     }
@@ -703,6 +713,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
             s.resize(w, h, 1, ResizeFilter_Box);
             Surface tmp = s;
             if (!s.isNormalMap()) tmp.toGamma(io.outputGamma);
+            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
             if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
             images.push_back(s);
         }
@@ -733,6 +744,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
                     tmp = img;
                     tmp.toGamma(io.outputGamma);
                 }
+                if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
                 if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
             }
             const int mipPadding = 3 - ((imageSize + 3) % 4);
@@ -741,7 +753,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         return true;
     }
 
-    if (canUseSourceImages && !userMips) {
+    if (canUseSourceImages && !userMips && !binarizeAlpha) {
         // fused device pipeline
         NvttbProcessDesc d;
         memset(&d, 0, sizeof d);
@@ -786,6 +798,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         {
             Surface tmp = img;
             if (!img.isNormalMap()) tmp.toGamma(io.outputGamma);
+            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
             if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
         }
         for (int mip = 1; mip < mipmapCount; mip++) {
@@ -818,6 +831,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
                 tmp = img;
                 tmp.toGamma(io.outputGamma);
             }
+            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
             if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
         }
     }

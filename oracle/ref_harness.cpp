@@ -115,6 +115,8 @@ struct RefProcessDesc {
     int outputHeader;    // bool
     int container;       // nvtt::Container
     int threads;         // 0 default pool, 1 sequential
+    int quantization;    // CompressionOptions::setQuantization: bit 0 colour dithering, bit 1 alpha dithering, bit 2 binary alpha
+    int alphaThreshold;  // 0..255 (127 = the default)
 };
 
 // Whole InputOptions pipeline: Compressor::process (src/nvtt/Context.cpp:117-120,217-346).
@@ -135,6 +137,7 @@ long ref_process(const RefProcessDesc *d, const void *const *images, unsigned ch
     io.setAlphaMode((AlphaMode)d->alphaMode);
     CompressionOptions co;
     setup_co(co, d->format, d->quality, d->colorWeights, d->pixelType);
+    if (d->quantization) co.setQuantization((d->quantization & 1) != 0, (d->quantization & 2) != 0, (d->quantization & 4) != 0, d->alphaThreshold);
     OutputOptions oo;
     MemHandler mh;
     ErrCount eh;

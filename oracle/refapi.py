@@ -36,6 +36,7 @@ class RefProcessDesc(C.Structure):
         ("format", C.c_int), ("quality", C.c_int), ("pixelType", C.c_int),
         ("colorWeights", C.c_float * 4),
         ("outputHeader", C.c_int), ("container", C.c_int), ("threads", C.c_int),
+        ("quantization", C.c_int), ("alphaThreshold", C.c_int),
     ]
 
 
@@ -111,9 +112,10 @@ def process(images, input_format, w, h, fmt, quality, *, wrap=WrapMode_Mirror, m
             mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
             to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
             pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), header=False, container=Container_DDS,
-            texture_type=TextureType_2D, threads=0, fast=False):
+            texture_type=TextureType_2D, threads=0, fast=False, quantization=0, alpha_threshold=127):
     """Whole Compressor::process pipeline on the reference; images = list of per-face level-0 arrays."""
     d = RefProcessDesc()
+    d.quantization, d.alphaThreshold = quantization, alpha_threshold
     d.inputFormat, d.textureType, d.width, d.height, d.faces = input_format, texture_type, w, h, len(images)
     d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
     d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = kaiser

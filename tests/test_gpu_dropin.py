@@ -50,6 +50,7 @@ def _process(L, ref, images, fmt, quality, w, h, **kw):
     d.alphaMode, d.format, d.quality, d.pixelType = kw.get("alpha_mode", 0), fmt, quality, 0
     d.colorWeights = (C.c_float * 4)(1, 1, 1, 1)
     d.outputHeader, d.container, d.threads = int(kw.get("header", True)), kw.get("container", 0), 0
+    d.quantization, d.alphaThreshold = kw.get("quantization", 0), kw.get("alpha_threshold", 127)
     imgs = [np.ascontiguousarray(i) for i in images]
     ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
     n = L.ref_process(C.byref(d), ptrs, None, 0)
@@ -78,6 +79,18 @@ def test_process_with_header_identical(nvtt, ref, ours):
         want = _process(ref.lib(), ref, [img], fmt, q, w, h, **kw)
         assert got.size == want.size
         assert np.array_equal(got, want), (fmt, kw)
+
+
+def test_quantization_settings_identical(nvtt, ref, ours):
+    """CompressionOptions::setQuantization as nvcompress uses it (-bc1a: alpha dithering + binary alpha, -bc2: alpha
+    dithering: both no-ops for BCn, Context.cpp:519-541) and binary alpha alone (non-dithered binarize of the alpha plane)."""
+    img = nvtt.synth.photo_bgra8(64, 48, seed=31, alpha=True)
+    for fmt, q in ((ref.Format_DXT1a, 2 | 4), (ref.Format_BC2, 2), (ref.Format_DXT1a, 4), (ref.Format_BC3, 4)):
+        for thr in (127, 40):
+            kw = dict(mip_filter=0, quantization=q, alpha_threshold=thr)
+            got = _process(ours, ref, [img], fmt, 1, 64, 48, **kw)
+            want = _process(ref.lib(), ref, [img], fmt, 1, 64, 48, **kw)
+            assert got.size == want.size and np.array_equal(got, want), (fmt, q, thr)
 
 
 def test_ktx_cube_identical(nvtt, ref, ours):

@@ -28,7 +28,7 @@ def _assert_blocks_equal(got, want, bs, what):
 
 
 @pytest.mark.parametrize("fmt_name,quality", [("BC1", 0), ("BC1", 1), ("BC1", 2), ("BC1", 3), ("BC4", 0), ("BC4", 1), ("BC5", 0),
-                                              ("BC5", 1), ("BC3", 1), ("BC3", 2), ("BC4", 2), ("BC5", 2), ("BC5", 3), ("BC3", 3), ("BC2", 1), ("BC2", 2), ("BC3n", 1), ("BC3n", 2), ("BC2", 0), ("BC3", 0), ("BC3n", 0)])
+                                              ("BC5", 1), ("BC3", 1), ("BC3", 2), ("BC4", 2), ("BC5", 2), ("BC5", 3), ("BC3", 3), ("BC2", 1), ("BC2", 2), ("BC3n", 1), ("BC3n", 2), ("BC3n", 3), ("BC2", 0), ("BC3", 0), ("BC3n", 0)])
 def test_level_encode_bit_exact(nvtt, ref, ctx, fmt_name, quality):
     fmt = getattr(nvtt, "Format_" + fmt_name)
     bs = 8 if fmt_name in ("BC4", "BC1") else 16
