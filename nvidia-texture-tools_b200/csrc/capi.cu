@@ -768,7 +768,11 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
         // fused X+Y in shared memory: the dw x sh intermediate never reaches HBM
         Polyphase2DParams Q{src, dst, sw, sh, dw, dh, px.window, py.window, px.weights, px.left, py.weights, py.left, wrap};
         dim3 grid((dw + NVB_PF_TILE - 1) / NVB_PF_TILE, (dh + NVB_PF_TILE - 1) / NVB_PF_TILE, 4);
-        NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, k_polyphase_2d, grid, 256, Q);
+        // compile-time windows for the 2:1 mip filters (Kaiser 13, Mitchell 9, Triangle 5 taps), run-time windows otherwise
+        if (Q.winx == 13 && Q.winy == 13) NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<13, 13>), grid, 256, Q);
+        else if (Q.winx == 9 && Q.winy == 9) NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<9, 9>), grid, 256, Q);
+        else if (Q.winx == 5 && Q.winy == 5) NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<5, 5>), grid, 256, Q);
+        else NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<0, 0>), grid, 256, Q);
         CK(cudaGetLastError());
         return NVTTB_OK;
     }

@@ -266,15 +266,19 @@ struct Polyphase2DParams {
 #define NVB_PF_HALF ((NVB_PF_EXT + 1) / 2 + 1)
 #define NVB_PF_COL(cc) ((((cc) & 1) ? NVB_PF_HALF : 0) + ((cc) >> 1))
 
-__global__ void __launch_bounds__(256) k_polyphase_2d(Polyphase2DParams P) {
+// WX / WY: compile-time window sizes of the X and Y kernels (13 = Kaiser, 9 = Mitchell, 5 = Triangle at 2:1), 0 = run time.
+// With known windows the tap loops are fully unrolled, the X weights of a lane sit in registers and the staged columns are
+// addressed as (even base | odd base) + constant; the sums add the same products in the same ascending tap order.
+template <int WX, int WY> __global__ void __launch_bounds__(256) k_polyphase_2d_t(Polyphase2DParams P) {
     __shared__ float s_in[NVB_PF_EXT][2 * NVB_PF_HALF];
     __shared__ float s_tmp[NVB_PF_EXT][NVB_PF_TILE + 1];
     const int c = blockIdx.z;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int tx0 = blockIdx.x * NVB_PF_TILE, ty0 = blockIdx.y * NVB_PF_TILE;
     const int tw = min(NVB_PF_TILE, P.dw - tx0), th = min(NVB_PF_TILE, P.dh - ty0);
-    const int x_lo = P.leftx[tx0], x_hi = P.leftx[tx0 + tw - 1] + P.winx;
-    const int y_lo = P.lefty[ty0], y_hi = P.lefty[ty0 + th - 1] + P.winy;
+    const int winx = WX ? WX : P.winx, winy = WY ? WY : P.winy;
+    const int x_lo = P.leftx[tx0], x_hi = P.leftx[tx0 + tw - 1] + winx;
+    const int y_lo = P.lefty[ty0], y_hi = P.lefty[ty0 + th - 1] + winy;
     const int ncols = x_hi - x_lo, nrows = y_hi - y_lo;
     const float *plane = P.src + (size_t)c * P.sw * P.sh;
     // 1. stage the footprint: one warp per row, lanes along x (coalesced); wrap only for tiles that touch the border
@@ -288,42 +292,60 @@ __global__ void __launch_bounds__(256) k_polyphase_2d(Polyphase2DParams P) {
         }
     }
     __syncthreads();
-    // 2. X pass for every staged row: lane = output column, warp w owns rows w, w+8, ...; the taps are walked once and
-    //    every row keeps its own running sum, so each sum still adds its taps in ascending order
+    // 2. X pass for every staged row: lane = output column, warp w owns rows w, w+8, ...
     if (lane < tw) {
-        const float *wt = P.wx + (size_t)(tx0 + lane) * P.winx;
+        const float *wt = P.wx + (size_t)(tx0 + lane) * winx;
         const int off = P.leftx[tx0 + lane] - x_lo;
-        float acc[(NVB_PF_EXT + 7) / 8];
+        if (WX) {
+            float w[WX ? WX : 1];
 #pragma unroll
-        for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) acc[k] = 0.0f;
-        for (int j = 0; j < P.winx; j++) {
-            const float w = wt[j];
-            const int col = NVB_PF_COL(off + j);
+            for (int j = 0; j < WX; j++) w[j] = wt[j];
+            const int cE = NVB_PF_COL(off), cO = NVB_PF_COL(off + 1);  // column off + 2m lives at cE + m, off + 2m + 1 at cO + m
+            for (int r = wid; r < nrows; r += 8) {
+                const float *row = s_in[r];
+                float a = 0.0f;
+#pragma unroll
+                for (int j = 0; j < WX; j++) a += w[j] * row[((j & 1) ? cO : cE) + (j >> 1)];
+                s_tmp[r][lane] = a;
+            }
+        } else {
+            // the taps are walked once and every row keeps its own running sum, so each sum still adds its taps in ascending order
+            float acc[(NVB_PF_EXT + 7) / 8];
+#pragma unroll
+            for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) acc[k] = 0.0f;
+            for (int j = 0; j < winx; j++) {
+                const float w = wt[j];
+                const int col = NVB_PF_COL(off + j);
+#pragma unroll
+                for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) {
+                    const int r = wid + 8 * k;
+                    if (r < nrows) acc[k] += w * s_in[r][col];
+                }
+            }
 #pragma unroll
             for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) {
                 const int r = wid + 8 * k;
-                if (r < nrows) acc[k] += w * s_in[r][col];
+                if (r < nrows) s_tmp[r][lane] = acc[k];
             }
-        }
-#pragma unroll
-        for (int k = 0; k < (NVB_PF_EXT + 7) / 8; k++) {
-            const int r = wid + 8 * k;
-            if (r < nrows) s_tmp[r][lane] = acc[k];
         }
     }
     __syncthreads();
     // 3. Y pass: warp w owns output rows w, w+8, w+16, w+24
     if (lane < tw) {
         for (int oy = wid; oy < th; oy += 8) {
-            const float *wt = P.wy + (size_t)(ty0 + oy) * P.winy;
+            const float *wt = P.wy + (size_t)(ty0 + oy) * winy;
             const int off = P.lefty[ty0 + oy] - y_lo;
             float sum = 0;
-            for (int j = 0; j < P.winy; j++) sum += wt[j] * s_tmp[off + j][lane];
+            if (WY) {
+#pragma unroll
+                for (int j = 0; j < WY; j++) sum += wt[j] * s_tmp[off + j][lane];
+            } else {
+                for (int j = 0; j < winy; j++) sum += wt[j] * s_tmp[off + j][lane];
+            }
             P.dst[(size_t)c * P.dw * P.dh + (size_t)(ty0 + oy) * P.dw + tx0 + lane] = sum;
         }
     }
 }
-
 // ---------------------------------------------------------------------------------------------------------
 // Normal-map helpers.  k_scale_bias: ptr = scale*ptr + bias on planes 0..2.  k_normalize: normalizeSafe with
 // epsilon 0 (zero vector stays zero).  k_renormalize = expandNormals -> normalizeNormalMap -> packNormals

@@ -243,7 +243,12 @@ void emu_resize(const float *src, int sw, int sh, float *dst, int dw, int dh, in
     };
     if (!getenv("NVB_EMU_UNFUSED") && ext(tx) <= NVB_PF_EXT && ext(ty) <= NVB_PF_EXT && tx.window <= NVB_PF_MAXWIN && ty.window <= NVB_PF_MAXWIN) {
         Polyphase2DParams Q{src, dst, sw, sh, dw, dh, tx.window, ty.window, tx.weights.data(), tx.left.data(), ty.weights.data(), ty.left.data(), wrap};
-        emu::launch(dim3((dw + NVB_PF_TILE - 1) / NVB_PF_TILE, (dh + NVB_PF_TILE - 1) / NVB_PF_TILE, 4), dim3(256), 0, [&] { k_polyphase_2d(Q); });
+        emu::launch(dim3((dw + NVB_PF_TILE - 1) / NVB_PF_TILE, (dh + NVB_PF_TILE - 1) / NVB_PF_TILE, 4), dim3(256), 0, [&] {
+            if (Q.winx == 13 && Q.winy == 13) k_polyphase_2d_t<13, 13>(Q);
+            else if (Q.winx == 9 && Q.winy == 9) k_polyphase_2d_t<9, 9>(Q);
+            else if (Q.winx == 5 && Q.winy == 5) k_polyphase_2d_t<5, 5>(Q);
+            else k_polyphase_2d_t<0, 0>(Q);
+        });
         return;
     }
     std::vector<float> tmp((size_t)dw * sh * 4);
