@@ -154,22 +154,35 @@ template <int NIDX> NVB_DEV float zs_eval(const float4 *px, int np, int a0, int 
             for (int j = 0; j < NIDX; ++j)
                 pal[ch][j] = (float)zoh_finish_unquantize((ua[ch] * avpcl_wc(NIDX, NIDX - 1 - j) + ub[ch] * avpcl_wc(NIDX, j) + 32) >> 6, sgn);
     }
+    // two palette entries per FADD2 / FMUL2; the sum of the squares stays scalar (see bx_eval in bc7_search.cuh)
+    float2 npal[3][NIDX / 2];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+        for (int j = 0; j < NIDX / 2; ++j) npal[ch][j] = make_float2(-pal[ch][2 * j], -pal[ch][2 * j + 1]);
     float tot = 0;
     for (int i = 0; i < np; ++i) {
         const float4 c = px[i];
+        const float2 cx = f2splat(c.x), cy = f2splat(c.y), cz = f2splat(c.z), imp = f2splat(c.w);
         float best = 0;
         bool live = true;
 #pragma unroll
-        for (int j = 0; j < NIDX; ++j) {
-            const float x = c.x - pal[0][j], y = c.y - pal[1][j], z = c.z - pal[2][j];
-            const float e = (x * x + y * y + z * z) * c.w;
-            if (j == 0) {
-                best = e;
-            } else {
-                // "stop at the first increase (or at error 0)" scan of the reference, without branches
-                const bool gt = e > best, lt = e < best;
-                live = live && !gt;
-                best = (live && lt) ? e : best;
+        for (int jp = 0; jp < NIDX / 2; ++jp) {
+            const float2 x = f2add(cx, npal[0][jp]), y = f2add(cy, npal[1][jp]), z = f2add(cz, npal[2][jp]);
+            const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
+            const float2 n = make_float2(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y));
+            const float2 e2 = f2mul(n, imp);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float e = h ? e2.y : e2.x;
+                if (jp == 0 && h == 0) {
+                    best = e;
+                } else {
+                    // "stop at the first increase (or at error 0)" scan of the reference, without branches
+                    const bool gt = e > best, lt = e < best;
+                    live = live && !gt;
+                    best = (live && lt) ? e : best;
+                }
             }
         }
         tot += best;

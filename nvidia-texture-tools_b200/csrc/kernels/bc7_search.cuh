@@ -111,26 +111,40 @@ template <int M> NVB_DEV float bx_eval(const float4 *px, int np, unsigned A, uns
         }
         bx_lerp_row<N>(a, b, pal[ch], 1);
     }
+    // Two palette entries per instruction: the differences and squares issue as FADD2 / FMUL2 (c - p == c + (-p) exactly);
+    // the sums that consume the squares stay scalar (ptxas would contract a packed add of a packed product into FFMA2,
+    // nvb_common.cuh), in the reference's order ((x^2 + y^2) + z^2) + w^2.
+    float2 npal[C::NCH][N / 2];
+#pragma unroll
+    for (int ch = 0; ch < C::NCH; ch++)
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) npal[ch][j] = make_float2(-pal[ch][2 * j], -pal[ch][2 * j + 1]);
     float tot = 0;
     unsigned long long id = 0;
     for (int i = 0; i < np; ++i) {
         const float4 c = px[i];
         const float ww = c.w;
+        const float2 cx = f2splat(c.x), cy = f2splat(c.y), cz = f2splat(c.z), cw = f2splat(c.w);
         float best = 0;
         int bj = 0;
         bool live = true;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const float x = c.x - pal[0][j], y = c.y - pal[1][j], z = c.z - pal[2][j];
-            float e;
+        for (int jp = 0; jp < N / 2; ++jp) {
+            const float2 x = f2add(cx, npal[0][jp]), y = f2add(cy, npal[1][jp]), z = f2add(cz, npal[2][jp]);
+            const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
+            float e0, e1;
             if (C::NCH == 3) {
-                e = x * x + y * y + z * z + ww;
+                e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), ww);
+                e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), ww);
             } else {
-                const float w = c.w - pal[C::NCH - 1][j];
-                e = x * x + y * y + z * z + w * w;
+                const float2 w = f2add(cw, npal[C::NCH - 1][jp]);
+                const float2 w2 = f2mul(w, w);
+                e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), w2.x);
+                e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), w2.y);
             }
-            if (j == 0) best = e;
-            else NVB_BX_SCAN_STEP(e, j)
+            if (jp == 0) best = e0;
+            else NVB_BX_SCAN_STEP(e0, 2 * jp)
+            NVB_BX_SCAN_STEP(e1, 2 * jp + 1)
         }
         tot += best;
         id = (id << 4) | (unsigned long long)bj;  // only ever compared for equality
