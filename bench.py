@@ -210,9 +210,25 @@ def main():
     p_col = (C.c_void_p * 1)(h_col.data_ptr())
     p_nrm = (C.c_void_p * 1)(h_nrm.data_ptr())
 
-    def step_e2e():
+    def step_e2e_sequential():
         ctx._ck(ctx.L.nvttb_process(ctx.h, C.byref(desc3), p_col, m.HOST, emit_cb, None))
         ctx._ck(ctx.L.nvttb_process(ctx.h, C.byref(desc5), p_nrm, m.HOST, emit_cb, None))
+
+    # The two textures of a step are independent: a caller with a second context encodes them from two host threads, so
+    # that one texture's copies run under the other's kernels (the C ABI is thread-safe per context; the reference would
+    # serialise the two process() calls on its global thread pool).
+    from concurrent.futures import ThreadPoolExecutor
+    ctx2 = m.Context(local)
+    pool = ThreadPoolExecutor(2)
+
+    def _one(c, desc, ptrs):
+        c._ck(c.L.nvttb_process(c.h, C.byref(desc), ptrs, m.HOST, emit_cb, None))
+
+    def step_e2e():
+        a = pool.submit(_one, ctx, desc3, p_col)
+        b = pool.submit(_one, ctx2, desc5, p_nrm)
+        a.result()
+        b.result()
 
     def barrier():
         if use_dist:
@@ -258,6 +274,17 @@ def main():
     barrier()
     dt = max_over_ranks(dt)
     e2e_value = world * mpix_step * args.steps / dt
+    # the same step with one context and one host thread (the two calls back to back), for comparison
+    for _ in range(2):
+        step_e2e_sequential()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_sequential()
+    ctx.synchronize()
+    dt_seq = time.perf_counter() - t0
+    barrier()
+    dt_seq = max_over_ranks(dt_seq)
 
     line = None
     if rank == 0:
@@ -309,7 +336,9 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * SIZE * SIZE * 4,
-                    "d2h_bytes_per_step": 2 * out_bytes, "ms_per_step": dt / args.steps * 1e3},
+                    "d2h_bytes_per_step": 2 * out_bytes, "ms_per_step": dt / args.steps * 1e3,
+                    "how": "nvttb_process with pinned host buffers; the step's two textures on two contexts from two host threads",
+                    "one_context_sequential": {"value": world * mpix_step * args.steps / dt_seq, "ms_per_step": dt_seq / args.steps * 1e3}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
     barrier()
