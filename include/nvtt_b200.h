@@ -136,6 +136,9 @@ NVTTB_API int nvttb_surface_set_image_2d(NvttbSurface *s, int format, int decode
  * AlphaMode_Transparency.  *out = FLT_MAX when the layouts differ (as in the reference). */
 NVTTB_API int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
 NVTTB_API int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
+/* nvtt::angularError = nv::rmsAngularError (src/nvtt/Surface.cpp:3287-3291, src/nvimage/ErrorMetric.cpp:475-511): RMS angle
+ * between the unpacked, normalised normals, in radians (acosf: CUDA vs glibc, 1e-5 relative). */
+NVTTB_API int nvttb_angular_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
 /* Surface::data(): copy planar fp32 RGBA (4*w*h floats) to the host. */
 NVTTB_API int nvttb_surface_download(const NvttbSurface *s, float *out);
 /* Device pointer of the planar fp32 data (valid until the next op on the surface). */

@@ -61,7 +61,7 @@ EXPORTS = [
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
     "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
-    "nvttb_surface_binarize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error",
+    "nvttb_surface_binarize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
 ]
@@ -108,6 +108,7 @@ def lib():
     L.nvttb_surface_binarize.argtypes = [vp, ci, cf, ci]
     L.nvttb_rms_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_rms_alpha_error.argtypes = [vp, vp, C.POINTER(cf)]
+    L.nvttb_angular_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_surface_to_linear.argtypes = [vp, cf]
     L.nvttb_surface_to_gamma.argtypes = [vp, cf]
     L.nvttb_surface_build_next_mipmap.argtypes = [vp, ci, ci, cf, C.POINTER(cf), C.POINTER(ci)]
@@ -297,6 +298,11 @@ class Surface:
         """nvtt::rmsError(self as reference, img)."""
         v = C.c_float()
         self.ctx._ck(self.L.nvttb_rms_error(self.h, img.h, C.byref(v)))
+        return v.value
+
+    def angular_error(self, img):
+        v = C.c_float()
+        self.ctx._ck(self.L.nvttb_angular_error(self.h, img.h, C.byref(v)))
         return v.value
 
     def rms_alpha_error(self, img):

@@ -1059,6 +1059,7 @@ int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, floa
     return error_metric(reference, img, (reference && reference->alphaMode == AM_Transparency) ? 1 : 0, out);
 }
 int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 2, out); }
+int nvttb_angular_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 3, out); }
 
 int nvttb_surface_to_linear(NvttbSurface *s, float gamma) {
     if (!s) return NVTTB_ERR_INVALID_INPUT;

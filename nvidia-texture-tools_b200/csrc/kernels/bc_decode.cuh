@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128) k_decode_blocks(DecodeParams P) {
 struct ErrorParams {
     const float *ref, *img;  // planar fp32 [4][count]
     size_t count;
-    int mode;                // 0: rmsColorError, 1: rmsColorError alpha-weighted (a0*a0), 2: rmsAlphaError
+    int mode;                // 0: rmsColorError, 1: rmsColorError alpha-weighted (a0*a0), 2: rmsAlphaError, 3: rmsAngularError
     double *partial;         // one per CTA
 };
 
@@ -366,6 +366,20 @@ __global__ void __launch_bounds__(256) k_error_metric(ErrorParams P) {
         if (P.mode == 2) {
             const float a = P.img[i + P.count * 3] - P.ref[i + P.count * 3];
             acc += (double)(a * a);
+        } else if (P.mode == 3) {
+            // nv::rmsAngularError (ErrorMetric.cpp:475-511): unpack, normalizeSafe(v, 0, 0), angle = acosf(clamp(dot)); the
+            // reference's acosf is glibc's, ours CUDA's: the metric is compared with a 1e-5 relative tolerance
+            float n0[3], n1[3];
+            for (int k = 0; k < 3; k++) {
+                n0[k] = 2.0f * P.ref[i + P.count * k] - 1.0f;
+                n1[k] = 2.0f * P.img[i + P.count * k] - 1.0f;
+            }
+            const float l0 = sqrtf(n0[0] * n0[0] + n0[1] * n0[1] + n0[2] * n0[2]), l1 = sqrtf(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+            const float s0 = (fabsf(l0) <= 0.0f) ? 0.0f : 1.0f / l0, s1 = (fabsf(l1) <= 0.0f) ? 0.0f : 1.0f / l1;
+            float d = 0.0f;
+            if (s0 != 0.0f && s1 != 0.0f) d = (n0[0] * s0) * (n1[0] * s1) + (n0[1] * s0) * (n1[1] * s1) + (n0[2] * s0) * (n1[2] * s1);
+            const float angle = acosf(nv_clamp(d, -1.0f, 1.0f));
+            acc += (double)(angle * angle);
         } else {
             const float r = P.ref[i] - P.img[i], g = P.ref[i + P.count] - P.img[i + P.count], b = P.ref[i + P.count * 2] - P.img[i + P.count * 2];
             float a = 1.0f;

@@ -184,6 +184,7 @@ struct Surface {
 // src/nvtt/nvtt.h:699-700
 NVTT_API float rmsError(const Surface &reference, const Surface &img);
 NVTT_API float rmsAlphaError(const Surface &reference, const Surface &img);
+NVTT_API float angularError(const Surface &reference, const Surface &img);
 
 NVTT_API unsigned int version();
 NVTT_API const char *errorString(Error e);

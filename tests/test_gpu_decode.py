@@ -16,6 +16,7 @@ def _harness(path):
     L = C.CDLL(path)
     L.ref_decode_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_rms_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.ref_angular_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     return L
 
 
@@ -171,3 +172,19 @@ def test_rms_error_matches_reference(nvtt, ctx, libs):
             (a0, b0), (a1, b1) = vals
             assert a1 > 0 and abs(a0 - a1) <= 1e-6 * a1, (fmt, am, a0, a1)
             assert abs(b0 - b1) <= 1e-6 * max(b1, 1e-30), (fmt, am, b0, b1)
+
+
+def test_angular_error_matches_reference(nvtt, ctx, libs):
+    """nvtt::angularError of a BC5 / BC3n encoded normal map: acosf differs between glibc and CUDA, hence 1e-5 relative."""
+    ours, theirs = libs
+    w, h = 128, 96
+    planar = nvtt.synth.planar_from_bgra8(nvtt.synth.normal_bgra8(w, h, seed=3))
+    rgba = np.ascontiguousarray(np.moveaxis(planar, 0, 2))
+    for fmt in (7, 1):
+        blocks = ctx.encode_level(fmt, 1, planar)
+        vals = []
+        for L in (ours, theirs):
+            v = C.c_float()
+            assert L.ref_angular_error(fmt, w, h, blocks.ctypes.data, rgba.ctypes.data, C.byref(v)) == 1
+            vals.append(v.value)
+        assert vals[1] > 0 and abs(vals[0] - vals[1]) <= 1e-5 * vals[1], (fmt, vals)
