@@ -120,9 +120,11 @@ NVTTB_API int nvttb_surface_resize(NvttbSurface *s, int w, int h, int resizeFilt
 NVTTB_API int nvttb_surface_expand_normals(NvttbSurface *s);
 NVTTB_API int nvttb_surface_normalize_normal_map(NvttbSurface *s);
 NVTTB_API int nvttb_surface_pack_normals(NvttbSurface *s);
-/* Surface::binarize(channel, threshold, dither)  src/nvtt/Surface.cpp:2656-2713.  dither != 0 (Floyd-Steinberg) is not
- * implemented (NVTTB_ERR_UNSUPPORTED_FEATURE); the compress pipeline never asks for it (Context.cpp:533-540). */
+/* Surface::binarize(channel, threshold, dither) and Surface::quantize(channel, bits, exactEndPoints, dither)
+ * src/nvtt/Surface.cpp:2656-2775.  dither != 0 = the reference's Floyd-Steinberg scan (bit-identical: a skewed wavefront on
+ * one SM per plane, so it is slow next to everything else here - use it the way the reference does, for final output). */
 NVTTB_API int nvttb_surface_binarize(NvttbSurface *s, int channel, float threshold, int dither);
+NVTTB_API int nvttb_surface_quantize(NvttbSurface *s, int channel, int bits, int exactEndPoints, int dither);
 /* Surface::toGreyScale / toNormalMap  src/nvtt/Surface.cpp:1732-1756,2794-2808 */
 NVTTB_API int nvttb_surface_to_grey_scale(NvttbSurface *s, float r, float g, float b, float a);
 NVTTB_API int nvttb_surface_to_normal_map(NvttbSurface *s, float sm, float medium, float big, float large);

@@ -44,9 +44,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize", "k_quantize"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -1142,17 +1142,51 @@ static int scale_bias(NvttbSurface *s, float scale, float bias) {
 }
 int nvttb_surface_expand_normals(NvttbSurface *s) { return s ? scale_bias(s, 2.0f, -1.0f) : NVTTB_ERR_INVALID_INPUT; }
 int nvttb_surface_pack_normals(NvttbSurface *s) { return s ? scale_bias(s, 0.5f, 0.5f) : NVTTB_ERR_INVALID_INPUT; }
-int nvttb_surface_binarize(NvttbSurface *s, int channel, float threshold, int dither) {
-    if (!s || channel < 0 || channel > 3) return NVTTB_ERR_INVALID_INPUT;
+static int quantize_channel(NvttbSurface *s, int channel, QuantizeParams P) {
     NvttbContext *ctx = s->ctx;
+    if (channel < 0 || channel > 3) return NVTTB_ERR_INVALID_INPUT;
     if (!s->buf.p) return NVTTB_OK;
-    if (dither) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "binarize with Floyd-Steinberg dithering is not implemented");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)s->w * s->h;
-    BinarizeParams P{(float *)s->buf.p + (size_t)channel * n, n, threshold};
-    NVB_LAUNCH(ctx, K_BINARIZE, (double)n, k_binarize, grid_for(n, 256), 256, P);
+    P.data = (float *)s->buf.p + (size_t)channel * n;
+    P.w = s->w;
+    P.h = s->h;
+    P.carry = nullptr;
+    if (P.dither) {
+        // Floyd-Steinberg: one CTA walks the plane as a wavefront (k_quantize_dither); two rows of carried errors
+        int rc = ensure(ctx, ctx->tmp_filter, (size_t)2 * s->w * sizeof(float));
+        if (rc != NVTTB_OK) return rc;
+        P.carry = (float *)ctx->tmp_filter.p;
+        NVB_LAUNCH(ctx, K_QUANTIZE, (double)n, k_quantize_dither, 1, NVB_FS_ROWS, P);
+    } else {
+        NVB_LAUNCH(ctx, K_QUANTIZE, (double)n, k_quantize, grid_for(n, 256), 256, P);
+    }
     CK(cudaGetLastError());
     return NVTTB_OK;
+}
+int nvttb_surface_binarize(NvttbSurface *s, int channel, float threshold, int dither) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    QuantizeParams P = {};
+    P.binarize = 1;
+    P.threshold = threshold;
+    P.dither = dither ? 1 : 0;
+    return quantize_channel(s, channel, P);
+}
+int nvttb_surface_quantize(NvttbSurface *s, int channel, int bits, int exactEndPoints, int dither) {
+    if (!s || bits < 1 || bits > 24) return NVTTB_ERR_INVALID_INPUT;
+    QuantizeParams P = {};
+    P.binarize = 0;
+    P.dither = dither ? 1 : 0;
+    if (exactEndPoints) {  // floor(x * (range - 1) + 0.5) / (range - 1)
+        P.scale = (float)((1 << bits) - 1);
+        P.offset0 = 0.5f;
+        P.offset1 = 0.0f;
+    } else {  // (floor(x * range) + 0.5) / range
+        P.scale = (float)(1 << bits);
+        P.offset0 = 0.0f;
+        P.offset1 = 0.5f;
+    }
+    return quantize_channel(s, channel, P);
 }
 int nvttb_surface_normalize_normal_map(NvttbSurface *s) {
     if (!s) return NVTTB_ERR_INVALID_INPUT;

@@ -372,6 +372,73 @@ __global__ void __launch_bounds__(256) k_binarize(BinarizeParams P) {
         P.data[i] = (P.data[i] > P.threshold) ? 1.0f : 0.0f;
 }
 
+// Surface::quantize(channel, bits, exactEndPoints, dither) and Surface::binarize(channel, threshold, dither = true)
+// (src/nvtt/Surface.cpp:2656-2775).  Without dithering: element-wise.  With dithering: the reference's Floyd-Steinberg scan,
+// where the value of texel (x, y) depends on the quantisation error d of (x-1, y) and of (x-1, y-1), (x, y-1), (x+1, y-1):
+//     E(x, y) = (((0 + 1/16 d(x-1,y-1)) + 5/16 d(x,y-1)) + 3/16 d(x+1,y-1)) + 7/16 d(x-1,y)        [row1[] / row0[] cells]
+//     q = Q(f + E),  d = f - q   (sic: the error that is propagated is f - q, not (f + E) - q)
+// That recurrence is a wavefront with skew 2: one CTA per channel, one thread per row of a band of 1024 rows, thread r
+// works on x = t - 2r at step t and reads the three errors of the row above from a 4-deep history in shared memory (one
+// __syncthreads per step).  The last row of a band leaves its errors in global memory for the first row of the next band.
+// Every cell is accumulated in the reference's order, so the result is bit-identical.
+struct QuantizeParams {
+    float *data;       // the channel's plane
+    int w, h;
+    float scale, offset0, offset1;  // quantize: q = saturate((floorf(v * scale + offset0) + offset1) / scale)
+    float threshold;   // binarize: q = float(v > threshold)
+    int binarize;
+    int dither;
+    float *carry;      // dither: w floats of scratch (errors of the last row of the previous band)
+};
+NVB_DEV float quantize_value(const QuantizeParams &P, float v) {
+    if (P.binarize) return (v > P.threshold) ? 1.0f : 0.0f;
+    return nv_clamp((floorf(v * P.scale + P.offset0) + P.offset1) / P.scale, 0.0f, 1.0f);
+}
+__global__ void __launch_bounds__(256) k_quantize(QuantizeParams P) {
+    const size_t n = (size_t)P.w * P.h;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        P.data[i] = quantize_value(P, P.data[i]);
+}
+#define NVB_FS_ROWS 1024
+__global__ void __launch_bounds__(NVB_FS_ROWS) k_quantize_dither(QuantizeParams P) {
+    __shared__ float s_hist[NVB_FS_ROWS][4];  // s_hist[r][t & 3] = d of row r computed at step t
+    const int r = threadIdx.x;
+    int band = 0;
+    for (int y0 = 0; y0 < P.h; y0 += NVB_FS_ROWS, ++band) {
+        const int rows = min(NVB_FS_ROWS, P.h - y0);
+        const int y = y0 + r;
+        const bool active = r < rows;
+        float *row = P.data + (size_t)(active ? y : 0) * P.w;
+        const float *carry_in = P.carry + (size_t)(band & 1) * P.w;         // errors of the last row of the previous band
+        float *carry_out = P.carry + (size_t)((band + 1) & 1) * P.w;
+        float dl = 0.0f;  // d(x-1, y)
+        const int steps = P.w + 2 * (rows - 1);
+        for (int t = 0; t < steps; t++) {
+            const int x = t - 2 * r;
+            float d = 0.0f;
+            if (active && x >= 0 && x < P.w) {
+                float e = 0.0f;  // the row1[] cell: zero-initialised, then += in the order of the reference's scan
+                if (y > 0) {
+                    // thread r-1 computed x+1 at step t-1, x at t-2 and x-1 at t-3
+                    if (x - 1 >= 0) e += (1.0f / 16.0f) * (r > 0 ? s_hist[r - 1][(t - 3) & 3] : carry_in[x - 1]);
+                    e += (5.0f / 16.0f) * (r > 0 ? s_hist[r - 1][(t - 2) & 3] : carry_in[x]);
+                    if (x + 1 < P.w) e += (3.0f / 16.0f) * (r > 0 ? s_hist[r - 1][(t - 1) & 3] : carry_in[x + 1]);
+                }
+                if (x > 0) e += (7.0f / 16.0f) * dl;
+                const float f = row[x];
+                const float q = quantize_value(P, f + e);
+                d = f - q;
+                row[x] = q;
+                dl = d;
+                if (r == rows - 1) carry_out[x] = d;
+            }
+            // slot t & 3 was last read during step t-1 (as "t-4"... i.e. never again): safe to overwrite before the barrier
+            s_hist[r][t & 3] = d;
+            __syncthreads();
+        }
+    }
+}
+
 struct NormalizeParams {
     float *data;
     size_t pixels;

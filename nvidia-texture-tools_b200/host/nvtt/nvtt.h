@@ -174,6 +174,7 @@ struct Surface {
     NVTT_API void toGreyScale(float redScale, float greenScale, float blueScale, float alphaScale);
     NVTT_API void toNormalMap(float sm, float medium, float big, float large);
     NVTT_API void binarize(int channel, float threshold, bool dither);
+    NVTT_API void quantize(int channel, int bits, bool exactEndPoints, bool dither);
     NVTT_API void normalizeNormalMap();
     NVTT_API void packNormals(float scale = 0.5f, float bias = 0.5f);
     NVTT_API void expandNormals(float scale = 2.0f, float bias = -1.0f);

@@ -408,6 +408,11 @@ void Surface::binarize(int channel, float threshold, bool dither) {
     m->hostValid = false;
     nvttb_surface_binarize(m->s, channel, threshold, dither ? 1 : 0);
 }
+void Surface::quantize(int channel, int bits, bool exactEndPoints, bool dither) {
+    if (isNull()) return;
+    m->hostValid = false;
+    nvttb_surface_quantize(m->s, channel, bits, exactEndPoints ? 1 : 0, dither ? 1 : 0);
+}
 void Surface::packNormals(float scale, float bias) {
     if (isNull()) return;
     m->hostValid = false;
@@ -651,6 +656,16 @@ bool Compressor::compress(const Surface &img, int face, int mipmap, const Compre
     return compress_level(m, img.alphaMode(), img.width(), img.height(), 1, face, mipmap, nvttb_surface_device_data(img.m->s), NVTTB_DEVICE, co.m, oo.m);
 }
 
+// Compressor::Private::quantize (Context.cpp:519-541)
+static void quantize_surface(Surface &img, const CompressionOptions::Private &co) {
+    if (co.enableColorDithering && co.format >= Format_BC1 && co.format <= Format_BC3) {
+        img.quantize(0, 5, true, true);
+        img.quantize(1, 6, true, true);
+        img.quantize(2, 5, true, true);
+    }
+    if (!co.enableAlphaDithering && co.binaryAlpha) img.binarize(3, float(co.alphaThreshold) / 255.0f, co.enableAlphaDithering);
+}
+
 // Compressor::Private::compress(InputOptions...)  (Context.cpp:217-346), DDS order.
 bool Compressor::process(const InputOptions &inputOptions, const CompressionOptions &compressionOptions, const OutputOptions &outputOptions) const {
     const InputOptions::Private &io = inputOptions.m;
@@ -677,12 +692,13 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         oo.error(Error_CudaError);
         return false;
     }
-    // Compressor::Private::quantize (Context.cpp:519-541): colour dithering acts on BC1..BC3 (Floyd-Steinberg: not implemented);
+    // Compressor::Private::quantize (Context.cpp:519-541): colour dithering acts on BC1..BC3 (5/6/5 bits, Floyd-Steinberg);
     // alpha dithering only on Format_RGB, i.e. never here; binary alpha = non-dithered binarize, and only when alpha dithering
     // is off (so nvcompress's settings for -bc1a / -bc2 are both no-ops, as in the reference).
     const bool colorDither = co.enableColorDithering && co.format >= Format_BC1 && co.format <= Format_BC3;
     const bool binarizeAlpha = !co.enableAlphaDithering && co.binaryAlpha;
-    if (depth != 1 || colorDither || !nvttb_format_supported(co.format, co.quality)) {
+    const bool quantizeStep = colorDither || binarizeAlpha;
+    if (depth != 1 || !nvttb_format_supported(co.format, co.quality)) {
         oo.error(Error_UnsupportedFeature);
         return false;
     }
@@ -713,7 +729,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
             s.resize(w, h, 1, ResizeFilter_Box);
             Surface tmp = s;
             if (!s.isNormalMap()) tmp.toGamma(io.outputGamma);
-            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
+            if (quantizeStep) quantize_surface(tmp, co);
             if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
             images.push_back(s);
         }
@@ -744,7 +760,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
                     tmp = img;
                     tmp.toGamma(io.outputGamma);
                 }
-                if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
+                if (quantizeStep) quantize_surface(tmp, co);
                 if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
             }
             const int mipPadding = 3 - ((imageSize + 3) % 4);
@@ -753,7 +769,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         return true;
     }
 
-    if (canUseSourceImages && !userMips && !binarizeAlpha) {
+    if (canUseSourceImages && !userMips && !quantizeStep) {
         // fused device pipeline
         NvttbProcessDesc d;
         memset(&d, 0, sizeof d);
@@ -798,7 +814,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         {
             Surface tmp = img;
             if (!img.isNormalMap()) tmp.toGamma(io.outputGamma);
-            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
+            if (quantizeStep) quantize_surface(tmp, co);
             if (!compress(tmp, f, 0, compressionOptions, outputOptions)) return false;
         }
         for (int mip = 1; mip < mipmapCount; mip++) {
@@ -831,7 +847,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
                 tmp = img;
                 tmp.toGamma(io.outputGamma);
             }
-            if (binarizeAlpha) tmp.binarize(3, float(co.alphaThreshold) / 255.0f, false);  // quantize(tmp, ...)
+            if (quantizeStep) quantize_surface(tmp, co);
             if (!compress(tmp, f, mip, compressionOptions, outputOptions)) return false;
         }
     }

@@ -216,6 +216,8 @@ void ref_surf_pack_normals(void *h) { ((Surface *)h)->packNormals(); }
 void ref_surf_normalize_normal_map(void *h) { ((Surface *)h)->normalizeNormalMap(); }
 void ref_surf_to_grey_scale(void *h, float r, float g, float b, float a) { ((Surface *)h)->toGreyScale(r, g, b, a); }
 void ref_surf_to_normal_map(void *h, float sm, float md, float bg, float lg) { ((Surface *)h)->toNormalMap(sm, md, bg, lg); }
+void ref_surf_quantize(void *h, int channel, int bits, int exactEndPoints, int dither) { ((Surface *)h)->quantize(channel, bits, exactEndPoints != 0, dither != 0); }
+void ref_surf_binarize(void *h, int channel, float threshold, int dither) { ((Surface *)h)->binarize(channel, threshold, dither != 0); }
 
 // Decode a BCn level with the library's decoder (Surface::setImage2D, src/nvtt/Surface.cpp:908-1118) -> planar fp32.
 int ref_decode_ex(int format, int decoder, int w, int h, const void *data, float *out) {

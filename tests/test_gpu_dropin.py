@@ -37,6 +37,8 @@ def _load_harness(ref, so):
     L.ref_surf_to_linear.argtypes = [C.c_void_p, C.c_float]
     L.ref_surf_to_gamma.argtypes = [C.c_void_p, C.c_float]
     L.ref_surf_build_next_mipmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.ref_surf_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ref_surf_binarize.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
     return L
 
 
@@ -91,6 +93,38 @@ def test_quantization_settings_identical(nvtt, ref, ours):
             got = _process(ours, ref, [img], fmt, 1, 64, 48, **kw)
             want = _process(ref.lib(), ref, [img], fmt, 1, 64, 48, **kw)
             assert got.size == want.size and np.array_equal(got, want), (fmt, q, thr)
+
+
+def test_surface_quantize_and_binarize_identical(nvtt, ref, ours):
+    """Surface::quantize / binarize, plain and with the Floyd-Steinberg scan (more rows than one 1024-row band, odd sizes)."""
+    ref.lib().ref_surf_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    ref.lib().ref_surf_binarize.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+    for (w, h) in ((37, 22), (64, 1100), (1, 5), (300, 3)):
+        im8 = nvtt.synth.photo_bgra8(w, h, seed=w + h, alpha=True)
+        for dither in (0, 1):
+            outs = []
+            for L in (ours, ref.lib()):
+                s = L.ref_surf_create(2, 0, 0)
+                assert L.ref_surf_set_image(s, 0, w, h, im8.ctypes.data)
+                L.ref_surf_quantize(s, 0, 5, 1, dither)
+                L.ref_surf_quantize(s, 1, 6, 1, dither)
+                L.ref_surf_quantize(s, 2, 3, 0, dither)
+                L.ref_surf_binarize(s, 3, 0.4, dither)
+                o = np.empty((4, h, w), np.float32)
+                L.ref_surf_get(s, o.ctypes.data)
+                L.ref_surf_destroy(s)
+                outs.append(o)
+            assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32)), (w, h, dither)
+
+
+def test_color_dithering_pipeline_identical(nvtt, ref, ours):
+    """setQuantization(colorDithering = true): 5/6/5-bit Floyd-Steinberg on every mip level before BC1 / BC3 (Context.cpp:519-531)."""
+    img = nvtt.synth.photo_bgra8(96, 72, seed=41, alpha=True)
+    for fmt in (ref.Format_BC1, ref.Format_BC3):
+        kw = dict(mip_filter=0, quantization=1)
+        got = _process(ours, ref, [img], fmt, 1, 96, 72, **kw)
+        want = _process(ref.lib(), ref, [img], fmt, 1, 96, 72, **kw)
+        assert got.size == want.size and np.array_equal(got, want), fmt
 
 
 def test_ktx_cube_identical(nvtt, ref, ours):
