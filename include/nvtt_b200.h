@@ -84,6 +84,7 @@ typedef struct NvttbEncodeDesc {
     float colorWeights[4]; /* CompressionOptions::setColorWeights */
     int width, height;     /* texels; depth is 1 */
     int applyToGamma;      /* 1: fuse Surface::toGamma(2.2) on R,G,B into the block gather (pipeline use) */
+    float rgbmThreshold;   /* CompressionOptions::setRGBMThreshold (Format_BC3_RGBM; the reference's default is 0.15) */
 } NvttbEncodeDesc;
 
 /* Bytes of one encoded level = blocks * block size (nv::computeImageSize, src/nvtt/Surface.cpp:210-218); 0 if unsupported. */

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200.so")
 
 # nvtt enums (src/nvtt/nvtt.h:80-277 of the reference)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
-Format_BC6, Format_BC7 = 10, 11
+Format_BC6, Format_BC7, Format_BC3_RGBM = 10, 11, 12
 Format_BC1, Format_BC2, Format_BC3, Format_BC3n = Format_DXT1, Format_DXT3, Format_DXT5, Format_DXT5n
 Quality_Fastest, Quality_Normal, Quality_Production, Quality_Highest = range(4)
 WrapMode_Clamp, WrapMode_Repeat, WrapMode_Mirror = range(3)
@@ -32,7 +32,8 @@ class NvttbError(RuntimeError):
 
 class EncodeDesc(C.Structure):
     _fields_ = [("format", C.c_int), ("quality", C.c_int), ("alphaMode", C.c_int), ("pixelType", C.c_int),
-                ("colorWeights", C.c_float * 4), ("width", C.c_int), ("height", C.c_int), ("applyToGamma", C.c_int)]
+                ("colorWeights", C.c_float * 4), ("width", C.c_int), ("height", C.c_int), ("applyToGamma", C.c_int),
+                ("rgbmThreshold", C.c_float)]
 
 
 class ProcessDesc(C.Structure):
@@ -133,8 +134,9 @@ def lib():
 
 
 def make_encode_desc(fmt, quality, w=0, h=0, alpha_mode=AlphaMode_None, color_weights=(1, 1, 1, 1),
-                     pixel_type=PixelType_UnsignedNorm, apply_to_gamma=False):
+                     pixel_type=PixelType_UnsignedNorm, apply_to_gamma=False, rgbm_threshold=0.15):
     d = EncodeDesc()
+    d.rgbmThreshold = rgbm_threshold
     d.format, d.quality, d.alphaMode, d.pixelType = fmt, quality, alpha_mode, pixel_type
     d.colorWeights = (C.c_float * 4)(*color_weights)
     d.width, d.height, d.applyToGamma = w, h, int(apply_to_gamma)

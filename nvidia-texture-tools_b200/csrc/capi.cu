@@ -26,7 +26,7 @@
 using namespace nvb;
 
 // nvtt enums used here (src/nvtt/nvtt.h:80-277)
-enum { F_RGB = 0, F_DXT1 = 1, F_DXT1a = 2, F_DXT3 = 3, F_DXT5 = 4, F_DXT5n = 5, F_BC4 = 6, F_BC5 = 7, F_BC6 = 10, F_BC7 = 11 };
+enum { F_RGB = 0, F_DXT1 = 1, F_DXT1a = 2, F_DXT3 = 3, F_DXT5 = 4, F_DXT5n = 5, F_BC4 = 6, F_BC5 = 7, F_BC6 = 10, F_BC7 = 11, F_BC3_RGBM = 12 };
 enum { Q_Fastest = 0, Q_Normal = 1, Q_Production = 2, Q_Highest = 3 };
 enum { AM_None = 0, AM_Transparency = 1, AM_Premultiplied = 2 };
 enum { MF_Box = 0, MF_Triangle = 1, MF_Kaiser = 2 };
@@ -165,7 +165,7 @@ static inline unsigned grid_for(size_t items, int per_cta) {
 static int block_bytes(int format) {
     switch (format) {
     case F_DXT1: case F_DXT1a: case F_BC4: return 8;
-    case F_DXT3: case F_DXT5: case F_DXT5n: case F_BC5: case F_BC6: case F_BC7: return 16;
+    case F_DXT3: case F_DXT5: case F_DXT5n: case F_BC5: case F_BC6: case F_BC7: case F_BC3_RGBM: return 16;
     default: return 0;
     }
 }
@@ -421,7 +421,8 @@ int nvttb_format_supported(int format, int quality) {
         return quality >= Q_Fastest && quality <= Q_Highest;
     case F_BC6:
     case F_BC7:
-        return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102)
+    case F_BC3_RGBM:
+        return 1;  // quality is ignored for BC6 / BC7 (CompressorDX11.cpp:42-102) and BC3-RGBM (BlockCompressor.cpp:235-238)
     default:
         return 0;
     }
@@ -529,6 +530,35 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.match5 = ctx->d_icbc_match;
         P.match6 = ctx->d_icbc_match + 512;
         NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
+    } else if (d->format == F_BC3_RGBM) {
+        // CompressorBC3_RGBM -> compress_dxt5_rgbm (BlockCompressor.cpp:235-238, CompressorDXT5_RGBM.cpp:54-118):
+        // colour block = ICBC Quality_Default (Level 8) on (R,G,B)/M with weights w*M, no 3-colour mode, colour weights 1;
+        // alpha block = weighted brute-force fit of the multiplier that compensates the colour block's error
+        Bc1Params P;
+        P.lv = lv;
+        P.out = d_out;
+        P.out_stride = 16;
+        P.out_offset = 8;
+        P.level = 8;
+        P.transparency = (d->alphaMode == AM_Transparency);
+        P.cw[0] = P.cw[1] = P.cw[2] = 1.0f;
+        P.four = ctx->d_icbc_splits;
+        P.three = ctx->d_icbc_splits + ctx->icbc_four_count;
+        P.four_total = ctx->d_icbc_totals;
+        P.three_total = ctx->d_icbc_totals + 16;
+        P.midpoints5 = ctx->d_icbc_mid;
+        P.midpoints6 = ctx->d_icbc_mid + 32;
+        P.match5 = ctx->d_icbc_match;
+        P.match6 = ctx->d_icbc_match + 512;
+        P.rgbm = 1;
+        P.rgbm_min = d->rgbmThreshold;
+        NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
+        RgbmAlphaParams A;
+        A.lv = lv;
+        A.out = d_out;
+        A.min_m = d->rgbmThreshold;
+        A.transparency = P.transparency;
+        NVB_LAUNCH(ctx, K_ALPHA_OPT, (double)w * h, k_rgbm_alpha, grid_for(nb, 4), 128, A);
     } else if (d->format == F_BC4) {
         // Fastest/Normal -> QuickCompress, Production/Highest -> OptimalCompress (Context.cpp:1098-1115)
         alpha(0, 8, 0, d->quality >= Q_Production);

@@ -40,6 +40,8 @@ struct Bc1Params {
     const float *midpoints6;      // [64]
     const unsigned char *match5;  // [256][2] ICBC single-colour tables
     const unsigned char *match6;  // [256][2]
+    int rgbm = 0;                 // BC3-RGBM colour block: texels become (R,G,B)/M, weights w*M, no 3-colour mode
+    float rgbm_min = 0.15f;       //   M = max(R, G, B, rgbm_min)   (CompressorDXT5_RGBM.cpp:23-49)
 };
 
 #define NVB_BC1_GROUPS 8
@@ -369,6 +371,16 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
         wt = 1.0f;
         if (P.transparency) wt = icbc_saturate(load_texel(P.lv, 3, px, py));
     }
+    if (P.rgbm) {
+        // convert_to_rgbm (CompressorDXT5_RGBM.cpp:23-49)
+        const float R = icbc_saturate(cx), G = icbc_saturate(cy), B = icbc_saturate(cz);
+        const float M = nv_max(nv_max(R, G), nv_max(B, P.rgbm_min));
+        cx = R / M;
+        cy = G / M;
+        cz = B / M;
+        const float weight_sum = group_ordered_sum(gm, wt);
+        wt = (weight_sum == 0) ? 1.0f : wt * M;
+    }
     unsigned char *dst = P.out + (size_t)blkid * P.out_stride + P.out_offset;
     Bc1Block out;
     out.c0 = out.c1 = out.indices = 0;
@@ -493,8 +505,8 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
         float best = icbc_output_block(P, gm, l, true, false, f4.sx, f4.sy, f4.sz, f4.ex, f4.ey, f4.ez, cx, cy, cz, wt, &cf);
         // three colour mode (Levels 8/9: always tried; transparent black allowed)
         int sat_count = count;
-        bool do_three = true;
-        if (any_black) {
+        bool do_three = !P.rgbm;  // compress_dxt5_rgbm passes three_color_mode = false
+        if (do_three && any_black) {
             // skip_blacks on the reduced set, then a new SAT
             const float4 q = (l < count) ? S.pts[l] : make_float4(1.f, 1.f, 1.f, 0.f);
             const bool keep = (l < count) && !((q.x < 1.0f / 8) && (q.y < 1.0f / 8) && (q.z < 1.0f / 8));

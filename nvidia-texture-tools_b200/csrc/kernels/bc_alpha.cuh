@@ -479,4 +479,145 @@ __global__ void __launch_bounds__(128) k_dxt1g_optimal(AlphaBlocksParams P) {
     }
 }
 
+// ---- BC3-RGBM multiplier block (compress_dxt5_rgbm, CompressorDXT5_RGBM.cpp:54-118) ---------------------------------------
+// After the colour block (R,G,B)/M has been encoded: decode it, solve the per-texel multiplier m in the least-squares sense,
+// quantise it to 8 bits and run OptimalCompress::compressDXT5A on those values *with the texel weights* (fp32 error sums in
+// texel order, computeAlphaError :189-217).  One warp per block; every lane holds the block, the (alpha0, alpha1) pairs are
+// striped over the lanes as in k_alpha_optimal.
+struct RgbmAlphaParams {
+    LevelView lv;
+    unsigned char *out;   // 16-byte BC3 blocks: alpha block at +0, colour block (already written) at +8
+    float min_m;
+    int transparency;     // AlphaMode_Transparency: texel weight = saturate(alpha), else 1 (0 outside the image)
+};
+
+NVB_DEV float alpha_pair_error_w(const unsigned src[16], const float w[16], unsigned a0, unsigned a1) {
+    unsigned pal[8];
+    alpha_palette(a0, a1, pal);
+    float total = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        int best = 0x7fffffff;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            const int d = (int)src[i] - (int)pal[p];
+            best = min(best, d * d);
+        }
+        total += (float)best * w[i];
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(128) k_rgbm_alpha(RgbmAlphaParams P) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int nblocks = P.lv.bw * P.lv.bh;
+    for (int blk = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); blk < nblocks; blk += gridDim.x * warps_per_cta) {
+        unsigned char *dst = P.out + (size_t)blk * 16;
+        // colour block -> 8-bit palette (BlockDXT1::evaluatePalette, D3D10)
+        const uint2 cb = *reinterpret_cast<const uint2 *>(dst + 8);
+        const unsigned c0 = cb.x & 0xFFFFu, c1 = cb.x >> 16;
+        int pr[4], pg[4], pb[4];
+        {
+            const int r0 = (c0 >> 11) & 31, g0 = (c0 >> 5) & 63, b0 = c0 & 31, r1 = (c1 >> 11) & 31, g1 = (c1 >> 5) & 63, b1 = c1 & 31;
+            pr[0] = (r0 << 3) | (r0 >> 2); pg[0] = (g0 << 2) | (g0 >> 4); pb[0] = (b0 << 3) | (b0 >> 2);
+            pr[1] = (r1 << 3) | (r1 >> 2); pg[1] = (g1 << 2) | (g1 >> 4); pb[1] = (b1 << 3) | (b1 >> 2);
+            if (c0 > c1) {
+                pr[2] = (2 * pr[0] + pr[1]) / 3; pg[2] = (2 * pg[0] + pg[1]) / 3; pb[2] = (2 * pb[0] + pb[1]) / 3;
+                pr[3] = (2 * pr[1] + pr[0]) / 3; pg[3] = (2 * pg[1] + pg[0]) / 3; pb[3] = (2 * pb[1] + pb[0]) / 3;
+            } else {
+                pr[2] = (pr[0] + pr[1]) / 2; pg[2] = (pg[0] + pg[1]) / 2; pb[2] = (pb[0] + pb[1]) / 2;
+                pr[3] = pg[3] = pb[3] = 0;
+            }
+        }
+        unsigned src[16];
+        float w[16];
+        const int bx = blk % P.lv.bw, by = blk / P.lv.bw;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int x = bx * 4 + (i & 3), y = by * 4 + (i >> 2);
+            float cx = 0.0f, cy = 0.0f, cz = 0.0f, wt = 0.0f;
+            if (x < P.lv.w && y < P.lv.h) {
+                cx = load_texel(P.lv, 0, x, y);
+                cy = load_texel(P.lv, 1, x, y);
+                cz = load_texel(P.lv, 2, x, y);
+                wt = P.transparency ? nv_clamp(load_texel(P.lv, 3, x, y), 0.0f, 1.0f) : 1.0f;
+            }
+            const float R = nv_clamp(cx, 0.0f, 1.0f), G = nv_clamp(cy, 0.0f, 1.0f), B = nv_clamp(cz, 0.0f, 1.0f);
+            const unsigned idx = (cb.y >> (2 * i)) & 3u;
+            const float rm = (float)pr[idx] / 255.0f, gm = (float)pg[idx] / 255.0f, bm = (float)pb[idx] / 255.0f;
+            float m = (rm * R + gm * G + bm * B) / (rm * rm + gm * gm + bm * bm);
+            m = (m - P.min_m) / (1 - P.min_m);
+            // U8(ftoi_round(saturate(m) * 255.0f)): cvtss2si, round to nearest even
+            src[i] = (unsigned)__float2int_rn(nv_clamp(m, 0.0f, 1.0f) * 255.0f) & 0xFFu;
+            w[i] = wt;
+        }
+        int mina = 255, maxa = 0, mina_no01 = 255, maxa_no01 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int a = (int)src[i];
+            mina = min(mina, a);
+            maxa = max(maxa, a);
+            if (a != 0 && a != 255) {
+                mina_no01 = min(mina_no01, a);
+                maxa_no01 = max(maxa_no01, a);
+            }
+        }
+        unsigned a0, a1;
+        if (maxa - mina < 8) {
+            a0 = (unsigned)maxa;
+            a1 = (unsigned)mina;
+        } else if (maxa_no01 - mina_no01 < 6) {
+            a0 = (unsigned)mina_no01;
+            a1 = (unsigned)maxa_no01;
+        } else {
+            float besterror = alpha_pair_error_w(src, w, 0, 0);  // zero-filled output block (see k_alpha_optimal)
+            unsigned bestk = 0xffffffffu;
+            unsigned bestpair = ((unsigned)maxa << 8) | (unsigned)mina;
+            const int lo8 = (mina <= 8) ? 0 : mina - 8, hi8 = (maxa >= 255 - 8) ? 255 : maxa + 8;
+            const int R8 = hi8 - lo8;
+            const int n8 = (R8 > 9) ? ((R8 - 9) * (R8 - 8)) / 2 : 0;
+            const int lo6 = (mina_no01 <= 6) ? 0 : mina_no01 - 6, hi6 = (maxa_no01 >= 255 - 6) ? 255 : maxa_no01 + 6;
+            const int R6 = hi6 - lo6;
+            const int n6 = (R6 > 9) ? ((R6 - 9) * (R6 - 8)) / 2 : 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const int lo = pass ? lo6 : lo8, hi = pass ? hi6 : hi8, n = pass ? n6 : n8;
+                const unsigned kbase = pass ? (unsigned)n8 : 0u;
+                int row = 0, col = lane;
+                while (row < hi - lo - 9 && col > row) { col -= row + 1; row++; }
+                for (int k = lane; k < n; k += 32) {
+                    const unsigned x0 = (unsigned)(lo + 9 + row), x1 = (unsigned)(lo + col);
+                    const float e = pass ? alpha_pair_error_w(src, w, x1, x0) : alpha_pair_error_w(src, w, x0, x1);
+                    if (e < besterror) {
+                        besterror = e;
+                        bestk = kbase + (unsigned)k;
+                        bestpair = pass ? ((x1 << 8) | x0) : ((x0 << 8) | x1);
+                    }
+                    col += 32;
+                    while (col > row) { col -= row + 1; row++; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float oe = __shfl_xor_sync(0xffffffffu, besterror, d);
+                const unsigned ok = __shfl_xor_sync(0xffffffffu, bestk, d);
+                const unsigned op = __shfl_xor_sync(0xffffffffu, bestpair, d);
+                if (oe < besterror || (oe == besterror && ok < bestk)) {
+                    besterror = oe;
+                    bestk = ok;
+                    bestpair = op;
+                }
+            }
+            a0 = bestpair >> 8;
+            a1 = bestpair & 0xFF;
+        }
+        if (lane == 0) {
+            unsigned long long b = ((unsigned long long)a1 << 8) | a0;
+            alpha_compute_indices(src, a0, a1, &b);
+            *reinterpret_cast<uint2 *>(dst) = make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
+        }
+    }
+}
+
 }  // namespace nvb

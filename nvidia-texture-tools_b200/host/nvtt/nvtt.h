@@ -46,6 +46,7 @@ struct CompressionOptions {
     NVTT_API void setColorWeights(float red, float green, float blue, float alpha = 1.0f);
     NVTT_API void setPixelType(PixelType pixelType);
     NVTT_API void setQuantization(bool colorDithering, bool alphaDithering, bool binaryAlpha, int alphaThreshold = 127);
+    NVTT_API void setRGBMThreshold(float min_m);
     NVTT_API void setTargetDecoder(Decoder decoder);
     NVTT_API Format format() const;
     struct Private;

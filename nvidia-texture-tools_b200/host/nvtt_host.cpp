@@ -97,6 +97,7 @@ struct CompressionOptions::Private {
     Decoder decoder;
     bool enableColorDithering, enableAlphaDithering, binaryAlpha;
     int alphaThreshold;
+    float rgbmThreshold;
 };
 CompressionOptions::CompressionOptions() : m(*new Private()) { reset(); }
 CompressionOptions::~CompressionOptions() { delete &m; }
@@ -108,7 +109,9 @@ void CompressionOptions::reset() {
     m.decoder = Decoder_D3D10;
     m.enableColorDithering = m.enableAlphaDithering = m.binaryAlpha = false;
     m.alphaThreshold = 127;
+    m.rgbmThreshold = 0.15f;  // CompressionOptions.cpp:53
 }
+void CompressionOptions::setRGBMThreshold(float min_m) { m.rgbmThreshold = min_m; }
 void CompressionOptions::setFormat(Format f) { m.format = f; }
 void CompressionOptions::setQuality(Quality q) { m.quality = q; }
 void CompressionOptions::setColorWeights(float r, float g, float b, float a) {
@@ -452,6 +455,7 @@ void fill_encode(NvttbEncodeDesc *e, const CompressionOptions::Private &co, Alph
     e->width = w;
     e->height = h;
     e->applyToGamma = 0;
+    e->rgbmThreshold = co.rgbmThreshold;
 }
 int image_size(int w, int h, int d, Format f) { return ((w + 3) / 4) * ((h + 3) / 4) * blockSize(f) * d; }
 

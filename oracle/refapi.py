@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 # nvtt enums (src/nvtt/nvtt.h:80-277)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
-Format_DXT1n, Format_CTX1, Format_BC6, Format_BC7 = 8, 9, 10, 11
+Format_DXT1n, Format_CTX1, Format_BC6, Format_BC7, Format_BC3_RGBM = 8, 9, 10, 11, 12
 Format_BC1, Format_BC2, Format_BC3, Format_BC3n = Format_DXT1, Format_DXT3, Format_DXT5, Format_DXT5n
 Quality_Fastest, Quality_Normal, Quality_Production, Quality_Highest = range(4)
 WrapMode_Clamp, WrapMode_Repeat, WrapMode_Mirror = range(3)

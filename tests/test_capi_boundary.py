@@ -70,7 +70,7 @@ def test_dds_header_matches_reference(ref):
     ours.ref_process.argtypes = [C.POINTER(ref.RefProcessDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_long]
     img = np.zeros((8, 8, 4), np.uint8)
     for fmt in (ref.Format_BC1, ref.Format_DXT1a, ref.Format_BC2, ref.Format_BC3, ref.Format_BC3n, ref.Format_BC4, ref.Format_BC5,
-                ref.Format_BC6, ref.Format_BC7):
+                ref.Format_BC6, ref.Format_BC7, ref.Format_BC3_RGBM):
         for container in (ref.Container_DDS, ref.Container_DDS10, ref.Container_KTX):
             for normal in (False, True):
                 for (ttype, faces) in ((ref.TextureType_2D, 1), (ref.TextureType_Cube, 6)):

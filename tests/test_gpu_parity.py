@@ -390,3 +390,18 @@ def test_block_row_sharding_of_one_image(nvtt, ref, ctx):
         # the big levels really are split: no band carries the whole level 0 when it divides
         if (h // 4) % world == 0 and h % 4 == 0:
             assert all(n == layout[0][0][1] for _, n in layout[0]) and layout[0][0][1] * world == ((w + 3) // 4) * (h // 4) * (8 if fmt_name == "BC1" else 16)
+
+
+def test_bc3_rgbm_bit_exact(nvtt, ref, ctx):
+    """Format_BC3_RGBM (compress_dxt5_rgbm): ICBC colour block on (R,G,B)/M with weights w*M + weighted brute-force multiplier
+    block; opaque, alpha-weighted, ragged sizes, HDR-ish input above 1 (saturated by the encoder)."""
+    rng = np.random.default_rng(23)
+    for (w, h) in SIZES:
+        imgs = list(_images(nvtt, w, h))
+        imgs.append(("bright", (rng.random((4, h, w)) * 1.5).astype(np.float32)))
+        imgs.append(("dark", (rng.random((4, h, w)) * 0.1).astype(np.float32)))
+        for name, img in imgs:
+            for am in (0, 1):
+                got = ctx.encode_level(12, 1, img, alpha_mode=am)
+                want = ref.compress_level(12, 1, img, alpha_mode=am)
+                _assert_blocks_equal(got, want, 16, "BC3_RGBM %s %dx%d alphaMode %d" % (name, w, h, am))
