@@ -405,3 +405,38 @@ def test_bc3_rgbm_bit_exact(nvtt, ref, ctx):
                 got = ctx.encode_level(12, 1, img, alpha_mode=am)
                 want = ref.compress_level(12, 1, img, alpha_mode=am)
                 _assert_blocks_equal(got, want, 16, "BC3_RGBM %s %dx%d alphaMode %d" % (name, w, h, am))
+
+
+def _sample_blocks_strip(img, idxs, bw):
+    """planar [4,h,w] -> planar [4,4,4*n]: the 4x4 tiles of the sampled blocks side by side (blocks are encoded independently)."""
+    tiles = [img[:, (i // bw) * 4:(i // bw) * 4 + 4, (i % bw) * 4:(i % bw) * 4 + 4] for i in idxs]
+    return np.ascontiguousarray(np.concatenate(tiles, axis=2))
+
+
+def test_config3_config4_full_size_properties(nvtt, ref, ctx):
+    """BASELINE configs[3] / [4] at sizes where the BC7 pipeline runs in several chunks of 32 768 blocks and the BC6H one over a
+    whole 2048^2 face: sampled blocks (chunk boundaries included) must equal the reference's encoding of the same 4x4 tiles."""
+    rng = np.random.default_rng(77)
+    # BC7: 1040 x 1024 = 260 x 256 blocks = 66 560 blocks = 2 full chunks + a partial one
+    w, h = 1040, 1024
+    img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(w, h, seed=1234, alpha=True))
+    adv = nvtt.synth.planar_from_bgra8(nvtt.synth.adversarial_bgra8(256, 256, seed=5))
+    img[:, 300:556, 400:656] = adv
+    got = ctx.encode_level(nvtt.Format_BC7, 1, img).reshape(-1, 16)
+    bw, nb = w // 4, (w // 4) * (h // 4)
+    assert got.shape[0] == nb
+    idxs = [0, 32767, 32768, 32769, 65535, 65536, 65537, nb - 1] + [int(i) for i in rng.integers(0, nb, 184)]
+    want = ref.compress_level(ref.Format_BC7, 1, _sample_blocks_strip(img, idxs, bw)).reshape(-1, 16)
+    bad = [i for k, i in enumerate(idxs) if not np.array_equal(got[i], want[k])]
+    assert not bad, "BC7 1040x1024: blocks %s differ from the reference" % bad[:8]
+    # determinism across two runs of the chunked, dynamically scheduled search
+    assert np.array_equal(got, ctx.encode_level(nvtt.Format_BC7, 1, img).reshape(-1, 16))
+    # BC6H: one 2048^2 HDR face
+    w = h = 2048
+    hdr = _hdr_planar(nvtt, w, h, 11)
+    got = ctx.encode_level(nvtt.Format_BC6, 1, hdr, pixel_type=nvtt.PixelType_UnsignedFloat).reshape(-1, 16)
+    bw, nb = w // 4, (w // 4) * (h // 4)
+    idxs = [0, nb - 1] + [int(i) for i in rng.integers(0, nb, 510)]
+    want = ref.compress_level(ref.Format_BC6, 1, _sample_blocks_strip(hdr, idxs, bw), pixel_type=nvtt.PixelType_UnsignedFloat).reshape(-1, 16)
+    bad = [i for k, i in enumerate(idxs) if not np.array_equal(got[i], want[k])]
+    assert not bad, "BC6H 2048x2048: blocks %s differ from the reference" % bad[:8]
