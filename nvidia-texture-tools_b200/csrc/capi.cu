@@ -1049,7 +1049,8 @@ int nvttb_surface_set_image_2d(NvttbSurface *s, int format, int decoder, int w, 
     P.out = (float *)s->buf.p;
     P.w = w; P.h = h; P.bw = bw; P.bh = bh;
     P.format = format; P.decoder = decoder; P.bc6_signed = bc6Signed;
-    NVB_LAUNCH(ctx, K_DECODE, (double)w * h, k_decode_blocks, grid_for((size_t)bw * bh, 128), 128, P);
+    if (format == F_BC6 || format == F_BC7) NVB_LAUNCH(ctx, K_DECODE, (double)w * h, k_decode_blocks, grid_for((size_t)bw * bh, 128), 128, P);
+    else NVB_LAUNCH(ctx, K_DECODE, (double)w * h, k_decode_dxt, grid_for((size_t)bw * bh, 128), 128, P);
     CK(cudaGetLastError());
     s->w = w;
     s->h = h;

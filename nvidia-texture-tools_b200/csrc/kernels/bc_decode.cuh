@@ -347,6 +347,116 @@ __global__ void __launch_bounds__(128) k_decode_blocks(DecodeParams P) {
     }
 }
 
+// ---- the DXT family (BC1, BC2, BC3, BC3n, BC3-RGBM, BC4, BC5) without arrays that need local memory -------------------------
+// Same values as dec_dxt1 / dec_alpha5 above; palette entries are picked with selects / computed per texel, and the final
+// float(c) / 255.0f (an IEEE division: c * (1/255) differs in 126 of the 256 cases) comes from a 256-entry table that every
+// CTA fills with real divisions.  One thread per block, 16-byte row segments per plane.
+NVB_DEV unsigned dxt_alpha_entry(int a0, int a1, bool d3d9, unsigned k) {
+    if (k == 0) return (unsigned)a0;
+    if (k == 1) return (unsigned)a1;
+    if (a0 > a1) return (unsigned)(((8 - (int)k) * a0 + ((int)k - 1) * a1 + (d3d9 ? 3 : 0)) / 7) & 0xFFu;
+    if (k == 6) return 0u;
+    if (k == 7) return 255u;
+    return (unsigned)(((6 - (int)k) * a0 + ((int)k - 1) * a1 + (d3d9 ? 2 : 0)) / 5) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(128) k_decode_dxt(DecodeParams P) {
+    __shared__ float s_unorm[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i * 1.0f / 255.0f;
+    __syncthreads();
+    const int nblocks = P.bw * P.bh;
+    const size_t plane = (size_t)P.w * P.h;
+    const int f = P.format;
+    const bool has_colour = (f == 1 || f == 3 || f == 4 || f == 5 || f == 12);
+    const int bs = (f == 1 || f == 6) ? 8 : 16;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += gridDim.x * blockDim.x) {
+        const int bx = blk % P.bw, by = blk / P.bw;
+        const unsigned char *b = P.blocks + (size_t)blk * bs;
+        uint2 w0 = *reinterpret_cast<const uint2 *>(b), w1 = make_uint2(0u, 0u);
+        if (bs == 16) w1 = *reinterpret_cast<const uint2 *>(b + 8);
+        // colour palette (r, g, b, a packed as bytes 0..3)
+        unsigned p0 = 0, p1 = 0, p2 = 0, p3 = 0, cbits = 0;
+        if (has_colour) {
+            const uint2 cw = (bs == 16) ? w1 : w0;
+            const unsigned c0 = cw.x & 0xFFFFu, c1 = cw.x >> 16;
+            cbits = cw.y;
+            const int r0 = (c0 >> 11) & 31, g0 = (c0 >> 5) & 63, b0 = c0 & 31, r1 = (c1 >> 11) & 31, g1 = (c1 >> 5) & 63, b1 = c1 & 31;
+            int R[4], G[4], B[4], A3 = 0xFF;
+            if (P.decoder != 2) {
+                R[0] = (r0 << 3) | (r0 >> 2); G[0] = (g0 << 2) | (g0 >> 4); B[0] = (b0 << 3) | (b0 >> 2);
+                R[1] = (r1 << 3) | (r1 >> 2); G[1] = (g1 << 2) | (g1 >> 4); B[1] = (b1 << 3) | (b1 >> 2);
+                if (c0 > c1) {
+                    R[2] = (2 * R[0] + R[1]) / 3; G[2] = (2 * G[0] + G[1]) / 3; B[2] = (2 * B[0] + B[1]) / 3;
+                    R[3] = (2 * R[1] + R[0]) / 3; G[3] = (2 * G[1] + G[0]) / 3; B[3] = (2 * B[1] + B[0]) / 3;
+                } else {
+                    R[2] = (R[0] + R[1]) / 2; G[2] = (G[0] + G[1]) / 2; B[2] = (B[0] + B[1]) / 2;
+                    R[3] = G[3] = B[3] = 0; A3 = 0;
+                }
+            } else {
+                R[0] = ((3 * r0 * 22) / 8) & 0xFF; G[0] = (g0 << 2) | (g0 >> 4); B[0] = ((3 * b0 * 22) / 8) & 0xFF;
+                R[1] = ((3 * r1 * 22) / 8) & 0xFF; G[1] = (g1 << 2) | (g1 >> 4); B[1] = ((3 * b1 * 22) / 8) & 0xFF;
+                const int gdiff = G[1] - G[0];
+                if (c0 > c1) {
+                    R[2] = (((2 * r0 + r1) * 22) / 8) & 0xFF; G[2] = ((256 * G[0] + gdiff / 4 + 128 + gdiff * 80) / 256) & 0xFF; B[2] = (((2 * b0 + b1) * 22) / 8) & 0xFF;
+                    R[3] = (((2 * r1 + r0) * 22) / 8) & 0xFF; G[3] = ((256 * G[1] - gdiff / 4 + 128 - gdiff * 80) / 256) & 0xFF; B[3] = (((2 * b1 + b0) * 22) / 8) & 0xFF;
+                } else {
+                    R[2] = (((r0 + r1) * 33) / 8) & 0xFF; G[2] = ((256 * G[0] + gdiff / 4 + 128 + gdiff * 128) / 256) & 0xFF; B[2] = (((b0 + b1) * 33) / 8) & 0xFF;
+                    R[3] = G[3] = B[3] = 0; A3 = 0;
+                }
+            }
+            p0 = (unsigned)R[0] | ((unsigned)G[0] << 8) | ((unsigned)B[0] << 16) | 0xFF000000u;
+            p1 = (unsigned)R[1] | ((unsigned)G[1] << 8) | ((unsigned)B[1] << 16) | 0xFF000000u;
+            p2 = (unsigned)R[2] | ((unsigned)G[2] << 8) | ((unsigned)B[2] << 16) | 0xFF000000u;
+            p3 = (unsigned)R[3] | ((unsigned)G[3] << 8) | ((unsigned)B[3] << 16) | ((unsigned)A3 << 24);
+        }
+        const unsigned long long abits0 = (((unsigned long long)w0.y << 32) | w0.x) >> 16;  // 48 index bits of the first alpha block
+        const unsigned long long abits1 = (((unsigned long long)w1.y << 32) | w1.x) >> 16;
+        const int a00 = (int)(w0.x & 0xFF), a01 = (int)((w0.x >> 8) & 0xFF), a10 = (int)(w1.x & 0xFF), a11 = (int)((w1.x >> 8) & 0xFF);
+        const bool full = (bx * 4 + 4 <= P.w) && ((P.w & 3) == 0);
+#pragma unroll
+        for (int yy = 0; yy < 4; yy++) {
+            const int y = by * 4 + yy;
+            if (y >= P.h) break;
+            float v[4][4];  // [texel of the row][channel]
+#pragma unroll
+            for (int xx = 0; xx < 4; xx++) {
+                const int i = yy * 4 + xx;
+                unsigned r = 0, g = 0, bl = 0, a = 255;
+                if (has_colour) {
+                    const unsigned ci = (cbits >> (2 * i)) & 3u;
+                    const unsigned c = ci == 0 ? p0 : ci == 1 ? p1 : ci == 2 ? p2 : p3;
+                    r = c & 0xFF; g = (c >> 8) & 0xFF; bl = (c >> 16) & 0xFF; a = c >> 24;
+                }
+                if (f == 3) {  // explicit 4-bit alpha
+                    const unsigned long long all = ((unsigned long long)w0.y << 32) | w0.x;
+                    const unsigned a4 = (unsigned)(all >> (4 * i)) & 15u;
+                    a = (a4 << 4) | a4;
+                } else if (f == 4 || f == 5 || f == 12) {
+                    a = dxt_alpha_entry(a00, a01, false, (unsigned)(abits0 >> (3 * i)) & 7u);
+                } else if (f == 6) {
+                    r = g = bl = dxt_alpha_entry(a00, a01, P.decoder == 1, (unsigned)(abits0 >> (3 * i)) & 7u);
+                } else if (f == 7) {
+                    r = dxt_alpha_entry(a00, a01, P.decoder == 1, (unsigned)(abits0 >> (3 * i)) & 7u);
+                    g = dxt_alpha_entry(a10, a11, P.decoder == 1, (unsigned)(abits1 >> (3 * i)) & 7u);
+                    bl = 0;
+                }
+                v[xx][0] = s_unorm[r]; v[xx][1] = s_unorm[g]; v[xx][2] = s_unorm[bl]; v[xx][3] = s_unorm[a];
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                float *row = P.out + ch * plane + (size_t)y * P.w + bx * 4;
+                if (full) {
+                    *reinterpret_cast<float4 *>(row) = make_float4(v[0][ch], v[1][ch], v[2][ch], v[3][ch]);
+                } else {
+#pragma unroll
+                    for (int xx = 0; xx < 4; xx++)
+                        if (bx * 4 + xx < P.w) row[xx] = v[xx][ch];
+                }
+            }
+        }
+    }
+}
+
 // ---- nv::rmsColorError / rmsAlphaError -------------------------------------------------------------------------------------
 // The reference adds fp32 terms into one double in texel order.  Here every thread accumulates a strided subset in
 // double, a CTA reduces in shared memory and the per-CTA partial sums are added on the host in double.  The terms are
