@@ -682,24 +682,28 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         const double units = (double)w * h;
         CK(cudaMemsetAsync(S.counters, 0, NVB_BC6_COUNTERS * sizeof(unsigned), ctx->stream));
         NVB_LAUNCH(ctx, K_BC6_TILES, units, k_bc6_tiles, (unsigned)(((size_t)nb * 16 + 255) / 256), 256, S, tiles);
-        NVB_LAUNCH(ctx, K_BC6_ROUGH, units, k_bc6_rough, grid_for(nb, NVB_BC6_ROUGH_WARPS), NVB_BC6_ROUGH_WARPS * 32, P);
         const int padded = (nb + 127) / 128 * 128;
-        NVB_LAUNCH(ctx, K_BC6_SETUP, units, k_bc6_setup, 2 * padded / 128, 128, S, padded);
-        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<0>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
-        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<1>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
         // searchers are handed out dynamically, at most what the GPU holds (searchers per thread tuned on B200:
-        // profiles/r1e_summary.md; NVB_BC6_SPT1/2 override for experiments).  The one-region searches (16
-        // texels x 16 palette entries) are the long ones and start first, on a second stream beside the two-region ones.
+        // profiles/r1e_summary.md; NVB_BC6_SPT1/2 override for experiments).
         static const int spt1 = getenv("NVB_BC6_SPT1") ? atoi(getenv("NVB_BC6_SPT1")) : 1, spt2 = getenv("NVB_BC6_SPT2") ? atoi(getenv("NVB_BC6_SPT2")) : 2;
         size_t g1 = ((size_t)nb / spt1 + 127) / 128, g2 = ((size_t)nb * 2 / spt2 + 127) / 128;
         if (g1 > 148u * 5u) g1 = 148u * 5u;
         if (g2 > 148u * 6u) g2 = 148u * 6u;
         if (g1 < 1) g1 = 1;
         if (g2 < 1) g2 = 1;
+        // Two independent chains after the tiles: the one-region encoding (line fit, setup, the long 16 x 16 searches) on a
+        // second stream, the two-region one (32-shape ranking, setup, order, searches) on the context's stream; finish joins.
         CK(cudaEventRecord(ctx->ev_fork[0], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->mode_stream[0], ctx->ev_fork[0], 0));
-        NVB_LAUNCH_ON(ctx, ctx->mode_stream[0], K_BC6_SEARCH, units, k_bc6_search<1>, (unsigned)g1, 128, S);
-        CK(cudaEventRecord(ctx->ev_join[0][0], ctx->mode_stream[0]));
+        cudaStream_t s1 = ctx->mode_stream[0];
+        CK(cudaStreamWaitEvent(s1, ctx->ev_fork[0], 0));
+        NVB_LAUNCH_ON(ctx, s1, K_BC6_ROUGH, units, k_bc6_rough_one, (unsigned)((nb + 127) / 128), 128, S);
+        NVB_LAUNCH_ON(ctx, s1, K_BC6_SETUP, units, k_bc6_setup, (unsigned)((nb + 127) / 128), 128, S, padded, 0);
+        NVB_LAUNCH_ON(ctx, s1, K_BC6_SEARCH, units, k_bc6_search<1>, (unsigned)g1, 128, S);
+        CK(cudaEventRecord(ctx->ev_join[0][0], s1));
+        NVB_LAUNCH(ctx, K_BC6_ROUGH, units, k_bc6_rough, grid_for(nb, NVB_BC6_ROUGH_WARPS), NVB_BC6_ROUGH_WARPS * 32, P, 2);
+        NVB_LAUNCH(ctx, K_BC6_SETUP, units, k_bc6_setup, (unsigned)((nb + 127) / 128), 128, S, padded, 1);
+        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<0>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
+        NVB_LAUNCH(ctx, K_BC6_ORDER, units, k_bc6_order<1>, (unsigned)(((size_t)nb * 2 + 255) / 256), 256, S);
         NVB_LAUNCH(ctx, K_BC6_SEARCH, units, k_bc6_search<2>, (unsigned)g2, 128, S);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0][0], 0));
         NVB_LAUNCH(ctx, K_BC6_FINISH, units, k_bc6_finish, 2 * padded / 128, 128, S, padded);

@@ -514,7 +514,8 @@ template <int NR> NVB_DEV float zoh_refine(const ZohTile &t, int shape, const fl
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 #define NVB_BC6_ROUGH_WARPS 4
 
-__global__ void __launch_bounds__(NVB_BC6_ROUGH_WARPS * 32) k_bc6_rough(Bc6Params P) {
+// which: bit 0 = the one-region line fit (lane 0), bit 1 = the 32 two-region shapes; 3 = both (k_bc6_refine path)
+__global__ void __launch_bounds__(NVB_BC6_ROUGH_WARPS * 32) k_bc6_rough(Bc6Params P, int which) {
     __shared__ float s_c[NVB_BC6_ROUGH_WARPS][16][3];
     __shared__ float s_imp[NVB_BC6_ROUGH_WARPS][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -524,6 +525,14 @@ __global__ void __launch_bounds__(NVB_BC6_ROUGH_WARPS * 32) k_bc6_rough(Bc6Param
         __syncwarp();
         if (lane < 16) zoh_load_texel(P, blk % P.lv.bw, blk / P.lv.bw, lane, s_c[wib][lane], &s_imp[wib][lane]);
         __syncwarp();
+        float *dst = P.rough + (size_t)blk * 20;
+        if ((which & 1) && lane == 0) {
+            float ep1[1][6];
+            zoh_rough<1>(s_c[wib], s_imp[wib], 0, sgn, ep1);
+#pragma unroll
+            for (int k = 0; k < 6; k++) dst[k] = ep1[0][k];
+        }
+        if (!(which & 2)) continue;
         float ep2[2][6];
         float mse = zoh_rough<2>(s_c[wib], s_imp[wib], lane, sgn, ep2);
         // first strict minimum in shape order; the reference stops once the best error is <= 0, which the same
@@ -539,18 +548,11 @@ __global__ void __launch_bounds__(NVB_BC6_ROUGH_WARPS * 32) k_bc6_rough(Bc6Param
                 bests = os;
             }
         }
-        float *dst = P.rough + (size_t)blk * 20;
         if (bests == 64) bests = 0;  // no shape beat FLT_MAX (cannot happen for finite input): the reference keeps shape 0
         if (lane == bests) {
 #pragma unroll
             for (int k = 0; k < 12; k++) dst[6 + k] = ep2[k / 6][k % 6];
             dst[18] = (float)bests;
-        }
-        if (lane == 0) {
-            float ep1[1][6];
-            zoh_rough<1>(s_c[wib], s_imp[wib], 0, sgn, ep1);
-#pragma unroll
-            for (int k = 0; k < 6; k++) dst[k] = ep1[0][k];
         }
     }
 }

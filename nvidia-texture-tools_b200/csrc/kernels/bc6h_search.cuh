@@ -40,6 +40,23 @@ __global__ void __launch_bounds__(256) k_bc6_tiles(Bc6SearchParams S, float4 *ti
     tiles[t] = make_float4(c[0], c[1], c[2], imp);
 }
 
+// roughone for every block of the level: one thread per block (the one-region chain does not wait for the 32-shape ranking)
+__global__ void __launch_bounds__(128) k_bc6_rough_one(Bc6SearchParams S) {
+    const int nblocks = S.P.lv.bw * S.P.lv.bh;
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= nblocks) return;
+    float c[16][3], imp[16];
+    for (int i = 0; i < 16; i++) {
+        const float4 v = S.tiles[(size_t)blk * 16 + i];
+        c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z;
+        imp[i] = v.w;
+    }
+    float ep1[1][6];
+    zoh_rough<1>(c, imp, 0, S.P.is_signed != 0, ep1);
+    float *dst = S.P.rough + (size_t)blk * 20;
+    for (int k = 0; k < 6; k++) dst[k] = ep1[0][k];
+}
+
 NVB_DEV void zs_read_tile(const float4 *tiles, int blk, ZohTile &t) {
     for (int i = 0; i < 16; i++) {
         const float4 c = tiles[(size_t)blk * 16 + i];
@@ -89,11 +106,12 @@ template <int NR> NVB_DEV void zs_setup(const Bc6SearchParams &S, int blk, const
 }
 
 // thread t < padded: one-region kind of block t; t >= padded: two-region kind of block t - padded
-__global__ void __launch_bounds__(128) k_bc6_setup(Bc6SearchParams S, int padded) {
+// only_kind < 0: both kinds in one launch (padded layout above); 0 / 1: thread t = block t of that kind
+__global__ void __launch_bounds__(128) k_bc6_setup(Bc6SearchParams S, int padded, int only_kind) {
     const int nblocks = S.P.lv.bw * S.P.lv.bh;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int kind = t >= padded;
-    const int blk = kind ? t - padded : t;
+    const int kind = only_kind < 0 ? (t >= padded) : only_kind;
+    const int blk = (only_kind < 0 && kind) ? t - padded : t;
     if (blk >= nblocks) return;
     const bool sgn = S.P.is_signed != 0;
     ZohTile tile;

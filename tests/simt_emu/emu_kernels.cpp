@@ -150,7 +150,7 @@ void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency,
     std::vector<float> rough((size_t)nb * 20), err((size_t)nb * 2);
     std::vector<unsigned char> cand((size_t)nb * 32);
     P.rough = rough.data(); P.cand = cand.data(); P.cand_err = err.data();
-    emu::launch(dim3((nb + NVB_BC6_ROUGH_WARPS - 1) / NVB_BC6_ROUGH_WARPS), dim3(NVB_BC6_ROUGH_WARPS * 32), 0, [&] { k_bc6_rough(P); });
+    emu::launch(dim3((nb + NVB_BC6_ROUGH_WARPS - 1) / NVB_BC6_ROUGH_WARPS), dim3(NVB_BC6_ROUGH_WARPS * 32), 0, [&] { k_bc6_rough(P, 3); });
     int padded = (nb + 127) / 128 * 128;
     const char *how = getenv("NVB_EMU_BC6");
     if (how && !strcmp(how, "scalar")) {  // thread per (block, kind)
@@ -164,7 +164,7 @@ void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency,
         S.P = P; S.tiles = tiles.data(); S.meta = meta.data(); S.setup = setup.data(); S.setup_idx = sidx.data(); S.res = res.data();
         S.perm = perm.data(); S.counters = counters.data();
         emu::launch(dim3((nb * 16 + 255) / 256), dim3(256), 0, [&] { k_bc6_tiles(S, tiles.data()); });
-        emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_setup(S, padded); });
+        emu::launch(dim3(2 * padded / 128), dim3(128), 0, [&] { k_bc6_setup(S, padded, -1); });
         emu::launch(dim3((nb * 2 + 255) / 256), dim3(256), 0, [&] { k_bc6_order<0>(S); });
         emu::launch(dim3((nb * 2 + 255) / 256), dim3(256), 0, [&] { k_bc6_order<1>(S); });
         emu::launch(dim3(2), dim3(128), 0, [&] { k_bc6_search<1>(S); });
