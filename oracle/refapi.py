@@ -80,6 +80,10 @@ def _load(name):
     L.ref_surf_to_grey_scale.argtypes = [C.c_void_p] + [C.c_float] * 4
     L.ref_surf_to_normal_map.argtypes = [C.c_void_p] + [C.c_float] * 4
     L.ref_decode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_decode_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_rms_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.ref_surf_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ref_surf_binarize.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
     return L
 
 
@@ -185,11 +189,34 @@ class Surface:
     def normalize_normal_map(self):
         self.L.ref_surf_normalize_normal_map(self.h)
 
+    def quantize(self, channel, bits, exact_end_points, dither):
+        self.L.ref_surf_quantize(self.h, channel, bits, int(exact_end_points), int(dither))
+
+    def binarize(self, channel, threshold, dither):
+        self.L.ref_surf_binarize(self.h, channel, threshold, int(dither))
+
     def to_grey_scale(self, r, g, b, a):
         self.L.ref_surf_to_grey_scale(self.h, r, g, b, a)
 
     def to_normal_map(self, sm, md, bg, lg):
         self.L.ref_surf_to_normal_map(self.h, sm, md, bg, lg)
+
+
+def decode_ex(fmt, decoder, w, h, data):
+    """Surface::setImage2D(fmt, decoder, ...) of the reference -> planar fp32 [4,h,w]."""
+    out = np.empty((4, h, w), np.float32)
+    data = np.ascontiguousarray(data)
+    assert lib().ref_decode_ex(fmt, decoder, w, h, data.ctypes.data, out.ctypes.data)
+    return out
+
+
+def rms_error(fmt, w, h, blocks, rgba32f, alpha_mode=0):
+    """(nvtt::rmsError, nvtt::rmsAlphaError) between an RGBA32F image and the decoded BCn level."""
+    a, b = C.c_float(), C.c_float()
+    blocks = np.ascontiguousarray(blocks)
+    rgba32f = np.ascontiguousarray(rgba32f, dtype=np.float32)
+    assert lib().ref_rms_error(fmt, w, h, blocks.ctypes.data, rgba32f.ctypes.data, alpha_mode, C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def decode(fmt, w, h, data):

@@ -62,3 +62,44 @@ def imageop_cases():
             for filt, params, name in ((0, None, "box"), (1, None, "tri"), (2, (3.0, 4.0, 1.0), "kaiser")):
                 c["ops_%s_wrap%d_%dx%d" % (name, wrap, w, h)] = ("photo", w, h, wrap, filt, params)
     return c
+
+
+# ---- golden_v2.npz: what was added after v1 (more format/quality pairs, decoders, quantisation, containers, metrics) -------
+def level_cases_v2():
+    c = {}
+    for kind in ("photo", "adv", "dark"):
+        for (w, h) in ((48, 40), (13, 7)):
+            for fmt, name, qs in ((5, "bc3n", (2, 3)), (3, "bc2", (2, 3)), (2, "bc1a", (2, 3)), (7, "bc5", (3,)), (6, "bc4", (3,))):
+                for q in qs:
+                    c["level_%s_%s_%dx%d_q%d" % (name, kind, w, h, q)] = (kind, w, h, fmt, q, 0, (1, 1, 1, 1), 0)
+            for am in (0, 1):
+                c["level_bc3rgbm_%s_%dx%d_am%d" % (kind, w, h, am)] = (kind, w, h, 12, 1, am, (1, 1, 1, 1), 0)
+    return c
+
+
+def decode_cases():
+    """key -> (level case whose reference blocks are decoded, is it in v2, nvtt::Decoder)"""
+    c = {}
+    for name, src, v2 in (("bc1", "level_bc1_photo_48x40_q1", False), ("bc2", "level_bc2_adv_13x7_q1", False), ("bc3", "level_bc3_photo_48x40_q2", False),
+                          ("bc3n", "level_bc3n_photo_48x40_q1", False), ("bc4", "level_bc4_dark_13x7_q1", False), ("bc5", "level_bc5_photo_48x40_q1", False),
+                          ("bc3rgbm", "level_bc3rgbm_photo_48x40_am0", True)):
+        for dec in (0, 1, 2):
+            c["decode_%s_dec%d" % (name, dec)] = (src, v2, dec)
+    c["decode_bc6_unsigned"] = ("level_bc6_hdr_32x24_pt5", False, 0)
+    c["decode_bc7"] = ("level_bc7_adv_24x16", False, 0)  # contains no mode-0 block the reference could not decode
+    return c
+
+
+def quantize_cases():
+    """key -> (w, h, dither): 5/6/3-bit quantize of r, g, b (the last without exact end points) + binarize of alpha at 0.4"""
+    return {"quantize_%dx%d_dither%d" % (w, h, d): (w, h, d) for (w, h) in ((37, 22), (64, 1100), (300, 3)) for d in (0, 1)}
+
+
+def pipeline_cases_v2():
+    return {
+        "pipe_ktx_bc3_kaiser_40": ("photo", 40, 40, 4, 1, dict(mip_filter=2, container=2, header=True)),
+        "pipe_ktx_bc5_normal_tri_32": ("normal", 32, 32, 7, 1, dict(mip_filter=1, normal_map=True, container=2, header=True)),
+        "pipe_dds10_bc7_box_16x12": ("photo", 16, 12, 11, 1, dict(mip_filter=0, container=1, header=True)),
+        "pipe_bc1_color_dither_96x72": ("photo", 96, 72, 1, 1, dict(mip_filter=0, quantization=1)),
+        "pipe_bc3_binary_alpha_64x48": ("photo", 64, 48, 4, 1, dict(mip_filter=0, quantization=4, alpha_threshold=40)),
+    }

@@ -48,6 +48,75 @@ def test_gpu_image_ops_match_golden(nvtt, ctx, golden):
         assert np.array_equal(np.stack(hashes), golden[key]), key
 
 
+@pytest.fixture(scope="module")
+def golden2():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_v2.npz"))
+
+
+def test_gpu_v2_levels_decoders_quantize_metrics_match_golden(nvtt, ctx, golden, golden2):
+    """golden_v2.npz (reference outputs, tests/golden/make_golden.py): the later format / quality pairs, every decoder
+    flavour, quantize / binarize with and without Floyd-Steinberg, rmsError / rmsAlphaError."""
+    lc1, lc2 = G.level_cases(), G.level_cases_v2()
+    for key, (kind, w, h, fmt, q, am, cw, pt) in lc2.items():
+        img = G.make_input(kind, w, h, planar=True)
+        got = ctx.encode_level(fmt, q, img, alpha_mode=am, color_weights=cw, pixel_type=pt)
+        assert np.array_equal(got, golden2[key]), key
+    for key, (src, in_v2, dec) in G.decode_cases().items():
+        kind, w, h, fmt = (lc2 if in_v2 else lc1)[src][:4]
+        blocks = (golden2 if in_v2 else golden)[src]
+        s = nvtt.Surface(ctx)
+        s.set_image_2d(fmt, w, h, blocks, decoder=dec)
+        assert np.array_equal(_sha(s.get()), golden2[key]), key
+    for key, (w, h, dither) in G.quantize_cases().items():
+        s = nvtt.Surface(ctx)
+        s.set_image(0, w, h, nvtt.synth.photo_bgra8(w, h, seed=w + h, alpha=True))
+        for ch, bits, exact in ((0, 5, 1), (1, 6, 1), (2, 3, 0)):
+            ctx._ck(ctx.L.nvttb_surface_quantize(s.h, ch, bits, exact, dither))
+        ctx._ck(ctx.L.nvttb_surface_binarize(s.h, 3, 0.4, dither))
+        assert np.array_equal(_sha(s.get()), golden2[key]), key
+    for name, src in (("bc1", "level_bc1_photo_48x40_q1"), ("bc3", "level_bc3_photo_48x40_q2")):
+        kind, w, h, fmt = lc1[src][:4]
+        for am in (0, 1):
+            ref_s = nvtt.Surface(ctx, alpha_mode=am)
+            ref_s.set_image(nvtt.InputFormat_RGBA_32F, w, h, np.ascontiguousarray(np.moveaxis(G.make_input(kind, w, h, planar=True), 0, 2)))
+            dec = nvtt.Surface(ctx)
+            dec.set_image_2d(fmt, w, h, golden[src])
+            want = golden2["metric_%s_am%d" % (name, am)]
+            got = (ref_s.rms_error(dec), ref_s.rms_alpha_error(dec))
+            for g, wv in zip(got, want):
+                assert abs(g - wv) <= 1e-6 * max(abs(float(wv)), 1e-30), (name, am, got, want)  # fp64 sums in a different order
+
+
+def test_gpu_v2_containers_and_quantisation_pipeline_match_golden(nvtt, golden2):
+    """KTX / DDS10 streams, colour dithering and binary alpha through the C++ mirror of nvtt::Compressor::process."""
+    import ctypes as C
+    import refapi
+    so = os.path.join(ROOT, "tests", "_build", "libnvtt_b200_harness.so")
+    if not os.path.exists(so):
+        pytest.fail("tests/_build/libnvtt_b200_harness.so missing: run __graft_entry__.build()")
+    L = C.CDLL(so)
+    L.ref_process.restype = C.c_long
+    L.ref_process.argtypes = [C.POINTER(refapi.RefProcessDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_long]
+    for key, (kind, w, h, fmt, q, kw) in G.pipeline_cases_v2().items():
+        img = np.ascontiguousarray(G.make_input(kind, w, h, planar=False))
+        d = refapi.RefProcessDesc()
+        d.inputFormat, d.textureType, d.width, d.height, d.faces = 0, 0, w, h, 1
+        d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = 2, kw.get("mip_filter", 0), 1, -1
+        d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = 3.0, 4.0, 1.0
+        d.inputGamma, d.outputGamma = 2.2, 2.2
+        d.isNormalMap, d.convertToNormalMap, d.normalizeMipmaps = int(kw.get("normal_map", False)), 0, 1
+        d.alphaMode, d.format, d.quality, d.pixelType = 0, fmt, q, 0
+        d.colorWeights = (C.c_float * 4)(1, 1, 1, 1)
+        d.outputHeader, d.container, d.threads = int(kw.get("header", False)), kw.get("container", 0), 0
+        d.quantization, d.alphaThreshold = kw.get("quantization", 0), kw.get("alpha_threshold", 127)
+        ptrs = (C.c_void_p * 1)(img.ctypes.data)
+        n = L.ref_process(C.byref(d), ptrs, None, 0)
+        assert n == golden2[key].size, (key, n, golden2[key].size)
+        out = np.empty(n, np.uint8)
+        assert L.ref_process(C.byref(d), ptrs, out.ctypes.data, n) == n
+        assert np.array_equal(out, golden2[key]), key
+
+
 def test_gpu_matches_oracle_restatement(nvtt, ctx):
     import oracleapi
     if not oracleapi.available():
