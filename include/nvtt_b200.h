@@ -174,6 +174,10 @@ typedef struct NvttbProcessDesc {
      * count divides by bandCount; the remaining small levels are encoded by band 0 alone.  The call then produces, per
      * face, the concatenation of this band's slices (see nvttb_process_band_slice); emit is called with the slice. */
     int bandIndex, bandCount;
+    /* nvttb_process_to_device only, with bandCount > 1: out_device is the WHOLE encoded chain of the processed faces (as one
+     * GPU would produce it) and this band stores its slices at their final offsets.  The buffer may live on another GPU
+     * (peer memory, see nvttb_ipc_*): the encoder's stores then go over NVLink and no gather is needed afterwards. */
+    int bandOutputInPlace;
 } NvttbProcessDesc;
 
 /* Called once per (face, mip) in the reference's order (face-major, mip-minor); data is host memory owned by the
@@ -194,6 +198,19 @@ NVTTB_API size_t nvttb_process_output_size(const NvttbProcessDesc *desc);
  * the level, *bytes = its size (0: this band emits nothing for the level).  With bandCount <= 1 the slice is the level.
  * Replaces nothing in the reference (it has no multi-device path); it is the contract between ranks for the gather. */
 NVTTB_API int nvttb_process_band_slice(const NvttbProcessDesc *desc, int level, size_t *offset, size_t *bytes);
+/* ---- one output buffer shared by the GPUs of a box (block-row sharding of one image) ------------------------------------
+ * The owner allocates the chain buffer and exports it; the other ranks (processes) open it and pass the pointer to
+ * nvttb_process_to_device with bandOutputInPlace = 1.  Thin wrappers over cudaMalloc / cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle(lazy peer access) / cudaIpcCloseMemHandle; the 64 handle bytes travel over any transport.
+ * Replaces nothing in the reference (it has no multi-device path). */
+NVTTB_API int nvttb_device_alloc(NvttbContext *ctx, size_t bytes, void **device_ptr);
+NVTTB_API int nvttb_device_free(NvttbContext *ctx, void *device_ptr);
+NVTTB_API int nvttb_ipc_export(NvttbContext *ctx, void *device_ptr, unsigned char handle[64]);
+NVTTB_API int nvttb_ipc_open(NvttbContext *ctx, const unsigned char handle[64], void **device_ptr);
+NVTTB_API int nvttb_ipc_close(NvttbContext *ctx, void *device_ptr);
+/* Bytes of the whole chain of the processed faces, ignoring the band fields (the size of the shared buffer above). */
+NVTTB_API size_t nvttb_process_whole_output_size(const NvttbProcessDesc *desc);
+
 /* Number of mip levels the pipeline produces (nv::countMipmaps, src/nvtt/Surface.cpp:181-193, capped by maxLevel). */
 NVTTB_API int nvttb_process_mip_count(const NvttbProcessDesc *desc);
 

@@ -44,7 +44,7 @@ class ProcessDesc(C.Structure):
                 ("isNormalMap", C.c_int), ("convertToNormalMap", C.c_int), ("normalizeMipmaps", C.c_int),
                 ("heightFactors", C.c_float * 4), ("bumpFrequencyScale", C.c_float * 4),
                 ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int),
-                ("bandIndex", C.c_int), ("bandCount", C.c_int)]
+                ("bandIndex", C.c_int), ("bandCount", C.c_int), ("bandOutputInPlace", C.c_int)]
 
 
 class KernelStat(C.Structure):
@@ -65,6 +65,7 @@ EXPORTS = [
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
+    "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
 ]
 
 _lib = None
@@ -127,6 +128,13 @@ def lib():
     L.nvttb_process_to_device.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, sz, C.POINTER(sz)]
     L.nvttb_process_output_size.argtypes = [C.POINTER(ProcessDesc)]
     L.nvttb_process_output_size.restype = sz
+    L.nvttb_process_whole_output_size.argtypes = [C.POINTER(ProcessDesc)]
+    L.nvttb_process_whole_output_size.restype = sz
+    L.nvttb_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.nvttb_device_free.argtypes = [vp, vp]
+    L.nvttb_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.nvttb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.nvttb_ipc_close.argtypes = [vp, vp]
     L.nvttb_process_mip_count.argtypes = [C.POINTER(ProcessDesc)]
     L.nvttb_process_band_slice.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L
@@ -147,8 +155,9 @@ def make_process_desc(input_format, w, h, fmt, quality, *, faces=1, wrap=WrapMod
                       mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
                       to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
                       pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), first_face=0, last_face=0, band_index=0,
-                      band_count=0):
+                      band_count=0, band_output_in_place=False):
     d = ProcessDesc()
+    d.bandOutputInPlace = int(band_output_in_place)
     d.inputFormat, d.width, d.height, d.faceCount = input_format, w, h, faces
     d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
     d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = kaiser

@@ -1321,6 +1321,13 @@ static size_t face_bytes(const NvttbProcessDesc *d) {
     return total;
 }
 
+static size_t whole_face_bytes(const NvttbProcessDesc *d) {
+    NvttbProcessDesc t = *d;
+    t.bandIndex = 0;
+    t.bandCount = 0;
+    return face_bytes(&t);
+}
+
 extern "C" int nvttb_process_band_slice(const NvttbProcessDesc *d, int level, size_t *offset, size_t *bytes) {
     if (!d || !offset || !bytes || level < 0 || level >= nvttb_process_mip_count(d)) return NVTTB_ERR_INVALID_INPUT;
     int w = d->width, h = d->height;
@@ -1384,6 +1391,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     for (int f = f0; f < f1; f++) {
         unsigned char *out = d_out + (size_t)(f - f0) * fbytes;
         unsigned char *hout = h_out ? h_out + (size_t)(f - f0) * fbytes : nullptr;
+        // bandOutputInPlace: d_out is the whole chain of the processed faces
+        unsigned char *whole_face = d_out + (size_t)(f - f0) * whole_face_bytes(d);
+        size_t level_off = 0;
         bool level0_done = false;
         if (banded) {
             if (!images[f]) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad input image");
@@ -1471,9 +1481,17 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 int y0, y1;
                 if (band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) {
                     e.height = y1 - y0;
-                    if ((rc = encode_device(ctx, &e, src + (size_t)y0 * w, w, y1 - y0, out, (size_t)w * h)) != NVTTB_OK) { cleanup(); return rc; }
+                    unsigned char *dst = out;
+                    if (d->bandOutputInPlace) {
+                        // final position of the slice inside the whole chain (possibly peer memory: the stores cross NVLink)
+                        size_t soff = 0, sbytes = 0;
+                        nvttb_process_band_slice(d, m, &soff, &sbytes);
+                        dst = whole_face + level_off + soff;
+                    }
+                    if ((rc = encode_device(ctx, &e, src + (size_t)y0 * w, w, y1 - y0, dst, (size_t)w * h)) != NVTTB_OK) { cleanup(); return rc; }
                     out += nvttb_level_size(e.format, w, y1 - y0);
                 }
+                level_off += nvttb_level_size(e.format, w, h);
                 continue;
             }
             if (!(m == 0 && level0_done)) {
@@ -1512,6 +1530,48 @@ static int check_process(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     return NVTTB_OK;
 }
 
+size_t nvttb_process_whole_output_size(const NvttbProcessDesc *d) {
+    if (!d) return 0;
+    int f0 = d->firstFace, f1 = d->lastFace;
+    if (f0 == 0 && f1 == 0) f1 = d->faceCount;
+    return whole_face_bytes(d) * (size_t)(f1 > f0 ? f1 - f0 : 0);
+}
+int nvttb_device_alloc(NvttbContext *ctx, size_t bytes, void **device_ptr) {
+    if (!ctx || !device_ptr) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(device_ptr, bytes));
+    return NVTTB_OK;
+}
+int nvttb_device_free(NvttbContext *ctx, void *device_ptr) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(device_ptr));
+    return NVTTB_OK;
+}
+int nvttb_ipc_export(NvttbContext *ctx, void *device_ptr, unsigned char handle[64]) {
+    if (!ctx || !device_ptr || !handle) return NVTTB_ERR_INVALID_INPUT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, 64);
+    return NVTTB_OK;
+}
+int nvttb_ipc_open(NvttbContext *ctx, const unsigned char handle[64], void **device_ptr) {
+    if (!ctx || !device_ptr || !handle) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return NVTTB_OK;
+}
+int nvttb_ipc_close(NvttbContext *ctx, void *device_ptr) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(device_ptr));
+    return NVTTB_OK;
+}
+
 int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, void *out_device,
                             size_t out_capacity, size_t *written) {
     int f0, f1, rc;
@@ -1522,7 +1582,9 @@ int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *d, const 
         if (written) *written = 0;
         return NVTTB_OK;
     }
-    if (!out_device || out_capacity < total) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
+    const bool in_place = d->bandCount > 1 && d->bandOutputInPlace;
+    const size_t need = in_place ? whole_face_bytes(d) * (size_t)(f1 - f0) : total;
+    if (!out_device || out_capacity < need) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
     if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)out_device)) != NVTTB_OK) return rc;
     if (written) *written = total;
     return NVTTB_OK;

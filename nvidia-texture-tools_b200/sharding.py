@@ -67,3 +67,43 @@ def assemble_bands(layout, per_band_bytes):
                 cur[b] += n
         levels.append(lvl)
     return np.concatenate(levels)
+
+
+class SharedOutput:
+    """ONE device buffer on rank `owner` that every rank's encoder writes its block rows into directly (peer memory over
+    NVLink / NVSwitch): the gather of the BCn slices disappears into the encode kernels' stores.  The owner allocates with
+    nvttb_device_alloc and exports a CUDA IPC handle; the 64 handle bytes go through torch.distributed; the others open it.
+    `ptr` is the device pointer valid in this process (pass it to process_to_device with band_output_in_place=True)."""
+
+    def __init__(self, ctx, nbytes, owner=0):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.owner, self.nbytes = ctx, owner, nbytes
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        L = ctx.L
+        dev = torch.device("cuda", torch.cuda.current_device()) if (dist.is_initialized() and dist.get_backend() == "nccl") else torch.device("cpu")
+        handle = torch.zeros(64, dtype=torch.uint8)
+        p = C.c_void_p()
+        if self.rank == owner:
+            ctx._ck(L.nvttb_device_alloc(ctx.h, nbytes, C.byref(p)))
+            buf = C.create_string_buffer(64)
+            ctx._ck(L.nvttb_ipc_export(ctx.h, p, buf))
+            handle = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            h = handle.to(dev)
+            dist.broadcast(h, src=owner)
+            handle = h.cpu()
+        if self.rank != owner:
+            ctx._ck(L.nvttb_ipc_open(ctx.h, bytes(handle.numpy().tobytes()), C.byref(p)))
+        self.ptr = p.value
+
+    def close(self):
+        import ctypes as C
+        if self.ptr is None:
+            return
+        if self.rank == self.owner:
+            self.ctx.L.nvttb_device_free(self.ctx.h, C.c_void_p(self.ptr))
+        else:
+            self.ctx.L.nvttb_ipc_close(self.ctx.h, C.c_void_p(self.ptr))
+        self.ptr = None
