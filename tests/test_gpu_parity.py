@@ -387,6 +387,19 @@ def test_block_row_sharding_of_one_image(nvtt, ref, ctx):
         assert np.array_equal(got, whole), (w, h, fmt_name, world)
         if fmt_name != "BC7":
             assert np.array_equal(got, ref.process([img], 0, w, h, fmt, q, **kw))
+        # bandOutputInPlace: every band stores its slices at their final offsets of ONE chain buffer (on several GPUs that
+        # buffer is peer memory of the owner; here the same device buffer is handed to every band in turn)
+        import ctypes as C
+        import torch
+        d_img = torch.from_numpy(img).cuda()
+        nw = int(nvtt.lib().nvttb_process_whole_output_size(d0))
+        assert nw == whole.size
+        shared = torch.zeros(nw, dtype=torch.uint8, device="cuda")
+        for b in range(world):
+            d = nvtt.make_process_desc(0, w, h, fmt, q, band_index=b, band_count=world, band_output_in_place=True, **kw)
+            ctx.process_to_device([d_img.data_ptr()], d, shared.data_ptr(), nw)
+        ctx.synchronize()
+        assert np.array_equal(shared.cpu().numpy(), whole), (w, h, fmt_name, world, "in place")
         # the big levels really are split: no band carries the whole level 0 when it divides
         if (h // 4) % world == 0 and h % 4 == 0:
             assert all(n == layout[0][0][1] for _, n in layout[0]) and layout[0][0][1] * world == ((w + 3) // 4) * (h // 4) * (8 if fmt_name == "BC1" else 16)
