@@ -472,7 +472,9 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
     size_t sgrid = (searchers / spt + 127) / 128;
     if (sgrid > 148u * 6u) sgrid = 148u * 6u;
     if (sgrid < 1) sgrid = 1;
-    NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 0>), (unsigned)sgrid, 128, S);
+    // two trials per loop trip where the palettes fit in registers (not mode 6: 16 entries x 4 channels; not the split modes)
+    if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7) NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search2<M>), (unsigned)sgrid, 128, S);
+    else NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 0>), (unsigned)sgrid, 128, S);
     if constexpr (M == 4) {
         cudaMemsetAsync(S.counters, 0, sizeof(unsigned), st);
         NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 1>), (unsigned)sgrid, 128, S);

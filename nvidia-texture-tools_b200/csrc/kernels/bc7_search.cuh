@@ -153,6 +153,82 @@ template <int M> NVB_DEV float bx_eval(const float4 *px, int np, unsigned A, uns
     return tot;
 }
 
+// negated palette of one trial as (entry 2j, entry 2j+1) pairs
+template <int M> NVB_DEV void bx_neg_palette(unsigned A, unsigned B, int la, int lb, float2 npal[Bc7Cfg<M>::NCH][Bc7Cfg<M>::NIDX / 2]) {
+    using C = Bc7Cfg<M>;
+    constexpr int N = C::NIDX;
+#pragma unroll
+    for (int ch = 0; ch < C::NCH; ch++) {
+        int a, b;
+        if (C::LSB == 0) {
+            a = avpcl_unquantize(bx_get(A, ch), C::PREC);
+            b = avpcl_unquantize(bx_get(B, ch), C::PREC);
+        } else {
+            const int lbb = (C::LSB == 1) ? la : lb;
+            a = avpcl_unquantize((bx_get(A, ch) << 1) | la, C::PREC + 1);
+            b = avpcl_unquantize((bx_get(B, ch) << 1) | lbb, C::PREC + 1);
+        }
+        float row[N];
+        bx_lerp_row<N>(a, b, row, 1);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) npal[ch][j] = make_float2(-row[2 * j], -row[2 * j + 1]);
+    }
+}
+
+// map_colors of TWO trials over the same texels (the texel is read and splatted once); same arithmetic per trial as bx_eval
+template <int M> NVB_DEV void bx_eval2(const float4 *px, int np, unsigned A0, unsigned B0, unsigned A1, unsigned B1, int la, int lb,
+                                       float &err0, float &err1, Bc7Idx<false> &idx0, Bc7Idx<false> &idx1) {
+    using C = Bc7Cfg<M>;
+    constexpr int N = C::NIDX;
+    float2 np0[C::NCH][N / 2], np1[C::NCH][N / 2];
+    bx_neg_palette<M>(A0, B0, la, lb, np0);
+    bx_neg_palette<M>(A1, B1, la, lb, np1);
+    float tot0 = 0, tot1 = 0;
+    unsigned long long id0 = 0, id1 = 0;
+    for (int i = 0; i < np; ++i) {
+        const float4 c = px[i];
+        const float ww = c.w;
+        const float2 cx = f2splat(c.x), cy = f2splat(c.y), cz = f2splat(c.z), cw = f2splat(c.w);
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            float best = 0;
+            int bj = 0;
+            bool live = true;
+#pragma unroll
+            for (int jp = 0; jp < N / 2; ++jp) {
+                const float2 p0 = t ? np1[0][jp] : np0[0][jp], p1 = t ? np1[1][jp] : np0[1][jp], p2 = t ? np1[2][jp] : np0[2][jp];
+                const float2 x = f2add(cx, p0), y = f2add(cy, p1), z = f2add(cz, p2);
+                const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
+                float e0, e1;
+                if (C::NCH == 3) {
+                    e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), ww);
+                    e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), ww);
+                } else {
+                    const float2 p3 = t ? np1[C::NCH - 1][jp] : np0[C::NCH - 1][jp];
+                    const float2 w = f2add(cw, p3);
+                    const float2 w2 = f2mul(w, w);
+                    e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), w2.x);
+                    e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), w2.y);
+                }
+                if (jp == 0) best = e0;
+                else NVB_BX_SCAN_STEP(e0, 2 * jp)
+                NVB_BX_SCAN_STEP(e1, 2 * jp + 1)
+            }
+            if (t == 0) {
+                tot0 += best;
+                id0 = (id0 << 4) | (unsigned long long)bj;
+            } else {
+                tot1 += best;
+                id1 = (id1 << 4) | (unsigned long long)bj;
+            }
+        }
+    }
+    err0 = tot0;
+    err1 = tot1;
+    idx0.lo = id0;
+    idx1.lo = id1;
+}
+
 // map_colors of modes 4,5 for one trial (all 16 texels; rotation applied to the texel as it is read)
 template <int M, int IM> NVB_DEV float bx_eval_split(const float4 *px, int rot, unsigned A, unsigned B, Bc7Idx<true> &idx) {
     constexpr int NRGB = (M == 5) ? 4 : (IM == 1 ? 8 : 4), NA = (M == 5) ? 4 : (IM == 1 ? 4 : 8);
@@ -575,6 +651,398 @@ template <int M, int IM> __global__ void __launch_bounds__(128) k_bc7_search(Bc7
 #undef NVB_BX_TRY_PERT
 #undef NVB_BX_EXH_EMIT
 }
+
+// Two trials per loop trip (modes 0, 1, 2, 3, 7): the -step / +step pair of a perturb_one level, two consecutive (a, b) pairs
+// of exhaustive().  The results are consumed in the reference's order (the second one against the threshold the first one may
+// have lowered), so the accepted steps are the same; what changes is that the state transitions - which run with one or
+// two active lanes - are paid once per two trials, and the texel is read and splatted once for both.
+template <int M> __global__ void __launch_bounds__(128) k_bc7_search2(Bc7SearchParams S) {
+    constexpr int IM = 0;
+    using X = Bc7X<M>;
+    using Idx = Bc7Idx<X::SPLIT>;
+    constexpr int NCAND_SPLIT = 4 * (M == 4 ? 2 : 1);
+    // this thread's texels: 16 float4 + 1 of padding, so that the 128-bit reads of 8 adjacent lanes hit 32 different banks
+    __shared__ float4 s_px[128 * 17];
+    float4 *px = s_px + threadIdx.x * 17;
+    long long s = 0;
+    long long total;
+    int ncand = 1;
+    if constexpr (X::SPLIT) total = (long long)S.nblk * 4;
+    else {
+        ncand = Bc7Cfg<M>::NITEMS;
+        total = (long long)S.nblk * ncand * X::NR * X::NLSB;
+    }
+    const int nblocks = S.P.lv.bw * S.P.lv.bh;
+
+    // searcher state
+    int phase = BXP_LOAD;
+    int np = 0, rot = 0;
+    long long slot = 0;          // where the result goes
+    unsigned A = 0, B = 0;       // current best endpoints ("opt"), 8 bits per channel
+    int la = 0, lb = 0;
+    float opt_err = 0;
+    int ch = 0;
+    // perturb_one
+    int pk = 0, do_b = 0, pv = 0, step = 0, sgn = -1, beststep = 0;
+    bool improved = false;
+    float pmin = 0;              // min_err of perturb_one / best_err of exhaustive
+    Idx pidx;                    // indices of the best trial of the running perturb_one / exhaustive
+    float err0 = 0;
+    int va = 0;
+    Idx t0, orig_idx, new_idx;
+    // exhaustive
+    bool first = true, exh_done = false;
+    float exh_orig = 0;
+    int eo = 0, ei = 0, ta = 0, tb = 0, amin = 0, bmin = 0;
+    pidx.clear(); t0.clear(); orig_idx.clear(); new_idx.clear();
+
+#ifdef NVB_EMU_STATS
+    int st_trials = 0, st_iters = 0;
+#endif
+    // next step of perturb_one's (step, sign) walk
+#define NVB_BX_ADV_SIGN()                  \
+    {                                      \
+        if (improved) pv += beststep;      \
+        improved = false;                  \
+        step >>= 1;                        \
+    }
+    // the trial of the current (step, sign), or — out of range — on to the next one
+#define NVB_BX_TRY_PERT()                                                                     \
+    {                                                                                         \
+        /* step <= half the range: at least one of pv - step / pv + step is in range */       \
+        const int vm_ = pv - step, vp_ = pv + step;                                           \
+        const bool okm_ = vm_ >= 0, okp_ = vp_ < (1 << X::prec(ch));                          \
+        const int v0_ = okm_ ? vm_ : vp_;                                                     \
+        s0sign = okm_ ? -1 : 1;                                                               \
+        have1 = okm_ && okp_;                                                                 \
+        const int v1_ = have1 ? vp_ : v0_;                                                    \
+        tA = do_b ? A : bx_set(A, ch, v0_);                                                   \
+        tB = do_b ? bx_set(B, ch, v0_) : B;                                                   \
+        tA1 = do_b ? A : bx_set(A, ch, v1_);                                                  \
+        tB1 = do_b ? bx_set(B, ch, v1_) : B;                                                  \
+        phase = BXP_PERT_WAIT;                                                                \
+        have = true;                                                                          \
+    }
+    // the trial under exhaustive()'s cursor, and the cursor moved on
+#define NVB_BX_EXH_EMIT()                                                                                             \
+    {                                                                                                                 \
+        const int prec_ = X::prec(ch), A0_ = bx_get(A, ch), B0_ = bx_get(B, ch);                                      \
+        const int alow_ = max(0, A0_ - 3), ahigh_ = min((1 << prec_) - 1, A0_ + 3);                                   \
+        const int blow_ = max(0, B0_ - 3), bhigh_ = min((1 << prec_) - 1, B0_ + 3);                                   \
+        const bool a_le_b_ = A0_ <= B0_;                                                                              \
+        const int o_end_ = a_le_b_ ? ahigh_ : bhigh_ - 1, i_end_ = a_le_b_ ? bhigh_ - 1 : ahigh_, lowi_ = a_le_b_ ? blow_ : alow_; \
+        ta = a_le_b_ ? eo : ei;                                                                                       \
+        tb = a_le_b_ ? ei : eo;                                                                                       \
+        tA = bx_set(A, ch, ta);                                                                                       \
+        tB = bx_set(B, ch, tb);                                                                                       \
+        ++ei;                                                                                                         \
+        while (!exh_done && ei > i_end_) {                                                                            \
+            ++eo;                                                                                                     \
+            if (eo > o_end_) exh_done = true;                                                                         \
+            else ei = max(eo, lowi_);                                                                                 \
+        }                                                                                                             \
+        have1 = !exh_done;                                                                                            \
+        ta1 = ta; tb1 = tb; tA1 = tA; tB1 = tB;                                                                       \
+        if (have1) {                                                                                                  \
+            ta1 = a_le_b_ ? eo : ei;                                                                                  \
+            tb1 = a_le_b_ ? ei : eo;                                                                                  \
+            tA1 = bx_set(A, ch, ta1);                                                                                 \
+            tB1 = bx_set(B, ch, tb1);                                                                                 \
+            ++ei;                                                                                                     \
+            while (!exh_done && ei > i_end_) {                                                                        \
+                ++eo;                                                                                                 \
+                if (eo > o_end_) exh_done = true;                                                                     \
+                else ei = max(eo, lowi_);                                                                             \
+            }                                                                                                         \
+        }                                                                                                             \
+        phase = BXP_EXH_WAIT;                                                                                         \
+        have = true;                                                                                                  \
+    }
+
+    unsigned tA = 0, tB = 0, tA1 = 0, tB1 = 0;  // the two trials of a trip
+    int s0sign = -1, ta1 = 0, tb1 = 0;
+    bool have = false, have1 = false;
+    for (;;) {
+        // slow path: lanes whose next trial is not simply the next step of the running perturb_one / exhaustive walk
+        while (!have && phase != BXP_EXIT) {
+#ifdef NVB_EMU_STATS
+            ++st_iters;
+#endif
+            switch (phase) {
+            case BXP_LOAD: {
+                // searchers are handed out one at a time: the searches differ a lot in length (every improvement restarts
+                // the channel loop), a static assignment would leave most lanes of a warp waiting for the longest one
+                s = (long long)atomicAdd(S.counters, 1u);
+                if (s >= total) {
+                    phase = BXP_EXIT;
+                    break;
+                }
+                uint4 su;
+                if constexpr (X::SPLIT) {
+                    const int blk = (int)(s >> 2);
+                    rot = (int)(s & 3);
+                    slot = (long long)blk * NCAND_SPLIT + rot * (M == 4 ? 2 : 1) + IM;
+                    su = S.setup[slot];
+                    const float4 *tile = S.tiles + (size_t)blk * 16;
+                    np = 16;
+                    la = lb = 0;
+                    for (int i = 0; i < 16; i++) {
+                        float4 c = __ldg(tile + i);
+                        // AGBR / RABG / RGAB: swap channel rot-1 with alpha
+                        const float w0 = c.w;
+                        c.w = rot == 1 ? c.x : rot == 2 ? c.y : rot == 3 ? c.z : c.w;
+                        c.x = rot == 1 ? w0 : c.x;
+                        c.y = rot == 2 ? w0 : c.y;
+                        c.z = rot == 3 ? w0 : c.z;
+                        px[i] = c;
+                    }
+                } else {
+                    using C = Bc7Cfg<M>;
+                    const int lsbmode = (int)(s % X::NLSB);
+                    const long long q = s / X::NLSB;
+                    const unsigned e = S.perm ? S.perm[q] : (unsigned)q;
+                    const int region = (int)(e % X::NR);
+                    const int cand = (int)((e / X::NR) % ncand);
+                    const int blk = (int)(e / (X::NR * ncand));
+                    slot = (long long)e * X::NLSB + lsbmode;
+                    su = S.setup[e];
+                    const float4 *tile = S.tiles + (size_t)blk * 16;
+                    int shape = 0;
+                    if constexpr (C::NSH > 1) shape = S.P.shapes[((size_t)Bc7Slot<M>::v * nblocks + S.blk0 + blk) * 16 + cand];
+                    np = 0;
+                    for (int i = 0; i < 16; i++)
+                        if (bc7_region<C::NR>(shape, i) == region) {
+                            float4 c = __ldg(tile + i);
+                            if (C::NCH == 3) {
+                                const float w = c.w - 255.0f;  // the palette's alpha is 255 in the RGB modes
+                                c.w = w * w;
+                            }
+                            px[np++] = c;
+                        }
+                    la = lsbmode & 1;
+                    lb = (X::LSB == 2) ? (lsbmode >> 1) & 1 : 0;
+                }
+                A = su.x;
+                B = su.y;
+                if (X::LSB != 0) {
+                    // in_err = map_colors(temp_in with this lsb combination)
+                    tA = tA1 = A;
+                    tB = tB1 = B;
+                    have1 = false;
+                    phase = BXP_INIT_WAIT;
+                    have = true;
+                } else {
+                    opt_err = __uint_as_float(su.w);
+                    ch = 0;
+                    phase = BXP_CH_START;
+                }
+                break;
+            }
+            case BXP_CH_START:
+                if (ch >= X::NCH) {
+                    ch = 0;
+                    first = true;
+                    phase = BXP_EXH_CH_START;
+                } else {
+                    pk = 0;
+                    do_b = 0;
+                    pv = bx_get(A, ch);
+                    pmin = opt_err;
+                    step = 1 << (X::prec(ch) - 1);
+                    sgn = -1;
+                    improved = false;
+                    phase = BXP_PERT_EMIT;
+                    NVB_BX_TRY_PERT()
+                }
+                break;
+            case BXP_PERT_EMIT:
+                if (step == 0) phase = BXP_PERT_FIN;
+                else NVB_BX_TRY_PERT()
+                break;
+            case BXP_PERT_FIN: {
+                bool again = false;  // start another perturb_one on endpoint do_b
+                if (pk == 0) {
+                    err0 = pmin;
+                    va = pv;
+                    t0 = pidx;
+                    pk = 1;
+                    do_b = 1;
+                    again = true;
+                } else if (pk == 1) {
+                    const float err1 = pmin;
+                    if (err0 < err1) {
+                        if (!(err0 >= opt_err)) {
+                            new_idx = orig_idx = t0;
+                            A = bx_set(A, ch, va);
+                            opt_err = err0;
+                            do_b = 1;
+                            again = true;
+                        }
+                    } else {
+                        if (!(err1 >= opt_err)) {
+                            new_idx = orig_idx = pidx;
+                            B = bx_set(B, ch, pv);
+                            opt_err = err1;
+                            do_b = 0;
+                            again = true;
+                        }
+                    }
+                    pk = 2;
+                    if (!again) {  // `continue`: next channel without the restart test
+                        ++ch;
+                        phase = BXP_CH_START;
+                    }
+                } else {
+                    if (pmin >= opt_err) {
+                        if (orig_idx.differs(new_idx)) ch = -1;  // indices changed: start over
+                        ++ch;
+                        phase = BXP_CH_START;
+                    } else {
+                        new_idx = pidx;
+                        if (do_b == 0) A = bx_set(A, ch, pv);
+                        else B = bx_set(B, ch, pv);
+                        opt_err = pmin;
+                        do_b = 1 - do_b;
+                        again = true;
+                    }
+                }
+                if (again) {
+                    pv = bx_get(do_b ? B : A, ch);
+                    pmin = opt_err;
+                    step = 1 << (X::prec(ch) - 1);
+                    sgn = -1;
+                    improved = false;
+                    phase = BXP_PERT_EMIT;
+                    NVB_BX_TRY_PERT()
+                }
+                break;
+            }
+            case BXP_EXH_CH_START: {
+                if (ch >= X::NCH) {
+                    phase = BXP_STORE;
+                    break;
+                }
+                exh_orig = opt_err;
+                pmin = exh_orig;
+                if (exh_orig == 0) {  // exhaustive() returns at once; nothing can improve
+                    ++ch;
+                    break;
+                }
+                const int prec = X::prec(ch), A0 = bx_get(A, ch), B0 = bx_get(B, ch);
+                const int alow = max(0, A0 - 3), ahigh = min((1 << prec) - 1, A0 + 3);
+                const int blow = max(0, B0 - 3), bhigh = min((1 << prec) - 1, B0 + 3);
+                const bool a_le_b = A0 <= B0;
+                const int o_end = a_le_b ? ahigh : bhigh - 1, i_end = a_le_b ? bhigh - 1 : ahigh, lowi = a_le_b ? blow : alow;
+                eo = a_le_b ? alow : blow;
+                exh_done = eo > o_end;
+                if (!exh_done) ei = max(eo, lowi);
+                while (!exh_done && ei > i_end) {
+                    ++eo;
+                    if (eo > o_end) exh_done = true;
+                    else ei = max(eo, lowi);
+                }
+                phase = BXP_EXH_CH_END;
+                if (!exh_done) NVB_BX_EXH_EMIT()
+                break;
+            }
+            case BXP_EXH_EMIT:
+                if (exh_done) phase = BXP_EXH_CH_END;
+                else NVB_BX_EXH_EMIT()
+                break;
+            case BXP_EXH_CH_END: {
+                const float new_err = pmin;
+                if (pmin < exh_orig) {
+                    A = bx_set(A, ch, amin);
+                    B = bx_set(B, ch, bmin);
+                    t0 = pidx;
+                    if (X::EXHREF) opt_err = pmin;  // modes 0 and 3 pass the error by reference
+                }
+                if (new_err < opt_err) {
+                    opt_err = new_err;
+                    if (first) {
+                        orig_idx = t0;
+                        first = false;
+                    } else if (orig_idx.differs(t0)) {
+                        ch = -1;
+                        first = true;
+                    }
+                }
+                ++ch;
+                phase = BXP_EXH_CH_START;
+                break;
+            }
+            case BXP_STORE:
+                S.res[slot] = make_uint4(A, B, (unsigned)(la | (lb << 1)), __float_as_uint(opt_err));
+#ifdef NVB_EMU_STATS
+                emu_bx_stat(M, np, st_trials, st_iters);
+                st_trials = st_iters = 0;
+#endif
+                phase = BXP_LOAD;
+                break;
+            default:
+                break;
+            }
+        }
+        // Every lane of the warp stays in the loop until the last one has run out of work (idle lanes carry np = 0), so the
+        // vote below is executed by all 32 lanes: it is the explicit reconvergence point in front of the trial evaluation.
+        // (Without it ptxas treats the hand-out loop as a possible spin loop and lets the warp run on in pieces.)
+        if (__all_sync(0xffffffffu, phase == BXP_EXIT)) break;
+        if (phase == BXP_EXIT) np = 0;
+
+#ifdef NVB_EMU_STATS
+        ++st_trials;
+#endif
+        // ---- the one expensive step: every live lane of the warp is here together ----
+        Idx ti, ti1;
+        float err, err1;
+        bx_eval2<M>(px, np, tA, tB, tA1, tB1, la, lb, err, err1, ti, ti1);
+
+        // consume the result and, on the common path, produce the next trial right here (all lanes together)
+        have = false;
+        if (phase == BXP_EXIT) {
+            // idle lane
+        } else if (phase == BXP_INIT_WAIT) {
+            opt_err = err;
+            ch = 0;
+            phase = BXP_CH_START;
+        } else if (phase == BXP_PERT_WAIT) {
+            if (err < pmin) {
+                improved = true;
+                pmin = err;
+                beststep = s0sign * step;
+                pidx = ti;
+            }
+            if (have1 && err1 < pmin) {  // the +step trial, against the threshold the -step trial may have lowered
+                improved = true;
+                pmin = err1;
+                beststep = step;
+                pidx = ti1;
+            }
+            NVB_BX_ADV_SIGN()
+            phase = BXP_PERT_FIN;
+            if (step != 0) NVB_BX_TRY_PERT()
+        } else {  // BXP_EXH_WAIT
+            if (err < pmin) {
+                amin = ta;
+                bmin = tb;
+                pmin = err;
+                pidx = ti;
+            }
+            if (have1 && err1 < pmin) {
+                amin = ta1;
+                bmin = tb1;
+                pmin = err1;
+                pidx = ti1;
+            }
+            phase = BXP_EXH_CH_END;
+            if (!exh_done) NVB_BX_EXH_EMIT()
+        }
+    }
+#undef NVB_BX_ADV_SIGN
+#undef NVB_BX_TRY_PERT
+#undef NVB_BX_EXH_EMIT
+}
+
 
 // ---- order the (candidate, region) entries of a chunk by texel count -----------------------------------------------------------
 // Lanes of a warp walk the texels of their regions in lock step; a warp whose regions have 3 and 13 texels runs 13 steps

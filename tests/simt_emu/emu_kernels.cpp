@@ -85,7 +85,12 @@ template <int M, int NCAND> static void emu_bc7_mode(Bc7Params &P, int nb) {
             emu::launch(dim3(og), dim3(256), 0, [&] { k_bc7_order<M, NCAND, 1>(S); });
         }
         const int grid = 3;  // few threads: every thread walks several searchers
-        emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 0>(S); });
+        if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7) {
+            if (how && !strcmp(how, "search1")) emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 0>(S); });
+            else emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search2<M>(S); });
+        } else {
+            emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 0>(S); });
+        }
         if constexpr (M == 4) {
             counters[0] = 0;
             emu::launch(dim3(grid), dim3(128), 0, [&] { k_bc7_search<M, 1>(S); });
