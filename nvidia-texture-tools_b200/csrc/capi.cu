@@ -531,7 +531,9 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.midpoints6 = ctx->d_icbc_mid + 32;
         P.match5 = ctx->d_icbc_match;
         P.match6 = ctx->d_icbc_match + 512;
-        NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
+#define NVB_BC1_GO(KFN) NVB_LAUNCH(ctx, K_BC1, (double)w * h, KFN, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P)
+        NVB_BC1_DISPATCH(P, NVB_BC1_GO);
+#undef NVB_BC1_GO
     } else if (d->format == F_BC3_RGBM) {
         // CompressorBC3_RGBM -> compress_dxt5_rgbm (BlockCompressor.cpp:235-238, CompressorDXT5_RGBM.cpp:54-118):
         // colour block = ICBC Quality_Default (Level 8) on (R,G,B)/M with weights w*M, no 3-colour mode, colour weights 1;
@@ -554,7 +556,9 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         P.match6 = ctx->d_icbc_match + 512;
         P.rgbm = 1;
         P.rgbm_min = d->rgbmThreshold;
-        NVB_LAUNCH(ctx, K_BC1, (double)w * h, k_bc1_icbc, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P);
+#define NVB_BC1_GO(KFN) NVB_LAUNCH(ctx, K_BC1, (double)w * h, KFN, (nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS, NVB_BC1_GROUPS * 16, P)
+        NVB_BC1_DISPATCH(P, NVB_BC1_GO);
+#undef NVB_BC1_GO
         RgbmAlphaParams A;
         A.lv = lv;
         A.out = d_out;

@@ -314,7 +314,72 @@ NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const 
     return e1[0] * msq[0] + e1[1] * msq[1] + e1[2] * msq[2];
 }
 
+// Two splits at once (A, B): every quantity of icbc_eval_split is carried as a pair so that the multiplications issue as
+// FMUL2 and the product-free subtractions as FADD2; a sum that consumes a product stays two scalar FADDs (ptxas would
+// contract a packed add of a packed product into FFMA2, nvb_common.cuh).  Operation for operation the same arithmetic per
+// split; only the errors are returned (the winner is re-evaluated by icbc_eval_split for its endpoints).
+NVB_DEV float2 icbc_round_pair(float2 x, float grid, float gridrcp) {
+    const float2 s = make_float2(icbc_saturate(x.x), icbc_saturate(x.y));
+    const float2 t = f2add_s(f2mul(s, f2splat(grid)), f2splat(0.5f));
+    return f2mul(make_float2((float)x86_ftoi(t.x), (float)x86_ftoi(t.y)), f2splat(gridrcp));
+}
 template <bool FOUR>
+NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, float4 sum, const float msq[3]) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int a0 = (int)(pka & 31) - 1, a1 = (int)((pka >> 5) & 31) - 1, a2 = (int)((pka >> 10) & 31) - 1;
+    const int b0 = (int)(pkb & 31) - 1, b1 = (int)((pkb >> 5) & 31) - 1, b2 = (int)((pkb >> 10) & 31) - 1;
+    const float4 sa0 = (a0 >= 0) ? sat[a0] : zero, sb0 = (b0 >= 0) ? sat[b0] : zero;
+    const float4 sa1 = (a1 >= 0) ? sat[a1] : zero, sb1 = (b1 >= 0) ? sat[b1] : zero;
+    const float2 s0[4] = {make_float2(sa0.x, sb0.x), make_float2(sa0.y, sb0.y), make_float2(sa0.z, sb0.z), make_float2(sa0.w, sb0.w)};
+    const float2 s1[4] = {make_float2(sa1.x, sb1.x), make_float2(sa1.y, sb1.y), make_float2(sa1.z, sb1.z), make_float2(sa1.w, sb1.w)};
+    float2 alpha2, beta2, ab, ax[3];
+    if (FOUR) {
+        const float4 sa2 = (a2 >= 0) ? sat[a2] : zero, sb2 = (b2 >= 0) ? sat[b2] : zero;
+        const float2 s2[4] = {make_float2(sa2.x, sb2.x), make_float2(sa2.y, sb2.y), make_float2(sa2.z, sb2.z), make_float2(sa2.w, sb2.w)};
+        const float2 w3 = f2sub(f2splat(sum.w), s2[3]);
+        const float2 w2 = f2sub(s2[3], s1[3]), w1 = f2sub(s1[3], s0[3]), w0 = s0[3];
+        alpha2 = f2add_s(f2mul(w2, f2splat(1.0f / 9.0f)), f2add_s(f2mul(w1, f2splat(4.0f / 9.0f)), w0));
+        beta2 = f2add_s(f2mul(w1, f2splat(1.0f / 9.0f)), f2add_s(f2mul(w2, f2splat(4.0f / 9.0f)), w3));
+        ab = f2mul(f2add(w1, w2), f2splat(2.0f / 9.0f));
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float2 x2 = f2sub(s2[k], s1[k]), x1 = f2sub(s1[k], s0[k]);
+            ax[k] = f2add_s(f2mul(x2, f2splat(1.0f / 3.0f)), f2add_s(f2mul(x1, f2splat(2.0f / 3.0f)), s0[k]));
+        }
+    } else {
+        const float2 w2 = f2sub(f2splat(sum.w), s1[3]);
+        const float2 w1 = f2sub(s1[3], s0[3]), w0 = s0[3];
+        ab = f2mul(w1, f2splat(0.25f));
+        alpha2 = f2add_s(w0, ab);
+        beta2 = f2add_s(w2, ab);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float2 x1 = f2sub(s1[k], s0[k]);
+            ax[k] = f2add_s(s0[k], f2mul(x1, f2splat(0.5f)));
+        }
+    }
+    const float2 det = f2sub_s(f2mul(alpha2, beta2), f2mul(ab, ab));
+    const float2 factor = make_float2(1.0f / det.x, 1.0f / det.y);
+    const float S3[3] = {sum.x, sum.y, sum.z};
+    float2 e1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float2 alphax = ax[k];
+        const float2 betax = f2sub(f2splat(S3[k]), alphax);
+        float2 av = f2mul(f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab)), factor);
+        float2 bv = f2mul(f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab)), factor);
+        av = (k == 1) ? icbc_round_pair(av, 63.0f, 1.0f / 63.0f) : icbc_round_pair(av, 31.0f, 1.0f / 31.0f);
+        bv = (k == 1) ? icbc_round_pair(bv, 63.0f, 1.0f / 63.0f) : icbc_round_pair(bv, 31.0f, 1.0f / 31.0f);
+        const float2 e2 = f2mul(f2sub_s(f2mul(av, f2sub_s(f2mul(bv, ab), alphax)), f2mul(bv, betax)), f2splat(2.0f));
+        e1[k] = f2add_s(f2mul(f2mul(av, av), alpha2), f2add_s(f2mul(f2mul(bv, bv), beta2), e2));
+    }
+    return f2add_s(f2add_s(f2mul(e1[0], f2splat(msq[0])), f2mul(e1[1], f2splat(msq[1]))), f2mul(e1[2], f2splat(msq[2])));
+}
+
+// PAIR: two splits per trip with packed fp32 (fewer issue slots, more code).  The level-9 kernel keeps the scalar loop: its
+// instruction-cache footprint is already the limiter (ncu: stalled_no_instruction 2.7 -> 4.4 per issue with the packed loop,
+// 8192² Production 65.5 -> 70 ms), while the level-8 kernel gains (48.0 -> ~45 ms).
+template <bool FOUR, bool PAIR>
 NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, unsigned gm, int l, int count) {
     const float4 sum = S.sat[count - 1];
     const float msq[3] = {P.cw[0] * P.cw[0], P.cw[1] * P.cw[1], P.cw[2] * P.cw[2]};
@@ -323,11 +388,27 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
     float besterror = FLT_MAX;
     int besti = 0x7fffffff;
     float a[3], b[3];
-    for (int i = l; i < total; i += 16) {
-        const float e = icbc_eval_split<FOUR>(S.sat, __ldg(tab + i), sum, msq, a, b);
-        if (e < besterror) {
-            besterror = e;
+    if (!PAIR) {
+        for (int i = l; i < total; i += 16) {
+            const float e = icbc_eval_split<FOUR>(S.sat, __ldg(tab + i), sum, msq, a, b);
+            if (e < besterror) {
+                besterror = e;
+                besti = i;
+            }
+        }
+    }
+    // two splits per trip (i and i + 16); the last, unpaired one re-uses split i for the idle half
+    for (int i = l; PAIR && i < total; i += 32) {
+        const bool two = i + 16 < total;
+        const unsigned pka = __ldg(tab + i), pkb = two ? __ldg(tab + i + 16) : pka;
+        const float2 e = icbc_eval_pair<FOUR>(S.sat, pka, pkb, sum, msq);
+        if (e.x < besterror) {
+            besterror = e.x;
             besti = i;
+        }
+        if (two && e.y < besterror) {
+            besterror = e.y;
+            besti = i + 16;
         }
     }
 #pragma unroll
@@ -349,7 +430,10 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
     return r;
 }
 
-__global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
+// One instantiation per ICBC level (1 = box fit, 8 = cluster fit, 9 = cluster fit + refinement) and for the BC3-RGBM colour
+// block: the generic kernel was 177 KB of SASS - more than the instruction cache - and warps in different phases of it
+// evicted each other's code (Production got slower when the cluster fit got bigger).
+template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16, 9) k_bc1_icbc_t(Bc1Params P) {
     __shared__ Bc1GroupSmem smem[NVB_BC1_GROUPS];
     const int grp = threadIdx.x >> 4;
     const int l = threadIdx.x & 15;
@@ -371,7 +455,7 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
         wt = 1.0f;
         if (P.transparency) wt = icbc_saturate(load_texel(P.lv, 3, px, py));
     }
-    if (P.rgbm) {
+    if (RGBM) {
         // convert_to_rgbm (CompressorDXT5_RGBM.cpp:23-49)
         const float R = icbc_saturate(cx), G = icbc_saturate(cy), B = icbc_saturate(cz);
         const float M = nv_max(nv_max(R, G), nv_max(B, P.rgbm_min));
@@ -388,7 +472,7 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
     int count = 16;
     bool any_black = false;
 
-    if (P.level >= 2) {
+    if (LEVEL >= 2) {
         // ---- reduce_colors: merge texel i into the first earlier cluster within 1/256 per channel ----
         const float threshold = 1.0f / 256;
         float qx = 0.0f, qy = 0.0f, qz = 0.0f, qw = 0.0f;  // cluster l (valid for l < n)
@@ -442,7 +526,7 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
         __syncwarp(gm);
     }
 
-    if (P.level == 1) {
+    if (LEVEL == 1) {
         // ---- box fit on all 16 (un-reduced, padding included) colours + least squares refit ----
         // fit_colors_bbox: fold over the texels in order with icbc::max/min semantics
         float c0x = 0.0f, c0y = 0.0f, c0z = 0.0f, c1x = 1.0f, c1y = 1.0f, c1z = 1.0f;
@@ -500,12 +584,12 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
     } else {
         // ---- compress_dxt1_cluster_fit ----
         icbc_compute_sat(S, gm, l, count);
-        FitResult f4 = icbc_cluster_fit<true>(P, S, gm, l, count);
+        FitResult f4 = icbc_cluster_fit<true, LEVEL != 9>(P, S, gm, l, count);
         Bc1Block cf;
         float best = icbc_output_block(P, gm, l, true, false, f4.sx, f4.sy, f4.sz, f4.ex, f4.ey, f4.ez, cx, cy, cz, wt, &cf);
         // three colour mode (Levels 8/9: always tried; transparent black allowed)
         int sat_count = count;
-        bool do_three = !P.rgbm;  // compress_dxt5_rgbm passes three_color_mode = false
+        bool do_three = !RGBM;  // compress_dxt5_rgbm passes three_color_mode = false
         if (do_three && any_black) {
             // skip_blacks on the reduced set, then a new SAT
             const float4 q = (l < count) ? S.pts[l] : make_float4(1.f, 1.f, 1.f, 0.f);
@@ -523,7 +607,7 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
             }
         }
         if (do_three) {
-            FitResult f3 = icbc_cluster_fit<false>(P, S, gm, l, sat_count);
+            FitResult f3 = icbc_cluster_fit<false, LEVEL != 9>(P, S, gm, l, sat_count);
             Bc1Block tb;
             const float te = icbc_output_block(P, gm, l, false, true, f3.sx, f3.sy, f3.sz, f3.ex, f3.ey, f3.ez, cx, cy, cz, wt, &tb);
             if (te < best) {
@@ -535,7 +619,7 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
             out = cf;
             error = best;
         }
-        if (P.level == 9) {
+        if (LEVEL == 9) {
             // ---- refine_endpoints (three_color_mode == true: no endpoint re-ordering) ----
             // The reference walks up to 256 single-step endpoint moves one after the other and stops 33 candidates after the
             // last accepted one.  Between two acceptances every candidate is measured against the same block and the same
@@ -609,5 +693,14 @@ __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16) k_bc1_icbc(Bc1Params P) {
     }
     if (l == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(out.c0 | (out.c1 << 16), out.indices);
 }
+
+// host-side dispatch on (P.level, P.rgbm): LAUNCH(kernel) is expanded with the matching instantiation
+#define NVB_BC1_DISPATCH(P, LAUNCH)                                  \
+    do {                                                             \
+        if ((P).rgbm) { LAUNCH((k_bc1_icbc_t<8, true>)); }           \
+        else if ((P).level == 1) { LAUNCH((k_bc1_icbc_t<1, false>)); } \
+        else if ((P).level == 9) { LAUNCH((k_bc1_icbc_t<9, false>)); } \
+        else { LAUNCH((k_bc1_icbc_t<8, false>)); }                   \
+    } while (0)
 
 }  // namespace nvb

@@ -12,6 +12,12 @@
 #endif
 
 #define NVB_DEV __device__ __forceinline__
+// a real call instead of another inlined copy: for big helpers used at several places of one kernel (instruction-cache footprint)
+#ifdef NVB_EMU
+#define NVB_DEV_CALL static inline
+#else
+#define NVB_DEV_CALL __device__ __noinline__
+#endif
 // read-only lookup tables defined in headers (global memory, L1/L2-cached; plain static data under the emulator)
 #ifdef NVB_EMU
 #define NVB_TABLE static const

@@ -143,7 +143,11 @@ void emu_bc1(const float *planar, int w, int h, const float *cw, int level, int 
     P.four = g_four.data(); P.three = g_three.data(); P.four_total = g_four_total; P.three_total = g_three_total;
     P.midpoints5 = g_mid5; P.midpoints6 = g_mid6; P.match5 = g_match5; P.match6 = g_match6;
     int nb = P.lv.bw * P.lv.bh;
-    emu::launch(dim3((nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS), dim3(NVB_BC1_GROUPS * 16), 0, [&] { k_bc1_icbc(P); });
+    emu::launch(dim3((nb + NVB_BC1_GROUPS - 1) / NVB_BC1_GROUPS), dim3(NVB_BC1_GROUPS * 16), 0, [&] {
+#define EMU_BC1_GO(KFN) KFN(P)
+        NVB_BC1_DISPATCH(P, EMU_BC1_GO);
+#undef EMU_BC1_GO
+    });
 }
 
 void emu_bc6(const float *planar, int w, int h, int is_signed, int transparency, unsigned char *out, int gamma) {
