@@ -142,6 +142,9 @@ NVTTB_API int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSu
 /* nvtt::angularError = nv::rmsAngularError (src/nvtt/Surface.cpp:3287-3291, src/nvimage/ErrorMetric.cpp:475-511): RMS angle
  * between the unpacked, normalised normals, in radians (acosf: CUDA vs glibc, 1e-5 relative). */
 NVTTB_API int nvttb_angular_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
+/* nvtt::cieLabError = nv::cieLabError (src/nvtt/Surface.cpp:3282-3285, src/nvimage/ErrorMetric.cpp:192-342): mean length of the
+ * CIE-Lab difference; built on powf, so CUDA and glibc agree to ~1e-4 relative, not bit for bit. */
+NVTTB_API int nvttb_cielab_error(const NvttbSurface *reference, const NvttbSurface *img, float *out);
 /* Surface::data(): copy planar fp32 RGBA (4*w*h floats) to the host. */
 NVTTB_API int nvttb_surface_download(const NvttbSurface *s, float *out);
 /* Device pointer of the planar fp32 data (valid until the next op on the surface). */

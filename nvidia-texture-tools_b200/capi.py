@@ -62,7 +62,7 @@ EXPORTS = [
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
     "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
-    "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error",
+    "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
     "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
@@ -112,6 +112,7 @@ def lib():
     L.nvttb_rms_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_rms_alpha_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_angular_error.argtypes = [vp, vp, C.POINTER(cf)]
+    L.nvttb_cielab_error.argtypes = [vp, vp, C.POINTER(cf)]
     L.nvttb_surface_to_linear.argtypes = [vp, cf]
     L.nvttb_surface_to_gamma.argtypes = [vp, cf]
     L.nvttb_surface_build_next_mipmap.argtypes = [vp, ci, ci, cf, C.POINTER(cf), C.POINTER(ci)]
@@ -310,6 +311,11 @@ class Surface:
         """nvtt::rmsError(self as reference, img)."""
         v = C.c_float()
         self.ctx._ck(self.L.nvttb_rms_error(self.h, img.h, C.byref(v)))
+        return v.value
+
+    def cielab_error(self, img):
+        v = C.c_float()
+        self.ctx._ck(self.L.nvttb_cielab_error(self.h, img.h, C.byref(v)))
         return v.value
 
     def angular_error(self, img):

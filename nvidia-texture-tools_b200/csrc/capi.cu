@@ -1093,7 +1093,7 @@ static int error_metric(const NvttbSurface *ref, const NvttbSurface *img, int mo
     CK(cudaStreamSynchronize(ctx->stream));
     double mse = 0;
     for (unsigned i = 0; i < grid; i++) mse += part[i];
-    *out = (float)sqrt(mse / (double)(unsigned)count);
+    *out = (mode == 4) ? (float)(mse / (double)(unsigned)count) : (float)sqrt(mse / (double)(unsigned)count);
     return NVTTB_OK;
 }
 int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) {
@@ -1101,6 +1101,7 @@ int nvttb_rms_error(const NvttbSurface *reference, const NvttbSurface *img, floa
 }
 int nvttb_rms_alpha_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 2, out); }
 int nvttb_angular_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 3, out); }
+int nvttb_cielab_error(const NvttbSurface *reference, const NvttbSurface *img, float *out) { return error_metric(reference, img, 4, out); }
 
 int nvttb_surface_to_linear(NvttbSurface *s, float gamma) {
     if (!s) return NVTTB_ERR_INVALID_INPUT;

@@ -465,9 +465,27 @@ __global__ void __launch_bounds__(128) k_decode_dxt(DecodeParams P) {
 struct ErrorParams {
     const float *ref, *img;  // planar fp32 [4][count]
     size_t count;
-    int mode;                // 0: rmsColorError, 1: rmsColorError alpha-weighted (a0*a0), 2: rmsAlphaError, 3: rmsAngularError
+    int mode;                // 0: rmsColorError, 1: rmsColorError alpha-weighted (a0*a0), 2: rmsAlphaError, 3: rmsAngularError, 4: cieLabError (sum of |dLab|)
     double *partial;         // one per CTA
 };
+
+// rgbToCieLab (ErrorMetric.cpp:192-278): powf(c, 2.2) -> XYZ -> Lab.  powf is libm's in the reference and CUDA's here, so
+// nvtt::cieLabError is compared with a relative tolerance (1e-4), not bit for bit.
+NVB_DEV float cielab_f(float t) {
+    const float epsilon = powf(6.0f / 29.0f, 3);
+    if (t > epsilon) return powf(t, 1.0f / 3.0f);
+    return 1.0f / 3.0f * powf(29.0f / 6.0f, 2) * t + 4.0f / 29.0f;
+}
+NVB_DEV void rgb_to_cielab(float r, float g, float b, float lab[3]) {
+    const float lr = powf(r, 2.2f), lg = powf(g, 2.2f), lb = powf(b, 2.2f);
+    const float X = 0.412453f * lr + 0.357580f * lg + 0.180423f * lb;
+    const float Y = 0.212671f * lr + 0.715160f * lg + 0.072169f * lb;
+    const float Z = 0.019334f * lr + 0.119193f * lg + 0.950227f * lb;
+    const float fx = cielab_f(X / 0.950456f), fy = cielab_f(Y / 1.0f), fz = cielab_f(Z / 1.088754f);
+    lab[0] = 116 * fx - 16;
+    lab[1] = 500 * (fx - fy);
+    lab[2] = 200 * (fy - fz);
+}
 
 __global__ void __launch_bounds__(256) k_error_metric(ErrorParams P) {
     __shared__ double s_sum[256];
@@ -476,6 +494,12 @@ __global__ void __launch_bounds__(256) k_error_metric(ErrorParams P) {
         if (P.mode == 2) {
             const float a = P.img[i + P.count * 3] - P.ref[i + P.count * 3];
             acc += (double)(a * a);
+        } else if (P.mode == 4) {
+            float l0[3], l1[3];
+            rgb_to_cielab(P.ref[i], P.ref[i + P.count], P.ref[i + P.count * 2], l0);
+            rgb_to_cielab(P.img[i], P.img[i + P.count], P.img[i + P.count * 2], l1);
+            const float dx = l0[0] - l1[0], dy = l0[1] - l1[1], dz = l0[2] - l1[2];
+            acc += (double)sqrtf(dx * dx + dy * dy + dz * dz);
         } else if (P.mode == 3) {
             // nv::rmsAngularError (ErrorMetric.cpp:475-511): unpack, normalizeSafe(v, 0, 0), angle = acosf(clamp(dot)); the
             // reference's acosf is glibc's, ours CUDA's: the metric is compared with a 1e-5 relative tolerance

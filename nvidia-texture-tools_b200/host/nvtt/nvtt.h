@@ -187,6 +187,7 @@ struct Surface {
 NVTT_API float rmsError(const Surface &reference, const Surface &img);
 NVTT_API float rmsAlphaError(const Surface &reference, const Surface &img);
 NVTT_API float angularError(const Surface &reference, const Surface &img);
+NVTT_API float cieLabError(const Surface &reference, const Surface &img);
 
 NVTT_API unsigned int version();
 NVTT_API const char *errorString(Error e);

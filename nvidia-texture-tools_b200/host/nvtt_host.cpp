@@ -863,6 +863,11 @@ float nvtt::rmsError(const Surface &reference, const Surface &img) {
     if (reference.m->s && img.m->s) nvttb_rms_error(reference.m->s, img.m->s, &v);
     return v;
 }
+float nvtt::cieLabError(const Surface &reference, const Surface &img) {
+    float v = FLT_MAX;
+    if (reference.m->s && img.m->s) nvttb_cielab_error(reference.m->s, img.m->s, &v);
+    return v;
+}
 float nvtt::angularError(const Surface &reference, const Surface &img) {
     float v = FLT_MAX;
     if (reference.m->s && img.m->s) nvttb_angular_error(reference.m->s, img.m->s, &v);

@@ -238,6 +238,14 @@ int ref_rms_error(int format, int w, int h, const void *blocks, const float *rgb
     *rmsAlpha = nvtt::rmsAlphaError(ref, img);
     return 1;
 }
+// nvtt::cieLabError between an RGBA32F image and its decoded BCn level
+int ref_cielab_error(int format, int w, int h, const void *blocks, const float *rgba32f, float *out) {
+    Surface ref, img;
+    if (!ref.setImage(InputFormat_RGBA_32F, w, h, 1, rgba32f)) return 0;
+    if (!img.setImage2D((Format)format, Decoder_D3D10, w, h, blocks)) return 0;
+    *out = nvtt::cieLabError(ref, img);
+    return 1;
+}
 // nvtt::angularError between a packed normal map (RGBA32F) and its decoded BCn level
 int ref_angular_error(int format, int w, int h, const void *blocks, const float *rgba32f, float *out) {
     Surface ref, img;

@@ -17,6 +17,7 @@ def _harness(path):
     L.ref_decode_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_rms_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ref_angular_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.ref_cielab_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     return L
 
 
@@ -188,3 +189,19 @@ def test_angular_error_matches_reference(nvtt, ctx, libs):
             assert L.ref_angular_error(fmt, w, h, blocks.ctypes.data, rgba.ctypes.data, C.byref(v)) == 1
             vals.append(v.value)
         assert vals[1] > 0 and abs(vals[0] - vals[1]) <= 1e-5 * vals[1], (fmt, vals)
+
+
+def test_cielab_error_matches_reference(nvtt, ctx, libs):
+    """nvtt::cieLabError of BC1 / BC3 encoded photos: powf differs between glibc and CUDA, hence 1e-4 relative."""
+    ours, theirs = libs
+    w, h = 128, 96
+    planar = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(w, h, seed=13, alpha=True))
+    rgba = np.ascontiguousarray(np.moveaxis(planar, 0, 2))
+    for fmt in (1, 4):
+        blocks = ctx.encode_level(fmt, 1, planar)
+        vals = []
+        for L in (ours, theirs):
+            v = C.c_float()
+            assert L.ref_cielab_error(fmt, w, h, blocks.ctypes.data, rgba.ctypes.data, C.byref(v)) == 1
+            vals.append(v.value)
+        assert vals[1] > 0 and abs(vals[0] - vals[1]) <= 1e-4 * vals[1], (fmt, vals)
