@@ -99,43 +99,50 @@ NVB_DEV SquishSplit squish_eval_split(const float4 *T, int i0, int i1, int i2, f
     return r;
 }
 
-// Two splits at once: every quantity of squish_eval_split is carried as a (split A, split B) pair so that the
-// multiplications issue as FMUL2 and the product-free additions as FADD2.  Operation for operation the same arithmetic
-// as squish_eval_split (each lane of a pair is an independent IEEE round-to-nearest op), only the errors are returned.
+// Two splits at once, as packed fp32 pairs (FMUL2 / FADD2 / unfused FFMA2-by-one sums).  Operation for operation the same
+// arithmetic as squish_eval_split - each half of a pair is an independent IEEE round-to-nearest op - only the errors are
+// returned.  The pairing follows the registers an LDS.128 of a T row fills: the R and G channels of ONE split are already an
+// aligned register pair (x, y), so they go through squish_chan_pair together with the split's weights sums broadcast; only
+// the B channel and the weight sums are paired across the two splits (A, B), which costs the register moves.
+NVB_DEV pf2 squish_chan_pair(pf2 X0, pf2 X1, pf2 X2, pf2 xs, pf2 alpha2, pf2 beta2, pf2 ab, float fx, float fy, pf2 g, pf2 gr) {
+    const pf2 c23 = pf2_splat(2.0f / 3.0f), c13 = pf2_splat(1.0f / 3.0f);
+    const pf2 alphax = pf2_add_s(pf2_add_s(X0, pf2_mul(X1, c23)), pf2_mul(X2, c13));
+    const pf2 betax = pf2_sub(xs, alphax);
+    const pf2 at = pf2_sub_s(pf2_mul(alphax, beta2), pf2_mul(betax, ab));
+    const pf2 bt = pf2_sub_s(pf2_mul(betax, alpha2), pf2_mul(alphax, ab));
+    // min(1, max(0, t * factor)) with NaN -> 0 is exactly a saturating multiply
+    pf2 a = pf2_pack(__saturatef(__fmul_rn(pf2_lo(at), fx)), __saturatef(__fmul_rn(pf2_hi(at), fy)));
+    pf2 b = pf2_pack(__saturatef(__fmul_rn(pf2_lo(bt), fx)), __saturatef(__fmul_rn(pf2_hi(bt), fy)));
+    const pf2 ha = pf2_add_s(pf2_mul(g, a), pf2_splat(0.5f)), hb = pf2_add_s(pf2_mul(g, b), pf2_splat(0.5f));
+    a = pf2_mul(pf2_pack(floorf(pf2_lo(ha)), floorf(pf2_hi(ha))), gr);
+    b = pf2_mul(pf2_pack(floorf(pf2_lo(hb)), floorf(pf2_hi(hb))), gr);
+    const pf2 s1 = pf2_add_s(pf2_mul(pf2_mul(a, a), alpha2), pf2_mul(pf2_mul(b, b), beta2));
+    const pf2 d = pf2_sub_s(pf2_sub_s(pf2_mul(pf2_mul(a, b), ab), pf2_mul(a, alphax)), pf2_mul(b, betax));
+    return pf2_add(s1, pf2_add(d, d));
+}
+
 NVB_DEV float2 squish_eval_pair(const float4 *T, unsigned pa, unsigned pb, float4 xsum, float mx, float my, float mz) {
     const float4 a0 = T[pa & 0xFF], a1 = T[(pa >> 8) & 0xFF], a2 = T[pa >> 16];
     const float4 b0 = T[pb & 0xFF], b1 = T[(pb >> 8) & 0xFF], b2 = T[pb >> 16];
-    const float2 w0 = make_float2(a0.w, b0.w), w1 = make_float2(a1.w, b1.w), w2 = make_float2(a2.w, b2.w);
-    const float2 w3 = f2sub(f2sub(f2sub(f2splat(xsum.w), w0), w1), w2);
-    const float2 c49 = f2splat(4.0f / 9.0f), c19 = f2splat(1.0f / 9.0f), c29 = f2splat(2.0f / 9.0f);
-    const float2 alpha2 = f2add_s(f2add_s(w0, f2mul(w1, c49)), f2mul(w2, c19));
-    const float2 beta2 = f2add_s(f2add_s(w3, f2mul(w2, c49)), f2mul(w1, c19));
-    const float2 ab = f2mul(f2add(w1, w2), c29);
-    const float2 det = f2sub_s(f2mul(alpha2, beta2), f2mul(ab, ab));
-    const float2 factor = make_float2(1.0f / det.x, 1.0f / det.y);
-    const float2 c23 = f2splat(2.0f / 3.0f), c13 = f2splat(1.0f / 3.0f);
-    float2 e[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const float2 X0 = (k == 0) ? make_float2(a0.x, b0.x) : (k == 1) ? make_float2(a0.y, b0.y) : make_float2(a0.z, b0.z);
-        const float2 X1 = (k == 0) ? make_float2(a1.x, b1.x) : (k == 1) ? make_float2(a1.y, b1.y) : make_float2(a1.z, b1.z);
-        const float2 X2 = (k == 0) ? make_float2(a2.x, b2.x) : (k == 1) ? make_float2(a2.y, b2.y) : make_float2(a2.z, b2.z);
-        const float xs = (k == 0) ? xsum.x : (k == 1) ? xsum.y : xsum.z;
-        const float g = (k == 1) ? 63.0f : 31.0f, gr = (k == 1) ? (1.0f / 63.0f) : (1.0f / 31.0f);
-        const float2 alphax = f2add_s(f2add_s(X0, f2mul(X1, c23)), f2mul(X2, c13));
-        const float2 betax = f2sub(f2splat(xs), alphax);
-        const float2 an = f2mul(f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab)), factor);
-        const float2 bn = f2mul(f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab)), factor);
-        float2 a = make_float2(std_min(1.0f, std_max(0.0f, an.x)), std_min(1.0f, std_max(0.0f, an.y)));
-        float2 b = make_float2(std_min(1.0f, std_max(0.0f, bn.x)), std_min(1.0f, std_max(0.0f, bn.y)));
-        const float2 ga = f2mul(f2splat(g), a), gb = f2mul(f2splat(g), b);
-        a = f2mul(make_float2(floorf(__fadd_rn(ga.x, 0.5f)), floorf(__fadd_rn(ga.y, 0.5f))), f2splat(gr));
-        b = f2mul(make_float2(floorf(__fadd_rn(gb.x, 0.5f)), floorf(__fadd_rn(gb.y, 0.5f))), f2splat(gr));
-        const float2 s1 = f2add_s(f2mul(f2mul(a, a), alpha2), f2mul(f2mul(b, b), beta2));
-        const float2 d = f2sub_s(f2sub_s(f2mul(f2mul(a, b), ab), f2mul(a, alphax)), f2mul(b, betax));
-        e[k] = f2add(s1, f2add(d, d));
-    }
-    return f2add_s(f2add_s(f2mul(e[0], f2splat(mx)), f2mul(e[1], f2splat(my))), f2mul(e[2], f2splat(mz)));
+    const pf2 w0 = pf2_pack(a0.w, b0.w), w1 = pf2_pack(a1.w, b1.w), w2 = pf2_pack(a2.w, b2.w);
+    const pf2 w3 = pf2_sub(pf2_sub(pf2_sub(pf2_splat(xsum.w), w0), w1), w2);
+    const pf2 c49 = pf2_splat(4.0f / 9.0f), c19 = pf2_splat(1.0f / 9.0f), c29 = pf2_splat(2.0f / 9.0f);
+    const pf2 alpha2 = pf2_add_s(pf2_add_s(w0, pf2_mul(w1, c49)), pf2_mul(w2, c19));
+    const pf2 beta2 = pf2_add_s(pf2_add_s(w3, pf2_mul(w2, c49)), pf2_mul(w1, c19));
+    const pf2 ab = pf2_mul(pf2_add(w1, w2), c29);
+    const pf2 det = pf2_sub_s(pf2_mul(alpha2, beta2), pf2_mul(ab, ab));
+    const float fA = 1.0f / pf2_lo(det), fB = 1.0f / pf2_hi(det);
+    const pf2 gxy = pf2_pack(31.0f, 63.0f), grxy = pf2_pack(1.0f / 31.0f, 1.0f / 63.0f);
+    const pf2 xsxy = pf2_pack(xsum.x, xsum.y);
+    const pf2 eA = squish_chan_pair(pf2_pack(a0.x, a0.y), pf2_pack(a1.x, a1.y), pf2_pack(a2.x, a2.y), xsxy, pf2_splat(pf2_lo(alpha2)),
+                                    pf2_splat(pf2_lo(beta2)), pf2_splat(pf2_lo(ab)), fA, fA, gxy, grxy);
+    const pf2 eB = squish_chan_pair(pf2_pack(b0.x, b0.y), pf2_pack(b1.x, b1.y), pf2_pack(b2.x, b2.y), xsxy, pf2_splat(pf2_hi(alpha2)),
+                                    pf2_splat(pf2_hi(beta2)), pf2_splat(pf2_hi(ab)), fB, fB, gxy, grxy);
+    const pf2 eZ = squish_chan_pair(pf2_pack(a0.z, b0.z), pf2_pack(a1.z, b1.z), pf2_pack(a2.z, b2.z), pf2_splat(xsum.z), alpha2, beta2,
+                                    ab, fA, fB, pf2_splat(31.0f), pf2_splat(1.0f / 31.0f));
+    const pf2 mxy = pf2_pack(mx, my);
+    const pf2 pA = pf2_mul(eA, mxy), pB = pf2_mul(eB, mxy), pZ = pf2_mul(eZ, pf2_splat(mz));
+    return make_float2(__fadd_rn(__fadd_rn(pf2_lo(pA), pf2_hi(pA)), pf2_lo(pZ)), __fadd_rn(__fadd_rn(pf2_lo(pB), pf2_hi(pB)), pf2_hi(pZ)));
 }
 
 // WeightedClusterFit::Compress3 (weightedclusterfit.cpp:370-472): clusters at 0, 1/2, 1

@@ -58,9 +58,67 @@ NVB_DEV float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 NVB_DEV float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 NVB_DEV float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 #endif
+#ifdef NVB_EMU
 NVB_DEV float2 f2add_s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 NVB_DEV float2 f2sub_s(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+#else
+// An unfused packed sum in ONE issue slot: fma(a, 1, b) rounds a*1 + b once, i.e. it IS add.rn(a, b) bit for bit (and
+// fma(b, -1, a) is sub.rn(a, b)), and an FFMA2 cannot be contracted with the FMUL2 that produced its operand.  The ones
+// live in constant memory so that neither NVVM nor ptxas can see their value and fold the fma back into an add.
+static __constant__ float2 nvb_one2 = {1.0f, 1.0f};
+static __constant__ float2 nvb_mone2 = {-1.0f, -1.0f};
+NVB_DEV float2 f2add_s(float2 a, float2 b) { return __ffma2_rn(a, nvb_one2, b); }
+NVB_DEV float2 f2sub_s(float2 a, float2 b) { return __ffma2_rn(b, nvb_mone2, a); }
+#endif
 NVB_DEV float2 f2splat(float v) { return make_float2(v, v); }
+
+// The same pairs kept PACKED in one 64-bit register across operations (pf2): the float2 intrinsics above re-pack their
+// operands at every call and ptxas then materialises a fresh register pair per use; with pf2 a pair is packed once.
+//   pf2_add / pf2_sub: plain FADD2, only for operands that are not products.  pf2_add_s / pf2_sub_s: the unfused
+//   FFMA2-by-one sum, safe after a product.
+#ifdef NVB_EMU
+typedef float2 pf2;
+NVB_DEV pf2 pf2_pack(float lo, float hi) { return make_float2(lo, hi); }
+NVB_DEV float pf2_lo(pf2 v) { return v.x; }
+NVB_DEV float pf2_hi(pf2 v) { return v.y; }
+NVB_DEV pf2 pf2_mul(pf2 a, pf2 b) { return f2mul(a, b); }
+NVB_DEV pf2 pf2_add(pf2 a, pf2 b) { return f2add(a, b); }
+NVB_DEV pf2 pf2_sub(pf2 a, pf2 b) { return f2sub(a, b); }
+NVB_DEV pf2 pf2_add_s(pf2 a, pf2 b) { return f2add_s(a, b); }
+NVB_DEV pf2 pf2_sub_s(pf2 a, pf2 b) { return f2sub_s(a, b); }
+#else
+typedef unsigned long long pf2;
+NVB_DEV pf2 pf2_pack(float lo, float hi) {
+    pf2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+NVB_DEV float pf2_lo(pf2 v) { return __uint_as_float((unsigned)v); }
+NVB_DEV float pf2_hi(pf2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+NVB_DEV pf2 pf2_mul(pf2 a, pf2 b) {
+    pf2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+NVB_DEV pf2 pf2_fma(pf2 a, pf2 b, pf2 c) {
+    pf2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+NVB_DEV pf2 pf2_add(pf2 a, pf2 b) {
+    pf2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+NVB_DEV pf2 pf2_sub(pf2 a, pf2 b) {
+    pf2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+NVB_DEV pf2 pf2_add_s(pf2 a, pf2 b) { return pf2_fma(a, *reinterpret_cast<const pf2 *>(&nvb_one2), b); }
+NVB_DEV pf2 pf2_sub_s(pf2 a, pf2 b) { return pf2_fma(b, *reinterpret_cast<const pf2 *>(&nvb_mone2), a); }
+#endif
+NVB_DEV pf2 pf2_splat(float v) { return pf2_pack(v, v); }
 
 // ---- gamma 2.2 approximations (src/nvmath/Gamma.cpp:311-354) -------------------------------------------
 // table[k] = float(2^((k-127)*p/q)) for the 9 "sign|exponent" bits; the tables are generated on the host by
