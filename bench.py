@@ -316,17 +316,19 @@ def main():
             "per_kernel_ms": {n: round(v["total_ms"], 4) for n, v in sorted(prof.items())},
         }
         if dom[0] == "k_bc3_color":
-            # From the committed ncu --set full capture of this kernel on this input (profiles/r1c_ncu_bc3_color.txt):
+            # From the committed ncu --set full capture of this kernel on this input (profiles/r1i_ncu_bc3_color.txt):
             # DRAM bytes and warp instructions of the level-0 launch.  The live CUDA-event time of the same launch turns the
             # instruction count into an issue rate against 148 SMs x 4 schedulers x 1 warp-instruction per clock.
             roofline["traffic"] = 211.0e6 + 14.8e6
-            winst = 6.54e9
+            winst = 9505.0 * (SIZE // 4) * (SIZE // 4) / 2  # 9505 warp-instructions per warp of two 4x4 blocks
             if sm_mhz:
                 issue_peak = 148 * 4 * sm_mhz * 1e6
                 issue_ach = winst / (k["max_ms"] / 1e3)
                 roofline["issue"] = {"bound": "sm_issue", "achieved": issue_ach, "peak": issue_peak, "unit": "warp-inst/s",
                                      "frac": issue_ach / issue_peak, "warp_insts_per_launch": winst,
-                                     "source": "smsp__inst_executed.sum of the 4096x4096 level-0 launch, profiles/r1c_ncu_bc3_color.txt; "
+                                     "fma_pipe_active_pct_ncu": 72.7,
+                                     "source": "smsp__inst_executed.sum per warp of the level-0 launch (profiles/r1i_ncu_bc3_color.txt, same synthetic image "
+                                               "at 2048x2048) x the warps of this launch; the kernel is FP32-pipe bound (math-pipe throttle is its top stall); "
                                                "time = this run's CUDA events; clock = median SM clock sampled during the timed region"}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:

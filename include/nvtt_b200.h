@@ -96,6 +96,26 @@ NVTTB_API int nvttb_format_supported(int format, int quality);
 NVTTB_API int nvttb_encode_level(NvttbContext *ctx, const NvttbEncodeDesc *desc, const float *rgba, int rgba_location,
                                  void *out, int out_location, size_t out_capacity);
 
+/* ---- Format_RGB / Format_RGBA: uncompressed pixel formats -------------------------------------------------
+ * Replaces PixelFormatConverter::compress (src/nvtt/CompressorRGB.cpp:410-575) and, for the size, nv::computeImageSize's
+ * Format_RGBA branch (src/nvtt/Surface.cpp:210-214).  The fields are CompressionOptions::Private's after
+ * setPixelFormat(bitcount, masks) / setPixelFormat(rsize, gsize, bsize, asize) / setPixelType / setPitchAlignment
+ * (src/nvtt/CompressionOptions.cpp:113-173): bitcount != 0 selects the mask form.  PixelType_SharedExp 9/9/9/5 (RGB9E5)
+ * is not implemented (size 0 / NVTTB_ERR_UNSUPPORTED_FEATURE); the signed types write zeros, as the reference does. */
+typedef struct NvttbPixelFormatDesc {
+    int pixelType;                        /* nvtt::PixelType */
+    unsigned bitcount;                    /* mask form: bits per pixel (<= 32); 0 = size form */
+    unsigned rmask, gmask, bmask, amask;  /* mask form */
+    unsigned rsize, gsize, bsize, asize;  /* size form (and the float channel widths: 0, 10, 11, 16 or 32) */
+    int pitchAlignment;                   /* bytes, power of two (default 1) */
+    int width, height;                    /* texels; depth is 1 */
+} NvttbPixelFormatDesc;
+/* Bytes of one level = height * computeBytePitch(width, bits, pitchAlignment); 0 if the description is unsupported. */
+NVTTB_API size_t nvttb_pixel_format_level_size(const NvttbPixelFormatDesc *desc);
+/* rgba: planar fp32 [4][h][w] on host or device; out: height scanlines of the pitch above, host or device. */
+NVTTB_API int nvttb_convert_level(NvttbContext *ctx, const NvttbPixelFormatDesc *desc, const float *rgba, int rgba_location,
+                                  void *out, int out_location, size_t out_capacity);
+
 /* ---- Surface ops on the device (the image-op seam called from src/nvtt/Context.cpp:267-343) ------------- */
 NVTTB_API int nvttb_surface_create(NvttbContext *ctx, NvttbSurface **out);
 NVTTB_API void nvttb_surface_destroy(NvttbSurface *s);

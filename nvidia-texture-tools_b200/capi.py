@@ -36,6 +36,28 @@ class EncodeDesc(C.Structure):
                 ("rgbmThreshold", C.c_float)]
 
 
+class PixelFormatDesc(C.Structure):
+    """NvttbPixelFormatDesc: CompressionOptions' Format_RGBA layout (setPixelFormat / setPixelType / setPitchAlignment)."""
+    _fields_ = [("pixelType", C.c_int), ("bitcount", C.c_uint),
+                ("rmask", C.c_uint), ("gmask", C.c_uint), ("bmask", C.c_uint), ("amask", C.c_uint),
+                ("rsize", C.c_uint), ("gsize", C.c_uint), ("bsize", C.c_uint), ("asize", C.c_uint),
+                ("pitchAlignment", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+def make_pixel_format_desc(w, h, masks=None, sizes=None, pixel_type=0, pitch_alignment=1):
+    """masks = (bitcount, rmask, gmask, bmask, amask) or sizes = (r, g, b, a); neither = the reference's default BGRA8."""
+    d = PixelFormatDesc()
+    d.pixelType, d.pitchAlignment, d.width, d.height = pixel_type, pitch_alignment, w, h
+    if sizes is not None:
+        d.bitcount = 0
+        d.rsize, d.gsize, d.bsize, d.asize = sizes
+    else:
+        d.bitcount, d.rmask, d.gmask, d.bmask, d.amask = masks or (32, 0xFF0000, 0xFF00, 0xFF, 0xFF000000)
+        if masks is None:
+            d.rsize = d.gsize = d.bsize = d.asize = 8
+    return d
+
+
 class ProcessDesc(C.Structure):
     _fields_ = [("inputFormat", C.c_int), ("width", C.c_int), ("height", C.c_int), ("faceCount", C.c_int),
                 ("wrapMode", C.c_int), ("mipmapFilter", C.c_int), ("generateMipmaps", C.c_int), ("maxLevel", C.c_int),
@@ -56,7 +78,7 @@ EMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C
 
 EXPORTS = [
     "nvttb_device_count", "nvttb_context_create", "nvttb_context_destroy", "nvttb_last_error", "nvttb_launch_count",
-    "nvttb_synchronize", "nvttb_stream", "nvttb_timer_start", "nvttb_timer_stop", "nvttb_profile_begin", "nvttb_profile_end", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level",
+    "nvttb_synchronize", "nvttb_stream", "nvttb_timer_start", "nvttb_timer_stop", "nvttb_profile_begin", "nvttb_profile_end", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level", "nvttb_pixel_format_level_size", "nvttb_convert_level",
     "nvttb_surface_create", "nvttb_surface_destroy", "nvttb_surface_clone", "nvttb_surface_set_wrap_mode",
     "nvttb_surface_set_alpha_mode", "nvttb_surface_set_normal_map", "nvttb_surface_width", "nvttb_surface_height",
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
@@ -97,6 +119,9 @@ def lib():
     L.nvttb_level_size.restype = sz
     L.nvttb_format_supported.argtypes = [ci, ci]
     L.nvttb_encode_level.argtypes = [vp, C.POINTER(EncodeDesc), vp, ci, vp, ci, sz]
+    L.nvttb_pixel_format_level_size.argtypes = [C.POINTER(PixelFormatDesc)]
+    L.nvttb_pixel_format_level_size.restype = sz
+    L.nvttb_convert_level.argtypes = [vp, C.POINTER(PixelFormatDesc), vp, ci, vp, ci, sz]
     L.nvttb_surface_create.argtypes = [vp, C.POINTER(vp)]
     L.nvttb_surface_destroy.argtypes = [vp]
     L.nvttb_surface_clone.argtypes = [vp, C.POINTER(vp)]
@@ -234,6 +259,21 @@ class Context:
         out = np.empty(n, np.uint8)
         self._ck(self.L.nvttb_encode_level(self.h, C.byref(d), a.ctypes.data, HOST, out.ctypes.data, HOST, n))
         return out
+
+    def convert_level(self, planar_rgba, **kw):
+        """Format_RGBA: planar_rgba float32 [4,h,w] on the host -> np.uint8 scanlines (PixelFormatConverter::compress)."""
+        a = np.ascontiguousarray(planar_rgba, dtype=np.float32)
+        _, h, w = a.shape
+        d = make_pixel_format_desc(w, h, **kw)
+        n = self.L.nvttb_pixel_format_level_size(C.byref(d))
+        if n == 0:
+            raise RuntimeError("unsupported pixel format")
+        out = np.empty(n, np.uint8)
+        self._ck(self.L.nvttb_convert_level(self.h, C.byref(d), a.ctypes.data, HOST, out.ctypes.data, HOST, n))
+        return out
+
+    def convert_level_device(self, desc, d_rgba_ptr, d_out_ptr, cap):
+        self._ck(self.L.nvttb_convert_level(self.h, C.byref(desc), d_rgba_ptr, DEVICE, d_out_ptr, DEVICE, cap))
 
     def encode_level_device(self, desc, d_rgba_ptr, d_out_ptr, cap):
         self._ck(self.L.nvttb_encode_level(self.h, C.byref(desc), d_rgba_ptr, DEVICE, d_out_ptr, DEVICE, cap))

@@ -14,6 +14,7 @@
 #include "kernels/bc6h_search.cuh"
 #include "kernels/image_ops.cuh"
 #include "kernels/bc_decode.cuh"
+#include "kernels/pixel_format.cuh"
 
 #include <cuda_runtime.h>
 #include <map>
@@ -44,9 +45,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_PIXEL_FORMAT, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize", "k_quantize"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize", "k_quantize", "k_pixel_format"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -971,6 +972,132 @@ int nvttb_encode_level(NvttbContext *ctx, const NvttbEncodeDesc *desc, const flo
         d_out = (unsigned char *)ctx->out_dev.p;
     }
     if ((rc = encode_device(ctx, desc, d_rgba, w, h, d_out)) != NVTTB_OK) return rc;
+    if (out_location == NVTTB_HOST) {
+        CK(cudaMemcpyAsync(out, d_out, size, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (rgba_location == NVTTB_HOST) {
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return NVTTB_OK;
+}
+
+// ---- Format_RGB / Format_RGBA: PixelFormatConverter::compress (src/nvtt/CompressorRGB.cpp:410-575) --------------------------
+namespace {
+struct PixelLayout {
+    unsigned bitCount, pitch;
+    int kind, aligned;
+    unsigned size[4], shift[4];
+};
+void mask_shift_size(unsigned mask, unsigned *shift, unsigned *size) {  // PixelFormat::maskShiftAndSize
+    *shift = 0;
+    *size = 0;
+    if (!mask) return;
+    while ((mask & 1) == 0) { ++*shift; mask >>= 1; }
+    while ((mask & 1) == 1) { ++*size; mask >>= 1; }
+}
+// 0 when the description is one the reference asserts on (more than 32 bits of fixed point, bad float sizes are zero-padded as there)
+bool pixel_layout(const NvttbPixelFormatDesc *d, PixelLayout *L) {
+    if (d->width <= 0 || d->height <= 0 || d->pitchAlignment <= 0 || (d->pitchAlignment & (d->pitchAlignment - 1))) return false;
+    memset(L, 0, sizeof *L);
+    const unsigned sz[4] = {d->rsize, d->gsize, d->bsize, d->asize};
+    if (d->pixelType == 4 /* PixelType_Float */) {
+        for (int i = 0; i < 4; i++) { if (sz[i] > 32) return false; L->size[i] = sz[i]; }
+        L->bitCount = sz[0] + sz[1] + sz[2] + sz[3];
+        L->kind = 2;
+        L->aligned = 1;
+        for (int i = 0; i < 4; i++) if (sz[i] != 0 && sz[i] != 16 && sz[i] != 32) L->aligned = 0;
+    } else {
+        if (d->bitcount != 0) {
+            L->bitCount = d->bitcount;
+            const unsigned mask[4] = {d->rmask, d->gmask, d->bmask, d->amask};
+            for (int i = 0; i < 4; i++) mask_shift_size(mask[i], &L->shift[i], &L->size[i]);
+        } else {
+            for (int i = 0; i < 4; i++) { if (sz[i] > 32) return false; L->size[i] = sz[i]; }
+            L->bitCount = sz[0] + sz[1] + sz[2] + sz[3];
+            L->shift[3] = 0;
+            L->shift[2] = L->shift[3] + sz[3];
+            L->shift[1] = L->shift[2] + sz[2];
+            L->shift[0] = L->shift[1] + sz[1];
+        }
+        if (L->bitCount > 32) return false;  // nvCheck(bitCount <= 32)
+        // UnsignedNorm = 0, UnsignedInt = 2; SignedNorm / SignedInt write zero components; SharedExp writes zeros unless 9/9/9/5
+        if (d->pixelType == 0) L->kind = 0;
+        else if (d->pixelType == 2) L->kind = 1;
+        else if (d->pixelType == 6 /* PixelType_SharedExp */ && sz[0] == 9 && sz[1] == 9 && sz[2] == 9 && sz[3] == 5) return false;  // RGB9E5: not implemented
+        else L->kind = 3;
+        L->aligned = (L->bitCount % 8) == 0;
+    }
+    if (L->bitCount == 0) return false;
+    const unsigned alignBits = 8u * (unsigned)d->pitchAlignment;  // computeBitPitch / computeBytePitch (nvimage.h:11-24)
+    const unsigned bitPitch = (((unsigned)d->width * L->bitCount + alignBits - 1) / alignBits) * alignBits;
+    L->pitch = (bitPitch + 7) / 8;
+    return true;
+}
+}  // namespace
+
+size_t nvttb_pixel_format_level_size(const NvttbPixelFormatDesc *desc) {
+    PixelLayout L;
+    if (!desc || !pixel_layout(desc, &L)) return 0;
+    return (size_t)L.pitch * desc->height;
+}
+
+static int convert_device(NvttbContext *ctx, const NvttbPixelFormatDesc *d, const PixelLayout &L, const float *d_rgba, unsigned char *d_out) {
+    PixelFormatParams P;
+    P.lv.data = d_rgba;
+    P.lv.plane = (size_t)d->width * d->height;
+    P.lv.w = d->width;
+    P.lv.h = d->height;
+    P.lv.bw = (d->width + 3) / 4;
+    P.lv.bh = (d->height + 3) / 4;
+    P.lv.to_gamma_table = nullptr;
+    P.out = d_out;
+    P.pitch = L.pitch;
+    P.bitCount = L.bitCount;
+    P.kind = L.kind;
+    for (int i = 0; i < 4; i++) { P.size[i] = L.size[i]; P.shift[i] = L.shift[i]; }
+    // four pixels per thread when every row start and every 4-pixel group stays 16-byte aligned in both images
+    int mode = 0;
+    const unsigned bytes = L.bitCount / 8;
+    if (L.aligned && L.kind <= 1 && (bytes == 1 || bytes == 2 || bytes == 4)) mode = (int)bytes;
+    else if (L.kind == 2 && L.size[0] == 16 && L.size[1] == 16 && L.size[2] == 16 && L.size[3] == 16) mode = 8;
+    else if (L.kind == 2 && L.size[0] == 32 && L.size[1] == 32 && L.size[2] == 32 && L.size[3] == 32) mode = 16;
+    if (mode && d->width % 4 == 0 && L.pitch == (unsigned)d->width * bytes && ((size_t)d_rgba & 15) == 0 && ((size_t)d_out & 15) == 0 &&
+        (((size_t)d->width * d->height) & 3) == 0) {
+        const dim3 grid(grid_for(d->width / 4, 256), d->height);
+        NVB_LAUNCH(ctx, K_PIXEL_FORMAT, (double)d->width * d->height, k_pixel_format_x4, grid, 256, P, mode);
+    } else if (L.aligned) {
+        const dim3 grid(grid_for(d->width, 256), d->height);
+        NVB_LAUNCH(ctx, K_PIXEL_FORMAT, (double)d->width * d->height, k_pixel_format, grid, 256, P);
+    } else {
+        NVB_LAUNCH(ctx, K_PIXEL_FORMAT, (double)d->width * d->height, k_pixel_format_rows, grid_for(d->height, 64), 64, P);
+    }
+    return NVTTB_OK;
+}
+
+int nvttb_convert_level(NvttbContext *ctx, const NvttbPixelFormatDesc *desc, const float *rgba, int rgba_location, void *out,
+                        int out_location, size_t out_capacity) {
+    if (!ctx || !desc || !rgba || !out) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null argument");
+    PixelLayout L;
+    if (!pixel_layout(desc, &L)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "unsupported pixel format");
+    if (desc->height > 65535) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "level too tall");
+    CK(cudaSetDevice(ctx->device));
+    const int w = desc->width, h = desc->height;
+    const size_t size = (size_t)L.pitch * h;
+    if (out_capacity < size) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
+    int rc;
+    const float *d_rgba = rgba;
+    if (rgba_location == NVTTB_HOST) {
+        const size_t bytes = (size_t)w * h * 4 * sizeof(float);
+        if ((rc = ensure(ctx, ctx->tmp_level, bytes)) != NVTTB_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->tmp_level.p, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_rgba = (const float *)ctx->tmp_level.p;
+    }
+    unsigned char *d_out = (unsigned char *)out;
+    if (out_location == NVTTB_HOST) {
+        if ((rc = ensure(ctx, ctx->out_dev, size)) != NVTTB_OK) return rc;
+        d_out = (unsigned char *)ctx->out_dev.p;
+    }
+    if ((rc = convert_device(ctx, desc, L, d_rgba, d_out)) != NVTTB_OK) return rc;
     if (out_location == NVTTB_HOST) {
         CK(cudaMemcpyAsync(out, d_out, size, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

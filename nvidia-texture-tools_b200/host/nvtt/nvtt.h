@@ -44,7 +44,10 @@ struct CompressionOptions {
     NVTT_API void setFormat(Format format);
     NVTT_API void setQuality(Quality quality);
     NVTT_API void setColorWeights(float red, float green, float blue, float alpha = 1.0f);
+    NVTT_API void setPixelFormat(unsigned int bitcount, unsigned int rmask, unsigned int gmask, unsigned int bmask, unsigned int amask);
+    NVTT_API void setPixelFormat(unsigned char rsize, unsigned char gsize, unsigned char bsize, unsigned char asize);
     NVTT_API void setPixelType(PixelType pixelType);
+    NVTT_API void setPitchAlignment(int pitchAlignment);
     NVTT_API void setQuantization(bool colorDithering, bool alphaDithering, bool binaryAlpha, int alphaThreshold = 127);
     NVTT_API void setRGBMThreshold(float min_m);
     NVTT_API void setTargetDecoder(Decoder decoder);

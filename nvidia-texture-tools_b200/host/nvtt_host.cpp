@@ -98,6 +98,14 @@ struct CompressionOptions::Private {
     bool enableColorDithering, enableAlphaDithering, binaryAlpha;
     int alphaThreshold;
     float rgbmThreshold;
+    // Format_RGB / Format_RGBA (CompressionOptions.h:40-75)
+    unsigned bitcount, rmask, gmask, bmask, amask;
+    unsigned char rsize, gsize, bsize, asize;
+    int pitchAlignment;
+    unsigned getBitCount() const {
+        if (format == Format_RGBA) return bitcount != 0 ? bitcount : (unsigned)rsize + gsize + bsize + asize;
+        return 0;
+    }
 };
 CompressionOptions::CompressionOptions() : m(*new Private()) { reset(); }
 CompressionOptions::~CompressionOptions() { delete &m; }
@@ -110,7 +118,23 @@ void CompressionOptions::reset() {
     m.enableColorDithering = m.enableAlphaDithering = m.binaryAlpha = false;
     m.alphaThreshold = 127;
     m.rgbmThreshold = 0.15f;  // CompressionOptions.cpp:53
+    m.bitcount = 32;
+    m.bmask = 0x000000FF; m.gmask = 0x0000FF00; m.rmask = 0x00FF0000; m.amask = 0xFF000000;
+    m.rsize = m.gsize = m.bsize = m.asize = 8;
+    m.pitchAlignment = 1;
 }
+// CompressionOptions.cpp:113-173
+void CompressionOptions::setPixelFormat(unsigned int bitCount, unsigned int rmask, unsigned int gmask, unsigned int bmask, unsigned int amask) {
+    m.bitcount = bitCount;
+    m.rmask = rmask; m.gmask = gmask; m.bmask = bmask; m.amask = amask;
+    m.rsize = m.gsize = m.bsize = m.asize = 0;
+}
+void CompressionOptions::setPixelFormat(unsigned char rsize, unsigned char gsize, unsigned char bsize, unsigned char asize) {
+    m.bitcount = 0;
+    m.rmask = m.gmask = m.bmask = m.amask = 0;
+    m.rsize = rsize; m.gsize = gsize; m.bsize = bsize; m.asize = asize;
+}
+void CompressionOptions::setPitchAlignment(int pitchAlignment) { m.pitchAlignment = pitchAlignment; }
 void CompressionOptions::setRGBMThreshold(float min_m) { m.rgbmThreshold = min_m; }
 void CompressionOptions::setFormat(Format f) { m.format = f; }
 void CompressionOptions::setQuality(Quality q) { m.quality = q; }
@@ -457,7 +481,37 @@ void fill_encode(NvttbEncodeDesc *e, const CompressionOptions::Private &co, Alph
     e->applyToGamma = 0;
     e->rgbmThreshold = co.rgbmThreshold;
 }
-int image_size(int w, int h, int d, Format f) { return ((w + 3) / 4) * ((h + 3) / 4) * blockSize(f) * d; }
+void fill_pixel_format(NvttbPixelFormatDesc *p, const CompressionOptions::Private &co, int w, int h) {
+    p->pixelType = co.pixelType;
+    p->bitcount = co.bitcount;
+    p->rmask = co.rmask; p->gmask = co.gmask; p->bmask = co.bmask; p->amask = co.amask;
+    p->rsize = co.rsize; p->gsize = co.gsize; p->bsize = co.bsize; p->asize = co.asize;
+    p->pitchAlignment = co.pitchAlignment;
+    p->width = w;
+    p->height = h;
+}
+unsigned byte_pitch(unsigned w, unsigned bitsize, unsigned alignmentInBytes) {  // nv::computeBytePitch (nvimage.h:11-24)
+    const unsigned a = 8 * alignmentInBytes;
+    return (((w * bitsize + a - 1) / a) * a + 7) / 8;
+}
+// nv::computeImageSize (Surface.cpp:210-218)
+int image_size(int w, int h, int d, const CompressionOptions::Private &co) {
+    if (co.format == Format_RGBA) return d * h * (int)byte_pitch(w, co.getBitCount(), co.pitchAlignment);
+    return ((w + 3) / 4) * ((h + 3) / 4) * blockSize(co.format) * d;
+}
+// findDXGIFormat (src/nvimage/DirectDrawSurface.cpp:483-546): the mask layouts that have a DXGI equivalent
+uint32_t find_dxgi_format(unsigned bitcount, unsigned r, unsigned g, unsigned b, unsigned a) {
+    static const struct { uint32_t dxgi, bits, r, g, b, a; } t[] = {
+        {87, 32, 0xFF0000, 0xFF00, 0xFF, 0xFF000000}, {88, 32, 0xFF0000, 0xFF00, 0xFF, 0},  {85, 16, 0xF800, 0x7E0, 0x1F, 0},
+        {86, 16, 0x7C00, 0x3E0, 0x1F, 0x8000},        {65, 8, 0, 0, 0, 8},                  {24, 32, 0x3FF, 0xFFC00, 0x3FF00000, 0xC0000000},
+        {28, 32, 0xFF, 0xFF00, 0xFF0000, 0xFF000000}, {35, 32, 0xFFFF, 0xFFFF0000, 0, 0},   {61, 8, 0xFF, 0, 0, 0},
+        {56, 16, 0xFFFF, 0, 0, 0},                    {49, 16, 0xFF, 0xFF00, 0, 0},
+    };
+    // (the reference's table also lists layouts without a DXGI code; they resolve to DXGI_FORMAT_UNKNOWN = unsupported, like no match)
+    for (const auto &e : t)
+        if (e.bits == bitcount && e.r == r && e.g == g && e.b == b && e.a == a) return e.dxgi;
+    return 0;
+}
 
 struct DDSHeaderBytes {  // nvimage/DirectDrawSurface.h:283-430 layout, little endian
     uint32_t fourcc, size, flags, height, width, pitch, depth, mipmapcount, reserved[11];
@@ -522,7 +576,7 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
         else if (f == Format_BC5) { kh.glInternalFormat = 0x8DBD; kh.glBaseInternalFormat = 0x8227; }
         else if (f == Format_BC6) { kh.glInternalFormat = (co.pixelType == PixelType_Float) ? 0x8E8E : 0x8E8F; kh.glBaseInternalFormat = 0x1907; }
         else if (f == Format_BC7) { kh.glInternalFormat = oo.srgb ? 0x8E8D : 0x8E8C; kh.glBaseInternalFormat = 0x1908; }
-        else supported = false;  // RGBA / ETC / PVR: out of scope of this library
+        else supported = false;  // ETC / PVR: out of scope of this library; RGBA in a KTX container: not implemented
         if (!supported) {
             oo.error(Error_UnsupportedOutputFormat);
             return false;
@@ -562,7 +616,19 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
     if (oo.container == Container_DDS10) {
         hd.pf_flags = 0x4;
         hd.pf_fourcc = fourcc('D', 'X', '1', '0');
-        if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) {
+        if (f == Format_RGBA) {  // Context.cpp:649-682
+            const unsigned bitcount = co.getBitCount();
+            if (co.pixelType == PixelType_Float) {
+                if (co.rsize == 16 && co.gsize == 16 && co.bsize == 16 && co.asize == 16) hd.dxgiFormat = 10;  // R16G16B16A16_FLOAT
+                else if (co.rsize == 11 && co.gsize == 11 && co.bsize == 10 && co.asize == 0) hd.dxgiFormat = 26;  // R11G11B10_FLOAT
+                else supported = false;
+            } else if (bitcount == 16 && co.rsize == 16) {
+                hd.dxgiFormat = 56;  // R16_UNORM
+            } else {
+                hd.dxgiFormat = find_dxgi_format(co.bitcount, co.rmask, co.gmask, co.bmask, co.amask);
+                if (hd.dxgiFormat == 0) supported = false;
+            }
+        } else if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) {
             hd.dxgiFormat = oo.srgb ? 72 : 71;
             if (f == Format_DXT1a) hd.pf_flags |= 0x1;
             if (isNormalMap) hd.pf_flags |= 0x80000000u;
@@ -577,9 +643,51 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
     } else {
         hd.flags &= ~0x8u;
         hd.flags |= 0x80000;  // LINEARSIZE
-        hd.pitch = (uint32_t)image_size(w, h, d, f);
+        hd.pitch = (uint32_t)image_size(w, h, d, co);
         hd.pf_flags = 0x4;
-        if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) { hd.pf_fourcc = fourcc('D', 'X', 'T', '1'); if (isNormalMap) hd.pf_flags |= 0x80000000u; }
+        if (f == Format_RGBA) {  // Context.cpp:726-793
+            hd.flags &= ~0x80000u;
+            hd.flags |= 0x8;  // PITCH
+            hd.pitch = byte_pitch(w, co.getBitCount(), co.pitchAlignment);
+            if (co.pixelType == PixelType_Float) {
+                const int rs = co.rsize, gs = co.gsize, bs = co.bsize, as = co.asize;
+                if (rs == 16 && gs == 0 && bs == 0 && as == 0) hd.pf_fourcc = 111;        // D3DFMT_R16F
+                else if (rs == 16 && gs == 16 && bs == 0 && as == 0) hd.pf_fourcc = 112;  // D3DFMT_G16R16F
+                else if (rs == 16 && gs == 16 && bs == 16 && as == 16) hd.pf_fourcc = 113;
+                else if (rs == 32 && gs == 0 && bs == 0 && as == 0) hd.pf_fourcc = 114;
+                else if (rs == 32 && gs == 32 && bs == 0 && as == 0) hd.pf_fourcc = 115;
+                else if (rs == 32 && gs == 32 && bs == 32 && as == 32) hd.pf_fourcc = 116;
+                else supported = false;
+            } else {
+                unsigned bitcount = co.getBitCount(), rmask = co.rmask, gmask = co.gmask, bmask = co.bmask, amask = co.amask;
+                if (co.bitcount == 0 && bitcount <= 32) {
+                    const unsigned ashift = 0, bshift = ashift + co.asize, gshift = bshift + co.bsize, rshift = gshift + co.gsize;
+                    rmask = ((1u << co.rsize) - 1) << rshift;
+                    gmask = ((1u << co.gsize) - 1) << gshift;
+                    bmask = ((1u << co.bsize) - 1) << bshift;
+                    amask = ((1u << co.asize) - 1) << ashift;
+                } else if (co.bitcount == 0) {
+                    supported = false;
+                }
+                if (supported) {  // DDSHeader::setPixelFormat (DirectDrawSurface.cpp:730-783)
+                    hd.pf_flags = 0;
+                    if (rmask != 0 || gmask != 0 || bmask != 0) {
+                        hd.pf_flags = (gmask == 0 && bmask == 0) ? 0x20000u : 0x40u;  // LUMINANCE : RGB
+                        if (amask != 0) hd.pf_flags |= 0x1;                            // ALPHAPIXELS
+                    } else if (amask != 0) {
+                        hd.pf_flags |= 0x2;  // ALPHA
+                    }
+                    if (bitcount == 0) {
+                        unsigned total = rmask | gmask | bmask | amask;
+                        while (total != 0) { bitcount++; total >>= 1; }
+                    }
+                    hd.pf_fourcc = 0;
+                    hd.pf_bitcount = bitcount;
+                    hd.pf_rmask = rmask; hd.pf_gmask = gmask; hd.pf_bmask = bmask; hd.pf_amask = amask;
+                }
+            }
+        }
+        else if (f == Format_DXT1 || f == Format_DXT1a || f == Format_DXT1n) { hd.pf_fourcc = fourcc('D', 'X', 'T', '1'); if (isNormalMap) hd.pf_flags |= 0x80000000u; }
         else if (f == Format_DXT3) hd.pf_fourcc = fourcc('D', 'X', 'T', '3');
         else if (f == Format_DXT5 || f == Format_BC3_RGBM) hd.pf_fourcc = fourcc('D', 'X', 'T', '5');
         else if (f == Format_DXT5n) { hd.pf_fourcc = fourcc('D', 'X', 'T', '5'); if (isNormalMap) { hd.pf_flags |= 0x80000000u; hd.pf_bitcount = fourcc('A', '2', 'D', '5'); } }
@@ -605,7 +713,7 @@ bool Compressor::outputHeader(const Surface &img, int mipmapCount, const Compres
 int Compressor::estimateSize(int w, int h, int d, int mipmapCount, const CompressionOptions &co) const {
     int size = 0;
     for (int i = 0; i < mipmapCount; i++) {
-        size += image_size(w, h, d, co.m.format);
+        size += image_size(w, h, d, co.m);
         w = imax(1, w / 2); h = imax(1, h / 2); d = imax(1, d / 2);
     }
     return size;
@@ -627,13 +735,26 @@ int Compressor::estimateSize(const InputOptions &io, const CompressionOptions &c
 // Compressor::Private::compress(AlphaMode,w,h,d,face,mip,rgba,...)  (Context.cpp:486-516)
 static bool compress_level(const Compressor::Private &m, AlphaMode am, int w, int h, int d, int face, int mip, const float *rgba, int loc,
                            const CompressionOptions::Private &co, const OutputOptions::Private &oo) {
-    const int size = image_size(w, h, d, co.format);
+    const int size = image_size(w, h, d, co);
     if (oo.outputHandler) oo.outputHandler->beginImage(size, w, h, d, face, mip);
     bool ok = true;
     NvttbContext *ctx = g_gpu.get();
     if (!ctx || !m.cudaEnabled) {
         oo.error(Error_CudaError);
         ok = false;
+    } else if (d == 1 && co.format == Format_RGBA) {
+        NvttbPixelFormatDesc p;
+        fill_pixel_format(&p, co, w, h);
+        std::vector<unsigned char> out((size_t)size);
+        const int rc = (size > 0 && (size_t)size == nvttb_pixel_format_level_size(&p))
+                           ? nvttb_convert_level(ctx, &p, rgba, loc, out.data(), NVTTB_HOST, out.size())
+                           : NVTTB_ERR_UNSUPPORTED_FEATURE;
+        if (rc != NVTTB_OK) {
+            oo.error((Error)(rc - 1));
+            ok = false;
+        } else {
+            oo.writeData(out.data(), size);
+        }
     } else if (d != 1 || !nvttb_format_supported(co.format, co.quality)) {
         oo.error(Error_UnsupportedFeature);  // reference: signals the error and still returns true (Context.cpp:504-515)
     } else {
@@ -667,6 +788,12 @@ static void quantize_surface(Surface &img, const CompressionOptions::Private &co
         img.quantize(1, 6, true, true);
         img.quantize(2, 5, true, true);
     }
+    if (co.enableColorDithering && co.format == Format_RGB) {
+        img.quantize(0, co.rsize, true, true);
+        img.quantize(1, co.gsize, true, true);
+        img.quantize(2, co.bsize, true, true);
+    }
+    if (co.enableAlphaDithering && co.format == Format_RGB) img.quantize(3, co.asize, true, true);
     if (!co.enableAlphaDithering && co.binaryAlpha) img.binarize(3, float(co.alphaThreshold) / 255.0f, co.enableAlphaDithering);
 }
 
@@ -699,10 +826,11 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
     // Compressor::Private::quantize (Context.cpp:519-541): colour dithering acts on BC1..BC3 (5/6/5 bits, Floyd-Steinberg);
     // alpha dithering only on Format_RGB, i.e. never here; binary alpha = non-dithered binarize, and only when alpha dithering
     // is off (so nvcompress's settings for -bc1a / -bc2 are both no-ops, as in the reference).
-    const bool colorDither = co.enableColorDithering && co.format >= Format_BC1 && co.format <= Format_BC3;
+    const bool isRGB = co.format == Format_RGB;
+    const bool colorDither = co.enableColorDithering && ((co.format >= Format_BC1 && co.format <= Format_BC3) || isRGB);
     const bool binarizeAlpha = !co.enableAlphaDithering && co.binaryAlpha;
-    const bool quantizeStep = colorDither || binarizeAlpha;
-    if (depth != 1 || !nvttb_format_supported(co.format, co.quality)) {
+    const bool quantizeStep = colorDither || binarizeAlpha || (isRGB && co.enableAlphaDithering);
+    if (depth != 1 || !(isRGB || nvttb_format_supported(co.format, co.quality))) {
         oo.error(Error_UnsupportedFeature);
         return false;
     }
@@ -773,7 +901,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         return true;
     }
 
-    if (canUseSourceImages && !userMips && !quantizeStep) {
+    if (canUseSourceImages && !userMips && !quantizeStep && !isRGB) {
         // fused device pipeline
         NvttbProcessDesc d;
         memset(&d, 0, sizeof d);

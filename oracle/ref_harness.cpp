@@ -117,6 +117,12 @@ struct RefProcessDesc {
     int threads;         // 0 default pool, 1 sequential
     int quantization;    // CompressionOptions::setQuantization: bit 0 colour dithering, bit 1 alpha dithering, bit 2 binary alpha
     int alphaThreshold;  // 0..255 (127 = the default)
+    // Format_RGB / Format_RGBA only.  pixelFormatMode: 0 = CompressionOptions defaults, 1 = setPixelFormat(bitcount, masks),
+    // 2 = setPixelFormat(rsize, gsize, bsize, asize); pitchAlignment 0 = leave the default (1)
+    int pixelFormatMode;
+    unsigned bitcount, rmask, gmask, bmask, amask;
+    int rsize, gsize, bsize, asize;
+    int pitchAlignment;
 };
 
 // Whole InputOptions pipeline: Compressor::process (src/nvtt/Context.cpp:117-120,217-346).
@@ -138,6 +144,9 @@ long ref_process(const RefProcessDesc *d, const void *const *images, unsigned ch
     CompressionOptions co;
     setup_co(co, d->format, d->quality, d->colorWeights, d->pixelType);
     if (d->quantization) co.setQuantization((d->quantization & 1) != 0, (d->quantization & 2) != 0, (d->quantization & 4) != 0, d->alphaThreshold);
+    if (d->pixelFormatMode == 1) co.setPixelFormat(d->bitcount, d->rmask, d->gmask, d->bmask, d->amask);
+    else if (d->pixelFormatMode == 2) co.setPixelFormat((unsigned char)d->rsize, (unsigned char)d->gsize, (unsigned char)d->bsize, (unsigned char)d->asize);
+    if (d->pitchAlignment > 0) co.setPitchAlignment(d->pitchAlignment);
     OutputOptions oo;
     MemHandler mh;
     ErrCount eh;

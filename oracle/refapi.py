@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 # nvtt enums (src/nvtt/nvtt.h:80-277)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
+Format_RGBA = Format_RGB
 Format_DXT1n, Format_CTX1, Format_BC6, Format_BC7, Format_BC3_RGBM = 8, 9, 10, 11, 12
 Format_BC1, Format_BC2, Format_BC3, Format_BC3n = Format_DXT1, Format_DXT3, Format_DXT5, Format_DXT5n
 Quality_Fastest, Quality_Normal, Quality_Production, Quality_Highest = range(4)
@@ -37,6 +38,10 @@ class RefProcessDesc(C.Structure):
         ("colorWeights", C.c_float * 4),
         ("outputHeader", C.c_int), ("container", C.c_int), ("threads", C.c_int),
         ("quantization", C.c_int), ("alphaThreshold", C.c_int),
+        ("pixelFormatMode", C.c_int),
+        ("bitcount", C.c_uint), ("rmask", C.c_uint), ("gmask", C.c_uint), ("bmask", C.c_uint), ("amask", C.c_uint),
+        ("rsize", C.c_int), ("gsize", C.c_int), ("bsize", C.c_int), ("asize", C.c_int),
+        ("pitchAlignment", C.c_int),
     ]
 
 
@@ -116,9 +121,12 @@ def process(images, input_format, w, h, fmt, quality, *, wrap=WrapMode_Mirror, m
             mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
             to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
             pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), header=False, container=Container_DDS,
-            texture_type=TextureType_2D, threads=0, fast=False, quantization=0, alpha_threshold=127):
-    """Whole Compressor::process pipeline on the reference; images = list of per-face level-0 arrays."""
+            texture_type=TextureType_2D, threads=0, fast=False, quantization=0, alpha_threshold=127,
+            pixel_masks=None, pixel_sizes=None, pitch_alignment=0):
+    """Whole Compressor::process pipeline on the reference; images = list of per-face level-0 arrays.
+    pixel_masks = (bitcount, rmask, gmask, bmask, amask) or pixel_sizes = (r, g, b, a) select the Format_RGBA layout."""
     d = RefProcessDesc()
+    set_pixel_format(d, pixel_masks, pixel_sizes, pitch_alignment)
     d.quantization, d.alphaThreshold = quantization, alpha_threshold
     d.inputFormat, d.textureType, d.width, d.height, d.faces = input_format, texture_type, w, h, len(images)
     d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
@@ -139,6 +147,17 @@ def process(images, input_format, w, h, fmt, quality, *, wrap=WrapMode_Mirror, m
     if r != n:
         raise RuntimeError("ref_process failed on second pass")
     return out
+
+
+def set_pixel_format(d, pixel_masks=None, pixel_sizes=None, pitch_alignment=0):
+    d.pixelFormatMode = 0
+    if pixel_masks is not None:
+        d.pixelFormatMode = 1
+        d.bitcount, d.rmask, d.gmask, d.bmask, d.amask = pixel_masks
+    elif pixel_sizes is not None:
+        d.pixelFormatMode = 2
+        d.rsize, d.gsize, d.bsize, d.asize = pixel_sizes
+    d.pitchAlignment = pitch_alignment
 
 
 class Surface:

@@ -49,7 +49,9 @@ def _process(L, ref, images, fmt, quality, w, h, **kw):
     d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = 3.0, 4.0, 1.0
     d.inputGamma, d.outputGamma = 2.2, 2.2
     d.isNormalMap, d.convertToNormalMap, d.normalizeMipmaps = int(kw.get("normal_map", False)), 0, 1
-    d.alphaMode, d.format, d.quality, d.pixelType = kw.get("alpha_mode", 0), fmt, quality, 0
+    d.alphaMode, d.format, d.quality, d.pixelType = kw.get("alpha_mode", 0), fmt, quality, kw.get("pixel_type", 0)
+    d.inputFormat = kw.get("input_format", 0)
+    ref.set_pixel_format(d, kw.get("pixel_masks"), kw.get("pixel_sizes"), kw.get("pitch_alignment", 0))
     d.colorWeights = (C.c_float * 4)(1, 1, 1, 1)
     d.outputHeader, d.container, d.threads = int(kw.get("header", True)), kw.get("container", 0), 0
     d.quantization, d.alphaThreshold = kw.get("quantization", 0), kw.get("alpha_threshold", 127)
@@ -162,3 +164,58 @@ def test_raw_compress_and_surface_api_identical(nvtt, ref, ours):
     assert len(outs[0]) == len(outs[1]) == 6
     for a, b in zip(*outs):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_rgba_pixel_formats_identical(nvtt, ref, ours):
+    """Format_RGBA (PixelFormatConverter, CompressorRGB.cpp:410-575) through Compressor::process: default BGRA8, mask and size
+    layouts, luminance, 16-bit, 24-bit with 4-byte pitch alignment, half / float / 11-11-10 float channels, UnsignedInt,
+    the zero-filled signed types, odd widths; DDS header included."""
+    s = nvtt.synth
+    w, h = 37, 22
+    img = s.photo_bgra8(w, h, seed=21, alpha=True)
+    cases = [
+        dict(),
+        dict(pixel_masks=(32, 0xFF, 0xFF00, 0xFF0000, 0xFF000000)),
+        dict(pixel_masks=(24, 0xFF0000, 0xFF00, 0xFF, 0), pitch_alignment=4),
+        dict(pixel_masks=(16, 0xF800, 0x7E0, 0x1F, 0)),
+        dict(pixel_masks=(16, 0x7C00, 0x3E0, 0x1F, 0x8000), pitch_alignment=8),
+        dict(pixel_masks=(8, 0xFF, 0, 0, 0)),
+        dict(pixel_masks=(8, 0, 0, 0, 0xFF)),
+        dict(pixel_masks=(32, 0x3FF00000, 0xFFC00, 0x3FF, 0xC0000000)),
+        dict(pixel_masks=(12, 0xF00, 0xF0, 0xF, 0)),
+        dict(pixel_sizes=(5, 6, 5, 0)),
+        dict(pixel_sizes=(8, 8, 8, 8)),
+        dict(pixel_sizes=(10, 10, 10, 2)),
+        dict(pixel_sizes=(16, 0, 0, 0)),
+        dict(pixel_sizes=(3, 3, 2, 0), quantization=1),
+        dict(pixel_sizes=(4, 4, 4, 4), quantization=3),
+        dict(pixel_sizes=(8, 8, 8, 8), pixel_type=2),
+        dict(pixel_sizes=(8, 8, 8, 8), pixel_type=1),
+        dict(pixel_sizes=(16, 16, 16, 16), pixel_type=4),
+        dict(pixel_sizes=(32, 32, 32, 32), pixel_type=4),
+        dict(pixel_sizes=(16, 16, 0, 0), pixel_type=4),
+        dict(pixel_sizes=(32, 0, 0, 0), pixel_type=4, pitch_alignment=4),
+        dict(pixel_sizes=(11, 11, 10, 0), pixel_type=4, header=False),
+    ]
+    for kw in cases:
+        kw = dict(kw)
+        kw.setdefault("header", True)
+        got = _process(ours, ref, [img], ref.Format_RGBA, 1, w, h, mip_filter=0, **kw)
+        want = _process(ref.lib(), ref, [img], ref.Format_RGBA, 1, w, h, mip_filter=0, **kw)
+        assert got.size == want.size, kw
+        assert np.array_equal(got, want), (kw, int(np.flatnonzero(got != want)[0]))
+    # widths that are a multiple of four take the four-pixels-per-thread kernel
+    img4 = s.photo_bgra8(64, 24, seed=22, alpha=True)
+    for kw in (dict(), dict(pixel_masks=(16, 0xF800, 0x7E0, 0x1F, 0)), dict(pixel_masks=(8, 0xFF, 0, 0, 0)), dict(pixel_sizes=(10, 10, 10, 2)),
+               dict(pixel_sizes=(16, 16, 16, 16), pixel_type=4), dict(pixel_sizes=(32, 32, 32, 32), pixel_type=4),
+               dict(pixel_masks=(24, 0xFF0000, 0xFF00, 0xFF, 0)), dict(pixel_sizes=(8, 8, 8, 8), pitch_alignment=8)):
+        got = _process(ours, ref, [img4], ref.Format_RGBA, 1, 64, 24, mip_filter=0, **kw)
+        want = _process(ref.lib(), ref, [img4], ref.Format_RGBA, 1, 64, 24, mip_filter=0, **kw)
+        assert np.array_equal(got, want), kw
+    # HDR input through the float layouts, DX10 container
+    hdr = s.hdr_rgba16f(24, 16, seed=5).view("uint16")
+    for kw in (dict(pixel_sizes=(16, 16, 16, 16), pixel_type=4, container=1), dict(pixel_sizes=(11, 11, 10, 0), pixel_type=4, container=1),
+               dict(pixel_sizes=(32, 32, 32, 32), pixel_type=4)):
+        got = _process(ours, ref, [hdr], ref.Format_RGBA, 1, 24, 16, mip_filter=0, input_format=1, **kw)
+        want = _process(ref.lib(), ref, [hdr], ref.Format_RGBA, 1, 24, 16, mip_filter=0, input_format=1, **kw)
+        assert np.array_equal(got, want), kw
