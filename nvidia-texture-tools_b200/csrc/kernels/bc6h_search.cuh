@@ -172,7 +172,7 @@ template <int NIDX> NVB_DEV float zs_eval(const float4 *px, int np, int a0, int 
             for (int j = 0; j < NIDX; ++j)
                 pal[ch][j] = (float)zoh_finish_unquantize((ua[ch] * avpcl_wc(NIDX, NIDX - 1 - j) + ub[ch] * avpcl_wc(NIDX, j) + 32) >> 6, sgn);
     }
-    // two palette entries per FADD2 / FMUL2; the sum of the squares stays scalar (see bx_eval in bc7_search.cuh)
+    // two palette entries per FADD2 / FMUL2; the sum of the squares is the unfused FFMA2-by-one add (see bx_eval in bc7_search.cuh)
     float2 npal[3][NIDX / 2];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++)
@@ -188,7 +188,7 @@ template <int NIDX> NVB_DEV float zs_eval(const float4 *px, int np, int a0, int 
         for (int jp = 0; jp < NIDX / 2; ++jp) {
             const float2 x = f2add(cx, npal[0][jp]), y = f2add(cy, npal[1][jp]), z = f2add(cz, npal[2][jp]);
             const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
-            const float2 n = make_float2(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y));
+            const float2 n = f2add_s(f2add_s(xx, yy), zz);
             const float2 e2 = f2mul(n, imp);
 #pragma unroll
             for (int h = 0; h < 2; h++) {

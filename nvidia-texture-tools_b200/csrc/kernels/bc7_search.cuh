@@ -112,8 +112,8 @@ template <int M> NVB_DEV float bx_eval(const float4 *px, int np, unsigned A, uns
         bx_lerp_row<N>(a, b, pal[ch], 1);
     }
     // Two palette entries per instruction: the differences and squares issue as FADD2 / FMUL2 (c - p == c + (-p) exactly);
-    // the sums that consume the squares stay scalar (ptxas would contract a packed add of a packed product into FFMA2,
-    // nvb_common.cuh), in the reference's order ((x^2 + y^2) + z^2) + w^2.
+    // the sums that consume the squares are the unfused FFMA2-by-one adds of nvb_common.cuh (a plain packed add of a packed
+    // product would be contracted by ptxas), in the reference's order ((x^2 + y^2) + z^2) + w^2.
     float2 npal[C::NCH][N / 2];
 #pragma unroll
     for (int ch = 0; ch < C::NCH; ch++)
@@ -134,13 +134,15 @@ template <int M> NVB_DEV float bx_eval(const float4 *px, int np, unsigned A, uns
             const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
             float e0, e1;
             if (C::NCH == 3) {
-                e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), ww);
-                e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), ww);
+                const float2 e = f2add_s(f2add_s(f2add_s(xx, yy), zz), f2splat(ww));
+                e0 = e.x;
+                e1 = e.y;
             } else {
                 const float2 w = f2add(cw, npal[C::NCH - 1][jp]);
                 const float2 w2 = f2mul(w, w);
-                e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), w2.x);
-                e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), w2.y);
+                const float2 e = f2add_s(f2add_s(f2add_s(xx, yy), zz), w2);
+                e0 = e.x;
+                e1 = e.y;
             }
             if (jp == 0) best = e0;
             else NVB_BX_SCAN_STEP(e0, 2 * jp)
@@ -201,14 +203,16 @@ template <int M> NVB_DEV void bx_eval2(const float4 *px, int np, unsigned A0, un
                 const float2 xx = f2mul(x, x), yy = f2mul(y, y), zz = f2mul(z, z);
                 float e0, e1;
                 if (C::NCH == 3) {
-                    e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), ww);
-                    e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), ww);
+                    const float2 e = f2add_s(f2add_s(f2add_s(xx, yy), zz), f2splat(ww));
+                    e0 = e.x;
+                    e1 = e.y;
                 } else {
                     const float2 p3 = t ? np1[C::NCH - 1][jp] : np0[C::NCH - 1][jp];
                     const float2 w = f2add(cw, p3);
                     const float2 w2 = f2mul(w, w);
-                    e0 = __fadd_rn(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), w2.x);
-                    e1 = __fadd_rn(__fadd_rn(__fadd_rn(xx.y, yy.y), zz.y), w2.y);
+                    const float2 e = f2add_s(f2add_s(f2add_s(xx, yy), zz), w2);
+                    e0 = e.x;
+                    e1 = e.y;
                 }
                 if (jp == 0) best = e0;
                 else NVB_BX_SCAN_STEP(e0, 2 * jp)
