@@ -62,17 +62,14 @@ NVB_DEV void pf_put_raw(PfStream &s, unsigned v, int nbytes) {  // putFloat / pu
 }
 
 NVB_DEV unsigned pf_to_float11(float f) {
-    if (f < 0) f = 0;
-    if (f > 65024) f = 65024;
-    const unsigned u = __float_as_uint(f);
+    // the clamps select BITS: a float min/max would replace a NaN's payload by the canonical one, the reference's compares keep it
+    const unsigned u = (f < 0.0f) ? 0u : (f > 65024.0f) ? 0x477E0000u : __float_as_uint(f);
     const unsigned E = ((u >> 23) & 0xFF) - 127 + 15;
     const unsigned M = (u & 0x7FFFFF) >> (23 - 6);
     return (E << 6) | M;
 }
 NVB_DEV unsigned pf_to_float10(float f) {
-    if (f < 0) f = 0;
-    if (f > 64512) f = 64512;
-    const unsigned u = __float_as_uint(f);
+    const unsigned u = (f < 0.0f) ? 0u : (f > 64512.0f) ? 0x477C0000u : __float_as_uint(f);
     const unsigned E = ((u >> 23) & 0xFF) - 127 + 15;
     const unsigned M = (u & 0x7FFFFF) >> (23 - 5);
     return (E << 5) | M;

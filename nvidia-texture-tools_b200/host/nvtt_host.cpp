@@ -499,6 +499,13 @@ int image_size(int w, int h, int d, const CompressionOptions::Private &co) {
     if (co.format == Format_RGBA) return d * h * (int)byte_pitch(w, co.getBitCount(), co.pitchAlignment);
     return ((w + 3) / 4) * ((h + 3) / 4) * blockSize(co.format) * d;
 }
+// Compressor::Private::estimateSize for one level (Context.cpp:1225-1245), the KTX imageSize field: unlike the public
+// estimateSize it reads `bitcount` directly, so a Format_RGBA layout given as channel sizes (bitcount == 0) reports 0 bytes
+// (and gets no mip padding).  Kept.
+int ktx_level_size(int w, int h, const CompressionOptions::Private &co) {
+    if (co.format == Format_RGBA) return h * (int)byte_pitch(w, co.bitcount, co.pitchAlignment);
+    return image_size(w, h, 1, co);
+}
 // findDXGIFormat (src/nvimage/DirectDrawSurface.cpp:483-546): the mask layouts that have a DXGI equivalent
 uint32_t find_dxgi_format(unsigned bitcount, unsigned r, unsigned g, unsigned b, unsigned a) {
     static const struct { uint32_t dxgi, bits, r, g, b, a; } t[] = {
@@ -568,7 +575,28 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
         kh.numberOfMipmapLevels = mipmapCount;
         const Format f = co.format;
         bool supported = true;
-        if (f == Format_DXT1 || f == Format_DXT1n) { kh.glInternalFormat = oo.srgb ? 0x8C4C : 0x83F0; kh.glBaseInternalFormat = 0x1907; }
+        if (f == Format_RGBA) {  // Context.cpp:904-951
+            const unsigned bitcount = co.getBitCount();
+            auto gl = [&](uint32_t type, uint32_t typeSize, uint32_t format, uint32_t internal) {
+                kh.glType = type; kh.glTypeSize = typeSize; kh.glFormat = format; kh.glInternalFormat = internal; kh.glBaseInternalFormat = format;
+            };
+            if (co.pixelType == PixelType_Float) {
+                if (co.rsize == 16 && co.gsize == 16 && co.bsize == 16 && co.asize == 16) gl(0x140B, 2, 0x1908, 0x881A);      // half, RGBA16F
+                else if (co.rsize == 11 && co.gsize == 11 && co.bsize == 10 && co.asize == 0) gl(0x8C3B, 4, 0x1907, 0x8C3A);  // R11F_G11F_B10F
+                else supported = false;
+            } else if (bitcount == 16 && co.rsize == 16) {
+                gl(0x1403, 2, 0x1903, 0x822A);  // unsigned short, R16
+            } else if (co.bitcount == 24 && co.rmask == 0xFF0000 && co.gmask == 0xFF00 && co.bmask == 0xFF && co.amask == 0) {
+                gl(0x1401, 1, 0x80E0, 0x8051);  // BGR, RGB8
+            } else if (co.bitcount == 32 && co.rmask == 0xFF0000 && co.gmask == 0xFF00 && co.bmask == 0xFF && co.amask == 0xFF000000) {
+                gl(0x1401, 1, 0x80E1, 0x8058);  // BGRA, RGBA8
+            } else if (co.bitcount == 32 && co.rmask == 0xFF && co.gmask == 0xFF00 && co.bmask == 0xFF0000 && co.amask == 0xFF000000) {
+                gl(0x1401, 1, 0x1908, 0x8058);  // RGBA, RGBA8
+            } else {
+                supported = false;
+            }
+        }
+        else if (f == Format_DXT1 || f == Format_DXT1n) { kh.glInternalFormat = oo.srgb ? 0x8C4C : 0x83F0; kh.glBaseInternalFormat = 0x1907; }
         else if (f == Format_DXT1a) { kh.glInternalFormat = oo.srgb ? 0x8C4D : 0x83F1; kh.glBaseInternalFormat = 0x1908; }
         else if (f == Format_DXT3) { kh.glInternalFormat = oo.srgb ? 0x8C4E : 0x83F2; kh.glBaseInternalFormat = 0x1908; }
         else if (f == Format_DXT5 || f == Format_DXT5n || f == Format_BC3_RGBM) { kh.glInternalFormat = oo.srgb ? 0x8C4F : 0x83F3; kh.glBaseInternalFormat = 0x1908; }
@@ -576,7 +604,7 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
         else if (f == Format_BC5) { kh.glInternalFormat = 0x8DBD; kh.glBaseInternalFormat = 0x8227; }
         else if (f == Format_BC6) { kh.glInternalFormat = (co.pixelType == PixelType_Float) ? 0x8E8E : 0x8E8F; kh.glBaseInternalFormat = 0x1907; }
         else if (f == Format_BC7) { kh.glInternalFormat = oo.srgb ? 0x8E8D : 0x8E8C; kh.glBaseInternalFormat = 0x1908; }
-        else supported = false;  // ETC / PVR: out of scope of this library; RGBA in a KTX container: not implemented
+        else supported = false;  // ETC / PVR: out of scope of this library
         if (!supported) {
             oo.error(Error_UnsupportedOutputFormat);
             return false;
@@ -662,10 +690,11 @@ bool Compressor::outputHeader(TextureType textureType, int w, int h, int d, int 
                 unsigned bitcount = co.getBitCount(), rmask = co.rmask, gmask = co.gmask, bmask = co.bmask, amask = co.amask;
                 if (co.bitcount == 0 && bitcount <= 32) {
                     const unsigned ashift = 0, bshift = ashift + co.asize, gshift = bshift + co.bsize, rshift = gshift + co.gsize;
-                    rmask = ((1u << co.rsize) - 1) << rshift;
-                    gmask = ((1u << co.gsize) - 1) << gshift;
-                    bmask = ((1u << co.bsize) - 1) << bshift;
-                    amask = ((1u << co.asize) - 1) << ashift;
+                    // the reference shifts ints by up to 32 here; x86 takes the count modulo 32, made explicit
+                    rmask = ((1u << (co.rsize & 31)) - 1) << (rshift & 31);
+                    gmask = ((1u << (co.gsize & 31)) - 1) << (gshift & 31);
+                    bmask = ((1u << (co.bsize & 31)) - 1) << (bshift & 31);
+                    amask = ((1u << (co.asize & 31)) - 1) << (ashift & 31);
                 } else if (co.bitcount == 0) {
                     supported = false;
                 }
@@ -845,7 +874,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         // are renormalised without the expand / pack pair of the DDS loop.
         std::vector<Surface> images;
         int w = width, h = height;
-        uint32_t imageSize = (uint32_t)estimateSize(w, h, 1, 1, compressionOptions) * faceCount;
+        uint32_t imageSize = (uint32_t)ktx_level_size(w, h, co) * faceCount;
         oo.writeData(&imageSize, 4);
         for (int f = 0; f < faceCount; f++) {
             Surface s;
@@ -869,7 +898,7 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         for (int mip = 1; mip < mipmapCount; mip++) {
             w = imax(1, w / 2);
             h = imax(1, h / 2);
-            imageSize = (uint32_t)estimateSize(w, h, 1, 1, compressionOptions) * faceCount;
+            imageSize = (uint32_t)ktx_level_size(w, h, co) * faceCount;
             oo.writeData(&imageSize, 4);
             for (int f = 0; f < faceCount; f++) {
                 Surface &img = images[f];

@@ -992,6 +992,133 @@ static void icbc_compress(int level, const V3 col[16], const float wts[16], cons
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Format_RGB / Format_RGBA: PixelFormatConverter::compress (src/nvtt/CompressorRGB.cpp:410-575) with its BitStream
+ * (:332-404), toFloat11 / toFloat10 (:129-160), PixelFormat::convert and maskShiftAndSize (src/nvimage/PixelFormat.h:37-76),
+ * nv::half_from_float (src/nvmath/Half.cpp:378-441) and computeBytePitch (src/nvimage/nvimage.h:11-24).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int pixelType;                       /* nvtt::PixelType */
+    unsigned bitcount;                   /* != 0: mask form */
+    unsigned rmask, gmask, bmask, amask;
+    unsigned rsize, gsize, bsize, asize; /* size form and float channel widths */
+    int pitchAlignment;
+    int width, height;
+} OrcPixelFormatDesc;
+
+static int msb_set(uint32_t v) { return (int32_t)v < 0; }
+static uint32_t sels(uint32_t test, uint32_t a, uint32_t b) { return msb_set(test) ? a : b; }
+/* the select network of half_from_float, same data flow; x86 masks shift counts to 5 bits */
+static uint16_t half_from_float_bits(uint32_t f) {
+    const uint32_t f_s = f & 0x80000000u, f_e = f & 0x7f800000u, f_m = f & 0x007fffffu;
+    const uint32_t h_s = (f_s >> 16) & 0xffffu;
+    const uint32_t e_amount = (f_e >> 23) & 0xffffu;
+    const uint32_t e_half_bias = e_amount - 0x70u;
+    const uint32_t f_snan = f & 0x7fc00000u;
+    const uint32_t m_rounded = f_m + ((f_m & 0x00001000u) << 1);
+    const uint32_t denorm_sa = 1u - e_half_bias;
+    const uint32_t h_m_denorm = ((m_rounded | 0x00800000u) >> (denorm_sa & 31u)) >> 13;
+    const uint32_t m_nan = f_m >> 13;
+    const uint32_t h_em_norm = (e_half_bias << 10) | (m_rounded >> 13);
+    const uint32_t flagged = 0x8fu - e_half_bias;
+    uint32_t r = sels(0u - (m_rounded & 0x00800000u), (e_half_bias + 1u) << 10, h_em_norm);
+    r = sels(flagged, 0x7c00u | m_nan, r);
+    r = sels(flagged & (m_nan - 1u), 0x7c01u, r);
+    r = sels((0x1fu - e_half_bias) | (flagged & (f_m - 1u)), 0x7c00u, r);
+    r = sels(~(0x70u - e_amount), h_m_denorm, r);
+    r = sels(~(f_snan - 0x7fc00000u), 0x7e00u, r);
+    return (uint16_t)(h_s | r);
+}
+
+typedef struct { uint8_t *ptr, *end; uint8_t buffer, bits; } OrcBitStream;
+static void bs_byte(OrcBitStream *s, unsigned v) { if (s->ptr < s->end) *s->ptr = (uint8_t)v; s->ptr++; }
+static void bs_put_bits(OrcBitStream *s, uint32_t p, unsigned n) {
+    uint64_t buffer = (uint32_t)(((uint32_t)s->buffer << (n & 31u)) | p);  /* int << int | uint: 32-bit, then widened */
+    unsigned bits = s->bits + n;
+    while (bits >= 8) { bs_byte(s, (unsigned)(buffer & 0xFF)); buffer >>= 8; bits -= 8; }
+    s->buffer = (uint8_t)buffer;
+    s->bits = (uint8_t)bits;
+}
+static void bs_put_raw(OrcBitStream *s, uint32_t v, int nbytes) { for (int i = 0; i < nbytes; i++) bs_byte(s, (v >> (8 * i)) & 0xFF); }
+static uint32_t float_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static uint32_t to_float11(float f) {
+    if (f < 0) f = 0;
+    if (f > 65024) f = 65024;
+    const uint32_t u = float_bits(f);
+    return ((((u >> 23) & 0xFF) - 127 + 15) << 6) | ((u & 0x7FFFFF) >> 17);
+}
+static uint32_t to_float10(float f) {
+    if (f < 0) f = 0;
+    if (f > 64512) f = 64512;
+    const uint32_t u = float_bits(f);
+    return ((((u >> 23) & 0xFF) - 127 + 15) << 5) | ((u & 0x7FFFFF) >> 18);
+}
+static void bs_put_float_channel(OrcBitStream *s, float v, unsigned size) {
+    if (size == 32) bs_put_raw(s, float_bits(v), 4);
+    else if (size == 16) bs_put_raw(s, half_from_float_bits(float_bits(v)), 2);
+    else if (size == 11) bs_put_bits(s, to_float11(v), 11);
+    else if (size == 10) bs_put_bits(s, to_float10(v), 10);
+    else bs_put_bits(s, 0, size);
+}
+static uint32_t pf_convert(uint32_t c, unsigned inbits, unsigned outbits) { /* PixelFormat.h:37-53 */
+    if (inbits == 0) return 0;
+    if (inbits >= outbits) return c >> (inbits - outbits);
+    return (c << (outbits - inbits)) | pf_convert(c, inbits, outbits - inbits);
+}
+static void mask_shift_size(uint32_t mask, unsigned *shift, unsigned *size) {
+    *shift = 0; *size = 0;
+    if (!mask) return;
+    while ((mask & 1) == 0) { ++*shift; mask >>= 1; }
+    while ((mask & 1) == 1) { ++*size; mask >>= 1; }
+}
+static int iround_nv(float f) { return (int)floorf(f + 0.5f); }
+
+/* out == NULL: returns the level size (0 = layout the reference asserts on, or RGB9E5 which is not restated) */
+long orc_convert_level(const OrcPixelFormatDesc *d, const float *planar, uint8_t *out) {
+    unsigned size[4] = {d->rsize, d->gsize, d->bsize, d->asize}, shift[4] = {0, 0, 0, 0}, bitCount;
+    const int isFloat = d->pixelType == 4;
+    if (isFloat) {
+        bitCount = size[0] + size[1] + size[2] + size[3];
+    } else if (d->bitcount != 0) {
+        bitCount = d->bitcount;
+        const uint32_t mask[4] = {d->rmask, d->gmask, d->bmask, d->amask};
+        for (int i = 0; i < 4; i++) mask_shift_size(mask[i], &shift[i], &size[i]);
+    } else {
+        bitCount = size[0] + size[1] + size[2] + size[3];
+        shift[3] = 0; shift[2] = size[3]; shift[1] = shift[2] + size[2]; shift[0] = shift[1] + size[1];
+    }
+    if (bitCount == 0 || (!isFloat && bitCount > 32)) return 0;
+    if (d->pixelType == 6 && size[0] == 9 && size[1] == 9 && size[2] == 9 && size[3] == 5) return 0;
+    const unsigned alignBits = 8u * (unsigned)d->pitchAlignment;
+    const unsigned pitch = ((((unsigned)d->width * bitCount + alignBits - 1) / alignBits) * alignBits + 7) / 8;
+    const long total = (long)pitch * d->height;
+    if (!out) return total;
+    const size_t whd = (size_t)d->width * d->height;
+    for (int y = 0; y < d->height; y++) {
+        OrcBitStream s = {out + (size_t)y * pitch, out + (size_t)(y + 1) * pitch, 0, 0};
+        const float *src = planar + (size_t)y * d->width;
+        for (int x = 0; x < d->width; x++) {
+            const float c[4] = {src[x], src[x + whd], src[x + 2 * whd], src[x + 3 * whd]};
+            if (isFloat) {
+                for (int i = 0; i < 4; i++) bs_put_float_channel(&s, c[i], size[i]);
+            } else if (d->pixelType == 0 || d->pixelType == 2) {
+                uint32_t p = 0;
+                for (int i = 0; i < 4; i++) {
+                    const float v = (d->pixelType == 0) ? c[i] * 65535.0f : c[i];
+                    const int iv = iround_nv(fclamp_nv(v, 0.0f, 65535.0f));
+                    p |= pf_convert((uint32_t)iv, 16, size[i]) << (shift[i] & 31u);
+                }
+                bs_put_bits(&s, p, bitCount);
+            } else {
+                bs_put_bits(&s, 0, bitCount); /* signed types: zero components; other SharedExp layouts: zeros */
+            }
+        }
+        if (s.bits) { bs_byte(&s, s.buffer); s.buffer = 0; s.bits = 0; } /* flush + zero padding of align() */
+        while (s.ptr < s.end) bs_byte(&s, 0);
+    }
+    return total;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * One level: Compressor::Private::compress + ColorBlockCompressor / FloatColorCompressor (BlockCompressor.cpp:60-205)
  * format: nvtt::Format (1 BC1, 4 BC3, 6 BC4, 7 BC5); returns bytes written, 0 if unsupported.
  * ------------------------------------------------------------------------------------------------------------- */

@@ -44,6 +44,37 @@ def lib():
     return _lib
 
 
+class OrcPixelFormatDesc(C.Structure):
+    _fields_ = [("pixelType", C.c_int), ("bitcount", C.c_uint),
+                ("rmask", C.c_uint), ("gmask", C.c_uint), ("bmask", C.c_uint), ("amask", C.c_uint),
+                ("rsize", C.c_uint), ("gsize", C.c_uint), ("bsize", C.c_uint), ("asize", C.c_uint),
+                ("pitchAlignment", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+def convert_level(planar_rgba, masks=None, sizes=None, pixel_type=0, pitch_alignment=1):
+    """Format_RGBA: PixelFormatConverter::compress of one level.  masks = (bitcount, r, g, b, a) or sizes = (r, g, b, a);
+    neither = CompressionOptions' default BGRA8."""
+    a = np.ascontiguousarray(planar_rgba, dtype=np.float32)
+    _, h, w = a.shape
+    d = OrcPixelFormatDesc()
+    d.pixelType, d.pitchAlignment, d.width, d.height = pixel_type, pitch_alignment, w, h
+    if sizes is not None:
+        d.rsize, d.gsize, d.bsize, d.asize = sizes
+    else:
+        d.bitcount, d.rmask, d.gmask, d.bmask, d.amask = masks or (32, 0xFF0000, 0xFF00, 0xFF, 0xFF000000)
+        if masks is None:
+            d.rsize = d.gsize = d.bsize = d.asize = 8
+    L = lib()
+    L.orc_convert_level.restype = C.c_long
+    L.orc_convert_level.argtypes = [C.POINTER(OrcPixelFormatDesc), C.c_void_p, C.c_void_p]
+    n = L.orc_convert_level(C.byref(d), a.ctypes.data, None)
+    if n <= 0:
+        raise RuntimeError("orc_convert_level: unsupported layout")
+    out = np.zeros(n, np.uint8)
+    assert L.orc_convert_level(C.byref(d), a.ctypes.data, out.ctypes.data) == n
+    return out
+
+
 def block_bytes(fmt):
     return 8 if fmt in (1, 2, 6) else 16
 

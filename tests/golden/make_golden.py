@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refapi as R  # noqa: E402
 from golden_cases import level_cases, pipeline_cases, imageop_cases, make_input  # noqa: E402
-from golden_cases import level_cases_v2, decode_cases, quantize_cases, pipeline_cases_v2  # noqa: E402
+from golden_cases import level_cases_v2, decode_cases, quantize_cases, pipeline_cases_v2, pixel_format_cases  # noqa: E402
 
 
 def sha(a):
@@ -81,6 +81,17 @@ def main():
         for am in (0, 1):
             out["metric_%s_am%d" % (name, am)] = np.array(R.rms_error(fmt, w, h, v1[src], rgba, am), np.float32)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v2.npz")
+    if "--v2" in sys.argv or not os.path.exists(path):
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes,", len(out), "vectors")
+    # ---- v3: Format_RGBA layouts; one level through Compressor::process (gamma 1 -> no toLinear / toGamma, no mips, no header):
+    # the stream is PixelFormatConverter::compress of the BGRA8 image as floats (c / 255) ----
+    out = {}
+    for key, (w, h, kw) in pixel_format_cases().items():
+        img = synth.photo_bgra8(w, h, seed=w * 3 + h, alpha=True)
+        out[key] = R.process([img], 0, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_masks=kw.get("masks"), pixel_sizes=kw.get("sizes"),
+                             pixel_type=kw.get("pixel_type", 0), pitch_alignment=kw.get("pitch_alignment", 0))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v3.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "vectors")
 

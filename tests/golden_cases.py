@@ -103,3 +103,34 @@ def pipeline_cases_v2():
         "pipe_bc1_color_dither_96x72": ("photo", 96, 72, 1, 1, dict(mip_filter=0, quantization=1)),
         "pipe_bc3_binary_alpha_64x48": ("photo", 64, 48, 4, 1, dict(mip_filter=0, quantization=4, alpha_threshold=40)),
     }
+
+
+def pixel_format_cases():
+    """Format_RGBA layouts (PixelFormatConverter, CompressorRGB.cpp:410-575).  key -> (w, h, kwargs of convert_level)."""
+    c = {}
+    layouts = {
+        "bgra8": dict(),
+        "rgba8": dict(masks=(32, 0xFF, 0xFF00, 0xFF0000, 0xFF000000)),
+        "rgb8_align4": dict(masks=(24, 0xFF0000, 0xFF00, 0xFF, 0), pitch_alignment=4),
+        "r5g6b5": dict(masks=(16, 0xF800, 0x7E0, 0x1F, 0)),
+        "a1r5g5b5_align8": dict(masks=(16, 0x7C00, 0x3E0, 0x1F, 0x8000), pitch_alignment=8),
+        "l8": dict(masks=(8, 0xFF, 0, 0, 0)),
+        "a8": dict(masks=(8, 0, 0, 0, 0xFF)),
+        "a2r10g10b10": dict(masks=(32, 0x3FF00000, 0xFFC00, 0x3FF, 0xC0000000)),
+        "x4r4g4b4_12bit": dict(masks=(12, 0xF00, 0xF0, 0xF, 0)),
+        "sizes_5650": dict(sizes=(5, 6, 5, 0)),
+        "sizes_10_10_10_2": dict(sizes=(10, 10, 10, 2)),
+        "sizes_r16": dict(sizes=(16, 0, 0, 0)),
+        "sizes_3320_7bit_stream": dict(sizes=(3, 2, 2, 0)),
+        "uint8888": dict(sizes=(8, 8, 8, 8), pixel_type=2),
+        "snorm_zero": dict(sizes=(8, 8, 8, 8), pixel_type=1),
+        "rgba16f": dict(sizes=(16, 16, 16, 16), pixel_type=4),
+        "rgba32f": dict(sizes=(32, 32, 32, 32), pixel_type=4),
+        "rg16f": dict(sizes=(16, 16, 0, 0), pixel_type=4),
+        "r32f_align4": dict(sizes=(32, 0, 0, 0), pixel_type=4, pitch_alignment=4),
+        "r11g11b10f": dict(sizes=(11, 11, 10, 0), pixel_type=4),
+    }
+    for name, kw in layouts.items():
+        for (w, h) in ((37, 22), (64, 12)):
+            c["pixfmt_%s_%dx%d" % (name, w, h)] = (w, h, kw)
+    return c

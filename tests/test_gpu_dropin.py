@@ -212,6 +212,14 @@ def test_rgba_pixel_formats_identical(nvtt, ref, ours):
         got = _process(ours, ref, [img4], ref.Format_RGBA, 1, 64, 24, mip_filter=0, **kw)
         want = _process(ref.lib(), ref, [img4], ref.Format_RGBA, 1, 64, 24, mip_filter=0, **kw)
         assert np.array_equal(got, want), kw
+    # KTX and DDS10 containers (glType / glFormat lookup, DXGI lookup)
+    for kw in (dict(container=2), dict(container=2, pixel_masks=(32, 0xFF, 0xFF00, 0xFF0000, 0xFF000000)),
+               dict(container=2, pixel_masks=(24, 0xFF0000, 0xFF00, 0xFF, 0)), dict(container=2, pixel_sizes=(16, 0, 0, 0)),
+               dict(container=2, pixel_sizes=(16, 16, 16, 16), pixel_type=4), dict(container=1), dict(container=1, pixel_masks=(16, 0xF800, 0x7E0, 0x1F, 0)),
+               dict(container=1, pixel_sizes=(16, 0, 0, 0)), dict(container=1, pixel_masks=(8, 0xFF, 0, 0, 0))):
+        got = _process(ours, ref, [img], ref.Format_RGBA, 1, w, h, mip_filter=0, **kw)
+        want = _process(ref.lib(), ref, [img], ref.Format_RGBA, 1, w, h, mip_filter=0, **kw)
+        assert np.array_equal(got, want), kw
     # HDR input through the float layouts, DX10 container
     hdr = s.hdr_rgba16f(24, 16, seed=5).view("uint16")
     for kw in (dict(pixel_sizes=(16, 16, 16, 16), pixel_type=4, container=1), dict(pixel_sizes=(11, 11, 10, 0), pixel_type=4, container=1),

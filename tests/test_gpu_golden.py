@@ -132,3 +132,32 @@ def test_gpu_matches_oracle_restatement(nvtt, ctx):
             got = ctx.process_bytes([img], d)
             want = oracleapi.process([img], 0, w, h, fmt, q, **kw)
             assert np.array_equal(got, want), (w, h, fmt, q, kw)
+
+
+def test_gpu_pixel_formats_match_golden_and_oracle(nvtt, ctx):
+    """Format_RGBA writer (nvttb_convert_level) against golden_v3.npz (reference output) for 20 layouts x 2 sizes - one of
+    which takes the four-pixels-per-thread kernel - and against the oracle on HDR / negative / Inf / NaN / denormal values
+    and on a 1024 x 512 image (x4 kernel at full width, odd-width variant through the per-pixel kernel)."""
+    import oracleapi
+    if not oracleapi.available():
+        pytest.fail("oracle/_build/liboracle.so missing: run __graft_entry__.build()")
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "golden_v3.npz"))
+    s = nvtt.synth
+    for key, (w, h, kw) in G.pixel_format_cases().items():
+        img = s.planar_from_bgra8(s.photo_bgra8(w, h, seed=w * 3 + h, alpha=True))
+        got = ctx.convert_level(img, **kw)
+        assert got.size == g3[key].size and np.array_equal(got, g3[key]), key
+    rng = np.random.default_rng(11)
+    for (w, h) in ((29, 7), (64, 9), (1024, 512), (1023, 3)):
+        vals = np.exp(rng.normal(0, 4, (4, h, w))).astype(np.float32) * rng.choice([1.0, 1.0, 1.0, -1.0], (4, h, w)).astype(np.float32)
+        vals[:, 0, :8] = np.array([0.0, -0.0, 1.0, 65504.0, 65520.0, 1e-8, 6.1e-5, 70000.0], np.float32)
+        vals[:, h - 1, :4] = np.array([np.inf, -np.inf, np.nan, 5.96e-8], np.float32)
+        unit = rng.random((4, h, w), dtype=np.float32) * 1.2 - 0.1
+        for kw in (dict(sizes=(16, 16, 16, 16), pixel_type=4), dict(sizes=(32, 32, 32, 32), pixel_type=4), dict(sizes=(16, 0, 0, 0), pixel_type=4),
+                   dict(sizes=(11, 11, 10, 0), pixel_type=4), dict(sizes=(8, 8, 8, 8), pixel_type=2), dict(sizes=(16, 16, 0, 0), pixel_type=2),
+                   dict(), dict(masks=(16, 0xF800, 0x7E0, 0x1F, 0)), dict(masks=(8, 0xFF, 0, 0, 0)), dict(sizes=(10, 10, 10, 2)),
+                   dict(masks=(24, 0xFF0000, 0xFF00, 0xFF, 0), pitch_alignment=4), dict(sizes=(3, 2, 2, 0))):
+            for img in (vals, unit):
+                got = ctx.convert_level(img, **kw)
+                want = oracleapi.convert_level(img, **kw)
+                assert np.array_equal(got, want), (w, h, kw)

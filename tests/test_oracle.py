@@ -57,6 +57,33 @@ def test_oracle_image_ops_match_golden(orc, golden):
         assert np.array_equal(np.stack(hashes), golden[key]), key
 
 
+def test_oracle_pixel_formats_match_golden(orc, nvtt):
+    """Format_RGBA layouts: orc_convert_level against golden_v3.npz (the reference's Compressor::process output)."""
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "golden_v3.npz"))
+    s = nvtt.synth
+    for key, (w, h, kw) in G.pixel_format_cases().items():
+        img = s.planar_from_bgra8(s.photo_bgra8(w, h, seed=w * 3 + h, alpha=True))
+        got = orc.convert_level(img, **kw)
+        assert got.size == g3[key].size and np.array_equal(got, g3[key]), key
+
+
+def test_oracle_pixel_formats_vs_reference_direct(orc, ref, nvtt):
+    """HDR / out-of-range / special values through the float, uint and fixed layouts against the reference itself."""
+    rng = np.random.default_rng(11)
+    w, h = 29, 7
+    vals = np.exp(rng.normal(0, 4, (h, w, 4))).astype(np.float32) * rng.choice([1.0, 1.0, 1.0, -1.0], (h, w, 4)).astype(np.float32)
+    vals[0, :8, :] = np.array([0.0, -0.0, 1.0, 65504.0, 65520.0, 1e-8, 6.1e-5, 70000.0], np.float32)[:, None]
+    vals[1, :4, :] = np.array([np.inf, -np.inf, np.nan, 5.96e-8], np.float32)[:, None]
+    planar = np.ascontiguousarray(np.moveaxis(vals, 2, 0))
+    for kw in (dict(sizes=(16, 16, 16, 16), pixel_type=4), dict(sizes=(32, 32, 32, 32), pixel_type=4), dict(sizes=(16, 0, 0, 0), pixel_type=4),
+               dict(sizes=(11, 11, 10, 0), pixel_type=4), dict(sizes=(8, 8, 8, 8), pixel_type=2), dict(sizes=(16, 16, 0, 0), pixel_type=2),
+               dict(), dict(masks=(16, 0xF800, 0x7E0, 0x1F, 0)), dict(sizes=(10, 10, 10, 2))):
+        a = orc.convert_level(planar, **kw)
+        b = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_masks=kw.get("masks"), pixel_sizes=kw.get("sizes"),
+                        pixel_type=kw.get("pixel_type", 0), pitch_alignment=kw.get("pitch_alignment", 0))
+        assert np.array_equal(a, b), (kw, int(np.flatnonzero(a != b)[0]) if a.size == b.size else (a.size, b.size))
+
+
 def test_oracle_vs_reference_direct(orc, ref, nvtt):
     """Wider sweep against the reference itself (only where oracle/_ref exists)."""
     s = nvtt.synth
