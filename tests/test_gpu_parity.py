@@ -453,3 +453,28 @@ def test_config3_config4_full_size_properties(nvtt, ref, ctx):
     want = ref.compress_level(ref.Format_BC6, 1, _sample_blocks_strip(hdr, idxs, bw), pixel_type=nvtt.PixelType_UnsignedFloat).reshape(-1, 16)
     bad = [i for k, i in enumerate(idxs) if not np.array_equal(got[i], want[k])]
     assert not bad, "BC6H 2048x2048: blocks %s differ from the reference" % bad[:8]
+
+
+def test_16384_square_levels_sampled_blocks(nvtt, ref, ctx):
+    """Four times the texels of the largest BASELINE config (16384^2 = 16.8 M blocks per level): index arithmetic beyond 2^31
+    bytes of planar input.  Sampled blocks of BC1 Fastest / Normal, BC3 and BC5 must equal the reference's encoding of the same tiles."""
+    rng = np.random.default_rng(5)
+    base = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(2048, 2048, seed=99, alpha=True))
+    n = 16384
+    img = np.empty((4, n, n), np.float32)
+    for ty in range(8):
+        for tx in range(8):
+            # every tile differs: rolled copy plus a small per-tile offset, kept inside [0, 1]
+            t = np.roll(base, (17 * ty + 3, 29 * tx + 5), axis=(1, 2))
+            img[:, ty * 2048:(ty + 1) * 2048, tx * 2048:(tx + 1) * 2048] = np.clip(t * 0.9 + 0.0125 * ((ty * 8 + tx) % 8), 0.0, 1.0)
+    bw = n // 4
+    nb = bw * bw
+    idxs = [0, bw - 1, nb - bw, nb - 1, nb // 2 + 12345] + [int(i) for i in rng.integers(0, nb, 123)]
+    strip = _sample_blocks_strip(img, idxs, bw)
+    for fmt, q in ((nvtt.Format_BC1, 0), (nvtt.Format_BC1, 1), (nvtt.Format_BC3, 1), (nvtt.Format_BC5, 1)):
+        bs = 8 if fmt == nvtt.Format_BC1 else 16
+        got = ctx.encode_level(fmt, q, img).reshape(-1, bs)
+        assert got.shape[0] == nb
+        want = ref.compress_level(fmt, q, strip).reshape(-1, bs)
+        bad = [i for k, i in enumerate(idxs) if not np.array_equal(got[i], want[k])]
+        assert not bad, "16384^2 fmt %d q%d: blocks %s differ from the reference" % (fmt, q, bad[:8])
