@@ -12,6 +12,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/pixel_format.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/host_tables.h"
 
 using namespace nvb;
@@ -291,5 +292,19 @@ void emu_to_normal_map(const float *src, float *dst, int w, int h, int wrap, con
 void emu_scale_bias(float *data, size_t pixels, float scale, float bias) {
     ScaleBiasParams P{data, 3 * pixels, scale, bias};
     emu::launch(dim3((unsigned)((P.count + 255) / 256)), dim3(256), 0, [&] { k_scale_bias(P); });
+}
+
+// Format_RGBA writer.  path: 0 = k_pixel_format_x4 (mode = bytes per pixel, 8 = RGBA16F, 16 = RGBA32F), 1 = k_pixel_format, 2 = k_pixel_format_rows.
+// The layout (kind, sizes, shifts, bit count, pitch) is derived by the caller exactly as capi.cu: pixel_layout() does.
+void emu_pixel_format(const float *planar, int w, int h, unsigned char *out, unsigned pitch, unsigned bitCount, int kind, const unsigned *size,
+                      const unsigned *shift, int path, int mode) {
+    PixelFormatParams P;
+    P.lv.data = planar; P.lv.plane = (size_t)w * h; P.lv.w = w; P.lv.h = h; P.lv.bw = (w + 3) / 4; P.lv.bh = (h + 3) / 4;
+    P.lv.to_gamma_table = nullptr;
+    P.out = out; P.pitch = pitch; P.bitCount = bitCount; P.kind = kind;
+    for (int i = 0; i < 4; i++) { P.size[i] = size[i]; P.shift[i] = shift[i]; }
+    if (path == 0) emu::launch(dim3((w / 4 + 255) / 256, h), dim3(256), 0, [&] { k_pixel_format_x4(P, mode); });
+    else if (path == 1) emu::launch(dim3((w + 255) / 256, h), dim3(256), 0, [&] { k_pixel_format(P); });
+    else emu::launch(dim3((h + 63) / 64), dim3(64), 0, [&] { k_pixel_format_rows(P); });
 }
 }

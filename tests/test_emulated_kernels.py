@@ -121,3 +121,56 @@ def test_search_designs_agree(emu):
     assert _run_child({"NVB_EMU_BC7": "coop"}, child("photo", 8, 8, 11)) == _run_child({"NVB_EMU_BC7": "scalar"}, child("photo", 8, 8, 11))
     for kind, w, h in (("hdr", 32, 24), ("photo", 13, 7)):
         assert _run_child({"NVB_EMU_BC6": "scalar"}, child(kind, w, h, 10)) == _run_child({"NVB_EMU_BC6": ""}, child(kind, w, h, 10)), kind
+
+
+def _pixel_layout(w, kw):
+    """capi.cu: pixel_layout() restated for the emulator test: (kind, bitCount, sizes, shifts, pitch, aligned)."""
+    pt, align = kw.get("pixel_type", 0), kw.get("pitch_alignment", 1)
+    size, shift = [0, 0, 0, 0], [0, 0, 0, 0]
+    if kw.get("sizes") is not None:
+        size = list(kw["sizes"])
+        bits = sum(size)
+        shift = [size[1] + size[2] + size[3], size[2] + size[3], size[3], 0]
+    else:
+        bits, *masks = kw.get("masks") or (32, 0xFF0000, 0xFF00, 0xFF, 0xFF000000)
+        for i, m in enumerate(masks):
+            if m:
+                while not (m >> shift[i]) & 1:
+                    shift[i] += 1
+                while (m >> (shift[i] + size[i])) & 1:
+                    size[i] += 1
+    if pt == 4:
+        kind, aligned = 2, all(s in (0, 16, 32) for s in size)
+        shift = [0, 0, 0, 0]
+    else:
+        kind, aligned = {0: 0, 2: 1}.get(pt, 3), bits % 8 == 0
+    abits = 8 * align
+    pitch = ((w * bits + abits - 1) // abits * abits + 7) // 8
+    return kind, bits, size, shift, pitch, aligned
+
+
+def test_emulated_pixel_format_kernels_match_golden(emu, nvtt):
+    """The three Format_RGBA kernels under the CPU emulator against golden_v3.npz (reference output)."""
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "golden_v3.npz"))
+    s = nvtt.synth
+    U4 = C.c_uint * 4
+    emu.emu_pixel_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_int, U4, U4, C.c_int, C.c_int]
+    ran = set()
+    for key, (w, h, kw) in G.pixel_format_cases().items():
+        img = np.ascontiguousarray(s.planar_from_bgra8(s.photo_bgra8(w, h, seed=w * 3 + h, alpha=True)), dtype=np.float32)
+        kind, bits, size, shift, pitch, aligned = _pixel_layout(w, kw)
+        nbytes = bits // 8
+        mode = 0
+        if aligned and kind <= 1 and nbytes in (1, 2, 4):
+            mode = nbytes
+        elif kind == 2 and size == [16] * 4:
+            mode = 8
+        elif kind == 2 and size == [32] * 4:
+            mode = 16
+        paths = [2] + ([1] if aligned else []) + ([0] if mode and w % 4 == 0 and pitch == w * nbytes else [])
+        for path in paths:  # the per-scanline stream is the general kernel: it must agree everywhere
+            out = np.full(pitch * h, 0xCD, np.uint8)
+            emu.emu_pixel_format(img.ctypes.data, w, h, out.ctypes.data, pitch, bits, kind, U4(*size), U4(*shift), path, mode)
+            assert out.size == g3[key].size and np.array_equal(out, g3[key]), (key, path)
+            ran.add(path)
+    assert ran == {0, 1, 2}
