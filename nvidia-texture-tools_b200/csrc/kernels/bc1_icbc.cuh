@@ -67,9 +67,10 @@ NVB_DEV float group_ordered_sum(unsigned gm, float t) {
 }
 
 NVB_DEV unsigned icbc_vector3_to_color16(const Bc1Params &P, float x, float y, float z) {
-    unsigned r = (unsigned)x86_ftoi(nv_clamp(x * 31.0f, 0.0f, 31.0f));
-    unsigned g = (unsigned)x86_ftoi(nv_clamp(y * 63.0f, 0.0f, 63.0f));
-    unsigned b = (unsigned)x86_ftoi(nv_clamp(z * 31.0f, 0.0f, 31.0f));
+    // nv_clamp maps NaN to the lower bound: the operands are always inside [0, 63], plain truncation is the x86 conversion
+    unsigned r = (unsigned)__float2int_rz(nv_clamp(x * 31.0f, 0.0f, 31.0f));
+    unsigned g = (unsigned)__float2int_rz(nv_clamp(y * 63.0f, 0.0f, 63.0f));
+    unsigned b = (unsigned)__float2int_rz(nv_clamp(z * 31.0f, 0.0f, 31.0f));
     r += (x > P.midpoints5[r]) ? 1u : 0u;
     g += (y > P.midpoints6[g]) ? 1u : 0u;
     b += (z > P.midpoints5[b]) ? 1u : 0u;
@@ -257,8 +258,10 @@ struct FitResult {
     float sx, sy, sz, ex, ey, ez;
 };
 
-NVB_DEV float icbc_round5(float x) { return (float)x86_ftoi(icbc_saturate(x) * 31.0f + 0.5f) * (1.0f / 31.0f); }
-NVB_DEV float icbc_round6(float x) { return (float)x86_ftoi(icbc_saturate(x) * 63.0f + 0.5f) * (1.0f / 63.0f); }
+// float(int(v)) with v = saturate(x) * grid + 0.5: v lies in [0.5, grid + 0.5] (the saturate maps NaN to 0), so the x86
+// conversion's out-of-range cases cannot occur and the round trip through int is exactly truncf (one FRND.TRUNC)
+NVB_DEV float icbc_round5(float x) { return truncf(icbc_saturate(x) * 31.0f + 0.5f) * (1.0f / 31.0f); }
+NVB_DEV float icbc_round6(float x) { return truncf(icbc_saturate(x) * 63.0f + 0.5f) * (1.0f / 63.0f); }
 
 // One split of cluster_fit_four (FOUR) or cluster_fit_three.  Returns the error; a/b = snapped endpoints.
 template <bool FOUR>
@@ -318,10 +321,12 @@ NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const 
 // FMUL2 and the product-free subtractions as FADD2; a sum that consumes a product stays two scalar FADDs (ptxas would
 // contract a packed add of a packed product into FFMA2, nvb_common.cuh).  Operation for operation the same arithmetic per
 // split; only the errors are returned (the winner is re-evaluated by icbc_eval_split for its endpoints).
-NVB_DEV float2 icbc_round_pair(float2 x, float grid, float gridrcp) {
-    const float2 s = make_float2(icbc_saturate(x.x), icbc_saturate(x.y));
+// x = t * factor; saturate(x) = min(max(x, 0), 1) with NaN -> 0 is the .SAT of the scalar multiply (one instruction per
+// value instead of half an FMUL2 plus a clamp)
+NVB_DEV float2 icbc_round_pair(float2 num, float2 factor, float grid, float gridrcp) {
+    const float2 s = make_float2(__saturatef(__fmul_rn(num.x, factor.x)), __saturatef(__fmul_rn(num.y, factor.y)));
     const float2 t = f2add_s(f2mul(s, f2splat(grid)), f2splat(0.5f));
-    return f2mul(make_float2((float)x86_ftoi(t.x), (float)x86_ftoi(t.y)), f2splat(gridrcp));
+    return f2mul(make_float2(truncf(t.x), truncf(t.y)), f2splat(gridrcp));
 }
 template <bool FOUR>
 NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, float4 sum, const float msq[3]) {
@@ -366,10 +371,10 @@ NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, flo
     for (int k = 0; k < 3; k++) {
         const float2 alphax = ax[k];
         const float2 betax = f2sub(f2splat(S3[k]), alphax);
-        float2 av = f2mul(f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab)), factor);
-        float2 bv = f2mul(f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab)), factor);
-        av = (k == 1) ? icbc_round_pair(av, 63.0f, 1.0f / 63.0f) : icbc_round_pair(av, 31.0f, 1.0f / 31.0f);
-        bv = (k == 1) ? icbc_round_pair(bv, 63.0f, 1.0f / 63.0f) : icbc_round_pair(bv, 31.0f, 1.0f / 31.0f);
+        const float2 at = f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab));
+        const float2 bt = f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab));
+        const float2 av = (k == 1) ? icbc_round_pair(at, factor, 63.0f, 1.0f / 63.0f) : icbc_round_pair(at, factor, 31.0f, 1.0f / 31.0f);
+        const float2 bv = (k == 1) ? icbc_round_pair(bt, factor, 63.0f, 1.0f / 63.0f) : icbc_round_pair(bt, factor, 31.0f, 1.0f / 31.0f);
         const float2 e2 = f2mul(f2sub_s(f2mul(av, f2sub_s(f2mul(bv, ab), alphax)), f2mul(bv, betax)), f2splat(2.0f));
         e1[k] = f2add_s(f2mul(f2mul(av, av), alpha2), f2add_s(f2mul(f2mul(bv, bv), beta2), e2));
     }
@@ -508,9 +513,9 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
         if (count == 1) {
             // compress_dxt1_single_color_optimal(vector3_to_color32(colors[0]))
             if (l == 0) {
-                const unsigned r = (unsigned)x86_ftoi(icbc_saturate(qx) * 255 + 0.5f) & 0xFF;
-                const unsigned g = (unsigned)x86_ftoi(icbc_saturate(qy) * 255 + 0.5f) & 0xFF;
-                const unsigned b = (unsigned)x86_ftoi(icbc_saturate(qz) * 255 + 0.5f) & 0xFF;
+                const unsigned r = (unsigned)__float2int_rz(icbc_saturate(qx) * 255 + 0.5f) & 0xFF;
+                const unsigned g = (unsigned)__float2int_rz(icbc_saturate(qy) * 255 + 0.5f) & 0xFF;
+                const unsigned b = (unsigned)__float2int_rz(icbc_saturate(qz) * 255 + 0.5f) & 0xFF;
                 unsigned c0 = ((unsigned)P.match5[r * 2 + 0] << 11) | ((unsigned)P.match6[g * 2 + 0] << 5) | P.match5[b * 2 + 0];
                 unsigned c1 = ((unsigned)P.match5[r * 2 + 1] << 11) | ((unsigned)P.match6[g * 2 + 1] << 5) | P.match5[b * 2 + 1];
                 unsigned indices = 0xaaaaaaaau;

@@ -97,7 +97,7 @@ NVB_DEV unsigned pf_convert16(unsigned c, unsigned outbits) {
 // iround(clamp(v, 0, 65535)) = int(floorf(x + 0.5f)); nv::clamp = min(max(x, a), b) with nv::max(a,b) = a>b?a:b, so NaN -> lower bound
 NVB_DEV unsigned pf_to_u16(float v) {
     float c = nv_clamp(v, 0.0f, 65535.0f);
-    return (unsigned)x86_ftoi(floorf(c + 0.5f));
+    return (unsigned)__float2int_rz(floorf(c + 0.5f));  // c is inside [0, 65535]: no out-of-range case
 }
 
 // the fixed-point pixel: 16-bit components converted to their field widths and or'ed together
