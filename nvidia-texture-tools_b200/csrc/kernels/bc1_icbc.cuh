@@ -48,7 +48,8 @@ struct Bc1Params {
 
 struct Bc1GroupSmem {
     float4 pts[16];   // reduced colour set (x,y,z,weight)
-    float4 sat[16];   // summed-area table along the principal axis
+    float4 sat[17];   // summed-area table along the principal axis: sat[0] = 0, sat[k + 1] = sum of the first k + 1 ordered points
+                      // (the split tables store index + 1 with 0 = "nothing", so a split reads sat[field] without a test)
 };
 
 struct Bc1Block {
@@ -240,12 +241,13 @@ NVB_DEV void icbc_compute_sat(Bc1GroupSmem &S, unsigned gm, int l, int n) {
         if (j < n && (dj < dps || (dj == dps && j < l))) rank++;
     }
     __syncwarp(gm);  // everyone is done reading S.sat from a previous call
-    if (l < n) S.sat[rank] = make_float4(mine.x * mine.w, mine.y * mine.w, mine.z * mine.w, mine.w);
+    if (l < n) S.sat[rank + 1] = make_float4(mine.x * mine.w, mine.y * mine.w, mine.z * mine.w, mine.w);
     __syncwarp(gm);
     // inclusive prefix sums, sequentially (lane 0), in the reference's order
     if (l == 0) {
-        float4 acc = S.sat[0];
-        for (int i = 1; i < n; i++) {
+        S.sat[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = S.sat[1];
+        for (int i = 2; i <= n; i++) {
             const float4 s = S.sat[i];
             acc.x = acc.x + s.x; acc.y = acc.y + s.y; acc.z = acc.z + s.z; acc.w = acc.w + s.w;
             S.sat[i] = acc;
@@ -266,14 +268,13 @@ NVB_DEV float icbc_round6(float x) { return truncf(icbc_saturate(x) * 63.0f + 0.
 // One split of cluster_fit_four (FOUR) or cluster_fit_three.  Returns the error; a/b = snapped endpoints.
 template <bool FOUR>
 NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const float msq[3], float a[3], float b[3]) {
-    const int c0 = (int)(pk & 31) - 1, c1 = (int)((pk >> 5) & 31) - 1, c2 = (int)((pk >> 10) & 31) - 1;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 s0 = (c0 >= 0) ? sat[c0] : zero;
-    const float4 s1 = (c1 >= 0) ? sat[c1] : zero;
+    const int c0 = (int)(pk & 31), c1 = (int)((pk >> 5) & 31), c2 = (int)((pk >> 10) & 31);  // index + 1; sat[0] = 0
+    const float4 s0 = sat[c0];
+    const float4 s1 = sat[c1];
     float alpha2_sum, beta2_sum, alphabeta_sum;
     float ax[3];
     if (FOUR) {
-        const float4 s2 = (c2 >= 0) ? sat[c2] : zero;
+        const float4 s2 = sat[c2];
         const float w3 = sum.w - s2.w;
         const float x2[3] = {s2.x - s1.x, s2.y - s1.y, s2.z - s1.z};
         const float x1[3] = {s1.x - s0.x, s1.y - s0.y, s1.z - s0.z};
@@ -330,16 +331,15 @@ NVB_DEV float2 icbc_round_pair(float2 num, float2 factor, float grid, float grid
 }
 template <bool FOUR>
 NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, float4 sum, const float msq[3]) {
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int a0 = (int)(pka & 31) - 1, a1 = (int)((pka >> 5) & 31) - 1, a2 = (int)((pka >> 10) & 31) - 1;
-    const int b0 = (int)(pkb & 31) - 1, b1 = (int)((pkb >> 5) & 31) - 1, b2 = (int)((pkb >> 10) & 31) - 1;
-    const float4 sa0 = (a0 >= 0) ? sat[a0] : zero, sb0 = (b0 >= 0) ? sat[b0] : zero;
-    const float4 sa1 = (a1 >= 0) ? sat[a1] : zero, sb1 = (b1 >= 0) ? sat[b1] : zero;
+    const int a0 = (int)(pka & 31), a1 = (int)((pka >> 5) & 31), a2 = (int)((pka >> 10) & 31);  // index + 1; sat[0] = 0
+    const int b0 = (int)(pkb & 31), b1 = (int)((pkb >> 5) & 31), b2 = (int)((pkb >> 10) & 31);
+    const float4 sa0 = sat[a0], sb0 = sat[b0];
+    const float4 sa1 = sat[a1], sb1 = sat[b1];
     const float2 s0[4] = {make_float2(sa0.x, sb0.x), make_float2(sa0.y, sb0.y), make_float2(sa0.z, sb0.z), make_float2(sa0.w, sb0.w)};
     const float2 s1[4] = {make_float2(sa1.x, sb1.x), make_float2(sa1.y, sb1.y), make_float2(sa1.z, sb1.z), make_float2(sa1.w, sb1.w)};
     float2 alpha2, beta2, ab, ax[3];
     if (FOUR) {
-        const float4 sa2 = (a2 >= 0) ? sat[a2] : zero, sb2 = (b2 >= 0) ? sat[b2] : zero;
+        const float4 sa2 = sat[a2], sb2 = sat[b2];
         const float2 s2[4] = {make_float2(sa2.x, sb2.x), make_float2(sa2.y, sb2.y), make_float2(sa2.z, sb2.z), make_float2(sa2.w, sb2.w)};
         const float2 w3 = f2sub(f2splat(sum.w), s2[3]);
         const float2 w2 = f2sub(s2[3], s1[3]), w1 = f2sub(s1[3], s0[3]), w0 = s0[3];
@@ -386,7 +386,7 @@ NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, flo
 // 8192² Production 65.5 -> 70 ms), while the level-8 kernel gains (48.0 -> ~45 ms).
 template <bool FOUR, bool PAIR>
 NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, unsigned gm, int l, int count) {
-    const float4 sum = S.sat[count - 1];
+    const float4 sum = S.sat[count];
     const float msq[3] = {P.cw[0] * P.cw[0], P.cw[1] * P.cw[1], P.cw[2] * P.cw[2]};
     const unsigned short *tab = FOUR ? P.four : P.three;
     const int total = FOUR ? P.four_total[count - 1] : P.three_total[count - 1];
