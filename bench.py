@@ -319,7 +319,9 @@ def main():
             # From the committed ncu --set full capture of this kernel on this input (profiles/r1i_ncu_bc3_color.txt):
             # DRAM bytes and warp instructions of the level-0 launch.  The live CUDA-event time of the same launch turns the
             # instruction count into an issue rate against 148 SMs x 4 schedulers x 1 warp-instruction per clock.
-            roofline["traffic"] = 211.0e6 + 14.8e6
+            # dram__bytes_read 50.4 MB + dram__bytes_write 0.06 MB at 2048x2048 (the 4 MB of blocks were still in L2 when the capture
+            # ended), scaled by the texel count of this launch; algorithmic bytes are 5 B/texel = 83.9 MB at 4096x4096
+            roofline["traffic"] = (50.4e6 + 0.06e6) * (SIZE * SIZE) / (2048.0 * 2048.0)
             winst = 9505.0 * (SIZE // 4) * (SIZE // 4) / 2  # 9505 warp-instructions per warp of two 4x4 blocks
             if sm_mhz:
                 issue_peak = 148 * 4 * sm_mhz * 1e6
