@@ -283,12 +283,33 @@ template <int WX, int WY> __global__ void __launch_bounds__(256) k_polyphase_2d_
     const float *plane = P.src + (size_t)c * P.sw * P.sh;
     // 1. stage the footprint: one warp per row, lanes along x (coalesced); wrap only for tiles that touch the border
     const bool interior = x_lo >= 0 && x_hi <= P.sw && y_lo >= 0 && y_hi <= P.sh;
-    for (int r = wid; r < nrows; r += 8) {
-        const int sy = interior ? y_lo + r : wrap_coord(y_lo + r, P.sh, P.wrap);
-        const float *row = plane + (size_t)sy * P.sw;
-        for (int cc = lane; cc < ncols; cc += 32) {
-            const int sx = interior ? x_lo + cc : wrap_coord(x_lo + cc, P.sw, P.wrap);
-            s_in[r][NVB_PF_COL(cc)] = row[sx];
+    // Four rows x three column groups = up to 12 independent loads in flight per thread before the first store (the plain
+    // load -> store loop left the kernel waiting on one global load at a time: long-scoreboard 11 per issue, 13 % of HBM peak).
+    static_assert(NVB_PF_EXT <= 96, "three column groups of 32 cover a staged row");
+    for (int r0 = wid; r0 < nrows; r0 += 32) {
+        float v[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = r0 + 8 * k;
+            const bool rok = r < nrows;
+            const int sy = !rok ? 0 : interior ? y_lo + r : wrap_coord(y_lo + r, P.sh, P.wrap);
+            const float *row = plane + (size_t)sy * P.sw;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int cc = lane + 32 * j;
+                const bool ok = rok && cc < ncols;
+                const int sx = !ok ? 0 : interior ? x_lo + cc : wrap_coord(x_lo + cc, P.sw, P.wrap);
+                v[k][j] = ok ? __ldg(row + sx) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = r0 + 8 * k;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int cc = lane + 32 * j;
+                if (r < nrows && cc < ncols) s_in[r][NVB_PF_COL(cc)] = v[k][j];
+            }
         }
     }
     __syncthreads();
