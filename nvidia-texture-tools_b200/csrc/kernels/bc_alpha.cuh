@@ -41,24 +41,27 @@ NVB_DEV void alpha_palette(unsigned a0, unsigned a1, unsigned pal[8]) {
 NVB_DEV unsigned alpha_compute_indices(const unsigned src[16], unsigned a0, unsigned a1, unsigned long long *blk) {
     unsigned pal[8];
     alpha_palette(a0, a1, pal);
+    // The reference scans the eight entries and keeps the first strictly smaller squared distance.  Same result without the
+    // compare / select chain: key_p = 8 * (pal_p - a)^2 + p orders by error first and by entry number among equal errors, and
+    // key_p = (8 pal_p^2 + p) - 16 pal_p * a + 8 a^2, whose last term does not depend on p - so one multiply-add per entry
+    // and a running minimum (exact integer arithmetic, |terms| < 2^21).
+    int A[8], B[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        A[p] = (int)(pal[p] * pal[p] * 8u) + p;
+        B[p] = -16 * (int)pal[p];
+    }
     unsigned total = 0;
     unsigned long long bits = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        int alpha = (int)src[i];
-        unsigned besterror = 256 * 256;
-        unsigned best = 8;
+        const int alpha = (int)src[i];
+        int m = alpha * B[0] + A[0];
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            int d = (int)pal[p] - alpha;
-            unsigned error = (unsigned)(d * d);
-            if (error < besterror) {
-                besterror = error;
-                best = p;
-            }
-        }
-        total += besterror;
-        bits |= (unsigned long long)(best & 7) << (3 * i);
+        for (int p = 1; p < 8; p++) m = min(m, alpha * B[p] + A[p]);
+        const unsigned key = (unsigned)(m + 8 * alpha * alpha);
+        total += key >> 3;
+        bits |= (unsigned long long)(key & 7u) << (3 * i);
     }
     *blk = (*blk & 0xFFFFull) | (bits << 16);
     return total;
@@ -247,16 +250,21 @@ __global__ void __launch_bounds__(128) k_alpha_blocks(AlphaBlocksParams P) {
 NVB_DEV unsigned alpha_pair_error(const unsigned src[16], unsigned a0, unsigned a1) {
     unsigned pal[8];
     alpha_palette(a0, a1, pal);
+    // min_p (a - pal_p)^2 = a^2 + min_p (pal_p^2 - 2 pal_p a): one multiply-add per entry and a running minimum
+    int A[8], B[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        A[p] = (int)(pal[p] * pal[p]);
+        B[p] = -2 * (int)pal[p];
+    }
     unsigned total = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        unsigned best = 0x7fffffffu;
+        const int alpha = (int)src[i];
+        int m = alpha * B[0] + A[0];
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            const int d = (int)src[i] - (int)pal[p];
-            best = min(best, (unsigned)(d * d));
-        }
-        total += best;
+        for (int p = 1; p < 8; p++) m = min(m, alpha * B[p] + A[p]);
+        total += (unsigned)(m + alpha * alpha);
     }
     return total;
 }
