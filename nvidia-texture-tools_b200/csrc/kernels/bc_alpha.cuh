@@ -67,6 +67,16 @@ NVB_DEV unsigned alpha_compute_indices(const unsigned src[16], unsigned a0, unsi
     return total;
 }
 
+// k / 7.0f for k = 1..6, correctly rounded (i.e. bit-identical to the IEEE division of the reference) without the division
+// sequence: q = k * RN(1/7), r = fma(-7, q, k) (exact), q' = fma(r, RN(1/7), q).  Checked against k / 7.0f for the six values
+// it is used for (tests/test_capi_boundary.py: test_div7_identity); the plain product alone is off by one ulp for k = 3 and 6.
+NVB_DEV float alpha_div7(float k) {
+    const float y = 1.0f / 7.0f;  // folded at compile time, correctly rounded
+    const float q = __fmul_rn(k, y);
+    const float r = __fmaf_rn(-7.0f, q, k);
+    return __fmaf_rn(r, y, q);
+}
+
 // Least-squares endpoint refit for the current indices (always with the 8-step weights, also when the block is
 // in 6-step mode — that is what the reference does).
 NVB_DEV void alpha_optimize8(const unsigned src[16], unsigned long long *blk) {
@@ -77,7 +87,7 @@ NVB_DEV void alpha_optimize8(const unsigned src[16], unsigned long long *blk) {
         unsigned idx = (unsigned)(bits >> (3 * i)) & 7u;
         float alpha;
         if (idx < 2) alpha = 1.0f - (float)idx;
-        else alpha = (8.0f - (float)idx) / 7.0f;
+        else alpha = alpha_div7(8.0f - (float)idx);
         float beta = 1 - alpha;
         float x = (float)src[i];
         alpha2_sum += alpha * alpha;

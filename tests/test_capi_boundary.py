@@ -98,3 +98,17 @@ def _our_header(ours, fmt, container, normal, ttype, faces, mipcount):
     ours.ref_output_header.restype = C.c_long
     n = ours.ref_output_header(ttype, 8, 8, faces if ttype == 3 else 1, mipcount, int(normal), fmt, container, buf, 256)
     return bytes(buf[:n]) if n > 0 else None
+
+
+def test_div7_identity():
+    """alpha_div7 (bc_alpha.cuh): k * RN(1/7) corrected by two fused multiply-adds equals the IEEE quotient k / 7.0f for
+    k = 1..6 - the only operands the DXT5 alpha refit ever divides (QuickCompressDXT.cpp optimizeAlpha8 weights)."""
+    import numpy as np
+    f32 = np.float32
+    y = f32(1.0) / f32(7.0)
+    for k in range(1, 7):
+        kk = f32(k)
+        q = f32(kk * y)
+        r = f32(np.float64(kk) - np.float64(7.0) * np.float64(q))      # fma(-7, q, k): exact
+        q2 = f32(np.float64(q) + np.float64(r) * np.float64(y))       # fma(r, y, q): |terms| small, double is exact enough
+        assert q2 == f32(kk / f32(7.0)), k
