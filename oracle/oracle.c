@@ -3,6 +3,10 @@
  * BCn + mip hot path (NVTT 2.1.2).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may link or call this file; the product (nvidia-texture-tools_b200/) never does.
  *
+ * Restated here: image ops (setImage, gamma, box / polyphase mips, renormalise), BC1 (ICBC levels 1 / 8 / 9), BC3 colour (squish
+ * weighted cluster fit), BC4 / BC5 / BC3 alpha (quick, iterative and brute-force), and the Format_RGBA pixel-format writer
+ * (orc_convert_level).  BC2, BC3n, BC1a, BC6H and BC7 are checked against oracle/_ref directly.
+ *
  * Parity status: PINNED.  Every function here is checked bit-for-bit against oracle/_ref (the unmodified reference
  * built with -O2 -ffp-contract=off -DICBC_SIMD=0 -DSQUISH_USE_SSE=0, see oracle/build_ref.sh) by tests/test_oracle.py
  * when /root/reference is available, and against the golden vectors in tests/golden/ (generated from that build by
