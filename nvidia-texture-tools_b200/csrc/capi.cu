@@ -832,7 +832,12 @@ static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidt
                            const float *src, int sw, int sh, float *dst, int dw, int dh) {
     if (mipmapFilter == MF_Box && filterWidth == 0.5f && alphaMode != AM_Transparency) {
         BoxDownParams P{src, dst, sw, sh, dw, dh, 4};
-        NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down, grid_for((size_t)dw * dh * 4, 256), 256, P);
+        if ((sw & 3) == 0 && (sh & 1) == 0 && sh >= 2 && dh <= 65535 && ((size_t)src & 15) == 0 && ((size_t)dst & 7) == 0) {
+            const dim3 grid(grid_for((size_t)dw / 2, 256), dh, 4);
+            NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down_even4, grid, 256, P);
+        } else {
+            NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down, grid_for((size_t)dw * dh * 4, 256), 256, P);
+        }
         CK(cudaGetLastError());
         return NVTTB_OK;
     }
