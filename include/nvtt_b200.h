@@ -192,15 +192,26 @@ typedef struct NvttbProcessDesc {
     int alphaMode;     /* nvtt::AlphaMode */
     NvttbEncodeDesc encode; /* format, quality, colour weights, pixel type (width/height/applyToGamma ignored) */
     int firstFace, lastFace;   /* process faces [firstFace, lastFace); 0,0 = all (multi-GPU sharding by face) */
-    /* Block-row sharding of ONE image over bandCount GPUs (bandCount <= 1: off).  Every band builds the whole fp32 mip
-     * chain (cheap, keeps every level bit-identical) but encodes only its own block rows of each level whose block-row
-     * count divides by bandCount; the remaining small levels are encoded by band 0 alone.  The call then produces, per
-     * face, the concatenation of this band's slices (see nvttb_process_band_slice); emit is called with the slice. */
+    /* Block-row sharding of ONE image over bandCount GPUs (bandCount <= 1: off).  Level 0 is cut into chunks of
+     * bandChunkRows texel rows (a multiple of 4; 0 = height / bandCount, i.e. one contiguous band per GPU) and chunk c belongs
+     * to band c % bandCount (cyclic: content of different cost is spread over the GPUs).  A mip level is distributed while a
+     * chunk still covers whole block rows of it (bandChunkRows % (4 << level) == 0); the remaining small levels ("the tail")
+     * are encoded by band 0 alone.  nvttb_process_band_slices is the layout contract.  The call produces, per face, the
+     * concatenation of this band's slices level by level; emit is called once per level with them. */
     int bandIndex, bandCount;
-    /* nvttb_process_to_device only, with bandCount > 1: out_device is the WHOLE encoded chain of the processed faces (as one
-     * GPU would produce it) and this band stores its slices at their final offsets.  The buffer may live on another GPU
-     * (peer memory, see nvttb_ipc_*): the encoder's stores then go over NVLink and no gather is needed afterwards. */
+    /* nvttb_process_to_device / nvttb_process_shard only, with bandCount > 1: out_device is the WHOLE encoded chain of the
+     * processed faces (as one GPU would produce it) and this band stores its slices at their final offsets.  The buffer may live
+     * on another GPU (peer memory, see nvttb_ipc_*): the encoder's stores then go over NVLink and no gather is needed. */
     int bandOutputInPlace;
+    int bandChunkRows;
+    /* Band-local front end (Box mip filter, 2.2 / 1.0 gammas, one face per call): with bandExchange != NULL a band uploads,
+     * converts and down-samples ONLY its own chunks; the rows of the last distributed level travel to band 0 through this
+     * buffer (device memory on band 0's GPU, nvttb_process_exchange_size bytes, zero-filled once; the other bands map it as
+     * peer memory) with release/acquire flags over NVLink, and band 0 runs the tail from it on a second stream.
+     * bandSequence: 1, 2, 3, ... - the same number on every band for one image, one more for the next image that uses the
+     * same exchange buffer.  With bandExchange == NULL every band builds the whole fp32 chain (any filter, no exchange). */
+    void *bandExchange;
+    unsigned bandSequence;
 } NvttbProcessDesc;
 
 /* Called once per (face, mip) in the reference's order (face-major, mip-minor); data is host memory owned by the
@@ -217,10 +228,27 @@ NVTTB_API int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc 
                                       int images_location, void *out_device, size_t out_capacity, size_t *written);
 /* Total bytes nvttb_process emits for this description (Compressor::estimateSize, src/nvtt/Context.cpp:122-137). */
 NVTTB_API size_t nvttb_process_output_size(const NvttbProcessDesc *desc);
-/* Where band `desc->bandIndex` of `desc->bandCount` sits inside mip level `level`: *offset = byte offset of the slice in
- * the level, *bytes = its size (0: this band emits nothing for the level).  With bandCount <= 1 the slice is the level.
- * Replaces nothing in the reference (it has no multi-device path); it is the contract between ranks for the gather. */
-NVTTB_API int nvttb_process_band_slice(const NvttbProcessDesc *desc, int level, size_t *offset, size_t *bytes);
+/* Where band `desc->bandIndex` of `desc->bandCount` sits inside mip level `level`: `*count` slices of `*bytes` bytes each, the
+ * first at byte `*offset` of the level and the following ones `*pitch` bytes apart (*count = 0: this band emits nothing for the
+ * level).  With bandCount <= 1 the one slice is the level.  Replaces nothing in the reference (it has no multi-device path);
+ * it is the contract between the GPUs of a box for assembling one image. */
+NVTTB_API int nvttb_process_band_slices(const NvttbProcessDesc *desc, int level, size_t *offset, size_t *bytes, size_t *pitch, int *count);
+/* Bytes of the exchange buffer of the band-local front end (0: the description does not qualify and bandExchange is ignored). */
+NVTTB_API size_t nvttb_process_exchange_size(const NvttbProcessDesc *desc);
+/* One band's share of ONE block-row sharded image (desc->bandCount > 1).  out_device: whole-chain layout (this GPU's or a
+ * peer's memory; NULL = an internal buffer); out_host (optional): pinned / registered host memory in the whole-chain layout -
+ * the band's slices are also copied there (each GPU writes its slice of the output over its own PCIe link).  Host images may
+ * be pageable or pinned.  Synchronous when out_host or a host image is given, asynchronous on the context's stream otherwise. */
+NVTTB_API int nvttb_process_shard(NvttbContext *ctx, const NvttbProcessDesc *desc, const void *const *images, int images_location,
+                                  void *out_device, void *out_host);
+/* The whole pipeline for host images on SEVERAL GPUs of one process (one host thread per context): large single images are
+ * block-row sharded (band-local front end where it applies), cube faces / array slices are dealt out face by face.  emit sees
+ * exactly what nvttb_process would produce on one GPU.  contexts[0] owns the pinned output buffer. */
+NVTTB_API int nvttb_process_multi(NvttbContext *const *contexts, int context_count, const NvttbProcessDesc *desc,
+                                  const void *const *images, NvttbEmitFn emit, void *user);
+/* cudaHostRegister / cudaHostUnregister (portable): lets several processes (one per GPU) DMA into one shared host buffer. */
+NVTTB_API int nvttb_host_register(NvttbContext *ctx, void *host_ptr, size_t bytes);
+NVTTB_API int nvttb_host_unregister(NvttbContext *ctx, void *host_ptr);
 /* ---- one output buffer shared by the GPUs of a box (block-row sharding of one image) ------------------------------------
  * The owner allocates the chain buffer and exports it; the other ranks (processes) open it and pass the pointer to
  * nvttb_process_to_device with bandOutputInPlace = 1.  Thin wrappers over cudaMalloc / cudaIpcGetMemHandle /

@@ -66,7 +66,8 @@ class ProcessDesc(C.Structure):
                 ("isNormalMap", C.c_int), ("convertToNormalMap", C.c_int), ("normalizeMipmaps", C.c_int),
                 ("heightFactors", C.c_float * 4), ("bumpFrequencyScale", C.c_float * 4),
                 ("alphaMode", C.c_int), ("encode", EncodeDesc), ("firstFace", C.c_int), ("lastFace", C.c_int),
-                ("bandIndex", C.c_int), ("bandCount", C.c_int), ("bandOutputInPlace", C.c_int)]
+                ("bandIndex", C.c_int), ("bandCount", C.c_int), ("bandOutputInPlace", C.c_int), ("bandChunkRows", C.c_int),
+                ("bandExchange", C.c_void_p), ("bandSequence", C.c_uint)]
 
 
 class KernelStat(C.Structure):
@@ -86,7 +87,8 @@ EXPORTS = [
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
-    "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slice",
+    "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slices",
+    "nvttb_process_exchange_size", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
     "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
 ]
 
@@ -162,7 +164,13 @@ def lib():
     L.nvttb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.nvttb_ipc_close.argtypes = [vp, vp]
     L.nvttb_process_mip_count.argtypes = [C.POINTER(ProcessDesc)]
-    L.nvttb_process_band_slice.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.nvttb_process_band_slices.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
+    L.nvttb_process_exchange_size.argtypes = [C.POINTER(ProcessDesc)]
+    L.nvttb_process_exchange_size.restype = sz
+    L.nvttb_process_shard.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, vp]
+    L.nvttb_process_multi.argtypes = [C.POINTER(vp), ci, C.POINTER(ProcessDesc), C.POINTER(vp), EMIT_FN, vp]
+    L.nvttb_host_register.argtypes = [vp, vp, sz]
+    L.nvttb_host_unregister.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -181,9 +189,10 @@ def make_process_desc(input_format, w, h, fmt, quality, *, faces=1, wrap=WrapMod
                       mipmaps=True, max_level=-1, kaiser=(3.0, 4.0, 1.0), gamma=(2.2, 2.2), normal_map=False,
                       to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
                       pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), first_face=0, last_face=0, band_index=0,
-                      band_count=0, band_output_in_place=False):
+                      band_count=0, band_output_in_place=False, band_chunk_rows=0, band_exchange=None, band_sequence=0):
     d = ProcessDesc()
     d.bandOutputInPlace = int(band_output_in_place)
+    d.bandChunkRows, d.bandExchange, d.bandSequence = band_chunk_rows, band_exchange, band_sequence
     d.inputFormat, d.width, d.height, d.faceCount = input_format, w, h, faces
     d.wrapMode, d.mipmapFilter, d.generateMipmaps, d.maxLevel = wrap, mip_filter, int(mipmaps), max_level
     d.kaiserWidth, d.kaiserAlpha, d.kaiserStretch = kaiser
@@ -302,6 +311,11 @@ class Context:
         self._ck(self.L.nvttb_process_to_device(self.h, C.byref(desc), ptrs, location, d_out_ptr, cap, C.byref(written)))
         return written.value
 
+    def process_shard(self, images, desc, d_out_ptr=None, h_out_ptr=None, location=HOST):
+        """nvttb_process_shard: this band's share of one block-row sharded image, whole-chain layout on device and / or host."""
+        ptrs, keep = self._image_ptrs(images, location)
+        self._ck(self.L.nvttb_process_shard(self.h, C.byref(desc), ptrs, location, d_out_ptr, h_out_ptr))
+
     @staticmethod
     def _image_ptrs(images, location):
         keep = []
@@ -314,6 +328,24 @@ class Context:
             else:
                 vals.append(int(im))
         return (C.c_void_p * len(vals))(*vals), keep
+
+
+def process_multi(contexts, images, desc):
+    """nvttb_process_multi: host images -> whole chain, on all the given contexts (GPUs) of this process.
+    Returns list of (face, mip, w, h, bytes)."""
+    out = []
+
+    def _emit(user, face, mip, w, h, d, data, size):
+        out.append((face, mip, w, h, np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (size,)).copy()))
+        return 1
+
+    cb = EMIT_FN(_emit)
+    ptrs, keep = Context._image_ptrs(images, HOST)
+    hs = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = lib().nvttb_process_multi(hs, len(contexts), C.byref(desc), ptrs, cb, None)
+    if rc != 0:
+        raise NvttbError(rc, lib().nvttb_last_error(contexts[0].h).decode())
+    return out
 
 
 class Surface:

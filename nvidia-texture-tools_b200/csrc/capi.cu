@@ -15,10 +15,12 @@
 #include "kernels/image_ops.cuh"
 #include "kernels/bc_decode.cuh"
 #include "kernels/pixel_format.cuh"
+#include "kernels/shard_exchange.cuh"
 
 #include <cuda_runtime.h>
 #include <map>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 #include <string.h>
@@ -45,9 +47,9 @@ struct PolyDev {
     int *left = nullptr;
 };
 
-enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_PIXEL_FORMAT, K_COUNT };
+enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_PIXEL_FORMAT, K_XCHG, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_alpha_blocks", "k_alpha_optimal", "k_alpha_dxt3", "k_bc3_color", "k_bc1a_color", "k_bc1_icbc", "k_dxt1_quick", "k_bc6_rough", "k_bc6_tiles", "k_bc6_setup", "k_bc6_order", "k_bc6_search", "k_bc6_finish", "k_bc6_select", "k_bc7_rough", "k_bc7_tiles", "k_bc7_setup", "k_bc7_order", "k_bc7_search", "k_bc7_finish", "k_bc7_select", "k_set_image", "k_gamma", "k_box_down",
-                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize", "k_quantize", "k_pixel_format"};
+                                                  "k_polyphase_x", "k_polyphase_y", "k_polyphase_2d", "k_normalize", "k_scale_bias", "k_grey_scale", "k_to_normal_map", "k_decode_blocks", "k_error_metric", "k_binarize", "k_quantize", "k_pixel_format", "k_xchg"};
 struct ProfRec {
     int kid;
     cudaEvent_t a, b;
@@ -86,6 +88,14 @@ struct NvttbContext {
     unsigned char *d_icbc_match = nullptr;
     int icbc_four_count = 0;
     DevBuf in_stage, tmp_filter, tmp_level, out_dev, lvlA, lvlB, enc_scratch;
+    // block-row sharding of one image: band 0 runs the tail levels on tail_stream (own encoder scratch, own level buffers)
+    // while its share of the big levels is still being encoded on `stream`
+    cudaStream_t tail_stream = nullptr;
+    enum { MAX_LEVELS = 32 };
+    cudaEvent_t ev_lvl[MAX_LEVELS] = {}, ev_tail_done = nullptr;
+    DevBuf tail_scratch, tail_lvl, exchange;
+    unsigned *h_fault = nullptr;  // host-mapped: set by a device-side wait that timed out
+    unsigned multi_seq = 0;       // nvttb_process_multi: image counter of the exchange buffer this context owns
     void *h_out = nullptr;  // pinned
     size_t h_out_cap = 0;
     std::map<std::tuple<int, unsigned, unsigned, unsigned, int, int>, PolyDev> poly_cache;
@@ -150,9 +160,16 @@ static int ensure_pinned(NvttbContext *ctx, size_t bytes) {
     if (ctx->h_out) CK(cudaFreeHost(ctx->h_out));
     ctx->h_out = nullptr;
     ctx->h_out_cap = 0;
-    CK(cudaMallocHost(&ctx->h_out, bytes));
+    CK(cudaHostAlloc(&ctx->h_out, bytes, cudaHostAllocPortable));
     ctx->h_out_cap = bytes;
     return NVTTB_OK;
+}
+
+// experiment overrides read from the environment: positive integers only (they are used as divisors)
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    const int x = v ? atoi(v) : dflt;
+    return x >= 1 ? x : dflt;
 }
 
 static inline unsigned grid_for(size_t items, int per_cta) {
@@ -213,6 +230,12 @@ int nvttb_context_create(int device, NvttbContext **out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork[p], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_tail_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < NvttbContext::MAX_LEVELS; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_lvl[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaHostAlloc((void **)&ctx->h_fault, sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    *ctx->h_fault = 0;
     float tg[512], tl[512];
     build_gamma_tables(tg, tl);
     std::vector<uint16_t> cand;
@@ -306,6 +329,15 @@ void nvttb_context_destroy(NvttbContext *ctx) {
     cudaFree(ctx->lvlA.p);
     cudaFree(ctx->lvlB.p);
     cudaFree(ctx->enc_scratch.p);
+    cudaStreamSynchronize(ctx->tail_stream);
+    cudaFree(ctx->tail_scratch.p);
+    cudaFree(ctx->tail_lvl.p);
+    cudaFree(ctx->exchange.p);
+    if (ctx->h_fault) cudaFreeHost(ctx->h_fault);
+    for (int i = 0; i < NvttbContext::MAX_LEVELS; i++)
+        if (ctx->ev_lvl[i]) cudaEventDestroy(ctx->ev_lvl[i]);
+    if (ctx->ev_tail_done) cudaEventDestroy(ctx->ev_tail_done);
+    cudaStreamDestroy(ctx->tail_stream);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     for (auto &kv : ctx->poly_cache) {
         cudaFree(kv.second.weights);
@@ -335,7 +367,12 @@ uint64_t nvttb_launch_count(const NvttbContext *ctx) { return ctx ? ctx->launche
 void *nvttb_stream(NvttbContext *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int nvttb_synchronize(NvttbContext *ctx) {
     if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_fault && *ctx->h_fault) {
+        *ctx->h_fault = 0;
+        return fail(ctx, NVTTB_ERR_CUDA, "sharded image: a band never delivered its rows (device-side wait timed out)");
+    }
     return NVTTB_OK;
 }
 
@@ -445,7 +482,7 @@ static constexpr size_t kBc7ChunkBytesPerBlock = 256 + Bc7ModeBytes<0, 4>::per_b
                                                  Bc7ModeBytes<3, 16>::per_block + Bc7ModeBytes<4, 8>::per_block + Bc7ModeBytes<5, 4>::per_block +
                                                  Bc7ModeBytes<6, 1>::per_block + Bc7ModeBytes<7, 16>::per_block;
 
-template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, unsigned *counters, int parity, double units) {
+template <int M, int NCAND> static int launch_bc7_mode(NvttbContext *ctx, Bc7SearchParams S, unsigned char *&arena, unsigned *counters, int parity, double units) {
     using X = Bc7X<M>;
     using B = Bc7ModeBytes<M, NCAND>;
     const int n = S.nblk;
@@ -456,8 +493,8 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
     S.counters = counters + M * 64;
     arena += B::per_block * NVB_BC7_CHUNK;
     cudaStream_t st = ctx->mode_stream[M];
-    cudaStreamWaitEvent(st, ctx->ev_fork[parity], 0);
-    cudaMemsetAsync(S.counters, 0, NVB_BX_COUNTERS * sizeof(unsigned), st);
+    CK(cudaStreamWaitEvent(st, ctx->ev_fork[parity], 0));
+    CK(cudaMemsetAsync(S.counters, 0, NVB_BX_COUNTERS * sizeof(unsigned), st));
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7)
         NVB_LAUNCH_ON(ctx, st, K_BC7_ROUGH, units, k_bc7_rough<M>, grid_for(n, NVB_BC7_ROUGH_WARPS), NVB_BC7_ROUGH_WARPS * 32, S.P, S.blk0, S.blk0 + n);
     const unsigned cgrid = (unsigned)(((size_t)n * NCAND + 127) / 128);
@@ -469,7 +506,7 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
     }
     // searchers are handed out dynamically; ~2 per thread on small levels (tuned on B200), at most what the GPU can hold
     const size_t searchers = (size_t)n * (X::SPLIT ? 4 : NCAND * X::NR * X::NLSB);
-    static const int spt = getenv("NVB_BC7_SPT") ? atoi(getenv("NVB_BC7_SPT")) : 2;
+    static const int spt = env_int("NVB_BC7_SPT", 2);
     size_t sgrid = (searchers / spt + 127) / 128;
     if (sgrid > 148u * 6u) sgrid = 148u * 6u;
     if (sgrid < 1) sgrid = 1;
@@ -477,16 +514,18 @@ template <int M, int NCAND> static void launch_bc7_mode(NvttbContext *ctx, Bc7Se
     if constexpr (M == 0 || M == 1 || M == 2 || M == 3 || M == 7) NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search2<M>), (unsigned)sgrid, 128, S);
     else NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 0>), (unsigned)sgrid, 128, S);
     if constexpr (M == 4) {
-        cudaMemsetAsync(S.counters, 0, sizeof(unsigned), st);
+        CK(cudaMemsetAsync(S.counters, 0, sizeof(unsigned), st));
         NVB_LAUNCH_ON(ctx, st, K_BC7_SEARCH, units, (k_bc7_search<M, 1>), (unsigned)sgrid, 128, S);
     }
     NVB_LAUNCH_ON(ctx, st, K_BC7_FINISH, units, (k_bc7_finish<M, NCAND>), cgrid, 128, S);
-    cudaEventRecord(ctx->ev_join[parity][M], st);
+    CK(cudaEventRecord(ctx->ev_join[parity][M], st));
+    return NVTTB_OK;
 }
 
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
 // d_rgba points at row 0 of the rows to encode (h of them); plane = floats between the planes of the level they belong to
-static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out, size_t plane = 0) {
+struct CycView { int rpc, n, i; };  // LevelView::cyc_*: the rows are one GPU's concatenated chunks of a sharded level
+static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const float *d_rgba, int w, int h, unsigned char *d_out, size_t plane = 0, const CycView *cyc = nullptr) {
     if (!nvttb_format_supported(d->format, d->quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
     LevelView lv;
     lv.data = d_rgba;
@@ -496,6 +535,11 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     lv.bw = (w + 3) / 4;
     lv.bh = (h + 3) / 4;
     lv.to_gamma_table = d->applyToGamma ? ctx->d_to_gamma : nullptr;
+    if (cyc) {
+        lv.cyc_rpc = cyc->rpc;
+        lv.cyc_n = cyc->n;
+        lv.cyc_i = cyc->i;
+    }
     const int nb = lv.bw * lv.bh;
     auto alpha = [&](int channel, int stride, int offset, bool optimal) {
         AlphaBlocksParams P;
@@ -692,7 +736,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         const int padded = (nb + 127) / 128 * 128;
         // searchers are handed out dynamically, at most what the GPU holds (searchers per thread tuned on B200:
         // profiles/r1e_summary.md; NVB_BC6_SPT1/2 override for experiments).
-        static const int spt1 = getenv("NVB_BC6_SPT1") ? atoi(getenv("NVB_BC6_SPT1")) : 1, spt2 = getenv("NVB_BC6_SPT2") ? atoi(getenv("NVB_BC6_SPT2")) : 2;
+        static const int spt1 = env_int("NVB_BC6_SPT1", 1), spt2 = env_int("NVB_BC6_SPT2", 2);
         size_t g1 = ((size_t)nb / spt1 + 127) / 128, g2 = ((size_t)nb * 2 / spt2 + 127) / 128;
         if (g1 > 148u * 5u) g1 = 148u * 5u;
         if (g2 > 148u * 6u) g2 = 148u * 6u;
@@ -751,14 +795,14 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
                 for (int m = 0; m < 8; m++) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[parity][m], 0));
             NVB_LAUNCH(ctx, K_BC7_TILES, cu, k_bc7_tiles, (unsigned)((S.nblk * 16 + 255) / 256), 256, S, tiles);
             CK(cudaEventRecord(ctx->ev_fork[parity], ctx->stream));  // level, scratch and tiles are ready at this point of ctx->stream
-            launch_bc7_mode<6, 1>(ctx, S, arena, counters, parity, cu);  // few, very long searches: start them first
-            launch_bc7_mode<3, 16>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<7, 16>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<1, 16>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<0, 4>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<2, 16>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<4, 8>(ctx, S, arena, counters, parity, cu);
-            launch_bc7_mode<5, 4>(ctx, S, arena, counters, parity, cu);
+            if ((rc = launch_bc7_mode<6, 1>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;  // few, very long searches: start them first
+            if ((rc = launch_bc7_mode<3, 16>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<7, 16>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<1, 16>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<0, 4>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<2, 16>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<4, 8>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
+            if ((rc = launch_bc7_mode<5, 4>(ctx, S, arena, counters, parity, cu)) != NVTTB_OK) return rc;
         }
         // join: the last chunk of every mode stream (stream order covers the earlier ones)
         for (int m = 0; m < 8; m++) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[(nchunks - 1) & 1][m], 0));
@@ -1433,29 +1477,76 @@ int nvttb_process_mip_count(const NvttbProcessDesc *d) {
     return count;
 }
 
-// rows [*y0,*y1) of a w x h level that band (b of n) encodes; returns false when the band has nothing in this level
-static bool band_rows(int h, int b, int n, int *y0, int *y1) {
-    const int bh = (h + 3) / 4;
-    if (n <= 1) { *y0 = 0; *y1 = h; return true; }
-    if (bh % n == 0 && (h & 3) == 0) {
-        *y0 = (bh / n) * b * 4;
-        *y1 = (bh / n) * (b + 1) * 4;
-        return true;
+// ---- block-row sharding of one image (NvttbProcessDesc.band*) ---------------------------------------------------------------
+struct ShardGeom {
+    int N = 1, b = 0;  // bands, this band
+    int C = 0;         // level-0 texel rows per chunk; 0 = nothing can be distributed (band 0 encodes every level)
+    int K = 0;         // chunks per band
+};
+// false: not sharded
+static bool shard_geom(const NvttbProcessDesc *d, ShardGeom *g) {
+    *g = ShardGeom();
+    if (d->bandCount <= 1) return false;
+    g->N = d->bandCount;
+    g->b = d->bandIndex;
+    const int H = d->height;
+    const int C = d->bandChunkRows > 0 ? d->bandChunkRows : (H % d->bandCount == 0 ? H / d->bandCount : 0);
+    if (C <= 0 || (C & 3) != 0 || H % C != 0 || (H / C) % d->bandCount != 0) return true;
+    g->C = C;
+    g->K = H / C / d->bandCount;
+    return true;
+}
+// block rows of one chunk at level m (whose height is h); 0 = the level is not distributed
+static int level_rpc(const NvttbProcessDesc *d, const ShardGeom &g, int m, int h) {
+    if (g.C == 0 || m > 24) return 0;
+    const int q = 4 << m;
+    if (g.C % q != 0 || ((long long)h << m) != (long long)d->height) return 0;
+    return g.C / q;
+}
+static void level_extent(const NvttbProcessDesc *d, int level, int *w, int *h) {
+    int lw = d->width, lh = d->height;
+    for (int m = 0; m < level; m++) {
+        lw = lw / 2 > 1 ? lw / 2 : 1;
+        lh = lh / 2 > 1 ? lh / 2 : 1;
     }
-    *y0 = 0;
-    *y1 = h;
-    return b == 0;  // small / ragged levels: band 0 encodes the whole level
+    *w = lw;
+    *h = lh;
+}
+
+extern "C" int nvttb_process_band_slices(const NvttbProcessDesc *d, int level, size_t *offset, size_t *bytes, size_t *pitch, int *count) {
+    if (!d || !offset || !bytes || !pitch || !count || level < 0 || level >= nvttb_process_mip_count(d)) return NVTTB_ERR_INVALID_INPUT;
+    int w, h;
+    level_extent(d, level, &w, &h);
+    ShardGeom g;
+    *offset = 0;
+    *pitch = 0;
+    if (!shard_geom(d, &g)) {
+        *bytes = nvttb_level_size(d->encode.format, w, h);
+        *count = 1;
+        return NVTTB_OK;
+    }
+    const int rpc = level_rpc(d, g, level, h);
+    if (rpc == 0) {  // tail level: band 0 encodes all of it
+        *bytes = g.b == 0 ? nvttb_level_size(d->encode.format, w, h) : 0;
+        *count = g.b == 0 ? 1 : 0;
+        return NVTTB_OK;
+    }
+    const size_t row_bytes = (size_t)((w + 3) / 4) * block_bytes(d->encode.format);
+    *bytes = (size_t)rpc * row_bytes;
+    *pitch = (size_t)g.N * rpc * row_bytes;
+    *offset = (size_t)g.b * rpc * row_bytes;
+    *count = g.K;
+    return NVTTB_OK;
 }
 
 static size_t face_bytes(const NvttbProcessDesc *d) {
     const int mips = nvttb_process_mip_count(d);
     size_t total = 0;
-    int w = d->width, h = d->height;
     for (int m = 0; m < mips; m++) {
-        int y0, y1;
-        if (band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) total += nvttb_level_size(d->encode.format, w, y1 - y0);
-        w = w / 2 > 1 ? w / 2 : 1;
-        h = h / 2 > 1 ? h / 2 : 1;
+        size_t off, bytes, pitch;
+        int count;
+        nvttb_process_band_slices(d, m, &off, &bytes, &pitch, &count);
+        total += bytes * (size_t)count;
     }
     return total;
 }
@@ -1467,24 +1558,6 @@ static size_t whole_face_bytes(const NvttbProcessDesc *d) {
     return face_bytes(&t);
 }
 
-extern "C" int nvttb_process_band_slice(const NvttbProcessDesc *d, int level, size_t *offset, size_t *bytes) {
-    if (!d || !offset || !bytes || level < 0 || level >= nvttb_process_mip_count(d)) return NVTTB_ERR_INVALID_INPUT;
-    int w = d->width, h = d->height;
-    for (int m = 0; m < level; m++) {
-        w = w / 2 > 1 ? w / 2 : 1;
-        h = h / 2 > 1 ? h / 2 : 1;
-    }
-    int y0, y1;
-    if (!band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) {
-        *offset = 0;
-        *bytes = 0;
-        return NVTTB_OK;
-    }
-    *offset = (size_t)(y0 / 4) * ((w + 3) / 4) * block_bytes(d->encode.format);
-    *bytes = nvttb_level_size(d->encode.format, w, y1 - y0);
-    return NVTTB_OK;
-}
-
 size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
     if (!d) return 0;
     return face_bytes(d) * (size_t)(d->faceCount > 0 ? d->faceCount : 1);
@@ -1493,8 +1566,9 @@ size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
 // Runs faces [f0,f1) and leaves their encoded chains in d_out (face-major, mip-minor).
 // h_out (optional, pinned host memory of the same layout as d_out): finished pieces are copied back on d2h_stream while
 // the rest of the chain is still being computed; the caller synchronises d2h_stream.
+// in_place (sharded images only): d_out is the whole chain of the processed faces and the band's slices go to their final offsets.
 static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, int f0, int f1,
-                         unsigned char *d_out, unsigned char *h_out = nullptr) {
+                         unsigned char *d_out, unsigned char *h_out = nullptr, bool in_place = false) {
     const int mips = nvttb_process_mip_count(d);
     const size_t fbytes = face_bytes(d);
     const int W = d->width, H = d->height;
@@ -1521,7 +1595,8 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     // b+1 (h2d_stream) runs under the encode of band b (stream) and the D2H copy of band b's blocks (d2h_stream) under
     // everything that follows.  Needs the per-texel-only prologue (fused toLinear or none).
     const size_t bpp = input_bpp(d->inputFormat);
-    const bool sharded = d->bandCount > 1;
+    ShardGeom geom;
+    const bool sharded = shard_geom(d, &geom);
     const bool banded = !sharded && loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
     const int bhTotal = (H + 3) / 4;
     const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
@@ -1530,15 +1605,16 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     for (int f = f0; f < f1; f++) {
         unsigned char *out = d_out + (size_t)(f - f0) * fbytes;
         unsigned char *hout = h_out ? h_out + (size_t)(f - f0) * fbytes : nullptr;
-        // bandOutputInPlace: d_out is the whole chain of the processed faces
+        // in_place: d_out is the whole chain of the processed faces
         unsigned char *whole_face = d_out + (size_t)(f - f0) * whole_face_bytes(d);
         size_t level_off = 0;
         bool level0_done = false;
         if (banded) {
             if (!images[f]) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad input image");
             if ((rc = ensure(ctx, ctx->in_stage, (size_t)W * H * bpp)) != NVTTB_OK) { cleanup(); return rc; }
-            // the staging buffer is still being read by the previous face's conversion kernels
-            if (f > f0) CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
+            // the staging buffer may still be read by conversion kernels of the previous face or of an earlier call (an event
+            // that was never recorded is complete, so the wait is free the first time)
+            CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
             for (int b = 0; b < nbands; b++) {
                 const int y0 = b * bandBlockRows * 4, y1 = (b + 1) * bandBlockRows * 4 < H ? (b + 1) * bandBlockRows * 4 : H;
                 if (y0 >= y1) continue;
@@ -1568,7 +1644,8 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
             level0_done = true;
         } else {
-            // setImage (+ toLinear)
+            // setImage (+ toLinear).  The staging buffer is shared with the banded pipeline's copy stream.
+            if (loc == NVTTB_HOST) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
             if ((rc = set_image_device(ctx, d->inputFormat, W, H, images[f], loc, (float *)A.p, linFast)) != NVTTB_OK) { cleanup(); return rc; }
             if (colour && !linFast) {
                 if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
@@ -1616,19 +1693,17 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 src = (const float *)ctx->tmp_level.p;
             }
             if (sharded) {
-                // block-row sharding of one image: every band has the whole fp32 level, each encodes its own rows
-                int y0, y1;
-                if (band_rows(h, d->bandIndex, d->bandCount, &y0, &y1)) {
-                    e.height = y1 - y0;
-                    unsigned char *dst = out;
-                    if (d->bandOutputInPlace) {
-                        // final position of the slice inside the whole chain (possibly peer memory: the stores cross NVLink)
-                        size_t soff = 0, sbytes = 0;
-                        nvttb_process_band_slice(d, m, &soff, &sbytes);
-                        dst = whole_face + level_off + soff;
-                    }
-                    if ((rc = encode_device(ctx, &e, src + (size_t)y0 * w, w, y1 - y0, dst, (size_t)w * h)) != NVTTB_OK) { cleanup(); return rc; }
-                    out += nvttb_level_size(e.format, w, y1 - y0);
+                // every band has the whole fp32 level (replicated front end); each encodes the rows of its own chunks
+                size_t soff, sbytes, spitch;
+                int scount;
+                nvttb_process_band_slices(d, m, &soff, &sbytes, &spitch, &scount);
+                const int rpc = level_rpc(d, geom, m, h);
+                for (int j = 0; j < scount; j++) {
+                    const int y0 = rpc ? (j * geom.N + geom.b) * rpc * 4 : 0, rows = rpc ? rpc * 4 : h;
+                    e.height = rows;
+                    unsigned char *dst = in_place ? whole_face + level_off + soff + (size_t)j * spitch : out;
+                    if ((rc = encode_device(ctx, &e, src + (size_t)y0 * w, w, rows, dst, (size_t)w * h)) != NVTTB_OK) { cleanup(); return rc; }
+                    out += sbytes;
                 }
                 level_off += nvttb_level_size(e.format, w, h);
                 continue;
@@ -1638,7 +1713,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             }
             out += nvttb_level_size(e.format, w, h);
         }
-        if (hout) {
+        if (hout && !in_place) {
             // whatever of this face has not been sent yet: the mip tail (banded) or the whole chain
             const size_t done = level0_done ? nvttb_level_size(d->encode.format, W, H) : 0;
             if (fbytes > done) {
@@ -1653,10 +1728,211 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     return NVTTB_OK;
 }
 
+// ---- band-local front end of a sharded image ------------------------------------------------------------------------------------
+struct LocalPlan {
+    ShardGeom g;
+    int mips = 0;
+    int k = -1;  // last distributed level
+    int wk = 0, hk = 0;
+};
+// true when a band can build everything it encodes from its own chunks of the source image: 2x2 Box mips (a chunk of
+// 4 << k rows down-samples to whole block rows of levels 0..k without looking at its neighbours) and per-texel colour ops only
+static bool shard_local_plan(const NvttbProcessDesc *d, LocalPlan *p) {
+    *p = LocalPlan();
+    if (!shard_geom(d, &p->g) || p->g.C == 0) return false;
+    const bool toNormal = d->convertToNormalMap != 0;
+    const bool colour = !(d->isNormalMap || toNormal);
+    if (toNormal || d->mipmapFilter != MF_Box || d->alphaMode == AM_Transparency || input_bpp(d->inputFormat) == 0) return false;
+    if (colour && !(d->inputGamma == 2.2f || nv_equal(d->inputGamma, 1.0f))) return false;
+    if (colour && !(d->outputGamma == 2.2f || nv_equal(d->outputGamma, 1.0f))) return false;
+    p->mips = nvttb_process_mip_count(d);
+    int w = d->width, h = d->height;
+    for (int m = 0; m < p->mips; m++) {
+        if (level_rpc(d, p->g, m, h) == 0) break;
+        if (((long long)w << m) != (long long)d->width || (m > 0 && (w & 1) && w != 1)) return false;  // widths must halve exactly too
+        p->k = m;
+        p->wk = w;
+        p->hk = h;
+        w = w / 2 > 1 ? w / 2 : 1;
+        h = h / 2 > 1 ? h / 2 : 1;
+    }
+    return p->k >= 0;
+}
+
+extern "C" size_t nvttb_process_exchange_size(const NvttbProcessDesc *d) {
+    LocalPlan p;
+    if (!d || !shard_local_plan(d, &p)) return 0;
+    return (size_t)NVB_XCHG_HEADER + (size_t)2 * 4 * p.wk * p.hk * sizeof(float);
+}
+
+// One face of a sharded image on band g.b: upload / convert / down-sample the band's own chunks, hand the rows of level k to
+// band 0, encode the band's rows of levels 0..k; band 0 also runs the tail (levels k+1..) on tail_stream.
+// out: whole-face layout on the device (possibly a peer's memory); h_out: whole-face layout on the host, or null.
+static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, const LocalPlan &pl, const void *image, int loc,
+                               unsigned char *out, unsigned char *h_out) {
+    const ShardGeom &g = pl.g;
+    const int N = g.N, b = g.b, C = g.C, K = g.K, k = pl.k, mips = pl.mips;
+    const int W = d->width;
+    const size_t bpp = input_bpp(d->inputFormat);
+    const int HL = K * C;  // rows of the band's level 0 (its chunks concatenated)
+    if (!image) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad input image");
+    if (mips > NvttbContext::MAX_LEVELS) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "too many levels");
+    int rc;
+    size_t loff[NvttbContext::MAX_LEVELS], lvl_off[NvttbContext::MAX_LEVELS + 1], tot = 0;
+    for (int m = 0; m <= k; m++) {
+        loff[m] = tot;
+        tot += (size_t)4 * (W >> m) * (HL >> m);
+    }
+    lvl_off[0] = 0;
+    {
+        int w = W, h = d->height;
+        for (int m = 0; m < mips; m++) {
+            lvl_off[m + 1] = lvl_off[m] + nvttb_level_size(d->encode.format, w, h);
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+        }
+    }
+    if ((rc = ensure(ctx, ctx->lvlA, tot * sizeof(float))) != NVTTB_OK) return rc;
+    float *const chain = (float *)ctx->lvlA.p;
+    const bool isNormal = d->isNormalMap != 0;
+    const bool colour = !isNormal;
+    const bool linFast = colour && d->inputGamma == 2.2f;
+    const bool gamFast = colour && d->outputGamma == 2.2f;
+    const size_t bs = (size_t)block_bytes(d->encode.format);
+    const bool tail = k < mips - 1;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->tail_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+    };
+    NvttbEncodeDesc e = d->encode;
+    e.alphaMode = d->alphaMode;
+    e.applyToGamma = gamFast ? 1 : 0;
+    const bool host_in = loc == NVTTB_HOST;
+    const bool per_chunk_events = K <= NvttbContext::MAX_BANDS;
+    const size_t chunk_in = (size_t)C * W * bpp;
+    // 1. the band's chunks: upload (copy stream), convert and - for host input - encode level 0 chunk by chunk, so that
+    //    the copies of the following chunks hide under the encode
+    if (host_in) {
+        if ((rc = ensure(ctx, ctx->in_stage, (size_t)HL * W * bpp)) != NVTTB_OK) return rc;
+        CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
+        for (int j = 0; j < K; j++) {
+            const size_t c = (size_t)j * N + b;
+            CK(cudaMemcpyAsync((char *)ctx->in_stage.p + j * chunk_in, (const char *)image + c * chunk_in, chunk_in, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            if (per_chunk_events) CK(cudaEventRecord(ctx->ev_up[j], ctx->h2d_stream));
+        }
+        if (!per_chunk_events) CK(cudaEventRecord(ctx->ev_up[0], ctx->h2d_stream));
+    }
+    const int rpc0 = C / 4;
+    const size_t row_bytes0 = (size_t)((W + 3) / 4) * bs;
+    for (int j = 0; j < K; j++) {
+        const size_t c = (size_t)j * N + b;
+        if (host_in && (per_chunk_events || j == 0)) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[per_chunk_events ? j : 0], 0));
+        const char *src = host_in ? (const char *)ctx->in_stage.p + j * chunk_in : (const char *)image + c * chunk_in;
+        float *rows = chain + (size_t)j * C * W;
+        if ((rc = convert_device(ctx, d->inputFormat, src, (size_t)C * W, rows, (size_t)W * HL, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+        if (host_in) {
+            e.width = W;
+            e.height = C;
+            const size_t ooff = lvl_off[0] + c * rpc0 * row_bytes0;
+            if ((rc = encode_device(ctx, &e, rows, W, C, out + ooff, (size_t)W * HL)) != NVTTB_OK) { cleanup(); return rc; }
+            if (h_out) {
+                cudaEvent_t ev = per_chunk_events ? ctx->ev_enc[j] : ctx->ev_enc[0];
+                CK(cudaEventRecord(ev, ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
+                CK(cudaMemcpyAsync(h_out + ooff, out + ooff, (size_t)rpc0 * row_bytes0, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        }
+    }
+    if (host_in) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+    // 2. the band's rows of levels 1..k
+    for (int m = 1; m <= k; m++) {
+        float *lm = chain + loff[m];
+        if ((rc = next_mip_device(ctx, MF_Box, 0.5f, 0.0f, 0.0f, d->alphaMode, d->wrapMode, chain + loff[m - 1], W >> (m - 1), HL >> (m - 1), lm, W >> m, HL >> m)) != NVTTB_OK) { cleanup(); return rc; }
+        if (isNormal && d->normalizeMipmaps) {
+            NormalizeParams P{lm, (size_t)(W >> m) * (HL >> m), 1};
+            NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
+        }
+    }
+    // 3. rows of level k -> band 0 (peer stores), then the arrival flag
+    unsigned *xhdr = (unsigned *)d->bandExchange;
+    const unsigned seq = d->bandSequence;
+    float *ximg = tail ? (float *)((char *)d->bandExchange + NVB_XCHG_HEADER) + (size_t)(seq & 1u) * 4 * pl.wk * pl.hk : nullptr;
+    if (tail) {
+        // the buffer of this parity was last used by image seq - 2: band 0 must have finished reading it
+        if (seq >= 3) NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_wait, 1, 32, xhdr + NVB_XCHG_ACK, 1, seq - 2, ctx->h_fault);
+        ExportRowsParams X{chain + loff[k], ximg, pl.wk, HL >> k, pl.hk, C >> k, N, b};
+        NVB_LAUNCH(ctx, K_XCHG, (double)X.w * X.hl, k_export_rows, grid_for((size_t)4 * X.w * X.hl, 256), 256, X);
+        NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_signal, 1, 1, xhdr + b, seq);
+    }
+    // 4. band 0: the tail levels from the exchanged level, on the second stream with its own scratch
+    if (tail && b == 0) {
+        const int w1 = pl.wk / 2 > 1 ? pl.wk / 2 : 1, h1 = pl.hk / 2 > 1 ? pl.hk / 2 : 1;
+        const size_t lvl1 = (size_t)4 * w1 * h1;
+        if ((rc = ensure(ctx, ctx->tail_lvl, 2 * lvl1 * sizeof(float))) != NVTTB_OK) { cleanup(); return rc; }
+        std::swap(ctx->stream, ctx->tail_stream);
+        std::swap(ctx->enc_scratch, ctx->tail_scratch);
+        auto unswap = [&]() {
+            std::swap(ctx->stream, ctx->tail_stream);
+            std::swap(ctx->enc_scratch, ctx->tail_scratch);
+        };
+        NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_wait, 1, NVB_XCHG_FLAGS, xhdr, N, seq, ctx->h_fault);
+        const float *cur = ximg;
+        int w = pl.wk, h = pl.hk;
+        for (int m = k + 1; m < mips; m++) {
+            const int dw = w / 2 > 1 ? w / 2 : 1, dh = h / 2 > 1 ? h / 2 : 1;
+            float *nxt = (float *)ctx->tail_lvl.p + (size_t)((m - k - 1) & 1) * lvl1;
+            if ((rc = next_mip_device(ctx, MF_Box, 0.5f, 0.0f, 0.0f, d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh)) != NVTTB_OK) { unswap(); cleanup(); return rc; }
+            if (m == k + 1) NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_signal, 1, 1, xhdr + NVB_XCHG_ACK, seq);  // the exchanged level has been read
+            cur = nxt;
+            w = dw;
+            h = dh;
+            if (isNormal && d->normalizeMipmaps) {
+                NormalizeParams P{nxt, (size_t)w * h, 1};
+                NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
+            }
+            e.width = w;
+            e.height = h;
+            if ((rc = encode_device(ctx, &e, cur, w, h, out + lvl_off[m])) != NVTTB_OK) { unswap(); cleanup(); return rc; }
+        }
+        if (h_out) {
+            cudaError_t ce = cudaEventRecord(ctx->ev_tail, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_tail, 0);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_out + lvl_off[k + 1], out + lvl_off[k + 1], lvl_off[mips] - lvl_off[k + 1], cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            if (ce != cudaSuccess) { unswap(); cleanup(); return fail(ctx, NVTTB_ERR_CUDA, "tail copy", ce); }
+        }
+        cudaError_t ce = cudaEventRecord(ctx->ev_tail_done, ctx->stream);
+        unswap();
+        if (ce != cudaSuccess) { cleanup(); return fail(ctx, NVTTB_ERR_CUDA, "cudaEventRecord", ce); }
+    }
+    // 5. the band's rows of the distributed levels: one launch per level over the concatenated chunks
+    for (int m = host_in ? 1 : 0; m <= k; m++) {
+        const int w = W >> m, hl = HL >> m;
+        const int rpc = C / (4 << m);
+        const size_t row_bytes = (size_t)((w + 3) / 4) * bs;
+        e.width = w;
+        e.height = hl;
+        CycView cyc{rpc, N, b};
+        if ((rc = encode_device(ctx, &e, chain + loff[m], w, hl, out + lvl_off[m], 0, &cyc)) != NVTTB_OK) { cleanup(); return rc; }
+        if (h_out) {
+            CK(cudaEventRecord(ctx->ev_lvl[m], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_lvl[m], 0));
+            const size_t first = lvl_off[m] + (size_t)b * rpc * row_bytes, pitch = (size_t)N * rpc * row_bytes;
+            CK(cudaMemcpy2DAsync(h_out + first, pitch, out + first, pitch, (size_t)rpc * row_bytes, K, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+    }
+    if (tail && b == 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail_done, 0));
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+
 static int check_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int *f0, int *f1) {
     if (!ctx || !d || !images) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null argument");
     if (d->width <= 0 || d->height <= 0 || d->faceCount <= 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad extent");
     if (d->bandCount > 1 && (d->bandIndex < 0 || d->bandIndex >= d->bandCount)) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad band index");
+    if (d->bandCount > 1 && d->bandChunkRows < 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad band chunk rows");
+    if (d->firstFace < 0 || d->lastFace < 0 || (d->lastFace != 0 && d->lastFace < d->firstFace)) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bad face range");
     if (!nvttb_format_supported(d->encode.format, d->encode.quality)) return fail(ctx, NVTTB_ERR_UNSUPPORTED_FEATURE, "format/quality not implemented");
     *f0 = 0;
     *f1 = d->faceCount;
@@ -1679,6 +1955,7 @@ int nvttb_device_alloc(NvttbContext *ctx, size_t bytes, void **device_ptr) {
     if (!ctx || !device_ptr) return NVTTB_ERR_INVALID_INPUT;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMalloc(device_ptr, bytes));
+    CK(cudaMemset(*device_ptr, 0, bytes));  // exchange buffers start with all flags down
     return NVTTB_OK;
 }
 int nvttb_device_free(NvttbContext *ctx, void *device_ptr) {
@@ -1710,22 +1987,112 @@ int nvttb_ipc_close(NvttbContext *ctx, void *device_ptr) {
     CK(cudaIpcCloseMemHandle(device_ptr));
     return NVTTB_OK;
 }
+int nvttb_host_register(NvttbContext *ctx, void *host_ptr, size_t bytes) {
+    if (!ctx || !host_ptr || !bytes) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return NVTTB_OK;
+}
+int nvttb_host_unregister(NvttbContext *ctx, void *host_ptr) {
+    if (!ctx || !host_ptr) return NVTTB_ERR_INVALID_INPUT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(host_ptr));
+    return NVTTB_OK;
+}
 
+// Asynchronous on the context's stream when the images are on the device.  With HOST images the call returns once the
+// texels have been consumed (the caller may free them) - the encoded chain is complete after nvttb_synchronize.
 int nvttb_process_to_device(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, void *out_device,
                             size_t out_capacity, size_t *written) {
     int f0, f1, rc;
     if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t total = face_bytes(d) * (size_t)(f1 - f0);
-    if (total == 0) {
+    const bool in_place = d->bandCount > 1 && d->bandOutputInPlace;
+    if (total == 0 && !in_place) {
         if (written) *written = 0;
         return NVTTB_OK;
     }
-    const bool in_place = d->bandCount > 1 && d->bandOutputInPlace;
     const size_t need = in_place ? whole_face_bytes(d) * (size_t)(f1 - f0) : total;
     if (!out_device || out_capacity < need) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "output buffer too small");
-    if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)out_device)) != NVTTB_OK) return rc;
+    LocalPlan pl;
+    if (in_place && d->bandExchange && f1 - f0 == 1 && shard_local_plan(d, &pl)) {
+        if (d->bandSequence == 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bandSequence must start at 1");
+        rc = process_shard_local(ctx, d, pl, images[f0], loc, (unsigned char *)out_device, nullptr);
+    } else {
+        rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)out_device, nullptr, in_place);
+    }
+    if (rc != NVTTB_OK) return rc;
+    if (loc == NVTTB_HOST) {
+        CK(cudaStreamSynchronize(ctx->h2d_stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (written) *written = total;
+    return NVTTB_OK;
+}
+
+int nvttb_process_shard(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, void *out_device, void *out_host) {
+    int f0, f1, rc;
+    if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
+    if (d->bandCount <= 1) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "nvttb_process_shard needs bandCount > 1");
+    CK(cudaSetDevice(ctx->device));
+    const size_t wbytes = whole_face_bytes(d), need = wbytes * (size_t)(f1 - f0);
+    unsigned char *out = (unsigned char *)out_device;
+    if (!out) {
+        if ((rc = ensure(ctx, ctx->out_dev, need)) != NVTTB_OK) return rc;
+        out = (unsigned char *)ctx->out_dev.p;
+    }
+    LocalPlan pl;
+    if (d->bandExchange && f1 - f0 == 1 && shard_local_plan(d, &pl)) {
+        if (d->bandSequence == 0) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bandSequence must start at 1");
+        if ((rc = process_shard_local(ctx, d, pl, images[f0], loc, out, (unsigned char *)out_host)) != NVTTB_OK) return rc;
+    } else {
+        if ((rc = process_faces(ctx, d, images, loc, f0, f1, out, nullptr, true)) != NVTTB_OK) return rc;
+        if (out_host) {
+            const int mips = nvttb_process_mip_count(d);
+            for (int f = f0; f < f1; f++) {
+                size_t lo = (size_t)(f - f0) * wbytes;
+                int w = d->width, h = d->height;
+                for (int m = 0; m < mips; m++) {
+                    size_t off, bytes, pitch;
+                    int count;
+                    nvttb_process_band_slices(d, m, &off, &bytes, &pitch, &count);
+                    if (count == 1) CK(cudaMemcpyAsync((char *)out_host + lo + off, out + lo + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                    else if (count > 1) CK(cudaMemcpy2DAsync((char *)out_host + lo + off, pitch, out + lo + off, pitch, bytes, count, cudaMemcpyDeviceToHost, ctx->stream));
+                    lo += nvttb_level_size(d->encode.format, w, h);
+                    w = w / 2 > 1 ? w / 2 : 1;
+                    h = h / 2 > 1 ? h / 2 : 1;
+                }
+            }
+        }
+    }
+    if (out_host || loc == NVTTB_HOST) {
+        CK(cudaStreamSynchronize(ctx->h2d_stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->d2h_stream));
+        if (*ctx->h_fault) {
+            *ctx->h_fault = 0;
+            return fail(ctx, NVTTB_ERR_CUDA, "sharded image: a band never delivered its rows (device-side wait timed out)");
+        }
+    }
+    return NVTTB_OK;
+}
+
+static int emit_chain(NvttbContext *ctx, const NvttbProcessDesc *d, int f0, int f1, const unsigned char *p, NvttbEmitFn emit, void *user) {
+    const int mips = nvttb_process_mip_count(d);
+    for (int f = f0; f < f1; f++) {
+        int w = d->width, h = d->height;
+        for (int m = 0; m < mips; m++) {
+            size_t off, bytes, pitch;
+            int count;
+            nvttb_process_band_slices(d, m, &off, &bytes, &pitch, &count);
+            const size_t sz = bytes * (size_t)count;
+            if (sz != 0 && !emit(user, f, m, w, h, 1, p, sz)) return fail(ctx, NVTTB_ERR_FILE_WRITE, "emit callback asked to stop");
+            p += sz;
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+        }
+    }
     return NVTTB_OK;
 }
 
@@ -1733,6 +2100,8 @@ int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *cons
     int f0, f1, rc;
     if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
     if (!emit) return fail(ctx, NVTTB_ERR_FILE_OPEN, "no output handler");
+    // the emit path owns a buffer of this band's bytes only: in-place (whole-chain) output is nvttb_process_to_device / _shard
+    if (d->bandCount > 1 && d->bandOutputInPlace) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "bandOutputInPlace needs nvttb_process_to_device or nvttb_process_shard");
     CK(cudaSetDevice(ctx->device));
     const size_t fbytes = face_bytes(d);
     const size_t total = fbytes * (size_t)(f1 - f0);
@@ -1742,20 +2111,110 @@ int nvttb_process(NvttbContext *ctx, const NvttbProcessDesc *d, const void *cons
     if ((rc = process_faces(ctx, d, images, loc, f0, f1, (unsigned char *)ctx->out_dev.p, (unsigned char *)ctx->h_out)) != NVTTB_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->d2h_stream));
-    const int mips = nvttb_process_mip_count(d);
-    const unsigned char *p = (const unsigned char *)ctx->h_out;
-    for (int f = f0; f < f1; f++) {
-        int w = d->width, h = d->height;
-        for (int m = 0; m < mips; m++) {
-            size_t sz = nvttb_level_size(d->encode.format, w, h), off = 0;
-            if (d->bandCount > 1) nvttb_process_band_slice(d, m, &off, &sz);
-            if (sz != 0 && !emit(user, f, m, w, h, 1, p, sz)) return fail(ctx, NVTTB_ERR_FILE_WRITE, "emit callback asked to stop");
-            p += sz;
-            w = w / 2 > 1 ? w / 2 : 1;
-            h = h / 2 > 1 ? h / 2 : 1;
+    return emit_chain(ctx, d, f0, f1, (const unsigned char *)ctx->h_out, emit, user);
+}
+
+// ---- several GPUs, one process ------------------------------------------------------------------------------------------------
+// level-0 rows per chunk for n bands: 4 * 2^j with whole chunks, the same number per band, and about four chunks per band
+static int auto_chunk_rows(int H, int n) {
+    int best = 0;
+    for (int C = 4; C <= H; C <<= 1) {
+        if (H % C != 0 || (H / C) % n != 0) continue;
+        best = C;
+        if (H / C / n <= 4) break;
+    }
+    return best;
+}
+
+int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc *d, const void *const *images, NvttbEmitFn emit, void *user) {
+    if (!ctxs || n <= 0 || !ctxs[0]) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = ctxs[0];
+    for (int i = 1; i < n; i++)
+        if (!ctxs[i]) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "null context");
+    if (n == 1 || !d || d->bandCount > 1) return nvttb_process(ctx, d, images, NVTTB_HOST, emit, user);
+    int f0, f1, rc;
+    if ((rc = check_process(ctx, d, images, &f0, &f1)) != NVTTB_OK) return rc;
+    if (!emit) return fail(ctx, NVTTB_ERR_FILE_OPEN, "no output handler");
+    const int faces = f1 - f0;
+    const size_t wbytes = whole_face_bytes(d), total = wbytes * (size_t)faces;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_pinned(ctx, total)) != NVTTB_OK) return rc;
+    unsigned char *const h_out = (unsigned char *)ctx->h_out;
+    std::vector<int> rcs(n, NVTTB_OK);
+    if (faces >= n || (size_t)d->width * d->height < ((size_t)1 << 20)) {
+        // independent faces / array slices (or images too small to cut): deal them out, each GPU copies its chains home
+        const int users = faces < n ? faces : n;
+        std::vector<std::thread> th;
+        for (int t = 0; t < users; t++) {
+            th.emplace_back([&, t]() {
+                NvttbContext *c = ctxs[t];
+                const int lo = f0 + (int)((long long)faces * t / users), hi = f0 + (int)((long long)faces * (t + 1) / users);
+                if (hi <= lo) return;
+                int r = cudaSetDevice(c->device) == cudaSuccess ? NVTTB_OK : NVTTB_ERR_CUDA;
+                if (r == NVTTB_OK) r = ensure(c, c->out_dev, wbytes * (size_t)(hi - lo));
+                if (r == NVTTB_OK) r = process_faces(c, d, images, NVTTB_HOST, lo, hi, (unsigned char *)c->out_dev.p, h_out + (size_t)(lo - f0) * wbytes);
+                if (r == NVTTB_OK && (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaStreamSynchronize(c->d2h_stream) != cudaSuccess)) r = NVTTB_ERR_CUDA;
+                rcs[t] = r;
+            });
+        }
+        for (auto &x : th) x.join();
+    } else {
+        // one large image at a time, block-row sharded over the largest number of GPUs that divides it evenly
+        int bands = n, C = 0;
+        for (; bands > 1; bands--)
+            if ((C = auto_chunk_rows(d->height, bands)) != 0) break;
+        if (bands <= 1) return nvttb_process(ctx, d, images, NVTTB_HOST, emit, user);
+        NvttbProcessDesc base = *d;
+        base.bandCount = bands;
+        base.bandChunkRows = C;
+        base.bandOutputInPlace = 1;
+        base.bandExchange = nullptr;
+        // band-local front end: needs the exchange buffer on GPU 0 and peer access to it from the others
+        bool peers = true;
+        for (int t = 1; t < bands && peers; t++) {
+            int can = 0;
+            if (ctxs[t]->device == ctx->device) continue;  // several contexts on one GPU (tests): plain device memory
+            if (cudaDeviceCanAccessPeer(&can, ctxs[t]->device, ctx->device) != cudaSuccess || !can) peers = false;
+            if (peers) {
+                cudaSetDevice(ctxs[t]->device);
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) peers = false;
+                cudaGetLastError();
+            }
+        }
+        CK(cudaSetDevice(ctx->device));
+        const size_t xbytes = nvttb_process_exchange_size(&base);
+        if (peers && xbytes) {
+            if (ctx->exchange.cap < xbytes) {
+                if ((rc = ensure(ctx, ctx->exchange, xbytes)) != NVTTB_OK) return rc;
+                CK(cudaMemset(ctx->exchange.p, 0, xbytes));
+                ctx->multi_seq = 0;
+            }
+            base.bandExchange = ctx->exchange.p;
+        }
+        for (int f = f0; f < f1; f++) {
+            base.firstFace = f;
+            base.lastFace = f + 1;
+            base.bandSequence = ++ctx->multi_seq;
+            std::vector<std::thread> th;
+            for (int t = 0; t < bands; t++) {
+                th.emplace_back([&, t]() {
+                    NvttbProcessDesc mine = base;
+                    mine.bandIndex = t;
+                    rcs[t] = nvttb_process_shard(ctxs[t], &mine, images, NVTTB_HOST, nullptr, h_out + (size_t)(f - f0) * wbytes);
+                });
+            }
+            for (auto &x : th) x.join();
+            for (int t = 0; t < bands; t++)
+                if (rcs[t] != NVTTB_OK) break;
         }
     }
-    return NVTTB_OK;
+    for (int t = 0; t < n; t++)
+        if (rcs[t] != NVTTB_OK) {
+            if (t != 0) ctx->err = std::string("GPU ") + std::to_string(ctxs[t]->device) + ": " + ctxs[t]->err;
+            return rcs[t];
+        }
+    return emit_chain(ctx, d, f0, f1, h_out, emit, user);
 }
 
 }  // extern "C"

@@ -470,7 +470,7 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
         const float weight_sum = group_ordered_sum(gm, wt);
         wt = (weight_sum == 0) ? 1.0f : wt * M;
     }
-    unsigned char *dst = P.out + (size_t)blkid * P.out_stride + P.out_offset;
+    unsigned char *dst = P.out + nvb_out_block(P.lv, blkid) * P.out_stride + P.out_offset;
     Bc1Block out;
     out.c0 = out.c1 = out.indices = 0;
     float error = FLT_MAX;

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128) k_dxt1_quick(Dxt1QuickParams P) {
             c1 = k0;
             indices = quick_indices3(block, maxc, minc);
         }
-        *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) = make_uint2(c0 | (c1 << 16), indices);
+        *reinterpret_cast<uint2 *>(P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset) = make_uint2(c0 | (c1 << 16), indices);
     }
 }
 

@@ -235,7 +235,7 @@ template <bool DXT1A> NVB_DEV void bc3_color_body(const Bc3ColorParams &P) {
     const int n = __popc(uniq);
     const int myPoint = (first >= 0) ? __popc(uniq & ((1u << first) - 1u)) : 0;  // m_remap[l]
 
-    unsigned char *dst = P.out + (size_t)blk * P.out_stride + P.out_offset;
+    unsigned char *dst = P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset;
 
     if (DXT1A) {
         // CompressorDXT1a: rgba.isSingleColor() looks at the RGB of all 16 texels, transparent ones included

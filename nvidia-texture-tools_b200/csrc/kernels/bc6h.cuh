@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(256) k_bc6_select(Bc6Params P) {
     for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += gridDim.x * blockDim.x) {
         const float e1 = P.cand_err[(size_t)blk * 2], e2 = P.cand_err[(size_t)blk * 2 + 1];
         const int kind = (e1 <= e2) ? 0 : 1;  // ZOH::compress: mseone <= msetwo keeps the one-region block
-        *reinterpret_cast<uint4 *>(P.out + (size_t)blk * 16) = *reinterpret_cast<const uint4 *>(P.cand + ((size_t)blk * 2 + kind) * 16);
+        *reinterpret_cast<uint4 *>(P.out + nvb_out_block(P.lv, blk) * 16) = *reinterpret_cast<const uint4 *>(P.cand + ((size_t)blk * 2 + kind) * 16);
     }
 }
 

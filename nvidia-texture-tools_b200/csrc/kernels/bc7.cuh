@@ -1090,7 +1090,7 @@ __global__ void __launch_bounds__(256) k_bc7_select(Bc7Params P) {
         }
         uint4 v = make_uint4(0, 0, 0, 0);
         if (bm >= 0) v = *reinterpret_cast<const uint4 *>(P.cand + ((size_t)bm * nblocks + blk) * 16);
-        *reinterpret_cast<uint4 *>(P.out + (size_t)blk * 16) = v;
+        *reinterpret_cast<uint4 *>(P.out + nvb_out_block(P.lv, blk) * 16) = v;
     }
 }
 

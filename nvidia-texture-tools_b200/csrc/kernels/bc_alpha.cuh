@@ -164,7 +164,8 @@ NVB_DEV void alpha_gather_block(const LevelView &lv, int channel, int bx, int by
     const int x0 = bx * 4, y0 = by * 4;
     const float *plane = lv.data + (size_t)channel * lv.plane;
     const bool gam = (lv.to_gamma_table != nullptr && channel < 3);
-    if (x0 + 4 <= lv.w && y0 + 4 <= lv.h && (lv.w & 3) == 0) {
+    // 128-bit row loads need 16-byte aligned rows: width a multiple of 4 and an aligned plane (callers may pass any device pointer)
+    if (x0 + 4 <= lv.w && y0 + 4 <= lv.h && (lv.w & 3) == 0 && ((size_t)plane & 15) == 0) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const float4 v = *reinterpret_cast<const float4 *>(plane + (size_t)(y0 + i) * lv.w + x0);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(128) k_alpha_blocks(AlphaBlocksParams P) {
                 done = ++it >= 8;
             }
             if (done) {
-                *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+                *reinterpret_cast<uint2 *>(P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset) =
                     make_uint2((unsigned)(best & 0xFFFFFFFFu), (unsigned)(best >> 32));
                 blk += stride;
                 have = false;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(128) k_alpha_optimal(AlphaBlocksParams P) {
         if (lane == 0) {
             unsigned long long b = ((unsigned long long)a1 << 8) | a0;
             alpha_compute_indices(src, a0, a1, &b);
-            *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+            *reinterpret_cast<uint2 *>(P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset) =
                 make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
         }
     }
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(128) k_alpha_dxt3(AlphaBlocksParams P) {
         unsigned long long b = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) b |= (unsigned long long)alpha_quantize4(src[i]) << (4 * i);
-        *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) =
+        *reinterpret_cast<uint2 *>(P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset) =
             make_uint2((unsigned)(b & 0xFFFFFFFFu), (unsigned)(b >> 32));
     }
 }
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(128) k_dxt1g_optimal(AlphaBlocksParams P) {
             }
         }
         if (lane == 0)
-            *reinterpret_cast<uint2 *>(P.out + (size_t)blk * P.out_stride + P.out_offset) = make_uint2(c0 | (c1 << 16), indices);
+            *reinterpret_cast<uint2 *>(P.out + nvb_out_block(P.lv, blk) * P.out_stride + P.out_offset) = make_uint2(c0 | (c1 << 16), indices);
     }
 }
 
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(128) k_rgbm_alpha(RgbmAlphaParams P) {
     const int warps_per_cta = blockDim.x >> 5;
     const int nblocks = P.lv.bw * P.lv.bh;
     for (int blk = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); blk < nblocks; blk += gridDim.x * warps_per_cta) {
-        unsigned char *dst = P.out + (size_t)blk * 16;
+        unsigned char *dst = P.out + nvb_out_block(P.lv, blk) * 16;
         // colour block -> 8-bit palette (BlockDXT1::evaluatePalette, D3D10)
         const uint2 cb = *reinterpret_cast<const uint2 *>(dst + 8);
         const unsigned c0 = cb.x & 0xFFFFu, c1 = cb.x >> 16;

@@ -158,7 +158,18 @@ struct LevelView {
     int w, h;
     int bw, bh;                   // blocks per row / column = (w+3)/4, (h+3)/4
     const float *to_gamma_table;  // non-null => apply powf_5_11 to R,G,B while loading (fused Surface::toGamma)
+    // Block-row sharding of one image over several GPUs: this view is the concatenation of one GPU's row chunks; chunk j
+    // (cyc_rpc block rows of the view) is chunk j * cyc_n + cyc_i of the whole level.  cyc_rpc == 0: the view is the level.
+    int cyc_rpc = 0, cyc_n = 1, cyc_i = 0;
 };
+
+// index of block `blk` of the view (row-major) inside the whole level's output
+NVB_DEV size_t nvb_out_block(const LevelView &lv, int blk) {
+    if (lv.cyc_rpc == 0) return (size_t)blk;
+    const int by = blk / lv.bw, bx = blk - by * lv.bw;
+    const int c = by / lv.cyc_rpc, r = by - c * lv.cyc_rpc;
+    return (size_t)((c * lv.cyc_n + lv.cyc_i) * lv.cyc_rpc + r) * lv.bw + bx;
+}
 
 NVB_DEV float load_texel(const LevelView &lv, int c, int x, int y) {
     float v = lv.data[(size_t)c * lv.plane + (size_t)y * lv.w + x];

@@ -35,38 +35,52 @@ def gather_bytes(mine, dst=0):
 
 
 def band_layout(lib, desc, world):
-    """Per mip level and band: (offset, bytes) of the band's slice inside the level (nvttb_process_band_slice), for
-    block-row sharding of ONE image over `world` GPUs.  desc.bandCount must equal world."""
+    """Per mip level and band: (offset, bytes, pitch, count) of the band's slices inside the level
+    (nvttb_process_band_slices), for block-row sharding of ONE image over `world` GPUs (desc.bandChunkRows selects
+    contiguous bands or cyclic chunks)."""
     import ctypes as C
-    import copy
     mips = lib.nvttb_process_mip_count(C.byref(desc))
     out = []
     for m in range(mips):
         row = []
         for b in range(world):
-            d = copy.copy(desc)
+            d = type(desc).from_buffer_copy(desc)
             d.bandIndex, d.bandCount = b, world
-            off, n = C.c_size_t(0), C.c_size_t(0)
-            lib.nvttb_process_band_slice(C.byref(d), m, C.byref(off), C.byref(n))
-            row.append((off.value, n.value))
+            off, n, pitch, cnt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+            rc = lib.nvttb_process_band_slices(C.byref(d), m, C.byref(off), C.byref(n), C.byref(pitch), C.byref(cnt))
+            assert rc == 0, rc
+            row.append((off.value, n.value, pitch.value, cnt.value))
         out.append(row)
     return out
 
 
 def assemble_bands(layout, per_band_bytes):
     """per_band_bytes[b] = the bytes band b produced (its slices of every level, concatenated).  Returns the whole
-    mip chain (levels in order, each level = its band slices in band order) exactly as a single GPU would emit it."""
+    mip chain (levels in order) exactly as a single GPU would emit it."""
     cur = [0] * len(per_band_bytes)
     levels = []
     for row in layout:
-        size = max(off + n for off, n in row)
+        size = max((off + (cnt - 1) * pitch + n) for off, n, pitch, cnt in row if cnt)
         lvl = np.zeros(size, np.uint8)
-        for b, (off, n) in enumerate(row):
-            if n:
-                lvl[off:off + n] = per_band_bytes[b][cur[b]:cur[b] + n]
+        for b, (off, n, pitch, cnt) in enumerate(row):
+            for j in range(cnt):
+                lvl[off + j * pitch:off + j * pitch + n] = per_band_bytes[b][cur[b]:cur[b] + n]
                 cur[b] += n
         levels.append(lvl)
     return np.concatenate(levels)
+
+
+def auto_chunk_rows(height, world):
+    """Level-0 rows per chunk for cyclic block-row sharding: 4 * 2^j, whole chunks, the same number per band, about four
+    chunks per band (mirrors auto_chunk_rows in csrc/capi.cu).  0: the height cannot be dealt out evenly."""
+    best, c = 0, 4
+    while c <= height:
+        if height % c == 0 and (height // c) % world == 0:
+            best = c
+            if height // c // world <= 4:
+                break
+        c <<= 1
+    return best
 
 
 class SharedOutput:

@@ -402,7 +402,7 @@ def test_block_row_sharding_of_one_image(nvtt, ref, ctx):
         assert np.array_equal(shared.cpu().numpy(), whole), (w, h, fmt_name, world, "in place")
         # the big levels really are split: no band carries the whole level 0 when it divides
         if (h // 4) % world == 0 and h % 4 == 0:
-            assert all(n == layout[0][0][1] for _, n in layout[0]) and layout[0][0][1] * world == ((w + 3) // 4) * (h // 4) * (8 if fmt_name == "BC1" else 16)
+            assert all(n == layout[0][0][1] for _, n, _, _ in layout[0]) and layout[0][0][1] * world == ((w + 3) // 4) * (h // 4) * (8 if fmt_name == "BC1" else 16)
 
 
 def test_bc3_rgbm_bit_exact(nvtt, ref, ctx):

@@ -49,29 +49,38 @@ def _band_worker(rank, world, port, q):
     import oracleapi
     m = nvtt_b200_loader.load()
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-    w, h = 64, 32
-    img = m.synth.photo_bgra8(w, h, seed=9, alpha=True)
-    d = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=rank, band_count=world)
-    layout = m.sharding.band_layout(m.lib(), d, world)
-    # stand-in for this rank's GPU encode of its block rows (no GPU here): the oracle's whole chain, cut by the contract
-    whole = oracleapi.process([img], 0, w, h, 1, 1, mip_filter=0)
-    mine, base = [], 0
-    for row in layout:
-        off, n = row[rank]
-        mine.append(whole[base + off:base + off + n])
-        base += max(o + k for o, k in row)
-    mine = np.concatenate(mine) if mine else np.zeros(0, np.uint8)
-    sizes_ok = mine.size == int(m.lib().nvttb_process_output_size(d))
-    allb = m.sharding.gather_bytes(mine, dst=0)
+    ok = True
+    # contiguous bands (bandChunkRows = 0) and cyclic chunks of 8 level-0 rows (chunk c belongs to band c % world)
+    for w, h, chunk in ((64, 32, 0), (64, 32, 8), (40, 48, 4)):
+        img = m.synth.photo_bgra8(w, h, seed=9, alpha=True)
+        d = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=rank, band_count=world, band_chunk_rows=chunk)
+        layout = m.sharding.band_layout(m.lib(), d, world)
+        # stand-in for this rank's GPU encode of its block rows (no GPU here): the oracle's whole chain, cut by the contract
+        whole = oracleapi.process([img], 0, w, h, 1, 1, mip_filter=0)
+        mine, base = [], 0
+        for row in layout:
+            off, n, pitch, cnt = row[rank]
+            for j in range(cnt):
+                mine.append(whole[base + off + j * pitch:base + off + j * pitch + n])
+            base += max(o + (c - 1) * p + k for o, k, p, c in row if c)
+        mine = np.concatenate(mine) if mine else np.zeros(0, np.uint8)
+        sizes_ok = mine.size == int(m.lib().nvttb_process_output_size(d))
+        allb = m.sharding.gather_bytes(mine, dst=0)
+        if rank == 0:
+            per_band, p = [], 0
+            for b in range(world):
+                db = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=b, band_count=world, band_chunk_rows=chunk)
+                n = int(m.lib().nvttb_process_output_size(db))
+                per_band.append(allb[p:p + n])
+                p += n
+            got = m.sharding.assemble_bands(layout, per_band)
+            ok = ok and bool(sizes_ok and np.array_equal(got, whole))
+            # every block row of every level belongs to exactly one band
+            for row in layout:
+                covered = sorted((o + j * pt, o + j * pt + k) for o, k, pt, c in row for j in range(c))
+                ok = ok and covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
     if rank == 0:
-        per_band, p = [], 0
-        for b in range(world):
-            db = m.make_process_desc(0, w, h, 1, 1, mip_filter=0, band_index=b, band_count=world)
-            n = int(m.lib().nvttb_process_output_size(db))
-            per_band.append(allb[p:p + n])
-            p += n
-        got = m.sharding.assemble_bands(layout, per_band)
-        q.put(bool(sizes_ok and np.array_equal(got, whole)))
+        q.put(ok)
     dist.barrier()
     dist.destroy_process_group()
 
