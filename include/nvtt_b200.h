@@ -141,6 +141,17 @@ NVTTB_API int nvttb_surface_resize(NvttbSurface *s, int w, int h, int resizeFilt
 NVTTB_API int nvttb_surface_expand_normals(NvttbSurface *s);
 NVTTB_API int nvttb_surface_normalize_normal_map(NvttbSurface *s);
 NVTTB_API int nvttb_surface_pack_normals(NvttbSurface *s);
+/* Surface::scaleBias(channel, scale, bias) for `count` consecutive channels -> FloatImage::scaleBias (src/nvtt/Surface.cpp:1669-1677,
+ * src/nvimage/FloatImage.cpp:231-242); packNormals / expandNormals with caller-chosen values are scaleBias(0, 3, ...). */
+NVTTB_API int nvttb_surface_scale_bias(NvttbSurface *s, int channel, int count, float scale, float bias);
+/* Surface::clamp(channel, low, high)  src/nvtt/Surface.cpp:1679-1686 */
+NVTTB_API int nvttb_surface_clamp(NvttbSurface *s, int channel, float low, float high);
+/* Surface::range(channel, &min, &max, alpha_channel, alpha_ref)  src/nvtt/Surface.cpp:526-566 (alpha_channel < 0: no alpha test) */
+NVTTB_API int nvttb_surface_range(const NvttbSurface *s, int channel, int alpha_channel, float alpha_ref, float *range_min, float *range_max);
+/* Surface::toneMap(ToneMapper, params)  src/nvtt/Surface.cpp:2444-2494 (0 Linear, 1 Reindhart, 2 Halo, 3 Lightmap) */
+NVTTB_API int nvttb_surface_tone_map(NvttbSurface *s, int toneMapper);
+/* Surface::toRGBM(range, threshold)  src/nvtt/Surface.cpp:1862-1946 */
+NVTTB_API int nvttb_surface_to_rgbm(NvttbSurface *s, float range, float threshold);
 /* Surface::binarize(channel, threshold, dither) and Surface::quantize(channel, bits, exactEndPoints, dither)
  * src/nvtt/Surface.cpp:2656-2775.  dither != 0 = the reference's Floyd-Steinberg scan (bit-identical: a skewed wavefront on
  * one SM per plane, so it is slow next to everything else here - use it the way the reference does, for final output). */

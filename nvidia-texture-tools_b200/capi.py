@@ -85,6 +85,7 @@ EXPORTS = [
     "nvttb_surface_set_image", "nvttb_surface_to_linear", "nvttb_surface_to_gamma", "nvttb_surface_build_next_mipmap",
     "nvttb_surface_resize", "nvttb_surface_expand_normals", "nvttb_surface_normalize_normal_map",
     "nvttb_surface_pack_normals", "nvttb_surface_to_grey_scale", "nvttb_surface_to_normal_map",
+    "nvttb_surface_scale_bias", "nvttb_surface_clamp", "nvttb_surface_range", "nvttb_surface_tone_map", "nvttb_surface_to_rgbm",
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slices",
@@ -134,6 +135,11 @@ def lib():
     L.nvttb_surface_height.argtypes = [vp]
     L.nvttb_surface_set_image.argtypes = [vp, ci, ci, ci, vp, ci]
     L.nvttb_surface_set_image_2d.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci]
+    L.nvttb_surface_scale_bias.argtypes = [vp, ci, ci, cf, cf]
+    L.nvttb_surface_clamp.argtypes = [vp, ci, cf, cf]
+    L.nvttb_surface_range.argtypes = [vp, ci, ci, cf, C.POINTER(cf), C.POINTER(cf)]
+    L.nvttb_surface_tone_map.argtypes = [vp, ci]
+    L.nvttb_surface_to_rgbm.argtypes = [vp, cf, cf]
     L.nvttb_surface_binarize.argtypes = [vp, ci, cf, ci]
     L.nvttb_surface_quantize.argtypes = [vp, ci, ci, ci, ci]
     L.nvttb_rms_error.argtypes = [vp, vp, C.POINTER(cf)]

@@ -1360,6 +1360,76 @@ static int scale_bias(NvttbSurface *s, float scale, float bias) {
 }
 int nvttb_surface_expand_normals(NvttbSurface *s) { return s ? scale_bias(s, 2.0f, -1.0f) : NVTTB_ERR_INVALID_INPUT; }
 int nvttb_surface_pack_normals(NvttbSurface *s) { return s ? scale_bias(s, 0.5f, 0.5f) : NVTTB_ERR_INVALID_INPUT; }
+int nvttb_surface_scale_bias(NvttbSurface *s, int channel, int count, float scale, float bias) {
+    if (!s || channel < 0 || count < 1 || channel + count > 4) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)s->w * s->h;
+    ScaleBiasParams P{(float *)s->buf.p + (size_t)channel * n, (size_t)count * n, scale, bias};
+    NVB_LAUNCH(ctx, K_SCALE_BIAS, (double)n, k_scale_bias, grid_for(P.count, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+int nvttb_surface_clamp(NvttbSurface *s, int channel, float low, float high) {
+    if (!s || channel < 0 || channel > 3) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)s->w * s->h;
+    ClampParams P{(float *)s->buf.p + (size_t)channel * n, n, low, high};
+    NVB_LAUNCH(ctx, K_SCALE_BIAS, (double)n, k_clamp, grid_for(n, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+int nvttb_surface_range(const NvttbSurface *s, int channel, int alpha_channel, float alpha_ref, float *range_min, float *range_max) {
+    if (!s || channel < 0 || channel > 3 || alpha_channel > 3) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    if (s->buf.p) {
+        CK(cudaSetDevice(ctx->device));
+        const size_t n = (size_t)s->w * s->h;
+        const unsigned grid = grid_for(n, 256);
+        int rc = ensure(ctx, ctx->tmp_filter, (size_t)grid * sizeof(float2));
+        if (rc != NVTTB_OK) return rc;
+        RangeParams P{(const float *)s->buf.p + (size_t)channel * n, alpha_channel >= 0 ? (const float *)s->buf.p + (size_t)alpha_channel * n : nullptr,
+                      n, alpha_ref, (float2 *)ctx->tmp_filter.p};
+        NVB_LAUNCH(ctx, K_ERROR_METRIC, (double)n, k_range, grid, 256, P);
+        CK(cudaGetLastError());
+        std::vector<float2> part(grid);
+        CK(cudaMemcpyAsync(part.data(), P.partial, grid * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (unsigned i = 0; i < grid; i++) {
+            if (part[i].x < lo) lo = part[i].x;
+            if (part[i].y > hi) hi = part[i].y;
+        }
+    }
+    if (range_min) *range_min = lo;
+    if (range_max) *range_max = hi;
+    return NVTTB_OK;
+}
+int nvttb_surface_tone_map(NvttbSurface *s, int toneMapper) {
+    if (!s || toneMapper < 0 || toneMapper > 3) return NVTTB_ERR_INVALID_INPUT;
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    ToneMapParams P{(float *)s->buf.p, (size_t)s->w * s->h, toneMapper};
+    NVB_LAUNCH(ctx, K_SCALE_BIAS, (double)P.pixels, k_tone_map, grid_for(P.pixels, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
+int nvttb_surface_to_rgbm(NvttbSurface *s, float range, float threshold) {
+    if (!s) return NVTTB_ERR_INVALID_INPUT;
+    (void)range;  // shadowed by a local in the reference (Surface.cpp:1905): no effect there either
+    NvttbContext *ctx = s->ctx;
+    if (!s->buf.p) return NVTTB_OK;
+    CK(cudaSetDevice(ctx->device));
+    threshold = threshold < 1e-6f ? 1e-6f : (threshold > 1.0f ? 1.0f : threshold);
+    ToRgbmParams P{(float *)s->buf.p, (size_t)s->w * s->h, threshold};
+    NVB_LAUNCH(ctx, K_SCALE_BIAS, (double)P.pixels, k_to_rgbm, grid_for(P.pixels, 256), 256, P);
+    CK(cudaGetLastError());
+    return NVTTB_OK;
+}
 static int quantize_channel(NvttbSurface *s, int channel, QuantizeParams P) {
     NvttbContext *ctx = s->ctx;
     if (channel < 0 || channel > 3) return NVTTB_ERR_INVALID_INPUT;

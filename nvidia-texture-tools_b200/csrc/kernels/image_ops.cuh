@@ -396,6 +396,128 @@ __global__ void __launch_bounds__(256) k_scale_bias(ScaleBiasParams P) {
         P.data[i] = P.scale * P.data[i] + P.bias;
 }
 
+// FloatImage::clamp(channel, 1, low, high)  (src/nvimage/FloatImage.cpp:245-256): nv::clamp = min(max(x, low), high)
+struct ClampParams {
+    float *data;
+    size_t count;
+    float low, high;
+};
+__global__ void __launch_bounds__(256) k_clamp(ClampParams P) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x)
+        P.data[i] = nv_clamp(P.data[i], P.low, P.high);
+}
+
+// Surface::range(channel, &min, &max, alpha_channel, alpha_ref)  (src/nvtt/Surface.cpp:526-566): running `if (f < lo) lo = f;
+// if (f > hi) hi = f` from (FLT_MAX, -FLT_MAX), optionally only where alpha > alpha_ref.  Comparisons with NaN are false
+// there and here, so the result does not depend on the order of the scan.
+struct RangeParams {
+    const float *data;
+    const float *alpha;  // null: every texel counts
+    size_t count;
+    float alpha_ref;
+    float2 *partial;     // one (min, max) per CTA
+};
+__global__ void __launch_bounds__(256) k_range(RangeParams P) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += (size_t)gridDim.x * blockDim.x) {
+        if (P.alpha != nullptr && !(P.alpha[i] > P.alpha_ref)) continue;
+        const float f = P.data[i];
+        if (f < lo) lo = f;
+        if (f > hi) hi = f;
+    }
+    __shared__ float slo[8], shi[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float l2 = __shfl_xor_sync(0xFFFFFFFFu, lo, o), h2 = __shfl_xor_sync(0xFFFFFFFFu, hi, o);
+        if (l2 < lo) lo = l2;
+        if (h2 > hi) hi = h2;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) {
+            if (slo[i] < lo) lo = slo[i];
+            if (shi[i] > hi) hi = shi[i];
+        }
+        P.partial[blockIdx.x] = make_float2(lo, hi);
+    }
+}
+
+// Surface::toneMap  (src/nvtt/Surface.cpp:2444-2494).  mode 0 = Linear and 3 = Lightmap (same code there: scale r, g, b by
+// 1 / max3 when it exceeds 1), 1 = Reindhart (c / (c + 1)), 2 = Halo (1 - exp2f(-c); CUDA's exp2f, 2 ulp from glibc's).
+struct ToneMapParams {
+    float *data;
+    size_t pixels;
+    int mode;
+};
+__global__ void __launch_bounds__(256) k_tone_map(ToneMapParams P) {
+    const size_t n = P.pixels;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float r = P.data[i], g = P.data[n + i], b = P.data[2 * n + i];
+        if (P.mode == 0 || P.mode == 3) {
+            const float m = nv_max(r, nv_max(g, b));
+            if (m > 1.0f) {
+                const float s = 1.0f / m;
+                r *= s;
+                g *= s;
+                b *= s;
+            }
+        } else if (P.mode == 1) {
+            r /= r + 1;
+            g /= g + 1;
+            b /= b + 1;
+        } else {
+            r = 1 - exp2f(-r);
+            g = 1 - exp2f(-g);
+            b = 1 - exp2f(-b);
+        }
+        P.data[i] = r;
+        P.data[n + i] = g;
+        P.data[2 * n + i] = b;
+    }
+}
+
+// Surface::toRGBM(range, threshold)  (src/nvtt/Surface.cpp:1862-1946): per texel, search the 8-bit multiplier within +-16
+// of the analytic one for the smallest reconstruction error of the 8-bit quantised colour; first strict minimum wins.
+// (The `range` argument is shadowed by a local 255 in the reference, so it has no effect there either.)
+struct ToRgbmParams {
+    float *data;
+    size_t pixels;
+    float threshold;  // already clamped to [1e-6, 1]
+};
+__global__ void __launch_bounds__(256) k_to_rgbm(ToRgbmParams P) {
+    const size_t n = P.pixels;
+    const float threshold = P.threshold, range = 255.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float R = nv_clamp(P.data[i], 0.0f, 1.0f), G = nv_clamp(P.data[n + i], 0.0f, 1.0f), B = nv_clamp(P.data[2 * n + i], 0.0f, 1.0f);
+        float M = nv_max(nv_max(R, G), nv_max(B, threshold));
+        const int iM = __float2int_rn(ceilf((M - threshold) / (1 - threshold) * range));  // ftoi_ceil = cvtss2si(ceilf(x))
+        float bestM = 0.0f, bestError = FLT_MAX;
+        const int m0 = iM - 16 > 0 ? iM - 16 : 0, m1 = iM + 16 < 256 ? iM + 16 : 256;
+        for (int m = m0; m < m1; m++) {
+            const float fm = float(m) / range;
+            const float Mq = fm * (1 - threshold) + threshold;
+            const int ir = __float2int_rn(range * nv_clamp(R / Mq, 0.0f, 1.0f));
+            const int ig = __float2int_rn(range * nv_clamp(G / Mq, 0.0f, 1.0f));
+            const int ib = __float2int_rn(range * nv_clamp(B / Mq, 0.0f, 1.0f));
+            const float fr = (float(ir) / range) * Mq, fg = (float(ig) / range) * Mq, fb = (float(ib) / range) * Mq;
+            const float error = (R - fr) * (R - fr) + (G - fg) * (G - fg) + (B - fb) * (B - fb);
+            if (error < bestError) {
+                bestError = error;
+                bestM = Mq;
+            }
+        }
+        M = bestM;
+        P.data[i] = nv_clamp(R / M, 0.0f, 1.0f);
+        P.data[n + i] = nv_clamp(G / M, 0.0f, 1.0f);
+        P.data[2 * n + i] = nv_clamp(B / M, 0.0f, 1.0f);
+        P.data[3 * n + i] = (M - threshold) / (1 - threshold);
+    }
+}
+
 // Surface::binarize(channel, threshold, dither = false): c = float(c > threshold)   (src/nvtt/Surface.cpp:2656-2670)
 struct BinarizeParams {
     float *data;   // the channel's plane
