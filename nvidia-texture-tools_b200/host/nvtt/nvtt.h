@@ -36,6 +36,7 @@ enum RoundMode { RoundMode_None, RoundMode_ToNextPowerOfTwo, RoundMode_ToNearest
 enum AlphaMode { AlphaMode_None, AlphaMode_Transparency, AlphaMode_Premultiplied };
 enum Error { Error_Unknown, Error_InvalidInput, Error_UnsupportedFeature, Error_CudaError, Error_FileOpen, Error_FileWrite, Error_UnsupportedOutputFormat, Error_Count };
 enum Container { Container_DDS, Container_DDS10, Container_KTX };
+enum ToneMapper { ToneMapper_Linear, ToneMapper_Reindhart, ToneMapper_Halo, ToneMapper_Lightmap };
 
 struct CompressionOptions {
     NVTT_API CompressionOptions();
@@ -51,6 +52,7 @@ struct CompressionOptions {
     NVTT_API void setQuantization(bool colorDithering, bool alphaDithering, bool binaryAlpha, int alphaThreshold = 127);
     NVTT_API void setRGBMThreshold(float min_m);
     NVTT_API void setTargetDecoder(Decoder decoder);
+    NVTT_API void setExternalCompressor(const char *name);  // stored and ignored, as in a stock reference build (no HAVE_* codec)
     NVTT_API Format format() const;
     struct Private;
     Private &m;
@@ -166,7 +168,10 @@ struct Surface {
     NVTT_API bool isNormalMap() const;
     NVTT_API int countMipmaps() const;
     NVTT_API const float *data() const;  // host copy of the planar fp32 RGBA data, refreshed on demand
+    NVTT_API bool load(const char *fileName, bool *hasAlpha = 0);  // decodes through the installed SurfaceLoader (see below)
+    NVTT_API void range(int channel, float *rangeMin, float *rangeMax, int alpha_channel = -1, float alpha_ref = 0.f) const;
     NVTT_API bool setImage(InputFormat format, int w, int h, int d, const void *data);
+    NVTT_API bool setImage(InputFormat format, int w, int h, int d, const void *r, const void *g, const void *b, const void *a);
     NVTT_API bool setImage2D(Format format, Decoder decoder, int w, int h, const void *data);
     NVTT_API void resize(int w, int h, int d, ResizeFilter filter);
     NVTT_API void resize(int w, int h, int d, ResizeFilter filter, float filterWidth, const float *params = 0);
@@ -179,6 +184,10 @@ struct Surface {
     NVTT_API void toNormalMap(float sm, float medium, float big, float large);
     NVTT_API void binarize(int channel, float threshold, bool dither);
     NVTT_API void quantize(int channel, int bits, bool exactEndPoints, bool dither);
+    NVTT_API void scaleBias(int channel, float scale, float bias);
+    NVTT_API void clamp(int channel, float low = 0.0f, float high = 1.0f);
+    NVTT_API void toRGBM(float range = 1.0f, float threshold = 0.25f);
+    NVTT_API void toneMap(ToneMapper tm, float *parameters);
     NVTT_API void normalizeNormalMap();
     NVTT_API void packNormals(float scale = 0.5f, float bias = 0.5f);
     NVTT_API void expandNormals(float scale = 2.0f, float bias = -1.0f);
@@ -191,6 +200,12 @@ NVTT_API float rmsError(const Surface &reference, const Surface &img);
 NVTT_API float rmsAlphaError(const Surface &reference, const Surface &img);
 NVTT_API float angularError(const Surface &reference, const Surface &img);
 NVTT_API float cieLabError(const Surface &reference, const Surface &img);
+
+// Image FILE decoding is not part of the GPU path and this library links no image codecs: Surface::load hands the file name
+// to the loader installed here (an application - or the nvcompress build recipe - provides one on top of its own image reader;
+// it fills the surface with setImage / setImage2D).  Without a loader Surface::load returns false.  Not in the reference.
+typedef bool (*SurfaceLoader)(Surface &dst, const char *fileName, bool *hasAlpha);
+NVTT_API void setSurfaceLoader(SurfaceLoader loader);
 
 NVTT_API unsigned int version();
 NVTT_API const char *errorString(Error e);

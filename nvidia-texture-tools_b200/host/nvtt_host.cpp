@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#include <math.h>
 #include <string>
 #include <vector>
 
@@ -19,10 +20,13 @@ namespace {
 inline int imax(int a, int b) { return a > b ? a : b; }
 inline int imin(int a, int b) { return a < b ? a : b; }
 
-// One shared GPU context per process (device from NVTT_B200_DEVICE, default 0).
+// The GPU contexts of this process.  Surfaces and single-level calls live on the first one (device NVTT_B200_DEVICE,
+// default 0); Compressor::process spreads large jobs over all of them (nvttb_process_multi): NVTT_B200_DEVICES = "all"
+// (default), a count, or a comma-separated device list.
 struct Gpu {
     NvttbContext *ctx = nullptr;
-    bool tried = false;
+    std::vector<NvttbContext *> all;
+    bool tried = false, triedAll = false;
     NvttbContext *get() {
         if (!tried) {
             tried = true;
@@ -32,8 +36,40 @@ struct Gpu {
         }
         return ctx;
     }
+    const std::vector<NvttbContext *> &pool() {
+        if (!triedAll) {
+            triedAll = true;
+            NvttbContext *first = get();
+            if (first) {
+                all.push_back(first);
+                int firstDev = 0;
+                if (const char *e = getenv("NVTT_B200_DEVICE")) firstDev = atoi(e);
+                const int n = nvttb_device_count();
+                std::vector<int> devs;
+                const char *e = getenv("NVTT_B200_DEVICES");
+                if (e && strchr(e, ',')) {
+                    for (const char *p = e; *p;) {
+                        devs.push_back(atoi(p));
+                        p = strchr(p, ',');
+                        if (!p) break;
+                        p++;
+                    }
+                } else {
+                    int want = (e && strcmp(e, "all") != 0) ? atoi(e) : n;
+                    for (int d = 0; d < n && (int)devs.size() < want; d++) devs.push_back(d);
+                }
+                for (int d : devs) {
+                    if (d == firstDev || d < 0 || d >= n) continue;
+                    NvttbContext *c = nullptr;
+                    if (nvttb_context_create(d, &c) == NVTTB_OK) all.push_back(c);
+                }
+            }
+        }
+        return all;
+    }
 };
 Gpu g_gpu;
+SurfaceLoader g_surfaceLoader = nullptr;
 
 unsigned previousPowerOfTwo(unsigned v) {
     unsigned p = 1;
@@ -146,6 +182,7 @@ void CompressionOptions::setQuantization(bool c, bool a, bool b, int t) {
     m.enableColorDithering = c; m.enableAlphaDithering = a; m.binaryAlpha = b; m.alphaThreshold = t;
 }
 void CompressionOptions::setTargetDecoder(Decoder d) { m.decoder = d; }
+void CompressionOptions::setExternalCompressor(const char *) {}  // CompressionOptions.cpp:177; no external codec is ever compiled in
 Format CompressionOptions::format() const { return m.format; }
 
 struct InputOptions::Private {
@@ -440,15 +477,82 @@ void Surface::quantize(int channel, int bits, bool exactEndPoints, bool dither) 
     m->hostValid = false;
     nvttb_surface_quantize(m->s, channel, bits, exactEndPoints ? 1 : 0, dither ? 1 : 0);
 }
+// Surface::packNormals / expandNormals = scaleBias(0, 3, scale, bias) for any values (Surface.cpp:2952-2963)
 void Surface::packNormals(float scale, float bias) {
     if (isNull()) return;
     m->hostValid = false;
-    if (scale == 0.5f && bias == 0.5f) nvttb_surface_pack_normals(m->s);
+    nvttb_surface_scale_bias(m->s, 0, 3, scale, bias);
 }
 void Surface::expandNormals(float scale, float bias) {
     if (isNull()) return;
     m->hostValid = false;
-    if (scale == 2.0f && bias == -1.0f) nvttb_surface_expand_normals(m->s);
+    nvttb_surface_scale_bias(m->s, 0, 3, scale, bias);
+}
+namespace {
+bool nv_equal_f(float a, float b) {  // nv::equal (nvmath.h:139-143)
+    float mx = 1.0f;
+    if (fabsf(a) > mx) mx = fabsf(a);
+    if (fabsf(b) > mx) mx = fabsf(b);
+    return fabsf(a - b) <= 0.0001f * mx;
+}
+}  // namespace
+void Surface::scaleBias(int channel, float scale, float bias) {
+    if (isNull()) return;
+    if (nv_equal_f(scale, 1.0f) && nv_equal_f(bias, 0.0f)) return;  // Surface.cpp:1672
+    m->hostValid = false;
+    nvttb_surface_scale_bias(m->s, channel, 1, scale, bias);
+}
+void Surface::clamp(int channel, float low, float high) {
+    if (isNull()) return;
+    m->hostValid = false;
+    nvttb_surface_clamp(m->s, channel, low, high);
+}
+void Surface::toRGBM(float range, float threshold) {
+    if (isNull()) return;
+    m->hostValid = false;
+    nvttb_surface_to_rgbm(m->s, range, threshold);
+}
+void Surface::toneMap(ToneMapper tm, float *) {
+    if (isNull()) return;
+    m->hostValid = false;
+    nvttb_surface_tone_map(m->s, (int)tm);
+}
+void Surface::range(int channel, float *rangeMin, float *rangeMax, int alpha_channel, float alpha_ref) const {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    if (m->s) nvttb_surface_range(m->s, channel, alpha_channel, alpha_ref, &lo, &hi);
+    if (rangeMin) *rangeMin = lo;
+    if (rangeMax) *rangeMax = hi;
+}
+bool Surface::load(const char *fileName, bool *hasAlpha) {
+    if (!g_surfaceLoader || !fileName) return false;
+    return g_surfaceLoader(*this, fileName, hasAlpha);
+}
+void nvtt::setSurfaceLoader(SurfaceLoader loader) { g_surfaceLoader = loader; }
+// planar source channels (Surface.cpp:817-901): rearranged into the interleaved layout of the same InputFormat on the host
+// (a pure copy), then the regular device conversion
+bool Surface::setImage(InputFormat format, int w, int h, int d, const void *r, const void *g, const void *b, const void *a) {
+    if (d != 1 || w <= 0 || h <= 0) return false;
+    const size_t n = (size_t)w * h;
+    if (format == InputFormat_R_32F) return setImage(format, w, h, d, r);
+    if (format == InputFormat_BGRA_8UB) {
+        std::vector<unsigned char> t(n * 4);
+        const unsigned char *R = (const unsigned char *)r, *G = (const unsigned char *)g, *B = (const unsigned char *)b, *A = (const unsigned char *)a;
+        for (size_t i = 0; i < n; i++) { t[4 * i] = B[i]; t[4 * i + 1] = G[i]; t[4 * i + 2] = R[i]; t[4 * i + 3] = A[i]; }
+        return setImage(format, w, h, d, t.data());
+    }
+    if (format == InputFormat_RGBA_16F) {
+        std::vector<unsigned short> t(n * 4);
+        const unsigned short *R = (const unsigned short *)r, *G = (const unsigned short *)g, *B = (const unsigned short *)b, *A = (const unsigned short *)a;
+        for (size_t i = 0; i < n; i++) { t[4 * i] = R[i]; t[4 * i + 1] = G[i]; t[4 * i + 2] = B[i]; t[4 * i + 3] = A[i]; }
+        return setImage(format, w, h, d, t.data());
+    }
+    if (format == InputFormat_RGBA_32F) {
+        std::vector<float> t(n * 4);
+        const float *R = (const float *)r, *G = (const float *)g, *B = (const float *)b, *A = (const float *)a;
+        for (size_t i = 0; i < n; i++) { t[4 * i] = R[i]; t[4 * i + 1] = G[i]; t[4 * i + 2] = B[i]; t[4 * i + 3] = A[i]; }
+        return setImage(format, w, h, d, t.data());
+    }
+    return false;
 }
 
 // ---- Compressor ---------------------------------------------------------------------------------------------
@@ -949,7 +1053,10 @@ bool Compressor::process(const InputOptions &inputOptions, const CompressionOpti
         std::vector<const void *> ptrs(faceCount);
         for (int f = 0; f < faceCount; f++) ptrs[f] = io.images[f].data();
         EmitCtx ec{&oo};
-        const int rc = nvttb_process(ctx, &d, ptrs.data(), NVTTB_HOST, emit_cb, &ec);
+        // every visible GPU works on the job: one large image is block-row sharded, faces / array slices are dealt out
+        const std::vector<NvttbContext *> &pool = g_gpu.pool();
+        const int rc = pool.size() > 1 ? nvttb_process_multi(pool.data(), (int)pool.size(), &d, ptrs.data(), emit_cb, &ec)
+                                       : nvttb_process(ctx, &d, ptrs.data(), NVTTB_HOST, emit_cb, &ec);
         if (rc != NVTTB_OK) {
             oo.error((Error)(rc - 1));
             return false;
