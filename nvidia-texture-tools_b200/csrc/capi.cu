@@ -1943,9 +1943,13 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
         if ((rc = ensure(ctx, ctx->tail_lvl, 2 * lvl1 * sizeof(float))) != NVTTB_OK) { cleanup(); return rc; }
         std::swap(ctx->stream, ctx->tail_stream);
         std::swap(ctx->enc_scratch, ctx->tail_scratch);
+        // per-launch event timing (nvttb_profile_*) describes the main stream; launches that overlap it would be counted twice
+        const bool was_profiling = ctx->profiling;
+        ctx->profiling = false;
         auto unswap = [&]() {
             std::swap(ctx->stream, ctx->tail_stream);
             std::swap(ctx->enc_scratch, ctx->tail_scratch);
+            ctx->profiling = was_profiling;
         };
         NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_wait, 1, NVB_XCHG_FLAGS, xhdr, N, seq, ctx->h_fault);
         const float *cur = ximg;

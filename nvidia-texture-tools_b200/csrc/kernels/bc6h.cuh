@@ -557,6 +557,7 @@ __global__ void __launch_bounds__(NVB_BC6_ROUGH_WARPS * 32) k_bc6_rough(Bc6Param
     }
 }
 
+#ifdef NVB_EMU  // cross-check design for the CPU emulator tests only (tests/simt_emu): not part of the product library
 // Thread t < padded: one-region refine of block t; t >= padded: two-region refine of block t - padded (padded = nblocks
 // rounded up to the CTA size, so a CTA never mixes the two kinds).
 __global__ void __launch_bounds__(128) k_bc6_refine(Bc6Params P, int padded) {
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(128) k_bc6_refine(Bc6Params P, int padded) {
     }
     P.cand_err[(size_t)blk * 2 + kind] = err;
 }
+#endif  // NVB_EMU
 
 __global__ void __launch_bounds__(256) k_bc6_select(Bc6Params P) {
     const int nblocks = P.lv.bw * P.lv.bh;

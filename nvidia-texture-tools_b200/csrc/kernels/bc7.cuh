@@ -1043,6 +1043,7 @@ template <int GROUP> NVB_DEV void bc7_group_min(float &err, int &rank, uint4 &bl
     }
 }
 
+#ifdef NVB_EMU  // cross-check design for the CPU emulator tests only (tests/simt_emu): not part of the product library
 // One thread per (block, candidate).  NCAND candidates of a block are adjacent lanes.
 template <int M, int NCAND> __global__ void __launch_bounds__(128) k_bc7_refine(Bc7Params P) {
     const int nblocks = P.lv.bw * P.lv.bh;
@@ -1075,6 +1076,7 @@ template <int M, int NCAND> __global__ void __launch_bounds__(128) k_bc7_refine(
         P.cand_err[(size_t)M * nblocks + blk] = err;
     }
 }
+#endif  // NVB_EMU
 
 __global__ void __launch_bounds__(256) k_bc7_select(Bc7Params P) {
     const int nblocks = P.lv.bw * P.lv.bh;

@@ -8,7 +8,7 @@
 // point of the loop.  The 32 lanes of a warp are therefore always converged in the trial evaluation, whatever phase
 // (first / alternating perturbation, +-3 exhaustive window, restart) each of them is in; only the few instructions
 // that pick the next trial diverge.  The thread-per-candidate kernels (bc7.cuh) and the warp-per-candidate kernels
-// (bc7_coop.cuh) execute the same search; all three give bit-identical blocks.
+// (tests/simt_emu/bc7_coop.cuh, emulator only) execute the same search; all three give bit-identical blocks.
 //
 //   k_bc7_tiles        texels of the chunk's blocks (x255, zero outside the image) as [block][16] float4
 //   k_bc7_setup<M>     thread per candidate: rough fit, quantise, assign, anchor swap  -> start endpoints + error per region

@@ -1,3 +1,4 @@
+// TEST INFRASTRUCTURE ONLY (CPU emulator cross-check of the BC7 search): never compiled into the product library.
 // Warp-cooperative BC7 refinement: one warp per candidate (block, mode, shape rank | rotation x index mode).
 //
 // Same search as bc7.cuh (and therefore as src/bc7/avpcl_mode*.cpp), re-mapped so that a warp — not a thread — walks the
@@ -13,7 +14,7 @@
 // sum above the threshold implies a total above it), so evaluating K trials together and resolving them in the
 // reference's order gives the same accepted steps.  Results are bit-identical to the thread-per-candidate kernels.
 #pragma once
-#include "bc7.cuh"
+#include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
 
 namespace nvb {
 

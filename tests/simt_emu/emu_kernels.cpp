@@ -8,7 +8,7 @@
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc1_quick.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7.cuh"
-#include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_coop.cuh"
+#include "bc7_coop.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc7_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/bc6h_search.cuh"
 #include "../../nvidia-texture-tools_b200/csrc/kernels/image_ops.cuh"
