@@ -252,6 +252,11 @@ NVTTB_API size_t nvttb_process_exchange_size(const NvttbProcessDesc *desc);
  * be pageable or pinned.  Synchronous when out_host or a host image is given, asynchronous on the context's stream otherwise. */
 NVTTB_API int nvttb_process_shard(NvttbContext *ctx, const NvttbProcessDesc *desc, const void *const *images, int images_location,
                                   void *out_device, void *out_host);
+/* Sizes every device buffer a band-local nvttb_process_shard / nvttb_process_to_device call with this description will use, so
+ * that the call itself allocates nothing.  Needed when several bands share one GPU (band 0 keeps a waiting kernel resident
+ * until all bands have delivered, and a cudaMalloc on that GPU may wait for it); harmless otherwise.  own_output: the call will
+ * be given out_device = NULL. */
+NVTTB_API int nvttb_process_prepare(NvttbContext *ctx, const NvttbProcessDesc *desc, int images_location, int own_output);
 /* The whole pipeline for host images on SEVERAL GPUs of one process (one host thread per context): large single images are
  * block-row sharded (band-local front end where it applies), cube faces / array slices are dealt out face by face.  emit sees
  * exactly what nvttb_process would produce on one GPU.  contexts[0] owns the pinned output buffer. */

@@ -89,7 +89,7 @@ EXPORTS = [
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slices",
-    "nvttb_process_exchange_size", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
+    "nvttb_process_exchange_size", "nvttb_process_prepare", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
     "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
 ]
 
@@ -173,6 +173,7 @@ def lib():
     L.nvttb_process_band_slices.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
     L.nvttb_process_exchange_size.argtypes = [C.POINTER(ProcessDesc)]
     L.nvttb_process_exchange_size.restype = sz
+    L.nvttb_process_prepare.argtypes = [vp, C.POINTER(ProcessDesc), ci, ci]
     L.nvttb_process_shard.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, vp]
     L.nvttb_process_multi.argtypes = [C.POINTER(vp), ci, C.POINTER(ProcessDesc), C.POINTER(vp), EMIT_FN, vp]
     L.nvttb_host_register.argtypes = [vp, vp, sz]
@@ -316,6 +317,10 @@ class Context:
         written = C.c_size_t(0)
         self._ck(self.L.nvttb_process_to_device(self.h, C.byref(desc), ptrs, location, d_out_ptr, cap, C.byref(written)))
         return written.value
+
+    def process_prepare(self, desc, location=HOST, own_output=True):
+        """nvttb_process_prepare: size the buffers of a band-local shard call up front (several bands on one GPU)."""
+        self._ck(self.L.nvttb_process_prepare(self.h, C.byref(desc), location, int(own_output)))
 
     def process_shard(self, images, desc, d_out_ptr=None, h_out_ptr=None, location=HOST):
         """nvttb_process_shard: this band's share of one block-row sharded image, whole-chain layout on device and / or host."""

@@ -16,8 +16,10 @@
 #include "kernels/bc_decode.cuh"
 #include "kernels/pixel_format.cuh"
 #include "kernels/shard_exchange.cuh"
+#include "kernels/polyphase_tma.cuh"
 
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <map>
 #include <string>
 #include <thread>
@@ -45,6 +47,10 @@ struct PolyDev {
     int max_extent = 0;  // most source samples any NVB_PF_TILE-wide run of outputs touches (for the fused 2-D kernel)
     float *weights = nullptr;
     int *left = nullptr;
+    // exact 2:1 tables: every output has the same weights and left[i] = 2 i + left0 (checked on the host table)
+    bool uniform2 = false;
+    int left0 = 0;
+    float w0[NVB_PT_MAXW] = {};
 };
 
 enum { K_ALPHA = 0, K_ALPHA_OPT, K_ALPHA_DXT3, K_BC3_COLOR, K_BC1A_COLOR, K_BC1, K_DXT1_QUICK, K_BC6_ROUGH, K_BC6_TILES, K_BC6_SETUP, K_BC6_ORDER, K_BC6_SEARCH, K_BC6_FINISH, K_BC6_SELECT, K_BC7_ROUGH, K_BC7_TILES, K_BC7_SETUP, K_BC7_ORDER, K_BC7_SEARCH, K_BC7_FINISH, K_BC7_SELECT, K_SET_IMAGE, K_GAMMA, K_BOX_DOWN, K_POLY_X, K_POLY_Y, K_POLY_2D, K_NORMALIZE, K_SCALE_BIAS, K_GREY_SCALE, K_NORMAL_MAP, K_DECODE, K_ERROR_METRIC, K_BINARIZE, K_QUANTIZE, K_PIXEL_FORMAT, K_XCHG, K_COUNT };
@@ -522,6 +528,15 @@ template <int M, int NCAND> static int launch_bc7_mode(NvttbContext *ctx, Bc7Sea
     return NVTTB_OK;
 }
 
+// encoder scratch of one level (BC6H / BC7 only): what encode_device sizes ctx->enc_scratch to
+static constexpr size_t kBc6ScratchPerBlock = 80 + 32 + 8 + 256 + 32 + 96 + 16 + 96 + 8;
+static size_t encoder_scratch_bytes(int format, int w, int h) {
+    const size_t nb = (size_t)((w + 3) / 4) * ((h + 3) / 4);
+    if (format == F_BC6) return nb * kBc6ScratchPerBlock + 256 + 64;
+    if (format == F_BC7) return nb * (80 + 128 + 32) + 16 + kBc7CounterBytes + (size_t)NVB_BC7_CHUNK * (kBc7ChunkBytesPerBlock + 256);
+    return 0;
+}
+
 // ---- level encode on device buffers (async on ctx->stream) --------------------------------------------------
 // d_rgba points at row 0 of the rows to encode (h of them); plane = floats between the planes of the level they belong to
 struct CycView { int rpc, n, i; };  // LevelView::cyc_*: the rows are one GPU's concatenated chunks of a sharded level
@@ -706,8 +721,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     else if (d->format == F_BC6) {
         // scratch per block: 20 floats of rough endpoints, 2 candidate blocks, 2 errors; then the searcher records:
         // texel tile (256), meta (2 x 16), start endpoints (3 x 32), start indices (2 x 8), results (3 x 32), order (2 x 4)
-        const size_t per_block = 80 + 32 + 8 + 256 + 32 + 96 + 16 + 96 + 8;
-        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * per_block + 256 + 64);
+        int rc = ensure(ctx, ctx->enc_scratch, encoder_scratch_bytes(F_BC6, w, h));
         if (rc != NVTTB_OK) return rc;
         Bc6Params P;
         P.lv = lv;
@@ -763,7 +777,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
     else if (d->format == F_BC7) {
         // scratch per block of the level: 5 x 16 shape bytes, 8 x 16 candidate bytes, 8 errors; per block of a chunk: the
         // texel tile and the setup / result records of every searcher (Bc7ModeBytes)
-        int rc = ensure(ctx, ctx->enc_scratch, (size_t)nb * (80 + 128 + 32) + 16 + kBc7CounterBytes + (size_t)NVB_BC7_CHUNK * (kBc7ChunkBytesPerBlock + 256));
+        int rc = ensure(ctx, ctx->enc_scratch, encoder_scratch_bytes(F_BC7, w, h));
         if (rc != NVTTB_OK) return rc;
         Bc7Params P;
         P.lv = lv;
@@ -834,6 +848,15 @@ static int get_poly(NvttbContext *ctx, const FilterDesc &f, int src, int dst, Po
         const int ext = t.left[i1] + t.window - t.left[i0];
         if (ext > pd.max_extent) pd.max_extent = ext;
     }
+    if (dst * 2 == src && t.window <= NVB_PT_MAXW && t.length > 0) {
+        pd.uniform2 = true;
+        pd.left0 = t.left[0];
+        for (int i = 0; i < t.length && pd.uniform2; i++) {
+            if (t.left[i] != 2 * i + pd.left0) pd.uniform2 = false;
+            if (memcmp(&t.weights[(size_t)i * t.window], &t.weights[0], t.window * sizeof(float)) != 0) pd.uniform2 = false;
+        }
+        for (int j = 0; j < t.window; j++) pd.w0[j] = t.weights[j];
+    }
     CK(cudaMalloc(&pd.weights, t.weights.size() * sizeof(float)));
     CK(cudaMalloc(&pd.left, t.left.size() * sizeof(int)));
     CK(cudaMemcpy(pd.weights, t.weights.data(), t.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -844,11 +867,83 @@ static int get_poly(NvttbContext *ctx, const FilterDesc &f, int src, int dst, Po
 }
 
 // src (sw x sh) -> dst (dw x dh), X pass into ctx->tmp_filter then Y pass (FloatImage::resize, FloatImage.cpp:761-808)
-static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const float *src, int sw, int sh, float *dst, int dw, int dh) {
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled tensor_map_encoder() {
+    static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (PFN_encodeTiled)p;
+    }();
+    return fn;
+}
+
+template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDev &px, const PolyDev &py, int wrap, const float *src, int sw, int sh,
+                                                 float *dst, int dw, int dh, bool normalize, bool *done) {
+    using G = PtGeom<W>;
+    PFN_encodeTiled enc = tensor_map_encoder();
+    if (!enc) return NVTTB_OK;  // *done stays false: the caller takes the plain kernel
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)sw, (cuuint64_t)sh, 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)sw * 4, (cuuint64_t)sw * sh * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)G::BOX_W, (cuuint32_t)G::IN_H, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return NVTTB_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_polyphase_tma<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        attr_set = true;
+    }
+    PolyTmaParams Q;
+    Q.src = src; Q.dst = dst; Q.sw = sw; Q.sh = sh; Q.dw = dw; Q.dh = dh; Q.wrap = wrap;
+    Q.left0x = px.left0; Q.left0y = py.left0;
+    for (int j = 0; j < NVB_PT_MAXW; j++) { Q.wx[j] = px.w0[j]; Q.wy[j] = py.w0[j]; }
+    Q.tiles_x = (dw + NVB_PT_TW - 1) / NVB_PT_TW;
+    Q.tiles_y = (dh + NVB_PT_TH - 1) / NVB_PT_TH;
+    Q.normalize = normalize ? 1 : 0;
+    const int ntiles = Q.tiles_x * Q.tiles_y;
+    const int grid = ntiles < 148 * 3 ? ntiles : 148 * 3;  // persistent: three CTAs per SM (69 KB of shared memory each)
+    ProfRec r_;
+    if (ctx->profiling) {
+        r_.kid = K_POLY_2D; r_.units = (double)dw * dh;
+        cudaEventCreate(&r_.a); cudaEventCreate(&r_.b); cudaEventRecord(r_.a, ctx->stream);
+    }
+    k_polyphase_tma<W><<<grid, NVB_PT_THREADS, G::SMEM_BYTES, ctx->stream>>>(map, Q);
+    if (ctx->profiling) { cudaEventRecord(r_.b, ctx->stream); ctx->prof.push_back(r_); }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *done = true;
+    return NVTTB_OK;
+}
+
+// normalize: also apply the normal-map renormalisation of a mip (expand -> normalise -> pack) to planes 0..2 of dst
+static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false) {
     PolyDev px, py;
     int rc;
     if ((rc = get_poly(ctx, f, sw, dw, &px)) != NVTTB_OK) return rc;
     if ((rc = get_poly(ctx, f, sh, dh, &py)) != NVTTB_OK) return rc;
+    auto post = [&]() -> int {
+        if (normalize) {
+            NormalizeParams P{dst, (size_t)dw * dh, 1};
+            NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
+            CK(cudaGetLastError());
+        }
+        return NVTTB_OK;
+    };
+    static const bool no_tma = getenv("NVB_NO_TMA") != nullptr;
+    if (!no_tma && px.uniform2 && py.uniform2 && px.window == py.window && (sw & 3) == 0 && ((size_t)src & 15) == 0 && dw >= 2 * NVB_PT_TW && dh >= 2 * NVB_PT_TH) {
+        // TMA-fed persistent kernel for the 2:1 mip filters (+ fused renormalisation)
+        bool done = false;
+        if (px.window == 13) rc = launch_polyphase_tma<13>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
+        else if (px.window == 9) rc = launch_polyphase_tma<9>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
+        else if (px.window == 5) rc = launch_polyphase_tma<5>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
+        if (rc != NVTTB_OK) return rc;
+        if (done) return NVTTB_OK;
+    }
     if (px.max_extent <= NVB_PF_EXT && py.max_extent <= NVB_PF_EXT && px.window <= NVB_PF_MAXWIN && py.window <= NVB_PF_MAXWIN) {
         // fused X+Y in shared memory: the dw x sh intermediate never reaches HBM
         Polyphase2DParams Q{src, dst, sw, sh, dw, dh, px.window, py.window, px.weights, px.left, py.weights, py.left, wrap};
@@ -859,7 +954,7 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
         else if (Q.winx == 5 && Q.winy == 5) NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<5, 5>), grid, 256, Q);
         else NVB_LAUNCH(ctx, K_POLY_2D, (double)dw * dh, (k_polyphase_2d_t<0, 0>), grid, 256, Q);
         CK(cudaGetLastError());
-        return NVTTB_OK;
+        return post();
     }
     if ((rc = ensure(ctx, ctx->tmp_filter, (size_t)dw * sh * 4 * sizeof(float))) != NVTTB_OK) return rc;
     float *tmp = (float *)ctx->tmp_filter.p;
@@ -868,12 +963,12 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
     PolyphaseParams Y{tmp, dst, dw, sh, dw, dh, 4, py.window, py.weights, py.left, wrap};
     NVB_LAUNCH(ctx, K_POLY_Y, (double)dw * dh, k_polyphase_y, grid_for((size_t)dw * dh * 4, 256), 256, Y);
     CK(cudaGetLastError());
-    return NVTTB_OK;
+    return post();
 }
 
 // Surface::buildNextMipmap semantics on raw device buffers.  Returns via *dw,*dh the new size.
 static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidth, float p0, float p1, int alphaMode, int wrap,
-                           const float *src, int sw, int sh, float *dst, int dw, int dh) {
+                           const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false) {
     if (mipmapFilter == MF_Box && filterWidth == 0.5f && alphaMode != AM_Transparency) {
         BoxDownParams P{src, dst, sw, sh, dw, dh, 4};
         if ((sw & 3) == 0 && (sh & 1) == 0 && sh >= 2 && dh <= 65535 && ((size_t)src & 15) == 0 && ((size_t)dst & 7) == 0) {
@@ -881,6 +976,10 @@ static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidt
             NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down_even4, grid, 256, P);
         } else {
             NVB_LAUNCH(ctx, K_BOX_DOWN, (double)dw * dh, k_box_down, grid_for((size_t)dw * dh * 4, 256), 256, P);
+        }
+        if (normalize) {
+            NormalizeParams N{dst, (size_t)dw * dh, 1};
+            NVB_LAUNCH(ctx, K_NORMALIZE, (double)N.pixels, k_normalize, grid_for(N.pixels, 256), 256, N);
         }
         CK(cudaGetLastError());
         return NVTTB_OK;
@@ -890,7 +989,7 @@ static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidt
     f.width = filterWidth;
     f.p0 = (f.kind == Filter_Kaiser) ? p0 : 0.0f;
     f.p1 = (f.kind == Filter_Kaiser) ? p1 : 0.0f;
-    return resize_device(ctx, f, wrap, src, sw, sh, dst, dw, dh);
+    return resize_device(ctx, f, wrap, src, sw, sh, dst, dw, dh, normalize);
 }
 
 static void default_filter(int filter, float *width, float params[2]) {
@@ -1740,14 +1839,11 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                     pr[0] = d->kaiserAlpha;
                     pr[1] = d->kaiserStretch;
                 }
-                if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh)) != NVTTB_OK) { cleanup(); return rc; }
+                // normal maps: the mip is renormalised (expand -> normalise -> pack) before it is encoded and down-sampled again
+                if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh, isNormal && d->normalizeMipmaps)) != NVTTB_OK) { cleanup(); return rc; }
                 float *t = cur; cur = nxt; nxt = t;
                 w = dw;
                 h = dh;
-                if (isNormal && d->normalizeMipmaps) {
-                    NormalizeParams P{cur, (size_t)w * h, 1};
-                    NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
-                }
             }
             // tmp = img; tmp.toGamma(outputGamma); compress(tmp)
             NvttbEncodeDesc e = d->encode;
@@ -1835,6 +1931,37 @@ extern "C" size_t nvttb_process_exchange_size(const NvttbProcessDesc *d) {
     return (size_t)NVB_XCHG_HEADER + (size_t)2 * 4 * p.wk * p.hk * sizeof(float);
 }
 
+// Every device buffer one band-local shard call needs, sized up front.  A cudaMalloc / cudaFree may wait for the device to go
+// idle, and band 0 keeps a waiting kernel resident until every band has delivered its rows - so nothing may allocate once
+// the first launch of the image is out (matters when several bands share one GPU, as in the tests; and for band 0 itself).
+static int shard_local_prepare(NvttbContext *ctx, const NvttbProcessDesc *d, const LocalPlan &pl, bool host_in, bool own_out) {
+    const ShardGeom &g = pl.g;
+    const int W = d->width, HL = g.K * g.C;
+    int rc;
+    size_t tot = 0;
+    for (int m = 0; m <= pl.k; m++) tot += (size_t)4 * (W >> m) * (HL >> m);
+    if ((rc = ensure(ctx, ctx->lvlA, tot * sizeof(float))) != NVTTB_OK) return rc;
+    if (host_in && (rc = ensure(ctx, ctx->in_stage, (size_t)HL * W * input_bpp(d->inputFormat))) != NVTTB_OK) return rc;
+    if (own_out && (rc = ensure(ctx, ctx->out_dev, whole_face_bytes(d))) != NVTTB_OK) return rc;
+    const size_t es = encoder_scratch_bytes(d->encode.format, W, HL);
+    if (es && (rc = ensure(ctx, ctx->enc_scratch, es)) != NVTTB_OK) return rc;
+    if (pl.k < pl.mips - 1 && g.b == 0) {
+        const int w1 = pl.wk / 2 > 1 ? pl.wk / 2 : 1, h1 = pl.hk / 2 > 1 ? pl.hk / 2 : 1;
+        if ((rc = ensure(ctx, ctx->tail_lvl, (size_t)2 * 4 * w1 * h1 * sizeof(float))) != NVTTB_OK) return rc;
+        const size_t ts = encoder_scratch_bytes(d->encode.format, w1, h1);
+        if (ts && (rc = ensure(ctx, ctx->tail_scratch, ts)) != NVTTB_OK) return rc;
+    }
+    return NVTTB_OK;
+}
+
+extern "C" int nvttb_process_prepare(NvttbContext *ctx, const NvttbProcessDesc *d, int images_location, int own_output) {
+    if (!ctx || !d) return NVTTB_ERR_INVALID_INPUT;
+    LocalPlan pl;
+    if (d->bandCount <= 1 || !d->bandExchange || !shard_local_plan(d, &pl)) return NVTTB_OK;  // nothing waits on the device in the other paths
+    CK(cudaSetDevice(ctx->device));
+    return shard_local_prepare(ctx, d, pl, images_location == NVTTB_HOST, own_output != 0);
+}
+
 // One face of a sharded image on band g.b: upload / convert / down-sample the band's own chunks, hand the rows of level k to
 // band 0, encode the band's rows of levels 0..k; band 0 also runs the tail (levels k+1..) on tail_stream.
 // out: whole-face layout on the device (possibly a peer's memory); h_out: whole-face layout on the host, or null.
@@ -1862,7 +1989,7 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
             h = h / 2 > 1 ? h / 2 : 1;
         }
     }
-    if ((rc = ensure(ctx, ctx->lvlA, tot * sizeof(float))) != NVTTB_OK) return rc;
+    if ((rc = shard_local_prepare(ctx, d, pl, loc == NVTTB_HOST, false)) != NVTTB_OK) return rc;
     float *const chain = (float *)ctx->lvlA.p;
     const bool isNormal = d->isNormalMap != 0;
     const bool colour = !isNormal;
@@ -1885,7 +2012,6 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     // 1. the band's chunks: upload (copy stream), convert and - for host input - encode level 0 chunk by chunk, so that
     //    the copies of the following chunks hide under the encode
     if (host_in) {
-        if ((rc = ensure(ctx, ctx->in_stage, (size_t)HL * W * bpp)) != NVTTB_OK) return rc;
         CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
         for (int j = 0; j < K; j++) {
             const size_t c = (size_t)j * N + b;
@@ -1940,7 +2066,6 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     if (tail && b == 0) {
         const int w1 = pl.wk / 2 > 1 ? pl.wk / 2 : 1, h1 = pl.hk / 2 > 1 ? pl.hk / 2 : 1;
         const size_t lvl1 = (size_t)4 * w1 * h1;
-        if ((rc = ensure(ctx, ctx->tail_lvl, 2 * lvl1 * sizeof(float))) != NVTTB_OK) { cleanup(); return rc; }
         std::swap(ctx->stream, ctx->tail_stream);
         std::swap(ctx->enc_scratch, ctx->tail_scratch);
         // per-launch event timing (nvttb_profile_*) describes the main stream; launches that overlap it would be counted twice
@@ -2265,6 +2390,13 @@ int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc
                 ctx->multi_seq = 0;
             }
             base.bandExchange = ctx->exchange.p;
+        }
+        if (base.bandExchange) {
+            for (int t = 0; t < bands; t++) {
+                NvttbProcessDesc mine = base;
+                mine.bandIndex = t;
+                if ((rc = nvttb_process_prepare(ctxs[t], &mine, NVTTB_HOST, 1)) != NVTTB_OK) return rc;
+            }
         }
         for (int f = f0; f < f1; f++) {
             base.firstFace = f;

@@ -61,6 +61,10 @@ def test_band_local_front_end_with_exchange(nvtt, ctx, case, host_input):
     ctxs = _contexts(nvtt, world)
     shared = torch.zeros(nw, dtype=torch.uint8, device="cuda")
     try:
+        for b in range(world):  # the bands share ONE GPU here: no allocation while band 0 waits on the device
+            ctxs[b].process_prepare(nvtt.make_process_desc(0, w, h, fmt, q, band_index=b, band_count=world, band_chunk_rows=chunk,
+                                                           band_output_in_place=True, band_exchange=xchg.value, band_sequence=1, **kw),
+                                    location=nvtt.HOST if host_input else nvtt.DEVICE, own_output=False)
         for seq in (1, 2, 3, 4):
             img = (nvtt.synth.photo_bgra8(w, h, seed=10 + seq, alpha=True) if not kw.get("normal_map")
                    else nvtt.synth.normal_bgra8(w, h, seed=10 + seq))
@@ -102,6 +106,9 @@ def test_shard_to_host_buffer(nvtt, ctx):
         try:
             import threading
             errs = []
+            for b in range(world):  # the bands share ONE GPU here: no allocation while band 0 waits on the device
+                ctxs[b].process_prepare(nvtt.make_process_desc(0, w, h, fmt, q, band_index=b, band_count=world, band_chunk_rows=chunk,
+                                                               band_output_in_place=True, band_exchange=xchg.value, band_sequence=1, **kw))
 
             def run(b):
                 try:
