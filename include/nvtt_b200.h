@@ -278,6 +278,25 @@ NVTTB_API int nvttb_ipc_close(NvttbContext *ctx, void *device_ptr);
 /* Bytes of the whole chain of the processed faces, ignoring the band fields (the size of the shared buffer above). */
 NVTTB_API size_t nvttb_process_whole_output_size(const NvttbProcessDesc *desc);
 
+/* ---- DDS / DDS10 container reader (host only): pre-made mip chains as pipeline input ------------------------------------------
+ * Replaces nv::DirectDrawSurface::load / isValid / isSupported / mipmapCount / surfaceSize / offset (src/nvimage/DirectDrawSurface.cpp
+ * :983-1100,1143-1322) for a file image in memory.  blockFormat: nvtt::Format of a BCn file (decode it with
+ * nvttb_surface_set_image_2d), else -1; inputFormat: nvtt::InputFormat when the surfaces can be handed to nvttb_process /
+ * InputOptions::setMipmapData as they are (B8G8R8A8, RGBA16F, RGBA32F, R32F), else -1. */
+typedef struct NvttbDdsInfo {
+    int width, height, depth;
+    int mipCount, faceCount, arraySize;  /* faceCount: 6 for a cube map, else 1 */
+    int textureType;                     /* nvtt::TextureType */
+    int blockFormat, inputFormat;
+    unsigned bitsPerPixel, blockBytes, headerBytes;
+    unsigned dxgiFormat, fourcc;
+    int hasAlpha, isNormalMap;
+} NvttbDdsInfo;
+/* NVTTB_ERR_INVALID_INPUT: not a DDS file / truncated; NVTTB_ERR_UNSUPPORTED_FEATURE: a layout the reference's reader rejects too */
+NVTTB_API int nvttb_dds_describe(const void *file, size_t bytes, NvttbDdsInfo *info);
+/* Byte offset and size of surface (face, mip) inside the file (faces of an array: face = slice * faceCount + cube face) */
+NVTTB_API int nvttb_dds_surface(const NvttbDdsInfo *info, int face, int mip, size_t *offset, size_t *bytes, int *width, int *height, int *depth);
+
 /* Number of mip levels the pipeline produces (nv::countMipmaps, src/nvtt/Surface.cpp:181-193, capped by maxLevel). */
 NVTTB_API int nvttb_process_mip_count(const NvttbProcessDesc *desc);
 

@@ -70,6 +70,31 @@ class ProcessDesc(C.Structure):
                 ("bandExchange", C.c_void_p), ("bandSequence", C.c_uint)]
 
 
+class DdsInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("depth", C.c_int), ("mipCount", C.c_int), ("faceCount", C.c_int),
+                ("arraySize", C.c_int), ("textureType", C.c_int), ("blockFormat", C.c_int), ("inputFormat", C.c_int),
+                ("bitsPerPixel", C.c_uint), ("blockBytes", C.c_uint), ("headerBytes", C.c_uint), ("dxgiFormat", C.c_uint),
+                ("fourcc", C.c_uint), ("hasAlpha", C.c_int), ("isNormalMap", C.c_int)]
+
+
+def read_dds(data):
+    """nvttb_dds_describe + nvttb_dds_surface on a .dds file image (bytes / uint8 array): returns (info, {(face, mip): (w, h, uint8 view)})."""
+    buf = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    L = lib()
+    info = DdsInfo()
+    rc = L.nvttb_dds_describe(buf.ctypes.data, buf.size, C.byref(info))
+    if rc != 0:
+        raise NvttbError(rc, "not a DDS file the reader supports")
+    faces = info.faceCount * (info.arraySize if info.textureType == 3 else 1)
+    out = {}
+    for f in range(faces):
+        for m in range(info.mipCount):
+            off, n, w, h, d = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_int(), C.c_int()
+            assert L.nvttb_dds_surface(C.byref(info), f, m, C.byref(off), C.byref(n), C.byref(w), C.byref(h), C.byref(d)) == 0
+            out[(f, m)] = (w.value, h.value, buf[off.value:off.value + n.value])
+    return info, out
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char_p), ("launches", C.c_int), ("total_ms", C.c_double), ("max_ms", C.c_double),
                 ("total_units", C.c_double), ("max_units", C.c_double)]
@@ -89,7 +114,7 @@ EXPORTS = [
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slices",
-    "nvttb_process_exchange_size", "nvttb_process_prepare", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
+    "nvttb_dds_describe", "nvttb_dds_surface", "nvttb_process_exchange_size", "nvttb_process_prepare", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
     "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
 ]
 
@@ -173,6 +198,8 @@ def lib():
     L.nvttb_process_band_slices.argtypes = [C.POINTER(ProcessDesc), C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
     L.nvttb_process_exchange_size.argtypes = [C.POINTER(ProcessDesc)]
     L.nvttb_process_exchange_size.restype = sz
+    L.nvttb_dds_describe.argtypes = [vp, sz, C.POINTER(DdsInfo)]
+    L.nvttb_dds_surface.argtypes = [C.POINTER(DdsInfo), ci, ci, C.POINTER(sz), C.POINTER(sz), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.nvttb_process_prepare.argtypes = [vp, C.POINTER(ProcessDesc), ci, ci]
     L.nvttb_process_shard.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, vp]
     L.nvttb_process_multi.argtypes = [C.POINTER(vp), ci, C.POINTER(ProcessDesc), C.POINTER(vp), EMIT_FN, vp]

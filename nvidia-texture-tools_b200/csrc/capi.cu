@@ -4,6 +4,7 @@
 // There is no CPU code path: without a CUDA device nvttb_context_create fails and nothing else can be called.
 #include "../../include/nvtt_b200.h"
 #include "host_tables.h"
+#include "dds_reader.h"
 #include "kernels/bc_alpha.cuh"
 #include "kernels/bc3_color.cuh"
 #include "kernels/bc1_icbc.cuh"
@@ -906,7 +907,9 @@ template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDe
     Q.tiles_y = (dh + NVB_PT_TH - 1) / NVB_PT_TH;
     Q.normalize = normalize ? 1 : 0;
     const int ntiles = Q.tiles_x * Q.tiles_y;
-    const int grid = ntiles < 148 * 3 ? ntiles : 148 * 3;  // persistent: three CTAs per SM (69 KB of shared memory each)
+    // persistent: three CTAs per SM (74 KB of shared memory each), every CTA the same number of tiles (+-1)
+    const int per_cta = (ntiles + 148 * 3 - 1) / (148 * 3);
+    const int grid = (ntiles + per_cta - 1) / per_cta;
     ProfRec r_;
     if (ctx->profiling) {
         r_.kid = K_POLY_2D; r_.units = (double)dw * dh;
@@ -935,7 +938,8 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
         return NVTTB_OK;
     };
     static const bool no_tma = getenv("NVB_NO_TMA") != nullptr;
-    if (!no_tma && px.uniform2 && py.uniform2 && px.window == py.window && (sw & 3) == 0 && ((size_t)src & 15) == 0 && dw >= 2 * NVB_PT_TW && dh >= 2 * NVB_PT_TH) {
+    if (!no_tma && px.uniform2 && py.uniform2 && px.window == py.window && px.left0 == -(px.window - 3) / 2 && py.left0 == px.left0 && (sw & 3) == 0 && ((size_t)src & 15) == 0 && dw >= 2 * NVB_PT_TW && dh >= 2 * NVB_PT_TH &&
+        (size_t)dw * dh >= (size_t)128 * NVB_PT_TW * NVB_PT_TH) {  // small levels: more (tile, plane) CTAs beat a persistent loop
         // TMA-fed persistent kernel for the 2:1 mip filters (+ fused renormalisation)
         bool done = false;
         if (px.window == 13) rc = launch_polyphase_tma<13>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);

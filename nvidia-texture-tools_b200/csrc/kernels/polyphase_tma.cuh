@@ -2,9 +2,10 @@
 //   * the source footprint of a 32x32 output tile (75x75 texels for Kaiser) is fetched by TMA (cp.async.bulk.tensor, 3-D tensor
 //     map over [plane][y][x]) into a two-stage shared-memory ring; an mbarrier per stage carries the transaction count, so the
 //     fetch of the next (tile, plane) runs under the arithmetic of the current one and no thread spends registers or issue
-//     slots on staging.  Tiles whose footprint crosses the image border (wrap modes) are staged by hand instead;
+//     slots on staging.  Where a footprint crosses the image border TMA writes zeros; those few positions are then patched
+//     with the texels the wrap mode (clamp / repeat / mirror) selects;
 //   * X pass (FloatImage::applyKernelX, FloatImage.cpp:1115-1144) and Y pass (applyKernelY, :1146-1176) are register blocked:
-//     a thread produces four neighbouring outputs from one sliding window (5 LDS.128 for 52 multiply-adds in X, 19 LDS.32
+//     a thread produces four neighbouring outputs from one sliding window (6 LDS.128 for 52 multiply-adds in X, 19 LDS.32
 //     for 52 in Y) instead of one shared-memory load per multiply-add - the old kernel was LSU bound (58 % LSU pipe);
 //   * the four planes of a tile are consecutive ring entries, so the normal-map renormalisation of the mip
 //     (expandNormals -> normalizeNormalMap -> packNormals, Context.cpp:329-334) is applied to the tile before it is written:
@@ -29,14 +30,22 @@ namespace nvb {
 template <int W> struct PtGeom {
     static constexpr int IN_W = 2 * NVB_PT_TW + W - 2;  // source columns under a tile
     static constexpr int IN_H = 2 * NVB_PT_TH + W - 2;
-    static constexpr int BOX_W = (IN_W + 3) & ~3;        // TMA box rows are multiples of 16 bytes
+    // The innermost TMA coordinate must be a multiple of 16 bytes (measured on B200: any other start faults with "illegal
+    // instruction", profiles/microbench/tma_probe.cu), so the box starts SHIFT texels left of the footprint: left0 = -(W - 3) / 2
+    // for a centred 2:1 filter, and 2 tx0 + left0 - SHIFT is a multiple of 4.
+    static constexpr int LEFT0 = -(W - 3) / 2;
+    static constexpr int SHIFT = ((LEFT0 % 4) + 4) % 4;
+    // box rows: a multiple of 16 bytes, and an ODD number of 16-byte groups so that lanes walking down the rows hit different banks
+    static constexpr int BOX_W0 = (SHIFT + IN_W + 3) & ~3;
+    static constexpr int BOX_W = ((BOX_W0 / 4) & 1) ? BOX_W0 : BOX_W0 + 4;
     static constexpr int TMP_PITCH = NVB_PT_TW + 4;
     static constexpr int STAGE_BYTES = ((BOX_W * IN_H * 4) + 127) & ~127;
     static constexpr int TMP_BYTES = ((IN_H * TMP_PITCH * 4) + 127) & ~127;
     static constexpr int OUT_PITCH = NVB_PT_TW + 1;
     static constexpr int OUT_BYTES = 3 * NVB_PT_TH * OUT_PITCH * 4;
     static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + TMP_BYTES + OUT_BYTES;
-    static constexpr int NV = (2 * 4 + W - 2 + 3) / 4;   // float4 loads per X-pass window
+    static constexpr int NV = (SHIFT + 2 * 4 + W - 2 + 3) / 4;   // float4 loads per X-pass window
+    static_assert(8 * (NVB_PT_TW / 4 - 1) + 4 * NV <= BOX_W, "the last window stays inside the staged row");
 };
 
 struct PolyTmaParams {
@@ -103,107 +112,120 @@ template <int W> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphas
     }
     __syncthreads();
 
-    struct Item {
-        int tx0, ty0, tw, th, plane, x_lo, y_lo;
+    // plain copies of what the loops need (kernel parameters would be re-read from the constant bank at every use)
+    const int sw = P.sw, sh = P.sh, dw = P.dw, dh = P.dh, wrap = P.wrap, tiles_x = P.tiles_x, normalize = P.normalize;
+    const int left0x = P.left0x, left0y = P.left0y;
+    const float *const src = P.src;
+    float *const dst = P.dst;
+    const size_t dn = (size_t)dw * dh;
+
+    struct Tile {
+        int tx0, ty0, tw, th, x_lo, y_lo;
         bool interior;
     };
-    auto item_of = [&](int it) {
-        Item I;
-        const int tile = (int)blockIdx.x + (it >> 2) * (int)gridDim.x;
-        I.plane = it & 3;
-        I.tx0 = (tile % P.tiles_x) * NVB_PT_TW;
-        I.ty0 = (tile / P.tiles_x) * NVB_PT_TH;
-        I.tw = min(NVB_PT_TW, P.dw - I.tx0);
-        I.th = min(NVB_PT_TH, P.dh - I.ty0);
-        I.x_lo = 2 * I.tx0 + P.left0x;
-        I.y_lo = 2 * I.ty0 + P.left0y;
+    auto tile_of = [&](int k) {  // k-th tile of this CTA
+        Tile T;
+        const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+        const int tyi = tile / tiles_x;
+        T.tx0 = (tile - tyi * tiles_x) * NVB_PT_TW;
+        T.ty0 = tyi * NVB_PT_TH;
+        T.tw = min(NVB_PT_TW, dw - T.tx0);
+        T.th = min(NVB_PT_TH, dh - T.ty0);
+        T.x_lo = 2 * T.tx0 + left0x;
+        T.y_lo = 2 * T.ty0 + left0y;
         // TMA fills what lies outside the image with zeros; the wrap modes need real texels there
-        I.interior = I.tw == NVB_PT_TW && I.th == NVB_PT_TH && I.x_lo >= 0 && I.y_lo >= 0 && I.x_lo + G::IN_W <= P.sw && I.y_lo + G::IN_H <= P.sh;
-        return I;
+        T.interior = T.tw == NVB_PT_TW && T.th == NVB_PT_TH && T.x_lo >= 0 && T.y_lo >= 0 && T.x_lo + G::IN_W <= sw && T.y_lo + G::IN_H <= sh;
+        return T;
     };
-    auto issue = [&](int it) {  // thread 0 only
-        const Item I = item_of(it);
-        if (!I.interior) return;
-        const int st = it & 1;
+    auto issue = [&](const Tile &T, int plane, int st) {  // thread 0 only
         // the stage was read (generic proxy) by the X pass two entries ago; order those reads before the async-proxy write
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         pt_mbar_expect_tx(&mbar[st], (unsigned)(G::BOX_W * G::IN_H * 4));
-        pt_tma_load_3d(st ? s_in1 : s_in0, &tmap, &mbar[st], I.x_lo, I.y_lo, I.plane);
+        pt_tma_load_3d(st ? s_in1 : s_in0, &tmap, &mbar[st], T.x_lo - G::SHIFT, T.y_lo, plane);
     };
 
+    // X-pass work split: thread -> (row, first column group); rows run along the lanes (conflict-free 128-bit accesses).
+    // NVB_PT_THREADS = 4 * XROWS: a thread owns one staged row and the column groups xg0 and xg0 + 4.
+    constexpr int XROWS = NVB_PT_THREADS / 4;
+    static_assert(XROWS >= G::IN_H && NVB_PT_TW / 4 == 8, "every staged row has a thread");
+    const int xr = tid % XROWS, xg0 = tid / XROWS;
+    const int yox = tid & (NVB_PT_TW - 1), ygy = tid >> 5;  // Y pass: column, group of four rows (warps 0..7)
+
     unsigned phase_bits = 0u;  // bit st = parity the next wait on stage st expects
-    if (nitems > 0 && tid == 0) issue(0);
+    Tile T = tile_of(0), Tn = T;
+    if (my_tiles > 0 && tid == 0) issue(T, 0, 0);
     for (int it = 0; it < nitems; it++) {
-        if (it + 1 < nitems && tid == 0) issue(it + 1);
-        const Item I = item_of(it);
-        const int st = it & 1;
+        const int plane = it & 3, st = it & 1;
+        if (plane == 3 && (it >> 2) + 1 < my_tiles) Tn = tile_of((it >> 2) + 1);
+        if (it + 1 < nitems && tid == 0) issue(plane == 3 ? Tn : T, (it + 1) & 3, st ^ 1);
         float *const s_in = st ? s_in1 : s_in0;
-        const int nrows = 2 * I.th + W - 2, ncols = 2 * I.tw + W - 2;
-        if (I.interior) {
-            pt_mbar_wait(&mbar[st], (phase_bits >> st) & 1u);
-            phase_bits ^= 1u << st;
-        } else {
-            const float *plane = P.src + (size_t)I.plane * P.sw * P.sh;
-            for (int i = tid; i < nrows * G::BOX_W; i += NVB_PT_THREADS) {
-                const int r = i / G::BOX_W, c = i - r * G::BOX_W;
-                float v = 0.0f;
-                if (c < ncols) v = __ldg(plane + (size_t)wrap_coord(I.y_lo + r, P.sh, P.wrap) * P.sw + wrap_coord(I.x_lo + c, P.sw, P.wrap));
-                s_in[i] = v;
+        pt_mbar_wait(&mbar[st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+        if (!T.interior) {
+            // border tile: TMA has filled what lies outside the image with zeros; the wrap mode wants real texels there.
+            // Only the few out-of-image positions of the footprint are patched (generic stores after the barrier completed).
+            const int nrows = 2 * T.th + W - 2, ncols = 2 * T.tw + W - 2;
+            const float *pl = src + (size_t)plane * sw * sh;
+            for (int i = tid; i < G::IN_H * G::BOX_W; i += NVB_PT_THREADS) {
+                const int r = i / G::BOX_W, c = i - r * G::BOX_W - G::SHIFT;
+                const int sy = T.y_lo + r, sx = T.x_lo + c;
+                if (((unsigned)sy >= (unsigned)sh || (unsigned)sx >= (unsigned)sw) && r < nrows && c >= 0 && c < ncols)
+                    s_in[i] = __ldg(pl + (size_t)wrap_coord(sy, sh, wrap) * sw + wrap_coord(sx, sw, wrap));
             }
             __syncthreads();
         }
-        // X pass: item = (source row, group of four output columns); lanes run along the rows (conflict-free 128-bit accesses)
-        for (int i = tid; i < nrows * (NVB_PT_TW / 4); i += NVB_PT_THREADS) {
-            const int g = i / nrows, r = i - g * nrows;
-            const float4 *row = reinterpret_cast<const float4 *>(s_in + r * G::BOX_W + 8 * g);
-            float s[4 * G::NV];
+        // X pass
+        if (xr < G::IN_H) {
 #pragma unroll
-            for (int k = 0; k < G::NV; k++) {
-                const float4 v = row[k];
-                s[4 * k] = v.x;
-                s[4 * k + 1] = v.y;
-                s[4 * k + 2] = v.z;
-                s[4 * k + 3] = v.w;
+            for (int half = 0; half < 2; half++) {
+                const int g = xg0 + 4 * half;
+                const float4 *row = reinterpret_cast<const float4 *>(s_in + xr * G::BOX_W + 8 * g);
+                float s[4 * G::NV];
+#pragma unroll
+                for (int k = 0; k < G::NV; k++) {
+                    const float4 v = row[k];
+                    s[4 * k] = v.x;
+                    s[4 * k + 1] = v.y;
+                    s[4 * k + 2] = v.z;
+                    s[4 * k + 3] = v.w;
+                }
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < W; j++) a += wx[j] * s[G::SHIFT + 2 * q + j];
+                    o[q] = a;
+                }
+                *reinterpret_cast<float4 *>(s_tmp + xr * G::TMP_PITCH + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            float o[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                float a = 0.0f;
-#pragma unroll
-                for (int j = 0; j < W; j++) a += wx[j] * s[2 * q + j];
-                o[q] = a;
-            }
-            *reinterpret_cast<float4 *>(s_tmp + r * G::TMP_PITCH + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
-        // Y pass: item = (output column, group of four output rows); lanes run along the columns
-        const bool keep = P.normalize && I.plane < 3;
-        float *const dplane = P.dst + (size_t)I.plane * P.dw * P.dh;
-        for (int i = tid; i < NVB_PT_TW * (NVB_PT_TH / 4); i += NVB_PT_THREADS) {
-            const int ox = i & (NVB_PT_TW - 1), gy = i >> 5;
-            if (4 * gy >= I.th) continue;
+        // Y pass
+        const bool keep = normalize && plane < 3;
+        if (ygy < NVB_PT_TH / 4 && 4 * ygy < T.th) {
             float s[2 * 4 + W - 2];
 #pragma unroll
-            for (int k = 0; k < 2 * 4 + W - 2; k++) s[k] = s_tmp[(8 * gy + k) * G::TMP_PITCH + ox];
+            for (int k = 0; k < 2 * 4 + W - 2; k++) s[k] = s_tmp[(8 * ygy + k) * G::TMP_PITCH + yox];
+            float *const drow = dst + (size_t)plane * dn + (size_t)(T.ty0 + 4 * ygy) * dw + T.tx0 + yox;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 float a = 0.0f;
 #pragma unroll
                 for (int j = 0; j < W; j++) a += wy[j] * s[2 * q + j];
-                const int oy = 4 * gy + q;
-                if (oy < I.th && ox < I.tw) {
-                    if (keep) s_out[(I.plane * NVB_PT_TH + oy) * G::OUT_PITCH + ox] = a;
-                    else dplane[(size_t)(I.ty0 + oy) * P.dw + I.tx0 + ox] = a;
+                const int oy = 4 * ygy + q;
+                if (oy < T.th && yox < T.tw) {
+                    if (keep) s_out[(plane * NVB_PT_TH + oy) * G::OUT_PITCH + yox] = a;
+                    else drow[(size_t)q * dw] = a;
                 }
             }
         }
         __syncthreads();
-        if (P.normalize && I.plane == 2) {
+        if (normalize && plane == 2) {
             // the tile's x, y, z are complete: FloatImage::scaleBias(2, -1), normalize (normalizeSafe, epsilon 0), scaleBias(0.5, 0.5)
-            const size_t dn = (size_t)P.dw * P.dh;
             for (int i = tid; i < NVB_PT_TW * NVB_PT_TH; i += NVB_PT_THREADS) {
                 const int ox = i & (NVB_PT_TW - 1), oy = i >> 5;
-                if (ox >= I.tw || oy >= I.th) continue;
+                if (ox >= T.tw || oy >= T.th) continue;
                 float x = s_out[(0 * NVB_PT_TH + oy) * G::OUT_PITCH + ox], y = s_out[(1 * NVB_PT_TH + oy) * G::OUT_PITCH + ox],
                       z = s_out[(2 * NVB_PT_TH + oy) * G::OUT_PITCH + ox];
                 x = 2.0f * x + -1.0f;
@@ -219,13 +241,14 @@ template <int W> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphas
                 x = 0.5f * x + 0.5f;
                 y = 0.5f * y + 0.5f;
                 z = 0.5f * z + 0.5f;
-                const size_t o = (size_t)(I.ty0 + oy) * P.dw + I.tx0 + ox;
-                P.dst[o] = x;
-                P.dst[dn + o] = y;
-                P.dst[2 * dn + o] = z;
+                const size_t o = (size_t)(T.ty0 + oy) * dw + T.tx0 + ox;
+                dst[o] = x;
+                dst[dn + o] = y;
+                dst[2 * dn + o] = z;
             }
             // s_out is next written by the Y pass of the following tile's plane 0, two barriers from here
         }
+        if (plane == 3) T = Tn;
     }
 }
 #endif  // NVB_EMU

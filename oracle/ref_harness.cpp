@@ -123,6 +123,12 @@ struct RefProcessDesc {
     unsigned bitcount, rmask, gmask, bmask, amask;
     int rsize, gsize, bsize, asize;
     int pitchAlignment;
+    // InputOptions::setMaxExtents / setRoundMode (0 / RoundMode_None = leave the defaults), and caller-supplied mip levels:
+    // mipImages[mip * faces + f] for mip >= 1 (userMips = number of levels incl. level 0 present in the array; NULL entries are
+    // levels the caller leaves to the filter)
+    int maxExtent, roundMode;
+    int userMips;
+    const void *const *mipImages;
 };
 
 // Whole InputOptions pipeline: Compressor::process (src/nvtt/Context.cpp:117-120,217-346).
@@ -132,6 +138,17 @@ long ref_process(const RefProcessDesc *d, const void *const *images, unsigned ch
     io.setTextureLayout((TextureType)d->textureType, d->width, d->height, 1, d->textureType == TextureType_Array ? d->faces : 1);
     io.setFormat((InputFormat)d->inputFormat);
     for (int f = 0; f < d->faces; f++) io.setMipmapData(images[f], d->width, d->height, 1, f, 0);
+    if (d->userMips > 1 && d->mipImages) {
+        int w = d->width, h = d->height;
+        for (int m = 1; m < d->userMips; m++) {
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+            for (int f = 0; f < d->faces; f++)
+                if (d->mipImages[m * d->faces + f]) io.setMipmapData(d->mipImages[m * d->faces + f], w, h, 1, f, m);
+        }
+    }
+    if (d->maxExtent > 0) io.setMaxExtents(d->maxExtent);
+    if (d->roundMode != 0) io.setRoundMode((RoundMode)d->roundMode);
     io.setWrapMode((WrapMode)d->wrapMode);
     io.setMipmapFilter((MipmapFilter)d->mipmapFilter);
     io.setMipmapGeneration(d->generateMipmaps != 0, d->maxLevel);

@@ -42,6 +42,7 @@ class RefProcessDesc(C.Structure):
         ("bitcount", C.c_uint), ("rmask", C.c_uint), ("gmask", C.c_uint), ("bmask", C.c_uint), ("amask", C.c_uint),
         ("rsize", C.c_int), ("gsize", C.c_int), ("bsize", C.c_int), ("asize", C.c_int),
         ("pitchAlignment", C.c_int),
+        ("maxExtent", C.c_int), ("roundMode", C.c_int), ("userMips", C.c_int), ("mipImages", C.c_void_p),
     ]
 
 
@@ -122,7 +123,7 @@ def process(images, input_format, w, h, fmt, quality, *, wrap=WrapMode_Mirror, m
             to_normal_map=False, normalize_mipmaps=True, alpha_mode=AlphaMode_None,
             pixel_type=PixelType_UnsignedNorm, color_weights=(1, 1, 1, 1), header=False, container=Container_DDS,
             texture_type=TextureType_2D, threads=0, fast=False, quantization=0, alpha_threshold=127,
-            pixel_masks=None, pixel_sizes=None, pitch_alignment=0):
+            pixel_masks=None, pixel_sizes=None, pitch_alignment=0, max_extent=0, round_mode=0, user_mips=None, lib_override=None):
     """Whole Compressor::process pipeline on the reference; images = list of per-face level-0 arrays.
     pixel_masks = (bitcount, rmask, gmask, bmask, amask) or pixel_sizes = (r, g, b, a) select the Format_RGBA layout."""
     d = RefProcessDesc()
@@ -138,7 +139,18 @@ def process(images, input_format, w, h, fmt, quality, *, wrap=WrapMode_Mirror, m
     d.outputHeader, d.container, d.threads = int(header), container, threads
     imgs = [np.ascontiguousarray(i) for i in images]
     ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
-    L = lib(fast)
+    d.maxExtent, d.roundMode = max_extent, round_mode
+    keep = []
+    if user_mips:  # {(face, mip): array} for mip >= 1
+        levels = max(m for _, m in user_mips) + 1
+        arr = (C.c_void_p * (levels * len(imgs)))()
+        for (f, m), a in user_mips.items():
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            arr[m * len(imgs) + f] = a.ctypes.data
+        keep.append(arr)
+        d.userMips, d.mipImages = levels, C.cast(arr, C.c_void_p)
+    L = lib_override if lib_override is not None else lib(fast)
     n = L.ref_process(C.byref(d), ptrs, None, 0)
     if n < 0:
         raise RuntimeError("ref_process failed")

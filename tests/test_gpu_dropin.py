@@ -129,6 +129,33 @@ def test_color_dithering_pipeline_identical(nvtt, ref, ours):
         assert got.size == want.size and np.array_equal(got, want), fmt
 
 
+def test_process_general_path_extents_round_modes_user_mips(nvtt, ref, ours):
+    """Compressor::process outside the fused pipeline (Context.cpp:233-245,291-323; Surface.cpp:220-327 getTargetExtent): input
+    resize through setMaxExtents with every RoundMode, and caller-supplied mip levels (all of them, or only the first ones -
+    the chain continues from the last supplied level with the filter)."""
+    img = nvtt.synth.photo_bgra8(200, 120, seed=12, alpha=True)
+    for fmt, q, kw in ((ref.Format_BC1, 1, dict(mip_filter=0)), (ref.Format_BC3, 1, dict(mip_filter=2)), (ref.Format_BC5, 1, dict(mip_filter=1, normal_map=True))):
+        for round_mode in range(7):
+            for max_extent in (0, 64, 100):
+                if round_mode == 0 and max_extent == 0:
+                    continue
+                a = ref.process([img], 0, 200, 120, fmt, q, header=True, max_extent=max_extent, round_mode=round_mode, lib_override=ours, **kw)
+                b = ref.process([img], 0, 200, 120, fmt, q, header=True, max_extent=max_extent, round_mode=round_mode, **kw)
+                assert a.size == b.size and np.array_equal(a, b), (fmt, round_mode, max_extent)
+    # user-supplied mip levels
+    base = nvtt.synth.photo_bgra8(64, 32, seed=13, alpha=True)
+    mips, w, h, m = {}, 64, 32, 0
+    while w > 1 or h > 1:
+        w, h, m = max(1, w // 2), max(1, h // 2), m + 1
+        mips[(0, m)] = nvtt.synth.photo_bgra8(w, h, seed=100 + m, alpha=True)  # deliberately unrelated to level 0
+    first_two = {k: v for k, v in mips.items() if k[1] <= 2}
+    for fmt, kw in ((ref.Format_BC1, dict(mip_filter=0)), (ref.Format_BC3, dict(mip_filter=2)), (ref.Format_BC1, dict(mip_filter=0, container=2))):
+        for user in (mips, first_two):
+            a = ref.process([base], 0, 64, 32, fmt, 1, header=True, user_mips=user, lib_override=ours, **kw)
+            b = ref.process([base], 0, 64, 32, fmt, 1, header=True, user_mips=user, **kw)
+            assert a.size == b.size and np.array_equal(a, b), (fmt, kw, len(user))
+
+
 def test_ktx_cube_identical(nvtt, ref, ours):
     """Six faces through the KTX container: the faces of a level are stored together (Context.cpp:347-472)."""
     faces = [nvtt.synth.photo_bgra8(32, 32, seed=20 + f) for f in range(6)]
