@@ -73,3 +73,14 @@ def test_nvcompress_byte_identical(files, name, args):
         a, b = np.frombuffer(got, np.uint8), np.frombuffer(want, np.uint8)
         bad = np.nonzero(a != b)[0]
         raise AssertionError("%s %s: %d of %d bytes differ, first at %d" % (name, args, bad.size, a.size, int(bad[0])))
+
+
+def test_nvcompress_dds_input_with_premade_mips(files):
+    """A .dds with its own mip chain as INPUT (tools/compress.cpp:506-557: every surface goes to InputOptions::setMipmapData)."""
+    src = os.path.join(files["dir"], "premade.dds")
+    _run(REF, ["-rgb", "-mipfilter", "kaiser"], files["alpha"], src)  # BGRA8 .dds with a Kaiser chain
+    for args in (["-bc1"], ["-bc3", "-alpha"], ["-bc1", "-nomips"]):
+        tag = "premade_" + "_".join(a.strip("-") for a in args)
+        want = _run(REF, args, src, os.path.join(files["dir"], tag + "_ref.dds"))
+        got = _run(OURS, args, src, os.path.join(files["dir"], tag + "_b200.dds"))
+        assert got == want, args
