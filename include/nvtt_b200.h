@@ -249,7 +249,9 @@ NVTTB_API size_t nvttb_process_exchange_size(const NvttbProcessDesc *desc);
 /* One band's share of ONE block-row sharded image (desc->bandCount > 1).  out_device: whole-chain layout (this GPU's or a
  * peer's memory; NULL = an internal buffer); out_host (optional): pinned / registered host memory in the whole-chain layout -
  * the band's slices are also copied there (each GPU writes its slice of the output over its own PCIe link).  Host images may
- * be pageable or pinned.  Synchronous when out_host or a host image is given, asynchronous on the context's stream otherwise. */
+ * be pageable or pinned - but when several bands share ONE GPU (tests) use pinned memory: a pageable copy is synchronous inside
+ * the driver and was measured to wait while band 0's device-side wait kernel is resident, so the band would never deliver.
+ * Synchronous when out_host or a host image is given, asynchronous on the context's stream otherwise. */
 NVTTB_API int nvttb_process_shard(NvttbContext *ctx, const NvttbProcessDesc *desc, const void *const *images, int images_location,
                                   void *out_device, void *out_host);
 /* Sizes every device buffer a band-local nvttb_process_shard / nvttb_process_to_device call with this description will use, so

@@ -206,6 +206,9 @@ int nvttb_device_count(void) {
 int nvttb_context_create(int device, NvttbContext **out) {
     if (!out) return NVTTB_ERR_INVALID_INPUT;
     *out = nullptr;
+    // Streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); the copy / tail / mode streams of a
+    // context overlap best when they do not share one.  Only effective before the process creates its CUDA context.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
@@ -229,7 +232,6 @@ int nvttb_context_create(int device, NvttbContext **out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     for (int i = 0; i < 8; i++) {
-        if ((e = cudaStreamCreateWithFlags(&ctx->mode_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
         for (int p = 0; p < 2; p++)
             if ((e = cudaEventCreateWithFlags(&ctx->ev_join[p][i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
@@ -474,6 +476,14 @@ int nvttb_format_supported(int format, int quality) {
 }
 
 }  // extern "C"
+
+// The side streams of the BC6H / BC7 encoders are created on first use: streams share a small number of hardware queues
+// (CUDA_DEVICE_MAX_CONNECTIONS), and work queued behind a waiting kernel of another stream in the same queue cannot start.
+static int ensure_mode_streams(NvttbContext *ctx) {
+    for (int i = 0; i < 8; i++)
+        if (!ctx->mode_stream[i]) CK(cudaStreamCreateWithFlags(&ctx->mode_stream[i], cudaStreamNonBlocking));
+    return NVTTB_OK;
+}
 
 // BC7, one mode of one chunk of blocks, on the mode's own stream: rough shape ranking (modes 0,1,2,3,7), start endpoints
 // per candidate, the searcher state machine, finish + reduction over the block's candidates.
@@ -724,6 +734,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         // texel tile (256), meta (2 x 16), start endpoints (3 x 32), start indices (2 x 8), results (3 x 32), order (2 x 4)
         int rc = ensure(ctx, ctx->enc_scratch, encoder_scratch_bytes(F_BC6, w, h));
         if (rc != NVTTB_OK) return rc;
+        if ((rc = ensure_mode_streams(ctx)) != NVTTB_OK) return rc;
         Bc6Params P;
         P.lv = lv;
         P.out = d_out;
@@ -780,6 +791,7 @@ static int encode_device(NvttbContext *ctx, const NvttbEncodeDesc *d, const floa
         // texel tile and the setup / result records of every searcher (Bc7ModeBytes)
         int rc = ensure(ctx, ctx->enc_scratch, encoder_scratch_bytes(F_BC7, w, h));
         if (rc != NVTTB_OK) return rc;
+        if ((rc = ensure_mode_streams(ctx)) != NVTTB_OK) return rc;
         Bc7Params P;
         P.lv = lv;
         P.out = d_out;
@@ -1949,6 +1961,7 @@ static int shard_local_prepare(NvttbContext *ctx, const NvttbProcessDesc *d, con
     if (own_out && (rc = ensure(ctx, ctx->out_dev, whole_face_bytes(d))) != NVTTB_OK) return rc;
     const size_t es = encoder_scratch_bytes(d->encode.format, W, HL);
     if (es && (rc = ensure(ctx, ctx->enc_scratch, es)) != NVTTB_OK) return rc;
+    if (es && (rc = ensure_mode_streams(ctx)) != NVTTB_OK) return rc;
     if (pl.k < pl.mips - 1 && g.b == 0) {
         const int w1 = pl.wk / 2 > 1 ? pl.wk / 2 : 1, h1 = pl.hk / 2 > 1 ? pl.hk / 2 : 1;
         if ((rc = ensure(ctx, ctx->tail_lvl, (size_t)2 * 4 * w1 * h1 * sizeof(float))) != NVTTB_OK) return rc;
@@ -2376,7 +2389,11 @@ int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc
         bool peers = true;
         for (int t = 1; t < bands && peers; t++) {
             int can = 0;
-            if (ctxs[t]->device == ctx->device) continue;  // several contexts on one GPU (tests): plain device memory
+            // Two bands on ONE GPU: the caller's images are usually pageable, a pageable copy is synchronous in the driver and
+            // (measured) waits while band 0's device-side wait is resident - the band would never deliver.  Replicated front end.
+            for (int u = 0; u < t; u++)
+                if (ctxs[u]->device == ctxs[t]->device) peers = false;
+            if (!peers) break;
             if (cudaDeviceCanAccessPeer(&can, ctxs[t]->device, ctx->device) != cudaSuccess || !can) peers = false;
             if (peers) {
                 cudaSetDevice(ctxs[t]->device);

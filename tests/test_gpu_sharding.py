@@ -10,8 +10,18 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _contexts(nvtt, n):
-    return [nvtt.Context(0) for _ in range(n)]
+def _contexts(nvtt, n, spread=False):
+    """n contexts on GPU 0 - or, with spread, dealt over the GPUs of the box (one GPU: all on it)."""
+    ndev = max(1, nvtt.lib().nvttb_device_count())
+    return [nvtt.Context(i % ndev if spread else 0) for i in range(n)]
+
+
+def _pinned(a):
+    """Host buffers of bands that share one GPU must be pinned (pageable copies are synchronous in the driver and wait while
+    band 0's device-side wait is resident).  Returns (numpy view, owner)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy(), t
 
 
 CASES = [
@@ -72,12 +82,13 @@ def test_band_local_front_end_with_exchange(nvtt, ctx, case, host_input):
             shared.zero_()
             torch.cuda.synchronize()
             d_img = torch.from_numpy(img).cuda()
+            pimg, _keep = _pinned(img)
             # band 0 last: with host input the call blocks until the texels are consumed, and band 0's tail waits for the others
             for b in list(range(1, world)) + [0]:
                 d = nvtt.make_process_desc(0, w, h, fmt, q, band_index=b, band_count=world, band_chunk_rows=chunk,
                                            band_output_in_place=True, band_exchange=xchg.value, band_sequence=seq, **kw)
                 if host_input:
-                    ctxs[b].process_to_device([img], d, shared.data_ptr(), nw, location=nvtt.HOST)
+                    ctxs[b].process_to_device([pimg], d, shared.data_ptr(), nw, location=nvtt.HOST)
                 else:
                     ctxs[b].process_to_device([d_img.data_ptr()], d, shared.data_ptr(), nw)
             for c in ctxs:
@@ -93,7 +104,7 @@ def test_shard_to_host_buffer(nvtt, ctx):
     """nvttb_process_shard with a host output: every band copies its slices into ONE host buffer in the whole-chain layout."""
     w, h, world, chunk = 256, 256, 4, 16
     L = nvtt.lib()
-    img = nvtt.synth.photo_bgra8(w, h, seed=21, alpha=True)
+    img, _keep_img = _pinned(nvtt.synth.photo_bgra8(w, h, seed=21, alpha=True))
     for fmt, q, kw in ((nvtt.Format_BC1, 2, {}), (nvtt.Format_BC3, 1, dict(mip_filter=2))):  # Kaiser: replicated front end
         whole = ctx.process_bytes([img], nvtt.make_process_desc(0, w, h, fmt, q, **kw))
         d0 = nvtt.make_process_desc(0, w, h, fmt, q, band_index=0, band_count=world, band_chunk_rows=chunk, **kw)
@@ -101,7 +112,7 @@ def test_shard_to_host_buffer(nvtt, ctx):
         xchg = C.c_void_p()
         if xbytes:
             ctx._ck(L.nvttb_device_alloc(ctx.h, xbytes, C.byref(xchg)))
-        host = np.zeros(whole.size, np.uint8)
+        host, _keep_host = _pinned(np.zeros(whole.size, np.uint8))
         ctxs = _contexts(nvtt, world)
         try:
             import threading
@@ -134,7 +145,7 @@ def test_shard_to_host_buffer(nvtt, ctx):
 
 def test_process_multi(nvtt, ref, ctx):
     """nvttb_process_multi: one call, several contexts (GPUs), host images in, the single-GPU emit sequence out."""
-    ctxs = _contexts(nvtt, 4)
+    ctxs = _contexts(nvtt, 4, spread=True)  # on a multi-GPU box: really one context per GPU (band-local front end, peer exchange)
     try:
         # one large image: block-row sharded (Box: band-local front end; Kaiser: replicated front end)
         img = nvtt.synth.photo_bgra8(1024, 1024, seed=2, alpha=True)
