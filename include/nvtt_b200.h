@@ -47,6 +47,11 @@ typedef struct NvttbSurface NvttbSurface; /* device-resident planar fp32 RGBA im
 /* ---- context -------------------------------------------------------------------------------------------- */
 /* Number of CUDA devices visible (0 if none / no driver).  Replaces nv::cuda::isHardwarePresent (src/nvtt/cuda/CudaUtils.cpp). */
 NVTTB_API int nvttb_device_count(void);
+/* Which arithmetic contract this build of the library follows: "strict" (libnvtt_b200.so: nvcc -fmad=false, every fp32
+ * operation rounded like the reference's -ffp-contract=off build - the parity contract) or "fastmath"
+ * (libnvtt_b200_fastmath.so: the same sources with FMA contraction allowed - faster, NOT bit-identical to the reference;
+ * SURVEY.md 7.2 item 7).  Same symbols in both; a caller picks one at link / dlopen time. */
+NVTTB_API const char *nvttb_build_variant(void);
 /* Create a context on `device`.  Replaces Compressor::Compressor + enableCudaAcceleration (src/nvtt/Context.cpp:61-98). */
 NVTTB_API int nvttb_context_create(int device, NvttbContext **out);
 NVTTB_API void nvttb_context_destroy(NvttbContext *ctx);

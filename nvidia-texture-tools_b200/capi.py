@@ -5,7 +5,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200.so")
+# NVTT_B200_FASTMATH=1 selects the FMA-contracted build (same C ABI, faster, outside the bit-exact parity contract)
+FASTMATH = os.environ.get("NVTT_B200_FASTMATH", "0") not in ("", "0")
+LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200_fastmath.so" if FASTMATH else "libnvtt_b200.so")
 
 # nvtt enums (src/nvtt/nvtt.h:80-277 of the reference)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)
@@ -103,7 +105,7 @@ class KernelStat(C.Structure):
 EMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t)
 
 EXPORTS = [
-    "nvttb_device_count", "nvttb_context_create", "nvttb_context_destroy", "nvttb_last_error", "nvttb_launch_count",
+    "nvttb_device_count", "nvttb_build_variant", "nvttb_context_create", "nvttb_context_destroy", "nvttb_last_error", "nvttb_launch_count",
     "nvttb_synchronize", "nvttb_stream", "nvttb_timer_start", "nvttb_timer_stop", "nvttb_profile_begin", "nvttb_profile_end", "nvttb_level_size", "nvttb_format_supported", "nvttb_encode_level", "nvttb_pixel_format_level_size", "nvttb_convert_level",
     "nvttb_surface_create", "nvttb_surface_destroy", "nvttb_surface_clone", "nvttb_surface_set_wrap_mode",
     "nvttb_surface_set_alpha_mode", "nvttb_surface_set_normal_map", "nvttb_surface_width", "nvttb_surface_height",
@@ -130,6 +132,7 @@ def lib():
         raise RuntimeError("%s is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     L = C.CDLL(LIB_PATH)
     vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    L.nvttb_build_variant.restype = C.c_char_p
     L.nvttb_context_create.argtypes = [ci, C.POINTER(vp)]
     L.nvttb_context_destroy.argtypes = [vp]
     L.nvttb_last_error.argtypes = [vp]

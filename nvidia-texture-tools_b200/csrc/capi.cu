@@ -373,6 +373,13 @@ void nvttb_context_destroy(NvttbContext *ctx) {
 
 const char *nvttb_last_error(const NvttbContext *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t nvttb_launch_count(const NvttbContext *ctx) { return ctx ? ctx->launches : 0; }
+const char *nvttb_build_variant(void) {
+#ifdef NVB_FASTMATH
+    return "fastmath";
+#else
+    return "strict";
+#endif
+}
 void *nvttb_stream(NvttbContext *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int nvttb_synchronize(NvttbContext *ctx) {
     if (!ctx) return NVTTB_ERR_INVALID_INPUT;

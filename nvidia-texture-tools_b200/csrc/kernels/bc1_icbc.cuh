@@ -96,15 +96,23 @@ NVB_DEV void icbc_palette32(unsigned c0, unsigned c1, unsigned pr[4], unsigned p
 struct Pal3 {
     float x[4], y[4], z[4];
 };
+// float(v) / 255.0f for an integer v in [0, 255], correctly rounded: q = v * r with r = fl(1 / 255), one Newton step on the
+// remainder - the IEEE division's own fast path without its range check and slow-path call (4 instructions instead of 12;
+// the palette is rebuilt for every refinement candidate).  Equal to the division for all 256 inputs: tests/test_capi_boundary.py.
+NVB_DEV float icbc_u8_to_float(unsigned v) {
+    const float x = (float)v, r = __uint_as_float(0x3b808081u);
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(r, __fmaf_rn(q, -255.0f, x), q);
+}
 NVB_DEV Pal3 icbc_palette_f(unsigned c0, unsigned c1) {
     unsigned pr[4], pg[4], pb[4];
     icbc_palette32(c0, c1, pr, pg, pb);
     Pal3 p;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        p.x[i] = (float)pr[i] / 255.0f;
-        p.y[i] = (float)pg[i] / 255.0f;
-        p.z[i] = (float)pb[i] / 255.0f;
+        p.x[i] = icbc_u8_to_float(pr[i]);
+        p.y[i] = icbc_u8_to_float(pg[i]);
+        p.z[i] = icbc_u8_to_float(pb[i]);
     }
     return p;
 }
@@ -115,11 +123,15 @@ NVB_DEV float dist2w(float cx, float cy, float cz, float px, float py, float pz)
     return dx * dx + dy * dy + dz * dz;
 }
 
+// U = the colour weights are (1, 1, 1), the reference's default: x * 1.0f is x bit for bit, so the kernels instantiated with
+// U leave those multiplications out (3 per split, 3 per texel of every refinement candidate).
+template <bool U> NVB_DEV float cw_mul(float x, float w) { return U ? x : x * w; }
+
 // per-texel squared error term of evaluate_mse: |(p - c) * w * 255|^2
-NVB_DEV float mse_term(float px, float py, float pz, float cx, float cy, float cz, const float cw[3]) {
-    const float dx = (px - cx) * cw[0] * 255.0f;
-    const float dy = (py - cy) * cw[1] * 255.0f;
-    const float dz = (pz - cz) * cw[2] * 255.0f;
+template <bool U> NVB_DEV float mse_term(float px, float py, float pz, float cx, float cy, float cz, const float cw[3]) {
+    const float dx = cw_mul<U>(px - cx, cw[0]) * 255.0f;
+    const float dy = cw_mul<U>(py - cy, cw[1]) * 255.0f;
+    const float dz = cw_mul<U>(pz - cz, cw[2]) * 255.0f;
     return dx * dx + dy * dy + dz * dz;
 }
 
@@ -133,6 +145,7 @@ NVB_DEV unsigned group_gather_bits2(unsigned gm, unsigned idx, int l) {
 NVB_DEV float select4(const float v[4], unsigned i) { return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : v[3]; }
 
 // output_block4 / output_block3: endpoints -> 565, palette, per-texel index, weighted MSE (ordered sum).
+template <bool U>
 NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool four, bool allow_black, float sx, float sy, float sz,
                                 float ex, float ey, float ez, float cx, float cy, float cz, float wt, Bc1Block *blk) {
     unsigned color0 = icbc_vector3_to_color16(P, sx, sy, sz);
@@ -141,12 +154,13 @@ NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool fou
         const unsigned t = color0; color0 = color1; color1 = t;
     }
     const Pal3 pal = icbc_palette_f(color0, color1);
-    const float vcx = cx * P.cw[0], vcy = cy * P.cw[1], vcz = cz * P.cw[2];
+    const float vcx = cw_mul<U>(cx, P.cw[0]), vcy = cw_mul<U>(cy, P.cw[1]), vcz = cw_mul<U>(cz, P.cw[2]);
     float d[4];
     unsigned idx;
     if (four) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = dist2w(vcx, vcy, vcz, pal.x[i] * P.cw[0], pal.y[i] * P.cw[1], pal.z[i] * P.cw[2]);
+        for (int i = 0; i < 4; i++)
+            d[i] = dist2w(vcx, vcy, vcz, cw_mul<U>(pal.x[i], P.cw[0]), cw_mul<U>(pal.y[i], P.cw[1]), cw_mul<U>(pal.z[i], P.cw[2]));
         const bool b1 = d[1] > d[2], b2 = d[0] > d[2];
         bool x0 = b1 && b2;
         const bool b0 = d[0] > d[3], b3 = d[1] > d[3];
@@ -157,7 +171,8 @@ NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool fou
     } else {
         // note the operand order vp - vc here (compute_indices3)
 #pragma unroll
-        for (int i = 0; i < 3; i++) d[i] = dist2w(pal.x[i] * P.cw[0], pal.y[i] * P.cw[1], pal.z[i] * P.cw[2], vcx, vcy, vcz);
+        for (int i = 0; i < 3; i++)
+            d[i] = dist2w(cw_mul<U>(pal.x[i], P.cw[0]), cw_mul<U>(pal.y[i], P.cw[1]), cw_mul<U>(pal.z[i], P.cw[2]), vcx, vcy, vcz);
         const bool i1 = d[1] < d[2];
         const bool i2 = (d[2] <= d[0]) && (d[2] <= d[1]);
         bool i3 = false;
@@ -171,15 +186,7 @@ NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool fou
     blk->c0 = color0;
     blk->c1 = color1;
     blk->indices = group_gather_bits2(gm, idx, l);
-    const float t = wt * mse_term(select4(pal.x, idx), select4(pal.y, idx), select4(pal.z, idx), cx, cy, cz, P.cw);
-    return group_ordered_sum(gm, t);
-}
-
-// evaluate_mse(input_colors, input_weights, color_weights, const BlockDXT1*)
-NVB_DEV float icbc_evaluate_block_mse(const Bc1Params &P, unsigned gm, int l, const Bc1Block &b, float cx, float cy, float cz, float wt) {
-    const Pal3 pal = icbc_palette_f(b.c0, b.c1);
-    const unsigned idx = (b.indices >> (2 * l)) & 3u;
-    const float t = wt * mse_term(select4(pal.x, idx), select4(pal.y, idx), select4(pal.z, idx), cx, cy, cz, P.cw);
+    const float t = wt * mse_term<U>(select4(pal.x, idx), select4(pal.y, idx), select4(pal.z, idx), cx, cy, cz, P.cw);
     return group_ordered_sum(gm, t);
 }
 
@@ -256,6 +263,16 @@ NVB_DEV void icbc_compute_sat(Bc1GroupSmem &S, unsigned gm, int l, int n) {
     __syncwarp(gm);
 }
 
+// refine_endpoints' table of endpoint moves (icbc.h:3329-3348), one word per channel: field k = deltas[k][channel] + 1
+constexpr unsigned icbc_delta_word(int ch) {
+    constexpr int deltas[16][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {1, 1, 0}, {1, 0, 1},
+                                   {0, 1, 1}, {-1, -1, 0}, {-1, 0, -1}, {0, -1, -1}, {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}};
+    unsigned w = 0;
+    for (int k = 0; k < 16; k++) w |= (unsigned)(deltas[k][ch] + 1) << (2 * k);
+    return w;
+}
+constexpr unsigned DWR = icbc_delta_word(0), DWG = icbc_delta_word(1), DWB = icbc_delta_word(2);
+
 struct FitResult {
     float sx, sy, sz, ex, ey, ez;
 };
@@ -266,7 +283,7 @@ NVB_DEV float icbc_round5(float x) { return truncf(icbc_saturate(x) * 31.0f + 0.
 NVB_DEV float icbc_round6(float x) { return truncf(icbc_saturate(x) * 63.0f + 0.5f) * (1.0f / 63.0f); }
 
 // One split of cluster_fit_four (FOUR) or cluster_fit_three.  Returns the error; a/b = snapped endpoints.
-template <bool FOUR>
+template <bool FOUR, bool U>
 NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const float msq[3], float a[3], float b[3]) {
     const int c0 = (int)(pk & 31), c1 = (int)((pk >> 5) & 31), c2 = (int)((pk >> 10) & 31);  // index + 1; sat[0] = 0
     const float4 s0 = sat[c0];
@@ -315,7 +332,7 @@ NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const 
         a[k] = av;
         b[k] = bv;
     }
-    return e1[0] * msq[0] + e1[1] * msq[1] + e1[2] * msq[2];
+    return cw_mul<U>(e1[0], msq[0]) + cw_mul<U>(e1[1], msq[1]) + cw_mul<U>(e1[2], msq[2]);
 }
 
 // Two splits at once (A, B): every quantity of icbc_eval_split is carried as a pair so that the multiplications issue as
@@ -329,7 +346,7 @@ NVB_DEV float2 icbc_round_pair(float2 num, float2 factor, float grid, float grid
     const float2 t = f2add_s(f2mul(s, f2splat(grid)), f2splat(0.5f));
     return f2mul(make_float2(truncf(t.x), truncf(t.y)), f2splat(gridrcp));
 }
-template <bool FOUR>
+template <bool FOUR, bool U>
 NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, float4 sum, const float msq[3]) {
     const int a0 = (int)(pka & 31), a1 = (int)((pka >> 5) & 31), a2 = (int)((pka >> 10) & 31);  // index + 1; sat[0] = 0
     const int b0 = (int)(pkb & 31), b1 = (int)((pkb >> 5) & 31), b2 = (int)((pkb >> 10) & 31);
@@ -378,13 +395,14 @@ NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, flo
         const float2 e2 = f2mul(f2sub_s(f2mul(av, f2sub_s(f2mul(bv, ab), alphax)), f2mul(bv, betax)), f2splat(2.0f));
         e1[k] = f2add_s(f2mul(f2mul(av, av), alpha2), f2add_s(f2mul(f2mul(bv, bv), beta2), e2));
     }
+    if (U) return f2add_s(f2add_s(e1[0], e1[1]), e1[2]);
     return f2add_s(f2add_s(f2mul(e1[0], f2splat(msq[0])), f2mul(e1[1], f2splat(msq[1]))), f2mul(e1[2], f2splat(msq[2])));
 }
 
-// PAIR: two splits per trip with packed fp32 (fewer issue slots, more code).  The level-9 kernel keeps the scalar loop: its
-// instruction-cache footprint is already the limiter (ncu: stalled_no_instruction 2.7 -> 4.4 per issue with the packed loop,
-// 8192² Production 65.5 -> 70 ms), while the level-8 kernel gains (48.0 -> ~45 ms).
-template <bool FOUR, bool PAIR>
+// PAIR: two splits per trip with packed fp32 (fewer issue slots, more code).  Used at every level; the level-9 kernel used to
+// keep the scalar loop because its instruction-cache footprint was the limiter - since the refinement shrank (exact /255 by
+// multiply + 2 FMAs, palette look-up through shared memory) the packed loop wins there too (8192² Production 45.8 -> 43.1 ms).
+template <bool FOUR, bool PAIR, bool U>
 NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, unsigned gm, int l, int count) {
     const float4 sum = S.sat[count];
     const float msq[3] = {P.cw[0] * P.cw[0], P.cw[1] * P.cw[1], P.cw[2] * P.cw[2]};
@@ -395,7 +413,7 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
     float a[3], b[3];
     if (!PAIR) {
         for (int i = l; i < total; i += 16) {
-            const float e = icbc_eval_split<FOUR>(S.sat, __ldg(tab + i), sum, msq, a, b);
+            const float e = icbc_eval_split<FOUR, U>(S.sat, __ldg(tab + i), sum, msq, a, b);
             if (e < besterror) {
                 besterror = e;
                 besti = i;
@@ -406,7 +424,7 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
     for (int i = l; PAIR && i < total; i += 32) {
         const bool two = i + 16 < total;
         const unsigned pka = __ldg(tab + i), pkb = two ? __ldg(tab + i + 16) : pka;
-        const float2 e = icbc_eval_pair<FOUR>(S.sat, pka, pkb, sum, msq);
+        const float2 e = icbc_eval_pair<FOUR, U>(S.sat, pka, pkb, sum, msq);
         if (e.x < besterror) {
             besterror = e.x;
             besti = i;
@@ -428,7 +446,7 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
     FitResult r;
     r.sx = r.sy = r.sz = r.ex = r.ey = r.ez = 0.0f;  // vbeststart / vbestend start at zero
     if (besti != 0x7fffffff) {
-        icbc_eval_split<FOUR>(S.sat, __ldg(tab + besti), sum, msq, a, b);
+        icbc_eval_split<FOUR, U>(S.sat, __ldg(tab + besti), sum, msq, a, b);
         r.sx = a[0]; r.sy = a[1]; r.sz = a[2];
         r.ex = b[0]; r.ey = b[1]; r.ez = b[2];
     }
@@ -438,8 +456,13 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
 // One instantiation per ICBC level (1 = box fit, 8 = cluster fit, 9 = cluster fit + refinement) and for the BC3-RGBM colour
 // block: the generic kernel was 177 KB of SASS - more than the instruction cache - and warps in different phases of it
 // evicted each other's code (Production got slower when the cluster fit got bigger).
-template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16, 9) k_bc1_icbc_t(Bc1Params P) {
+// U: colour weights (1, 1, 1) - see cw_mul.
+#define NVB_BC1_PAL_PITCH 5  // float4 per lane: 80 bytes, so that the 128-bit reads of 8 consecutive lanes touch all 32 banks once
+template <int LEVEL, bool RGBM, bool U> __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16, 9) k_bc1_icbc_t(Bc1Params P) {
     __shared__ Bc1GroupSmem smem[NVB_BC1_GROUPS];
+    // Level 9: the palette of the refinement candidate each lane is measuring, read back by palette index
+    __shared__ float4 s_pal[LEVEL == 9 ? NVB_BC1_GROUPS * 16 * NVB_BC1_PAL_PITCH : 1];
+    __shared__ __align__(16) int s_off[LEVEL == 9 ? NVB_BC1_GROUPS * 16 : 4];  // per block: byte offset of texel t's palette entry
     const int grp = threadIdx.x >> 4;
     const int l = threadIdx.x & 15;
     const int nblocks = P.lv.bw * P.lv.bh;
@@ -557,7 +580,7 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
             if (cov_xz < 0) { const float t = c0x; c0x = c1x; c1x = t; }
             if (cov_yz < 0) { const float t = c0y; c0y = c1y; c1y = t; }
         }
-        error = icbc_output_block(P, gm, l, true, false, c0x, c0y, c0z, c1x, c1y, c1z, cx, cy, cz, wt, &out);
+        error = icbc_output_block<U>(P, gm, l, true, false, c0x, c0y, c0z, c1x, c1y, c1z, cx, cy, cz, wt, &out);
         // optimize_end_points4 on the chosen indices (unweighted, all 16 texels)
         {
             const unsigned bits = out.indices >> (2 * l);
@@ -579,7 +602,7 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
                 const float by2 = icbc_saturate((bxy * alpha2_sum - axy * alphabeta_sum) * factor);
                 const float bz2 = icbc_saturate((bxz * alpha2_sum - axz * alphabeta_sum) * factor);
                 Bc1Block opt;
-                const float oe = icbc_output_block(P, gm, l, true, false, ax, ay, az, bx2, by2, bz2, cx, cy, cz, wt, &opt);
+                const float oe = icbc_output_block<U>(P, gm, l, true, false, ax, ay, az, bx2, by2, bz2, cx, cy, cz, wt, &opt);
                 if (oe < error) {
                     error = oe;
                     out = opt;
@@ -589,9 +612,9 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
     } else {
         // ---- compress_dxt1_cluster_fit ----
         icbc_compute_sat(S, gm, l, count);
-        FitResult f4 = icbc_cluster_fit<true, LEVEL != 9>(P, S, gm, l, count);
+        FitResult f4 = icbc_cluster_fit<true, true, U>(P, S, gm, l, count);
         Bc1Block cf;
-        float best = icbc_output_block(P, gm, l, true, false, f4.sx, f4.sy, f4.sz, f4.ex, f4.ey, f4.ez, cx, cy, cz, wt, &cf);
+        float best = icbc_output_block<U>(P, gm, l, true, false, f4.sx, f4.sy, f4.sz, f4.ex, f4.ey, f4.ez, cx, cy, cz, wt, &cf);
         // three colour mode (Levels 8/9: always tried; transparent black allowed)
         int sat_count = count;
         bool do_three = !RGBM;  // compress_dxt5_rgbm passes three_color_mode = false
@@ -612,9 +635,9 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
             }
         }
         if (do_three) {
-            FitResult f3 = icbc_cluster_fit<false, LEVEL != 9>(P, S, gm, l, sat_count);
+            FitResult f3 = icbc_cluster_fit<false, true, U>(P, S, gm, l, sat_count);
             Bc1Block tb;
-            const float te = icbc_output_block(P, gm, l, false, true, f3.sx, f3.sy, f3.sz, f3.ex, f3.ey, f3.ez, cx, cy, cz, wt, &tb);
+            const float te = icbc_output_block<U>(P, gm, l, false, true, f3.sx, f3.sy, f3.sz, f3.ex, f3.ey, f3.ez, cx, cy, cz, wt, &tb);
             if (te < best) {
                 best = te;
                 cf = tb;
@@ -632,10 +655,13 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
             // 16 texel errors in texel order), and the first improving one in candidate order is accepted.
             float best_error = error;
             int lastImprovement = 0;
-            const float vcx = cx * P.cw[0], vcy = cy * P.cw[1], vcz = cz * P.cw[2];
+            const float vcx = cw_mul<U>(cx, P.cw[0]), vcy = cw_mul<U>(cy, P.cw[1]), vcz = cw_mul<U>(cz, P.cw[2]);
+            const char *const my_pal = reinterpret_cast<const char *>(s_pal + threadIdx.x * NVB_BC1_PAL_PITCH);
+            int *const g_off = s_off + grp * 16;
             __syncwarp(gm);
             S.pts[l] = make_float4(cx, cy, cz, wt);
-            __syncwarp(gm);
+            unsigned acc_idx = 0;   // this texel's index at the last acceptance (the reference stores the indices it measured with)
+            bool accepted = false;
             int i = 0;
 #pragma unroll 1
             for (;;) {
@@ -643,38 +669,54 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
                 const Pal3 pal = icbc_palette_f(out.c0, out.c1);
                 float d[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) d[q] = dist2w(vcx, vcy, vcz, pal.x[q] * P.cw[0], pal.y[q] * P.cw[1], pal.z[q] * P.cw[2]);
+                for (int q = 0; q < 4; q++)
+                    d[q] = dist2w(vcx, vcy, vcz, cw_mul<U>(pal.x[q], P.cw[0]), cw_mul<U>(pal.y[q], P.cw[1]), cw_mul<U>(pal.z[q], P.cw[2]));
                 const bool i1 = (d[1] <= d[0]) && (d[1] < d[2]) && (d[1] < d[3]);
                 const bool i2 = (d[2] <= d[0]) && (d[2] <= d[1]) && (d[2] < d[3]);
                 const bool i3 = (d[3] <= d[0]) && (d[3] <= d[1]) && (d[3] <= d[2]);
                 const unsigned idx = ((i1 || i3) ? 1u : 0u) | ((i2 || i3) ? 2u : 0u);
-                const unsigned indices = group_gather_bits2(gm, idx, l);
+                // texel t's palette entry as a byte offset into a lane's palette slot, shared by the 16 candidates of a round
+                __syncwarp(gm);
+                g_off[l] = (int)(idx * 16u);
+                __syncwarp(gm);
                 for (;;) {
                     const int limit = min(255, lastImprovement + 33);  // last candidate the sequential loop reaches
                     const int ci = i + l;
-                    // deltas[ci % 16]
-                    // rows: (1,0,0)(0,1,0)(0,0,1)(-1,0,0)(0,-1,0)(0,0,-1)(1,1,0)(1,0,1)(0,1,1)(-1,-1,0)(-1,0,-1)(0,-1,-1)(-1,1,0)(1,-1,0)(0,-1,1)(0,1,-1)
-                    const int k = ci & 15;
-                    const int dr = (k == 0 || k == 6 || k == 7 || k == 13) ? 1 : (k == 3 || k == 9 || k == 10 || k == 12) ? -1 : 0;
-                    const int dg = (k == 1 || k == 6 || k == 8 || k == 12 || k == 15) ? 1 : (k == 4 || k == 9 || k == 11 || k == 13 || k == 14) ? -1 : 0;
-                    const int db = (k == 2 || k == 7 || k == 8 || k == 14) ? 1 : (k == 5 || k == 10 || k == 11 || k == 15) ? -1 : 0;
+                    // deltas[ci % 16], rows:
+                    // (1,0,0)(0,1,0)(0,0,1)(-1,0,0)(0,-1,0)(0,0,-1)(1,1,0)(1,0,1)(0,1,1)(-1,-1,0)(-1,0,-1)(0,-1,-1)(-1,1,0)(1,-1,0)(0,-1,1)(0,1,-1)
+                    // as 2-bit fields (delta + 1) of one word per channel
+                    const int k2 = 2 * (ci & 15);
+                    const unsigned dr = ((DWR >> k2) & 3u) - 1u;
+                    const unsigned dg = ((DWG >> k2) & 3u) - 1u;
+                    const unsigned db = ((DWB >> k2) & 3u) - 1u;
                     unsigned c0 = out.c0, c1 = out.c1;
                     {
                         unsigned c = ((ci / 16) & 1) ? c0 : c1;
-                        const unsigned r = (((c >> 11) & 31) + (unsigned)dr) & 31;
-                        const unsigned g = (((c >> 5) & 63) + (unsigned)dg) & 63;
-                        const unsigned b = ((c & 31) + (unsigned)db) & 31;
+                        const unsigned r = (((c >> 11) & 31) + dr) & 31;
+                        const unsigned g = (((c >> 5) & 63) + dg) & 63;
+                        const unsigned b = ((c & 31) + db) & 31;
                         c = (r << 11) | (g << 5) | b;
                         if ((ci / 16) & 1) c0 = c; else c1 = c;
                     }
-                    // evaluate_mse of the candidate block, texel by texel in order
-                    const Pal3 rp = icbc_palette_f(c0, c1);
+                    // evaluate_mse of the candidate block, texel by texel in order; the candidate's palette goes through this
+                    // lane's own shared-memory slot so that "palette[index of texel t]" is one LDS.128 instead of nine selects
+                    {
+                        const Pal3 rp = icbc_palette_f(c0, c1);
+                        float4 *const w = s_pal + threadIdx.x * NVB_BC1_PAL_PITCH;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) w[q] = make_float4(rp.x[q], rp.y[q], rp.z[q], 0.0f);
+                    }
                     float e = 0.0f;
-#pragma unroll 4
-                    for (int t = 0; t < 16; t++) {
-                        const float4 q = S.pts[t];
-                        const unsigned it = (indices >> (2 * t)) & 3u;
-                        e += q.w * mse_term(select4(rp.x, it), select4(rp.y, it), select4(rp.z, it), q.x, q.y, q.z, P.cw);
+#pragma unroll 2
+                    for (int t4 = 0; t4 < 4; t4++) {
+                        const int4 o4 = *reinterpret_cast<const int4 *>(g_off + 4 * t4);
+                        const int o[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float4 q = S.pts[4 * t4 + u];
+                            const float4 c = *reinterpret_cast<const float4 *>(my_pal + o[u]);
+                            e += q.w * mse_term<U>(c.x, c.y, c.z, q.x, q.y, q.z, P.cw);
+                        }
                     }
                     const bool better = (ci <= limit) && (e < best_error);
                     const unsigned bm = (__ballot_sync(gm, better) >> gsh) & 0xFFFFu;
@@ -683,7 +725,8 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
                         best_error = __shfl_sync(gm, e, wl, 16);
                         out.c0 = __shfl_sync(gm, c0, wl, 16);
                         out.c1 = __shfl_sync(gm, c1, wl, 16);
-                        out.indices = indices;
+                        acc_idx = idx;
+                        accepted = true;
                         lastImprovement = i + wl;
                         i += wl + 1;
                         break;  // `out` changed: new indices
@@ -693,6 +736,7 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
                 }
                 if (i > min(255, lastImprovement + 33)) break;
             }
+            if (accepted) out.indices = group_gather_bits2(gm, acc_idx, l);
             error = best_error;
         }
     }
@@ -700,12 +744,15 @@ template <int LEVEL, bool RGBM> __global__ void __launch_bounds__(NVB_BC1_GROUPS
 }
 
 // host-side dispatch on (P.level, P.rgbm): LAUNCH(kernel) is expanded with the matching instantiation
-#define NVB_BC1_DISPATCH(P, LAUNCH)                                  \
-    do {                                                             \
-        if ((P).rgbm) { LAUNCH((k_bc1_icbc_t<8, true>)); }           \
-        else if ((P).level == 1) { LAUNCH((k_bc1_icbc_t<1, false>)); } \
-        else if ((P).level == 9) { LAUNCH((k_bc1_icbc_t<9, false>)); } \
-        else { LAUNCH((k_bc1_icbc_t<8, false>)); }                   \
+#define NVB_BC1_DISPATCH(P, LAUNCH)                                                    \
+    do {                                                                               \
+        const bool unit_ = (P).cw[0] == 1.0f && (P).cw[1] == 1.0f && (P).cw[2] == 1.0f; \
+        if ((P).rgbm) { LAUNCH((k_bc1_icbc_t<8, true, false>)); }                      \
+        else if ((P).level == 1) { LAUNCH((k_bc1_icbc_t<1, false, false>)); }          \
+        else if ((P).level == 9 && unit_) { LAUNCH((k_bc1_icbc_t<9, false, true>)); }  \
+        else if ((P).level == 9) { LAUNCH((k_bc1_icbc_t<9, false, false>)); }          \
+        else if (unit_) { LAUNCH((k_bc1_icbc_t<8, false, true>)); }                    \
+        else { LAUNCH((k_bc1_icbc_t<8, false, false>)); }                              \
     } while (0)
 
 }  // namespace nvb

@@ -61,6 +61,10 @@ NVB_DEV float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x
 #ifdef NVB_EMU
 NVB_DEV float2 f2add_s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 NVB_DEV float2 f2sub_s(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+#elif defined(NVB_FASTMATH)
+// the fast-math build (libnvtt_b200_fastmath.so, outside the parity contract) lets ptxas contract these into FFMA2
+NVB_DEV float2 f2add_s(float2 a, float2 b) { return f2add(a, b); }
+NVB_DEV float2 f2sub_s(float2 a, float2 b) { return f2sub(a, b); }
 #else
 // An unfused packed sum in ONE issue slot: fma(a, 1, b) rounds a*1 + b once, i.e. it IS add.rn(a, b) bit for bit (and
 // fma(b, -1, a) is sub.rn(a, b)), and an FFMA2 cannot be contracted with the FMUL2 that produced its operand.  The ones
@@ -115,8 +119,13 @@ NVB_DEV pf2 pf2_sub(pf2 a, pf2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+#ifdef NVB_FASTMATH
+NVB_DEV pf2 pf2_add_s(pf2 a, pf2 b) { return pf2_add(a, b); }
+NVB_DEV pf2 pf2_sub_s(pf2 a, pf2 b) { return pf2_sub(a, b); }
+#else
 NVB_DEV pf2 pf2_add_s(pf2 a, pf2 b) { return pf2_fma(a, *reinterpret_cast<const pf2 *>(&nvb_one2), b); }
 NVB_DEV pf2 pf2_sub_s(pf2 a, pf2 b) { return pf2_fma(b, *reinterpret_cast<const pf2 *>(&nvb_mone2), a); }
+#endif
 #endif
 NVB_DEV pf2 pf2_splat(float v) { return pf2_pack(v, v); }
 

@@ -112,3 +112,24 @@ def test_div7_identity():
         r = f32(np.float64(kk) - np.float64(7.0) * np.float64(q))      # fma(-7, q, k): exact
         q2 = f32(np.float64(q) + np.float64(r) * np.float64(y))       # fma(r, y, q): |terms| small, double is exact enough
         assert q2 == f32(kk / f32(7.0)), k
+
+
+def test_div255_identity():
+    """icbc_u8_to_float (bc1_icbc.cuh): v * RN(1/255) corrected by two fused multiply-adds equals the IEEE quotient
+    float(v) / 255.0f for every v in 0..255 - the only operands the BC1 palette ever divides (icbc.h evaluate_palette)."""
+    import numpy as np
+    from fractions import Fraction
+    f32 = np.float32
+    r = np.frombuffer(np.uint32(0x3b808081).tobytes(), f32)[0]
+    assert r == f32(1.0) / f32(255.0)
+
+    def rn32(fr):  # correctly rounded float32 of an exact rational (no ties occur here; nearest of the three neighbours)
+        c = f32(float(fr))
+        return min((c, np.nextafter(c, f32(np.inf)), np.nextafter(c, f32(-np.inf))), key=lambda z: abs(Fraction(float(z)) - fr))
+
+    for v in range(256):
+        x = f32(v)
+        q = f32(x * r)
+        rem = rn32(Fraction(float(q)) * -255 + Fraction(float(x)))
+        got = rn32(Fraction(float(r)) * Fraction(float(rem)) + Fraction(float(q)))
+        assert got == f32(x / f32(255.0)), v
