@@ -264,6 +264,11 @@ NVTTB_API int nvttb_process_shard(NvttbContext *ctx, const NvttbProcessDesc *des
  * until all bands have delivered, and a cudaMalloc on that GPU may wait for it); harmless otherwise.  own_output: the call will
  * be given out_device = NULL. */
 NVTTB_API int nvttb_process_prepare(NvttbContext *ctx, const NvttbProcessDesc *desc, int images_location, int own_output);
+/* Restrict the CALLING host thread to the CPUs of the NUMA node the context's GPU is attached to (sysfs local_cpulist), so
+ * that the staging copies and launches of a one-thread-per-GPU / one-process-per-GPU caller stay on the local memory controller
+ * and PCIe root.  nvttb_process_multi does this for its own threads.  No-op where the topology is not exposed or when
+ * NVTT_B200_NO_AFFINITY is set.  The reference has no counterpart (its ThreadPool, src/nvthread/ThreadPool.cpp, is not NUMA aware). */
+NVTTB_API int nvttb_bind_thread_to_device(NvttbContext *ctx);
 /* The whole pipeline for host images on SEVERAL GPUs of one process (one host thread per context): large single images are
  * block-row sharded (band-local front end where it applies), cube faces / array slices are dealt out face by face.  emit sees
  * exactly what nvttb_process would produce on one GPU.  contexts[0] owns the pinned output buffer. */

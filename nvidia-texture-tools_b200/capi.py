@@ -116,7 +116,7 @@ EXPORTS = [
     "nvttb_surface_binarize", "nvttb_surface_quantize", "nvttb_surface_set_image_2d", "nvttb_rms_error", "nvttb_rms_alpha_error", "nvttb_angular_error", "nvttb_cielab_error",
     "nvttb_surface_download", "nvttb_surface_device_data", "nvttb_surface_encode", "nvttb_process",
     "nvttb_process_to_device", "nvttb_process_output_size", "nvttb_process_mip_count", "nvttb_process_band_slices",
-    "nvttb_dds_describe", "nvttb_dds_surface", "nvttb_process_exchange_size", "nvttb_process_prepare", "nvttb_process_shard", "nvttb_process_multi", "nvttb_host_register", "nvttb_host_unregister",
+    "nvttb_dds_describe", "nvttb_dds_surface", "nvttb_process_exchange_size", "nvttb_process_prepare", "nvttb_process_shard", "nvttb_process_multi", "nvttb_bind_thread_to_device", "nvttb_host_register", "nvttb_host_unregister",
     "nvttb_process_whole_output_size", "nvttb_device_alloc", "nvttb_device_free", "nvttb_ipc_export", "nvttb_ipc_open", "nvttb_ipc_close",
 ]
 
@@ -206,6 +206,7 @@ def lib():
     L.nvttb_process_prepare.argtypes = [vp, C.POINTER(ProcessDesc), ci, ci]
     L.nvttb_process_shard.argtypes = [vp, C.POINTER(ProcessDesc), C.POINTER(vp), ci, vp, vp]
     L.nvttb_process_multi.argtypes = [C.POINTER(vp), ci, C.POINTER(ProcessDesc), C.POINTER(vp), EMIT_FN, vp]
+    L.nvttb_bind_thread_to_device.argtypes = [vp]
     L.nvttb_host_register.argtypes = [vp, vp, sz]
     L.nvttb_host_unregister.argtypes = [vp, vp]
     _lib = L
@@ -295,6 +296,10 @@ class Context:
 
     def synchronize(self):
         self._ck(self.L.nvttb_synchronize(self.h))
+
+    def bind_thread(self):
+        """Keep the calling thread on the CPUs next to this context's GPU (no-op where sysfs does not expose the topology)."""
+        self._ck(self.L.nvttb_bind_thread_to_device(self.h))
 
     def encode_level(self, fmt, quality, planar_rgba, **kw):
         """planar_rgba float32 [4,h,w] on the host -> np.uint8 BCn bytes."""

@@ -28,6 +28,12 @@
 #include <vector>
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <ctype.h>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 using namespace nvb;
 
@@ -1194,7 +1200,12 @@ bool pixel_layout(const NvttbPixelFormatDesc *d, PixelLayout *L) {
         // UnsignedNorm = 0, UnsignedInt = 2; SignedNorm / SignedInt write zero components; SharedExp writes zeros unless 9/9/9/5
         if (d->pixelType == 0) L->kind = 0;
         else if (d->pixelType == 2) L->kind = 1;
-        else if (d->pixelType == 6 /* PixelType_SharedExp */ && sz[0] == 9 && sz[1] == 9 && sz[2] == 9 && sz[3] == 5) return false;  // RGB9E5: not implemented
+        else if (d->pixelType == 6 /* PixelType_SharedExp */ && L->size[0] == 9 && L->size[1] == 9 && L->size[2] == 9 && L->size[3] == 5) {
+            // R9G9B9E5 (toFloat3SE): always one 32-bit word per pixel - putBits(v.v, 32) whatever bitCount says - so only the
+            // layouts whose bitCount is 32 keep the scanline pitch consistent with what is written
+            if (L->bitCount != 32) return false;
+            L->kind = 4;
+        }
         else L->kind = 3;
         L->aligned = (L->bitCount % 8) == 0;
     }
@@ -2349,6 +2360,47 @@ static int auto_chunk_rows(int H, int n) {
     return best;
 }
 
+// Host threads of nvttb_process_multi: keep the thread that feeds GPU `device` (pageable -> pinned staging copies, launches)
+// on the CPUs of the NUMA node that GPU hangs off, so that its staging traffic stays on the local memory controller and its
+// PCIe root.  Linux sysfs only; silently does nothing when the topology is not exposed (containers, single-node hosts) or
+// NVTT_B200_NO_AFFINITY is set.
+static void pin_thread_near_device(int device) {
+#if defined(__linux__)
+    static const bool off = getenv("NVTT_B200_NO_AFFINITY") != nullptr;
+    if (off) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return;
+    char list[1024] = {0};
+    const bool ok = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+        int a = 0, b = 0;
+        const int got = sscanf(tok, "%d-%d", &a, &b);
+        if (got == 1) b = a;
+        if (got < 1 || a < 0 || b < a) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); count++; }
+    }
+    if (count > 0) pthread_setaffinity_np(pthread_self(), sizeof set, &set);  // failure (cgroup limits): stay where we are
+#else
+    (void)device;
+#endif
+}
+
+int nvttb_bind_thread_to_device(NvttbContext *ctx) {
+    if (!ctx) return NVTTB_ERR_INVALID_INPUT;
+    pin_thread_near_device(ctx->device);
+    return NVTTB_OK;
+}
+
 int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc *d, const void *const *images, NvttbEmitFn emit, void *user) {
     if (!ctxs || n <= 0 || !ctxs[0]) return NVTTB_ERR_INVALID_INPUT;
     NvttbContext *ctx = ctxs[0];
@@ -2373,6 +2425,7 @@ int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc
                 NvttbContext *c = ctxs[t];
                 const int lo = f0 + (int)((long long)faces * t / users), hi = f0 + (int)((long long)faces * (t + 1) / users);
                 if (hi <= lo) return;
+                pin_thread_near_device(c->device);
                 int r = cudaSetDevice(c->device) == cudaSuccess ? NVTTB_OK : NVTTB_ERR_CUDA;
                 if (r == NVTTB_OK) r = ensure(c, c->out_dev, wbytes * (size_t)(hi - lo));
                 if (r == NVTTB_OK) r = process_faces(c, d, images, NVTTB_HOST, lo, hi, (unsigned char *)c->out_dev.p, h_out + (size_t)(lo - f0) * wbytes);
@@ -2435,6 +2488,7 @@ int nvttb_process_multi(NvttbContext *const *ctxs, int n, const NvttbProcessDesc
                 th.emplace_back([&, t]() {
                     NvttbProcessDesc mine = base;
                     mine.bandIndex = t;
+                    pin_thread_near_device(ctxs[t]->device);
                     rcs[t] = nvttb_process_shard(ctxs[t], &mine, images, NVTTB_HOST, nullptr, h_out + (size_t)(f - f0) * wbytes);
                 });
             }

@@ -335,16 +335,29 @@ NVB_DEV float icbc_eval_split(const float4 *sat, unsigned pk, float4 sum, const 
     return cw_mul<U>(e1[0], msq[0]) + cw_mul<U>(e1[1], msq[1]) + cw_mul<U>(e1[2], msq[2]);
 }
 
-// Two splits at once (A, B): every quantity of icbc_eval_split is carried as a pair so that the multiplications issue as
-// FMUL2 and the product-free subtractions as FADD2; a sum that consumes a product stays two scalar FADDs (ptxas would
-// contract a packed add of a packed product into FFMA2, nvb_common.cuh).  Operation for operation the same arithmetic per
-// split; only the errors are returned (the winner is re-evaluated by icbc_eval_split for its endpoints).
+// Two splits at once (A, B) with packed fp32 (FMUL2 / FADD2 / unfused FFMA2-by-one sums), operation for operation the
+// arithmetic of icbc_eval_split; only the errors are returned (the winner is re-evaluated by icbc_eval_split for its
+// endpoints).  The pairing follows the registers an LDS.128 of a SAT row fills - (x, y) and (z, w) are aligned register
+// pairs already - so nothing has to be moved to form a pair:
+//   * the differences s2 - s1 and s1 - s0 are two FADD2 each;
+//   * alphax_sum = x2 / 3 + (x1 * 2 / 3 + x0) per channel and alpha2_sum = w2 / 9 + (w1 * 4 / 9 + w0) have the same shape, so
+//     the w lane of the (z, w) pair computes alpha2_sum with its own constants while the z lane computes the blue alphax_sum;
+//   * the R and G channels of ONE split go through icbc_chan_pair together (grid 31 | 63), with the split's alpha2 / beta2 /
+//     alphabeta sums and factor as broadcast scalar operands;
+//   * only the B channel and the few weight sums are paired across the two splits, which costs the register moves.
 // x = t * factor; saturate(x) = min(max(x, 0), 1) with NaN -> 0 is the .SAT of the scalar multiply (one instruction per
-// value instead of half an FMUL2 plus a clamp)
-NVB_DEV float2 icbc_round_pair(float2 num, float2 factor, float grid, float gridrcp) {
-    const float2 s = make_float2(__saturatef(__fmul_rn(num.x, factor.x)), __saturatef(__fmul_rn(num.y, factor.y)));
-    const float2 t = f2add_s(f2mul(s, f2splat(grid)), f2splat(0.5f));
-    return f2mul(make_float2(truncf(t.x), truncf(t.y)), f2splat(gridrcp));
+// value instead of half an FMUL2 plus a clamp).
+NVB_DEV pf2 icbc_chan_pair(pf2 alphax, pf2 S, pf2 alpha2, pf2 beta2, pf2 ab, float fx, float fy, pf2 g, pf2 gr) {
+    const pf2 betax = pf2_sub(S, alphax);
+    const pf2 at = pf2_sub_s(pf2_mul(alphax, beta2), pf2_mul(betax, ab));
+    const pf2 bt = pf2_sub_s(pf2_mul(betax, alpha2), pf2_mul(alphax, ab));
+    pf2 a = pf2_pack(__saturatef(__fmul_rn(pf2_lo(at), fx)), __saturatef(__fmul_rn(pf2_hi(at), fy)));
+    pf2 b = pf2_pack(__saturatef(__fmul_rn(pf2_lo(bt), fx)), __saturatef(__fmul_rn(pf2_hi(bt), fy)));
+    const pf2 ha = pf2_add_s(pf2_mul(a, g), pf2_splat(0.5f)), hb = pf2_add_s(pf2_mul(b, g), pf2_splat(0.5f));
+    a = pf2_mul(pf2_pack(truncf(pf2_lo(ha)), truncf(pf2_hi(ha))), gr);
+    b = pf2_mul(pf2_pack(truncf(pf2_lo(hb)), truncf(pf2_hi(hb))), gr);
+    const pf2 e2 = pf2_mul(pf2_sub_s(pf2_mul(a, pf2_sub_s(pf2_mul(b, ab), alphax)), pf2_mul(b, betax)), pf2_splat(2.0f));
+    return pf2_add_s(pf2_mul(pf2_mul(a, a), alpha2), pf2_add_s(pf2_mul(pf2_mul(b, b), beta2), e2));
 }
 template <bool FOUR, bool U>
 NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, float4 sum, const float msq[3]) {
@@ -352,51 +365,51 @@ NVB_DEV float2 icbc_eval_pair(const float4 *sat, unsigned pka, unsigned pkb, flo
     const int b0 = (int)(pkb & 31), b1 = (int)((pkb >> 5) & 31), b2 = (int)((pkb >> 10) & 31);
     const float4 sa0 = sat[a0], sb0 = sat[b0];
     const float4 sa1 = sat[a1], sb1 = sat[b1];
-    const float2 s0[4] = {make_float2(sa0.x, sb0.x), make_float2(sa0.y, sb0.y), make_float2(sa0.z, sb0.z), make_float2(sa0.w, sb0.w)};
-    const float2 s1[4] = {make_float2(sa1.x, sb1.x), make_float2(sa1.y, sb1.y), make_float2(sa1.z, sb1.z), make_float2(sa1.w, sb1.w)};
-    float2 alpha2, beta2, ab, ax[3];
+    // per split: lo = (x, y), hi = (z, w) of a SAT row
+    const pf2 a0l = pf2_pack(sa0.x, sa0.y), a0h = pf2_pack(sa0.z, sa0.w), b0l = pf2_pack(sb0.x, sb0.y), b0h = pf2_pack(sb0.z, sb0.w);
+    const pf2 a1l = pf2_pack(sa1.x, sa1.y), a1h = pf2_pack(sa1.z, sa1.w), b1l = pf2_pack(sb1.x, sb1.y), b1h = pf2_pack(sb1.z, sb1.w);
+    const pf2 dA1l = pf2_sub(a1l, a0l), dA1h = pf2_sub(a1h, a0h), dB1l = pf2_sub(b1l, b0l), dB1h = pf2_sub(b1h, b0h);  // x1 | w1
+    pf2 rAl, rAh, rBl, rBh;  // (alphax_sum.x, .y) and (alphax_sum.z, alpha2_sum) of each split
+    pf2 beta2, ab;           // (A, B)
     if (FOUR) {
         const float4 sa2 = sat[a2], sb2 = sat[b2];
-        const float2 s2[4] = {make_float2(sa2.x, sb2.x), make_float2(sa2.y, sb2.y), make_float2(sa2.z, sb2.z), make_float2(sa2.w, sb2.w)};
-        const float2 w3 = f2sub(f2splat(sum.w), s2[3]);
-        const float2 w2 = f2sub(s2[3], s1[3]), w1 = f2sub(s1[3], s0[3]), w0 = s0[3];
-        alpha2 = f2add_s(f2mul(w2, f2splat(1.0f / 9.0f)), f2add_s(f2mul(w1, f2splat(4.0f / 9.0f)), w0));
-        beta2 = f2add_s(f2mul(w1, f2splat(1.0f / 9.0f)), f2add_s(f2mul(w2, f2splat(4.0f / 9.0f)), w3));
-        ab = f2mul(f2add(w1, w2), f2splat(2.0f / 9.0f));
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float2 x2 = f2sub(s2[k], s1[k]), x1 = f2sub(s1[k], s0[k]);
-            ax[k] = f2add_s(f2mul(x2, f2splat(1.0f / 3.0f)), f2add_s(f2mul(x1, f2splat(2.0f / 3.0f)), s0[k]));
-        }
+        const pf2 a2l = pf2_pack(sa2.x, sa2.y), a2h = pf2_pack(sa2.z, sa2.w), b2l = pf2_pack(sb2.x, sb2.y), b2h = pf2_pack(sb2.z, sb2.w);
+        const pf2 dA2l = pf2_sub(a2l, a1l), dA2h = pf2_sub(a2h, a1h), dB2l = pf2_sub(b2l, b1l), dB2h = pf2_sub(b2h, b1h);  // x2 | w2
+        const pf2 c23 = pf2_splat(2.0f / 3.0f), c13 = pf2_splat(1.0f / 3.0f);
+        const pf2 c23_49 = pf2_pack(2.0f / 3.0f, 4.0f / 9.0f), c13_19 = pf2_pack(1.0f / 3.0f, 1.0f / 9.0f);
+        rAl = pf2_add_s(pf2_mul(dA2l, c13), pf2_add_s(pf2_mul(dA1l, c23), a0l));
+        rAh = pf2_add_s(pf2_mul(dA2h, c13_19), pf2_add_s(pf2_mul(dA1h, c23_49), a0h));
+        rBl = pf2_add_s(pf2_mul(dB2l, c13), pf2_add_s(pf2_mul(dB1l, c23), b0l));
+        rBh = pf2_add_s(pf2_mul(dB2h, c13_19), pf2_add_s(pf2_mul(dB1h, c23_49), b0h));
+        const pf2 w1 = pf2_pack(pf2_hi(dA1h), pf2_hi(dB1h)), w2 = pf2_pack(pf2_hi(dA2h), pf2_hi(dB2h));
+        const pf2 w3 = pf2_sub(pf2_splat(sum.w), pf2_pack(sa2.w, sb2.w));
+        beta2 = pf2_add_s(pf2_mul(w1, pf2_splat(1.0f / 9.0f)), pf2_add_s(pf2_mul(w2, pf2_splat(4.0f / 9.0f)), w3));
+        ab = pf2_mul(pf2_add(w1, w2), pf2_splat(2.0f / 9.0f));
     } else {
-        const float2 w2 = f2sub(f2splat(sum.w), s1[3]);
-        const float2 w1 = f2sub(s1[3], s0[3]), w0 = s0[3];
-        ab = f2mul(w1, f2splat(0.25f));
-        alpha2 = f2add_s(w0, ab);
-        beta2 = f2add_s(w2, ab);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float2 x1 = f2sub(s1[k], s0[k]);
-            ax[k] = f2add_s(s0[k], f2mul(x1, f2splat(0.5f)));
-        }
+        const pf2 ch = pf2_splat(0.5f), ch_q = pf2_pack(0.5f, 0.25f);
+        const pf2 tAh = pf2_mul(dA1h, ch_q), tBh = pf2_mul(dB1h, ch_q);  // (x1.z / 2, alphabeta_sum = w1 / 4)
+        rAl = pf2_add_s(a0l, pf2_mul(dA1l, ch));
+        rAh = pf2_add_s(a0h, tAh);
+        rBl = pf2_add_s(b0l, pf2_mul(dB1l, ch));
+        rBh = pf2_add_s(b0h, tBh);
+        ab = pf2_pack(pf2_hi(tAh), pf2_hi(tBh));
+        const pf2 w2 = pf2_sub(pf2_splat(sum.w), pf2_pack(sa1.w, sb1.w));
+        beta2 = pf2_add_s(w2, ab);
     }
-    const float2 det = f2sub_s(f2mul(alpha2, beta2), f2mul(ab, ab));
-    const float2 factor = make_float2(1.0f / det.x, 1.0f / det.y);
-    const float S3[3] = {sum.x, sum.y, sum.z};
-    float2 e1[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const float2 alphax = ax[k];
-        const float2 betax = f2sub(f2splat(S3[k]), alphax);
-        const float2 at = f2sub_s(f2mul(alphax, beta2), f2mul(betax, ab));
-        const float2 bt = f2sub_s(f2mul(betax, alpha2), f2mul(alphax, ab));
-        const float2 av = (k == 1) ? icbc_round_pair(at, factor, 63.0f, 1.0f / 63.0f) : icbc_round_pair(at, factor, 31.0f, 1.0f / 31.0f);
-        const float2 bv = (k == 1) ? icbc_round_pair(bt, factor, 63.0f, 1.0f / 63.0f) : icbc_round_pair(bt, factor, 31.0f, 1.0f / 31.0f);
-        const float2 e2 = f2mul(f2sub_s(f2mul(av, f2sub_s(f2mul(bv, ab), alphax)), f2mul(bv, betax)), f2splat(2.0f));
-        e1[k] = f2add_s(f2mul(f2mul(av, av), alpha2), f2add_s(f2mul(f2mul(bv, bv), beta2), e2));
-    }
-    if (U) return f2add_s(f2add_s(e1[0], e1[1]), e1[2]);
-    return f2add_s(f2add_s(f2mul(e1[0], f2splat(msq[0])), f2mul(e1[1], f2splat(msq[1]))), f2mul(e1[2], f2splat(msq[2])));
+    const pf2 alpha2 = pf2_pack(pf2_hi(rAh), pf2_hi(rBh));
+    const pf2 det = pf2_sub_s(pf2_mul(alpha2, beta2), pf2_mul(ab, ab));
+    const float fA = 1.0f / pf2_lo(det), fB = 1.0f / pf2_hi(det);
+    const pf2 gxy = pf2_pack(31.0f, 63.0f), grxy = pf2_pack(1.0f / 31.0f, 1.0f / 63.0f);
+    const pf2 sxy = pf2_pack(sum.x, sum.y);
+    const pf2 eA = icbc_chan_pair(rAl, sxy, pf2_splat(pf2_lo(alpha2)), pf2_splat(pf2_lo(beta2)), pf2_splat(pf2_lo(ab)), fA, fA, gxy, grxy);
+    const pf2 eB = icbc_chan_pair(rBl, sxy, pf2_splat(pf2_hi(alpha2)), pf2_splat(pf2_hi(beta2)), pf2_splat(pf2_hi(ab)), fB, fB, gxy, grxy);
+    const pf2 eZ = icbc_chan_pair(pf2_pack(pf2_lo(rAh), pf2_lo(rBh)), pf2_splat(sum.z), alpha2, beta2, ab, fA, fB, pf2_splat(31.0f),
+                                  pf2_splat(1.0f / 31.0f));
+    if (U)
+        return make_float2(__fadd_rn(__fadd_rn(pf2_lo(eA), pf2_hi(eA)), pf2_lo(eZ)), __fadd_rn(__fadd_rn(pf2_lo(eB), pf2_hi(eB)), pf2_hi(eZ)));
+    const pf2 mxy = pf2_pack(msq[0], msq[1]);
+    const pf2 pA = pf2_mul(eA, mxy), pB = pf2_mul(eB, mxy), pZ = pf2_mul(eZ, pf2_splat(msq[2]));
+    return make_float2(__fadd_rn(__fadd_rn(pf2_lo(pA), pf2_hi(pA)), pf2_lo(pZ)), __fadd_rn(__fadd_rn(pf2_lo(pB), pf2_hi(pB)), pf2_hi(pZ)));
 }
 
 // PAIR: two splits per trip with packed fp32 (fewer issue slots, more code).  Used at every level; the level-9 kernel used to

@@ -6,6 +6,7 @@
 //   toFloat11 / toFloat10                              src/nvtt/CompressorRGB.cpp:129-160
 //   PixelFormat::convert (16 -> n bits)                src/nvimage/PixelFormat.h:37-53
 //   nv::half_from_float                                src/nvmath/Half.cpp:378-441  (bc6h.cuh)
+//   toFloat3SE (R9G9B9E5, PixelType_SharedExp)         src/nvtt/CompressorRGB.cpp:231-269
 //
 // The reference walks every scanline through a small bit stream.  A pixel whose bit count is a whole number of bytes
 // (and, for float types, whose channels are 0/16/32 bits wide) always starts on an empty stream, so those formats - all
@@ -25,7 +26,7 @@ struct PixelFormatParams {
     unsigned char *out;   // h scanlines of `pitch` bytes
     unsigned pitch;       // computeBytePitch(w, bitCount, pitchAlignment)
     unsigned bitCount;
-    int kind;             // 0 UnsignedNorm, 1 UnsignedInt, 2 Float, 3 SharedExp / signed types (zeros, as the reference writes)
+    int kind;             // 0 UnsignedNorm, 1 UnsignedInt, 2 Float, 3 signed types / other SharedExp layouts (zeros, as the reference writes), 4 R9G9B9E5
     unsigned size[4];     // r, g, b, a
     unsigned shift[4];
 };
@@ -83,6 +84,35 @@ NVB_DEV void pf_put_float_channel(PfStream &s, float v, unsigned size) {
     else pf_put_bits(s, 0, size);
 }
 
+// ftoi_round = cvtss2si under the default rounding mode: nearest even; NaN and out-of-range give INT_MIN
+NVB_DEV int pf_ftoi_round(float f) {
+    return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rn(f) : (int)0x80000000;
+}
+// toFloat3SE as the reference's x86-64 build computes it.  Two things are kept on purpose:
+//   * the divisor 1 << (exp_shared - B - N) has a NEGATIVE shift count for every value below 256; x86 takes the count modulo
+//     32, so those pixels get the right exponent and zero mantissas (1 << 31 is INT_MIN: the quotient is a tiny negative);
+//   * the exponent comes from floor(log2f(max)), and a correctly rounded log2f returns k for the last few floats below 2^k.
+//     log2 in double, rounded to float, reproduces that (checked against glibc's log2f around every power of two:
+//     tests/test_oracle.py); the float pipeline never sees the double otherwise (this layout is rare: rank 4 of SURVEY 8f).
+NVB_DEV unsigned pf_to_float3se(float r, float g, float b) {
+    const int N = 9, B = 15;
+    const float sharedexp_max = 65408.0f;
+    r = nv_max(0.0f, nv_min(sharedexp_max, r));
+    g = nv_max(0.0f, nv_min(sharedexp_max, g));
+    b = nv_max(0.0f, nv_min(sharedexp_max, b));
+    const float max_c = nv_max(r, nv_max(g, b));
+    const float lg = (float)log2((double)max_c);  // log2f(0) = -inf -> floorf -> cvtss2si = INT_MIN
+    const int exp_shared_p = nv_max(-B - 1, pf_ftoi_round(floorf(lg))) + 1 + B;
+    const float dp = (float)(int)(1u << ((unsigned)(exp_shared_p - B - N) & 31u));
+    const int max_s = pf_ftoi_round(max_c / dp);
+    int exp_shared = exp_shared_p;
+    if (max_s == (1 << N)) exp_shared++;
+    const float ds = (float)(int)(1u << ((unsigned)(exp_shared - B - N) & 31u));
+    const unsigned xm = (unsigned)pf_ftoi_round(r / ds) & 0x1FFu, ym = (unsigned)pf_ftoi_round(g / ds) & 0x1FFu;
+    const unsigned zm = (unsigned)pf_ftoi_round(b / ds) & 0x1FFu;
+    return xm | (ym << 9) | (zm << 18) | (((unsigned)exp_shared & 31u) << 27);
+}
+
 // PixelFormat::convert(c, 16, outbits)
 NVB_DEV unsigned pf_convert16(unsigned c, unsigned outbits) {
     unsigned inbits = 16, r = 0;
@@ -125,6 +155,8 @@ NVB_DEV void pf_put_pixel(const PixelFormatParams &P, PfStream &s, int x, int y)
         pf_put_float_channel(s, a, P.size[3]);
     } else if (P.kind == 3) {
         pf_put_bits(s, 0, P.bitCount);
+    } else if (P.kind == 4) {
+        pf_put_bits(s, pf_to_float3se(r, g, b), 32);
     } else {
         pf_put_bits(s, pf_fixed_pixel(P, r, g, b, a), P.bitCount);
     }
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(256) k_pixel_format(PixelFormatParams P) {
     if (x >= P.lv.w) return;
     const unsigned bytes = P.bitCount >> 3;
     unsigned char *row = P.out + (size_t)y * P.pitch;
-    if (P.kind <= 1 && bytes == 4 && (P.pitch & 3u) == 0 && ((size_t)P.out & 3u) == 0) {
+    if ((P.kind <= 1 || P.kind == 4) && bytes == 4 && (P.pitch & 3u) == 0 && ((size_t)P.out & 3u) == 0) {
         // the common 32-bit case: one aligned store
         unsigned char tmp[4];
         PfStream s{tmp, 0, 0, 0, 4};

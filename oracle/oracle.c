@@ -1076,7 +1076,33 @@ static void mask_shift_size(uint32_t mask, unsigned *shift, unsigned *size) {
 }
 static int iround_nv(float f) { return (int)floorf(f + 0.5f); }
 
-/* out == NULL: returns the level size (0 = layout the reference asserts on, or RGB9E5 which is not restated) */
+/* toFloat3SE (CompressorRGB.cpp:231-269) as the reference's x86-64 build computes it: ftoi_round = cvtss2si (nearest even,
+ * INT_MIN for NaN / out of range), and 1 << n with a negative n takes the count modulo 32 (so every pixel below 256 gets
+ * zero mantissas - kept, the reference is the contract). */
+static int ftoi_round_x86(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)lrintf(f) : (int)0x80000000; }
+static float nvmax_f(float a, float b) { return (b < a) ? a : b; }
+static float nvmin_f(float a, float b) { return (a < b) ? a : b; }
+static uint32_t to_float3se(float r, float g, float b) {
+    const int N = 9, B = 15;
+    const float sharedexp_max = 65408.0f;
+    r = nvmax_f(0.0f, nvmin_f(sharedexp_max, r));
+    g = nvmax_f(0.0f, nvmin_f(sharedexp_max, g));
+    b = nvmax_f(0.0f, nvmin_f(sharedexp_max, b));
+    const float max_c = nvmax_f(r, nvmax_f(g, b));
+    int fl = ftoi_round_x86(floorf(log2f(max_c)));
+    if (fl < -B - 1) fl = -B - 1;
+    const int exp_shared_p = fl + 1 + B;
+    const float dp = (float)(int)(1u << ((unsigned)(exp_shared_p - B - N) & 31u));
+    const int max_s = ftoi_round_x86(max_c / dp);
+    int exp_shared = exp_shared_p;
+    if (max_s == (1 << N)) exp_shared++;
+    const float ds = (float)(int)(1u << ((unsigned)(exp_shared - B - N) & 31u));
+    const uint32_t xm = (uint32_t)ftoi_round_x86(r / ds) & 0x1FFu, ym = (uint32_t)ftoi_round_x86(g / ds) & 0x1FFu;
+    const uint32_t zm = (uint32_t)ftoi_round_x86(b / ds) & 0x1FFu;
+    return xm | (ym << 9) | (zm << 18) | (((uint32_t)exp_shared & 31u) << 27);
+}
+
+/* out == NULL: returns the level size (0 = layout the reference asserts on) */
 long orc_convert_level(const OrcPixelFormatDesc *d, const float *planar, uint8_t *out) {
     unsigned size[4] = {d->rsize, d->gsize, d->bsize, d->asize}, shift[4] = {0, 0, 0, 0}, bitCount;
     const int isFloat = d->pixelType == 4;
@@ -1091,7 +1117,8 @@ long orc_convert_level(const OrcPixelFormatDesc *d, const float *planar, uint8_t
         shift[3] = 0; shift[2] = size[3]; shift[1] = shift[2] + size[2]; shift[0] = shift[1] + size[1];
     }
     if (bitCount == 0 || (!isFloat && bitCount > 32)) return 0;
-    if (d->pixelType == 6 && size[0] == 9 && size[1] == 9 && size[2] == 9 && size[3] == 5) return 0;
+    const int rgb9e5 = d->pixelType == 6 && size[0] == 9 && size[1] == 9 && size[2] == 9 && size[3] == 5;
+    if (rgb9e5 && bitCount != 32) return 0; /* putBits(v.v, 32) whatever bitCount says: only 32-bit layouts are consistent */
     const unsigned alignBits = 8u * (unsigned)d->pitchAlignment;
     const unsigned pitch = ((((unsigned)d->width * bitCount + alignBits - 1) / alignBits) * alignBits + 7) / 8;
     const long total = (long)pitch * d->height;
@@ -1112,6 +1139,8 @@ long orc_convert_level(const OrcPixelFormatDesc *d, const float *planar, uint8_t
                     p |= pf_convert((uint32_t)iv, 16, size[i]) << (shift[i] & 31u);
                 }
                 bs_put_bits(&s, p, bitCount);
+            } else if (rgb9e5) {
+                bs_put_bits(&s, to_float3se(c[0], c[1], c[2]), 32);
             } else {
                 bs_put_bits(&s, 0, bitCount); /* signed types: zero components; other SharedExp layouts: zeros */
             }

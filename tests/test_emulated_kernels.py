@@ -174,3 +174,17 @@ def test_emulated_pixel_format_kernels_match_golden(emu, nvtt):
             assert out.size == g3[key].size and np.array_equal(out, g3[key]), (key, path)
             ran.add(path)
     assert ran == {0, 1, 2}
+
+
+def test_emulated_rgb9e5_matches_reference(emu, ref):
+    """k_pixel_format / k_pixel_format_rows with the R9G9B9E5 writer (kind 4) under the CPU emulator against the reference."""
+    from test_oracle import rgb9e5_probe_values
+    vals, w, h = rgb9e5_probe_values()
+    planar = np.ascontiguousarray(np.moveaxis(vals, 2, 0))
+    want = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_sizes=(9, 9, 9, 5), pixel_type=6)
+    U4 = C.c_uint * 4
+    emu.emu_pixel_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_int, U4, U4, C.c_int, C.c_int]
+    for path in (1, 2):
+        out = np.full(4 * w * h, 0xCD, np.uint8)
+        emu.emu_pixel_format(planar.ctypes.data, w, h, out.ctypes.data, 4 * w, 32, 4, U4(9, 9, 9, 5), U4(23, 14, 5, 0), path, 0)
+        assert np.array_equal(out, want), (path, int(np.flatnonzero(out != want)[0]) // 4)

@@ -223,6 +223,9 @@ def test_rgba_pixel_formats_identical(nvtt, ref, ours):
         dict(pixel_sizes=(16, 16, 0, 0), pixel_type=4),
         dict(pixel_sizes=(32, 0, 0, 0), pixel_type=4, pitch_alignment=4),
         dict(pixel_sizes=(11, 11, 10, 0), pixel_type=4, header=False),
+        dict(pixel_sizes=(9, 9, 9, 5), pixel_type=6),   # R9G9B9E5 (toFloat3SE)
+        dict(pixel_masks=(32, 0x1FF, 0x3FE00, 0x7FC0000, 0xF8000000), pixel_type=6),
+        dict(pixel_sizes=(8, 8, 8, 8), pixel_type=6),   # other shared-exponent layouts: zeros
     ]
     for kw in cases:
         kw = dict(kw)

@@ -161,3 +161,17 @@ def test_gpu_pixel_formats_match_golden_and_oracle(nvtt, ctx):
                 got = ctx.convert_level(img, **kw)
                 want = oracleapi.convert_level(img, **kw)
                 assert np.array_equal(got, want), (w, h, kw)
+
+
+@pytest.mark.gpu
+def test_gpu_rgb9e5_matches_reference(nvtt, ctx, ref):
+    """PixelType_SharedExp 9/9/9/5 (toFloat3SE, CompressorRGB.cpp:231-269) on the GPU against the reference: magnitudes across
+    the range, specials, and the floats either side of every power of two (floor(log2f) rounding); by sizes and by masks."""
+    from test_oracle import rgb9e5_probe_values
+    vals, w, h = rgb9e5_probe_values()
+    planar = np.ascontiguousarray(np.moveaxis(vals, 2, 0))
+    for kw in (dict(sizes=(9, 9, 9, 5)), dict(masks=(32, 0x1FF, 0x3FE00, 0x7FC0000, 0xF8000000))):
+        got = ctx.convert_level(planar, pixel_type=6, **kw)
+        want = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_masks=kw.get("masks"), pixel_sizes=kw.get("sizes"),
+                           pixel_type=6)
+        assert got.size == want.size and np.array_equal(got, want), (kw, int(np.flatnonzero(got != want)[0]) // 4)

@@ -84,6 +84,40 @@ def test_oracle_pixel_formats_vs_reference_direct(orc, ref, nvtt):
         assert np.array_equal(a, b), (kw, int(np.flatnonzero(a != b)[0]) if a.size == b.size else (a.size, b.size))
 
 
+def rgb9e5_probe_values():
+    """Inputs for the R9G9B9E5 writer: magnitudes across its range, specials, and the 48 floats either side of every power of
+    two from 2^-20 to 2^17 (where floor(log2f(x)) depends on how log2f rounds)."""
+    rng = np.random.default_rng(5)
+    v = [np.exp(rng.normal(0, 5, 4000)).astype(np.float32), rng.random(1000, dtype=np.float32) * 70000.0,
+         np.array([0.0, -0.0, 1e-30, 1e-8, 255.5, 256.0, 65408.0, 65408.01, 70000.0, np.inf, -np.inf, np.nan, -1.0, 5.9e-39], np.float32)]
+    for k in range(-20, 18):
+        base = np.float32(2.0 ** k).view(np.uint32)
+        v.append((np.arange(-48, 48, dtype=np.int64) + int(base)).astype(np.uint32).view(np.float32))
+    v = np.concatenate(v)
+    n = (v.size + 2) // 3 * 3
+    v = np.concatenate([v, np.zeros(n - v.size, np.float32)])
+    rgb = np.stack([v, np.roll(v, 1) * np.float32(0.37), np.roll(v, 2) * np.float32(0.051)], 1)  # every value is the maximum somewhere
+    w = 64
+    h = (rgb.shape[0] + w - 1) // w
+    img = np.zeros((h * w, 4), np.float32)
+    img[:rgb.shape[0], :3] = rgb
+    img[:, 3] = 1.0
+    return img.reshape(h, w, 4), w, h
+
+
+def test_oracle_rgb9e5_vs_reference(orc, ref):
+    """PixelType_SharedExp 9/9/9/5 (toFloat3SE, CompressorRGB.cpp:231-269), by sizes and by masks, against the reference itself -
+    including its x86 shift-count behaviour (zero mantissas below 256) and the log2f rounding at powers of two."""
+    vals, w, h = rgb9e5_probe_values()
+    planar = np.ascontiguousarray(np.moveaxis(vals, 2, 0))
+    for kw in (dict(sizes=(9, 9, 9, 5)), dict(masks=(32, 0x1FF, 0x3FE00, 0x7FC0000, 0xF8000000))):
+        a = orc.convert_level(planar, pixel_type=6, **kw)
+        b = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_masks=kw.get("masks"), pixel_sizes=kw.get("sizes"),
+                        pixel_type=6)
+        assert a.size == b.size and np.array_equal(a, b), (kw, int(np.flatnonzero(a != b)[0]) // 4)
+    assert np.count_nonzero(b.view(np.uint32) & 0x7FFFFFF) > 1000  # the mantissas are not all zero: values >= 256 are encoded
+
+
 def test_oracle_vs_reference_direct(orc, ref, nvtt):
     """Wider sweep against the reference itself (only where oracle/_ref exists)."""
     s = nvtt.synth
