@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # NVTT_B200_FASTMATH=1 selects the FMA-contracted build (same C ABI, faster, outside the bit-exact parity contract)
 FASTMATH = os.environ.get("NVTT_B200_FASTMATH", "0") not in ("", "0")
-LIB_PATH = os.path.join(_HERE, "lib", "libnvtt_b200_fastmath.so" if FASTMATH else "libnvtt_b200.so")
+LIB_PATH = os.environ.get("NVTT_B200_LIB") or os.path.join(_HERE, "lib", "libnvtt_b200_fastmath.so" if FASTMATH else "libnvtt_b200.so")
 
 # nvtt enums (src/nvtt/nvtt.h:80-277 of the reference)
 Format_RGB, Format_DXT1, Format_DXT1a, Format_DXT3, Format_DXT5, Format_DXT5n, Format_BC4, Format_BC5 = range(8)

@@ -45,6 +45,9 @@ struct Bc1Params {
 };
 
 #define NVB_BC1_GROUPS 8
+#ifndef NVB_BC1_MINB
+#define NVB_BC1_MINB 9  // resident CTAs per SM the register budget is set for (56 registers)
+#endif
 
 struct Bc1GroupSmem {
     float4 pts[16];   // reduced colour set (x,y,z,weight)
@@ -145,8 +148,17 @@ NVB_DEV unsigned group_gather_bits2(unsigned gm, unsigned idx, int l) {
 NVB_DEV float select4(const float v[4], unsigned i) { return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : v[3]; }
 
 // output_block4 / output_block3: endpoints -> 565, palette, per-texel index, weighted MSE (ordered sum).
+// NVB_BC1_CALLS: the two big helpers as real calls instead of 2-3 inlined copies each.  Instruction-cache experiment (ncu shows
+// 2.2 warps per issue stalled on "no instruction"): the Level 9 kernel shrinks from 5448 to 4408 instructions but gets slower
+// (8192² Production 42.0 -> 43.7 ms), and so does every register budget tried with it (NVB_BC1_MINB 8 / 10: 43.2 / 44.2 ms;
+// profiles/r2g_bc1_variants.txt) - so the inlined copies and 9 CTAs per SM stay.
+#ifdef NVB_BC1_CALLS
+#define NVB_BC1_HELPER NVB_DEV_CALL
+#else
+#define NVB_BC1_HELPER NVB_DEV
+#endif
 template <bool U>
-NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool four, bool allow_black, float sx, float sy, float sz,
+NVB_BC1_HELPER float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool four, bool allow_black, float sx, float sy, float sz,
                                 float ex, float ey, float ez, float cx, float cy, float cz, float wt, Bc1Block *blk) {
     unsigned color0 = icbc_vector3_to_color16(P, sx, sy, sz);
     unsigned color1 = icbc_vector3_to_color16(P, ex, ey, ez);
@@ -191,7 +203,7 @@ NVB_DEV float icbc_output_block(const Bc1Params &P, unsigned gm, int l, bool fou
 }
 
 // compute_sat on S.pts[0..n): PCA ordering + summed area table in S.sat.  All lanes of the group call it.
-NVB_DEV void icbc_compute_sat(Bc1GroupSmem &S, unsigned gm, int l, int n) {
+NVB_BC1_HELPER void icbc_compute_sat(Bc1GroupSmem &S, unsigned gm, int l, int n) {
     // centroid
     float total = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
     for (int i = 0; i < n; i++) {
@@ -471,7 +483,7 @@ NVB_DEV FitResult icbc_cluster_fit(const Bc1Params &P, const Bc1GroupSmem &S, un
 // evicted each other's code (Production got slower when the cluster fit got bigger).
 // U: colour weights (1, 1, 1) - see cw_mul.
 #define NVB_BC1_PAL_PITCH 5  // float4 per lane: 80 bytes, so that the 128-bit reads of 8 consecutive lanes touch all 32 banks once
-template <int LEVEL, bool RGBM, bool U> __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16, 9) k_bc1_icbc_t(Bc1Params P) {
+template <int LEVEL, bool RGBM, bool U> __global__ void __launch_bounds__(NVB_BC1_GROUPS * 16, NVB_BC1_MINB) k_bc1_icbc_t(Bc1Params P) {
     __shared__ Bc1GroupSmem smem[NVB_BC1_GROUPS];
     // Level 9: the palette of the refinement candidate each lane is measuring, read back by palette index
     __shared__ float4 s_pal[LEVEL == 9 ? NVB_BC1_GROUPS * 16 * NVB_BC1_PAL_PITCH : 1];
