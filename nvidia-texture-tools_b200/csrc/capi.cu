@@ -104,6 +104,12 @@ struct NvttbContext {
     // block-row sharding of one image: band 0 runs the tail levels on tail_stream (own encoder scratch, own level buffers)
     // while its share of the big levels is still being encoded on `stream`
     cudaStream_t tail_stream = nullptr;
+    // The mip levels of an image are built and encoded on side_stream (highest priority) while level 0 is still being encoded
+    // on `stream`: a small level cannot fill 148 SMs and costs at least the latency of one block (tens of microseconds for the
+    // cluster-fit encoders) - one after the other on one stream that is 1 % of a step on one GPU and 5 % when the image is
+    // spread over eight.  Side by side with level 0 their blocks simply take free slots.
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_side_go = nullptr, ev_side_done = nullptr, ev_cv[MAX_BANDS] = {};
     enum { MAX_LEVELS = 32 };
     cudaEvent_t ev_lvl[MAX_LEVELS] = {}, ev_tail_done = nullptr;
     DevBuf tail_scratch, tail_lvl, exchange;
@@ -246,7 +252,17 @@ int nvttb_context_create(int device, NvttbContext **out) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_tail_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {
+        // highest priority: their few blocks are scheduled ahead of the pending blocks of a big level on `stream`
+        int prio_lo = 0, prio_hi = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return bail("cudaDeviceGetStreamPriorityRange", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_side_go, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < NvttbContext::MAX_BANDS; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_cv[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < NvttbContext::MAX_LEVELS; i++)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_lvl[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void **)&ctx->h_fault, sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return bail("cudaHostAlloc", e);
@@ -353,6 +369,14 @@ void nvttb_context_destroy(NvttbContext *ctx) {
         if (ctx->ev_lvl[i]) cudaEventDestroy(ctx->ev_lvl[i]);
     if (ctx->ev_tail_done) cudaEventDestroy(ctx->ev_tail_done);
     cudaStreamDestroy(ctx->tail_stream);
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->ev_side_go) cudaEventDestroy(ctx->ev_side_go);
+    if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
+    for (int i = 0; i < NvttbContext::MAX_BANDS; i++)
+        if (ctx->ev_cv[i]) cudaEventDestroy(ctx->ev_cv[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     for (auto &kv : ctx->poly_cache) {
         cudaFree(kv.second.weights);
@@ -1770,22 +1794,51 @@ size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
 // h_out (optional, pinned host memory of the same layout as d_out): finished pieces are copied back on d2h_stream while
 // the rest of the chain is still being computed; the caller synchronises d2h_stream.
 // in_place (sharded images only): d_out is the whole chain of the processed faces and the band's slices go to their final offsets.
+// While alive (and `on`), everything the context launches goes to side_stream.  Per-launch event timing (nvttb_profile_*)
+// describes the main stream; launches that overlap it would be counted twice.
+struct SideScope {
+    NvttbContext *c;
+    bool on, prof;
+    SideScope(NvttbContext *ctx, bool enable) : c(ctx), on(enable), prof(ctx->profiling) {
+        if (on) {
+            std::swap(c->stream, c->side_stream);
+            c->profiling = false;
+        }
+    }
+    ~SideScope() {
+        if (on) {
+            std::swap(c->stream, c->side_stream);
+            c->profiling = prof;
+        }
+    }
+};
+
 static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const void *const *images, int loc, int f0, int f1,
                          unsigned char *d_out, unsigned char *h_out = nullptr, bool in_place = false) {
     const int mips = nvttb_process_mip_count(d);
     const size_t fbytes = face_bytes(d);
     const int W = d->width, H = d->height;
     int rc;
-    // ping-pong level buffers: A holds level m, B receives level m+1
+    // level buffers: A holds level 0, B the levels 1.. one after the other (every level stays until the face is done, so the
+    // encode of a level need not finish before the next ones are built)
     DevBuf &A = ctx->lvlA, &B = ctx->lvlB;  // persistent scratch: no cudaMalloc/cudaFree per call
     if ((rc = ensure(ctx, A, (size_t)W * H * 16)) != NVTTB_OK) return rc;
-    if (mips > 1) {
-        const int w1 = W / 2 > 1 ? W / 2 : 1, h1 = H / 2 > 1 ? H / 2 : 1;
-        if ((rc = ensure(ctx, B, (size_t)w1 * h1 * 16)) != NVTTB_OK) return rc;
+    if (mips > NvttbContext::MAX_LEVELS) return fail(ctx, NVTTB_ERR_INVALID_INPUT, "too many levels");
+    size_t mip_off[NvttbContext::MAX_LEVELS + 1];  // floats
+    mip_off[0] = mip_off[1] = 0;
+    {
+        int w = W, h = H;
+        for (int m = 1; m < mips; m++) {
+            w = w / 2 > 1 ? w / 2 : 1;
+            h = h / 2 > 1 ? h / 2 : 1;
+            mip_off[m + 1] = mip_off[m] + (((size_t)4 * w * h + 3) & ~(size_t)3);  // 16-byte aligned levels
+        }
     }
+    if (mips > 1 && (rc = ensure(ctx, B, mip_off[mips] * sizeof(float))) != NVTTB_OK) return rc;
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->h2d_stream);
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->side_stream);
         cudaStreamSynchronize(ctx->d2h_stream);
     };
     const bool toNormal = d->convertToNormalMap != 0;
@@ -1801,6 +1854,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     ShardGeom geom;
     const bool sharded = shard_geom(d, &geom);
     const bool banded = !sharded && loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
+    // mips on side_stream, beside the level-0 encode (not for the encoders that share per-context scratch, BC6H / BC7: they are
+    // long enough for the latency of a small level not to matter)
+    const bool use_side = mips > 1 && !sharded && !gamSlow && encoder_scratch_bytes(d->encode.format, W, H) == 0;
     const int bhTotal = (H + 3) / 4;
     const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
     const int bandBlockRows = (bhTotal + nbands - 1) / nbands;
@@ -1835,6 +1891,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[b], 0));
                 float *rows = (float *)A.p + (size_t)y0 * W;
                 if ((rc = convert_device(ctx, d->inputFormat, (const char *)ctx->in_stage.p + (size_t)y0 * W * bpp, (size_t)(y1 - y0) * W, rows, (size_t)W * H, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+                if (use_side && y1 == H) CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));  // level 0 is complete: the mips may start
                 e.height = y1 - y0;
                 const size_t ooff = (size_t)(y0 / 4) * bw0 * bs, obytes = (size_t)((y1 - y0 + 3) / 4) * bw0 * bs;
                 if ((rc = encode_device(ctx, &e, rows, W, y1 - y0, out + ooff, (size_t)W * H)) != NVTTB_OK) { cleanup(); return rc; }
@@ -1854,7 +1911,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 if ((rc = gamma_device(ctx, (float *)A.p, (size_t)W * H, true, d->inputGamma)) != NVTTB_OK) { cleanup(); return rc; }
             }
         }
-        float *cur = (float *)A.p, *nxt = (float *)B.p;
+        float *cur = (float *)A.p;
         if (toNormal) {
             // img.toGreyScale(heightFactors); img.toNormalMap(bumpFrequencyScale)  (Context.cpp:269-272)
             if ((rc = ensure(ctx, ctx->tmp_level, (size_t)W * H * 16)) != NVTTB_OK) { cleanup(); return rc; }
@@ -1862,8 +1919,13 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             if ((rc = normal_map_device(ctx, cur, (float *)ctx->tmp_level.p, W, H, d->wrapMode, d->bumpFrequencyScale)) != NVTTB_OK) { cleanup(); return rc; }
             CK(cudaMemcpyAsync(cur, ctx->tmp_level.p, (size_t)W * H * 16, cudaMemcpyDeviceToDevice, ctx->stream));
         }
+        if (use_side) {
+            if (!banded) CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));  // level 0 is complete
+            CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
+        }
         int w = W, h = H;
         for (int m = 0; m < mips; m++) {
+            SideScope side(ctx, use_side && m > 0);
             if (m > 0) {
                 const int dw = w / 2 > 1 ? w / 2 : 1, dh = h / 2 > 1 ? h / 2 : 1;
                 float fw, pr[2];
@@ -1874,8 +1936,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                     pr[1] = d->kaiserStretch;
                 }
                 // normal maps: the mip is renormalised (expand -> normalise -> pack) before it is encoded and down-sampled again
+                float *nxt = (float *)B.p + mip_off[m];
                 if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh, isNormal && d->normalizeMipmaps)) != NVTTB_OK) { cleanup(); return rc; }
-                float *t = cur; cur = nxt; nxt = t;
+                cur = nxt;
                 w = dw;
                 h = dh;
             }
@@ -1912,6 +1975,11 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
             }
             out += nvttb_level_size(e.format, w, h);
+        }
+        if (use_side) {
+            // the face is done when both streams are; the level buffers are reused by the next face
+            CK(cudaEventRecord(ctx->ev_side_done, ctx->side_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
         }
         if (hout && !in_place) {
             // whatever of this face has not been sent yet: the mip tail (banded) or the whole chain
@@ -2035,6 +2103,7 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->h2d_stream);
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->side_stream);
         cudaStreamSynchronize(ctx->tail_stream);
         cudaStreamSynchronize(ctx->d2h_stream);
     };
@@ -2044,6 +2113,16 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     const bool host_in = loc == NVTTB_HOST;
     const bool per_chunk_events = K <= NvttbContext::MAX_BANDS;
     const size_t chunk_in = (size_t)C * W * bpp;
+    // Everything but the level-0 encode runs on side_stream (process_faces explains why): conversion of the chunks as they
+    // arrive, the band's mip chain, the export to band 0 and the encodes of levels 1..k.  Not for the encoders that share
+    // per-context scratch (BC6H / BC7).
+    const bool use_side = encoder_scratch_bytes(d->encode.format, W, HL) == 0;
+    const bool side_conv = use_side && per_chunk_events;
+    if (use_side) {
+        // the previous image may still be read on `stream`: the side stream starts behind it
+        CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
+    }
     // 1. the band's chunks: upload (copy stream), convert and - for host input - encode level 0 chunk by chunk, so that
     //    the copies of the following chunks hide under the encode
     if (host_in) {
@@ -2059,11 +2138,17 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     const size_t row_bytes0 = (size_t)((W + 3) / 4) * bs;
     for (int j = 0; j < K; j++) {
         const size_t c = (size_t)j * N + b;
-        if (host_in && (per_chunk_events || j == 0)) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[per_chunk_events ? j : 0], 0));
-        const char *src = host_in ? (const char *)ctx->in_stage.p + j * chunk_in : (const char *)image + c * chunk_in;
         float *rows = chain + (size_t)j * C * W;
-        if ((rc = convert_device(ctx, d->inputFormat, src, (size_t)C * W, rows, (size_t)W * HL, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+        {
+            SideScope side(ctx, side_conv);
+            if (host_in && (per_chunk_events || j == 0)) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[per_chunk_events ? j : 0], 0));
+            const char *src = host_in ? (const char *)ctx->in_stage.p + j * chunk_in : (const char *)image + c * chunk_in;
+            if ((rc = convert_device(ctx, d->inputFormat, src, (size_t)C * W, rows, (size_t)W * HL, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+            if (side_conv) CK(cudaEventRecord(ctx->ev_cv[j], ctx->stream));
+            if (host_in && j == K - 1) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+        }
         if (host_in) {
+            if (side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[j], 0));
             e.width = W;
             e.height = C;
             const size_t ooff = lvl_off[0] + c * rpc0 * row_bytes0;
@@ -2076,14 +2161,21 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
             }
         }
     }
-    if (host_in) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+    if (use_side && !side_conv) {
+        // the chunks were converted on `stream`: the side stream continues from there
+        CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
+    }
     // 2. the band's rows of levels 1..k
-    for (int m = 1; m <= k; m++) {
-        float *lm = chain + loff[m];
-        if ((rc = next_mip_device(ctx, MF_Box, 0.5f, 0.0f, 0.0f, d->alphaMode, d->wrapMode, chain + loff[m - 1], W >> (m - 1), HL >> (m - 1), lm, W >> m, HL >> m)) != NVTTB_OK) { cleanup(); return rc; }
-        if (isNormal && d->normalizeMipmaps) {
-            NormalizeParams P{lm, (size_t)(W >> m) * (HL >> m), 1};
-            NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
+    {
+        SideScope side(ctx, use_side);
+        for (int m = 1; m <= k; m++) {
+            float *lm = chain + loff[m];
+            if ((rc = next_mip_device(ctx, MF_Box, 0.5f, 0.0f, 0.0f, d->alphaMode, d->wrapMode, chain + loff[m - 1], W >> (m - 1), HL >> (m - 1), lm, W >> m, HL >> m)) != NVTTB_OK) { cleanup(); return rc; }
+            if (isNormal && d->normalizeMipmaps) {
+                NormalizeParams P{lm, (size_t)(W >> m) * (HL >> m), 1};
+                NVB_LAUNCH(ctx, K_NORMALIZE, (double)P.pixels, k_normalize, grid_for(P.pixels, 256), 256, P);
+            }
         }
     }
     // 3. rows of level k -> band 0 (peer stores), then the arrival flag
@@ -2091,6 +2183,7 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     const unsigned seq = d->bandSequence;
     float *ximg = tail ? (float *)((char *)d->bandExchange + NVB_XCHG_HEADER) + (size_t)(seq & 1u) * 4 * pl.wk * pl.hk : nullptr;
     if (tail) {
+        SideScope side(ctx, use_side);
         // the buffer of this parity was last used by image seq - 2: band 0 must have finished reading it
         if (seq >= 3) NVB_LAUNCH(ctx, K_XCHG, 0.0, k_xchg_wait, 1, 32, xhdr + NVB_XCHG_ACK, 1, seq - 2, ctx->h_fault);
         ExportRowsParams X{chain + loff[k], ximg, pl.wk, HL >> k, pl.hk, C >> k, N, b};
@@ -2142,6 +2235,8 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     }
     // 5. the band's rows of the distributed levels: one launch per level over the concatenated chunks
     for (int m = host_in ? 1 : 0; m <= k; m++) {
+        SideScope side(ctx, use_side && m > 0);
+        if (m == 0 && side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[K - 1], 0));  // level 0 was converted on the side stream
         const int w = W >> m, hl = HL >> m;
         const int rpc = C / (4 << m);
         const size_t row_bytes = (size_t)((w + 3) / 4) * bs;
@@ -2155,6 +2250,10 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
             const size_t first = lvl_off[m] + (size_t)b * rpc * row_bytes, pitch = (size_t)N * rpc * row_bytes;
             CK(cudaMemcpy2DAsync(h_out + first, pitch, out + first, pitch, (size_t)rpc * row_bytes, K, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
+    }
+    if (use_side) {
+        CK(cudaEventRecord(ctx->ev_side_done, ctx->side_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
     }
     if (tail && b == 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail_done, 0));
     CK(cudaGetLastError());

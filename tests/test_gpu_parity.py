@@ -231,6 +231,14 @@ def test_surface_misc_bit_exact(nvtt, ref, ctx):
         a.set_image(fmt, w, h, data)
         b.set_image(fmt, w, h, data)
         assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "setImage fmt %d" % fmt
+    # RGBA16F: every one of the 2^16 half bit patterns (denormals, infinities, every NaN payload), in every channel
+    allh = np.arange(65536, dtype=np.uint16).reshape(256, 256, 1)
+    data = np.concatenate([allh, allh[::-1], np.roll(allh, 7, 0), allh.transpose(1, 0, 2)], 2).copy()
+    a = ref.Surface()
+    b = nvtt.Surface(ctx)
+    a.set_image(1, 256, 256, data)
+    b.set_image(1, 256, 256, data)
+    assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32)), "setImage RGBA16F: full half sweep"
     # normal-map renormalisation
     im8 = nvtt.synth.normal_bgra8(w, h)
     a = ref.Surface(normal_map=True)

@@ -132,6 +132,12 @@ def test_oracle_vs_reference_direct(orc, ref, nvtt):
                         a = orc.compress_level(fmt, q, img, am, (0.8, 1.0, 0.6, 1.0))
                         b = ref.compress_level(fmt, q, img, alpha_mode=am, color_weights=(0.8, 1.0, 0.6, 1.0))
                         assert np.array_equal(a, b), (w, h, fmt, q, am)
+    # every half bit pattern through setImage (half_to_float, Half.cpp)
+    allh = np.arange(65536, dtype=np.uint16).reshape(256, 256, 1)
+    sweep = np.concatenate([allh, allh[::-1], np.roll(allh, 7, 0), allh.transpose(1, 0, 2)], 2).copy()
+    r = ref.Surface()
+    r.set_image(1, 256, 256, sweep)
+    assert np.array_equal(orc.set_image(1, 256, 256, sweep).view(np.uint32), r.get().view(np.uint32))
     # fp16 input + Mitchell resize + renormalise
     hh = rng.integers(0, 65536, (16, 24, 4)).astype(np.uint16)
     r = ref.Surface()
