@@ -930,8 +930,16 @@ static PFN_encodeTiled tensor_map_encoder() {
     return fn;
 }
 
+// Optional block encode of the new level inside the filter kernel (k_polyphase_tma<W, true>): BC4 / BC5 quick alpha blocks.
+struct MipFuse {
+    unsigned char *out;     // the level's blocks
+    int channels, stride;   // 1 / 8 (BC4) or 2 / 16 (BC5)
+    const float *to_gamma;  // fused toGamma(2.2) table or null
+    bool done;              // set when the level was encoded by the filter kernel
+};
+
 template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDev &px, const PolyDev &py, int wrap, const float *src, int sw, int sh,
-                                                 float *dst, int dw, int dh, bool normalize, bool *done) {
+                                                 float *dst, int dw, int dh, bool normalize, bool *done, MipFuse *fuse = nullptr) {
     using G = PtGeom<W>;
     PFN_encodeTiled enc = tensor_map_encoder();
     if (!enc) return NVTTB_OK;  // *done stays false: the caller takes the plain kernel
@@ -945,7 +953,8 @@ template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDe
         return NVTTB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(k_polyphase_tma<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_polyphase_tma<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_polyphase_tma<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
         attr_set = true;
     }
     PolyTmaParams Q;
@@ -955,6 +964,12 @@ template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDe
     Q.tiles_x = (dw + NVB_PT_TW - 1) / NVB_PT_TW;
     Q.tiles_y = (dh + NVB_PT_TH - 1) / NVB_PT_TH;
     Q.normalize = normalize ? 1 : 0;
+    if (fuse) {
+        Q.enc_out = fuse->out;
+        Q.enc_channels = fuse->channels;
+        Q.enc_stride = fuse->stride;
+        Q.enc_to_gamma = fuse->to_gamma;
+    }
     const int ntiles = Q.tiles_x * Q.tiles_y;
     // persistent: three CTAs per SM (74 KB of shared memory each), every CTA the same number of tiles (+-1)
     const int per_cta = (ntiles + 148 * 3 - 1) / (148 * 3);
@@ -964,16 +979,19 @@ template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDe
         r_.kid = K_POLY_2D; r_.units = (double)dw * dh;
         cudaEventCreate(&r_.a); cudaEventCreate(&r_.b); cudaEventRecord(r_.a, ctx->stream);
     }
-    k_polyphase_tma<W><<<grid, NVB_PT_THREADS, G::SMEM_BYTES, ctx->stream>>>(map, Q);
+    if (fuse) k_polyphase_tma<W, true><<<grid, NVB_PT_THREADS, G::SMEM_BYTES, ctx->stream>>>(map, Q);
+    else k_polyphase_tma<W, false><<<grid, NVB_PT_THREADS, G::SMEM_BYTES, ctx->stream>>>(map, Q);
     if (ctx->profiling) { cudaEventRecord(r_.b, ctx->stream); ctx->prof.push_back(r_); }
     ctx->launches++;
     CK(cudaGetLastError());
     *done = true;
+    if (fuse) fuse->done = true;
     return NVTTB_OK;
 }
 
 // normalize: also apply the normal-map renormalisation of a mip (expand -> normalise -> pack) to planes 0..2 of dst
-static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false) {
+static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false,
+                         MipFuse *fuse = nullptr) {
     PolyDev px, py;
     int rc;
     if ((rc = get_poly(ctx, f, sw, dw, &px)) != NVTTB_OK) return rc;
@@ -991,9 +1009,9 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
         (size_t)dw * dh >= (size_t)128 * NVB_PT_TW * NVB_PT_TH) {  // small levels: more (tile, plane) CTAs beat a persistent loop
         // TMA-fed persistent kernel for the 2:1 mip filters (+ fused renormalisation)
         bool done = false;
-        if (px.window == 13) rc = launch_polyphase_tma<13>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
-        else if (px.window == 9) rc = launch_polyphase_tma<9>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
-        else if (px.window == 5) rc = launch_polyphase_tma<5>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done);
+        if (px.window == 13) rc = launch_polyphase_tma<13>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done, fuse);
+        else if (px.window == 9) rc = launch_polyphase_tma<9>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done, fuse);
+        else if (px.window == 5) rc = launch_polyphase_tma<5>(ctx, px, py, wrap, src, sw, sh, dst, dw, dh, normalize, &done, fuse);
         if (rc != NVTTB_OK) return rc;
         if (done) return NVTTB_OK;
     }
@@ -1021,7 +1039,7 @@ static int resize_device(NvttbContext *ctx, const FilterDesc &f, int wrap, const
 
 // Surface::buildNextMipmap semantics on raw device buffers.  Returns via *dw,*dh the new size.
 static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidth, float p0, float p1, int alphaMode, int wrap,
-                           const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false) {
+                           const float *src, int sw, int sh, float *dst, int dw, int dh, bool normalize = false, MipFuse *fuse = nullptr) {
     if (mipmapFilter == MF_Box && filterWidth == 0.5f && alphaMode != AM_Transparency) {
         BoxDownParams P{src, dst, sw, sh, dw, dh, 4};
         if ((sw & 3) == 0 && (sh & 1) == 0 && sh >= 2 && dh <= 65535 && ((size_t)src & 15) == 0 && ((size_t)dst & 7) == 0) {
@@ -1042,7 +1060,7 @@ static int next_mip_device(NvttbContext *ctx, int mipmapFilter, float filterWidt
     f.width = filterWidth;
     f.p0 = (f.kind == Filter_Kaiser) ? p0 : 0.0f;
     f.p1 = (f.kind == Filter_Kaiser) ? p1 : 0.0f;
-    return resize_device(ctx, f, wrap, src, sw, sh, dst, dw, dh, normalize);
+    return resize_device(ctx, f, wrap, src, sw, sh, dst, dw, dh, normalize, fuse);
 }
 
 static void default_filter(int filter, float *width, float params[2]) {
@@ -1857,6 +1875,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     // mips on side_stream, beside the level-0 encode (not for the encoders that share per-context scratch, BC6H / BC7: they are
     // long enough for the latency of a small level not to matter)
     const bool use_side = mips > 1 && !sharded && !gamSlow && encoder_scratch_bytes(d->encode.format, W, H) == 0;
+    // opt-in: the 2:1 filter kernel block-encodes the level it builds (BC4 / BC5 quick alpha blocks; polyphase_tma.cuh)
+    static const bool fused_env = getenv("NVTT_B200_FUSED_MIP_ENCODE") != nullptr;
+    const bool can_fuse = fused_env && !sharded && !gamSlow && (d->encode.format == F_BC4 || d->encode.format == F_BC5) && d->encode.quality < Q_Production;
     const int bhTotal = (H + 3) / 4;
     const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
     const int bandBlockRows = (bhTotal + nbands - 1) / nbands;
@@ -1926,6 +1947,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
         int w = W, h = H;
         for (int m = 0; m < mips; m++) {
             SideScope side(ctx, use_side && m > 0);
+            MipFuse fuse{nullptr, 0, 0, nullptr, false};
             if (m > 0) {
                 const int dw = w / 2 > 1 ? w / 2 : 1, dh = h / 2 > 1 ? h / 2 : 1;
                 float fw, pr[2];
@@ -1937,7 +1959,9 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 }
                 // normal maps: the mip is renormalised (expand -> normalise -> pack) before it is encoded and down-sampled again
                 float *nxt = (float *)B.p + mip_off[m];
-                if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh, isNormal && d->normalizeMipmaps)) != NVTTB_OK) { cleanup(); return rc; }
+                fuse = MipFuse{out, d->encode.format == F_BC5 ? 2 : 1, d->encode.format == F_BC5 ? 16 : 8, gamFast ? ctx->d_to_gamma : nullptr, false};
+                if ((rc = next_mip_device(ctx, d->mipmapFilter, fw, pr[0], pr[1], d->alphaMode, d->wrapMode, cur, w, h, nxt, dw, dh, isNormal && d->normalizeMipmaps,
+                                          can_fuse ? &fuse : nullptr)) != NVTTB_OK) { cleanup(); return rc; }
                 cur = nxt;
                 w = dw;
                 h = dh;
@@ -1971,7 +1995,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
                 level_off += nvttb_level_size(e.format, w, h);
                 continue;
             }
-            if (!(m == 0 && level0_done)) {
+            if (!(m == 0 && level0_done) && !fuse.done) {  // fuse.done: the filter kernel has encoded the level it built
                 if ((rc = encode_device(ctx, &e, src, w, h, out)) != NVTTB_OK) { cleanup(); return rc; }
             }
             out += nvttb_level_size(e.format, w, h);

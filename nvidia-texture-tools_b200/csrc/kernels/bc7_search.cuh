@@ -21,6 +21,7 @@
 // "err < threshold" that follows gives the same answer for the full sum.
 #pragma once
 #include "bc7.cuh"
+#include <type_traits>
 
 #ifdef NVB_EMU_STATS
 void emu_bx_stat(int mode, int np, int trials, int iters);
@@ -186,7 +187,10 @@ template <int M> NVB_DEV void bx_eval2(const float4 *px, int np, unsigned A0, un
     bx_neg_palette<M>(A0, B0, la, lb, np0);
     bx_neg_palette<M>(A1, B1, la, lb, np1);
     float tot0 = 0, tot1 = 0;
-    unsigned long long id0 = 0, id1 = 0;
+    // the index arrays are only compared for equality: with four palette entries 2 bits per texel fit one 32-bit word, and
+    // "id * 4 + j" is one instruction where the 64-bit shift-and-or takes three
+    typename std::conditional<(N <= 4), unsigned, unsigned long long>::type id0 = 0, id1 = 0;
+    constexpr int IDB = N <= 4 ? 2 : 4;
     for (int i = 0; i < np; ++i) {
         const float4 c = px[i];
         const float ww = c.w;
@@ -220,10 +224,10 @@ template <int M> NVB_DEV void bx_eval2(const float4 *px, int np, unsigned A0, un
             }
             if (t == 0) {
                 tot0 += best;
-                id0 = (id0 << 4) | (unsigned long long)bj;
+                id0 = (id0 << IDB) + (unsigned)bj;
             } else {
                 tot1 += best;
-                id1 = (id1 << 4) | (unsigned long long)bj;
+                id1 = (id1 << IDB) + (unsigned)bj;
             }
         }
     }

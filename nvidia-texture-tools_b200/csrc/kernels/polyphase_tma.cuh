@@ -9,13 +9,18 @@
 //     for 52 in Y) instead of one shared-memory load per multiply-add - the old kernel was LSU bound (58 % LSU pipe);
 //   * the four planes of a tile are consecutive ring entries, so the normal-map renormalisation of the mip
 //     (expandNormals -> normalizeNormalMap -> packNormals, Context.cpp:329-334) is applied to the tile before it is written:
-//     no separate pass over the new level.
+//     no separate pass over the new level;
+//   * FUSE (opt-in, NVTT_B200_FUSED_MIP_ENCODE): the tile of the NEW level is block-encoded where it lies - BC4 / BC5 at
+//     Quality_Fastest / Normal (QuickCompress::compressDXT5A, bc_alpha.cuh) from the quantised red (and green) plane kept in
+//     shared memory, 64 blocks x channels per tile, one thread each - so the level is never read back for its encode.
+//     Byte-identical to k_alpha_blocks; measured slower than the two kernels side by side, hence opt-in.
 // Every output is the same ascending-tap sum of single-rounded products as in k_polyphase_x / _y (no FMA), so results are
 // bit-identical to the reference.  At an exact 2:1 ratio every output column (row) has the same 13 weights and
 // left[i] = 2 i + left0 - the host checks both on the tables it built from the reference's formulae before taking this path.
 #pragma once
 #include "../nvb_common.cuh"
 #include "image_ops.cuh"
+#include "bc_alpha.cuh"
 #ifndef NVB_EMU
 #include <cuda.h>
 #endif
@@ -57,6 +62,10 @@ struct PolyTmaParams {
     float wx[NVB_PT_MAXW], wy[NVB_PT_MAXW];
     int tiles_x, tiles_y;
     int normalize;       // planes 0..2 of the new level: x = 2x - 1, normalise (zero stays zero), x = 0.5x + 0.5
+    // FUSE: block-encode the new level's first enc_channels planes (1 = BC4, 2 = BC5) as DXT5 alpha blocks
+    unsigned char *enc_out = nullptr;
+    int enc_channels = 0, enc_stride = 8;
+    const float *enc_to_gamma = nullptr;  // fused Surface::toGamma(2.2) of the colour pipeline (not for normal maps)
 };
 
 #ifndef NVB_EMU
@@ -87,10 +96,12 @@ NVB_DEV void pt_tma_load_3d(void *smem_dst, const CUtensorMap *map, unsigned lon
                  : "memory");
 }
 
-template <int W> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphase_tma(const __grid_constant__ CUtensorMap tmap, PolyTmaParams P) {
+template <int W, bool FUSE = false> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphase_tma(const __grid_constant__ CUtensorMap tmap, PolyTmaParams P) {
     using G = PtGeom<W>;
     extern __shared__ __align__(128) unsigned char pt_smem[];
     __shared__ __align__(8) unsigned long long mbar[2];
+    // FUSE: the tile's encoded channels, quantised like ColorBlock::init does (uint8(255 * clamp(v, 0, 1)), truncation)
+    __shared__ unsigned char s_q[FUSE ? 2 : 1][FUSE ? NVB_PT_TH : 1][FUSE ? NVB_PT_TW + 4 : 4];
     float *const s_in0 = reinterpret_cast<float *>(pt_smem);
     float *const s_in1 = reinterpret_cast<float *>(pt_smem + G::STAGE_BYTES);
     float *const s_tmp = reinterpret_cast<float *>(pt_smem + 2 * G::STAGE_BYTES);
@@ -217,6 +228,8 @@ template <int W> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphas
                 if (oy < T.th && yox < T.tw) {
                     if (keep) s_out[(plane * NVB_PT_TH + oy) * G::OUT_PITCH + yox] = a;
                     else drow[(size_t)q * dw] = a;
+                    if (FUSE && !normalize && plane < P.enc_channels)
+                        s_q[plane][oy][yox] = (unsigned char)quantize_u8_trunc(P.enc_to_gamma ? nvb_powf_5_11(a, P.enc_to_gamma) : a);
                 }
             }
         }
@@ -245,8 +258,30 @@ template <int W> __global__ void __launch_bounds__(NVB_PT_THREADS, 3) k_polyphas
                 dst[o] = x;
                 dst[dn + o] = y;
                 dst[2 * dn + o] = z;
+                if (FUSE) {  // normal maps are not gamma corrected (Context.cpp:337-343)
+                    s_q[0][oy][ox] = (unsigned char)quantize_u8_trunc(x);
+                    if (P.enc_channels > 1) s_q[1][oy][ox] = (unsigned char)quantize_u8_trunc(y);
+                }
             }
             // s_out is next written by the Y pass of the following tile's plane 0, two barriers from here
+        }
+        if (FUSE && plane == (normalize ? 2 : P.enc_channels - 1)) {
+            // the encoded channels of the tile are complete: one thread per (4x4 block, channel), partial blocks at the image
+            // edge repeat their texels by modulo like alpha_gather_block (ColorBlock::init)
+            if (normalize) __syncthreads();  // the renormalised values (the plain path is behind the Y pass's barrier already)
+            const int nbx = (T.tw + 3) >> 2, nby = (T.th + 3) >> 2;
+            for (int u = tid; u < 64 * P.enc_channels; u += NVB_PT_THREADS) {
+                const int chan = u >> 6, bx = u & 7, by = (u >> 3) & 7;
+                if (bx >= nbx || by >= nby) continue;
+                const int twb = min(T.tw - 4 * bx, 4), thb = min(T.th - 4 * by, 4);
+                unsigned v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = s_q[chan][4 * by + (i >> 2) % thb][4 * bx + (i & 3) % twb];
+                const unsigned long long blk = alpha_quick_compress(v);
+                const size_t bi = (size_t)(T.ty0 / 4 + by) * ((dw + 3) >> 2) + (T.tx0 / 4 + bx);
+                *reinterpret_cast<uint2 *>(P.enc_out + bi * P.enc_stride + 8 * chan) = make_uint2((unsigned)(blk & 0xFFFFFFFFu), (unsigned)(blk >> 32));
+            }
+            // s_q is next written two (plain) or three (normal map) barriers from here
         }
         if (plane == 3) T = Tn;
     }
