@@ -78,7 +78,7 @@ struct NvttbContext {
     // copy engines run beside the kernels: host->device bands are uploaded on h2d_stream while earlier bands are
     // converted and encoded on `stream`; finished level-0 bands go back on d2h_stream while the mip chain is computed
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-    enum { MAX_BANDS = 8 };
+    enum { MAX_BANDS = 9 };
     cudaEvent_t ev_up[MAX_BANDS] = {}, ev_enc[MAX_BANDS] = {}, ev_stage_free = nullptr, ev_tail = nullptr;
     // BC7: the eight mode searches of a level are independent until the final select, so each runs on its own stream
     // (small levels cannot fill 148 SMs with one mode's candidates; together they do)
@@ -110,6 +110,10 @@ struct NvttbContext {
     // spread over eight.  Side by side with level 0 their blocks simply take free slots.
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side_go = nullptr, ev_side_done = nullptr, ev_cv[MAX_BANDS] = {};
+    // host input, level 0 band by band: odd bands are encoded on alt_stream, so that a band starts while the last blocks of the
+    // one before it are still running (a cluster-fit block takes ~100 us; eight drains are 1 % of an 8192² image)
+    cudaStream_t alt_stream = nullptr;
+    cudaEvent_t ev_alt_done = nullptr;
     enum { MAX_LEVELS = 32 };
     cudaEvent_t ev_lvl[MAX_LEVELS] = {}, ev_tail_done = nullptr;
     DevBuf tail_scratch, tail_lvl, exchange;
@@ -259,6 +263,8 @@ int nvttb_context_create(int device, NvttbContext **out) {
         if ((e = cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->alt_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_alt_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_go, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < NvttbContext::MAX_BANDS; i++)
@@ -373,6 +379,11 @@ void nvttb_context_destroy(NvttbContext *ctx) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
     }
+    if (ctx->alt_stream) {
+        cudaStreamSynchronize(ctx->alt_stream);
+        cudaStreamDestroy(ctx->alt_stream);
+    }
+    if (ctx->ev_alt_done) cudaEventDestroy(ctx->ev_alt_done);
     if (ctx->ev_side_go) cudaEventDestroy(ctx->ev_side_go);
     if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
     for (int i = 0; i < NvttbContext::MAX_BANDS; i++)
@@ -1816,16 +1827,17 @@ size_t nvttb_process_output_size(const NvttbProcessDesc *d) {
 // describes the main stream; launches that overlap it would be counted twice.
 struct SideScope {
     NvttbContext *c;
+    cudaStream_t *other;
     bool on, prof;
-    SideScope(NvttbContext *ctx, bool enable) : c(ctx), on(enable), prof(ctx->profiling) {
+    SideScope(NvttbContext *ctx, bool enable, cudaStream_t *which = nullptr) : c(ctx), other(which ? which : &ctx->side_stream), on(enable), prof(ctx->profiling) {
         if (on) {
-            std::swap(c->stream, c->side_stream);
+            std::swap(c->stream, *other);
             c->profiling = false;
         }
     }
     ~SideScope() {
         if (on) {
-            std::swap(c->stream, c->side_stream);
+            std::swap(c->stream, *other);
             c->profiling = prof;
         }
     }
@@ -1857,6 +1869,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
         cudaStreamSynchronize(ctx->h2d_stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamSynchronize(ctx->alt_stream);
         cudaStreamSynchronize(ctx->d2h_stream);
     };
     const bool toNormal = d->convertToNormalMap != 0;
@@ -1879,8 +1892,23 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     static const bool fused_env = getenv("NVTT_B200_FUSED_MIP_ENCODE") != nullptr;
     const bool can_fuse = fused_env && !sharded && !gamSlow && (d->encode.format == F_BC4 || d->encode.format == F_BC5) && d->encode.quality < Q_Production;
     const int bhTotal = (H + 3) / 4;
-    const int nbands = banded ? (bhTotal >= 8 * NvttbContext::MAX_BANDS ? NvttbContext::MAX_BANDS : 2) : 1;
-    const int bandBlockRows = (bhTotal + nbands - 1) / nbands;
+    // Band boundaries in texel rows.  Large images: eight bands, the first one cut again at 1/8 of its rows - nothing can be
+    // encoded before the first band has arrived, and uploading is ~8x faster than encoding (BC1 Production), so a first band of
+    // 1/64 of the image (4 MB of an 8192² BGRA8 image: 0.08 ms instead of 0.64 ms) still hides the upload of the next one.
+    int band_y[NvttbContext::MAX_BANDS + 1];
+    int nbands = 1;
+    band_y[0] = 0;
+    band_y[1] = H;
+    if (banded) {
+        const int even = bhTotal >= 64 ? 8 : 2;
+        const int bandBlockRows = (bhTotal + even - 1) / even;
+        nbands = 0;
+        if (even == 8 && bandBlockRows >= 16) band_y[++nbands] = (bandBlockRows / 8) * 4;
+        for (int b = 1; b <= even; b++) {
+            const int y = b * bandBlockRows * 4 < H ? b * bandBlockRows * 4 : H;
+            if (y > band_y[nbands]) band_y[++nbands] = y;
+        }
+    }
     const size_t bs = (size_t)block_bytes(d->encode.format), bw0 = (size_t)((W + 3) / 4);
     for (int f = f0; f < f1; f++) {
         unsigned char *out = d_out + (size_t)(f - f0) * fbytes;
@@ -1896,8 +1924,7 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             // that was never recorded is complete, so the wait is free the first time)
             CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
             for (int b = 0; b < nbands; b++) {
-                const int y0 = b * bandBlockRows * 4, y1 = (b + 1) * bandBlockRows * 4 < H ? (b + 1) * bandBlockRows * 4 : H;
-                if (y0 >= y1) continue;
+                const int y0 = band_y[b], y1 = band_y[b + 1];
                 const size_t off = (size_t)y0 * W * bpp;
                 CK(cudaMemcpyAsync((char *)ctx->in_stage.p + off, (const char *)images[f] + off, (size_t)(y1 - y0) * W * bpp, cudaMemcpyHostToDevice, ctx->h2d_stream));
                 CK(cudaEventRecord(ctx->ev_up[b], ctx->h2d_stream));
@@ -1906,23 +1933,39 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             e.width = W;
             e.alphaMode = d->alphaMode;
             e.applyToGamma = gamFast ? 1 : 0;
+            if (use_side) {
+                // the level buffer may still be read on `stream` by the previous face / call: the side stream starts behind it
+                CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
+            }
             for (int b = 0; b < nbands; b++) {
-                const int y0 = b * bandBlockRows * 4, y1 = (b + 1) * bandBlockRows * 4 < H ? (b + 1) * bandBlockRows * 4 : H;
-                if (y0 >= y1) continue;
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[b], 0));
+                const int y0 = band_y[b], y1 = band_y[b + 1];
                 float *rows = (float *)A.p + (size_t)y0 * W;
-                if ((rc = convert_device(ctx, d->inputFormat, (const char *)ctx->in_stage.p + (size_t)y0 * W * bpp, (size_t)(y1 - y0) * W, rows, (size_t)W * H, linFast)) != NVTTB_OK) { cleanup(); return rc; }
-                if (use_side && y1 == H) CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));  // level 0 is complete: the mips may start
+                {
+                    // conversion as soon as the band has arrived: on the (high priority) side stream when there is one, so that it
+                    // does not queue behind the encode of an earlier band
+                    SideScope side(ctx, use_side);
+                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[b], 0));
+                    if ((rc = convert_device(ctx, d->inputFormat, (const char *)ctx->in_stage.p + (size_t)y0 * W * bpp, (size_t)(y1 - y0) * W, rows, (size_t)W * H, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+                    if (use_side) CK(cudaEventRecord(ctx->ev_cv[b], ctx->stream));
+                    if (y1 == H) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));  // level 0 is complete (the mips follow on this stream)
+                }
                 e.height = y1 - y0;
                 const size_t ooff = (size_t)(y0 / 4) * bw0 * bs, obytes = (size_t)((y1 - y0 + 3) / 4) * bw0 * bs;
-                if ((rc = encode_device(ctx, &e, rows, W, y1 - y0, out + ooff, (size_t)W * H)) != NVTTB_OK) { cleanup(); return rc; }
-                if (hout) {
-                    CK(cudaEventRecord(ctx->ev_enc[b], ctx->stream));
-                    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_enc[b], 0));
-                    CK(cudaMemcpyAsync(hout + ooff, out + ooff, obytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                {
+                    SideScope alt(ctx, use_side && (b & 1), &ctx->alt_stream);  // odd bands on the second encode stream
+                    if (use_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[b], 0));
+                    if (use_side && b == 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_go, 0));  // alt_stream too starts behind the previous image
+                    if ((rc = encode_device(ctx, &e, rows, W, y1 - y0, out + ooff, (size_t)W * H)) != NVTTB_OK) { cleanup(); return rc; }
+                    if (hout) {
+                        CK(cudaEventRecord(ctx->ev_enc[b], ctx->stream));
+                        CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_enc[b], 0));
+                        CK(cudaMemcpyAsync(hout + ooff, out + ooff, obytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    }
+                    if (use_side && (b & 1)) CK(cudaEventRecord(ctx->ev_alt_done, ctx->stream));
                 }
             }
-            CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+            if (use_side && nbands > 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_alt_done, 0));
             level0_done = true;
         } else {
             // setImage (+ toLinear).  The staging buffer is shared with the banded pipeline's copy stream.
@@ -1940,10 +1983,10 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             if ((rc = normal_map_device(ctx, cur, (float *)ctx->tmp_level.p, W, H, d->wrapMode, d->bumpFrequencyScale)) != NVTTB_OK) { cleanup(); return rc; }
             CK(cudaMemcpyAsync(cur, ctx->tmp_level.p, (size_t)W * H * 16, cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        if (use_side) {
-            if (!banded) CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));  // level 0 is complete
+        if (use_side && !banded) {
+            CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));  // level 0 is complete
             CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
-        }
+        }  // banded: level 0 was converted on the side stream itself
         int w = W, h = H;
         for (int m = 0; m < mips; m++) {
             SideScope side(ctx, use_side && m > 0);
@@ -2000,20 +2043,24 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
             }
             out += nvttb_level_size(e.format, w, h);
         }
-        if (use_side) {
-            // the face is done when both streams are; the level buffers are reused by the next face
-            CK(cudaEventRecord(ctx->ev_side_done, ctx->side_stream));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
-        }
+        if (use_side) CK(cudaEventRecord(ctx->ev_side_done, ctx->side_stream));
         if (hout && !in_place) {
             // whatever of this face has not been sent yet: the mip tail (banded) or the whole chain
             const size_t done = level0_done ? nvttb_level_size(d->encode.format, W, H) : 0;
             if (fbytes > done) {
-                CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
-                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_tail, 0));
+                if (use_side && level0_done) {
+                    // the mips were encoded on the side stream: they go home as soon as they are done, under the level-0 encode
+                    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_side_done, 0));
+                } else {
+                    if (use_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
+                    CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
+                    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_tail, 0));
+                }
                 CK(cudaMemcpyAsync(hout + done, d_out + (size_t)(f - f0) * fbytes + done, fbytes - done, cudaMemcpyDeviceToHost, ctx->d2h_stream));
             }
         }
+        // the face is done when both streams are; the level buffers are reused by the next face
+        if (use_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
         // the level buffers are reused by the next face: same stream, so ordering is implicit
     }
     CK(cudaGetLastError());
