@@ -2175,6 +2175,7 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
         cudaStreamSynchronize(ctx->h2d_stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamSynchronize(ctx->alt_stream);
         cudaStreamSynchronize(ctx->tail_stream);
         cudaStreamSynchronize(ctx->d2h_stream);
     };
@@ -2219,7 +2220,11 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
             if (host_in && j == K - 1) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
         }
         if (host_in) {
+            // odd chunks on the second encode stream: a chunk starts while the last blocks of the one before it are still running
+            const bool on_alt = side_conv && (j & 1);
+            SideScope alt(ctx, on_alt, &ctx->alt_stream);
             if (side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[j], 0));
+            if (on_alt && j == 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_go, 0));  // alt_stream too starts behind the previous image
             e.width = W;
             e.height = C;
             const size_t ooff = lvl_off[0] + c * rpc0 * row_bytes0;
@@ -2230,8 +2235,10 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
                 CK(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
                 CK(cudaMemcpyAsync(h_out + ooff, out + ooff, (size_t)rpc0 * row_bytes0, cudaMemcpyDeviceToHost, ctx->d2h_stream));
             }
+            if (on_alt) CK(cudaEventRecord(ctx->ev_alt_done, ctx->stream));
         }
     }
+    if (host_in && side_conv && K > 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_alt_done, 0));
     if (use_side && !side_conv) {
         // the chunks were converted on `stream`: the side stream continues from there
         CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
