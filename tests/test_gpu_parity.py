@@ -520,3 +520,45 @@ def test_16384_square_levels_sampled_blocks(nvtt, ref, ctx):
         want = ref.compress_level(fmt, q, strip).reshape(-1, bs)
         bad = [i for k, i in enumerate(idxs) if not np.array_equal(got[i], want[k])]
         assert not bad, "16384^2 fmt %d q%d: blocks %s differ from the reference" % (fmt, q, bad[:8])
+
+
+def test_gamma_dense_float_sweep(nvtt, ref, ctx):
+    """toLinear / toGamma (powf_11_5 / powf_5_11 table x polynomial, Gamma.cpp:311-354) on a dense sweep of the fp32 bit
+    patterns of [0, 1]: every 64th pattern per channel with a different residue in R, G, B (50 M values), plus values just
+    outside the range, negatives, infinities and NaNs; bit-exact against the reference."""
+    n = 4096
+    base = np.arange(n * n, dtype=np.uint64) * 64
+    top = np.uint64(0x3F800000)
+    img = np.empty((n, n, 4), np.uint32)
+    for c, off in enumerate((0, 21, 42)):
+        img[..., c] = np.minimum(base + off, top).astype(np.uint32).reshape(n, n)
+    special = np.array([1.0000001, 1.5, 2.0, 255.0, 65504.0, 3.4e38, -0.0, -1e-30, -0.5, -2.0, np.inf, -np.inf, np.nan, 1e-45, 1.1754942e-38],
+                       np.float32).view(np.uint32)
+    img[..., 3] = 0x3F800000
+    img[0, :special.size, 0] = special
+    img[1, :special.size, 1] = special
+    img[2, :special.size, 2] = special
+    data = img.view(np.float32)
+    for op in ("to_linear", "to_gamma"):
+        a = ref.Surface()
+        b = nvtt.Surface(ctx)
+        a.set_image(2, n, n, data)
+        b.set_image(2, n, n, data)
+        getattr(a, op)(2.2)
+        getattr(b, op)(2.2)
+        ga, gb = a.get().view(np.uint32), b.get().view(np.uint32)
+        assert np.array_equal(ga, gb), "%s: %d of %d values differ" % (op, int((ga != gb).sum()), ga.size)
+        del a, b, ga, gb
+
+
+def test_half_from_float_dense_sweep(nvtt, ref, ctx):
+    """nv::half_from_float (Half.cpp:378-441) through the RGBA16F pixel-format writer on every 257th fp32 bit pattern of the whole
+    32-bit range (16.7 M values: all exponents, denormals, both signs, infinities, NaN payloads), byte-identical to the reference."""
+    w, h = 4096, 1024
+    bits = (np.arange(w * h * 4, dtype=np.uint64) * 257 % (1 << 32)).astype(np.uint32).reshape(h, w, 4)
+    vals = bits.view(np.float32)
+    planar = np.ascontiguousarray(np.moveaxis(vals, 2, 0))
+    got = ctx.convert_level(planar, sizes=(16, 16, 16, 16), pixel_type=4)
+    want = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_sizes=(16, 16, 16, 16), pixel_type=4)
+    assert got.size == want.size
+    assert np.array_equal(got, want), "%d of %d halfs differ" % (int((got.view(np.uint16) != want.view(np.uint16)).sum()), got.size // 2)

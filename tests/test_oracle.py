@@ -151,3 +151,30 @@ def test_oracle_vs_reference_direct(orc, ref, nvtt):
     assert np.array_equal(o.view(np.uint32), r.get().view(np.uint32))
     r.expand_normals(); r.normalize_normal_map(); r.pack_normals()
     assert np.array_equal(orc.renormalize(o).view(np.uint32), r.get().view(np.uint32))
+
+
+def test_oracle_dense_sweeps_vs_reference(orc, ref):
+    """The oracle's gamma approximations and half_from_float against the reference on dense sweeps of the fp32 bit patterns:
+    every 256th pattern of [0, 1] through toLinear / toGamma (4 M values per channel, three residues) and every 1021st pattern of
+    the whole 32-bit range through the RGBA16F writer (4 M values)."""
+    n = 1024
+    base = np.arange(n * n, dtype=np.uint64) * 1016  # 1024 * 1024 * 1016 ~ 0x3F800000
+    img = np.empty((n, n, 4), np.uint32)
+    for c, off in enumerate((0, 337, 674)):
+        img[..., c] = np.minimum(base + off, np.uint64(0x3F800000)).astype(np.uint32).reshape(n, n)
+    img[..., 3] = 0x3F800000
+    special = np.array([1.0000001, 1.5, 255.0, 3.4e38, -0.0, -1e-30, -0.5, np.inf, -np.inf, np.nan, 1e-45], np.float32).view(np.uint32)
+    img[0, :special.size, 0] = special
+    data = img.view(np.float32)
+    for op in ("to_linear", "to_gamma"):
+        r = ref.Surface()
+        r.set_image(2, n, n, data)
+        getattr(r, op)(2.2)
+        o = getattr(orc, op)(orc.set_image(2, n, n, data), 2.2)
+        assert np.array_equal(o.view(np.uint32), r.get().view(np.uint32)), op
+    w, h = 1024, 1024
+    bits = (np.arange(w * h * 4, dtype=np.uint64) * 1021 % (1 << 32)).astype(np.uint32).reshape(h, w, 4)
+    vals = bits.view(np.float32)
+    a = orc.convert_level(np.ascontiguousarray(np.moveaxis(vals, 2, 0)), sizes=(16, 16, 16, 16), pixel_type=4)
+    b = ref.process([vals], 2, w, h, 0, 1, mipmaps=False, gamma=(1.0, 1.0), pixel_sizes=(16, 16, 16, 16), pixel_type=4)
+    assert np.array_equal(a, b)
