@@ -962,11 +962,13 @@ template <int W> static int launch_polyphase_tma(NvttbContext *ctx, const PolyDe
     if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return NVTTB_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // a function attribute belongs to the device that is current when it is set: once per device (each device has its own
+    // host thread in nvttb_process_multi, so the slots are not shared)
+    static bool attr_set[64] = {};
+    if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
         CK(cudaFuncSetAttribute(k_polyphase_tma<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
         CK(cudaFuncSetAttribute(k_polyphase_tma<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-        attr_set = true;
+        if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
     }
     PolyTmaParams Q;
     Q.src = src; Q.dst = dst; Q.sw = sw; Q.sh = sh; Q.dw = dw; Q.dh = dh; Q.wrap = wrap;
@@ -1158,7 +1160,10 @@ static size_t input_bpp(int inputFormat) {
 // convert `pixels` interleaved texels at d_src to planar fp32 at dst (plane stride `plane`), optionally fusing toLinear(2.2)
 static int convert_device(NvttbContext *ctx, int inputFormat, const void *d_src, size_t pixels, float *dst, size_t plane, bool fuseToLinear) {
     SetImageParams P{d_src, dst, (int)pixels, inputFormat, fuseToLinear ? ctx->d_to_linear : nullptr, plane};
-    NVB_LAUNCH(ctx, K_SET_IMAGE, (double)pixels, k_set_image, grid_for(pixels, 256), 256, P);
+    if (inputFormat == 0 && pixels >= 4096 && (pixels & 3) == 0 && (plane & 3) == 0 && ((size_t)d_src & 15) == 0 && ((size_t)dst & 15) == 0)
+        NVB_LAUNCH(ctx, K_SET_IMAGE, (double)pixels, k_set_image_bgra8_x4, grid_for(pixels / 4, 256), 256, P);
+    else
+        NVB_LAUNCH(ctx, K_SET_IMAGE, (double)pixels, k_set_image, grid_for(pixels, 256), 256, P);
     CK(cudaGetLastError());
     return NVTTB_OK;
 }

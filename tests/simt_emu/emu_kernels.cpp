@@ -225,6 +225,12 @@ void emu_set_image(const void *src, float *dst, int count, int format, int to_li
     emu::launch(dim3((count + 255) / 256), dim3(256), 0, [&] { k_set_image(P); });
 }
 
+void emu_set_image_x4(const void *src, float *dst, int count, int to_linear) {
+    init_tables();
+    SetImageParams P{src, dst, count, 0, to_linear ? g_to_linear : nullptr, (size_t)count};
+    emu::launch(dim3(3), dim3(256), 0, [&] { k_set_image_bgra8_x4(P); });  // few CTAs: exercises the grid-stride loop
+}
+
 void emu_gamma(float *data, size_t pixels, int mode, float power) {
     init_tables();
     GammaParams P{data, 3 * pixels, mode, mode == 0 ? g_to_linear : g_to_gamma, power};

@@ -188,3 +188,17 @@ def test_emulated_rgb9e5_matches_reference(emu, ref):
         out = np.full(4 * w * h, 0xCD, np.uint8)
         emu.emu_pixel_format(planar.ctypes.data, w, h, out.ctypes.data, 4 * w, 32, 4, U4(9, 9, 9, 5), U4(23, 14, 5, 0), path, 0)
         assert np.array_equal(out, want), (path, int(np.flatnonzero(out != want)[0]) // 4)
+
+
+def test_emulated_set_image_x4_matches_scalar_kernel(emu):
+    """k_set_image_bgra8_x4 (256-entry tables, four pixels per thread) against k_set_image, with and without the fused toLinear."""
+    rng = np.random.default_rng(9)
+    n = 4096 * 3
+    src = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+    src[:256, :] = np.arange(256, dtype=np.uint8)[:, None]  # every byte value in every channel
+    for lin in (0, 1):
+        a = np.zeros(4 * n, np.float32)
+        b = np.zeros(4 * n, np.float32)
+        emu.emu_set_image(C.c_void_p(src.ctypes.data), C.c_void_p(a.ctypes.data), n, 0, lin)
+        emu.emu_set_image_x4(C.c_void_p(src.ctypes.data), C.c_void_p(b.ctypes.data), n, lin)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), lin
