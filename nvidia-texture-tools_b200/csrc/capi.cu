@@ -2200,50 +2200,70 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
         CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_go, 0));
     }
-    // 1. the band's chunks: upload (copy stream), convert and - for host input - encode level 0 chunk by chunk, so that
-    //    the copies of the following chunks hide under the encode
+    // 1. the band's chunks: upload (copy stream), convert and - for host input - encode level 0 piece by piece, so that
+    //    the copies of the following pieces hide under the encode.  A piece is a chunk, except that the first chunk is cut at
+    //    1/8 of its rows: nothing can be encoded before the first piece has arrived, and all the GPUs of the box pull their
+    //    first piece from the same host memory at the same moment.
+    struct Piece { int j, r0, nr, ev; };  // chunk, first row inside it, rows, index of its events
+    Piece pieces[NvttbContext::MAX_BANDS + 1];
+    int npieces = 0;
+    {
+        const bool split = host_in && per_chunk_events && K + 1 <= NvttbContext::MAX_BANDS && C >= 64 && (C / 8) % 4 == 0;
+        for (int j = 0; j < K; j++) {
+            if (j == 0 && split) {
+                pieces[npieces++] = Piece{0, 0, C / 8, K};
+                pieces[npieces++] = Piece{0, C / 8, C - C / 8, 0};
+            } else {
+                pieces[npieces++] = Piece{j, 0, C, per_chunk_events ? j : 0};
+            }
+        }
+    }
+    const size_t row_in = (size_t)W * bpp;
     if (host_in) {
         CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_stage_free, 0));
-        for (int j = 0; j < K; j++) {
-            const size_t c = (size_t)j * N + b;
-            CK(cudaMemcpyAsync((char *)ctx->in_stage.p + j * chunk_in, (const char *)image + c * chunk_in, chunk_in, cudaMemcpyHostToDevice, ctx->h2d_stream));
-            if (per_chunk_events) CK(cudaEventRecord(ctx->ev_up[j], ctx->h2d_stream));
+        for (int q = 0; q < npieces; q++) {
+            const Piece &pc = pieces[q];
+            const size_t c = (size_t)pc.j * N + b;
+            CK(cudaMemcpyAsync((char *)ctx->in_stage.p + pc.j * chunk_in + pc.r0 * row_in, (const char *)image + c * chunk_in + pc.r0 * row_in,
+                               (size_t)pc.nr * row_in, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            if (per_chunk_events) CK(cudaEventRecord(ctx->ev_up[pc.ev], ctx->h2d_stream));
         }
         if (!per_chunk_events) CK(cudaEventRecord(ctx->ev_up[0], ctx->h2d_stream));
     }
     const int rpc0 = C / 4;
     const size_t row_bytes0 = (size_t)((W + 3) / 4) * bs;
-    for (int j = 0; j < K; j++) {
-        const size_t c = (size_t)j * N + b;
-        float *rows = chain + (size_t)j * C * W;
+    for (int q = 0; q < npieces; q++) {
+        const Piece &pc = pieces[q];
+        const size_t c = (size_t)pc.j * N + b;
+        float *rows = chain + ((size_t)pc.j * C + pc.r0) * W;
         {
             SideScope side(ctx, side_conv);
-            if (host_in && (per_chunk_events || j == 0)) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[per_chunk_events ? j : 0], 0));
-            const char *src = host_in ? (const char *)ctx->in_stage.p + j * chunk_in : (const char *)image + c * chunk_in;
-            if ((rc = convert_device(ctx, d->inputFormat, src, (size_t)C * W, rows, (size_t)W * HL, linFast)) != NVTTB_OK) { cleanup(); return rc; }
-            if (side_conv) CK(cudaEventRecord(ctx->ev_cv[j], ctx->stream));
-            if (host_in && j == K - 1) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
+            if (host_in && (per_chunk_events || q == 0)) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[pc.ev], 0));
+            const char *src = host_in ? (const char *)ctx->in_stage.p + pc.j * chunk_in + pc.r0 * row_in : (const char *)image + c * chunk_in + pc.r0 * row_in;
+            if ((rc = convert_device(ctx, d->inputFormat, src, (size_t)pc.nr * W, rows, (size_t)W * HL, linFast)) != NVTTB_OK) { cleanup(); return rc; }
+            if (side_conv) CK(cudaEventRecord(ctx->ev_cv[pc.ev], ctx->stream));
+            if (host_in && q == npieces - 1) CK(cudaEventRecord(ctx->ev_stage_free, ctx->stream));
         }
         if (host_in) {
-            // odd chunks on the second encode stream: a chunk starts while the last blocks of the one before it are still running
-            const bool on_alt = side_conv && (j & 1);
+            // odd pieces on the second encode stream: a piece starts while the last blocks of the one before it are still running
+            const bool on_alt = side_conv && (q & 1);
             SideScope alt(ctx, on_alt, &ctx->alt_stream);
-            if (side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[j], 0));
-            if (on_alt && j == 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_go, 0));  // alt_stream too starts behind the previous image
+            if (side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[pc.ev], 0));
+            if (on_alt && q == 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_go, 0));  // alt_stream too starts behind the previous image
             e.width = W;
-            e.height = C;
-            const size_t ooff = lvl_off[0] + c * rpc0 * row_bytes0;
-            if ((rc = encode_device(ctx, &e, rows, W, C, out + ooff, (size_t)W * HL)) != NVTTB_OK) { cleanup(); return rc; }
+            e.height = pc.nr;
+            const size_t ooff = lvl_off[0] + (c * rpc0 + pc.r0 / 4) * row_bytes0;
+            if ((rc = encode_device(ctx, &e, rows, W, pc.nr, out + ooff, (size_t)W * HL)) != NVTTB_OK) { cleanup(); return rc; }
             if (h_out) {
-                cudaEvent_t ev = per_chunk_events ? ctx->ev_enc[j] : ctx->ev_enc[0];
+                cudaEvent_t ev = ctx->ev_enc[pc.ev];
                 CK(cudaEventRecord(ev, ctx->stream));
                 CK(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
-                CK(cudaMemcpyAsync(h_out + ooff, out + ooff, (size_t)rpc0 * row_bytes0, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                CK(cudaMemcpyAsync(h_out + ooff, out + ooff, (size_t)(pc.nr / 4) * row_bytes0, cudaMemcpyDeviceToHost, ctx->d2h_stream));
             }
             if (on_alt) CK(cudaEventRecord(ctx->ev_alt_done, ctx->stream));
         }
     }
-    if (host_in && side_conv && K > 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_alt_done, 0));
+    if (host_in && side_conv && npieces > 1) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_alt_done, 0));
     if (use_side && !side_conv) {
         // the chunks were converted on `stream`: the side stream continues from there
         CK(cudaEventRecord(ctx->ev_side_go, ctx->stream));
@@ -2319,7 +2339,7 @@ static int process_shard_local(NvttbContext *ctx, const NvttbProcessDesc *d, con
     // 5. the band's rows of the distributed levels: one launch per level over the concatenated chunks
     for (int m = host_in ? 1 : 0; m <= k; m++) {
         SideScope side(ctx, use_side && m > 0);
-        if (m == 0 && side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[K - 1], 0));  // level 0 was converted on the side stream
+        if (m == 0 && side_conv) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cv[pieces[npieces - 1].ev], 0));  // level 0 was converted on the side stream
         const int w = W >> m, hl = HL >> m;
         const int rpc = C / (4 << m);
         const size_t row_bytes = (size_t)((w + 3) / 4) * bs;
