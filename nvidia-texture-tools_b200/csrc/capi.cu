@@ -1889,7 +1889,10 @@ static int process_faces(NvttbContext *ctx, const NvttbProcessDesc *d, const voi
     const size_t bpp = input_bpp(d->inputFormat);
     ShardGeom geom;
     const bool sharded = shard_geom(d, &geom);
-    const bool banded = !sharded && loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14);
+    // (not for BC6H: a level is a chain of seven kernels around a dynamically scheduled search, and one chain per band costs
+    // far more in tails - 348 instead of 220 ms for a 6 x 2048² cube - than the 0.6 ms per face the upload would hide)
+    const bool banded = !sharded && loc == NVTTB_HOST && bpp != 0 && !toNormal && !(colour && !linFast) && !gamSlow && H >= 64 && (size_t)W * H >= (1u << 14) &&
+                        d->encode.format != F_BC6;
     // mips on side_stream, beside the level-0 encode (not for the encoders that share per-context scratch, BC6H / BC7: they are
     // long enough for the latency of a small level not to matter)
     const bool use_side = mips > 1 && !sharded && !gamSlow && encoder_scratch_bytes(d->encode.format, W, H) == 0;
