@@ -535,7 +535,9 @@ static int ensure_mode_streams(NvttbContext *ctx) {
 
 // BC7, one mode of one chunk of blocks, on the mode's own stream: rough shape ranking (modes 0,1,2,3,7), start endpoints
 // per candidate, the searcher state machine, finish + reduction over the block's candidates.
-#define NVB_BC7_CHUNK 32768
+#ifndef NVB_BC7_CHUNK
+#define NVB_BC7_CHUNK 65536  // blocks per chunk (~12 KB of searcher records each): 8k 1210, 16k 1177, 32k 1146, 64k 1133 ms for a 2048² chain
+#endif
 template <int M, int NCAND> struct Bc7ModeBytes {
     using X = Bc7X<M>;
     static constexpr size_t setup = (size_t)NCAND * X::NR * 16, idx = (size_t)NCAND * 16, res = (size_t)NCAND * X::NR * X::NLSB * 16;

@@ -116,6 +116,12 @@ template <int W, bool FUSE = false> __global__ void __launch_bounds__(NVB_PT_THR
         wx[j] = P.wx[j];
         wy[j] = P.wy[j];
     }
+    // weight pairs for the packed products: X pairs start at the first tap whose sample sits at an even position of the window
+    pf2 wxp[W / 2 + 1], wyp[W / 2 + 1];
+#pragma unroll
+    for (int j = (G::SHIFT & 1); j + 1 < W; j += 2) wxp[(j - (G::SHIFT & 1)) / 2] = pf2_pack(P.wx[j], P.wx[j + 1]);
+#pragma unroll
+    for (int j = 0; j + 1 < W; j += 2) wyp[j / 2] = pf2_pack(P.wy[j], P.wy[j + 1]);
     if (tid == 0) {
         pt_mbar_init(&mbar[0], 1);
         pt_mbar_init(&mbar[1], 1);
@@ -200,12 +206,21 @@ template <int W, bool FUSE = false> __global__ void __launch_bounds__(NVB_PT_THR
                     s[4 * k + 2] = v.z;
                     s[4 * k + 3] = v.w;
                 }
+                // the products of two neighbouring taps are one FMUL2 (the staged values are aligned register pairs already, the
+                // weight pairs are packed once); the sum stays the reference's ascending chain of single-rounded adds
                 float o[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     float a = 0.0f;
+                    constexpr int J0 = G::SHIFT & 1;  // first tap whose sample sits at an even position
+                    if (J0) a += wx[0] * s[G::SHIFT + 2 * q];
 #pragma unroll
-                    for (int j = 0; j < W; j++) a += wx[j] * s[G::SHIFT + 2 * q + j];
+                    for (int j = J0; j + 1 < W; j += 2) {
+                        const pf2 pp = pf2_mul(wxp[(j - J0) / 2], pf2_pack(s[G::SHIFT + 2 * q + j], s[G::SHIFT + 2 * q + j + 1]));
+                        a += pf2_lo(pp);
+                        a += pf2_hi(pp);
+                    }
+                    if (((W - J0) & 1) != 0) a += wx[W - 1] * s[G::SHIFT + 2 * q + W - 1];
                     o[q] = a;
                 }
                 *reinterpret_cast<float4 *>(s_tmp + xr * G::TMP_PITCH + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
@@ -223,7 +238,12 @@ template <int W, bool FUSE = false> __global__ void __launch_bounds__(NVB_PT_THR
             for (int q = 0; q < 4; q++) {
                 float a = 0.0f;
 #pragma unroll
-                for (int j = 0; j < W; j++) a += wy[j] * s[2 * q + j];
+                for (int j = 0; j + 1 < W; j += 2) {
+                    const pf2 pp = pf2_mul(wyp[j / 2], pf2_pack(s[2 * q + j], s[2 * q + j + 1]));
+                    a += pf2_lo(pp);
+                    a += pf2_hi(pp);
+                }
+                if (W & 1) a += wy[W - 1] * s[2 * q + W - 1];
                 const int oy = 4 * ygy + q;
                 if (oy < T.th && yox < T.tw) {
                     if (keep) s_out[(plane * NVB_PT_TH + oy) * G::OUT_PITCH + yox] = a;

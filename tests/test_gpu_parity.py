@@ -469,10 +469,10 @@ def _sample_blocks_strip(img, idxs, bw):
 
 
 def test_config3_config4_full_size_properties(nvtt, ref, ctx):
-    """BASELINE configs[3] / [4] at sizes where the BC7 pipeline runs in several chunks of 32 768 blocks and the BC6H one over a
+    """BASELINE configs[3] / [4] at sizes where the BC7 pipeline runs in more than one chunk (65 536 blocks) and the BC6H one over a
     whole 2048^2 face: sampled blocks (chunk boundaries included) must equal the reference's encoding of the same 4x4 tiles."""
     rng = np.random.default_rng(77)
-    # BC7: 1040 x 1024 = 260 x 256 blocks = 66 560 blocks = 2 full chunks + a partial one
+    # BC7: 1040 x 1024 = 260 x 256 blocks = 66 560 blocks = a full chunk + a partial one (the old 32 768 boundary is sampled too)
     w, h = 1040, 1024
     img = nvtt.synth.planar_from_bgra8(nvtt.synth.photo_bgra8(w, h, seed=1234, alpha=True))
     adv = nvtt.synth.planar_from_bgra8(nvtt.synth.adversarial_bgra8(256, 256, seed=5))
