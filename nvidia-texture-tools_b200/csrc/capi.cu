@@ -2589,7 +2589,8 @@ static void pin_thread_near_device(int device) {
     cpu_set_t set;
     CPU_ZERO(&set);
     int count = 0;
-    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+    char *save = nullptr;  // strtok_r: this runs in one host thread per GPU at the same time
+    for (char *tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-31,64-95"
         int a = 0, b = 0;
         const int got = sscanf(tok, "%d-%d", &a, &b);
         if (got == 1) b = a;
