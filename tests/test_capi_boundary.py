@@ -18,6 +18,20 @@ def test_header_and_library_agree(nvtt):
     assert sorted(nvtt.EXPORTS) == declared
 
 
+def test_build_variants(nvtt):
+    """The strict (bit-exact) and the opt-in fast-math build export the same C ABI and say which one they are."""
+    import ctypes as C
+    L = nvtt.lib()
+    assert L.nvttb_build_variant() == b"strict"
+    fast = os.path.join(os.path.dirname(nvtt.capi.LIB_PATH), "libnvtt_b200_fastmath.so")
+    assert os.path.exists(fast), "run __graft_entry__.build()"
+    F = C.CDLL(fast)
+    F.nvttb_build_variant.restype = C.c_char_p
+    assert F.nvttb_build_variant() == b"fastmath"
+    missing = [n for n in nvtt.EXPORTS if not hasattr(F, n)]
+    assert not missing, missing
+
+
 def test_sizes_and_mip_counts(nvtt):
     L = nvtt.lib()
     assert L.nvttb_level_size(nvtt.Format_BC1, 2048, 2048) == 512 * 512 * 8
