@@ -33,6 +33,8 @@ CASES = [
     (256, 256, "BC4", 1, 2, 0, {}),          # contiguous bands
     (64, 64, "BC7", 1, 2, 8, {}),
     (128, 128, "BC1", 1, 4, 4, dict(gamma=(1.0, 1.0))),
+    (256, 512, "BC1", 2, 2, 64, {}),         # chunks of >= 64 rows: host input uploads / encodes the first chunk in two pieces
+    (128, 1024, "BC3", 1, 4, 128, {}),
 ]
 
 
